@@ -1,0 +1,149 @@
+/*
+ * s2t_b200.h -- C ABI of libs2t_b200.so: the B200 (sm_100a) implementation of
+ * speech2text's transducer-loss hot path.
+ *
+ * Every entry point replaces one call the reference makes into its un-vendored
+ * native dependencies (k2 / torchaudio); the reference-side binding is the
+ * ctypes stub in speech2text_b200/_lib.py (shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers into caller-owned buffers (the Python
+ *     host allocates them with torch); the library neither frees nor retains
+ *     them; outputs are fully written by the call (no pre-zeroing needed unless
+ *     a parameter says "accumulated");
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     performs no host synchronisation and no allocation;
+ *   - tensors are contiguous row-major with the shapes given; int64 index
+ *     tensors exactly as the reference produces them;
+ *   - return value 0 = success; non-zero = error, message via s2t_last_error()
+ *     (thread-local).  No C++ exceptions cross the boundary.
+ *   - rnnt_type is always "regular"; boundary rows are [0, 0, S_b, T_b].
+ */
+#ifndef S2T_B200_H_
+#define S2T_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2T_ABI_VERSION 1
+
+/* dtype codes for logits tensors */
+#define S2T_F32 0
+#define S2T_BF16 1
+#define S2T_F16 2
+/* activation codes (reference: model/joiner/joiner.py:44-49) */
+#define S2T_ACT_RELU 0
+#define S2T_ACT_TANH 1
+/* joiner arithmetic modes */
+#define S2T_MODE_FP32_SIMT 0 /* strict fp32 FMA contractions (parity mode)        */
+#define S2T_MODE_BF16_TC 1   /* bf16 operands, fp32 accumulate on tcgen05 / TMEM  */
+
+int s2t_abi_version(void);
+const char* s2t_last_error(void);
+
+/* ---------------------------------------------------------------------------
+ * k2.mutual_information_recursion(px, py, boundary, return_grad)
+ *   reference call sites: model/joiner/joiner.py:100-110 (inside rnnt_loss_smoothed),
+ *   model/loss/pruned_rnnt_loss.py:39-48 (inside rnnt_loss_pruned).
+ * px (B,S,T+1), py (B,S+1,T) fp32; boundary (B,4) int64 or NULL.
+ * alpha_ws: scratch (B,S+1,T+1) fp32.  scores (B).  px_grad/py_grad: occupation
+ * probabilities, same shapes as px/py, or both NULL for scores only.
+ */
+int s2t_mutual_information(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
+                           float* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * k2.rnnt_loss_smoothed(lm, am, symbols, termination_symbol, lm_only_scale,
+ *                       am_only_scale, boundary, reduction, return_grad=True)
+ *   reference call site: model/joiner/joiner.py:100-110.
+ * am (B,T,V), lm (B,S+1,V) fp32; symbols (B,S) int64.
+ * Outputs: am_max (B,T), lm_max (B,S+1), px (B,S,T+1), py (B,S+1,T),
+ * nrm (B,S+1,T) [log-normalisers, kept for the backward], alpha_ws (B,S+1,T+1),
+ * scores (B) = log P(y|x) per utterance (reduction is the caller's),
+ * px_grad (B,S,T+1), py_grad (B,S+1,T).
+ * lm_only_scale / am_only_scale must be 0 in this ABI version (the reference's
+ * configs never set them; non-zero returns an error).
+ */
+int s2t_simple_loss_fwd(const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
+                        int B, int T, int S, int V, int blank, float lm_only_scale, float am_only_scale,
+                        float* am_max, float* lm_max, float* px, float* py, float* nrm, float* alpha_ws,
+                        float* scores, float* px_grad, float* py_grad, void* stream);
+
+/* Backward of the above: grad_scores (B) = d loss / d scores[b].
+ * wbuf: scratch (B,S+1,T).  d_am (B,T,V), d_lm (B,S+1,V) are overwritten. */
+int s2t_simple_loss_bwd(const float* am, const float* lm, const int64_t* symbols, const float* am_max,
+                        const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,
+                        const float* grad_scores, int B, int T, int S, int V, int blank, float* wbuf,
+                        float* d_am, float* d_lm, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * k2.get_rnnt_prune_ranges(px_grad, py_grad, boundary, s_range)
+ *   reference call site: model/joiner/joiner.py:112-117.
+ * s_range must already be clamped by the caller (s_range > S -> S+1).
+ * variant 0 = "A" (k2 v1.24.3 get_rnnt_prune_ranges), 1 = "B" (SURVEY.md A.4).
+ * ranges (B,T,s_range) int64, bit-exact.
+ */
+int s2t_prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boundary, int B, int S, int T,
+                     int s_range, int variant, int64_t* ranges, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Loss on materialised logits (B,T,R,V) of dtype `dtype`:
+ *   ranges != NULL: k2.rnnt_loss_pruned          (model/loss/pruned_rnnt_loss.py:39-48)
+ *   ranges == NULL: torchaudio rnnt_loss, R = S+1 (model/loss/rnnt_loss.py:42-44)
+ * Outputs: lse, px, py, occ_px, occ_py (B,T,R) fp32; alpha_ws scratch (B,T+1,R);
+ * scores (B) = log P(y|x).
+ */
+int s2t_logits_loss_fwd(const void* logits, int dtype, const int64_t* symbols, const int64_t* ranges,
+                        const int64_t* boundary, int B, int T, int S, int R, int V, int blank,
+                        float delay_penalty, float* lse, float* px, float* py, float* alpha_ws, float* scores,
+                        float* occ_px, float* occ_py, void* stream);
+
+/* grad (B,T,R,V), same dtype as logits, overwritten with d loss / d logits given
+ * grad_scores[b] = d loss / d scores[b]:
+ *   grad = grad_scores[b] * clip(occ_px [c==sym] + occ_py [c==blank] - (occ_px+occ_py) softmax_c)
+ * where clip() is torchaudio's `clamp` (model/loss/rnnt_loss.py:27-29), applied when clamp > 0. */
+int s2t_logits_loss_bwd(const void* logits, int dtype, const int64_t* symbols, const int64_t* ranges,
+                        const float* lse, const float* occ_px, const float* occ_py, const float* grad_scores,
+                        int B, int T, int S, int R, int V, int blank, float clamp, void* grad, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused pruned joiner + loss: never materialises (B,T,R,V).
+ *   replaces k2.do_rnnt_pruning (joiner.py:121-123), add/act/out-projection
+ *   (joiner.py:176-178) and k2.rnnt_loss_pruned (pruned_rnnt_loss.py:39-48);
+ *   with ranges == NULL and R = S+1 it is the unpruned joiner (joiner.py:166-178)
+ *   + torchaudio rnnt_loss (rnnt_loss.py:42-44).
+ * am (B,T,V), lm (B,S+1,V) fp32 are the projected encoder / predictor outputs.
+ * W1 (I,V), b1 (I), W2 (V,I), b2 (V): out-projection; I == 0 and NULL weights
+ * when use_out_project=False.
+ * workspace: s2t_joiner_workspace_bytes() bytes; the SAME buffer, untouched,
+ * must be passed to the backward call (it carries the hidden activations).
+ */
+size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I);
+
+int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols,
+                        const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
+                        const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
+                        int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
+                        float* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream);
+
+/* d_am (B,T,V), d_lm (B,S+1,V), dW1, db1, dW2, db2 are overwritten. */
+int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols,
+                        const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
+                        const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
+                        int blank, float clamp, void* workspace, const float* lse, const float* occ_px,
+                        const float* occ_py, const float* grad_scores, float* d_am, float* d_lm, float* dW1,
+                        float* db1, float* dW2, float* db2, void* stream);
+
+/* Debug / materialised mode: write the logits (B,T,R,V) fp32 the fused path never stores. */
+int s2t_joiner_materialize(int mode, const float* am, const float* lm, const int64_t* ranges, const float* W1,
+                           const float* b1, const float* W2, const float* b2, int B, int T, int S, int R, int V,
+                           int I, int act, void* workspace, float* logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2T_B200_H_ */

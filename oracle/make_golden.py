@@ -1,0 +1,145 @@
+"""ORACLE tooling (test infrastructure, NOT product code).
+
+Mints the golden vectors under tests/golden/ by running the REFERENCE's own
+modules, verbatim, in this build container:
+
+    /root/reference/model/joiner/joiner.py        (Joiner, JoinerConfig)
+    /root/reference/model/loss/pruned_rnnt_loss.py (PrunedRnntLoss)
+    /root/reference/model/loss/rnnt_loss.py        (RnntLoss -> torchaudio)
+
+``k2`` (un-vendored, not installable here) is satisfied by oracle/k2_shim.py
+installed as ``sys.modules["k2"]``; ``onnx`` (only used by the export methods)
+by an empty stub module.  /root/reference does not exist on the GPU box, so the
+outputs are committed as small .npz fixtures and this script is the recipe.
+
+Inputs and weights are drawn from numpy RandomState streams (stable across
+torch versions) by ``oracle.cases.make_case`` so tests can regenerate them
+bit-exactly without the reference.
+
+Usage (build container only):  python -m oracle.make_golden
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REFERENCE = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _import_reference():
+    from oracle import k2_shim
+    sys.modules["k2"] = k2_shim
+    sys.modules.setdefault("onnx", types.ModuleType("onnx"))
+    # make sure `model.*` resolves to the reference, not to this repo's mirror
+    for name in [m for m in sys.modules if m == "model" or m.startswith("model.")]:
+        del sys.modules[name]
+    sys.path.insert(0, REFERENCE)
+    try:
+        joiner = importlib.import_module("model.joiner.joiner")
+        pruned = importlib.import_module("model.loss.pruned_rnnt_loss")
+        rnnt = importlib.import_module("model.loss.rnnt_loss")
+        assert joiner.__file__.startswith(REFERENCE), joiner.__file__
+        assert pruned.__file__.startswith(REFERENCE), pruned.__file__
+    finally:
+        sys.path.remove(REFERENCE)
+        for name in [m for m in sys.modules if m == "model" or m.startswith("model.")]:
+            del sys.modules[name]
+    return joiner, pruned, rnnt
+
+
+def summarize(t: torch.Tensor, max_elems: int = 16384):
+    """Full tensor if small, else a strided sub-sample + sum + L2 norm."""
+    flat = t.detach().reshape(-1).to(torch.float64 if t.is_floating_point() else t.dtype)
+    n = flat.numel()
+    stride = max(1, -(-n // max_elems))
+    sub = flat[::stride]
+    out = {
+        "stride": np.int64(stride),
+        "numel": np.int64(n),
+        "sub": sub.to(t.dtype).numpy(),
+    }
+    if t.is_floating_point():
+        out["sum"] = np.float64(flat.sum().item())
+        out["norm"] = np.float64(flat.norm().item())
+    return out
+
+
+def run_case(name, joiner_mod, pruned_mod, rnnt_mod, dtype=torch.float32):
+    from oracle.cases import CASES, make_case
+    spec = CASES[name]
+    case = make_case(name)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    joiner = joiner_mod.Joiner(joiner_mod.JoinerConfig(**spec["joiner"]))
+    joiner.load_state_dict({k: torch.from_numpy(v) for k, v in case["weights"].items()})
+    joiner = joiner.to(dtype)
+    enc = torch.from_numpy(case["encoder_out"]).to(dtype).requires_grad_(True)
+    pred = torch.from_numpy(case["predict_out"]).to(dtype).requires_grad_(True)
+    enc_len = torch.from_numpy(case["encoder_out_lengths"])
+    tgt_len = torch.from_numpy(case["target_lengths"])
+    tgt = torch.from_numpy(case["target"])
+
+    res = {}
+    if spec["joiner"].get("prune_range", 5) > 0:
+        loss_cfg = dict(spec.get("loss", {}))
+        loss_mod = pruned_mod.PrunedRnntLoss(pruned_mod.PrunedRnntLossConfig(**loss_cfg))
+        logits, boundary, ranges, simple = joiner(enc, enc_len, pred, tgt_len, tgt)
+        pruned = loss_mod(logits=logits, targets=tgt, logits_length=enc_len,
+                          targets_length=tgt_len, boundary=boundary, ranges=ranges)
+        # rnnt_task.py:496-499 / 514
+        total = (spec["simple_loss_scale"] * simple + spec["pruned_loss_scale"] * pruned).mean()
+        total.backward()
+        res["simple_loss"] = simple.detach().to(torch.float64).numpy()
+        res["pruned_loss"] = pruned.detach().to(torch.float64).numpy()
+        res["boundary"] = boundary.numpy()
+        res["ranges"] = ranges.numpy()
+        res["logits_shape"] = np.array(logits.shape, dtype=np.int64)
+        for k, v in summarize(logits).items():
+            res[f"logits.{k}"] = v
+    else:
+        loss_mod = rnnt_mod.RnntLoss(rnnt_mod.RnntLossConfig(**spec.get("loss", {})))
+        logits, boundary, ranges, simple = joiner(enc, enc_len, pred, tgt_len)
+        assert boundary is None and ranges is None and simple is None
+        loss = loss_mod(logits=logits.float(), targets=tgt, logits_length=enc_len,
+                        targets_length=tgt_len)
+        total = loss.mean()
+        total.backward()
+        res["rnnt_loss"] = loss.detach().to(torch.float64).numpy()
+        res["logits_shape"] = np.array(logits.shape, dtype=np.int64)
+    res["total_loss"] = total.detach().to(torch.float64).numpy()
+    grads = {"d_encoder_out": enc.grad, "d_predict_out": pred.grad}
+    for pname, p in joiner.named_parameters():
+        grads["d" + pname] = p.grad if p.grad is not None else torch.zeros_like(p)
+    for gname, g in grads.items():
+        for k, v in summarize(g).items():
+            res[f"{gname}.{k}"] = v
+    return res
+
+
+def main():
+    from oracle.cases import CASES
+    joiner_mod, pruned_mod, rnnt_mod = _import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    for name, spec in CASES.items():
+        for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            if dt == torch.float64 and spec["joiner"].get("prune_range", 5) <= 0:
+                continue  # torchaudio's rnnt_loss has no fp64 kernel
+            res = run_case(name, joiner_mod, pruned_mod, rnnt_mod, dt)
+            path = os.path.join(OUT, f"{name}.{tag}.npz")
+            np.savez_compressed(path, **res)
+            keys = [k for k in ("simple_loss", "pruned_loss", "rnnt_loss") if k in res]
+            print(f"{name}.{tag}: " + ", ".join(f"{k}={res[k]}" for k in keys),
+                  f"-> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, ROOT)
+    main()

@@ -1,0 +1,121 @@
+"""ORACLE (test infrastructure, NOT product code): plain-torch CPU port of the
+reference's host-side plumbing for the transducer-loss path, on top of
+oracle/k2_shim.py.  It exists because /root/reference cannot travel to the GPU
+box; tests/test_oracle.py checks it against the golden vectors that
+oracle/make_golden.py minted by running the reference verbatim.
+
+Follows, line by line in behaviour (not in text):
+  * Joiner.forward / _do_rnnt_prune  /root/reference/model/joiner/joiner.py:74-182
+  * PrunedRnntLoss.forward           /root/reference/model/loss/pruned_rnnt_loss.py:34-50
+  * RnntLoss.forward                 /root/reference/model/loss/rnnt_loss.py:31-45
+  * PrunedRnntTask.training_step mix /root/reference/task_factory/rnnt_task.py:469-499
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+arm may import this.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from oracle import k2_shim as k2
+
+
+def _act(name: str):
+    if name == "relu":
+        return torch.relu
+    if name == "tanh":
+        return torch.tanh
+    raise ValueError(f"Unsupported activation {name}")
+
+
+def joiner_forward(w: Dict[str, torch.Tensor], cfg: dict, encoder_out, encoder_out_lengths,
+                   predict_out, target_lengths, target: Optional[torch.Tensor] = None,
+                   prune_variant: Optional[str] = None):
+    """joiner.py:126-182.  ``w`` uses the reference's state_dict keys."""
+    prune_range = cfg.get("prune_range", 5)
+    act = _act(cfg.get("activation", "relu"))
+    am = F.linear(encoder_out, w["_enc_proj.weight"], w["_enc_proj.bias"])
+    lm = F.linear(predict_out, w["_pre_proj.weight"], w["_pre_proj.bias"])
+    boundary = ranges = simple_loss = None
+    if prune_range > 0:
+        assert target.shape[0] == target_lengths.shape[0]
+        boundary = torch.zeros((am.size(0), 4), dtype=torch.int64)
+        boundary[:, 2] = target_lengths
+        boundary[:, 3] = encoder_out_lengths
+        assert target.dim() == 2
+        simple_loss, (px_grad, py_grad) = k2.rnnt_loss_smoothed(
+            lm=lm.to(dtype=torch.float32),  # "Pruned rnnt loss strictly required fp32" (joiner.py:99-102)
+            am=am.to(dtype=torch.float32),
+            symbols=target,
+            termination_symbol=0,
+            lm_only_scale=cfg.get("lm_scale", 0.0),
+            am_only_scale=cfg.get("am_scale", 0.0),
+            boundary=boundary,
+            reduction="mean",
+            return_grad=True,
+        )
+        ranges = k2.get_rnnt_prune_ranges(px_grad=px_grad, py_grad=py_grad, boundary=boundary,
+                                          s_range=prune_range, variant=prune_variant)
+        am, lm = k2.do_rnnt_pruning(am=am, lm=lm, ranges=ranges)
+    else:
+        am = am.unsqueeze(2)
+        lm = lm.unsqueeze(1)
+    h = act(am + lm)
+    if cfg.get("use_out_project", True):
+        h = F.linear(h, w["_out_projection.0.weight"], w["_out_projection.0.bias"])
+        h = F.linear(h, w["_out_projection.1.weight"], w["_out_projection.1.bias"])
+    return h, boundary, ranges, simple_loss
+
+
+def pruned_rnnt_loss(logits, targets, boundary, ranges, termination_symbol=0,
+                     rnnt_type="regular", delay_penalty=0.0, reduction="mean"):
+    """pruned_rnnt_loss.py:34-50."""
+    return k2.rnnt_loss_pruned(
+        logits=logits.to(torch.float32),  # pruned_rnnt_loss.py:40
+        symbols=targets, ranges=ranges, termination_symbol=termination_symbol,
+        boundary=boundary, rnnt_type=rnnt_type, delay_penalty=delay_penalty,
+        reduction=reduction)
+
+
+def rnnt_loss(logits, targets, logits_length, targets_length, blank_label=0, clamp=-1,
+              reduction="mean"):
+    """rnnt_loss.py:31-45 (torchaudio's compiled CPU kernel)."""
+    import torchaudio
+    return torchaudio.functional.rnnt_loss(
+        logits, targets.to(torch.int32), logits_length.to(torch.int32),
+        targets_length.to(torch.int32), blank=blank_label, clamp=clamp, reduction=reduction)
+
+
+def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None):
+    """One fwd+bwd of the hot path exactly as rnnt_task.py:469-514 strings it
+    together.  Returns a dict of losses, ranges and gradients."""
+    cfg = spec["joiner"]
+    w = {k: (torch.as_tensor(v).to(dtype)).requires_grad_(True) for k, v in w.items()}
+    enc = torch.as_tensor(case["encoder_out"]).to(dtype).requires_grad_(True)
+    pred = torch.as_tensor(case["predict_out"]).to(dtype).requires_grad_(True)
+    enc_len = torch.as_tensor(case["encoder_out_lengths"])
+    tgt_len = torch.as_tensor(case["target_lengths"])
+    tgt = torch.as_tensor(case["target"])
+    out = {}
+    if cfg.get("prune_range", 5) > 0:
+        logits, boundary, ranges, simple = joiner_forward(w, cfg, enc, enc_len, pred, tgt_len,
+                                                          tgt, prune_variant)
+        pruned = pruned_rnnt_loss(logits, tgt, boundary, ranges, **spec.get("loss", {}))
+        total = (spec["simple_loss_scale"] * simple + spec["pruned_loss_scale"] * pruned).mean()
+        out.update(simple_loss=simple.detach(), pruned_loss=pruned.detach(),
+                   boundary=boundary, ranges=ranges, logits=logits.detach())
+    else:
+        logits, _, _, _ = joiner_forward(w, cfg, enc, enc_len, pred, tgt_len)
+        loss = rnnt_loss(logits.float(), tgt, enc_len, tgt_len, **spec.get("loss", {}))
+        total = loss.mean()
+        out.update(rnnt_loss=loss.detach(), logits=logits.detach())
+    total.backward()
+    out["total_loss"] = total.detach()
+    out["d_encoder_out"] = enc.grad
+    out["d_predict_out"] = pred.grad
+    for k, v in w.items():
+        out["d" + k] = v.grad if v.grad is not None else torch.zeros_like(v)
+    return out

@@ -1,0 +1,234 @@
+// extern "C" surface of libs2t_b200.so (declared in include/s2t_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/s2t_b200.h"
+#include "joiner.cuh"
+#include "lattice.cuh"
+
+namespace s2t {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+// implemented in the other translation units
+int simple_logprobs(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
+                    int S, int V, int blank, float* am_max, float* lm_max, float* px, float* py, float* nrm,
+                    cudaStream_t stream);
+int simple_backward(const float* am, const float* lm, const int64_t* sym, const float* am_max,
+                    const float* lm_max, const float* nrm, const float* occ_px, const float* occ_py,
+                    const float* coef, int B, int T, int S, int V, int blank, float* wbuf, float* d_am,
+                    float* d_lm, cudaStream_t stream);
+int prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boundary, int B, int S, int T, int R,
+                 int variant, int64_t* ranges, cudaStream_t stream);
+int lse_gather(const void* logits, int dtype, const int64_t* sym, const int64_t* ranges, const int64_t* boundary,
+               int B, int T, int R, int V, int S, int blank, float delay_penalty, float* lse, float* px, float* py,
+               cudaStream_t stream);
+int logits_grad(const void* logits, int dtype, const int64_t* sym, const int64_t* ranges, const float* lse,
+                const float* occ_px, const float* occ_py, const float* coef, int B, int T, int R, int V, int S,
+                int blank, float clamp, void* grad, cudaStream_t stream);
+
+static LatticeView simple_view(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
+                               float* alpha) {
+  LatticeView v{};
+  v.px = px;
+  v.py = py;
+  v.px_bs = (int64_t)S * (T + 1);
+  v.px_ts = 1;
+  v.px_rs = T + 1;
+  v.py_bs = (int64_t)(S + 1) * T;
+  v.py_ts = 1;
+  v.py_rs = T;
+  v.rx = S;
+  v.ry = S + 1;
+  v.ranges = nullptr;
+  v.boundary = boundary;
+  v.B = B;
+  v.S = S;
+  v.T = T;
+  v.alpha = alpha;
+  v.a_bs = (int64_t)(S + 1) * (T + 1);
+  v.a_ts = 1;
+  v.a_rs = T + 1;
+  return v;
+}
+
+static LatticeView band_view(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary,
+                             int B, int S, int T, int R, float* alpha) {
+  LatticeView v{};
+  v.px = px;
+  v.py = py;
+  v.px_bs = v.py_bs = (int64_t)T * R;
+  v.px_ts = v.py_ts = R;
+  v.px_rs = v.py_rs = 1;
+  v.rx = v.ry = R;
+  v.ranges = ranges;
+  v.rg_bs = (int64_t)T * R;
+  v.rg_ts = R;
+  v.boundary = boundary;
+  v.B = B;
+  v.S = S;
+  v.T = T;
+  v.alpha = alpha;
+  v.a_bs = (int64_t)(T + 1) * R;
+  v.a_ts = R;
+  v.a_rs = 1;
+  return v;
+}
+
+static int band_dp(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary, int B, int S,
+                   int T, int R, float* alpha, float* scores, float* occ_px, float* occ_py, cudaStream_t st) {
+  LatticeView v = band_view(px, py, ranges, boundary, B, S, T, R, alpha);
+  size_t n = (size_t)B * T * R * sizeof(float);
+  cudaMemsetAsync(occ_px, 0, n, st);
+  cudaMemsetAsync(occ_py, 0, n, st);
+  return launch_lattice_fwd_bwd(v, scores, occ_px, occ_py, st);
+}
+
+static JoinerProblem make_problem(const float* am, const float* lm, const int64_t* symbols, const int64_t* ranges,
+                                  const int64_t* boundary, const float* W1, const float* b1, const float* W2,
+                                  const float* b2, int B, int T, int S, int R, int V, int I, int act, int blank,
+                                  float delay_penalty) {
+  JoinerProblem p{};
+  p.am = am; p.lm = lm; p.sym = symbols; p.ranges = ranges; p.boundary = boundary;
+  p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
+  p.B = B; p.T = T; p.S = S; p.R = R; p.V = V; p.I = I;
+  p.act = act; p.blank = blank; p.delay_penalty = delay_penalty;
+  return p;
+}
+
+}  // namespace s2t
+
+using namespace s2t;
+
+extern "C" {
+
+int s2t_abi_version(void) { return S2T_ABI_VERSION; }
+const char* s2t_last_error(void) { return g_error; }
+
+int s2t_mutual_information(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
+                           float* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2T_REQUIRE(B >= 0 && S >= 0 && T >= 0, "mutual_information: negative dimension");
+  LatticeView v = simple_view(px, py, boundary, B, S, T, alpha_ws);
+  if (px_grad == nullptr || py_grad == nullptr) return launch_lattice_fwd(v, scores, st);
+  cudaMemsetAsync(px_grad, 0, (size_t)B * S * (T + 1) * sizeof(float), st);
+  cudaMemsetAsync(py_grad, 0, (size_t)B * (S + 1) * T * sizeof(float), st);
+  return launch_lattice_fwd_bwd(v, scores, px_grad, py_grad, st);
+}
+
+int s2t_simple_loss_fwd(const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
+                        int B, int T, int S, int V, int blank, float lm_only_scale, float am_only_scale,
+                        float* am_max, float* lm_max, float* px, float* py, float* nrm, float* alpha_ws,
+                        float* scores, float* px_grad, float* py_grad, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2T_REQUIRE(lm_only_scale == 0.f && am_only_scale == 0.f,
+              "simple_loss: non-zero lm_only_scale/am_only_scale (%g, %g) not supported by ABI v%d",
+              lm_only_scale, am_only_scale, S2T_ABI_VERSION);
+  S2T_REQUIRE(B > 0 && T > 0 && S >= 0 && V > 0, "simple_loss: bad dims B=%d T=%d S=%d V=%d", B, T, S, V);
+  S2T_REQUIRE(blank >= 0 && blank < V, "simple_loss: blank %d out of range", blank);
+  if (int rc = simple_logprobs(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm, st))
+    return rc;
+  return s2t_mutual_information(px, py, boundary, B, S, T, alpha_ws, scores, px_grad, py_grad, stream);
+}
+
+int s2t_simple_loss_bwd(const float* am, const float* lm, const int64_t* symbols, const float* am_max,
+                        const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,
+                        const float* grad_scores, int B, int T, int S, int V, int blank, float* wbuf,
+                        float* d_am, float* d_lm, void* stream) {
+  return simple_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, grad_scores, B, T, S, V, blank,
+                         wbuf, d_am, d_lm, (cudaStream_t)stream);
+}
+
+int s2t_prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boundary, int B, int S, int T,
+                     int s_range, int variant, int64_t* ranges, void* stream) {
+  S2T_REQUIRE(boundary != nullptr, "prune_ranges: boundary is required");
+  return prune_ranges(px_grad, py_grad, boundary, B, S, T, s_range, variant, ranges, (cudaStream_t)stream);
+}
+
+int s2t_logits_loss_fwd(const void* logits, int dtype, const int64_t* symbols, const int64_t* ranges,
+                        const int64_t* boundary, int B, int T, int S, int R, int V, int blank,
+                        float delay_penalty, float* lse, float* px, float* py, float* alpha_ws, float* scores,
+                        float* occ_px, float* occ_py, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2T_REQUIRE(ranges != nullptr || R == S + 1, "logits_loss: unpruned logits need R == S+1 (R=%d, S=%d)", R, S);
+  if (int rc = lse_gather(logits, dtype, symbols, ranges, boundary, B, T, R, V, S, blank, delay_penalty, lse, px,
+                          py, st))
+    return rc;
+  return band_dp(px, py, ranges, boundary, B, S, T, R, alpha_ws, scores, occ_px, occ_py, st);
+}
+
+int s2t_logits_loss_bwd(const void* logits, int dtype, const int64_t* symbols, const int64_t* ranges,
+                        const float* lse, const float* occ_px, const float* occ_py, const float* grad_scores,
+                        int B, int T, int S, int R, int V, int blank, float clamp, void* grad, void* stream) {
+  return logits_grad(logits, dtype, symbols, ranges, lse, occ_px, occ_py, grad_scores, B, T, R, V, S, blank, clamp,
+                     grad, (cudaStream_t)stream);
+}
+
+size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {
+  (void)mode;
+  return joiner_simt_workspace_bytes((int64_t)B * T * R, V, I, nullptr);
+}
+
+int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols,
+                        const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
+                        const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
+                        int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
+                        float* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT, "joiner_loss_fwd: mode %d not built", mode);
+  S2T_REQUIRE(ranges != nullptr || R == S + 1, "joiner_loss: unpruned joiner needs R == S+1 (R=%d, S=%d)", R, S);
+  S2T_REQUIRE(I == 0 || (W1 && b1 && W2 && b2), "joiner_loss: out-projection weights missing");
+  JoinerProblem p = make_problem(am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
+                                 delay_penalty);
+  if (int rc = joiner_simt_forward(p, workspace, lse, px, py, st)) return rc;
+  return band_dp(px, py, ranges, boundary, B, S, T, R, alpha_ws, scores, occ_px, occ_py, st);
+}
+
+int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols,
+                        const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
+                        const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
+                        int blank, float clamp, void* workspace, const float* lse, const float* occ_px,
+                        const float* occ_py, const float* grad_scores, float* d_am, float* d_lm, float* dW1,
+                        float* db1, float* dW2, float* db2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT, "joiner_loss_bwd: mode %d not built", mode);
+  JoinerProblem p = make_problem(am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
+                                 0.f);
+  cudaMemsetAsync(d_am, 0, (size_t)B * T * V * sizeof(float), st);
+  cudaMemsetAsync(d_lm, 0, (size_t)B * (S + 1) * V * sizeof(float), st);
+  if (I > 0) {
+    cudaMemsetAsync(dW1, 0, (size_t)I * V * sizeof(float), st);
+    cudaMemsetAsync(db1, 0, (size_t)I * sizeof(float), st);
+    cudaMemsetAsync(dW2, 0, (size_t)V * I * sizeof(float), st);
+    cudaMemsetAsync(db2, 0, (size_t)V * sizeof(float), st);
+  }
+  return joiner_simt_backward(p, workspace, lse, occ_px, occ_py, grad_scores, clamp, d_am, d_lm, dW1, db1, dW2, db2,
+                              st);
+}
+
+int s2t_joiner_materialize(int mode, const float* am, const float* lm, const int64_t* ranges, const float* W1,
+                           const float* b1, const float* W2, const float* b2, int B, int T, int S, int R, int V,
+                           int I, int act, void* workspace, float* logits, void* stream) {
+  S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT, "joiner_materialize: mode %d not built", mode);
+  JoinerProblem p = make_problem(am, lm, nullptr, ranges, nullptr, W1, b1, W2, b2, B, T, S, R, V, I, act, 0, 0.f);
+  return joiner_simt_materialize(p, workspace, logits, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// Prune-range selection: for every frame pick the window of `s_range` symbol
+// positions that carries the most occupation mass of the simple lattice, then
+// make the window starts monotone and gap-free.
+//
+// Replaces k2.get_rnnt_prune_ranges as called from
+// /root/reference/model/joiner/joiner.py:112-117  (k2 semantics: SURVEY.md A.4).
+// Integer output, bit-exact contract: identical (px_grad, py_grad) inputs, fp32
+// left-to-right summation over the window, first-maximum tie-break.
+//
+// One CTA per utterance:
+//   phase 1  thread-per-frame argmax over s (reads are coalesced along t: the
+//            occupation arrays are t-contiguous),
+//   phase 2  padding fix-up + two suffix-min scans (k2.monotonic_lower_bound)
+//            with the +-(R-1)*t transform between them, done in shared memory,
+//   phase 3  coalesced int64 store of ranges[b, t, 0..R).
+// HBM-bound integer/compare work: reads (S*(T+1) + (S+1)*T)*4 B, writes T*R*8 B
+// per utterance.
+#include "common.cuh"
+
+namespace s2t {
+namespace {
+
+constexpr int kThreads = 256;
+
+// suffix-min over sm[0..T) in place (Hillis-Steele, chunked from the right)
+__device__ void suffix_min_inplace(int* sm, int* tmp, int T) {
+  // process chunks of blockDim from the right end carrying the running min
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = INT_MAX;
+  __syncthreads();
+  const int n = blockDim.x;
+  for (int hi = T; hi > 0; hi -= n) {
+    const int lo = max(hi - n, 0);
+    const int len = hi - lo;
+    const int i = threadIdx.x;
+    int v = (i < len) ? sm[lo + i] : INT_MAX;
+    // inclusive suffix scan inside the chunk
+    for (int off = 1; off < n; off <<= 1) {
+      tmp[i] = v;
+      __syncthreads();
+      if (i + off < len) v = min(v, tmp[i + off]);
+      __syncthreads();
+    }
+    const int c = carry;
+    __syncthreads();
+    if (i < len) {
+      v = min(v, c);
+      sm[lo + i] = v;
+    }
+    __syncthreads();
+    if (i == 0) carry = v;  // element lo holds the min of everything to its right
+    __syncthreads();
+  }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads)
+prune_ranges_kernel(const float* __restrict__ px_grad, const float* __restrict__ py_grad,
+                    const int64_t* __restrict__ boundary, int S, int T, int R,
+                    int64_t* __restrict__ ranges) {
+  extern __shared__ int sm[];  // T ints + blockDim scratch
+  int* sbeg = sm;
+  int* tmp = sm + T;
+  const int b = blockIdx.x;
+  const int S1 = S + 1, T1 = T + 1;
+  const float* pxg = px_grad + (int64_t)b * S * T1;
+  const float* pyg = py_grad + (int64_t)b * S1 * T;
+  const int Sb = (int)boundary[4 * b + 2], Tb = (int)boundary[4 * b + 3];
+  const int pad = max(Sb - R + 1, 0);
+  const int ncand = S1 - R + 1;
+
+  // phase 1: argmax_s of the window score, one frame per thread
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    int best = 0;
+    if (t < Tb - 1) {
+      float best_v = kNegInf;
+      for (int s = 0; s < ncand; ++s) {
+        float v;
+        if (VARIANT == 0) {
+          // A: sum_k py_grad[s+k, t] (left to right) - px_grad[s-1, t]
+          float acc = __ldg(pyg + (int64_t)s * T + t);
+          for (int k = 1; k < R; ++k) acc += __ldg(pyg + (int64_t)(s + k) * T + t);
+          float pxp = (s == 0) ? 0.f : __ldg(pxg + (int64_t)(s - 1) * T1 + t);
+          v = acc - pxp;
+        } else {
+          // B: cs[s+R] - cs[s] with cs the running sum over s of px_grad + py_grad
+          // (evaluated as the two prefix sums k2 would form, sequentially from 0)
+          float cs_lo = 0.f;
+          for (int j = 0; j < s; ++j) {
+            float tot = (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+            cs_lo += tot;
+          }
+          float cs_hi = cs_lo;
+          for (int j = s; j < s + R; ++j) {
+            float tot = (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+            cs_hi += tot;
+          }
+          v = cs_hi - cs_lo;
+        }
+        if (v > best_v) {  // strict: first maximum wins
+          best_v = v;
+          best = s;
+        }
+      }
+    } else {
+      best = pad;  // last real frame and padding frames
+    }
+    sbeg[t] = best;
+  }
+  __syncthreads();
+
+  // phase 2: _adjust_pruning_lower_bound
+  suffix_min_inplace(sbeg, tmp, T);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) sbeg[t] = -(sbeg[t] - (R - 1) * t);
+  __syncthreads();
+  suffix_min_inplace(sbeg, tmp, T);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) sbeg[t] = -(max(sbeg[t], 0) - (R - 1) * t);
+  __syncthreads();
+
+  // phase 3
+  int64_t* out = ranges + (int64_t)b * T * R;
+  for (int i = threadIdx.x; i < T * R; i += blockDim.x) out[i] = (int64_t)sbeg[i / R] + (i % R);
+}
+
+}  // namespace
+
+int prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boundary, int B, int S,
+                 int T, int R, int variant, int64_t* ranges, cudaStream_t stream) {
+  S2T_REQUIRE(R >= 2 && R <= S + 1, "prune_ranges: s_range=%d must be in [2, S+1=%d]", R, S + 1);
+  S2T_REQUIRE(variant == 0 || variant == 1, "prune_ranges: unknown variant %d", variant);
+  if (B == 0 || T == 0) return 0;
+  size_t smem = (size_t)(T + kThreads) * sizeof(int);
+  S2T_REQUIRE(smem <= 200 * 1024, "prune_ranges: T=%d too long for one CTA", T);
+  auto kern = variant == 0 ? prune_ranges_kernel<0> : prune_ranges_kernel<1>;
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  kern<<<B, kThreads, smem, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
+  return check_launch("prune_ranges_kernel");
+}
+
+}  // namespace s2t

@@ -1,0 +1,306 @@
+"""torch.autograd wrappers around the C ABI (include/s2t_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and the
+autograd tape; all arithmetic on the hot path is in libs2t_b200.so.
+Function names mirror the k2 / torchaudio calls of the reference they replace.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, lib, ptr, stream
+
+PRUNE_VARIANTS = {"A": 0, "B": 1}
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+def _i64c(t: Tensor) -> Tensor:
+    return t.to(torch.int64).contiguous()
+
+
+def make_boundary(target_lengths: Tensor, encoder_out_lengths: Tensor, device) -> Tensor:
+    """/root/reference/model/joiner/joiner.py:89-93 -- rows [0, 0, S_b, T_b], int64.
+    Lengths may arrive as float tensors (joiner_test.py:56-58)."""
+    B = target_lengths.shape[0]
+    boundary = torch.zeros((B, 4), dtype=torch.int64, device=device)
+    boundary[:, 2] = target_lengths.to(device)
+    boundary[:, 3] = encoder_out_lengths.to(device)
+    return boundary
+
+
+# ---------------------------------------------------------------------------
+# k2.mutual_information_recursion
+# ---------------------------------------------------------------------------
+def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tensor] = None,
+                                 return_grad: bool = False):
+    """Scores (B,) and, optionally, the occupation probabilities.  Not
+    differentiable by itself (the fused losses below own the autograd edges)."""
+    px, py = _f32c(px), _f32c(py)
+    B, S, T1 = px.shape
+    T = py.shape[-1]
+    assert T1 == T + 1 and py.shape == (B, S + 1, T), (px.shape, py.shape)
+    if boundary is not None:
+        boundary = _i64c(boundary)
+    alpha = torch.empty((B, S + 1, T + 1), dtype=torch.float32, device=px.device)
+    scores = torch.empty((B,), dtype=torch.float32, device=px.device)
+    px_grad = torch.empty_like(px) if return_grad else None
+    py_grad = torch.empty_like(py) if return_grad else None
+    check(lib().s2t_mutual_information(ptr(px), ptr(py), ptr(boundary), B, S, T, ptr(alpha), ptr(scores),
+                                       ptr(px_grad), ptr(py_grad), stream()))
+    return (scores, (px_grad, py_grad)) if return_grad else scores
+
+
+# ---------------------------------------------------------------------------
+# k2.rnnt_loss_smoothed(..., return_grad=True)      joiner.py:100-110
+# ---------------------------------------------------------------------------
+class _SimpleLoss(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, am: Tensor, lm: Tensor, symbols: Tensor, boundary: Tensor, blank: int,
+                lm_only_scale: float, am_only_scale: float):
+        am, lm = _f32c(am), _f32c(lm)
+        symbols, boundary = _i64c(symbols), _i64c(boundary)
+        B, T, V = am.shape
+        S = lm.shape[1] - 1
+        assert lm.shape == (B, S + 1, V) and symbols.shape == (B, S), (am.shape, lm.shape, symbols.shape)
+        dev = am.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        am_max = torch.empty((B, T), **f32)
+        lm_max = torch.empty((B, S + 1), **f32)
+        px = torch.empty((B, S, T + 1), **f32)
+        py = torch.empty((B, S + 1, T), **f32)
+        nrm = torch.empty((B, S + 1, T), **f32)
+        alpha = torch.empty((B, S + 1, T + 1), **f32)
+        scores = torch.empty((B,), **f32)
+        px_grad = torch.empty((B, S, T + 1), **f32)
+        py_grad = torch.empty((B, S + 1, T), **f32)
+        check(lib().s2t_simple_loss_fwd(ptr(am), ptr(lm), ptr(symbols), ptr(boundary), B, T, S, V, blank,
+                                        float(lm_only_scale), float(am_only_scale), ptr(am_max), ptr(lm_max),
+                                        ptr(px), ptr(py), ptr(nrm), ptr(alpha), ptr(scores), ptr(px_grad),
+                                        ptr(py_grad), stream()))
+        ctx.save_for_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad)
+        ctx.blank = blank
+        ctx.mark_non_differentiable(px_grad, py_grad)
+        return scores, px_grad, py_grad
+
+    @staticmethod
+    def backward(ctx, grad_scores, _gx, _gy):
+        am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad = ctx.saved_tensors
+        B, T, V = am.shape
+        S = lm.shape[1] - 1
+        grad_scores = _f32c(grad_scores)
+        wbuf = torch.empty((B, S + 1, T), dtype=torch.float32, device=am.device)
+        d_am = torch.empty_like(am)
+        d_lm = torch.empty_like(lm)
+        check(lib().s2t_simple_loss_bwd(ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
+                                        ptr(px_grad), ptr(py_grad), ptr(grad_scores), B, T, S, V, ctx.blank,
+                                        ptr(wbuf), ptr(d_am), ptr(d_lm), stream()))
+        return d_am, d_lm, None, None, None, None, None
+
+
+def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
+                       lm_only_scale: float = 0.0, am_only_scale: float = 0.0,
+                       boundary: Optional[Tensor] = None, reduction: str = "mean",
+                       return_grad: bool = False):
+    """Drop-in for ``k2.rnnt_loss_smoothed`` (rnnt_type='regular')."""
+    if boundary is None:
+        B, T = am.shape[0], am.shape[1]
+        boundary = torch.zeros((B, 4), dtype=torch.int64, device=am.device)
+        boundary[:, 2] = lm.shape[1] - 1
+        boundary[:, 3] = T
+    scores, px_grad, py_grad = _SimpleLoss.apply(am, lm, symbols, boundary, termination_symbol,
+                                                 lm_only_scale, am_only_scale)
+    loss = _reduce(scores, reduction)
+    return (loss, (px_grad, py_grad)) if return_grad else loss
+
+
+def _reduce(scores: Tensor, reduction: str) -> Tensor:
+    if reduction == "none":
+        return -scores
+    if reduction == "mean":
+        return -torch.mean(scores)
+    if reduction == "sum":
+        return -torch.sum(scores)
+    raise ValueError(f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+
+
+# ---------------------------------------------------------------------------
+# k2.get_rnnt_prune_ranges                              joiner.py:112-117
+# ---------------------------------------------------------------------------
+def get_rnnt_prune_ranges(px_grad: Tensor, py_grad: Tensor, boundary: Tensor, s_range: int,
+                          variant: Optional[str] = None) -> Tensor:
+    variant = variant or os.environ.get("S2T_B200_PRUNE_VARIANT", "A")
+    px_grad, py_grad, boundary = _f32c(px_grad), _f32c(py_grad), _i64c(boundary)
+    B, S, T1 = px_grad.shape
+    T = py_grad.shape[-1]
+    assert T1 == T + 1, "only rnnt_type='regular' lattices are supported"
+    assert py_grad.shape == (B, S + 1, T), py_grad.shape
+    assert boundary.shape == (B, 4), boundary.shape
+    assert S >= 1, S
+    assert T >= S, (T, S)
+    if s_range > S:  # no symbol is pruned; keep indexing with ranges valid
+        s_range = S + 1
+    assert s_range >= 2, ("Pruning range for standard RNN-T should be equal to or greater than 2, "
+                          "or no valid paths could survive pruning.")
+    ranges = torch.empty((B, T, s_range), dtype=torch.int64, device=px_grad.device)
+    check(lib().s2t_prune_ranges(ptr(px_grad), ptr(py_grad), ptr(boundary), B, S, T, s_range,
+                                 PRUNE_VARIANTS[variant], ptr(ranges), stream()))
+    return ranges
+
+
+# ---------------------------------------------------------------------------
+# loss on materialised logits: k2.rnnt_loss_pruned / torchaudio rnnt_loss
+# ---------------------------------------------------------------------------
+class _LogitsLoss(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, logits: Tensor, symbols: Tensor, ranges: Optional[Tensor], boundary: Tensor,
+                blank: int, delay_penalty: float, clamp: float):
+        logits = logits.contiguous()
+        symbols, boundary = _i64c(symbols), _i64c(boundary)
+        B, T, R, V = logits.shape
+        S = symbols.shape[1]
+        if ranges is not None:
+            ranges = _i64c(ranges)
+            assert ranges.shape == (B, T, R), (ranges.shape, logits.shape)
+        dev = logits.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        lse = torch.empty((B, T, R), **f32)
+        px = torch.empty((B, T, R), **f32)
+        py = torch.empty((B, T, R), **f32)
+        occ_px = torch.empty((B, T, R), **f32)
+        occ_py = torch.empty((B, T, R), **f32)
+        alpha = torch.empty((B, T + 1, R), **f32)
+        scores = torch.empty((B,), **f32)
+        check(lib().s2t_logits_loss_fwd(ptr(logits), _lib.dtype_code(logits.dtype), ptr(symbols), ptr(ranges),
+                                        ptr(boundary), B, T, S, R, V, blank, float(delay_penalty), ptr(lse),
+                                        ptr(px), ptr(py), ptr(alpha), ptr(scores), ptr(occ_px), ptr(occ_py),
+                                        stream()))
+        ctx.save_for_backward(logits, symbols, ranges if ranges is not None else torch.empty(0, device=dev),
+                              lse, occ_px, occ_py)
+        ctx.has_ranges = ranges is not None
+        ctx.blank, ctx.clamp, ctx.S = blank, clamp, S
+        return scores
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        logits, symbols, ranges, lse, occ_px, occ_py = ctx.saved_tensors
+        B, T, R, V = logits.shape
+        grad = torch.empty_like(logits)
+        check(lib().s2t_logits_loss_bwd(ptr(logits), _lib.dtype_code(logits.dtype), ptr(symbols),
+                                        ptr(ranges if ctx.has_ranges else None), ptr(lse), ptr(occ_px),
+                                        ptr(occ_py), ptr(_f32c(grad_scores)), B, T, ctx.S, R, V, ctx.blank,
+                                        float(ctx.clamp), ptr(grad), stream()))
+        return grad, None, None, None, None, None, None
+
+
+def logits_scores(logits: Tensor, symbols: Tensor, ranges: Optional[Tensor], boundary: Tensor,
+                  blank: int = 0, delay_penalty: float = 0.0, clamp: float = -1.0) -> Tensor:
+    """log P(y|x) per utterance from a materialised (B,T,R,V) logits tensor."""
+    return _LogitsLoss.apply(logits, symbols, ranges, boundary, blank, delay_penalty, clamp)
+
+
+# ---------------------------------------------------------------------------
+# fused joiner + loss (logits never materialised)
+# ---------------------------------------------------------------------------
+class _JoinerLoss(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, am: Tensor, lm: Tensor, W1, b1, W2, b2, symbols: Tensor, ranges: Optional[Tensor],
+                boundary: Tensor, act: int, blank: int, delay_penalty: float, clamp: float, mode: int):
+        am, lm = _f32c(am), _f32c(lm)
+        symbols, boundary = _i64c(symbols), _i64c(boundary)
+        B, T, V = am.shape
+        S = lm.shape[1] - 1
+        dev = am.device
+        if ranges is not None:
+            ranges = _i64c(ranges)
+            R = ranges.shape[2]
+            assert ranges.shape == (B, T, R)
+        else:
+            R = S + 1
+        has_proj = W1 is not None
+        if has_proj:
+            W1, b1, W2, b2 = _f32c(W1), _f32c(b1), _f32c(W2), _f32c(b2)
+            I = W1.shape[0]
+            assert W1.shape == (I, V) and W2.shape == (V, I) and b1.shape == (I,) and b2.shape == (V,)
+        else:
+            I = 0
+        f32 = dict(dtype=torch.float32, device=dev)
+        nbytes = lib().s2t_joiner_workspace_bytes(mode, B, T, R, V, I)
+        workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        lse = torch.empty((B, T, R), **f32)
+        px = torch.empty((B, T, R), **f32)
+        py = torch.empty((B, T, R), **f32)
+        occ_px = torch.empty((B, T, R), **f32)
+        occ_py = torch.empty((B, T, R), **f32)
+        alpha = torch.empty((B, T + 1, R), **f32)
+        scores = torch.empty((B,), **f32)
+        check(lib().s2t_joiner_loss_fwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(ranges), ptr(boundary),
+                                        ptr(W1), ptr(b1), ptr(W2), ptr(b2), B, T, S, R, V, I, act, blank,
+                                        float(delay_penalty), ptr(workspace), ptr(lse), ptr(px), ptr(py),
+                                        ptr(alpha), ptr(scores), ptr(occ_px), ptr(occ_py), stream()))
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(am, lm, W1 if has_proj else empty, b1 if has_proj else empty,
+                              W2 if has_proj else empty, b2 if has_proj else empty, symbols,
+                              ranges if ranges is not None else empty, boundary, workspace, lse, occ_px, occ_py)
+        ctx.meta = (has_proj, ranges is not None, S, R, I, act, blank, clamp, mode)
+        return scores
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        (am, lm, W1, b1, W2, b2, symbols, ranges, boundary, workspace, lse, occ_px, occ_py) = ctx.saved_tensors
+        has_proj, has_ranges, S, R, I, act, blank, clamp, mode = ctx.meta
+        B, T, V = am.shape
+        d_am = torch.empty_like(am)
+        d_lm = torch.empty_like(lm)
+        if has_proj:
+            dW1, db1, dW2, db2 = (torch.empty_like(W1), torch.empty_like(b1), torch.empty_like(W2),
+                                  torch.empty_like(b2))
+        else:
+            W1 = b1 = W2 = b2 = dW1 = db1 = dW2 = db2 = None
+        check(lib().s2t_joiner_loss_bwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(ranges if has_ranges else None),
+                                        ptr(boundary), ptr(W1), ptr(b1), ptr(W2), ptr(b2), B, T, S, R, V, I, act,
+                                        blank, float(clamp), ptr(workspace), ptr(lse), ptr(occ_px), ptr(occ_py),
+                                        ptr(_f32c(grad_scores)), ptr(d_am), ptr(d_lm), ptr(dW1), ptr(db1),
+                                        ptr(dW2), ptr(db2), stream()))
+        return (d_am, d_lm, dW1, db1, dW2, db2, None, None, None, None, None, None, None, None)
+
+
+def joiner_scores(am: Tensor, lm: Tensor, W1, b1, W2, b2, symbols: Tensor, ranges: Optional[Tensor],
+                  boundary: Tensor, act: int, blank: int = 0, delay_penalty: float = 0.0,
+                  clamp: float = -1.0, mode: int = _lib.MODE_FP32_SIMT) -> Tensor:
+    """log P(y|x) per utterance of the (pruned or full) joiner lattice, fused."""
+    return _JoinerLoss.apply(am, lm, W1, b1, W2, b2, symbols, ranges, boundary, act, blank, delay_penalty,
+                             clamp, mode)
+
+
+def joiner_materialize(am: Tensor, lm: Tensor, W1, b1, W2, b2, ranges: Optional[Tensor], act: int,
+                       mode: int = _lib.MODE_FP32_SIMT) -> Tensor:
+    """The (B,T,R,V) logits the fused path never stores (debug / materialised mode, no autograd)."""
+    am, lm = _f32c(am.detach()), _f32c(lm.detach())
+    B, T, V = am.shape
+    S = lm.shape[1] - 1
+    if ranges is not None:
+        ranges = _i64c(ranges)
+        R = ranges.shape[2]
+    else:
+        R = S + 1
+    I = 0
+    if W1 is not None:
+        W1, b1, W2, b2 = (_f32c(x.detach()) for x in (W1, b1, W2, b2))
+        I = W1.shape[0]
+    nbytes = lib().s2t_joiner_workspace_bytes(mode, B, T, R, V, I)
+    workspace = torch.empty((nbytes,), dtype=torch.uint8, device=am.device)
+    logits = torch.empty((B, T, R, V), dtype=torch.float32, device=am.device)
+    check(lib().s2t_joiner_materialize(mode, ptr(am), ptr(lm), ptr(ranges), ptr(W1), ptr(b1), ptr(W2), ptr(b2),
+                                       B, T, S, R, V, I, act, ptr(workspace), ptr(logits), stream()))
+    return logits

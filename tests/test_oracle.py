@@ -1,0 +1,148 @@
+"""CPU tests of the oracle itself: the restatement must reproduce the golden
+vectors minted from the reference (oracle/make_golden.py) and agree with the
+independent anchors (torchaudio, fp64 autograd through a loop DP)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import check_summary, load_golden
+from oracle import k2_shim as k2
+from oracle import reference_port as port
+from oracle.cases import CASES, make_case
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_port_matches_reference_goldens(name, tag):
+    spec = CASES[name]
+    pruned = spec["joiner"].get("prune_range", 5) > 0
+    if tag == "f64" and not pruned:
+        pytest.skip("torchaudio has no fp64 kernel")
+    gold = load_golden(name, tag)
+    case = make_case(name)
+    dtype = torch.float32 if tag == "f32" else torch.float64
+    out = port.training_step_loss(case["weights"], spec, case, dtype=dtype)
+    tol = 2e-6 if tag == "f32" else 1e-12
+    if pruned:
+        assert np.array_equal(out["ranges"].numpy(), gold["ranges"])
+        assert np.array_equal(out["boundary"].numpy(), gold["boundary"])
+        np.testing.assert_allclose(out["simple_loss"].double().numpy(), gold["simple_loss"], rtol=tol)
+        np.testing.assert_allclose(out["pruned_loss"].double().numpy(), gold["pruned_loss"], rtol=tol)
+    else:
+        np.testing.assert_allclose(out["rnnt_loss"].double().numpy(), gold["rnnt_loss"], rtol=tol)
+    for key in [k[:-len(".stride")] for k in gold if k.endswith(".stride") and k.startswith("d")]:
+        check_summary(out[key], gold, key, rtol=50 * tol, what=f"{name}.{tag}")
+
+
+def test_f32_and_f64_goldens_agree():
+    """fp32 reference run vs fp64 reference run: the tolerance budget of north_star
+    (1e-5 loss, 1e-4 grads) has to be achievable by fp32 arithmetic at all."""
+    for name, spec in CASES.items():
+        if spec["joiner"].get("prune_range", 5) <= 0:
+            continue
+        g32, g64 = load_golden(name, "f32"), load_golden(name, "f64")
+        np.testing.assert_allclose(g32["pruned_loss"], g64["pruned_loss"], rtol=1e-5)
+        np.testing.assert_allclose(g32["simple_loss"], g64["simple_loss"], rtol=1e-5)
+        mism = (g32["ranges"] != g64["ranges"]).mean()
+        assert mism < 0.01, (name, mism)
+
+
+def _toy(B=3, T=20, S=7, V=11, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    am = torch.randn(B, T, V, generator=g)
+    lm = torch.randn(B, S + 1, V, generator=g)
+    sym = torch.randint(1, V, (B, S), generator=g)
+    Tl = torch.tensor([T, T - 5, T - 11])[:B]
+    Sl = torch.tensor([S, S - 2, S - 4])[:B]
+    boundary = torch.zeros(B, 4, dtype=torch.int64)
+    boundary[:, 2] = Sl
+    boundary[:, 3] = Tl
+    return am, lm, sym, Tl, Sl, boundary
+
+
+def test_simple_equals_torchaudio_on_trivial_joiner():
+    import torchaudio
+    am, lm, sym, Tl, Sl, boundary = _toy()
+    am.requires_grad_(True)
+    loss, _ = k2.rnnt_loss_smoothed(lm=lm, am=am, symbols=sym, termination_symbol=0, lm_only_scale=0.0,
+                                    am_only_scale=0.0, boundary=boundary, reduction="none", return_grad=True)
+    logits = am[:, :, None, :] + lm[:, None, :, :]
+    ta = torchaudio.functional.rnnt_loss(logits, sym.int(), Tl.int(), Sl.int(), blank=0, reduction="none")
+    torch.testing.assert_close(loss, ta, rtol=1e-5, atol=1e-5)
+    g1, = torch.autograd.grad(loss.sum(), am, retain_graph=True)
+    g2, = torch.autograd.grad(ta.sum(), am)
+    torch.testing.assert_close(g1, g2, rtol=1e-4, atol=2e-5)
+
+
+def test_pruned_equals_torchaudio_when_range_covers_lattice():
+    import torchaudio
+    am, lm, sym, Tl, Sl, boundary = _toy(seed=1)
+    S, V = sym.shape[1], am.shape[2]
+    _, (pxg, pyg) = k2.rnnt_loss_smoothed(lm=lm, am=am, symbols=sym, termination_symbol=0, lm_only_scale=0.0,
+                                          am_only_scale=0.0, boundary=boundary, reduction="none",
+                                          return_grad=True)
+    ranges = k2.get_rnnt_prune_ranges(pxg, pyg, boundary, S + 3)
+    assert ranges.shape[2] == S + 1
+    W = torch.randn(V, V, generator=torch.Generator().manual_seed(5))
+    am_p, lm_p = k2.do_rnnt_pruning(am, lm, ranges)
+    pl = k2.rnnt_loss_pruned(torch.tanh(am_p + lm_p) @ W, sym, ranges, 0, boundary, reduction="none")
+    full = torch.tanh(am[:, :, None, :] + lm[:, None, :, :]) @ W
+    ta = torchaudio.functional.rnnt_loss(full, sym.int(), Tl.int(), Sl.int(), blank=0, reduction="none")
+    torch.testing.assert_close(pl, ta, rtol=1e-5, atol=1e-5)
+
+
+def test_occupation_probs_match_fp64_autograd_of_loop_dp():
+    """Independent check of mutual_information backward: differentiate a plain
+    python loop DP in fp64 with autograd."""
+    g = torch.Generator().manual_seed(3)
+    B, S, T = 2, 4, 6
+    px = torch.randn(B, S, T + 1, generator=g, dtype=torch.float64)
+    py = torch.randn(B, S + 1, T, generator=g, dtype=torch.float64)
+    boundary = torch.tensor([[0, 0, 4, 6], [0, 0, 2, 5]])
+    px.requires_grad_(True)
+    py.requires_grad_(True)
+    tot = []
+    for b in range(B):
+        sb, tb, se, te = boundary[b].tolist()
+        p = {(sb, tb): torch.zeros((), dtype=torch.float64)}
+        for s in range(sb, se + 1):
+            for t in range(tb, te + 1):
+                if (s, t) == (sb, tb):
+                    continue
+                terms = []
+                if s > sb:
+                    terms.append(p[(s - 1, t)] + px[b, s - 1, t])
+                if t > tb:
+                    terms.append(p[(s, t - 1)] + py[b, s, t - 1])
+                p[(s, t)] = torch.logsumexp(torch.stack(terms), 0)
+        tot.append(p[(se, te)])
+    tot = torch.stack(tot)
+    gx, gy = torch.autograd.grad(tot.sum(), [px, py])
+    scores, (pxg, pyg) = k2.mutual_information_recursion(px.detach(), py.detach(), boundary, return_grad=True)
+    torch.testing.assert_close(scores, tot.detach(), rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(pxg, gx, rtol=1e-9, atol=1e-12)
+    torch.testing.assert_close(pyg, gy, rtol=1e-9, atol=1e-12)
+
+
+def test_prune_range_invariants():
+    am, lm, sym, Tl, Sl, boundary = _toy(B=3, T=40, S=12, V=9, seed=7)
+    _, (pxg, pyg) = k2.rnnt_loss_smoothed(lm=lm, am=am, symbols=sym, termination_symbol=0, lm_only_scale=0.0,
+                                          am_only_scale=0.0, boundary=boundary, reduction="none",
+                                          return_grad=True)
+    # occupation mass: exactly one blank per real frame
+    for b in range(3):
+        torch.testing.assert_close(pyg[b, :, :Tl[b]].sum(0), torch.ones(int(Tl[b])), rtol=1e-4, atol=1e-4)
+    for variant in ("A", "B"):
+        for R in (2, 3, 5):
+            r = k2.get_rnnt_prune_ranges(pxg, pyg, boundary, R, variant=variant)
+            s0 = r[:, :, 0]
+            assert (s0[:, 0] == 0).all()
+            d = s0[:, 1:] - s0[:, :-1]
+            assert (d >= 0).all() and (d <= R - 1).all()
+            for b in range(3):
+                assert s0[b, int(Tl[b]) - 1] == max(int(Sl[b]) - R + 1, 0)
+
+
+def test_monotonic_lower_bound():
+    x = torch.tensor([[3, 1, 4, 1, 5, 9, 2, 6]])
+    assert k2.monotonic_lower_bound(x).tolist() == [[1, 1, 1, 1, 2, 2, 2, 6]]
