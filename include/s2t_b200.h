@@ -45,16 +45,20 @@ extern "C" {
 int s2t_abi_version(void);
 const char* s2t_last_error(void);
 
+/* Bytes of lattice-DP scratch ("alpha_ws" below) for a lattice whose columns hold `slots`
+ * symbol positions: slots = S+1 for the k2 layout, R for (B,T,R) band / full layouts. */
+size_t s2t_lattice_workspace_bytes(int B, int S, int T, int slots);
+
 /* ---------------------------------------------------------------------------
  * k2.mutual_information_recursion(px, py, boundary, return_grad)
  *   reference call sites: model/joiner/joiner.py:100-110 (inside rnnt_loss_smoothed),
  *   model/loss/pruned_rnnt_loss.py:39-48 (inside rnnt_loss_pruned).
  * px (B,S,T+1), py (B,S+1,T) fp32; boundary (B,4) int64 or NULL.
- * alpha_ws: scratch (B,S+1,T+1) fp32.  scores (B).  px_grad/py_grad: occupation
+ * alpha_ws: scratch of s2t_lattice_workspace_bytes(B,S,T,S+1) bytes.  scores (B).  px_grad/py_grad: occupation
  * probabilities, same shapes as px/py, or both NULL for scores only.
  */
 int s2t_mutual_information(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
-                           float* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream);
+                           void* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream);
 
 /* ---------------------------------------------------------------------------
  * k2.rnnt_loss_smoothed(lm, am, symbols, termination_symbol, lm_only_scale,
@@ -62,7 +66,7 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
  *   reference call site: model/joiner/joiner.py:100-110.
  * am (B,T,V), lm (B,S+1,V) fp32; symbols (B,S) int64.
  * Outputs: am_max (B,T), lm_max (B,S+1), px (B,S,T+1), py (B,S+1,T),
- * nrm (B,S+1,T) [log-normalisers, kept for the backward], alpha_ws (B,S+1,T+1),
+ * nrm (B,S+1,T) [log-normalisers, kept for the backward], alpha_ws (scratch, as above),
  * scores (B) = log P(y|x) per utterance (reduction is the caller's),
  * px_grad (B,S,T+1), py_grad (B,S+1,T).
  * lm_only_scale / am_only_scale must be 0 in this ABI version (the reference's
@@ -94,12 +98,13 @@ int s2t_prune_ranges(const float* px_grad, const float* py_grad, const int64_t* 
  * Loss on materialised logits (B,T,R,V) of dtype `dtype`:
  *   ranges != NULL: k2.rnnt_loss_pruned          (model/loss/pruned_rnnt_loss.py:39-48)
  *   ranges == NULL: torchaudio rnnt_loss, R = S+1 (model/loss/rnnt_loss.py:42-44)
- * Outputs: lse, px, py, occ_px, occ_py (B,T,R) fp32; alpha_ws scratch (B,T+1,R);
+ * Outputs: lse, px, py, occ_px, occ_py (B,T,R) fp32; alpha_ws scratch of
+ * s2t_lattice_workspace_bytes(B,S,T,R) bytes;
  * scores (B) = log P(y|x).
  */
 int s2t_logits_loss_fwd(const void* logits, int dtype, const int64_t* symbols, const int64_t* ranges,
                         const int64_t* boundary, int B, int T, int S, int R, int V, int blank,
-                        float delay_penalty, float* lse, float* px, float* py, float* alpha_ws, float* scores,
+                        float delay_penalty, float* lse, float* px, float* py, void* alpha_ws, float* scores,
                         float* occ_px, float* occ_py, void* stream);
 
 /* grad (B,T,R,V), same dtype as logits, overwritten with d loss / d logits given
@@ -128,7 +133,7 @@ int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_
                         const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
                         const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
                         int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
-                        float* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream);
+                        void* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream);
 
 /* d_am (B,T,V), d_lm (B,S+1,V), dW1, db1, dW2, db2 are overwritten. */
 int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols,

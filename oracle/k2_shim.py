@@ -423,7 +423,12 @@ def get_rnnt_prune_ranges(
                              device=py_grad.device)
         tot = torch.cat((px_grad, px_pad), dim=1) + torch.cat(
             (py_grad, py_pad), dim=2)  # (B, S1, T1)
-        cs = torch.cumsum(torch.cat((px_pad, tot), dim=1), dim=1)  # (B,S1+1,T1)
+        # sequential cumsum over s in the working dtype (torch.cumsum accumulates
+        # fp32 in double on CPU and as a tree on GPU; the oracle fixes the order)
+        cs_rows = [torch.zeros((B, T1), dtype=tot.dtype, device=tot.device)]
+        for j in range(S1):
+            cs_rows.append(cs_rows[-1] + tot[:, j, :])
+        cs = torch.stack(cs_rows, dim=1)  # (B,S1+1,T1)
         diff = cs[:, s_range:, :] - cs[:, :S1 + 1 - s_range, :]
         s_begin = torch.argmax(diff[:, :, :T], dim=1)  # (B, T)
     else:

@@ -30,6 +30,7 @@ F = c_float
 _SIGNATURES = {
     "s2t_abi_version": (c_int, []),
     "s2t_last_error": (ctypes.c_char_p, []),
+    "s2t_lattice_workspace_bytes": (c_size_t, [I, I, I, I]),
     "s2t_mutual_information": (c_int, [P, P, P, I, I, I, P, P, P, P, P]),
     "s2t_simple_loss_fwd": (c_int, [P, P, P, P, I, I, I, I, I, F, F, P, P, P, P, P, P, P, P, P, P]),
     "s2t_simple_loss_bwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, P]),

@@ -45,7 +45,7 @@ int logits_grad(const void* logits, int dtype, const int64_t* sym, const int64_t
                 int blank, float clamp, void* grad, cudaStream_t stream);
 
 static LatticeView simple_view(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
-                               float* alpha) {
+                               void* ws) {
   LatticeView v{};
   v.px = px;
   v.py = py;
@@ -57,12 +57,13 @@ static LatticeView simple_view(const float* px, const float* py, const int64_t* 
   v.py_rs = T;
   v.rx = S;
   v.ry = S + 1;
+  v.px_at_tb = true;
   v.ranges = nullptr;
   v.boundary = boundary;
   v.B = B;
   v.S = S;
   v.T = T;
-  v.alpha = alpha;
+  lattice_carve_workspace(v, ws, S + 1);
   v.a_bs = (int64_t)(S + 1) * (T + 1);
   v.a_ts = 1;
   v.a_rs = T + 1;
@@ -70,7 +71,7 @@ static LatticeView simple_view(const float* px, const float* py, const int64_t* 
 }
 
 static LatticeView band_view(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary,
-                             int B, int S, int T, int R, float* alpha) {
+                             int B, int S, int T, int R, void* ws) {
   LatticeView v{};
   v.px = px;
   v.py = py;
@@ -78,6 +79,7 @@ static LatticeView band_view(const float* px, const float* py, const int64_t* ra
   v.px_ts = v.py_ts = R;
   v.px_rs = v.py_rs = 1;
   v.rx = v.ry = R;
+  v.px_at_tb = false;
   v.ranges = ranges;
   v.rg_bs = (int64_t)T * R;
   v.rg_ts = R;
@@ -85,7 +87,7 @@ static LatticeView band_view(const float* px, const float* py, const int64_t* ra
   v.B = B;
   v.S = S;
   v.T = T;
-  v.alpha = alpha;
+  lattice_carve_workspace(v, ws, R);
   v.a_bs = (int64_t)(T + 1) * R;
   v.a_ts = R;
   v.a_rs = 1;
@@ -93,7 +95,7 @@ static LatticeView band_view(const float* px, const float* py, const int64_t* ra
 }
 
 static int band_dp(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary, int B, int S,
-                   int T, int R, float* alpha, float* scores, float* occ_px, float* occ_py, cudaStream_t st) {
+                   int T, int R, void* alpha, float* scores, float* occ_px, float* occ_py, cudaStream_t st) {
   LatticeView v = band_view(px, py, ranges, boundary, B, S, T, R, alpha);
   size_t n = (size_t)B * T * R * sizeof(float);
   cudaMemsetAsync(occ_px, 0, n, st);
@@ -123,7 +125,7 @@ int s2t_abi_version(void) { return S2T_ABI_VERSION; }
 const char* s2t_last_error(void) { return g_error; }
 
 int s2t_mutual_information(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
-                           float* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream) {
+                           void* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(B >= 0 && S >= 0 && T >= 0, "mutual_information: negative dimension");
   LatticeView v = simple_view(px, py, boundary, B, S, T, alpha_ws);
@@ -164,7 +166,7 @@ int s2t_prune_ranges(const float* px_grad, const float* py_grad, const int64_t* 
 
 int s2t_logits_loss_fwd(const void* logits, int dtype, const int64_t* symbols, const int64_t* ranges,
                         const int64_t* boundary, int B, int T, int S, int R, int V, int blank,
-                        float delay_penalty, float* lse, float* px, float* py, float* alpha_ws, float* scores,
+                        float delay_penalty, float* lse, float* px, float* py, void* alpha_ws, float* scores,
                         float* occ_px, float* occ_py, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(ranges != nullptr || R == S + 1, "logits_loss: unpruned logits need R == S+1 (R=%d, S=%d)", R, S);
@@ -181,6 +183,10 @@ int s2t_logits_loss_bwd(const void* logits, int dtype, const int64_t* symbols, c
                      grad, (cudaStream_t)stream);
 }
 
+size_t s2t_lattice_workspace_bytes(int B, int S, int T, int slots) {
+  return lattice_workspace_bytes(B, S, T, slots);
+}
+
 size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {
   (void)mode;
   return joiner_simt_workspace_bytes((int64_t)B * T * R, V, I, nullptr);
@@ -190,7 +196,7 @@ int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_
                         const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
                         const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
                         int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
-                        float* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream) {
+                        void* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT, "joiner_loss_fwd: mode %d not built", mode);
   S2T_REQUIRE(ranges != nullptr || R == S + 1, "joiner_loss: unpruned joiner needs R == S+1 (R=%d, S=%d)", R, S);

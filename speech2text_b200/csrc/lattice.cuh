@@ -24,14 +24,22 @@ struct LatticeView {
   int64_t px_bs, px_ts, px_rs;
   int64_t py_bs, py_ts, py_rs;
   int rx, ry;
+  bool px_at_tb;  // k2 layout: px has T+1 columns and the column t == T_b is read (k2 stores -inf there);
+                  // band layouts: false, no symbol may be emitted after the last frame
   const int64_t* ranges;  // (B, T, R) or nullptr
   int64_t rg_bs, rg_ts;
   const int64_t* boundary;  // (B, 4) [0, 0, S_b, T_b] or nullptr
   int B, S, T;
-  // alpha scratch
-  float* alpha;
+  // scratch, carved from one workspace by lattice_carve_workspace()
+  float* alpha;  // alpha relative to aoff[diagonal]
   int64_t a_bs, a_ts, a_rs;
+  double* aoff;    // (B, S+T+2) fp64 offset of every alpha diagonal
+  double* logp_d;  // (B) log P(y|x) in fp64
 };
+
+// bytes of DP scratch for alpha with `slots` symbol positions per column (T+1 columns)
+size_t lattice_workspace_bytes(int B, int S, int T, int slots);
+void lattice_carve_workspace(LatticeView& v, void* ws, int slots);
 
 // Runs alpha, then beta + occupation.  occ_px / occ_py use the px / py strides
 // and must be zero-filled by the caller (cells outside the live region are not

@@ -26,6 +26,10 @@ def _i64c(t: Tensor) -> Tensor:
     return t.to(torch.int64).contiguous()
 
 
+def _dp_scratch(B: int, S: int, T: int, slots: int, device) -> Tensor:
+    return torch.empty((lib().s2t_lattice_workspace_bytes(B, S, T, slots),), dtype=torch.uint8, device=device)
+
+
 def make_boundary(target_lengths: Tensor, encoder_out_lengths: Tensor, device) -> Tensor:
     """/root/reference/model/joiner/joiner.py:89-93 -- rows [0, 0, S_b, T_b], int64.
     Lengths may arrive as float tensors (joiner_test.py:56-58)."""
@@ -49,7 +53,7 @@ def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tens
     assert T1 == T + 1 and py.shape == (B, S + 1, T), (px.shape, py.shape)
     if boundary is not None:
         boundary = _i64c(boundary)
-    alpha = torch.empty((B, S + 1, T + 1), dtype=torch.float32, device=px.device)
+    alpha = _dp_scratch(B, S, T, S + 1, px.device)
     scores = torch.empty((B,), dtype=torch.float32, device=px.device)
     px_grad = torch.empty_like(px) if return_grad else None
     py_grad = torch.empty_like(py) if return_grad else None
@@ -78,7 +82,7 @@ class _SimpleLoss(torch.autograd.Function):
         px = torch.empty((B, S, T + 1), **f32)
         py = torch.empty((B, S + 1, T), **f32)
         nrm = torch.empty((B, S + 1, T), **f32)
-        alpha = torch.empty((B, S + 1, T + 1), **f32)
+        alpha = _dp_scratch(B, S, T, S + 1, dev)
         scores = torch.empty((B,), **f32)
         px_grad = torch.empty((B, S, T + 1), **f32)
         py_grad = torch.empty((B, S + 1, T), **f32)
@@ -178,7 +182,7 @@ class _LogitsLoss(torch.autograd.Function):
         py = torch.empty((B, T, R), **f32)
         occ_px = torch.empty((B, T, R), **f32)
         occ_py = torch.empty((B, T, R), **f32)
-        alpha = torch.empty((B, T + 1, R), **f32)
+        alpha = _dp_scratch(B, S, T, R, dev)
         scores = torch.empty((B,), **f32)
         check(lib().s2t_logits_loss_fwd(ptr(logits), _lib.dtype_code(logits.dtype), ptr(symbols), ptr(ranges),
                                         ptr(boundary), B, T, S, R, V, blank, float(delay_penalty), ptr(lse),
@@ -242,7 +246,7 @@ class _JoinerLoss(torch.autograd.Function):
         py = torch.empty((B, T, R), **f32)
         occ_px = torch.empty((B, T, R), **f32)
         occ_py = torch.empty((B, T, R), **f32)
-        alpha = torch.empty((B, T + 1, R), **f32)
+        alpha = _dp_scratch(B, S, T, R, dev)
         scores = torch.empty((B,), **f32)
         check(lib().s2t_joiner_loss_fwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(ranges), ptr(boundary),
                                         ptr(W1), ptr(b1), ptr(W2), ptr(b2), B, T, S, R, V, I, act, blank,

@@ -1,0 +1,313 @@
+"""GPU parity tests: every call goes through the C ABI of libs2t_b200.so (via
+speech2text_b200.functional / the Joiner + Loss modules) and is compared with
+the CPU oracle on the same seeded inputs and with the golden vectors minted
+from the reference.
+
+Tolerances (north_star): fp32 relative 1e-5 on the loss, 1e-4 on gradients;
+prune ranges bit-exact given identical occupation inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import check_summary, load_golden, rel_err
+from oracle import k2_shim as k2
+from oracle import reference_port as port
+from oracle.cases import CASES, make_case
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand_lattice(B, S, T, seed, lens=None):
+    g = torch.Generator().manual_seed(seed)
+    px = torch.randn(B, S, T + 1, generator=g) - 1.0
+    py = torch.randn(B, S + 1, T, generator=g) - 1.0
+    boundary = torch.zeros(B, 4, dtype=torch.int64)
+    if lens is None:
+        boundary[:, 2] = torch.randint(1, S + 1, (B,), generator=g)
+        boundary[:, 3] = torch.randint(1, T + 1, (B,), generator=g)
+        boundary[0, 2], boundary[0, 3] = S, T
+    else:
+        boundary[:, 2] = torch.tensor(lens[0])
+        boundary[:, 3] = torch.tensor(lens[1])
+    return px, py, boundary
+
+
+@pytest.mark.parametrize("B,S,T", [(1, 1, 1), (3, 4, 6), (5, 31, 33), (4, 40, 150), (2, 123, 327), (2, 300, 64)])
+def test_mutual_information_matches_oracle(B, S, T):
+    from speech2text_b200 import functional as F2
+    px, py, boundary = _rand_lattice(B, S, T, seed=B * 1000 + S * 10 + T)
+    # k2 semantics: no symbol after the last frame
+    px = k2.fix_for_boundary(px, boundary)
+    # truth: the oracle recursion in fp64 on the same fp32 inputs (the fp32 oracle, like k2's fp32
+    # CPU kernel, is itself only good to a few ulp(|logP|) here)
+    s_ref, (gx_ref, gy_ref) = k2.mutual_information_recursion(px.double(), py.double(), boundary,
+                                                              return_grad=True)
+    s32, (gx32, gy32) = k2.mutual_information_recursion(px, py, boundary, return_grad=True)
+    s, (gx, gy) = F2.mutual_information_recursion(px.to(_dev()), py.to(_dev()), boundary.to(_dev()),
+                                                  return_grad=True)
+    torch.cuda.synchronize()
+    assert rel_err(s, s_ref) < 1e-6
+    assert rel_err(s, s32) < LOSS_RTOL
+    assert (gx.cpu() - gx_ref).abs().max() < 2e-5  # occupation probabilities live in [0, 1]
+    assert (gy.cpu() - gy_ref).abs().max() < 2e-5
+    assert (gx.cpu() - gx32).abs().max() < 2e-5 + 2 * (gx32 - gx_ref).abs().max()
+    assert (gy.cpu() - gy32).abs().max() < 2e-5 + 2 * (gy32 - gy_ref).abs().max()
+    # without a boundary tensor
+    s2 = F2.mutual_information_recursion(px.to(_dev()), py.to(_dev()), None)
+    s2_ref = k2.mutual_information_recursion(px, py, None)
+    assert rel_err(s2, s2_ref) < LOSS_RTOL
+
+
+def _toy(B, T, S, V, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    am = torch.randn(B, T, V, generator=g) * scale
+    lm = torch.randn(B, S + 1, V, generator=g) * scale
+    sym = torch.randint(1, V, (B, S), generator=g)
+    boundary = torch.zeros(B, 4, dtype=torch.int64)
+    Tl = torch.randint(max(S, T // 2), T + 1, (B,), generator=g)
+    Sl = torch.randint(1, S + 1, (B,), generator=g)
+    Tl[0], Sl[0] = T, S
+    Sl = torch.minimum(Sl, Tl)
+    for b in range(B):
+        sym[b, Sl[b]:] = 0
+    boundary[:, 2], boundary[:, 3] = Sl, Tl
+    return am, lm, sym, boundary
+
+
+@pytest.mark.parametrize("B,T,S,V", [(2, 9, 3, 5), (3, 50, 17, 33), (4, 200, 15, 128), (2, 130, 129, 257)])
+def test_simple_loss_and_grads_match_oracle(B, T, S, V):
+    from speech2text_b200 import functional as F2
+    am, lm, sym, boundary = _toy(B, T, S, V, seed=T + S + V)
+    # truth = the oracle in fp64 on the same fp32 inputs
+    am_r, lm_r = am.double().requires_grad_(True), lm.double().requires_grad_(True)
+    loss_r, (gx_r, gy_r) = k2.rnnt_loss_smoothed(lm=lm_r, am=am_r, symbols=sym, termination_symbol=0,
+                                                 lm_only_scale=0.0, am_only_scale=0.0, boundary=boundary,
+                                                 reduction="none", return_grad=True)
+    w = torch.linspace(0.5, 1.5, B)
+    (loss_r * w.double()).sum().backward()
+
+    am_g, lm_g = am.to(_dev()).requires_grad_(True), lm.to(_dev()).requires_grad_(True)
+    loss_g, (gx, gy) = F2.rnnt_loss_smoothed(lm=lm_g, am=am_g, symbols=sym.to(_dev()), termination_symbol=0,
+                                             boundary=boundary.to(_dev()), reduction="none", return_grad=True)
+    (loss_g * w.to(_dev())).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(loss_g, loss_r) < LOSS_RTOL
+    # px / py themselves are fp32 here (as in k2), so the occupations carry their rounding
+    assert (gx.cpu() - gx_r).abs().max() < 1e-4
+    assert (gy.cpu() - gy_r).abs().max() < 1e-4
+    assert rel_err(am_g.grad, am_r.grad) < GRAD_RTOL
+    assert rel_err(lm_g.grad, lm_r.grad) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+@pytest.mark.parametrize("B,T,S,V,R", [(3, 40, 12, 9, 2), (3, 40, 12, 9, 5), (4, 200, 15, 64, 5),
+                                       (2, 327, 123, 32, 5), (2, 30, 4, 8, 9), (2, 1100, 40, 8, 3)])
+def test_prune_ranges_bit_exact(variant, B, T, S, V, R):
+    """Identical occupation inputs (computed once by the oracle) -> identical int64 ranges."""
+    from speech2text_b200 import functional as F2
+    am, lm, sym, boundary = _toy(B, T, S, V, seed=R * 7 + T)
+    _, (gx, gy) = k2.rnnt_loss_smoothed(lm=lm, am=am, symbols=sym, termination_symbol=0, lm_only_scale=0.0,
+                                        am_only_scale=0.0, boundary=boundary, reduction="none",
+                                        return_grad=True)
+    ref = k2.get_rnnt_prune_ranges(gx, gy, boundary, R, variant=variant)
+    got = F2.get_rnnt_prune_ranges(gx.to(_dev()), gy.to(_dev()), boundary.to(_dev()), R, variant=variant)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.int64 and got.shape == ref.shape
+    assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_pruned_loss_on_materialised_logits(dtype):
+    from speech2text_b200 import functional as F2
+    B, T, S, V, R = 3, 60, 14, 37, 5
+    am, lm, sym, boundary = _toy(B, T, S, V, seed=11)
+    _, (gx, gy) = k2.rnnt_loss_smoothed(lm=lm, am=am, symbols=sym, termination_symbol=0, lm_only_scale=0.0,
+                                        am_only_scale=0.0, boundary=boundary, reduction="none",
+                                        return_grad=True)
+    ranges = k2.get_rnnt_prune_ranges(gx, gy, boundary, R)
+    g = torch.Generator().manual_seed(5)
+    logits = (torch.randn(B, T, R, V, generator=g) * 2).to(dtype)
+    lr = logits.float().clone().requires_grad_(True)
+    loss_r = k2.rnnt_loss_pruned(lr, sym, ranges, 0, boundary, delay_penalty=0.02, reduction="none")
+    w = torch.linspace(0.5, 1.5, B)
+    (loss_r * w).sum().backward()
+    lg = logits.to(_dev()).requires_grad_(True)
+    scores = F2.logits_scores(lg, sym.to(_dev()), ranges.to(_dev()), boundary.to(_dev()), blank=0,
+                              delay_penalty=0.02)
+    ((-scores) * w.to(_dev())).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(-scores, loss_r) < LOSS_RTOL
+    gtol = GRAD_RTOL if dtype == torch.float32 else 1e-2  # grad is rounded to the logits dtype
+    assert rel_err(lg.grad.float(), lr.grad) < gtol
+    assert lg.grad.dtype == dtype
+
+
+@pytest.mark.parametrize("clamp", [-1.0, 0.05])
+def test_vanilla_loss_on_materialised_logits_matches_torchaudio(clamp):
+    import torchaudio
+    from speech2text_b200.loss.rnnt_loss import RnntLoss, RnntLossConfig
+    B, T, U, V = 3, 40, 9, 21
+    g = torch.Generator().manual_seed(2)
+    logits = torch.randn(B, T, U + 1, V, generator=g)
+    tgt = torch.randint(1, V, (B, U), generator=g)
+    Tl = torch.tensor([40, 33, 12])
+    Ul = torch.tensor([9, 4, 7])
+    lr = logits.clone().requires_grad_(True)
+    ref = torchaudio.functional.rnnt_loss(lr, tgt.int(), Tl.int(), Ul.int(), blank=0, clamp=clamp,
+                                          reduction="mean")
+    ref.backward()
+    mod = RnntLoss(RnntLossConfig(blank_label=0, clamp=clamp, reduction="mean"))
+    lg = logits.to(_dev()).requires_grad_(True)
+    out = mod(logits=lg, targets=tgt.to(_dev()), logits_length=Tl.to(_dev()), targets_length=Ul.to(_dev()))
+    out.backward()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < LOSS_RTOL
+    assert rel_err(lg.grad, lr.grad) < GRAD_RTOL
+
+
+def _run_modules(name, fused: bool, monkeypatch, dtype=torch.float32):
+    """One fwd+bwd through the drop-in modules exactly as rnnt_task.py:469-514 strings them."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    monkeypatch.setenv("S2T_B200_FUSED", "1" if fused else "0")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", "fp32")
+    spec, case = CASES[name], make_case(name)
+    dev = _dev()
+    joiner = Joiner(JoinerConfig(**spec["joiner"]))
+    joiner.load_state_dict({k: torch.from_numpy(v) for k, v in case["weights"].items()})
+    joiner = joiner.to(dev)
+    enc = torch.from_numpy(case["encoder_out"]).to(dev).requires_grad_(True)
+    pred = torch.from_numpy(case["predict_out"]).to(dev).requires_grad_(True)
+    # lengths arrive as float tensors in the reference's tests (joiner_test.py:56-58)
+    enc_len = torch.from_numpy(case["encoder_out_lengths"]).float().to(dev)
+    tgt_len = torch.from_numpy(case["target_lengths"]).float().to(dev)
+    tgt = torch.from_numpy(case["target"]).to(dev)
+    out = {}
+    if spec["joiner"].get("prune_range", 5) > 0:
+        loss_mod = Loss({"model": "Pruned_Rnnt", "config": spec["loss"]})
+        logits, boundary, ranges, simple = joiner(enc, enc_len, pred, tgt_len, tgt)
+        pruned = loss_mod({"logits": logits, "logits_length": enc_len, "targets": tgt,
+                           "targets_length": tgt_len, "boundary": boundary, "ranges": ranges})
+        total = (spec["simple_loss_scale"] * simple + spec["pruned_loss_scale"] * pruned).mean()
+        out.update(simple_loss=simple, pruned_loss=pruned, ranges=ranges, boundary=boundary, logits=logits)
+    else:
+        loss_mod = Loss({"model": "Rnnt", "config": spec["loss"]})
+        logits, boundary, ranges, simple = joiner(enc, enc_len, pred, tgt_len)
+        assert boundary is None and ranges is None and simple is None
+        loss = loss_mod({"logits": logits, "logits_length": enc_len.long(), "targets": tgt,
+                         "targets_length": tgt_len.long()})
+        total = loss.mean()
+        out.update(rnnt_loss=loss, logits=logits)
+    total.backward()
+    torch.cuda.synchronize()
+    out["total_loss"] = total
+    out["d_encoder_out"], out["d_predict_out"] = enc.grad, pred.grad
+    for k, p in joiner.named_parameters():
+        out["d" + k] = p.grad
+    return out
+
+
+SUPPORTED = [n for n in CASES if CASES[n]["joiner"].get("lm_scale", 0.0) == 0.0]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", SUPPORTED)
+def test_training_step_matches_reference_goldens(name, fused, monkeypatch):
+    """Full hot path through the reference-facing modules vs the golden vectors minted by
+    running the reference verbatim (oracle/make_golden.py)."""
+    gold = load_golden(name, "f32")
+    out = _run_modules(name, fused, monkeypatch)
+    pruned = CASES[name]["joiner"].get("prune_range", 5) > 0
+    assert tuple(out["logits"].shape) == tuple(gold["logits_shape"])
+    if pruned:
+        assert np.array_equal(out["boundary"].cpu().numpy(), gold["boundary"])
+        mism = (out["ranges"].cpu().numpy() != gold["ranges"]).mean()
+        assert mism == 0.0, f"{name}: {mism:.4%} of range entries differ from the reference run"
+        np.testing.assert_allclose(out["simple_loss"].item(), gold["simple_loss"], rtol=LOSS_RTOL)
+        np.testing.assert_allclose(out["pruned_loss"].detach().cpu().double().numpy(), gold["pruned_loss"],
+                                   rtol=LOSS_RTOL)
+    else:
+        np.testing.assert_allclose(out["rnnt_loss"].item(), gold["rnnt_loss"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(out["total_loss"].item(), gold["total_loss"], rtol=LOSS_RTOL)
+    for key in [k[:-len(".stride")] for k in gold if k.endswith(".stride") and k.startswith("d")]:
+        check_summary(out[key], gold, key, rtol=GRAD_RTOL, what=name)
+
+
+@pytest.mark.parametrize("name", ["joiner_test", "tanh_smoothed", "range_clamped"])
+def test_lazy_logits_materialize_matches_port(name, monkeypatch):
+    """The logits the fused path never stores, written out by the debug entry point."""
+    spec, case = CASES[name], make_case(name)
+    if spec["joiner"].get("lm_scale", 0.0) != 0.0:
+        spec = dict(spec, joiner=dict(spec["joiner"], lm_scale=0.0, am_scale=0.0))
+    from speech2text_b200.joiner import Joiner, JoinerConfig
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    joiner = Joiner(JoinerConfig(**spec["joiner"]))
+    joiner.load_state_dict({k: torch.from_numpy(v) for k, v in case["weights"].items()})
+    joiner = joiner.to(_dev())
+    args = [torch.from_numpy(case[k]).to(_dev()) for k in
+            ("encoder_out", "encoder_out_lengths", "predict_out", "target_lengths", "target")]
+    handle, boundary, ranges, simple = joiner(*args)
+    w = {k: torch.from_numpy(v) for k, v in case["weights"].items()}
+    ref_logits, _, ref_ranges, ref_simple = port.joiner_forward(
+        w, spec["joiner"], *[torch.from_numpy(case[k]) for k in
+                             ("encoder_out", "encoder_out_lengths", "predict_out", "target_lengths", "target")])
+    assert torch.equal(ranges.cpu(), ref_ranges)
+    assert tuple(handle.shape) == tuple(ref_logits.shape)
+    got = handle.materialize()
+    torch.cuda.synchronize()
+    assert rel_err(got, ref_logits) < 1e-5
+    assert rel_err(simple, ref_simple) < LOSS_RTOL
+
+
+def test_smoothing_scales_raise_loudly(monkeypatch):
+    """Non-zero lm_scale / am_scale are not built in ABI v1: the call must fail, not fall back."""
+    from speech2text_b200._lib import S2TError
+    from speech2text_b200.joiner import Joiner, JoinerConfig
+    spec, case = CASES["tanh_smoothed"], make_case("tanh_smoothed")
+    joiner = Joiner(JoinerConfig(**spec["joiner"])).to(_dev())
+    args = [torch.from_numpy(case[k]).to(_dev()) for k in
+            ("encoder_out", "encoder_out_lengths", "predict_out", "target_lengths", "target")]
+    with pytest.raises(S2TError):
+        joiner(*args)
+
+
+def test_full_size_properties_c3():
+    """BASELINE config 3 size (B=64, T=400, U=100, V=500): size-independent properties of the
+    occupation probabilities and ranges (the oracle would take minutes here)."""
+    from speech2text_b200 import functional as F2
+    B, T, S, V, R = 64, 400, 100, 500, 5
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    am = torch.randn(B, T, V, generator=g, device="cuda") * 0.5
+    lm = torch.randn(B, S + 1, V, generator=g, device="cuda") * 0.5
+    sym = torch.randint(1, V - 1, (B, S), generator=g, device="cuda")
+    Tl = torch.randint(int(0.6 * T), T + 1, (B,), generator=g, device="cuda")
+    Sl = torch.clamp((Tl.float() * S / T * 0.9).long(), 1, S)
+    Tl[0], Sl[0] = T, S
+    boundary = torch.zeros(B, 4, dtype=torch.int64, device="cuda")
+    boundary[:, 2], boundary[:, 3] = Sl, Tl
+    loss, (gx, gy) = F2.rnnt_loss_smoothed(lm=lm, am=am, symbols=sym, termination_symbol=0, boundary=boundary,
+                                           reduction="none", return_grad=True)
+    ranges = F2.get_rnnt_prune_ranges(gx, gy, boundary, R)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and (loss > 0).all()
+    t_idx = torch.arange(T, device="cuda")[None, :]
+    live = (t_idx < Tl[:, None]).float()
+    # exactly one blank per live frame, S_b symbols per utterance
+    assert ((gy.sum(1) - live).abs().max() < 1e-3)
+    assert ((gx.sum((1, 2)) - Sl.float()).abs().max() < 1e-2)
+    assert (gx >= 0).all() and (gx <= 1 + 1e-4).all() and (gy >= 0).all() and (gy <= 1 + 1e-4).all()
+    s0 = ranges[:, :, 0]
+    assert (s0[:, 0] == 0).all()
+    d = s0[:, 1:] - s0[:, :-1]
+    assert (d >= 0).all() and (d <= R - 1).all()
+    last = torch.gather(s0, 1, (Tl - 1)[:, None]).squeeze(1)
+    assert torch.equal(last, torch.clamp(Sl - R + 1, min=0))
+    assert torch.equal(ranges[:, :, 1:] - ranges[:, :, :-1], torch.ones_like(ranges[:, :, 1:]))
