@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- pruned RNN-T loss forward+backward throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--mode fp32|bf16]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+One "step" = one pass of the hot path over one synthetic batch:
+(encoder_out, predict_out, lengths, labels) -> joiner projections -> simple loss +
+occupation probs -> prune ranges -> fused pruned joiner + loss -> backward to
+d_encoder_out, d_predict_out and all joiner weight gradients, loss = 0.5 simple + 0.5 pruned
+(/root/reference/task_factory/rnnt_task.py:469-514).  Under torchrun each rank owns its own
+utterances (weak scaling) and the step ends with ONE all-reduce of the flat joiner weight
+gradient and one of the scalar losses.
+
+Prints ONE JSON line (rank 0).  `value` = utterances/s with inputs resident in HBM; `e2e` =
+the same metric through the public module API with inputs in pinned HOST memory (H2D of the
+step's inputs and D2H of the losses inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "pruned RNN-T loss fwd+bwd utterances/sec"
+
+# BASELINE.json configs: the metric is quoted at 1/2/4/8 B200 on config 3.
+WORKLOADS = {
+    "c1": dict(B=4, T=327, U=123, V=128, D=256, R=5, I=0, act="relu",
+               desc="zipformer_stateless_pruned_rnnt.yaml joiner, sample_data-shaped lengths"),
+    "c3": dict(B=64, T=400, U=100, V=500, D=512, R=5, I=256, act="tanh",
+               desc="pruned RNN-T prune_range=5, synthetic B=64 T=400 U=100 V=500 D=512"),
+    "c5": dict(B=256, T=1000, U=250, V=5000, D=1024, R=5, I=256, act="tanh",
+               desc="large-vocab pruned RNN-T V=5000 D=1024 prune_range=5, B=256/GPU"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm=p["hbm_gbs"], tc_burst=p["bf16_tflops"], tc_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic inputs
+# ---------------------------------------------------------------------------------------------
+def make_batch(cfg, seed: int):
+    """Host tensors.  Longest item full length, others T_b ~ U[0.6T, T], S_b ~ T_b*U/T*U[0.8,1]."""
+    g = torch.Generator().manual_seed(seed)
+    B, T, U, V, D = cfg["B"], cfg["T"], cfg["U"], cfg["V"], cfg["D"]
+    enc = torch.randn(B, T, D, generator=g) * 0.5
+    pred = torch.randn(B, U + 1, D, generator=g) * 0.5
+    t_len = torch.randint(int(0.6 * T), T + 1, (B,), generator=g)
+    frac = 0.8 + 0.2 * torch.rand(B, generator=g)
+    s_len = torch.clamp(torch.round(t_len.float() * U / T * frac).long(), 1, U)
+    t_len[0], s_len[0] = T, U
+    s_len = torch.minimum(s_len, t_len)
+    labels = torch.randint(1, V - 1, (B, U), generator=g)
+    for b in range(B):
+        labels[b, s_len[b]:] = 0  # pad_sequence(padding_value=0), dataset/utils.py:189-191
+    return dict(enc=enc, pred=pred, t_len=t_len, s_len=s_len, labels=labels)
+
+
+def build_modules(cfg, device, mode: str):
+    from speech2text_b200 import Joiner, JoinerConfig, Loss
+    os.environ["S2T_B200_FUSED"] = "1"
+    os.environ["S2T_B200_JOINER_MODE"] = mode
+    torch.manual_seed(1234)  # build_task.py:49
+    joiner = Joiner(JoinerConfig(input_dim=cfg["D"], output_dim=cfg["V"], inner_dim=max(cfg["I"], 1),
+                                 activation=cfg["act"], prune_range=cfg["R"],
+                                 use_out_project=cfg["I"] > 0)).to(device)
+    loss = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
+    return joiner, loss
+
+
+def hot_path_step(joiner, loss_mod, enc, t_len, pred, s_len, labels):
+    """rnnt_task.py:469-499 through the reference-facing module API."""
+    logits, boundary, ranges, simple = joiner(enc, t_len, pred, s_len, labels)
+    pruned = loss_mod({"logits": logits, "logits_length": t_len, "targets": labels, "targets_length": s_len,
+                       "boundary": boundary, "ranges": ranges})
+    total = 0.5 * simple + 0.5 * pruned
+    total.backward()
+    return total, simple, pruned
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work of each kernel (per launch group), for the roofline of the dominant one
+# ---------------------------------------------------------------------------------------------
+def kernel_work(cfg):
+    B, T, U, V, D, R, I = (cfg[k] for k in ("B", "T", "U", "V", "D", "R", "I"))
+    M = B * T * R
+    S1 = U + 1
+    gemm = 2.0 * M * V * max(I, 1)
+    simple = 2.0 * B * S1 * T * V
+    lat_cells = B * (S1 * (T + 1))
+    band_cells = B * T * R
+    w = {
+        # name: (bound, algorithmic flops or bytes per launch)
+        "joiner_hidden_gemm": ("tensor", gemm), "joiner_logits_gemm": ("tensor", gemm),
+        "joiner_dhidden_gemm": ("tensor", gemm), "joiner_dW2_gemm": ("tensor", gemm),
+        "joiner_dW1_gemm": ("tensor", gemm), "joiner_djoint_gemm": ("tensor", gemm),
+        "simple_normaliser_gemm": ("tensor", simple), "simple_d_am_gemm": ("tensor", simple),
+        "simple_d_lm_gemm": ("tensor", simple),
+        "lse_gather_kernel": ("hbm", M * V * 4.0), "logits_grad_kernel": ("hbm", 2.0 * M * V * 4),
+        "joint_act_kernel": ("hbm", M * V * 4.0 * 3), "joint_grad_kernel": ("hbm", M * V * 4.0 * 5),
+        # simple lattice: alpha reads px,py, writes alpha; beta reads px,py,alpha, writes 2 occupations
+        "lattice_alpha_kernel": ("hbm", 12.0 * (lat_cells + band_cells) / 2),
+        "lattice_beta_kernel": ("hbm", 20.0 * (lat_cells + band_cells) / 2),
+        "prune_ranges_kernel": ("hbm", B * ((U * (T + 1) + S1 * T) * 4.0 + T * R * 8.0)),
+    }
+    return w
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # pragma: no cover
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # pragma: no cover
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU path (oracle port over the k2 restatement + torch CPU ops)
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None):
+    from oracle import reference_port as port
+    n = min(n_utts, cfg["B"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    jc = dict(input_dim=cfg["D"], output_dim=cfg["V"], inner_dim=max(cfg["I"], 1), activation=cfg["act"],
+              prune_range=cfg["R"], use_out_project=cfg["I"] > 0)
+    if joiner_state is None:
+        from oracle.cases import make_weights
+        import numpy as np
+        joiner_state = {k: torch.from_numpy(v) for k, v in make_weights(jc, np.random.RandomState(1234)).items()}
+    enc = batch["enc"][:n].clone()
+    pred = batch["pred"][:n].clone()
+    t_len, s_len, labels = batch["t_len"][:n].clone(), batch["s_len"][:n].clone(), batch["labels"][:n].clone()
+    # torchaudio-style constraint of the sample: keep padded shapes of the full batch
+
+    def one():
+        w = {k: v.clone().float().requires_grad_(True) for k, v in joiner_state.items()}
+        e = enc.clone().requires_grad_(True)
+        p = pred.clone().requires_grad_(True)
+        logits, boundary, ranges, simple = port.joiner_forward(w, jc, e, t_len, p, s_len, labels)
+        pruned = port.pruned_rnnt_loss(logits, labels, boundary, ranges)
+        (0.5 * simple + 0.5 * pruned).backward()
+
+    for _ in range(warmup):
+        one()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=n / sec, unit="utt/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{n} of {cfg['B']} utterances per step (same shapes/lengths as the GPU batch), "
+                       f"{steps} steps after {warmup} warm-up, {sec:.2f} s/step"), sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--mode", default=os.environ.get("S2T_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-utts", type=int, default=4, help="utterances per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"{args.workload}: {cfg['desc']}", "global_batch": cfg["B"] * world,
+              "per_gpu_batch": cfg["B"], "T": cfg["T"], "U": cfg["U"], "V": cfg["V"], "D": cfg["D"],
+              "prune_range": cfg["R"], "inner_dim": cfg["I"], "activation": cfg["act"],
+              "parallelism": f"utterance-sharded x{world}"}
+
+    # ----------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        batch = make_batch(cfg, 1234)
+        steps = max(1, min(args.steps, 3))
+        base, sec = cpu_arm(cfg, batch, args.cpu_utts, steps, min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "utt/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "utt/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ----------------------------------------------------------------------------- our arm
+    import torch.distributed as dist
+    from speech2text_b200 import _lib
+    from speech2text_b200.distributed import FlatGradBucket, reduce_scalars
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the CUDA library is missing
+
+    batch = make_batch(cfg, 1234 + rank)
+    joiner, loss_mod = build_modules(cfg, dev, args.mode)
+    bucket = FlatGradBucket(joiner.parameters())
+    d_in = {k: v.to(dev) for k, v in batch.items()}
+    enc = d_in["enc"].requires_grad_(True)
+    pred = d_in["pred"].requires_grad_(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        bucket.zero()
+        enc.grad = None
+        pred.grad = None
+        total, simple, pruned = hot_path_step(joiner, loss_mod, enc, d_in["t_len"], pred, d_in["s_len"],
+                                              d_in["labels"])
+        if world > 1:
+            bucket.all_reduce(average=True)
+            reduce_scalars([total, simple, pruned])
+        return total, simple, pruned
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    def timed(n_steps, fn):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        for s, e in evs:
+            flush.zero_()  # L2 flush, outside the timed interval
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    total_ms = timed(args.steps, step)
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+
+    # per-kernel device time, same steps again with the library's event timer on
+    _lib.profile_enable(True)
+    prof_ms = timed(args.steps, step)
+    _lib.profile_enable(False)
+    report = _lib.profile_report()
+
+    # end to end: pinned host inputs -> H2D -> public module API -> D2H of the losses
+    h_in = {k: v.pin_memory() for k, v in batch.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in h_in.values())
+    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        e = h_in["enc"].to(dev, non_blocking=True).requires_grad_(True)
+        p = h_in["pred"].to(dev, non_blocking=True).requires_grad_(True)
+        t_len = h_in["t_len"].to(dev, non_blocking=True)
+        s_len = h_in["s_len"].to(dev, non_blocking=True)
+        labels = h_in["labels"].to(dev, non_blocking=True)
+        bucket.zero()
+        total, simple, pruned = hot_path_step(joiner, loss_mod, e, t_len, p, s_len, labels)
+        if world > 1:
+            bucket.all_reduce(average=True)
+        vec = reduce_scalars([total, simple, pruned])
+        loss_host.copy_(vec, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_ms = timed(args.steps, e2e_step)
+    barrier()
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    utts = cfg["B"] * world * args.steps
+    value = utts / (total_ms / 1e3)
+    e2e_value = utts / (e2e_ms / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        work = kernel_work(cfg)
+        roof = None
+        if report:
+            top = max(report.items(), key=lambda kv: kv[1][1])
+            name, (cnt, ms) = top
+            bound, per_launch = work.get(name, ("hbm", 0.0))
+            avg_s = ms / cnt / 1e3
+            if bound == "tensor":
+                achieved = per_launch / avg_s / 1e12
+                peak, unit = pk["tc_sustained"], "TFLOP/s"
+            else:
+                achieved = per_launch / avg_s / 1e9
+                peak, unit = pk["hbm"], "GB/s"
+            roof = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak, "traffic": None, "peak_source": pk["source"],
+                    "avg_launch_ms": ms / cnt, "launches_timed": cnt,
+                    "share_of_step": ms / prof_ms,
+                    "how": "library CUDA-event timer around every launch, second pass of the same steps"}
+        kernels = {k: {"launches": c, "ms_per_step": ms / args.steps} for k, (c, ms) in
+                   sorted(report.items(), key=lambda kv: -kv[1][1])}
+        line = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16",
+                "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset, untimed)",
+                                                    joiner_mode=args.mode),
+                "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels_ms_per_step": kernels}
+        if not args.no_cpu_baseline and world == 1:
+            base, _ = cpu_arm(cfg, batch, args.cpu_utts, 2, 1,
+                              joiner_state={k: v.detach().cpu() for k, v in joiner.state_dict().items()})
+            line["cpu_baseline"] = base
+        elif not args.no_cpu_baseline:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

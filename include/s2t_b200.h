@@ -45,6 +45,14 @@ extern "C" {
 int s2t_abi_version(void);
 const char* s2t_last_error(void);
 
+/* Measurement hooks used by bench.py (no effect on results).
+ * s2t_launch_count: kernels launched by this library since load.
+ * s2t_profile_enable(1): bracket every launch with CUDA events on its stream;
+ * s2t_profile_report: wait for them, write "name\tcount\ttotal_ms\n" lines, clear. */
+long long s2t_launch_count(void);
+void s2t_profile_enable(int on);
+int s2t_profile_report(char* buf, size_t n);
+
 /* Bytes of lattice-DP scratch ("alpha_ws" below) for a lattice whose columns hold `slots`
  * symbol positions: slots = S+1 for the k2 layout, R for (B,T,R) band / full layouts. */
 size_t s2t_lattice_workspace_bytes(int B, int S, int T, int slots);

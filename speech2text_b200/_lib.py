@@ -30,6 +30,9 @@ F = c_float
 _SIGNATURES = {
     "s2t_abi_version": (c_int, []),
     "s2t_last_error": (ctypes.c_char_p, []),
+    "s2t_launch_count": (ctypes.c_longlong, []),
+    "s2t_profile_enable": (None, [I]),
+    "s2t_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "s2t_lattice_workspace_bytes": (c_size_t, [I, I, I, I]),
     "s2t_mutual_information": (c_int, [P, P, P, I, I, I, P, P, P, P, P]),
     "s2t_simple_loss_fwd": (c_int, [P, P, P, P, I, I, I, I, I, F, F, P, P, P, P, P, P, P, P, P, P]),
@@ -73,6 +76,25 @@ def lib() -> ctypes.CDLL:
             raise S2TError("libs2t_b200.so ABI version mismatch")
         _lib = handle
     return _lib
+
+
+def launch_count() -> int:
+    return int(lib().s2t_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    lib().s2t_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{kernel name: (launch groups, total device ms)} recorded since profile_enable(True)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().s2t_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def check(rc: int) -> None:

@@ -17,6 +17,21 @@ constexpr float kMinLogDiff = -15.942385152878742f;
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Counts kernel launches and, when bench.py enabled profiling, times them with CUDA events.
+class ProfScope {
+ public:
+  ProfScope(const char* name, cudaStream_t stream, int launches = 1);
+  ~ProfScope();
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+
+ private:
+  const char* name_;
+  cudaStream_t stream_;
+  cudaEvent_t start_, stop_;
+  bool on_;
+};
+
 #define S2T_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

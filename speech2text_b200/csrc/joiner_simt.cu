@@ -202,6 +202,7 @@ static int compute_chunk_logits(const JoinerProblem& p, const SimtWs& w, int64_t
     return launch_sgemm<true, true>(1, (int)rows, p.V, p.I, 1, a, b, ep, stream, "joiner_logits_gemm");
   }
   int64_t n = rows * p.V;
+  ProfScope prof("joint_act_kernel", stream);
   joint_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p.am, p.lm, w.am_off, w.lm_off, row0, rows,
                                                                      p.V, p.act, w.logits);
   return check_launch("joint_act_kernel");
@@ -212,8 +213,11 @@ int joiner_simt_forward(const JoinerProblem& p, void* workspace, float* lse, flo
   const int64_t M = (int64_t)p.B * p.T * p.R;
   if (M == 0) return 0;
   SimtWs w = carve(workspace, M, p.V, p.I);
-  row_offsets_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(p.ranges, M, p.T, p.R, p.S, p.V, w.am_off,
-                                                                       w.lm_off);
+  {
+    ProfScope prof("row_offsets_kernel", stream);
+    row_offsets_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(p.ranges, M, p.T, p.R, p.S, p.V, w.am_off,
+                                                                         w.lm_off);
+  }
   if (int rc = check_launch("row_offsets_kernel")) return rc;
   for (int64_t row0 = 0; row0 < M; row0 += w.chunk) {
     int64_t rows = (M - row0 < w.chunk) ? (M - row0) : w.chunk;
@@ -271,6 +275,7 @@ int joiner_simt_backward(const JoinerProblem& p, void* workspace, const float* l
         if (int rc = launch_sgemm<false, false>(1, p.V, p.I, (int)rows, splits, a, b, ep, stream, "joiner_dW2_gemm")) return rc;
       }
       {
+        ProfScope prof("col_sum_kernel", stream, 2);
         dim3 grid((p.V + 127) / 128, (unsigned)((rows + 255) / 256));
         col_sum_kernel<<<grid, 128, 0, stream>>>(G, rows, p.V, p.V, db2);
         dim3 grid2((p.I + 127) / 128, (unsigned)((rows + 255) / 256));
@@ -291,6 +296,7 @@ int joiner_simt_backward(const JoinerProblem& p, void* workspace, const float* l
       }
     } else {
       int64_t n = rows * p.V;
+      ProfScope prof("joint_grad_kernel", stream);
       joint_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(G, p.am, p.lm, w.am_off, w.lm_off, row0,
                                                                           rows, p.V, p.act, d_am, d_lm);
       if (int rc = check_launch("joint_grad_kernel")) return rc;

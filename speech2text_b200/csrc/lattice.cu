@@ -274,6 +274,7 @@ int launch_lattice_fwd(const LatticeView& v, float* logp, cudaStream_t stream) {
               v.S + 1);
   if (v.B == 0) return 0;
   int n = threads_for(v.S);
+  ProfScope prof("lattice_alpha_kernel", stream);
   lattice_alpha_kernel<<<v.B, n, (2 * n + 32) * sizeof(float), stream>>>(v, logp);
   return check_launch("lattice_alpha_kernel");
 }
@@ -284,6 +285,7 @@ int launch_lattice_fwd_bwd(const LatticeView& v, float* logp, float* occ_px, flo
   if (rc) return rc;
   if (v.B == 0) return 0;
   int n = threads_for(v.S);
+  ProfScope prof("lattice_beta_kernel", stream);
   lattice_beta_kernel<<<v.B, n, (2 * (n + 1) + 32) * sizeof(float), stream>>>(v, occ_px, occ_py);
   return check_launch("lattice_beta_kernel");
 }

@@ -158,6 +158,7 @@ int lse_gather_t(const void* logits, const int64_t* sym, const int64_t* ranges, 
   int64_t rows = (int64_t)B * T_ * R;
   if (rows == 0) return 0;
   const int wpb = 8;
+  ProfScope prof("lse_gather_kernel", stream);
   lse_gather_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       (const T*)logits, sym, ranges, boundary, 0, rows, T_ * R, R, V, S, blank, delay_penalty, lse, px, py);
   return check_launch("lse_gather_kernel");
@@ -170,6 +171,7 @@ int logits_grad_t(const void* logits, const int64_t* sym, const int64_t* ranges,
   int64_t rows = (int64_t)B * T_ * R;
   if (rows == 0) return 0;
   const int wpb = 8;
+  ProfScope prof("logits_grad_kernel", stream);
   logits_grad_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       (const T*)logits, sym, ranges, lse, occ_px, occ_py, coef, 0, rows, T_ * R, R, V, S, blank, clamp, (T*)grad);
   return check_launch("logits_grad_kernel");
@@ -181,6 +183,7 @@ int lse_gather_rows(const float* logits, const int64_t* sym, const int64_t* rang
                     float* lse, float* px, float* py, cudaStream_t stream) {
   if (rows == 0) return 0;
   const int wpb = 8;
+  ProfScope prof("lse_gather_kernel", stream);
   lse_gather_kernel<float><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       logits, sym, ranges, boundary, row0, rows, T * R, R, V, S, blank, delay_penalty, lse, px, py);
   return check_launch("lse_gather_kernel(rows)");
@@ -191,6 +194,7 @@ int logits_grad_rows(float* logits_inout, const int64_t* sym, const int64_t* ran
                      int T, int R, int V, int S, int blank, float clamp, cudaStream_t stream) {
   if (rows == 0) return 0;
   const int wpb = 8;
+  ProfScope prof("logits_grad_kernel", stream);
   logits_grad_kernel<float><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       logits_inout, sym, ranges, lse, occ_px, occ_py, coef, row0, rows, T * R, R, V, S, blank, clamp, logits_inout);
   return check_launch("logits_grad_kernel(rows)");

@@ -1,0 +1,84 @@
+// Launch accounting and an opt-in per-kernel CUDA-event timer for bench.py.
+//
+// Every kernel launch of the library goes through a ProfScope: it bumps the
+// launch counter (bench.py reports it as "gpu_launches") and, while profiling is
+// enabled, brackets the launch with two events on the launching stream so that
+// bench.py can attribute device time to kernels inside its own timed region
+// (no external profiler attached).
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace s2t {
+
+namespace {
+struct Entry {
+  const char* name;
+  cudaEvent_t start, stop;
+};
+std::atomic<long long> g_launches{0};
+std::atomic<bool> g_enabled{false};
+std::mutex g_mu;
+std::vector<Entry> g_entries;
+}  // namespace
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream, int launches) : name_(name), stream_(stream), on_(false) {
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (g_enabled.load(std::memory_order_relaxed)) {
+    on_ = true;
+    cudaEventCreate(&start_);
+    cudaEventCreate(&stop_);
+    cudaEventRecord(start_, stream_);
+  }
+}
+
+ProfScope::~ProfScope() {
+  if (!on_) return;
+  cudaEventRecord(stop_, stream_);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_entries.push_back(Entry{name_, start_, stop_});
+}
+
+}  // namespace s2t
+
+using namespace s2t;
+
+extern "C" {
+
+long long s2t_launch_count(void) { return g_launches.load(); }
+
+void s2t_profile_enable(int on) { g_enabled.store(on != 0); }
+
+// Waits for the recorded events, writes "name\tlaunch_groups\ttotal_ms\n" lines into buf
+// (truncated to n bytes) and clears the record.  Returns the number of distinct names.
+int s2t_profile_report(char* buf, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& e : g_entries) {
+    cudaEventSynchronize(e.stop);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.start, e.stop);
+    auto& a = agg[e.name];
+    a.first += 1;
+    a.second += ms;
+    cudaEventDestroy(e.start);
+    cudaEventDestroy(e.stop);
+  }
+  g_entries.clear();
+  size_t off = 0;
+  if (n > 0) buf[0] = 0;
+  for (auto& kv : agg) {
+    int w = snprintf(buf + off, off < n ? n - off : 0, "%s\t%d\t%.6f\n", kv.first.c_str(), kv.second.first,
+                     kv.second.second);
+    if (w < 0 || off + (size_t)w >= n) break;
+    off += (size_t)w;
+  }
+  return (int)agg.size();
+}
+
+}  // extern "C"

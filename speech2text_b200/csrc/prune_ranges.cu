@@ -135,6 +135,7 @@ int prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boun
   if (smem > 48 * 1024) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
+  ProfScope prof("prune_ranges_kernel", stream);
   kern<<<B, kThreads, smem, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
   return check_launch("prune_ranges_kernel");
 }

@@ -161,6 +161,7 @@ int launch_sgemm(int batches, int M, int N, int K, int k_splits, const AF& af, c
   if (k_splits < 1) k_splits = 1;
   dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM, batches * k_splits);
   S2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large (%u, %u)", what, grid.y, grid.z);
+  ProfScope prof(what, stream);
   sgemm_kernel<A_KCONTIG, B_KCONTIG, AF, BF, EF><<<grid, kGemmThreads, 0, stream>>>(M, N, K, k_splits, af, bf, ef);
   return check_launch(what);
 }

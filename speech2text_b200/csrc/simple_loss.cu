@@ -172,8 +172,11 @@ int simple_logprobs(const float* am, const float* lm, const int64_t* sym, const 
                     float* py, float* nrm, cudaStream_t stream) {
   const int wpb = 8;
   int64_t rows_am = (int64_t)B * T, rows_lm = (int64_t)B * (S + 1);
-  row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max);
-  row_max_kernel<<<(unsigned)((rows_lm + wpb - 1) / wpb), wpb * 32, 0, stream>>>(lm, rows_lm, V, lm_max);
+  {
+    ProfScope prof("row_max_kernel", stream, 2);
+    row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max);
+    row_max_kernel<<<(unsigned)((rows_lm + wpb - 1) / wpb), wpb * 32, 0, stream>>>(lm, rows_lm, V, lm_max);
+  }
   if (int rc = check_launch("row_max_kernel")) return rc;
   ExpRowOperand a{lm, lm_max, S + 1, V};
   ExpRowOperand bop{am, am_max, T, V};
@@ -187,8 +190,11 @@ int simple_backward(const float* am, const float* lm, const int64_t* sym, const 
                     float* d_lm, cudaStream_t stream) {
   int64_t total = (int64_t)B * (S + 1) * T;
   if (total == 0) return 0;
-  simple_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(occ_px, occ_py, nrm, am_max, lm_max,
-                                                                        coef, B, S, T, wbuf);
+  {
+    ProfScope prof("simple_w_kernel", stream);
+    simple_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(occ_px, occ_py, nrm, am_max, lm_max,
+                                                                          coef, B, S, T, wbuf);
+  }
   if (int rc = check_launch("simple_w_kernel")) return rc;
   // d_am: M = T (m = t), N = V, K = S+1
   {
@@ -205,6 +211,7 @@ int simple_backward(const float* am, const float* lm, const int64_t* sym, const 
     if (int rc = launch_sgemm<true, false>(B, S + 1, V, T, 1, a, bop, ep, stream, "simple_d_lm_gemm")) return rc;
   }
   int64_t nbt = (int64_t)B * T;
+  ProfScope prof2("simple_scatter_kernels", stream, 2);
   simple_scatter_am_kernel<<<(unsigned)((nbt + 127) / 128), 128, 0, stream>>>(occ_px, occ_py, sym, coef, B, S,
                                                                                T, V, blank, d_am);
   int64_t nbs = (int64_t)B * (S + 1);

@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing for the transducer-loss path: one process per GPU, utterances
+sharded across ranks, no data-path collective.  The only exchanges are the ones the
+reference gets from Lightning DDP (rnnt_task.py:506-512):
+one all-reduce of the joiner weight gradients (kept in ONE flat buffer so it is a
+single NCCL call over NVLink, no bucketing copies) and one of the scalar losses.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> range:
+    """Contiguous, balanced shard of ``range(n_items)`` for ``rank`` (first ranks get the remainder)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return range(lo, lo + base + (1 if rank < rem else 0))
+
+
+class FlatGradBucket:
+    """All gradients of ``params`` live in one flat fp32 buffer; ``p.grad`` are views into it.
+
+    autograd accumulates into an existing ``.grad`` in place, so after ``zero()`` a backward pass
+    leaves the flat buffer holding [dW_enc, db_enc, dW_pre, db_pre, dW1, db1, dW2, db2] ready for
+    a single all-reduce.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.attach()
+
+    def attach(self) -> None:
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce(self, average: bool = True, group=None, async_op: bool = False):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        if average:
+            self.flat.div_(dist.get_world_size(group))
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def reduce_scalars(values: Sequence[torch.Tensor], group=None) -> torch.Tensor:
+    """Mean over ranks of a few 0-d tensors in ONE all-reduce (the reference logs
+    train_loss, simple_loss, pruned_loss with sync_dist=True)."""
+    vec = torch.stack([v.detach().float().reshape(()) for v in values])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        vec /= dist.get_world_size(group)
+    return vec
