@@ -1,0 +1,94 @@
+// fp32 row/column-strided matrix -> bf16 "packed operand" (tc_prims.cuh): 128 x 64 blocks in the
+// swizzled shared-memory image, k-block major, zero padded.  Used for the weights (re-packed every
+// step: they change under training) and for fp32 activations that feed a tensor-core contraction.
+#include "tc_gemm.cuh"
+
+namespace s2t {
+namespace tc {
+namespace {
+
+// one thread per 16-byte chunk (8 consecutive k of one row)
+template <bool kRowsFastest>
+__global__ void pack_operand_kernel(const float* __restrict__ src, int64_t row_stride, int64_t col_stride,
+                                    int rows, int K, int row_blocks, int k_blocks, uint8_t* __restrict__ dst) {
+  const int64_t total = (int64_t)row_blocks * 128 * k_blocks * 8;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t r, ck;  // row, chunk index along K
+  if (kRowsFastest) {
+    r = i % ((int64_t)row_blocks * 128);
+    ck = i / ((int64_t)row_blocks * 128);
+  } else {
+    ck = i % ((int64_t)k_blocks * 8);
+    r = i / ((int64_t)k_blocks * 8);
+  }
+  const int k0 = (int)ck * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j;
+    v[j] = (r < rows && k < K) ? __ldg(src + r * row_stride + (int64_t)k * col_stride) : 0.f;
+  }
+  uint4 out;
+  out.x = pack_bf16x2(v[0], v[1]);
+  out.y = pack_bf16x2(v[2], v[3]);
+  out.z = pack_bf16x2(v[4], v[5]);
+  out.w = pack_bf16x2(v[6], v[7]);
+  const int rb = (int)(r / 128), kb = k0 / 64;
+  uint8_t* blk = dst + packed_block_index(rb, kb, row_blocks) * kBlockBytes;
+  *reinterpret_cast<uint4*>(blk + block_chunk_offset((int)(r % 128), (k0 % 64) / 8)) = out;
+}
+
+}  // namespace
+
+int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int rows, int K, uint8_t* dst,
+                 cudaStream_t stream) {
+  const int row_blocks = (rows + 127) / 128, k_blocks = (K + 63) / 64;
+  const int64_t total = (int64_t)row_blocks * 128 * k_blocks * 8;
+  if (total == 0) return 0;
+  ProfScope prof("pack_operand_kernel", stream);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (col_stride == 1) {
+    pack_operand_kernel<false><<<grid, 256, 0, stream>>>(src, row_stride, col_stride, rows, K, row_blocks, k_blocks, dst);
+  } else {
+    pack_operand_kernel<true><<<grid, 256, 0, stream>>>(src, row_stride, col_stride, rows, K, row_blocks, k_blocks, dst);
+  }
+  return check_launch("pack_operand_kernel");
+}
+
+}  // namespace tc
+}  // namespace s2t
+
+using namespace s2t;
+
+// Debug / test entry: C (M x N, fp32) = A (M x K) * B (N x K)^T with bf16-rounded operands on the
+// tensor cores.  ws must hold packed A + packed B.  bn in {128, 256}.
+extern "C" size_t s2t_tc_gemm_workspace_bytes(int M, int N, int K) {
+  return tc::packed_bytes(M, K) + tc::packed_bytes(((N + 255) / 256) * 256, K) + 256;
+}
+
+extern "C" int s2t_tc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int bn, int k_splits,
+                           void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2T_REQUIRE(bn == 128 || bn == 256, "tc_gemm: bn must be 128 or 256");
+  uint8_t* pa = (uint8_t*)ws;
+  uint8_t* pb = pa + tc::packed_bytes(M, K);
+  const int n_pad = ((N + 255) / 256) * 256;
+  if (int rc = tc::pack_operand(A, K, 1, M, K, pa, st)) return rc;
+  if (int rc = tc::pack_operand(B, K, 1, N, K, pb, st)) return rc;
+  // rows of B beyond N inside the padded row blocks were zero-filled by the pack kernel only up to
+  // the last 128-row block; make the whole padded operand defined
+  const int b_row_blocks = (N + 127) / 128;
+  const int m_tiles = (M + 127) / 128, k_blocks = (K + 63) / 64;
+  (void)n_pad;
+  tc::BulkA a{pa, m_tiles};
+  if (k_splits > 1) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
+  tc::StoreRowMajorEpi epi{C, N, M, N, k_splits > 1};
+  if (bn == 128) {
+    return tc::launch_gemm_stream<128, 4>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
+                                          "tc_gemm_debug_128");
+  }
+  S2T_REQUIRE(b_row_blocks % 2 == 0, "tc_gemm: bn=256 needs N padded to a multiple of 256 rows (N=%d)", N);
+  return tc::launch_gemm_stream<256, 3>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
+                                        "tc_gemm_debug_256");
+}
