@@ -188,7 +188,7 @@ size_t s2t_lattice_workspace_bytes(int B, int S, int T, int slots) {
 }
 
 size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {
-  (void)mode;
+  if (mode == S2T_MODE_BF16_TC) return joiner_tc_workspace_bytes((int64_t)B * T * R, V, I);
   return joiner_simt_workspace_bytes((int64_t)B * T * R, V, I, nullptr);
 }
 
@@ -198,12 +198,16 @@ int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_
                         int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
                         void* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT, "joiner_loss_fwd: mode %d not built", mode);
+  S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT || mode == S2T_MODE_BF16_TC, "joiner_loss_fwd: unknown mode %d", mode);
   S2T_REQUIRE(ranges != nullptr || R == S + 1, "joiner_loss: unpruned joiner needs R == S+1 (R=%d, S=%d)", R, S);
   S2T_REQUIRE(I == 0 || (W1 && b1 && W2 && b2), "joiner_loss: out-projection weights missing");
   JoinerProblem p = make_problem(am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
                                  delay_penalty);
-  if (int rc = joiner_simt_forward(p, workspace, lse, px, py, st)) return rc;
+  if (mode == S2T_MODE_BF16_TC) {
+    if (int rc = joiner_tc_forward(p, workspace, lse, px, py, st)) return rc;
+  } else {
+    if (int rc = joiner_simt_forward(p, workspace, lse, px, py, st)) return rc;
+  }
   return band_dp(px, py, ranges, boundary, B, S, T, R, alpha_ws, scores, occ_px, occ_py, st);
 }
 
@@ -214,7 +218,7 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
                         const float* occ_py, const float* grad_scores, float* d_am, float* d_lm, float* dW1,
                         float* db1, float* dW2, float* db2, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT, "joiner_loss_bwd: mode %d not built", mode);
+  S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT || mode == S2T_MODE_BF16_TC, "joiner_loss_bwd: unknown mode %d", mode);
   JoinerProblem p = make_problem(am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
                                  0.f);
   cudaMemsetAsync(d_am, 0, (size_t)B * T * V * sizeof(float), st);
@@ -224,6 +228,10 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
     cudaMemsetAsync(db1, 0, (size_t)I * sizeof(float), st);
     cudaMemsetAsync(dW2, 0, (size_t)V * I * sizeof(float), st);
     cudaMemsetAsync(db2, 0, (size_t)V * sizeof(float), st);
+  }
+  if (mode == S2T_MODE_BF16_TC) {
+    return joiner_tc_backward(p, workspace, lse, occ_px, occ_py, grad_scores, clamp, d_am, d_lm, dW1, db1, dW2, db2,
+                              st);
   }
   return joiner_simt_backward(p, workspace, lse, occ_px, occ_py, grad_scores, clamp, d_am, d_lm, dW1, db1, dW2, db2,
                               st);

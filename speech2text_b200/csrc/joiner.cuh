@@ -33,4 +33,11 @@ int joiner_simt_backward(const JoinerProblem& p, void* workspace, const float* l
                          const float* occ_py, const float* coef, float clamp, float* d_am, float* d_lm,
                          float* dW1, float* db1, float* dW2, float* db2, cudaStream_t stream);
 
+size_t joiner_tc_workspace_bytes(int64_t M, int V, int I);
+int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float* px, float* py,
+                      cudaStream_t stream);
+int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse, const float* occ_px,
+                       const float* occ_py, const float* coef, float clamp, float* d_am, float* d_lm,
+                       float* dW1, float* db1, float* dW2, float* db2, cudaStream_t stream);
+
 }  // namespace s2t

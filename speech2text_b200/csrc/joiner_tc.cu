@@ -1,0 +1,578 @@
+// Tensor-core (bf16 operands, fp32 accumulate in TMEM) pruned joiner + loss front end.
+//
+// Same contract as joiner_simt.cu -- replaces k2.do_rnnt_pruning, the add/activation/out-projection
+// of /root/reference/model/joiner/joiner.py:121-123, 176-178 and the logsumexp + gather of
+// k2.rnnt_loss_pruned (/root/reference/model/loss/pruned_rnnt_loss.py:39-48), plus their gradients
+//  -- but every contraction runs on tcgen05 through tc_gemm.cuh:
+//
+//   forward   hidden = act(am + lm[ranges]) W1^T + b1      A built on the fly (never in HBM)
+//             logits = hidden W2^T + b2  -> per-tile (max, sum-exp) + sym/blank gather in the
+//             epilogue; the (B,T,R,V) logits never leave TMEM/registers
+//   backward  G = d loss / d logits is recomputed tile by tile from hidden and lse, then
+//             dhidden = G W2, dW2 = G^T hidden, dJ = (dhidden W1) * act', dW1 = dhidden^T act(.)
+//
+// Row-chunking bounds the only (B,T,R,V)-sized scratch (the bf16 G of one chunk, kept in both
+// orientations for the two contractions that consume it).
+// TODO(perf): chain logits -> G -> dhidden inside one kernel so G stays in smem.
+#include "joiner.cuh"
+#include "tc_gemm.cuh"
+
+namespace s2t {
+namespace {
+
+using namespace tc;
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float act_fwd_fast(float x, int act) { return act == kRelu ? fmaxf(x, 0.f) : tanh_fast(x); }
+__device__ __forceinline__ float act_bwd_fast(float x, int act) {
+  if (act == kRelu) return x > 0.f ? 1.f : 0.f;
+  float y = tanh_fast(x);
+  return 1.f - y * y;
+}
+
+// lane l ends up with sum over the warp of v[l]   (31 shuffles)
+__device__ __forceinline__ float warp_column_sums(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = hi ? v[i] : v[i + off];
+      float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ---- per-row metadata -----------------------------------------------------------------------
+__global__ void tc_row_meta_kernel(const int64_t* __restrict__ ranges, const int64_t* __restrict__ sym,
+                                   int64_t rows, int T, int R, int S, int V, int blank,
+                                   int64_t* __restrict__ am_off, int64_t* __restrict__ lm_off,
+                                   int* __restrict__ row_sym) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  int64_t bt = m / R;
+  int r = (int)(m % R);
+  int64_t b = bt / T;
+  int s = ranges ? (int)ranges[m] : r;
+  int sc = min(max(s, 0), S);
+  am_off[m] = bt * V;
+  lm_off[m] = (b * (S + 1) + sc) * V;
+  if (row_sym) row_sym[m] = (sym && s >= 0 && s < S) ? (int)sym[b * S + s] : blank;
+}
+
+// ---- A producers ----------------------------------------------------------------------------
+// rows = joiner rows m, K = vocabulary: element = act(am[m, v] + lm[m, v])
+struct JointRowProducer {
+  static constexpr bool kBulk = false;
+  const float* am;
+  const float* lm;
+  const int64_t* am_off;
+  const int64_t* lm_off;
+  int64_t M;
+  int V, act;
+  __device__ void produce(uint8_t* block, int m_tile, int kb, int t) const {
+    const int64_t m = (int64_t)m_tile * 128 + t;
+    uint8_t* row = block + t * 128;
+    if (m >= M) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + (c << 4)) = make_uint4(0, 0, 0, 0);
+      return;
+    }
+    const float* a = am + am_off[m];
+    const float* l = lm + lm_off[m];
+    const bool vec = ((V & 3) == 0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int k0 = kb * 64 + c * 8;
+      float x[8];
+      if (vec && k0 + 8 <= V) {
+        float4 a0 = __ldg(reinterpret_cast<const float4*>(a + k0)), a1 = __ldg(reinterpret_cast<const float4*>(a + k0 + 4));
+        float4 l0 = __ldg(reinterpret_cast<const float4*>(l + k0)), l1 = __ldg(reinterpret_cast<const float4*>(l + k0 + 4));
+        x[0] = a0.x + l0.x; x[1] = a0.y + l0.y; x[2] = a0.z + l0.z; x[3] = a0.w + l0.w;
+        x[4] = a1.x + l1.x; x[5] = a1.y + l1.y; x[6] = a1.z + l1.z; x[7] = a1.w + l1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = act_fwd_fast(x[j], act);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (k0 + j < V) ? act_fwd_fast(__ldg(a + k0 + j) + __ldg(l + k0 + j), act) : 0.f;
+      }
+      uint4 out = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                             pack_bf16x2(x[6], x[7]));
+      *reinterpret_cast<uint4*>(row + (((c ^ (t & 7)) & 7) << 4)) = out;
+    }
+  }
+};
+
+// rows = vocabulary v, K = joiner rows m (chunk-local): element = act(am[m, v] + lm[m, v])
+struct JointColProducer {
+  static constexpr bool kBulk = false;
+  const float* am;
+  const float* lm;
+  const int64_t* am_off;
+  const int64_t* lm_off;
+  int64_t row0, M;
+  int V, act;
+  __device__ void produce(uint8_t* block, int v_tile, int kb, int t) const {
+    const int k = t & 63, half = t >> 6;
+    const int64_t m = row0 + (int64_t)kb * 64 + k;
+    const int v0 = v_tile * 128 + half * 64;
+    const bool live = m < M;
+    const float* a = live ? am + am_off[m] : am;
+    const float* l = live ? lm + lm_off[m] : lm;
+#pragma unroll 4
+    for (int i = 0; i < 64; ++i) {
+      const int v = v0 + i;
+      float x = (live && v < V) ? act_fwd_fast(__ldg(a + v) + __ldg(l + v), act) : 0.f;
+      *reinterpret_cast<__nv_bfloat16*>(block + block_elem_offset(half * 64 + i, k)) = __float2bfloat16(x);
+    }
+  }
+};
+
+// ---- epilogue helpers -----------------------------------------------------------------------
+// write 32 consecutive K-elements (columns n..n+31 of the accumulator) of row `r_glob` of a packed operand
+__device__ __forceinline__ void store_packed_row32(uint8_t* packed, int row_blocks, int64_t r_glob, int n,
+                                                   const float (&x)[32]) {
+  const int rb = (int)(r_glob >> 7), r = (int)(r_glob & 127);
+  uint8_t* blk = packed + packed_block_index(rb, n >> 6, row_blocks) * kBlockBytes;
+  const int c0 = (n & 63) >> 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 out = make_uint4(pack_bf16x2(x[c * 8 + 0], x[c * 8 + 1]), pack_bf16x2(x[c * 8 + 2], x[c * 8 + 3]),
+                           pack_bf16x2(x[c * 8 + 4], x[c * 8 + 5]), pack_bf16x2(x[c * 8 + 6], x[c * 8 + 7]));
+    *reinterpret_cast<uint4*>(blk + block_chunk_offset(r, c0 + c)) = out;
+  }
+}
+// transposed: element (row = n + j, k = k_glob) for j < 32
+__device__ __forceinline__ void store_packed_col32(uint8_t* packed, int row_blocks, int n, int64_t k_glob,
+                                                   const float (&x)[32]) {
+  const int kb = (int)(k_glob >> 6), k = (int)(k_glob & 63);
+  const int rb = n >> 7;  // n is a multiple of 32: the 32 rows share a row block
+  uint8_t* blk = packed + packed_block_index(rb, kb, row_blocks) * kBlockBytes;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    *reinterpret_cast<__nv_bfloat16*>(blk + block_elem_offset((n & 127) + j, k)) = __float2bfloat16(x[j]);
+  }
+}
+
+// hidden = acc + b1 -> Hp (rows m, K i) and HTp (rows i, K m)
+struct HiddenEpi {
+  const float* b1;
+  int I;
+  int64_t M;
+  uint8_t* Hp;
+  int h_row_blocks;
+  uint8_t* HTp;
+  int ht_row_blocks;
+  struct State {};
+  __device__ void begin(State&, const EpiCtx&) const {}
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    float x[32];
+    const bool live = ctx.m < M;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = (live && n + j < I) ? acc[j] + __ldg(b1 + n + j) : 0.f;
+    store_packed_row32(Hp, h_row_blocks, ctx.m, n, x);
+    store_packed_col32(HTp, ht_row_blocks, n, ctx.m, x);
+  }
+};
+
+// logits = acc + b2: per-tile (max, sum exp) and the gathered sym / blank logits
+struct LseEpi {
+  const float* b2;
+  const int* row_sym;
+  int V, blank, n_tiles;
+  int64_t M;
+  float* part;  // (M, n_tiles, 2)
+  float* sym_logit;
+  float* blank_logit;
+  struct State { float mx, sum; int csym; };
+  __device__ void begin(State& st, const EpiCtx& ctx) const {
+    st.mx = kNegInf;
+    st.sum = 0.f;
+    st.csym = ctx.m < M ? row_sym[ctx.m] : -1;
+  }
+  __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    if (ctx.m >= M || n >= V) return;
+    float x[32];
+    float cm = kNegInf;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      x[j] = (n + j < V) ? acc[j] + __ldg(b2 + n + j) : kNegInf;
+      cm = fmaxf(cm, x[j]);
+    }
+    if (cm > st.mx) {
+      st.sum *= exp2f((st.mx - cm) * kLog2e);
+      st.mx = cm;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += exp2f((x[j] - st.mx) * kLog2e);
+    st.sum += s;
+    if (st.csym >= n && st.csym < n + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j == st.csym) sym_logit[ctx.m] = x[j];
+    }
+    if (blank >= n && blank < n + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j == blank) blank_logit[ctx.m] = x[j];
+    }
+  }
+  __device__ void end(State& st, const EpiCtx& ctx) const {
+    if (ctx.m >= M) return;
+    float* p = part + ((int64_t)ctx.m * n_tiles + ctx.n_tile) * 2;
+    p[0] = st.mx;
+    p[1] = st.sum;
+  }
+};
+
+__global__ void lse_combine_kernel(const float* __restrict__ part, const float* __restrict__ sym_logit,
+                                   const float* __restrict__ blank_logit, const int64_t* __restrict__ boundary,
+                                   int64_t rows, int n_tiles, int T, int R, float delay_penalty,
+                                   float* __restrict__ lse, float* __restrict__ px, float* __restrict__ py) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const float* p = part + m * n_tiles * 2;
+  float mx = kNegInf;
+  for (int i = 0; i < n_tiles; ++i) mx = fmaxf(mx, p[2 * i]);
+  float s = 0.f;
+  for (int i = 0; i < n_tiles; ++i) s += p[2 * i + 1] * expf(p[2 * i] - mx);
+  const float l = mx + logf(s);
+  lse[m] = l;
+  float xv = sym_logit[m] - l;
+  if (delay_penalty != 0.f) {
+    const int b = (int)(m / ((int64_t)T * R));
+    const int t = (int)((m / R) % T);
+    const int Tb = boundary ? (int)boundary[4 * b + 3] : T;
+    xv += delay_penalty * (0.5f * (float)(Tb - 1) - (float)t);
+  }
+  px[m] = xv;
+  py[m] = blank_logit[m] - l;
+}
+
+// G = coef * clip(occ_px [v == sym] + occ_py [v == blank] - (occ_px + occ_py) softmax) for a row chunk
+struct GradEpi {
+  const float* b2;
+  const int* row_sym;
+  const float* lse;
+  const float* occ_px;
+  const float* occ_py;
+  const float* coef;  // per utterance
+  int64_t row0, M;
+  int TR, V, blank;
+  float clamp;
+  uint8_t* Gp;   // rows = chunk-local m, K = v (g_k_blocks blocks of 64: only ceil(V/64), not Vp/64)
+  int g_row_blocks, g_k_blocks;
+  uint8_t* GTp;  // rows = v, K = chunk-local m
+  int gt_row_blocks;
+  float* db2;
+  struct State { float l, ox, oy, cf; int csym; bool live; };
+  __device__ void begin(State& st, const EpiCtx& ctx) const {
+    const int64_t m = row0 + ctx.m;
+    st.live = m < M;
+    st.l = 0.f; st.ox = 0.f; st.oy = 0.f; st.cf = 0.f; st.csym = -1;
+    if (st.live) {
+      st.l = lse[m];
+      st.ox = occ_px[m];
+      st.oy = occ_py[m];
+      st.cf = coef[m / TR];
+      st.csym = row_sym[m];
+      if (st.ox + st.oy == 0.f || st.cf == 0.f) st.live = false;
+    }
+  }
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    float x[32];
+    const float g = st.ox + st.oy;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int v = n + j;
+      float val = 0.f;
+      if (st.live && v < V) {
+        val = -g * exp2f((acc[j] + __ldg(b2 + v) - st.l) * kLog2e);
+        if (v == st.csym) val += st.ox;
+        if (v == blank) val += st.oy;
+        if (clamp > 0.f) val = fminf(fmaxf(val, -clamp), clamp);
+        val *= st.cf;
+      }
+      x[j] = val;
+    }
+    if ((n >> 6) < g_k_blocks) store_packed_row32(Gp, g_row_blocks, ctx.m, n, x);
+    store_packed_col32(GTp, gt_row_blocks, n, ctx.m, x);
+    const float cs = warp_column_sums(x);
+    const int lane = threadIdx.x & 31;
+    if (n + lane < V && cs != 0.f) atomicAdd(db2 + n + lane, cs);
+  }
+};
+
+// dhidden -> DHp (rows chunk-local m, K i), DHTp (rows i, K chunk-local m), db1
+struct DHiddenEpi {
+  int I;
+  uint8_t* DHp;
+  int dh_row_blocks;
+  uint8_t* DHTp;
+  int dht_row_blocks;
+  float* db1;
+  struct State {};
+  __device__ void begin(State&, const EpiCtx&) const {}
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = (n + j < I) ? acc[j] : 0.f;
+    store_packed_row32(DHp, dh_row_blocks, ctx.m, n, x);
+    store_packed_col32(DHTp, dht_row_blocks, n, ctx.m, x);
+    const float cs = warp_column_sums(x);
+    const int lane = threadIdx.x & 31;
+    if (n + lane < I && cs != 0.f) atomicAdd(db1 + n + lane, cs);
+  }
+};
+
+// dJ = (dhidden W1)[m, v] * act'(am + lm) scattered into d_am / d_lm
+struct DJointEpi {
+  const float* am;
+  const float* lm;
+  const int64_t* am_off;
+  const int64_t* lm_off;
+  int64_t row0, M;
+  int V, act;
+  float* d_am;
+  float* d_lm;
+  struct State { int64_t ao, lo; bool live; };
+  __device__ void begin(State& st, const EpiCtx& ctx) const {
+    const int64_t m = row0 + ctx.m;
+    st.live = m < M;
+    st.ao = st.live ? am_off[m] : 0;
+    st.lo = st.live ? lm_off[m] : 0;
+  }
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State& st, const EpiCtx&, int n, const float (&acc)[32]) const {
+    if (!st.live) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int v = n + j;
+      if (v < V && acc[j] != 0.f) {
+        float dj = acc[j] * act_bwd_fast(__ldg(am + st.ao + v) + __ldg(lm + st.lo + v), act);
+        if (dj != 0.f) {
+          atomicAdd(d_am + st.ao + v, dj);
+          atomicAdd(d_lm + st.lo + v, dj);
+        }
+      }
+    }
+  }
+};
+
+// C^T accumulate: out[(n + j) * ld + m] += acc[j]     (dW1[i, v] from the (v, i) accumulator)
+struct StoreTransposedAtomicEpi {
+  float* out;
+  int64_t ld;
+  int M, N;  // valid rows (v) and columns (i) of the accumulator
+  struct State {};
+  __device__ void begin(State&, const EpiCtx&) const {}
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    if (ctx.m >= M) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < N && acc[j] != 0.f) atomicAdd(out + (int64_t)(n + j) * ld + ctx.m, acc[j]);
+  }
+};
+
+struct TcDims {
+  int64_t M;       // joiner rows
+  int Mt;          // row tiles of 128
+  int Vp, Ip;      // V, I padded to multiples of 256
+  int kbV, kbI;    // K blocks of 64 covering V, Ip
+  int n_tiles_v;   // Vp / 256
+  int64_t chunk;   // rows per backward chunk (multiple of 128)
+};
+
+TcDims tc_dims(int64_t M, int V, int I) {
+  TcDims d;
+  d.M = M;
+  d.Mt = (int)((M + 127) / 128);
+  d.Vp = ((V + 255) / 256) * 256;
+  d.Ip = ((I + 255) / 256) * 256;
+  d.kbV = (V + 63) / 64;
+  d.kbI = d.Ip / 64;
+  d.n_tiles_v = d.Vp / 256;
+  const size_t budget = (size_t)1 << 30;  // bytes of one orientation of the chunk's G
+  int64_t rows = (int64_t)(budget / ((size_t)d.kbV * 64 * 2));
+  rows = (rows / 128) * 128;
+  if (rows < 128) rows = 128;
+  int64_t all = (int64_t)d.Mt * 128;
+  d.chunk = rows < all ? rows : all;
+  return d;
+}
+
+struct TcWs {
+  int64_t* am_off;
+  int64_t* lm_off;
+  int* row_sym;
+  float* part;
+  float* sym_logit;
+  float* blank_logit;
+  uint8_t *W1p, *W2p, *W2Tp, *W1Tp;
+  uint8_t *Hp, *HTp;
+  uint8_t *Gp, *GTp, *DHp, *DHTp;
+  size_t bytes;
+};
+
+TcWs tc_carve(void* ws, const TcDims& d) {
+  TcWs w;
+  char* p = (char*)ws;
+  auto take = [&](size_t n) {
+    char* q = p;
+    p += (n + 1023) / 1024 * 1024;
+    return q;
+  };
+  const size_t rows_all = (size_t)d.Mt * 128;
+  const int ct = (int)(d.chunk / 128);
+  w.am_off = (int64_t*)take(d.M * sizeof(int64_t));
+  w.lm_off = (int64_t*)take(d.M * sizeof(int64_t));
+  w.row_sym = (int*)take(d.M * sizeof(int));
+  w.part = (float*)take((size_t)d.M * d.n_tiles_v * 2 * sizeof(float));
+  w.sym_logit = (float*)take(d.M * sizeof(float));
+  w.blank_logit = (float*)take(d.M * sizeof(float));
+  w.W1p = (uint8_t*)take((size_t)(d.Ip / 128) * d.kbV * kBlockBytes);
+  w.W2Tp = (uint8_t*)take((size_t)(d.Ip / 128) * d.kbV * kBlockBytes);
+  w.W2p = (uint8_t*)take((size_t)(d.Vp / 128) * d.kbI * kBlockBytes);
+  w.W1Tp = (uint8_t*)take((size_t)(d.Vp / 128) * d.kbI * kBlockBytes);
+  w.Hp = (uint8_t*)take((size_t)d.Mt * d.kbI * kBlockBytes);
+  w.HTp = (uint8_t*)take((size_t)(d.Ip / 128) * (rows_all / 64) * kBlockBytes);
+  w.Gp = (uint8_t*)take((size_t)ct * d.kbV * kBlockBytes);
+  w.GTp = (uint8_t*)take((size_t)(d.Vp / 128) * (d.chunk / 64) * kBlockBytes);
+  w.DHp = (uint8_t*)take((size_t)ct * d.kbI * kBlockBytes);
+  w.DHTp = (uint8_t*)take((size_t)(d.Ip / 128) * (d.chunk / 64) * kBlockBytes);
+  w.bytes = (size_t)(p - (char*)ws);
+  return w;
+}
+
+int pack_weights(const JoinerProblem& p, const TcDims& d, const TcWs& w, bool for_backward, cudaStream_t st) {
+  // W1 (I, V): rows i, K v          W2 (V, I): rows v, K i
+  if (int rc = pack_operand(p.W1, p.V, 1, p.I, p.V, d.Ip / 128, d.kbV, w.W1p, st)) return rc;
+  if (int rc = pack_operand(p.W2, p.I, 1, p.V, p.I, d.Vp / 128, d.kbI, w.W2p, st)) return rc;
+  if (for_backward) {
+    // W2^T: rows i, K v -> element (i, v) = W2[v * I + i]     W1^T: rows v, K i -> W1[i * V + v]
+    if (int rc = pack_operand(p.W2, 1, p.I, p.I, p.V, d.Ip / 128, d.kbV, w.W2Tp, st)) return rc;
+    if (int rc = pack_operand(p.W1, 1, p.V, p.V, p.I, d.Vp / 128, d.kbI, w.W1Tp, st)) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+size_t joiner_tc_workspace_bytes(int64_t M, int V, int I) {
+  TcDims d = tc_dims(M, V, I > 0 ? I : 256);
+  TcWs w = tc_carve(nullptr, d);
+  return w.bytes + 4096;
+}
+
+int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float* px, float* py,
+                      cudaStream_t stream) {
+  S2T_REQUIRE(p.I > 0, "bf16 tensor-core joiner needs the out-projection (use_out_project=True); "
+                       "the projection-free joiner has no contraction and runs in fp32 mode");
+  const int64_t M = (int64_t)p.B * p.T * p.R;
+  if (M == 0) return 0;
+  TcDims d = tc_dims(M, p.V, p.I);
+  TcWs w = tc_carve(workspace, d);
+  {
+    ProfScope prof("tc_row_meta_kernel", stream);
+    tc_row_meta_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(p.ranges, p.sym, M, p.T, p.R, p.S, p.V, p.blank,
+                                                                       w.am_off, w.lm_off, w.row_sym);
+  }
+  if (int rc = check_launch("tc_row_meta_kernel")) return rc;
+  if (int rc = pack_weights(p, d, w, false, stream)) return rc;
+  // hidden: M x Ip, K = V
+  {
+    JointRowProducer a{p.am, p.lm, w.am_off, w.lm_off, M, p.V, p.act};
+    HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt, w.HTp, d.Ip / 128};
+    if (int rc = launch_gemm_stream<256, 3>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
+                                            "tc_joiner_hidden_gemm"))
+      return rc;
+  }
+  // logits -> lse partials: M x Vp, K = Ip
+  {
+    BulkA a{w.Hp, d.Mt};
+    LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_tiles_v, M, w.part, w.sym_logit, w.blank_logit};
+    if (int rc = launch_gemm_stream<256, 3>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
+                                            "tc_joiner_logits_lse_gemm"))
+      return rc;
+  }
+  {
+    ProfScope prof("lse_combine_kernel", stream);
+    lse_combine_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(w.part, w.sym_logit, w.blank_logit, p.boundary,
+                                                                       M, d.n_tiles_v, p.T, p.R, p.delay_penalty, lse,
+                                                                       px, py);
+  }
+  return check_launch("lse_combine_kernel");
+}
+
+// Gradients are ACCUMULATED into d_am, d_lm, dW1, db1, dW2, db2 (the caller zero-fills).
+int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse, const float* occ_px,
+                       const float* occ_py, const float* coef, float clamp, float* d_am, float* d_lm, float* dW1,
+                       float* db1, float* dW2, float* db2, cudaStream_t stream) {
+  const int64_t M = (int64_t)p.B * p.T * p.R;
+  if (M == 0) return 0;
+  TcDims d = tc_dims(M, p.V, p.I);
+  TcWs w = tc_carve(workspace, d);
+  if (int rc = pack_weights(p, d, w, true, stream)) return rc;
+  const int sms = 148;
+  for (int64_t row0 = 0; row0 < (int64_t)d.Mt * 128; row0 += d.chunk) {
+    const int64_t rows_pad = ((int64_t)d.Mt * 128 - row0 < d.chunk) ? ((int64_t)d.Mt * 128 - row0) : d.chunk;
+    const int ct = (int)(rows_pad / 128);       // row tiles of this chunk
+    const int kbM = (int)(rows_pad / 64);       // K blocks when rows are the contraction index
+    const int tile0 = (int)(row0 / 128);
+    // G = d loss / d logits of the chunk, both orientations (+ db2)
+    {
+      BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
+      GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp,
+                 w.Gp, ct, d.kbV, w.GTp, d.Vp / 128, db2};
+      if (int rc = launch_gemm_stream<256, 3>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+                                              "tc_joiner_grad_logits_gemm"))
+        return rc;
+    }
+    // dhidden = G W2: rows m, N = Ip, K = V
+    {
+      BulkA a{w.Gp, ct};
+      DHiddenEpi ep{p.I, w.DHp, ct, w.DHTp, d.Ip / 128, db1};
+      if (int rc = launch_gemm_stream<256, 3>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
+                                              "tc_joiner_dhidden_gemm"))
+        return rc;
+    }
+    const int splits = max(1, min(kbM, sms / max(1, (d.Vp / 128) * (d.Ip / 256))));
+    // dW2[v, i] += sum_m G[m, v] hidden[m, i]: rows v, N = Ip, K = chunk rows
+    {
+      BulkA a{w.GTp, d.Vp / 128};
+      const uint8_t* ht = w.HTp + (size_t)(row0 / 64) * (d.Ip / 128) * kBlockBytes;  // K offset of the chunk
+      StoreRowMajorEpi ep{dW2, p.I, p.V, p.I, true};
+      if (int rc = launch_gemm_stream<256, 3>(a, ht, d.Ip / 128, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
+                                              "tc_joiner_dW2_gemm"))
+        return rc;
+    }
+    // dW1[i, v] += sum_m dhidden[m, i] act(.)[m, v]: accumulator rows v, N = Ip, K = chunk rows
+    {
+      JointColProducer a{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act};
+      StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
+      if (int rc = launch_gemm_stream<256, 3>(a, w.DHTp, d.Ip / 128, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
+                                              "tc_joiner_dW1_gemm"))
+        return rc;
+    }
+    // dJ = (dhidden W1) * act' -> d_am, d_lm: rows m, N = Vp, K = Ip
+    {
+      BulkA a{w.DHp, ct};
+      DJointEpi ep{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act, d_am, d_lm};
+      if (int rc = launch_gemm_stream<256, 3>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+                                              "tc_joiner_djoint_gemm"))
+        return rc;
+    }
+  }
+  return 0;
+}
+
+}  // namespace s2t

@@ -19,13 +19,32 @@
 //       // kBulk:  const uint8_t* packed; int row_blocks;
 //       // !kBulk: __device__ void produce(uint8_t* block, int m_tile, int kb, int t) const;  t in [0,128)
 //   };
-//   struct Epi { __device__ void operator()(int m, int n, const float (&acc)[32], int split) const; };
+//   struct Epi {
+//     struct State {...};                       // per-thread (= per output row) running state
+//     __device__ void begin(State&, const EpiCtx&) const;
+//     __device__ void chunk(State&, const EpiCtx&, int n, const float (&acc)[32]) const;   // 32 columns from n
+//     __device__ void end(State&, const EpiCtx&) const;
+//   };
+// During the epilogue all MMAs of the CTA have completed, so the operand ring is free:
+// EpiCtx::scratch points at it (kStages * stage bytes) for CTA-level reductions; epi_sync()
+// is a barrier over the 128 epilogue threads.
 #pragma once
 #include "common.cuh"
 #include "tc_prims.cuh"
 
 namespace s2t {
 namespace tc {
+
+struct EpiCtx {
+  int m;        // global output row of this thread
+  int t;        // epilogue thread index, 0..127 (row inside the tile = quarter * 32 + lane)
+  int row;      // row inside the 128-row tile
+  int m_tile, n_tile, split;
+  uint8_t* scratch;
+  int scratch_bytes;
+};
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct BulkA {
   static constexpr bool kBulk = true;
@@ -87,7 +106,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
         mbar_arrive_expect_tx(&full[s], (ASrc::kBulk ? kABytes : 0) + kBBytes);
-        if (ASrc::kBulk) {
+        if constexpr (ASrc::kBulk) {
           bulk_copy_g2s(sa, asrc.packed + packed_block_index(m_tile, kb, asrc.row_blocks) * kBlockBytes, kABytes,
                         &full[s]);
         }
@@ -115,7 +134,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     }
   } else {
     const int t = (warp - 2) * 32 + lane;
-    if (!ASrc::kBulk) {
+    if constexpr (!ASrc::kBulk) {
       for (int it = 0; it < n_it; ++it) {
         const int s = it % kStages, ph = (it / kStages) & 1, kb = kb0 + it;
         mbar_wait(&empty[s], ph ^ 1);
@@ -127,13 +146,24 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int quarter = warp & 3;  // TMEM lanes this warp may read
-    const int m = m_tile * 128 + quarter * 32 + lane;
+    EpiCtx ctx;
+    ctx.row = quarter * 32 + lane;
+    ctx.m = m_tile * 128 + ctx.row;
+    ctx.t = t;
+    ctx.m_tile = m_tile;
+    ctx.n_tile = n_tile;
+    ctx.split = split;
+    ctx.scratch = smem;
+    ctx.scratch_bytes = kStages * kStageBytes;
+    typename Epi::State st;
+    epi.begin(st, ctx);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
-      epi(m, n_tile * BN + c * 32, v, split);
+      epi.chunk(st, ctx, n_tile * BN + c * 32, v);
     }
+    epi.end(st, ctx);
   }
   tc_fence_before();
   __syncthreads();
@@ -171,7 +201,11 @@ struct StoreRowMajorEpi {
   int64_t ldc;
   int M, N;
   bool atomic;
-  __device__ void operator()(int m, int n, const float (&acc)[32], int) const {
+  struct State {};
+  __device__ void begin(State&, const EpiCtx&) const {}
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    const int m = ctx.m;
     if (m >= M) return;
     float* row = C + (int64_t)m * ldc;
 #pragma unroll
@@ -185,9 +219,10 @@ struct StoreRowMajorEpi {
 };
 
 // ---- packing ----------------------------------------------------------------------------------
-// fp32 src(r, k) = src[r * row_stride + k * col_stride]  ->  bf16 packed operand (rows x K), zero padded.
-int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int rows, int K, uint8_t* dst,
-                 cudaStream_t stream);
+// fp32 src(r, k) = src[r * row_stride + k * col_stride]  ->  bf16 packed operand of row_blocks x k_blocks
+// blocks, zero padded beyond (rows, K).
+int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int rows, int K, int row_blocks,
+                 int k_blocks, uint8_t* dst, cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace s2t

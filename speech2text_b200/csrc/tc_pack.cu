@@ -41,9 +41,9 @@ __global__ void pack_operand_kernel(const float* __restrict__ src, int64_t row_s
 
 }  // namespace
 
-int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int rows, int K, uint8_t* dst,
-                 cudaStream_t stream) {
-  const int row_blocks = (rows + 127) / 128, k_blocks = (K + 63) / 64;
+int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int rows, int K, int row_blocks,
+                 int k_blocks, uint8_t* dst, cudaStream_t stream) {
+  S2T_REQUIRE(row_blocks * 128 >= rows && k_blocks * 64 >= K, "pack_operand: padded dims too small");
   const int64_t total = (int64_t)row_blocks * 128 * k_blocks * 8;
   if (total == 0) return 0;
   ProfScope prof("pack_operand_kernel", stream);
@@ -74,13 +74,10 @@ extern "C" int s2t_tc_gemm(const float* A, const float* B, float* C, int M, int 
   uint8_t* pa = (uint8_t*)ws;
   uint8_t* pb = pa + tc::packed_bytes(M, K);
   const int n_pad = ((N + 255) / 256) * 256;
-  if (int rc = tc::pack_operand(A, K, 1, M, K, pa, st)) return rc;
-  if (int rc = tc::pack_operand(B, K, 1, N, K, pb, st)) return rc;
-  // rows of B beyond N inside the padded row blocks were zero-filled by the pack kernel only up to
-  // the last 128-row block; make the whole padded operand defined
-  const int b_row_blocks = (N + 127) / 128;
+  const int b_row_blocks = n_pad / 128;
   const int m_tiles = (M + 127) / 128, k_blocks = (K + 63) / 64;
-  (void)n_pad;
+  if (int rc = tc::pack_operand(A, K, 1, M, K, m_tiles, k_blocks, pa, st)) return rc;
+  if (int rc = tc::pack_operand(B, K, 1, N, K, b_row_blocks, k_blocks, pb, st)) return rc;
   tc::BulkA a{pa, m_tiles};
   if (k_splits > 1) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
   tc::StoreRowMajorEpi epi{C, N, M, N, k_splits > 1};
@@ -88,7 +85,6 @@ extern "C" int s2t_tc_gemm(const float* A, const float* B, float* C, int M, int 
     return tc::launch_gemm_stream<128, 4>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
                                           "tc_gemm_debug_128");
   }
-  S2T_REQUIRE(b_row_blocks % 2 == 0, "tc_gemm: bn=256 needs N padded to a multiple of 256 rows (N=%d)", N);
   return tc::launch_gemm_stream<256, 3>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
                                         "tc_gemm_debug_256");
 }

@@ -173,12 +173,12 @@ def test_vanilla_loss_on_materialised_logits_matches_torchaudio(clamp):
     assert rel_err(lg.grad, lr.grad) < GRAD_RTOL
 
 
-def _run_modules(name, fused: bool, monkeypatch, dtype=torch.float32):
+def _run_modules(name, fused: bool, monkeypatch, mode: str = "fp32"):
     """One fwd+bwd through the drop-in modules exactly as rnnt_task.py:469-514 strings them."""
     from model.joiner.joiner import Joiner, JoinerConfig
     from model.loss.loss import Loss
     monkeypatch.setenv("S2T_B200_FUSED", "1" if fused else "0")
-    monkeypatch.setenv("S2T_B200_JOINER_MODE", "fp32")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", mode)
     spec, case = CASES[name], make_case(name)
     dev = _dev()
     joiner = Joiner(JoinerConfig(**spec["joiner"]))
@@ -239,6 +239,31 @@ def test_training_step_matches_reference_goldens(name, fused, monkeypatch):
     np.testing.assert_allclose(out["total_loss"].item(), gold["total_loss"], rtol=LOSS_RTOL)
     for key in [k[:-len(".stride")] for k in gold if k.endswith(".stride") and k.startswith("d")]:
         check_summary(out[key], gold, key, rtol=GRAD_RTOL, what=name)
+
+
+BF16_RTOL = 1e-2  # north_star: bf16-joiner relative 1e-2
+
+
+@pytest.mark.parametrize("name", [n for n in SUPPORTED if CASES[n]["joiner"].get("use_out_project", True)])
+def test_bf16_tensor_core_joiner_matches_reference_goldens(name, monkeypatch):
+    """bf16 operands / fp32 accumulation on tcgen05 for every joiner contraction (fwd + bwd); the simple
+    loss, ranges and lattice DPs stay fp32, so ranges must still be identical."""
+    gold = load_golden(name, "f32")
+    out = _run_modules(name, True, monkeypatch, mode="bf16")
+    if "ranges" in out:
+        assert np.array_equal(out["ranges"].cpu().numpy(), gold["ranges"])
+        np.testing.assert_allclose(out["simple_loss"].item(), gold["simple_loss"], rtol=LOSS_RTOL)
+        np.testing.assert_allclose(out["pruned_loss"].detach().cpu().double().numpy(), gold["pruned_loss"],
+                                   rtol=BF16_RTOL)
+    np.testing.assert_allclose(out["total_loss"].item(), gold["total_loss"], rtol=BF16_RTOL)
+    for key in [k[:-len(".stride")] for k in gold if k.endswith(".stride") and k.startswith("d")]:
+        check_summary(out[key], gold, key, rtol=BF16_RTOL, what=name + "[bf16]")
+
+
+def test_bf16_mode_without_out_projection_fails_loudly(monkeypatch):
+    from speech2text_b200._lib import S2TError
+    with pytest.raises(S2TError):
+        _run_modules("joiner_test", True, monkeypatch, mode="bf16")
 
 
 @pytest.mark.parametrize("name", ["joiner_test", "tanh_smoothed", "range_clamped"])
