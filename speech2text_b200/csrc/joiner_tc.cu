@@ -65,7 +65,52 @@ __global__ void tc_row_meta_kernel(const int64_t* __restrict__ ranges, const int
 }
 
 // ---- A producers ----------------------------------------------------------------------------
-// rows = joiner rows m, K = vocabulary: element = act(am[m, v] + lm[m, v])
+// Both producers turn 64 consecutive vocabulary entries of one joiner row m into eight 16-byte
+// chunks act(am[m, v] + lm[m, v]) -> bf16.  Work is pipelined in half rows (32 entries): the
+// global loads of the next half are issued before the current half is converted, so one L2
+// round trip is exposed per pipeline fill, not per chunk.
+struct JointHalf {
+  float4 a[8], l[8];
+};
+
+__device__ __forceinline__ void joint_load_half(JointHalf& h, const float* a, const float* l, int v0, int V,
+                                                bool live, bool vec) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int v = v0 + q * 4;
+    if (live && vec && v + 4 <= V) {
+      h.a[q] = __ldg(reinterpret_cast<const float4*>(a + v));
+      h.l[q] = __ldg(reinterpret_cast<const float4*>(l + v));
+    } else {
+      float xa[4], xl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = live && (v + j < V);
+        xa[j] = ok ? __ldg(a + v + j) : 0.f;
+        xl[j] = ok ? __ldg(l + v + j) : 0.f;
+      }
+      h.a[q] = make_float4(xa[0], xa[1], xa[2], xa[3]);
+      h.l[q] = make_float4(xl[0], xl[1], xl[2], xl[3]);
+    }
+  }
+}
+
+// writes chunks c0 .. c0+3 of the 128-byte row at `row_base`; r7 = (row index & 7) for the swizzle.
+// Padding (v >= V or dead row) must come out as exact zeros: act(0) = 0 for relu and tanh.
+__device__ __forceinline__ void joint_emit_half(const JointHalf& h, uint8_t* row_base, int r7, int c0, int act) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 a0 = h.a[2 * c], a1 = h.a[2 * c + 1], l0 = h.l[2 * c], l1 = h.l[2 * c + 1];
+    uint4 out;
+    out.x = pack_bf16x2(act_fwd_fast(a0.x + l0.x, act), act_fwd_fast(a0.y + l0.y, act));
+    out.y = pack_bf16x2(act_fwd_fast(a0.z + l0.z, act), act_fwd_fast(a0.w + l0.w, act));
+    out.z = pack_bf16x2(act_fwd_fast(a1.x + l1.x, act), act_fwd_fast(a1.y + l1.y, act));
+    out.w = pack_bf16x2(act_fwd_fast(a1.z + l1.z, act), act_fwd_fast(a1.w + l1.w, act));
+    *reinterpret_cast<uint4*>(row_base + ((((c0 + c) ^ r7) & 7) << 4)) = out;
+  }
+}
+
+// K-major A: block rows = joiner rows m of the tile, K = vocabulary.
 struct JointRowProducer {
   static constexpr bool kBulk = false;
   const float* am;
@@ -74,41 +119,31 @@ struct JointRowProducer {
   const int64_t* lm_off;
   int64_t M;
   int V, act;
-  __device__ void produce(uint8_t* block, int m_tile, int kb, int t) const {
+  template <class W, class A>
+  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t,
+                      W wait_empty, A arrive_full) const {
     const int64_t m = (int64_t)m_tile * 128 + t;
-    uint8_t* row = block + t * 128;
-    if (m >= M) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + (c << 4)) = make_uint4(0, 0, 0, 0);
-      return;
-    }
-    const float* a = am + am_off[m];
-    const float* l = lm + lm_off[m];
+    const bool live = m < M;
+    const float* a = am + (live ? am_off[m] : 0);
+    const float* l = lm + (live ? lm_off[m] : 0);
     const bool vec = ((V & 3) == 0);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int k0 = kb * 64 + c * 8;
-      float x[8];
-      if (vec && k0 + 8 <= V) {
-        float4 a0 = __ldg(reinterpret_cast<const float4*>(a + k0)), a1 = __ldg(reinterpret_cast<const float4*>(a + k0 + 4));
-        float4 l0 = __ldg(reinterpret_cast<const float4*>(l + k0)), l1 = __ldg(reinterpret_cast<const float4*>(l + k0 + 4));
-        x[0] = a0.x + l0.x; x[1] = a0.y + l0.y; x[2] = a0.z + l0.z; x[3] = a0.w + l0.w;
-        x[4] = a1.x + l1.x; x[5] = a1.y + l1.y; x[6] = a1.z + l1.z; x[7] = a1.w + l1.w;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = act_fwd_fast(x[j], act);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (k0 + j < V) ? act_fwd_fast(__ldg(a + k0 + j) + __ldg(l + k0 + j), act) : 0.f;
-      }
-      uint4 out = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                             pack_bf16x2(x[6], x[7]));
-      *reinterpret_cast<uint4*>(row + (((c ^ (t & 7)) & 7) << 4)) = out;
+    const int H = 2 * n_it;
+    JointHalf cur, nxt;
+    joint_load_half(cur, a, l, ks0 * 64, V, live, vec);
+    for (int h = 0; h < H; ++h) {
+      const int it = h >> 1, half = h & 1;
+      if (h + 1 < H) joint_load_half(nxt, a, l, (ks0 + ((h + 1) >> 1)) * 64 + ((h + 1) & 1) * 32, V, live, vec);
+      if (half == 0) wait_empty(it);
+      uint8_t* row = smem + (it % stages) * stage_bytes + t * 128;
+      joint_emit_half(cur, row, t & 7, half * 4, act);
+      if (half == 1) arrive_full(it);
+      cur = nxt;
     }
   }
 };
 
-// rows = vocabulary v, K = joiner rows m (chunk-local): element = act(am[m, v] + lm[m, v])
-struct JointColProducer {
+// MN-major A: stage = 2 groups x [64 contraction rows (joiner rows m) x 64 vocabulary entries].
+struct JointMnProducer {
   static constexpr bool kBulk = false;
   const float* am;
   const float* lm;
@@ -116,18 +151,39 @@ struct JointColProducer {
   const int64_t* lm_off;
   int64_t row0, M;
   int V, act;
-  __device__ void produce(uint8_t* block, int v_tile, int kb, int t) const {
-    const int k = t & 63, half = t >> 6;
-    const int64_t m = row0 + (int64_t)kb * 64 + k;
-    const int v0 = v_tile * 128 + half * 64;
-    const bool live = m < M;
-    const float* a = live ? am + am_off[m] : am;
-    const float* l = live ? lm + lm_off[m] : lm;
-#pragma unroll 4
-    for (int i = 0; i < 64; ++i) {
-      const int v = v0 + i;
-      float x = (live && v < V) ? act_fwd_fast(__ldg(a + v) + __ldg(l + v), act) : 0.f;
-      *reinterpret_cast<__nv_bfloat16*>(block + block_elem_offset(half * 64 + i, k)) = __float2bfloat16(x);
+  template <class W, class A>
+  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int v_tile, int ks0, int n_it, int t,
+                      W wait_empty, A arrive_full) const {
+    const int r = t >> 1, g = t & 1;
+    const int v_base = v_tile * 128 + g * 64;
+    const bool vec = ((V & 3) == 0);
+    const int H = 2 * n_it;
+    auto row_ptrs = [&](int ks, const float*& a, const float*& l, bool& live) {
+      const int64_t m = row0 + (int64_t)ks * 64 + r;
+      live = m < M;
+      a = am + (live ? am_off[m] : 0);
+      l = lm + (live ? lm_off[m] : 0);
+    };
+    JointHalf cur, nxt;
+    {
+      const float *a, *l;
+      bool live;
+      row_ptrs(ks0, a, l, live);
+      joint_load_half(cur, a, l, v_base, V, live, vec);
+    }
+    for (int h = 0; h < H; ++h) {
+      const int it = h >> 1, half = h & 1;
+      if (h + 1 < H) {
+        const float *a, *l;
+        bool live;
+        row_ptrs(ks0 + ((h + 1) >> 1), a, l, live);
+        joint_load_half(nxt, a, l, v_base + ((h + 1) & 1) * 32, V, live, vec);
+      }
+      if (half == 0) wait_empty(it);
+      uint8_t* row = smem + (it % stages) * stage_bytes + g * kGroupBytes + r * 128;
+      joint_emit_half(cur, row, r & 7, half * 4, act);
+      if (half == 1) arrive_full(it);
+      cur = nxt;
     }
   }
 };
@@ -146,27 +202,13 @@ __device__ __forceinline__ void store_packed_row32(uint8_t* packed, int row_bloc
     *reinterpret_cast<uint4*>(blk + block_chunk_offset(r, c0 + c)) = out;
   }
 }
-// transposed: element (row = n + j, k = k_glob) for j < 32
-__device__ __forceinline__ void store_packed_col32(uint8_t* packed, int row_blocks, int n, int64_t k_glob,
-                                                   const float (&x)[32]) {
-  const int kb = (int)(k_glob >> 6), k = (int)(k_glob & 63);
-  const int rb = n >> 7;  // n is a multiple of 32: the 32 rows share a row block
-  uint8_t* blk = packed + packed_block_index(rb, kb, row_blocks) * kBlockBytes;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    *reinterpret_cast<__nv_bfloat16*>(blk + block_elem_offset((n & 127) + j, k)) = __float2bfloat16(x[j]);
-  }
-}
-
-// hidden = acc + b1 -> Hp (rows m, K i) and HTp (rows i, K m)
+// hidden = acc + b1 -> Hp (rows m, cols i)
 struct HiddenEpi {
   const float* b1;
   int I;
   int64_t M;
   uint8_t* Hp;
   int h_row_blocks;
-  uint8_t* HTp;
-  int ht_row_blocks;
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
   __device__ void end(State&, const EpiCtx&) const {}
@@ -176,7 +218,6 @@ struct HiddenEpi {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = (live && n + j < I) ? acc[j] + __ldg(b1 + n + j) : 0.f;
     store_packed_row32(Hp, h_row_blocks, ctx.m, n, x);
-    store_packed_col32(HTp, ht_row_blocks, n, ctx.m, x);
   }
 };
 
@@ -266,10 +307,8 @@ struct GradEpi {
   int64_t row0, M;
   int TR, V, blank;
   float clamp;
-  uint8_t* Gp;   // rows = chunk-local m, K = v (g_k_blocks blocks of 64: only ceil(V/64), not Vp/64)
-  int g_row_blocks, g_k_blocks;
-  uint8_t* GTp;  // rows = v, K = chunk-local m
-  int gt_row_blocks;
+  uint8_t* Gp;   // rows = chunk-local m, cols = v (Vp / 64 column blocks)
+  int g_row_blocks;
   float* db2;
   struct State { float l, ox, oy, cf; int csym; bool live; };
   __device__ void begin(State& st, const EpiCtx& ctx) const {
@@ -302,21 +341,18 @@ struct GradEpi {
       }
       x[j] = val;
     }
-    if ((n >> 6) < g_k_blocks) store_packed_row32(Gp, g_row_blocks, ctx.m, n, x);
-    store_packed_col32(GTp, gt_row_blocks, n, ctx.m, x);
+    store_packed_row32(Gp, g_row_blocks, ctx.m, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
     if (n + lane < V && cs != 0.f) atomicAdd(db2 + n + lane, cs);
   }
 };
 
-// dhidden -> DHp (rows chunk-local m, K i), DHTp (rows i, K chunk-local m), db1
+// dhidden -> DHp (rows chunk-local m, cols i), db1
 struct DHiddenEpi {
   int I;
   uint8_t* DHp;
   int dh_row_blocks;
-  uint8_t* DHTp;
-  int dht_row_blocks;
   float* db1;
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
@@ -326,7 +362,6 @@ struct DHiddenEpi {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = (n + j < I) ? acc[j] : 0.f;
     store_packed_row32(DHp, dh_row_blocks, ctx.m, n, x);
-    store_packed_col32(DHTp, dht_row_blocks, n, ctx.m, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
     if (n + lane < I && cs != 0.f) atomicAdd(db1 + n + lane, cs);
@@ -402,7 +437,7 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.kbI = d.Ip / 64;
   d.n_tiles_v = d.Vp / 256;
   const size_t budget = (size_t)1 << 30;  // bytes of one orientation of the chunk's G
-  int64_t rows = (int64_t)(budget / ((size_t)d.kbV * 64 * 2));
+  int64_t rows = (int64_t)(budget / ((size_t)d.Vp * 2));
   rows = (rows / 128) * 128;
   if (rows < 128) rows = 128;
   int64_t all = (int64_t)d.Mt * 128;
@@ -418,8 +453,8 @@ struct TcWs {
   float* sym_logit;
   float* blank_logit;
   uint8_t *W1p, *W2p, *W2Tp, *W1Tp;
-  uint8_t *Hp, *HTp;
-  uint8_t *Gp, *GTp, *DHp, *DHTp;
+  uint8_t* Hp;
+  uint8_t *Gp, *DHp;
   size_t bytes;
 };
 
@@ -431,7 +466,6 @@ TcWs tc_carve(void* ws, const TcDims& d) {
     p += (n + 1023) / 1024 * 1024;
     return q;
   };
-  const size_t rows_all = (size_t)d.Mt * 128;
   const int ct = (int)(d.chunk / 128);
   w.am_off = (int64_t*)take(d.M * sizeof(int64_t));
   w.lm_off = (int64_t*)take(d.M * sizeof(int64_t));
@@ -444,11 +478,8 @@ TcWs tc_carve(void* ws, const TcDims& d) {
   w.W2p = (uint8_t*)take((size_t)(d.Vp / 128) * d.kbI * kBlockBytes);
   w.W1Tp = (uint8_t*)take((size_t)(d.Vp / 128) * d.kbI * kBlockBytes);
   w.Hp = (uint8_t*)take((size_t)d.Mt * d.kbI * kBlockBytes);
-  w.HTp = (uint8_t*)take((size_t)(d.Ip / 128) * (rows_all / 64) * kBlockBytes);
-  w.Gp = (uint8_t*)take((size_t)ct * d.kbV * kBlockBytes);
-  w.GTp = (uint8_t*)take((size_t)(d.Vp / 128) * (d.chunk / 64) * kBlockBytes);
+  w.Gp = (uint8_t*)take((size_t)ct * (d.Vp / 64) * kBlockBytes);
   w.DHp = (uint8_t*)take((size_t)ct * d.kbI * kBlockBytes);
-  w.DHTp = (uint8_t*)take((size_t)(d.Ip / 128) * (d.chunk / 64) * kBlockBytes);
   w.bytes = (size_t)(p - (char*)ws);
   return w;
 }
@@ -491,8 +522,8 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   // hidden: M x Ip, K = V
   {
     JointRowProducer a{p.am, p.lm, w.am_off, w.lm_off, M, p.V, p.act};
-    HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt, w.HTp, d.Ip / 128};
-    if (int rc = launch_gemm_stream<256, 3>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
+    HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt};
+    if (int rc = launch_gemm_stream<256, 3, false>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
                                             "tc_joiner_hidden_gemm"))
       return rc;
   }
@@ -500,8 +531,8 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     BulkA a{w.Hp, d.Mt};
     LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_tiles_v, M, w.part, w.sym_logit, w.blank_logit};
-    if (int rc = launch_gemm_stream<256, 3>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
-                                            "tc_joiner_logits_lse_gemm"))
+    if (int rc = launch_gemm_stream<256, 3, false>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
+                                                   "tc_joiner_logits_lse_gemm"))
       return rc;
   }
   {
@@ -528,47 +559,45 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     const int ct = (int)(rows_pad / 128);       // row tiles of this chunk
     const int kbM = (int)(rows_pad / 64);       // K blocks when rows are the contraction index
     const int tile0 = (int)(row0 / 128);
-    // G = d loss / d logits of the chunk, both orientations (+ db2)
+    // G = d loss / d logits of the chunk (+ db2)
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
-      GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp,
-                 w.Gp, ct, d.kbV, w.GTp, d.Vp / 128, db2};
-      if (int rc = launch_gemm_stream<256, 3>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
-                                              "tc_joiner_grad_logits_gemm"))
+      GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
+      if (int rc = launch_gemm_stream<256, 3, false>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+                                                     "tc_joiner_grad_logits_gemm"))
         return rc;
     }
     // dhidden = G W2: rows m, N = Ip, K = V
     {
       BulkA a{w.Gp, ct};
-      DHiddenEpi ep{p.I, w.DHp, ct, w.DHTp, d.Ip / 128, db1};
-      if (int rc = launch_gemm_stream<256, 3>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
-                                              "tc_joiner_dhidden_gemm"))
+      DHiddenEpi ep{p.I, w.DHp, ct, db1};
+      if (int rc = launch_gemm_stream<256, 3, false>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
+                                                     "tc_joiner_dhidden_gemm"))
         return rc;
     }
     const int splits = max(1, min(kbM, sms / max(1, (d.Vp / 128) * (d.Ip / 256))));
-    // dW2[v, i] += sum_m G[m, v] hidden[m, i]: rows v, N = Ip, K = chunk rows
+    // dW2[v, i] += sum_m G[m, v] hidden[m, i]: both operands MN-major (contraction over the rows m)
     {
-      BulkA a{w.GTp, d.Vp / 128};
-      const uint8_t* ht = w.HTp + (size_t)(row0 / 64) * (d.Ip / 128) * kBlockBytes;  // K offset of the chunk
+      BulkA a{w.Gp, ct};
       StoreRowMajorEpi ep{dW2, p.I, p.V, p.I, true};
-      if (int rc = launch_gemm_stream<256, 3>(a, ht, d.Ip / 128, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
-                                              "tc_joiner_dW2_gemm"))
+      if (int rc = launch_gemm_stream<256, 3, true>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / 256,
+                                                    kbM, splits, ep, stream, "tc_joiner_dW2_gemm"))
         return rc;
     }
-    // dW1[i, v] += sum_m dhidden[m, i] act(.)[m, v]: accumulator rows v, N = Ip, K = chunk rows
+    // dW1[i, v] += sum_m dhidden[m, i] act(.)[m, v]: accumulator rows v (A built on the fly), cols i
     {
-      JointColProducer a{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act};
+      JointMnProducer a{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act};
       StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
-      if (int rc = launch_gemm_stream<256, 3>(a, w.DHTp, d.Ip / 128, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
-                                              "tc_joiner_dW1_gemm"))
+      if (int rc = launch_gemm_stream<256, 3, true>(a, w.DHp, ct, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
+                                                    "tc_joiner_dW1_gemm"))
         return rc;
     }
     // dJ = (dhidden W1) * act' -> d_am, d_lm: rows m, N = Vp, K = Ip
     {
       BulkA a{w.DHp, ct};
       DJointEpi ep{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act, d_am, d_lm};
-      if (int rc = launch_gemm_stream<256, 3>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
-                                              "tc_joiner_djoint_gemm"))
+      if (int rc = launch_gemm_stream<256, 3, false>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+                                                     "tc_joiner_djoint_gemm"))
         return rc;
     }
   }

@@ -1,23 +1,35 @@
 // bf16 x bf16 -> fp32 contractions on the 5th-generation tensor cores.
 //
-//     C[m, n] (+)= sum_k A[m, k] * B[n, k]
+//     K-major  (kMn = false):  C[m, n] (+)= sum_k A[m, k]  * B[n, k]     operands stored (rows, K)
+//     MN-major (kMn = true):   C[m, n] (+)= sum_k At[k, m] * Bt[k, n]    operands stored (K, rows)
 //
 // One CTA owns a 128 x BN output tile whose accumulator lives in TMEM; a single elected thread
-// issues tcgen05.mma (M=128, N=BN, K=16) over 64-wide K blocks that arrive in shared memory
+// issues tcgen05.mma (M=128, N=BN, K=16) over 64-deep K steps that arrive in shared memory
 // through a kStages-deep mbarrier ring.  Warp roles (192 threads):
 //   warp 0      bulk-copy issuer (cp.async.bulk, TMA engine) for the packed operands
 //   warp 1      TMEM allocation + MMA issue + commits
-//   warps 2..5  (a) optional on-the-fly A producer -- each thread builds one 128-byte row of the
-//               A block (e.g. act(am + lm[ranges]) -> bf16) directly in the swizzled smem image,
-//               so the operand never exists in HBM;  (b) epilogue: tcgen05.ld the accumulator
-//               (one TMEM lane = one output row per thread) and hand 32-column chunks to the
-//               epilogue functor.
-// B is always a packed operand (tc_prims.cuh); A is packed (BulkA) or produced.
+//   warps 2..5  (a) optional on-the-fly A producer -- the threads build the A stage (e.g.
+//               act(am + lm[ranges]) -> bf16) directly in the swizzled smem image, so the operand
+//               never exists in HBM;  (b) epilogue: tcgen05.ld the accumulator (one TMEM lane = one
+//               output row per thread) and hand 32-column chunks to the epilogue functor.
+//
+// Both modes read the SAME packed format (tc_prims.cuh): 128 x 64 blocks, 128 B per row, 16-byte
+// chunks XOR-swizzled by (row & 7).  For a K-major operand the block rows are the operand's
+// M/N index; for an MN-major operand the block rows are the contraction index and the 64
+// columns one "group" of the M/N index, so an activation written once as (rows = m, cols = i)
+// serves as K-major A of a row-wise contraction AND as MN-major operand of a reduction over m
+// (the weight-gradient contractions) without a transposed copy.
+//
+// smem stage layout
+//   K-major :  A block [128 rows x 128 B]            | B blocks [BN rows x 128 B]
+//   MN-major:  A groups 2 x [64 k-rows x 128 B]      | B groups (BN/64) x [64 k-rows x 128 B]
 //
 // Functor contracts
-//   struct ASrc { static constexpr bool kBulk; ...
-//       // kBulk:  const uint8_t* packed; int row_blocks;
-//       // !kBulk: __device__ void produce(uint8_t* block, int m_tile, int kb, int t) const;  t in [0,128)
+//   struct ASrc { static constexpr bool kBulk;
+//       // kBulk : const uint8_t* packed; int row_blocks;   (row blocks of the packed array)
+//       // !kBulk: template <class W, class A> __device__ void run(uint8_t* smem, int stage_bytes, int stages,
+//       //             int m_tile, int ks0, int n_it, int t, W wait_empty, A arrive_full) const;
+//       //         must, for it in [0, n_it): wait_empty(it); fill stage it % stages; arrive_full(it).
 //   };
 //   struct Epi {
 //     struct State {...};                       // per-thread (= per output row) running state
@@ -37,7 +49,7 @@ namespace tc {
 
 struct EpiCtx {
   int m;        // global output row of this thread
-  int t;        // epilogue thread index, 0..127 (row inside the tile = quarter * 32 + lane)
+  int t;        // epilogue thread index, 0..127
   int row;      // row inside the 128-row tile
   int m_tile, n_tile, split;
   uint8_t* scratch;
@@ -50,20 +62,37 @@ struct BulkA {
   static constexpr bool kBulk = true;
   const uint8_t* packed;
   int row_blocks;
-  __device__ void produce(uint8_t*, int, int, int) const {}
 };
 
 constexpr int kGemmThreads = 192;
+constexpr int kGroupBytes = 64 * 128;  // one MN-major group: 64 k-rows x 64 elements
 
 template <int BN, int kStages>
 constexpr size_t gemm_stream_smem_bytes() {
   return (size_t)kStages * (kBlockBytes + (BN / 128) * kBlockBytes) + 1024 /*align*/ + 256 /*barriers*/;
 }
 
-template <int BN, int kStages, class ASrc, class Epi>
+// MN-major smem descriptor: 8-row (K) groups 1024 B apart, 64-element (MN) groups lbo_bytes apart
+__device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can probe the encoding)
+  uint32_t lbo_bytes = kGroupBytes;
+  uint32_t sbo_bytes = 1024;
+  uint32_t k_advance_bytes = 2048;  // 16 k-rows
+};
+
+template <int BN, int kStages, bool kMn, class ASrc, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int k_blocks, int k_splits,
-                   Epi epi) {
+gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int k_steps, int k_splits,
+                   Epi epi, MnDebug mn) {
   static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
   constexpr int kABytes = kBlockBytes;
   constexpr int kBBytes = (BN / 128) * kBlockBytes;
@@ -78,10 +107,10 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
-  const int per = (k_blocks + k_splits - 1) / k_splits;
-  const int kb0 = split * per;
-  const int kb1 = min(k_blocks, kb0 + per);
-  const int n_it = kb1 - kb0;
+  const int per = (k_steps + k_splits - 1) / k_splits;
+  const int ks0 = split * per;
+  const int ks1 = min(k_steps, ks0 + per);
+  const int n_it = ks1 - ks0;
   if (n_it <= 0) return;
 
   if (threadIdx.x == 0) {
@@ -101,22 +130,42 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < n_it; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1, kb = kb0 + it;
+        const int s = it % kStages, ph = (it / kStages) & 1, ks = ks0 + it;
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
         mbar_arrive_expect_tx(&full[s], (ASrc::kBulk ? kABytes : 0) + kBBytes);
-        if constexpr (ASrc::kBulk) {
-          bulk_copy_g2s(sa, asrc.packed + packed_block_index(m_tile, kb, asrc.row_blocks) * kBlockBytes, kABytes,
-                        &full[s]);
+        if constexpr (!kMn) {
+          if constexpr (ASrc::kBulk) {
+            bulk_copy_g2s(sa, asrc.packed + packed_block_index(m_tile, ks, asrc.row_blocks) * kBlockBytes, kABytes,
+                          &full[s]);
+          }
+          bulk_copy_g2s(sb, b_packed + packed_block_index(n_tile * (BN / 128), ks, b_row_blocks) * kBlockBytes,
+                        kBBytes, &full[s]);
+        } else {
+          // k-step ks = 64 contraction rows = half of row block ks >> 1; group g = 64 columns = column block
+          const size_t half = (size_t)(ks & 1) * kGroupBytes;
+          if constexpr (ASrc::kBulk) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              bulk_copy_g2s(sa + g * kGroupBytes,
+                            asrc.packed + packed_block_index(ks >> 1, m_tile * 2 + g, asrc.row_blocks) * kBlockBytes + half,
+                            kGroupBytes, &full[s]);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g) {
+            bulk_copy_g2s(sb + g * kGroupBytes,
+                          b_packed + packed_block_index(ks >> 1, n_tile * (BN / 64) + g, b_row_blocks) * kBlockBytes + half,
+                          kGroupBytes, &full[s]);
+          }
         }
-        bulk_copy_g2s(sb, b_packed + packed_block_index(n_tile * (BN / 128), kb, b_row_blocks) * kBlockBytes,
-                      kBBytes, &full[s]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, BN);
+      uint32_t idesc = umma_idesc_bf16(128, BN);
+      if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       for (int it = 0; it < n_it; ++it) {
         const int s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&full[s], ph);
@@ -125,8 +174,15 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         const uint32_t sb = sa + kABytes;
 #pragma unroll
         for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-          umma_bf16(tmem_base, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc,
-                    (it > 0) || (k4 > 0));
+          uint64_t da, db;
+          if constexpr (!kMn) {
+            da = umma_smem_desc(sa + k4 * kUmmaK * 2);
+            db = umma_smem_desc(sb + k4 * kUmmaK * 2);
+          } else {
+            da = umma_smem_desc_mn(sa + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
+            db = umma_smem_desc_mn(sb + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
+          }
+          umma_bf16(tmem_base, da, db, idesc, (it > 0) || (k4 > 0));
         }
         umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
       }
@@ -135,13 +191,13 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   } else {
     const int t = (warp - 2) * 32 + lane;
     if constexpr (!ASrc::kBulk) {
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1, kb = kb0 + it;
-        mbar_wait(&empty[s], ph ^ 1);
-        asrc.produce(smem + s * kStageBytes, m_tile, kb, t);
-        fence_proxy_async_smem();
-        mbar_arrive(&full[s]);
-      }
+      asrc.run(
+          smem, kStageBytes, kStages, m_tile, ks0, n_it, t,
+          [&](int it) { mbar_wait(&empty[it % kStages], ((it / kStages) & 1) ^ 1); },
+          [&](int it) {
+            fence_proxy_async_smem();
+            mbar_arrive(&full[it % kStages]);
+          });
     }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
@@ -170,13 +226,14 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   if (warp == 1) tmem_dealloc<BN>(tmem_base);
 }
 
-template <int BN, int kStages, class ASrc, class Epi>
+template <int BN, int kStages, bool kMn, class ASrc, class Epi>
 int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
-                       int k_blocks, int k_splits, const Epi& epi, cudaStream_t stream, const char* what) {
-  if (m_tiles <= 0 || n_tiles <= 0 || k_blocks <= 0) return 0;
+                       int k_steps, int k_splits, const Epi& epi, cudaStream_t stream, const char* what,
+                       MnDebug mn = MnDebug()) {
+  if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0) return 0;
   if (k_splits < 1) k_splits = 1;
-  if (k_splits > k_blocks) k_splits = k_blocks;
-  auto kern = gemm_stream_kernel<BN, kStages, ASrc, Epi>;
+  if (k_splits > k_steps) k_splits = k_steps;
+  auto kern = gemm_stream_kernel<BN, kStages, kMn, ASrc, Epi>;
   constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages>();
   static bool configured = false;
   if (!configured) {
@@ -190,7 +247,7 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
   dim3 grid(n_tiles, m_tiles, k_splits);
   S2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", what);
   ProfScope prof(what, stream);
-  kern<<<grid, kGemmThreads, smem, stream>>>(asrc, b_packed, b_row_blocks, k_blocks, k_splits, epi);
+  kern<<<grid, kGemmThreads, smem, stream>>>(asrc, b_packed, b_row_blocks, k_steps, k_splits, epi, mn);
   return check_launch(what);
 }
 

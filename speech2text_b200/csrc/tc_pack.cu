@@ -82,9 +82,35 @@ extern "C" int s2t_tc_gemm(const float* A, const float* B, float* C, int M, int 
   if (k_splits > 1) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
   tc::StoreRowMajorEpi epi{C, N, M, N, k_splits > 1};
   if (bn == 128) {
-    return tc::launch_gemm_stream<128, 4>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
+    return tc::launch_gemm_stream<128, 4, false>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
                                           "tc_gemm_debug_128");
   }
-  return tc::launch_gemm_stream<256, 3>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
+  return tc::launch_gemm_stream<256, 3, false>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
                                         "tc_gemm_debug_256");
+}
+
+// Debug / test entry for MN-major operands: C (M x N) = At^T Bt with At (K x M), Bt (K x N) fp32 row-major.
+extern "C" size_t s2t_tc_gemm_mn_workspace_bytes(int M, int N, int K) {
+  const int rb = (K + 127) / 128;
+  return (size_t)rb * (((M + 127) / 128) * 2 + ((N + 255) / 256) * 4) * tc::kBlockBytes + 256;
+}
+
+extern "C" int s2t_tc_gemm_mn(const float* At, const float* Bt, float* C, int M, int N, int K, int k_splits,
+                              unsigned lbo, unsigned sbo, unsigned kadv, void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rb = (K + 127) / 128;
+  const int a_groups = ((M + 127) / 128) * 2, b_groups = ((N + 255) / 256) * 4;
+  uint8_t* pa = (uint8_t*)ws;
+  uint8_t* pb = pa + (size_t)rb * a_groups * tc::kBlockBytes;
+  if (int rc = tc::pack_operand(At, M, 1, K, M, rb, a_groups, pa, st)) return rc;
+  if (int rc = tc::pack_operand(Bt, N, 1, K, N, rb, b_groups, pb, st)) return rc;
+  tc::BulkA a{pa, rb};
+  if (k_splits > 1) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
+  tc::StoreRowMajorEpi epi{C, N, M, N, k_splits > 1};
+  tc::MnDebug mn;
+  if (lbo) mn.lbo_bytes = lbo;
+  if (sbo) mn.sbo_bytes = sbo;
+  if (kadv) mn.k_advance_bytes = kadv;
+  return tc::launch_gemm_stream<256, 3, true>(a, pb, rb, (M + 127) / 128, (N + 255) / 256, (K + 63) / 64, k_splits, epi,
+                                              st, "tc_gemm_mn_debug", mn);
 }
