@@ -368,8 +368,14 @@ struct DHiddenEpi {
   }
 };
 
-// dJ = (dhidden W1)[m, v] * act'(am + lm) scattered into d_am / d_lm
+// dJ = (dhidden W1)[m, v] * act'(am + lm) reduced into d_am / d_lm.
+// The 128 rows of a tile touch few distinct am rows (128/R frames) and lm rows (the band moves
+// slowly).  Once per tile the rows are bucketed by am-row and by lm-row (counting sort in the idle
+// operand ring); every 32-column chunk is then staged in shared memory, summed per bucket without
+// atomics, and only the per-bucket sums go to global memory: ~(128/R + band rows) * 32 atomics
+// per chunk instead of 2 * 128 * 32.
 struct DJointEpi {
+  static constexpr int kSlotsA = 128, kSlotsL = 128, kLd = 33;
   const float* am;
   const float* lm;
   const int64_t* am_off;
@@ -378,27 +384,110 @@ struct DJointEpi {
   int V, act;
   float* d_am;
   float* d_lm;
-  struct State { int64_t ao, lo; bool live; };
+  struct Scratch {
+    float dj[128 * kLd];
+    int64_t red[8];
+    int cnt[2][128], start[2][128];
+    int order[2][128];
+    int n_slots[2];
+  };
+  struct State {
+    int64_t ao, lo;
+    int64_t a_row0, l_row0;
+    bool live, direct;
+  };
   __device__ void begin(State& st, const EpiCtx& ctx) const {
+    Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
     const int64_t m = row0 + ctx.m;
+    const int lane = ctx.t & 31, w = ctx.t >> 5;
     st.live = m < M;
     st.ao = st.live ? am_off[m] : 0;
     st.lo = st.live ? lm_off[m] : 0;
+    // tile-wide minimum am / lm row ids
+    int64_t ka = st.live ? st.ao / V : INT64_MAX, kl = st.live ? st.lo / V : INT64_MAX;
+    int64_t ra = ka, rl = kl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      int64_t oa = __shfl_xor_sync(0xffffffffu, ra, o), ol = __shfl_xor_sync(0xffffffffu, rl, o);
+      ra = oa < ra ? oa : ra;
+      rl = ol < rl ? ol : rl;
+    }
+    if (lane == 0) {
+      sc.red[w] = ra;
+      sc.red[4 + w] = rl;
+    }
+    sc.cnt[0][ctx.t] = 0;
+    sc.cnt[1][ctx.t] = 0;
+    epi_sync();
+    ra = sc.red[0];
+    rl = sc.red[4];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+      ra = sc.red[i] < ra ? sc.red[i] : ra;
+      rl = sc.red[4 + i] < rl ? sc.red[4 + i] : rl;
+    }
+    st.a_row0 = ra;
+    st.l_row0 = rl;
+    const int64_t sa = st.live ? ka - ra : 0, sl = st.live ? kl - rl : 0;
+    st.direct = st.live && (sa >= kSlotsA || sl >= kSlotsL);  // far-apart rows: straight to global
+    int pa = 0, pl = 0;
+    const bool bucket = st.live && !st.direct;
+    if (bucket) {
+      pa = atomicAdd(&sc.cnt[0][(int)sa], 1);
+      pl = atomicAdd(&sc.cnt[1][(int)sl], 1);
+    }
+    epi_sync();
+    if (ctx.t < 2) {  // exclusive scans (128 entries each, once per tile)
+      int run = 0, last = 0;
+      for (int i = 0; i < 128; ++i) {
+        sc.start[ctx.t][i] = run;
+        run += sc.cnt[ctx.t][i];
+        if (sc.cnt[ctx.t][i]) last = i + 1;
+      }
+      sc.n_slots[ctx.t] = last;
+    }
+    epi_sync();
+    if (bucket) {
+      sc.order[0][sc.start[0][(int)sa] + pa] = ctx.t;
+      sc.order[1][sc.start[1][(int)sl] + pl] = ctx.t;
+    }
+    epi_sync();
   }
   __device__ void end(State&, const EpiCtx&) const {}
-  __device__ void chunk(State& st, const EpiCtx&, int n, const float (&acc)[32]) const {
-    if (!st.live) return;
+  __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
+    float* mine = sc.dj + ctx.t * kLd;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int v = n + j;
-      if (v < V && acc[j] != 0.f) {
-        float dj = acc[j] * act_bwd_fast(__ldg(am + st.ao + v) + __ldg(lm + st.lo + v), act);
-        if (dj != 0.f) {
+      float dj = 0.f;
+      if (st.live && v < V && acc[j] != 0.f) {
+        dj = acc[j] * act_bwd_fast(__ldg(am + st.ao + v) + __ldg(lm + st.lo + v), act);
+        if (st.direct && dj != 0.f) {
           atomicAdd(d_am + st.ao + v, dj);
           atomicAdd(d_lm + st.lo + v, dj);
+          dj = 0.f;
         }
       }
+      mine[j] = dj;
     }
+    epi_sync();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const int ns = sc.n_slots[which];
+      float* dst = which == 0 ? d_am : d_lm;
+      const int64_t base_row = which == 0 ? st.a_row0 : st.l_row0;
+      for (int i = ctx.t; i < ns * 32; i += 128) {
+        const int slot = i >> 5, j = i & 31;
+        const int c = sc.cnt[which][slot];
+        if (c == 0 || n + j >= V) continue;
+        const int s0 = sc.start[which][slot];
+        float sum = 0.f;
+        for (int k = 0; k < c; ++k) sum += sc.dj[sc.order[which][s0 + k] * kLd + j];
+        if (sum != 0.f) atomicAdd(dst + (base_row + slot) * V + n + j, sum);
+      }
+    }
+    epi_sync();
   }
 };
 
@@ -523,7 +612,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     JointRowProducer a{p.am, p.lm, w.am_off, w.lm_off, M, p.V, p.act};
     HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt};
-    if (int rc = launch_gemm_stream<256, 3, false>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
+    if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
                                             "tc_joiner_hidden_gemm"))
       return rc;
   }
@@ -531,7 +620,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     BulkA a{w.Hp, d.Mt};
     LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_tiles_v, M, w.part, w.sym_logit, w.blank_logit};
-    if (int rc = launch_gemm_stream<256, 3, false>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
+    if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                    "tc_joiner_logits_lse_gemm"))
       return rc;
   }
@@ -563,7 +652,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
-      if (int rc = launch_gemm_stream<256, 3, false>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                      "tc_joiner_grad_logits_gemm"))
         return rc;
     }
@@ -571,7 +660,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Gp, ct};
       DHiddenEpi ep{p.I, w.DHp, ct, db1};
-      if (int rc = launch_gemm_stream<256, 3, false>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
+      if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
                                                      "tc_joiner_dhidden_gemm"))
         return rc;
     }
@@ -580,7 +669,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Gp, ct};
       StoreRowMajorEpi ep{dW2, p.I, p.V, p.I, true};
-      if (int rc = launch_gemm_stream<256, 3, true>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / 256,
+      if (int rc = launch_gemm_stream<256, 3, true, 0>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / 256,
                                                     kbM, splits, ep, stream, "tc_joiner_dW2_gemm"))
         return rc;
     }
@@ -588,7 +677,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       JointMnProducer a{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act};
       StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
-      if (int rc = launch_gemm_stream<256, 3, true>(a, w.DHp, ct, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
+      if (int rc = launch_gemm_stream<256, 3, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
                                                     "tc_joiner_dW1_gemm"))
         return rc;
     }
@@ -596,7 +685,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       DJointEpi ep{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act, d_am, d_lm};
-      if (int rc = launch_gemm_stream<256, 3, false>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                      "tc_joiner_djoint_gemm"))
         return rc;
     }

@@ -1,0 +1,116 @@
+// nn.Linear on the tensor cores for the joiner's D -> V projections
+// (/root/reference/model/joiner/joiner.py:41-42, 148-149: _enc_proj / _pre_proj), fp32 output
+// (the simple loss downstream is fp32).  The forward runs as 3xTF32 (big/small operand split,
+// fp32-level accuracy): am / lm feed the simple-loss lattice whose occupation probabilities pick the
+// prune ranges by an argmax, and any visible perturbation of am / lm (bf16: 2^-9, plain tf32: 2^-11)
+// flips near-tie frames to a neighbouring window.  The backward contractions take bf16 operands.
+//
+//   forward   y = x W^T + b          K-major tf32: A = x copied on the fly, B = fp32 pack(W) (rows n, cols k)
+//   backward  dx = dy W              K-major:  A = pack(dy) (rows m, cols n), B = pack(W^T) (rows k, cols n)
+//             dW = dy^T x            MN-major: the SAME pack(dy) and pack(x), contraction over the rows m
+//             db = column sums of dy
+// pack(x) is written once in the forward call and reused by the backward call (workspace).
+#include "tc_gemm.cuh"
+
+namespace s2t {
+namespace {
+
+using namespace tc;
+
+__global__ void linear_col_sum_kernel(const float* __restrict__ x, int64_t rows, int ld, int N, float* __restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int64_t r0 = (int64_t)blockIdx.y * 512, r1 = min(rows, r0 + 512);
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) acc += x[r * ld + n];
+  atomicAdd(out + n, acc);
+}
+
+struct LinDims {
+  int Mt, Np, Kp;       // row tiles of x; N, K padded to multiples of 256
+  size_t px, pw, pdy, pwt;  // bf16 pack(x), fp32 pack(W), bf16 pack(dy), bf16 pack(W^T)
+};
+
+LinDims lin_dims(int64_t M, int N, int K) {
+  LinDims d;
+  d.Mt = (int)((M + 127) / 128);
+  d.Np = ((N + 255) / 256) * 256;
+  d.Kp = ((K + 255) / 256) * 256;
+  d.px = (size_t)d.Mt * (d.Kp / 64) * kBlockBytes;
+  d.pw = 2 * (size_t)(d.Np / 128) * (d.Kp / 32) * kBlockBytes;  // big | small
+  d.pdy = (size_t)d.Mt * (d.Np / 64) * kBlockBytes;
+  d.pwt = (size_t)(d.Kp / 128) * (d.Np / 64) * kBlockBytes;
+  return d;
+}
+
+}  // namespace
+}  // namespace s2t
+
+using namespace s2t;
+
+extern "C" {
+
+// workspace = [pack(x) | pack(W) | pack(dy) | pack(W^T)]; only pack(x) must survive until backward
+size_t s2t_linear_workspace_bytes(int64_t M, int N, int K) {
+  LinDims d = lin_dims(M, N, K);
+  return d.px + d.pw + d.pdy + d.pwt + 1024;
+}
+
+int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, int N, int K, void* ws, float* y,
+                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) return 0;
+  LinDims d = lin_dims(M, N, K);
+  uint8_t* px = (uint8_t*)ws;
+  uint8_t* pw = px + d.px;
+  if (int rc = tc::pack_operand(x, K, 1, (int)M, K, d.Mt, d.Kp / 64, px, st)) return rc;  // for dW in backward
+  uint8_t* pw_small = pw + d.pw / 2;
+  if (int rc = tc::pack_operand_f32(W, K, N, K, d.Np / 128, d.Kp / 32, 0, pw, st)) return rc;
+  if (int rc = tc::pack_operand_f32(W, K, N, K, d.Np / 128, d.Kp / 32, 1, pw_small, st)) return rc;
+  tc::RowCopyProducerF32 a{x, K, M, K, true};
+  tc::StoreRowMajorEpi ep{y, N, (int)M, N, false, b};
+  tc::MnDebug extra;
+  extra.b_small = pw_small;
+  return tc::launch_gemm_stream<256, 2, false, 2>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 31) / 32, 1, ep, st,
+                                                  "tc_linear_fwd_gemm_3xtf32", extra);
+}
+
+// dx (M,K), dW (N,K), db (N) are overwritten
+int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, void* ws, float* dx, float* dW,
+                   float* db, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) return 0;
+  LinDims d = lin_dims(M, N, K);
+  uint8_t* px = (uint8_t*)ws;
+  uint8_t* pdy = px + d.px + d.pw;
+  uint8_t* pwt = pdy + d.pdy;
+  if (int rc = tc::pack_operand(dy, N, 1, (int)M, N, d.Mt, d.Np / 64, pdy, st)) return rc;
+  // W^T: rows k, cols n -> element (k, n) = W[n * K + k]
+  if (int rc = tc::pack_operand(W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, st)) return rc;
+  if (dx) {
+    tc::BulkA a{pdy, d.Mt};
+    tc::StoreRowMajorEpi ep{dx, K, (int)M, K, false, nullptr};
+    if (int rc = tc::launch_gemm_stream<256, 3, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
+                                                       "tc_linear_dx_gemm"))
+      return rc;
+  }
+  {
+    cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), st);
+    cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
+    const int k_steps = d.Mt * 2;
+    const int tiles = (d.Np / 128) * (d.Kp / 256);
+    int splits = 148 / (tiles > 0 ? tiles : 1);
+    if (splits < 1) splits = 1;
+    tc::BulkA a{pdy, d.Mt};
+    tc::StoreRowMajorEpi ep{dW, K, N, K, true, nullptr};
+    if (int rc = tc::launch_gemm_stream<256, 3, true, 0>(a, px, d.Mt, d.Np / 128, d.Kp / 256, k_steps, splits, ep, st,
+                                                      "tc_linear_dW_gemm"))
+      return rc;
+    ProfScope prof("linear_col_sum_kernel", st);
+    dim3 grid((N + 127) / 128, (unsigned)((M + 511) / 512));
+    linear_col_sum_kernel<<<grid, 128, 0, st>>>(dy, M, N, N, db);
+  }
+  return check_launch("linear_bwd");
+}
+
+}  // extern "C"

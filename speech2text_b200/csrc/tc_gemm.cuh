@@ -67,9 +67,13 @@ struct BulkA {
 constexpr int kGemmThreads = 192;
 constexpr int kGroupBytes = 64 * 128;  // one MN-major group: 64 k-rows x 64 elements
 
-template <int BN, int kStages>
+// kKind: 0 = bf16 operands; 1 = tf32 (fp32 in smem, single pass); 2 = 3xTF32: every fp32 operand is held
+// as big = rn_tf32(x) and small = x - big, and D += A_big B_big + A_big B_small + A_small B_big, which
+// recovers fp32-level accuracy (error ~2^-21) on the tensor cores.
+template <int BN, int kStages, int kKind = 0>
 constexpr size_t gemm_stream_smem_bytes() {
-  return (size_t)kStages * (kBlockBytes + (BN / 128) * kBlockBytes) + 1024 /*align*/ + 256 /*barriers*/;
+  return (size_t)kStages * (kKind == 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes) + 1024 /*align*/ +
+         256 /*barriers*/;
 }
 
 // MN-major smem descriptor: 8-row (K) groups 1024 B apart, 64-element (MN) groups lbo_bytes apart
@@ -87,16 +91,20 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
   uint32_t lbo_bytes = kGroupBytes;
   uint32_t sbo_bytes = 1024;
   uint32_t k_advance_bytes = 2048;  // 16 k-rows
+  const uint8_t* b_small = nullptr;  // kKind == 2: packed residuals of B
 };
 
-template <int BN, int kStages, bool kMn, class ASrc, class Epi>
+template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int k_steps, int k_splits,
                    Epi epi, MnDebug mn) {
   static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
-  constexpr int kABytes = kBlockBytes;
-  constexpr int kBBytes = (BN / 128) * kBlockBytes;
+  constexpr int kParts = kKind == 2 ? 2 : 1;
+  constexpr int kABytes = kParts * kBlockBytes;
+  constexpr int kBPart = (BN / 128) * kBlockBytes;
+  constexpr int kBBytes = kParts * kBPart;
   constexpr int kStageBytes = kABytes + kBBytes;
+  static_assert(kKind != 2 || !ASrc::kBulk, "3xTF32 expects an on-the-fly A producer that writes big|small");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -141,7 +149,11 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
                           &full[s]);
           }
           bulk_copy_g2s(sb, b_packed + packed_block_index(n_tile * (BN / 128), ks, b_row_blocks) * kBlockBytes,
-                        kBBytes, &full[s]);
+                        kBPart, &full[s]);
+          if constexpr (kKind == 2) {
+            bulk_copy_g2s(sb + kBPart, mn.b_small + packed_block_index(n_tile * (BN / 128), ks, b_row_blocks) * kBlockBytes,
+                          kBPart, &full[s]);
+          }
         } else {
           // k-step ks = 64 contraction rows = half of row block ks >> 1; group g = 64 columns = column block
           const size_t half = (size_t)(ks & 1) * kGroupBytes;
@@ -164,7 +176,9 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t idesc = umma_idesc_bf16(128, BN);
+      // kKind 0: bf16 operands (64 per 128-byte row);  1: tf32 (fp32 in smem, 32 per row, K-major only)
+      static_assert(kKind == 0 || !kMn, "tf32 operands are K-major only");
+      uint32_t idesc = kKind == 0 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
       if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       for (int it = 0; it < n_it; ++it) {
         const int s = it % kStages, ph = (it / kStages) & 1;
@@ -182,7 +196,17 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
             da = umma_smem_desc_mn(sa + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
             db = umma_smem_desc_mn(sb + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
           }
-          umma_bf16(tmem_base, da, db, idesc, (it > 0) || (k4 > 0));
+          if constexpr (kKind == 0) {
+            umma_bf16(tmem_base, da, db, idesc, (it > 0) || (k4 > 0));
+          } else if constexpr (kKind == 1) {
+            umma_tf32(tmem_base, da, db, idesc, (it > 0) || (k4 > 0));
+          } else {
+            const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
+            const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
+            umma_tf32(tmem_base, da_s, db, idesc, (it > 0) || (k4 > 0));  // small terms first
+            umma_tf32(tmem_base, da, db_s, idesc, true);
+            umma_tf32(tmem_base, da, db, idesc, true);
+          }
         }
         umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
       }
@@ -226,15 +250,15 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   if (warp == 1) tmem_dealloc<BN>(tmem_base);
 }
 
-template <int BN, int kStages, bool kMn, class ASrc, class Epi>
+template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
 int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                        int k_steps, int k_splits, const Epi& epi, cudaStream_t stream, const char* what,
                        MnDebug mn = MnDebug()) {
   if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0) return 0;
   if (k_splits < 1) k_splits = 1;
   if (k_splits > k_steps) k_splits = k_steps;
-  auto kern = gemm_stream_kernel<BN, kStages, kMn, ASrc, Epi>;
-  constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages>();
+  auto kern = gemm_stream_kernel<BN, kStages, kMn, kKind, ASrc, Epi>;
+  constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, kKind>();
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -258,6 +282,7 @@ struct StoreRowMajorEpi {
   int64_t ldc;
   int M, N;
   bool atomic;
+  const float* bias = nullptr;  // added per column when not atomic
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
   __device__ void end(State&, const EpiCtx&) const {}
@@ -269,7 +294,7 @@ struct StoreRowMajorEpi {
     for (int j = 0; j < 32; ++j) {
       if (n + j < N) {
         if (atomic) atomicAdd(row + n + j, acc[j]);
-        else row[n + j] = acc[j];
+        else row[n + j] = acc[j] + (bias ? __ldg(bias + n + j) : 0.f);
       }
     }
   }
@@ -280,6 +305,65 @@ struct StoreRowMajorEpi {
 // blocks, zero padded beyond (rows, K).
 int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int rows, int K, int row_blocks,
                  int k_blocks, uint8_t* dst, cudaStream_t stream);
+// same block geometry with fp32 elements (32 per 128-byte row) for the tf32 contractions; k_blocks of 32
+// part 0: rn_tf32(x);  part 1: residual x - rn_tf32(x) (itself rounded to tf32)
+int pack_operand_f32(const float* src, int64_t row_stride, int rows, int K, int row_blocks, int k_blocks,
+                     int part, uint8_t* dst, cudaStream_t stream);
+
+// On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage.
+struct RowCopyProducerF32 {
+  static constexpr bool kBulk = false;
+  const float* x;
+  int64_t ld;
+  int64_t M;
+  int K;
+  bool split;  // also write the residual block right after the big block (3xTF32)
+  template <class W, class A>
+  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t,
+                      W wait_empty, A arrive_full) const {
+    const int64_t m = (int64_t)m_tile * 128 + t;
+    const bool live = m < M;
+    const float* row = x + (live ? m * ld : 0);
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    float4 cur[8], nxt[8];
+    auto load = [&](float4 (&dst)[8], int ks) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = ks * 32 + c * 4;
+        if (live && vec && k + 4 <= K) {
+          dst[c] = __ldg(reinterpret_cast<const float4*>(row + k));
+        } else {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = (live && k + j < K) ? __ldg(row + k + j) : 0.f;
+          dst[c] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    };
+    load(cur, ks0);
+    for (int it = 0; it < n_it; ++it) {
+      if (it + 1 < n_it) load(nxt, ks0 + it + 1);
+      wait_empty(it);
+      uint8_t* dst = smem + (it % stages) * stage_bytes + t * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 x4 = cur[c];
+        float4 v;
+        v.x = round_tf32(x4.x); v.y = round_tf32(x4.y); v.z = round_tf32(x4.z); v.w = round_tf32(x4.w);
+        *reinterpret_cast<float4*>(dst + (((c ^ (t & 7)) & 7) << 4)) = v;
+        if (split) {
+          float4 r;
+          r.x = round_tf32(x4.x - v.x); r.y = round_tf32(x4.y - v.y); r.z = round_tf32(x4.z - v.z);
+          r.w = round_tf32(x4.w - v.w);
+          *reinterpret_cast<float4*>(dst + kBlockBytes + (((c ^ (t & 7)) & 7) << 4)) = r;
+        }
+      }
+      arrive_full(it);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+    }
+  }
+};
 
 }  // namespace tc
 }  // namespace s2t

@@ -39,7 +39,39 @@ __global__ void pack_operand_kernel(const float* __restrict__ src, int64_t row_s
   *reinterpret_cast<uint4*>(blk + block_chunk_offset((int)(r % 128), (k0 % 64) / 8)) = out;
 }
 
+// fp32 elements: one thread per 16-byte chunk (4 consecutive k of one row), 32 k per block row
+__global__ void pack_operand_f32_kernel(const float* __restrict__ src, int64_t row_stride, int rows, int K,
+                                        int row_blocks, int k_blocks, int part, uint8_t* __restrict__ dst) {
+  const int64_t total = (int64_t)row_blocks * 128 * k_blocks * 8;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t ck = i % ((int64_t)k_blocks * 8);
+  const int64_t r = i / ((int64_t)k_blocks * 8);
+  const int k0 = (int)ck * 4;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = (r < rows && k0 + j < K) ? __ldg(src + r * row_stride + k0 + j) : 0.f;
+    float big = round_tf32(x);
+    v[j] = part == 0 ? big : round_tf32(x - big);
+  }
+  const int rb = (int)(r / 128), kb = k0 / 32;
+  uint8_t* blk = dst + packed_block_index(rb, kb, row_blocks) * kBlockBytes;
+  *reinterpret_cast<float4*>(blk + block_chunk_offset((int)(r % 128), (k0 % 32) / 4)) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 }  // namespace
+
+int pack_operand_f32(const float* src, int64_t row_stride, int rows, int K, int row_blocks, int k_blocks,
+                     int part, uint8_t* dst, cudaStream_t stream) {
+  S2T_REQUIRE(row_blocks * 128 >= rows && k_blocks * 32 >= K, "pack_operand_f32: padded dims too small");
+  const int64_t total = (int64_t)row_blocks * 128 * k_blocks * 8;
+  if (total == 0) return 0;
+  ProfScope prof("pack_operand_kernel", stream);
+  pack_operand_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, row_stride, rows, K, row_blocks,
+                                                                               k_blocks, part, dst);
+  return check_launch("pack_operand_f32_kernel");
+}
 
 int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int rows, int K, int row_blocks,
                  int k_blocks, uint8_t* dst, cudaStream_t stream) {
@@ -82,10 +114,10 @@ extern "C" int s2t_tc_gemm(const float* A, const float* B, float* C, int M, int 
   if (k_splits > 1) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
   tc::StoreRowMajorEpi epi{C, N, M, N, k_splits > 1};
   if (bn == 128) {
-    return tc::launch_gemm_stream<128, 4, false>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
+    return tc::launch_gemm_stream<128, 4, false, 0>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
                                           "tc_gemm_debug_128");
   }
-  return tc::launch_gemm_stream<256, 3, false>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
+  return tc::launch_gemm_stream<256, 3, false, 0>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
                                         "tc_gemm_debug_256");
 }
 
@@ -111,6 +143,6 @@ extern "C" int s2t_tc_gemm_mn(const float* At, const float* Bt, float* C, int M,
   if (lbo) mn.lbo_bytes = lbo;
   if (sbo) mn.sbo_bytes = sbo;
   if (kadv) mn.k_advance_bytes = kadv;
-  return tc::launch_gemm_stream<256, 3, true>(a, pb, rb, (M + 127) / 128, (N + 255) / 256, (K + 63) / 64, k_splits, epi,
+  return tc::launch_gemm_stream<256, 3, true, 0>(a, pb, rb, (M + 127) / 128, (N + 255) / 256, (K + 63) / 64, k_splits, epi,
                                               st, "tc_gemm_mn_debug", mn);
 }

@@ -308,3 +308,39 @@ def joiner_materialize(am: Tensor, lm: Tensor, W1, b1, W2, b2, ranges: Optional[
     check(lib().s2t_joiner_materialize(mode, ptr(am), ptr(lm), ptr(ranges), ptr(W1), ptr(b1), ptr(W2), ptr(b2),
                                        B, T, S, R, V, I, act, ptr(workspace), ptr(logits), stream()))
     return logits
+
+
+# ---------------------------------------------------------------------------
+# nn.Linear on the tensor cores (joiner projections, bf16 mode)
+# ---------------------------------------------------------------------------
+class _LinearTC(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x: Tensor, W: Tensor, b: Tensor):
+        lead = x.shape[:-1]
+        K = x.shape[-1]
+        x2 = _f32c(x).reshape(-1, K)
+        W, b = _f32c(W), _f32c(b)
+        M, N = x2.shape[0], W.shape[0]
+        ws = torch.empty((lib().s2t_linear_workspace_bytes(M, N, K),), dtype=torch.uint8, device=x.device)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        check(lib().s2t_linear_fwd(ptr(x2), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y), stream()))
+        ctx.save_for_backward(W, ws)
+        ctx.dims = (M, N, K, lead, x.requires_grad)
+        return y.reshape(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        W, ws = ctx.saved_tensors
+        M, N, K, lead, need_dx = ctx.dims
+        dy2 = _f32c(dy).reshape(M, N)
+        dx = torch.empty((M, K), dtype=torch.float32, device=dy.device) if need_dx else None
+        dW = torch.empty_like(W)
+        db = torch.empty((N,), dtype=torch.float32, device=dy.device)
+        check(lib().s2t_linear_bwd(ptr(dy2), ptr(W), M, N, K, ptr(ws), ptr(dx), ptr(dW), ptr(db), stream()))
+        return (dx.reshape(*lead, K) if need_dx else None), dW, db
+
+
+def linear_tc(x: Tensor, W: Tensor, b: Tensor) -> Tensor:
+    """``F.linear(x, W, b)`` with bf16 operands / fp32 accumulation on tcgen05; fp32 in, fp32 out."""
+    return _LinearTC.apply(x, W, b)

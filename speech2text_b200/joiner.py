@@ -197,8 +197,13 @@ class Joiner(nn.Module):
             raise _lib.S2TError("speech2text_b200.Joiner.forward needs CUDA tensors: this build has no "
                                 "CPU path (streaming_step and the ONNX exports are plain torch).")
         # Project both encoder_out and predictor_out into vocab_size
-        am = self._enc_proj(encoder_out)
-        lm = self._pre_proj(predict_out)
+        mode = _mode_from_env()
+        if mode == _lib.MODE_BF16_TC and os.environ.get("S2T_B200_PROJ_TC", "1") != "0":
+            am = F2.linear_tc(encoder_out, self._enc_proj.weight, self._enc_proj.bias)
+            lm = F2.linear_tc(predict_out, self._pre_proj.weight, self._pre_proj.bias)
+        else:
+            am = self._enc_proj(encoder_out)
+            lm = self._pre_proj(predict_out)
 
         if self.prune_range > 0:
             assert target.shape[0] == target_lengths.shape[0]
@@ -213,7 +218,7 @@ class Joiner(nn.Module):
         W1, b1, W2, b2 = self._out_proj_params()
         fused = os.environ.get("S2T_B200_FUSED", "1") != "0"
         if fused:
-            output = LazyJoinerLogits(am, lm, W1, b1, W2, b2, ranges, self._act_code, _mode_from_env())
+            output = LazyJoinerLogits(am, lm, W1, b1, W2, b2, ranges, self._act_code, mode)
         else:
             # the reference's own materialising ops (joiner.py:121-123, 166-178)
             if ranges is not None:
