@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/s2t_b200.h"
 #include "joiner.cuh"
@@ -96,6 +97,9 @@ static LatticeView band_view(const float* px, const float* py, const int64_t* ra
 
 static int band_dp(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary, int B, int S,
                    int T, int R, void* alpha, float* scores, float* occ_px, float* occ_py, cudaStream_t st) {
+  if (band_lattice_fast_ok(S, T, R) && !getenv("S2T_B200_GENERIC_DP")) {
+    return launch_band_lattice_fast(px, py, ranges, boundary, B, S, T, R, scores, occ_px, occ_py, st);
+  }
   LatticeView v = band_view(px, py, ranges, boundary, B, S, T, R, alpha);
   size_t n = (size_t)B * T * R * sizeof(float);
   cudaMemsetAsync(occ_px, 0, n, st);
@@ -128,6 +132,11 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
                            void* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(B >= 0 && S >= 0 && T >= 0, "mutual_information: negative dimension");
+  if (simple_lattice_fast_ok(S) && !getenv("S2T_B200_GENERIC_DP")) {
+    const bool grads = px_grad != nullptr && py_grad != nullptr;
+    return launch_simple_lattice_fast(px, py, boundary, B, S, T, alpha_ws, scores, grads ? px_grad : nullptr,
+                                      grads ? py_grad : nullptr, st);
+  }
   LatticeView v = simple_view(px, py, boundary, B, S, T, alpha_ws);
   if (px_grad == nullptr || py_grad == nullptr) return launch_lattice_fwd(v, scores, st);
   cudaMemsetAsync(px_grad, 0, (size_t)B * S * (T + 1) * sizeof(float), st);
@@ -184,7 +193,9 @@ int s2t_logits_loss_bwd(const void* logits, int dtype, const int64_t* symbols, c
 }
 
 size_t s2t_lattice_workspace_bytes(int B, int S, int T, int slots) {
-  return lattice_workspace_bytes(B, S, T, slots);
+  size_t generic = lattice_workspace_bytes(B, S, T, slots);
+  size_t fast = simple_lattice_fast_workspace_bytes(B, S, T);
+  return generic > fast ? generic : fast;
 }
 
 size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {

@@ -386,6 +386,8 @@ struct DJointEpi {
   float* d_lm;
   struct Scratch {
     float dj[128 * kLd];
+    float amS[128 * kLd];  // am / lm rows of the tile's buckets, current 32-column chunk
+    float lmS[128 * kLd];
     int64_t red[8];
     int cnt[2][128], start[2][128];
     int order[2][128];
@@ -394,6 +396,7 @@ struct DJointEpi {
   struct State {
     int64_t ao, lo;
     int64_t a_row0, l_row0;
+    int sa, sl;
     bool live, direct;
   };
   __device__ void begin(State& st, const EpiCtx& ctx) const {
@@ -430,6 +433,8 @@ struct DJointEpi {
     st.l_row0 = rl;
     const int64_t sa = st.live ? ka - ra : 0, sl = st.live ? kl - rl : 0;
     st.direct = st.live && (sa >= kSlotsA || sl >= kSlotsL);  // far-apart rows: straight to global
+    st.sa = (int)(sa < kSlotsA ? sa : 0);
+    st.sl = (int)(sl < kSlotsL ? sl : 0);
     int pa = 0, pl = 0;
     const bool bucket = st.live && !st.direct;
     if (bucket) {
@@ -457,12 +462,26 @@ struct DJointEpi {
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
     float* mine = sc.dj + ctx.t * kLd;
+    // stage the am / lm rows of the buckets for these 32 columns (coalesced 128-byte reads)
+    {
+      const int na = sc.n_slots[0], nl = sc.n_slots[1];
+      for (int i = ctx.t; i < (na + nl) * 32; i += 128) {
+        const int slot = i >> 5, j = i & 31;
+        if (n + j < V) {
+          if (slot < na) sc.amS[slot * kLd + j] = __ldg(am + (st.a_row0 + slot) * V + n + j);
+          else sc.lmS[(slot - na) * kLd + j] = __ldg(lm + (st.l_row0 + slot - na) * V + n + j);
+        }
+      }
+    }
+    epi_sync();
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int v = n + j;
       float dj = 0.f;
       if (st.live && v < V && acc[j] != 0.f) {
-        dj = acc[j] * act_bwd_fast(__ldg(am + st.ao + v) + __ldg(lm + st.lo + v), act);
+        const float x = st.direct ? __ldg(am + st.ao + v) + __ldg(lm + st.lo + v)
+                                  : sc.amS[st.sa * kLd + j] + sc.lmS[st.sl * kLd + j];
+        dj = acc[j] * act_bwd_fast(x, act);
         if (st.direct && dj != 0.f) {
           atomicAdd(d_am + st.ao + v, dj);
           atomicAdd(d_lm + st.lo + v, dj);

@@ -49,4 +49,15 @@ int launch_lattice_fwd_bwd(const LatticeView& v, float* logp, float* occ_px, flo
 // alpha only (scores without gradients)
 int launch_lattice_fwd(const LatticeView& v, float* logp, cudaStream_t stream);
 
+// warp-synchronous fast paths (lattice_fast.cu)
+bool simple_lattice_fast_ok(int S);
+size_t simple_lattice_fast_workspace_bytes(int B, int S, int T);
+// occ_px / occ_py may both be nullptr (scores only); otherwise every element of them is written
+int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
+                               void* ws, float* logp, float* occ_px, float* occ_py, cudaStream_t stream);
+bool band_lattice_fast_ok(int S, int T, int R);
+int launch_band_lattice_fast(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary,
+                             int B, int S, int T, int R, float* logp, float* occ_px, float* occ_py,
+                             cudaStream_t stream);
+
 }  // namespace s2t
