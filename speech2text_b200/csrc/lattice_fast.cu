@@ -32,11 +32,16 @@ using tc::mbar_wait;
 constexpr int kRebaseShift = 4;  // offsets are constant over 16 consecutive diagonals
 constexpr int kRingBlocks = 3;   // 32-diagonal blocks in the shared-memory ring
 
-__device__ __forceinline__ float log_add_fast(float x, float y) {
-  // same cut-off as k2's LogAdd; exp / log1p through the SFU
-  float mx = fmaxf(x, y), mn = fminf(x, y);
-  float d = mn - mx;  // <= 0, NaN when both are -inf
-  return (d >= kMinLogDiff) ? mx + log1pf(__expf(d)) : mx;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kMinLog2Diff = kMinLogDiff * kLog2e;  // k2's LogAdd cut-off, in the log2 domain
+
+// log2(2^x + 2^y): the recursions run in the log2 domain so that a log-add is MAX, SUB, EX2, ADD, LG2, ADD.
+// Both -inf gives NaN in d, the compare fails and -inf (the max) comes back, as in k2's LogAdd.
+__device__ __forceinline__ float log2_add(float x, float y) {
+  const float mx = fmaxf(x, y), mn = fminf(x, y);
+  const float d = mn - mx;
+  return (d >= kMinLog2Diff) ? mx + __log2f(1.f + exp2f(d)) : mx;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -47,25 +52,29 @@ struct SimpleArgs {
   const float* py;  // (B, S+1, T)
   const int64_t* boundary;
   int B, S, T;
-  int rows_pad;      // 32 * RPL
-  float* alpha_diag;  // (B, S+T+1, rows_pad)
+  int rows_pad;       // 32 * RPL
+  int diag_rows;      // diagonals allocated per utterance (multiple of 32)
+  float* alpha_diag;  // (B, diag_rows, rows_pad), log2 domain, relative to aoff
   float* beta_diag;
-  double* aoff;  // (B, n_off)
+  double* aoff;  // (B, n_off), log2 domain
   double* boff;
   int n_off;
-  double* logp_d;  // (B)
+  double* logp_d;  // (B), natural log
   float* logp;     // (B)
 };
 
+constexpr int kSimpleProducerWarps = 8;
+constexpr int kSimpleThreads = 32 * (1 + kSimpleProducerWarps);
+
 template <int RPL>
-__global__ void __launch_bounds__(160, 1) simple_lattice_kernel(SimpleArgs a) {
+__global__ void __launch_bounds__(kSimpleThreads, 1) simple_lattice_kernel(SimpleArgs a) {
   constexpr int ROWS = 32 * RPL;
   constexpr int RS = ROWS + 1;  // odd stride: the producers' diagonal scatter is conflict-free
   constexpr int W = 32 * kRingBlocks;
   extern __shared__ float sm[];
   float* ringX = sm;
   float* ringY = sm + W * RS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ringY + W * RS + (((W * RS * 2) & 1) ? 1 : 0));
+  uint64_t* full = reinterpret_cast<uint64_t*>(ringY + W * RS);  // 2 * W * RS floats: 8-byte aligned
   uint64_t* empty = full + kRingBlocks;
 
   const int b = blockIdx.x;
@@ -85,7 +94,7 @@ __global__ void __launch_bounds__(160, 1) simple_lattice_kernel(SimpleArgs a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingBlocks; ++i) {
-      mbar_init(&full[i], 4);
+      mbar_init(&full[i], kSimpleProducerWarps);
       mbar_init(&empty[i], 1);
     }
     tc::fence_mbar_init();
@@ -93,27 +102,30 @@ __global__ void __launch_bounds__(160, 1) simple_lattice_kernel(SimpleArgs a) {
   __syncthreads();
 
   if (warp > 0) {
-    // ---------------- producers: 4 warps, rows s = pw, pw + 4, ... ----------------
+    // ---- producers: rows s = pw, pw + 8, ...; lane = diagonal inside the block.  They write EVERY
+    // row of the ring (-inf outside the lattice) so that the recursion needs no masks.
     const int pw = warp - 1;
     for (int k = 0; k < nblk; ++k) {
-      const int D = is_beta ? (nblk - 1 - k) : k;  // diagonal block, processing order
+      const int D = is_beta ? (nblk - 1 - k) : k;
       const int slot = k % kRingBlocks;
       mbar_wait(&empty[slot], ((k / kRingBlocks) & 1) ^ 1);
-      const int d = 32 * D + lane;  // this lane's diagonal
+      const int d = 32 * D + lane;
       float* rx = ringX + (slot * 32 + lane) * RS;
       float* ry = ringY + (slot * 32 + lane) * RS;
-#pragma unroll 4
-      for (int s = pw; s <= Sb; s += 4) {
+#pragma unroll 8
+      for (int s = pw; s < ROWS; s += kSimpleProducerWarps) {
         const int t = d - s;
         float xv = kNegInf, yv = kNegInf;
-        if (!is_beta) {
-          // alpha: X = px(s-1, t), Y = py(s, t-1)
-          if (s >= 1 && t >= 0 && t <= Tb) xv = __ldg(px + (int64_t)(s - 1) * (a.T + 1) + t);
-          if (t >= 1 && t <= Tb) yv = __ldg(py + (int64_t)s * a.T + t - 1);
-        } else {
-          // beta: X = px(s, t), Y = py(s, t)
-          if (s < Sb && t >= 0 && t <= Tb) xv = __ldg(px + (int64_t)s * (a.T + 1) + t);
-          if (t >= 0 && t < Tb) yv = __ldg(py + (int64_t)s * a.T + t);
+        if (s <= Sb) {
+          if (!is_beta) {
+            // alpha step into (s, t): X = px(s-1, t), Y = py(s, t-1)
+            if (s >= 1 && t >= 0 && t <= Tb) xv = kLog2e * __ldg(px + (int64_t)(s - 1) * (a.T + 1) + t);
+            if (t >= 1 && t <= Tb) yv = kLog2e * __ldg(py + (int64_t)s * a.T + t - 1);
+          } else {
+            // beta step out of (s, t): X = px(s, t), Y = py(s, t)
+            if (s < Sb && t >= 0 && t <= Tb) xv = kLog2e * __ldg(px + (int64_t)s * (a.T + 1) + t);
+            if (t >= 0 && t < Tb) yv = kLog2e * __ldg(py + (int64_t)s * a.T + t);
+          }
         }
         rx[s] = xv;
         ry[s] = yv;
@@ -124,76 +136,82 @@ __global__ void __launch_bounds__(160, 1) simple_lattice_kernel(SimpleArgs a) {
     return;
   }
 
-  // ---------------- recursion warp ----------------
+  // ---- recursion warp: lane l holds rows l, l + 32, ... ----
   float v[RPL];
 #pragma unroll
   for (int j = 0; j < RPL; ++j) v[j] = kNegInf;
   double off = 0.0;
-  float* out = (is_beta ? a.beta_diag : a.alpha_diag) + (int64_t)b * (a.S + a.T + 1) * ROWS;
+  float* out = (is_beta ? a.beta_diag : a.alpha_diag) + (int64_t)b * a.diag_rows * ROWS;
   double* offs = (is_beta ? a.boff : a.aoff) + (int64_t)b * a.n_off;
+  const int src_lane = is_beta ? ((lane + 1) & 31) : ((lane + 31) & 31);
+  const int fin_j = Sb >> 5, fin_lane = Sb & 31;
+  float fin = kNegInf;
+  double fin_off = 0.0;
 
   for (int k = 0; k < nblk; ++k) {
     const int D = is_beta ? (nblk - 1 - k) : k;
     const int slot = k % kRingBlocks;
     mbar_wait(&full[slot], (k / kRingBlocks) & 1);
-    for (int ii = 0; ii < 32; ++ii) {
-      const int i = is_beta ? 31 - ii : ii;
-      const int d = 32 * D + i;
-      if (d > nd) continue;
-      // offsets are piecewise constant over 16 diagonals; record the one this diagonal is stored with
-      const bool period_start = is_beta ? ((d & 15) == 15 || d == nd) : ((d & 15) == 0);
-      if (period_start && lane == 0) offs[d >> kRebaseShift] = off;
-      const float* rx = ringX + (slot * 32 + i) * RS;
-      const float* ry = ringY + (slot * 32 + i) * RS;
-      float nv[RPL];
-      float rot[RPL];
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {  // two 16-diagonal periods per block
+      const int dh = is_beta ? (32 * D + 31 - 16 * h) : (32 * D + 16 * h);  // first diagonal of the period
+      if (lane == 0) offs[dh >> kRebaseShift] = off;
+#pragma unroll 4
+      for (int ii = 0; ii < 16; ++ii) {
+        const int d = is_beta ? dh - ii : dh + ii;
+        const float* rx = ringX + (slot * 32 + (d & 31)) * RS;
+        const float* ry = ringY + (slot * 32 + (d & 31)) * RS;
+        float rot[RPL];
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) rot[j] = __shfl_sync(0xffffffffu, v[j], is_beta ? ((lane + 1) & 31) : ((lane + 31) & 31));
+        for (int j = 0; j < RPL; ++j) rot[j] = __shfl_sync(0xffffffffu, v[j], src_lane);
+        float nv[RPL];
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) {
-        const int s = j * 32 + lane;
-        const int t = d - s;
-        float nb;  // neighbour row: s-1 (alpha) / s+1 (beta), previous diagonal
-        if (!is_beta) nb = (lane > 0) ? rot[j] : (j > 0 ? rot[j - 1] : kNegInf);
-        else nb = (lane < 31) ? rot[j] : (j < RPL - 1 ? rot[j + 1] : kNegInf);
-        const float xv = rx[s], yv = ry[s];
-        float val = log_add_fast(nb + xv, v[j] + yv);
-        const bool start = is_beta ? (s == Sb && t == Tb) : (d == 0 && s == 0);
-        if (start) val = 0.f;
-        if (s > Sb || t < 0 || t > Tb) val = kNegInf;
-        nv[j] = val;
-        out[(int64_t)d * ROWS + s] = val;
-      }
-#pragma unroll
-      for (int j = 0; j < RPL; ++j) v[j] = nv[j];
-      const bool period_end = is_beta ? ((d & 15) == 0) : ((d & 15) == 15);
-      if (period_end) {
-        float m = v[0];
-#pragma unroll
-        for (int j = 1; j < RPL; ++j) m = fmaxf(m, v[j]);
-        m = warp_max(m);
-        if (m - m == 0.f) {
-#pragma unroll
-          for (int j = 0; j < RPL; ++j) v[j] -= m;
-          off += (double)m;
+        for (int j = 0; j < RPL; ++j) {
+          float nb;  // neighbour row s-1 (alpha) / s+1 (beta) on the previous diagonal
+          if (!is_beta) nb = (lane > 0) ? rot[j] : (j > 0 ? rot[j - 1] : kNegInf);
+          else nb = (lane < 31) ? rot[j] : (j < RPL - 1 ? rot[j + 1] : kNegInf);
+          nv[j] = log2_add(nb + rx[j * 32 + lane], v[j] + ry[j * 32 + lane]);
         }
+        // the single source cell: alpha(0, 0) = 0 on diagonal 0, beta(S_b, T_b) = 0 on diagonal nd
+        if (!is_beta) {
+          if (d == 0 && lane == 0) nv[0] = 0.f;
+        } else if (d == nd && lane == fin_lane) {
+#pragma unroll
+          for (int j = 0; j < RPL; ++j)
+            if (j == fin_j) nv[j] = 0.f;
+        }
+        float* o = out + (int64_t)d * ROWS + lane;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          v[j] = nv[j];
+          o[j * 32] = nv[j];
+        }
+        if (!is_beta && d == nd) {  // log P(y|x) = alpha(S_b, T_b)
+          float mine = kNegInf;
+#pragma unroll
+          for (int j = 0; j < RPL; ++j)
+            if (j == fin_j) mine = v[j];
+          fin = __shfl_sync(0xffffffffu, mine, fin_lane);
+          fin_off = off;
+        }
+      }
+      float m = v[0];
+#pragma unroll
+      for (int j = 1; j < RPL; ++j) m = fmaxf(m, v[j]);
+      m = warp_max(m);
+      if (m - m == 0.f) {
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) v[j] -= m;
+        off += (double)m;
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[slot]);
   }
-  if (!is_beta) {
-    // log P(y|x) = alpha(S_b, T_b), held by lane S_b % 32, register S_b / 32 (diagonal nd was the last)
-    float mine = kNegInf;
-#pragma unroll
-    for (int j = 0; j < RPL; ++j)
-      if (j == Sb / 32) mine = v[j];
-    const float fin = __shfl_sync(0xffffffffu, mine, Sb & 31);
-    if (lane == 0) {
-      const double lp = (double)fin + off;
-      a.logp_d[b] = lp;
-      a.logp[b] = (float)lp;
-    }
+  if (!is_beta && lane == 0) {
+    const double lp = ((double)fin + fin_off) * (double)kLn2;
+    a.logp_d[b] = lp;
+    a.logp[b] = (float)lp;
   }
 }
 
@@ -214,8 +232,8 @@ __global__ void __launch_bounds__(256) simple_occupation_kernel(SimpleArgs a, fl
   Sb = min(max(Sb, 0), a.S);
   Tb = min(max(Tb, 0), a.T);
   const int nd = Sb + Tb;
-  const float* ad = a.alpha_diag + (int64_t)b * (a.S + a.T + 1) * ROWS;
-  const float* bd = a.beta_diag + (int64_t)b * (a.S + a.T + 1) * ROWS;
+  const float* ad = a.alpha_diag + (int64_t)b * a.diag_rows * ROWS;
+  const float* bd = a.beta_diag + (int64_t)b * a.diag_rows * ROWS;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int d0 = s0 + t0;
   const bool tile_live = (s0 <= Sb) && (t0 <= Tb);
@@ -239,15 +257,17 @@ __global__ void __launch_bounds__(256) simple_occupation_kernel(SimpleArgs a, fl
     float ox = 0.f, oy = 0.f;
     if (tile_live && lp_ok && s <= Sb && t <= Tb) {
       const int d = s + t;
-      const float cst = (float)(aoff[d >> kRebaseShift] + boff[(d + 1 <= nd ? d + 1 : nd) >> kRebaseShift] - lp);
+      // alpha / beta and their offsets are in the log2 domain
+      const float cst = (float)(aoff[d >> kRebaseShift] + boff[(d + 1 <= nd ? d + 1 : nd) >> kRebaseShift] -
+                                lp * (double)kLog2e);
       const float av = sA[rs + tx][rs];
       if (t < Tb) {
-        const float yv = __ldg(a.py + ((int64_t)b * (a.S + 1) + s) * a.T + t);
-        oy = __expf(av + yv + sB[rs + tx][rs] + cst);
+        const float yv = kLog2e * __ldg(a.py + ((int64_t)b * (a.S + 1) + s) * a.T + t);
+        oy = exp2f(av + yv + sB[rs + tx][rs] + cst);
       }
       if (s < Sb) {
-        const float xv = __ldg(a.px + ((int64_t)b * a.S + s) * (a.T + 1) + t);
-        ox = __expf(av + xv + sB[rs + tx][rs + 1] + cst);
+        const float xv = kLog2e * __ldg(a.px + ((int64_t)b * a.S + s) * (a.T + 1) + t);
+        ox = exp2f(av + xv + sB[rs + tx][rs + 1] + cst);
       }
     }
     if (s < a.S) occ_px[((int64_t)b * a.S + s) * (a.T + 1) + t] = ox;
@@ -272,16 +292,16 @@ struct BandArgs {
 __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
   extern __shared__ float sm[];
   const int T = a.T, R = a.R;
-  float* pxs = sm;
+  float* pxs = sm;            // log2 domain
   float* pys = pxs + T * R;
-  float* als = pys + T * R;
+  float* als = pys + T * R;   // alpha / beta relative to the offset of their diagonal
   float* bes = als + T * R;
-  int* sbs = reinterpret_cast<int*>(bes + T * R);  // sb[t], T + 1 entries (sb[Tb] = sb[Tb-1])
-  double* offs = reinterpret_cast<double*>(sbs + ((T + 2) & ~1));  // aoff | boff, n_off each
+  int* sbs = reinterpret_cast<int*>(bes + T * R);  // sb[t], T + 2 entries (padding frames repeat the last)
+  double* offs = reinterpret_cast<double*>(sbs + ((T + 3) & ~1));
   const int n_off = ((a.S + T + R) >> kRebaseShift) + 2;
   double* aoff = offs;
   double* boff = offs + n_off;
-  __shared__ double s_logp;
+  __shared__ double s_logp2;  // log2 P(y|x)
 
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,110 +317,132 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
   const int64_t* grg = a.ranges ? a.ranges + (int64_t)b * T * R : nullptr;
 
   for (int i = threadIdx.x; i < Tb * R; i += blockDim.x) {
-    pxs[i] = __ldg(gpx + i);
-    pys[i] = __ldg(gpy + i);
+    pxs[i] = kLog2e * __ldg(gpx + i);
+    pys[i] = kLog2e * __ldg(gpy + i);
   }
-  for (int t = threadIdx.x; t <= Tb; t += blockDim.x) {
+  for (int t = threadIdx.x; t <= Tb + 1 && t < T + 2; t += blockDim.x) {
     const int tt = min(t, max(Tb - 1, 0));
     sbs[t] = grg ? (int)grg[(int64_t)tt * R] : 0;
   }
-  if (threadIdx.x == 0) s_logp = -INFINITY;
+  if (threadIdx.x == 0) s_logp2 = -INFINITY;
   __syncthreads();
 
+  constexpr int kDone = 1 << 29;
   const int last_d = (Tb > 0) ? (Tb - 1 + sbs[Tb - 1] + R - 1) : -1;  // last diagonal that holds a band cell
+  const int n_periods = (last_d >> kRebaseShift) + 1;
   if (warp == 0 && Tb > 0) {
-    // ---- alpha: lane r owns slot r, frames ascending ----
-    int t = 0;
+    // ---- alpha: lane r owns slot r and walks the frames upwards.  Per frame it pre-loads the two
+    // incoming log-probs (already -inf when the move or the cell does not exist), so a step is two
+    // shuffles and one log2-add.
+    int t = 0, sb_cur = sbs[0];
+    int f = (lane < R) ? sb_cur + lane : kDone;  // diagonal of this lane's next cell
+    int delta = 0;
+    float xin = (lane > 0 && lane < R) ? pxs[lane - 1] : kNegInf;  // px(t, r-1)
+    float yin = kNegInf;                                            // py(t-1, r+delta): none for t = 0
+    float* ap = als + lane;
     float last = kNegInf;
     double off = 0.0;
-    for (int d = 0; d <= last_d; ++d) {
-      if ((d & 15) == 0 && lane == 0) aoff[d >> kRebaseShift] = off;
-      const bool act = (lane < R) && (t < Tb) && (t + sbs[t] + lane == d);
-      const int delta = (act && t > 0) ? (sbs[t] - sbs[t - 1]) : 0;
-      const float up_src = __shfl_up_sync(0xffffffffu, last, 1);
-      const float left_src = __shfl_sync(0xffffffffu, last, (lane + delta) & 31);
-      float val = kNegInf;
-      if (act) {
-        const int s = sbs[t] + lane;
-        if (s <= Sb) {
-          const float up = (lane > 0) ? up_src + pxs[t * R + lane - 1] : kNegInf;
-          const float left = (t > 0 && lane + delta < R) ? left_src + pys[(t - 1) * R + lane + delta] : kNegInf;
-          val = (t == 0 && s == 0) ? 0.f : log_add_fast(up, left);
+    for (int p = 0; p < n_periods; ++p) {
+      if (lane == 0) aoff[p] = off;
+#pragma unroll 4
+      for (int ii = 0; ii < 16; ++ii) {
+        const int d = 16 * p + ii;
+        const float up_src = __shfl_up_sync(0xffffffffu, last, 1);
+        const float left_src = __shfl_sync(0xffffffffu, last, (lane + delta) & 31);
+        float val = kNegInf;
+        if (f == d) {
+          val = log2_add(up_src + xin, left_src + yin);
+          if (d == 0) val = (lane == 0) ? 0.f : kNegInf;  // alpha(0, 0) = 0
+          if (sb_cur + lane > Sb) val = kNegInf;
+          *ap = val;
+          ap += R;
+          ++t;
+          if (t < Tb) {
+            const int sb_next = sbs[t];
+            delta = sb_next - sb_cur;
+            sb_cur = sb_next;
+            f = t + sb_cur + lane;
+            xin = (lane > 0) ? pxs[t * R + lane - 1] : kNegInf;
+            yin = (lane + delta < R) ? pys[(t - 1) * R + lane + delta] : kNegInf;
+          } else {
+            f = kDone;
+          }
         }
-        als[t * R + lane] = val;
-        ++t;
+        last = val;
       }
-      last = val;
-      if ((d & 15) == 15) {
-        const float m = warp_max(last);
-        // every lane's `last` is from this diagonal or -inf; older cells are already in als[]
-        if (m - m == 0.f) {
-          last -= m;
-          off += (double)m;
-        }
-      }
-    }
-    // log P = alpha(T_b-1, r*) + py(T_b-1, r*), r* = S_b - sb[T_b-1]
-    if (lane == 0) {
-      const int rs = Sb - sbs[Tb - 1];
-      double lp = -INFINITY;
-      if (rs >= 0 && rs < R) {
-        const int dd = Tb - 1 + sbs[Tb - 1] + rs;
-        // als[] values are relative to the offset in force on their own diagonal
-        lp = (double)als[(Tb - 1) * R + rs] + (double)pys[(Tb - 1) * R + rs];
-        (void)dd;
-        s_logp = lp;  // completed after the barrier with aoff[dd >> 4], the offset of that diagonal
+      const float m = warp_max(last);  // cells older than this diagonal already sit in als[]
+      if (m - m == 0.f) {
+        last -= m;
+        off += (double)m;
       }
     }
   } else if (warp == 1 && Tb > 0) {
-    // ---- beta: lane r owns slot r, frames descending ----
-    int t = Tb - 1;
+    // ---- beta: lane r owns slot r and walks the frames downwards ----
+    int t = Tb - 1, sb_cur = sbs[Tb - 1];
+    int f = (lane < R) ? t + sb_cur + lane : -kDone;
+    int delta = 0;  // sb[t+1] - sb[t]
+    const int s0 = sb_cur + lane;
+    float xout = (lane + 1 < R && s0 < Sb) ? pxs[t * R + lane] : kNegInf;  // px(t, r) -> slot r+1
+    float yout = (lane < R && s0 == Sb) ? pys[t * R + lane] : kNegInf;    // last frame: beta(s, T_b) = [s == S_b]
+    bool term = true;  // the blank move of the last frame ends the lattice
+    float* bp = bes + t * R + lane;
     float last = kNegInf;
     double off = 0.0;
-    for (int d = last_d; d >= 0; --d) {
-      if (((d & 15) == 15 || d == last_d) && lane == 0) boff[d >> kRebaseShift] = off;
-      const bool act = (lane < R) && (t >= 0) && (t + sbs[t] + lane == d);
-      const int delta = (act && t + 1 < Tb) ? (sbs[t + 1] - sbs[t]) : 0;
-      const float down_src = __shfl_down_sync(0xffffffffu, last, 1);
-      const float right_src = __shfl_sync(0xffffffffu, last, (lane - delta) & 31);
-      float val = kNegInf;
-      if (act) {
-        const int s = sbs[t] + lane;
-        if (s <= Sb) {
-          // symbol: to (s+1, t) = slot lane+1 of the same frame
-          const float bx = (lane + 1 < R && s < Sb) ? pxs[t * R + lane] + down_src : kNegInf;
-          float by;
-          if (t == Tb - 1) by = (s == Sb) ? pys[t * R + lane] : kNegInf;  // beta(s, T_b) = [s == S_b]
-          else by = (lane - delta >= 0) ? pys[t * R + lane] + right_src : kNegInf;
-          val = log_add_fast(bx, by);
+    for (int p = n_periods - 1; p >= 0; --p) {
+      if (lane == 0) boff[p] = off;
+#pragma unroll 4
+      for (int ii = 15; ii >= 0; --ii) {
+        const int d = 16 * p + ii;
+        const float down_src = __shfl_down_sync(0xffffffffu, last, 1);
+        const float right_src = __shfl_sync(0xffffffffu, last, (lane - delta) & 31);
+        float val = kNegInf;
+        if (f == d) {
+          val = log2_add(down_src + xout, term ? yout : right_src + yout);
+          if (sb_cur + lane > Sb) val = kNegInf;
+          *bp = val;
+          bp -= R;
+          --t;
+          term = false;
+          if (t >= 0) {
+            const int sb_prev = sbs[t];
+            delta = sb_cur - sb_prev;
+            sb_cur = sb_prev;
+            f = t + sb_cur + lane;
+            const int s = sb_cur + lane;
+            xout = (lane + 1 < R && s < Sb) ? pxs[t * R + lane] : kNegInf;
+            yout = (lane - delta >= 0) ? pys[t * R + lane] : kNegInf;
+          } else {
+            f = -kDone;
+          }
         }
-        bes[t * R + lane] = val;
-        --t;
+        last = val;
       }
-      last = val;
-      if ((d & 15) == 0) {
-        const float m = warp_max(last);
-        if (m - m == 0.f) {
-          last -= m;
-          off += (double)m;
-        }
+      const float m = warp_max(last);
+      if (m - m == 0.f) {
+        last -= m;
+        off += (double)m;
       }
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && Tb > 0) {
-    const int rs = Sb - sbs[Tb - 1];
-    if (rs >= 0 && rs < R) {
-      const int dd = Tb - 1 + sbs[Tb - 1] + rs;
-      s_logp = s_logp + aoff[dd >> kRebaseShift];
+  if (threadIdx.x == 0) {
+    double lp2 = -INFINITY;
+    if (Tb > 0) {
+      // log P = alpha(T_b-1, r*) + py(T_b-1, r*), r* = S_b - sb[T_b-1]
+      const int rs = Sb - sbs[Tb - 1];
+      if (rs >= 0 && rs < R) {
+        const int dd = Tb - 1 + sbs[Tb - 1] + rs;
+        lp2 = (double)als[(Tb - 1) * R + rs] + (double)pys[(Tb - 1) * R + rs] + aoff[dd >> kRebaseShift];
+      }
+    } else if (Sb == 0) {
+      lp2 = 0.0;  // no frames: only the empty transcript is possible
     }
-    a.logp[b] = (float)s_logp;
-  } else if (threadIdx.x == 0) {
-    a.logp[b] = (Sb == 0) ? 0.f : -INFINITY;  // no frames: only the empty transcript is possible
+    s_logp2 = lp2;
+    a.logp[b] = (float)(lp2 * (double)kLn2);
   }
   __syncthreads();
-  const double lp = s_logp;
-  const bool lp_ok = (lp - lp == 0.0) && Tb > 0;
+  const double lp2 = s_logp2;
+  const bool lp_ok = (lp2 - lp2 == 0.0) && Tb > 0;
   float* ox = a.occ_px + (int64_t)b * T * R;
   float* oy = a.occ_py + (int64_t)b * T * R;
   for (int i = threadIdx.x; i < T * R; i += blockDim.x) {
@@ -412,20 +454,18 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
         const int d = t + sbs[t] + r;
         const float av = als[i];
         const double ao = aoff[d >> kRebaseShift];
-        // blank: to (s, t+1)
         if (t == Tb - 1) {
-          if (s == Sb) vy = __expf((float)((double)av + (double)pys[i] + ao - lp));
+          if (s == Sb) vy = exp2f((float)((double)av + (double)pys[i] + ao - lp2));
         } else {
-          const int r2 = s - sbs[t + 1];
+          const int r2 = s - sbs[t + 1];  // blank: to (s, t+1)
           if (r2 >= 0 && r2 < R) {
-            const float cst = (float)(ao + boff[(d + 1) >> kRebaseShift] - lp);
-            vy = __expf(av + pys[i] + bes[(t + 1) * R + r2] + cst);
+            const float cst = (float)(ao + boff[(d + 1) >> kRebaseShift] - lp2);
+            vy = exp2f(av + pys[i] + bes[(t + 1) * R + r2] + cst);
           }
         }
-        // symbol: to (s+1, t)
-        if (r + 1 < R && s < Sb) {
-          const float cst = (float)(ao + boff[(d + 1) >> kRebaseShift] - lp);
-          vx = __expf(av + pxs[i] + bes[t * R + r + 1] + cst);
+        if (r + 1 < R && s < Sb) {  // symbol: to (s+1, t)
+          const float cst = (float)(ao + boff[(d + 1) >> kRebaseShift] - lp2);
+          vx = exp2f(av + pxs[i] + bes[t * R + r + 1] + cst);
         }
       }
     }
@@ -451,8 +491,9 @@ bool simple_lattice_fast_ok(int S) { return simple_rpl(S) > 0; }
 size_t simple_lattice_fast_workspace_bytes(int B, int S, int T) {
   const int rpl = simple_rpl(S);
   if (!rpl) return 0;
-  const size_t diag = (size_t)B * (S + T + 1) * 32 * rpl * sizeof(float);
-  const size_t n_off = ((S + T) >> kRebaseShift) + 2;
+  const size_t diag_rows = (size_t)((S + T) / 32 + 1) * 32;
+  const size_t diag = (size_t)B * diag_rows * 32 * rpl * sizeof(float);
+  const size_t n_off = diag_rows / 16 + 2;
   return 2 * diag + (2 * (size_t)B * n_off + B) * sizeof(double) + 64;
 }
 
@@ -465,8 +506,9 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
   a.px = px; a.py = py; a.boundary = boundary;
   a.B = B; a.S = S; a.T = T;
   a.rows_pad = 32 * rpl;
-  const size_t diag = (size_t)B * (S + T + 1) * a.rows_pad;
-  a.n_off = ((S + T) >> kRebaseShift) + 2;
+  a.diag_rows = ((S + T) / 32 + 1) * 32;
+  const size_t diag = (size_t)B * a.diag_rows * a.rows_pad;
+  a.n_off = a.diag_rows / 16 + 2;
   a.alpha_diag = (float*)ws;
   a.beta_diag = a.alpha_diag + diag;
   a.aoff = (double*)(a.beta_diag + diag + ((2 * diag) & 1));
@@ -479,7 +521,7 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
     dim3 grid(B, occ_px ? 2 : 1);
     auto launch = [&](auto kern) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<grid, 160, smem, stream>>>(a);
+      kern<<<grid, kSimpleThreads, smem, stream>>>(a);
     };
     switch (rpl) {
       case 1: launch(simple_lattice_kernel<1>); break;
@@ -500,7 +542,7 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
 
 static size_t band_smem_bytes(int S, int T, int R) {
   const size_t n_off = ((S + T + R) >> kRebaseShift) + 2;
-  return (size_t)4 * T * R * sizeof(float) + (size_t)((T + 2) & ~1) * sizeof(int) + 2 * n_off * sizeof(double) + 16;
+  return (size_t)4 * T * R * sizeof(float) + (size_t)((T + 3) & ~1) * sizeof(int) + 2 * n_off * sizeof(double) + 16;
 }
 
 bool band_lattice_fast_ok(int S, int T, int R) { return R <= 32 && band_smem_bytes(S, T, R) <= 200 * 1024; }

@@ -54,7 +54,7 @@ def test_mutual_information_matches_oracle(B, S, T):
     s, (gx, gy) = F2.mutual_information_recursion(px.to(_dev()), py.to(_dev()), boundary.to(_dev()),
                                                   return_grad=True)
     torch.cuda.synchronize()
-    assert rel_err(s, s_ref) < 1e-6
+    assert rel_err(s, s_ref) < 5e-6
     assert rel_err(s, s32) < LOSS_RTOL
     assert (gx.cpu() - gx_ref).abs().max() < 2e-5  # occupation probabilities live in [0, 1]
     assert (gy.cpu() - gy_ref).abs().max() < 2e-5
