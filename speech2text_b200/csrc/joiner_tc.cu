@@ -384,10 +384,11 @@ struct DJointEpi {
   int V, act;
   float* d_am;
   float* d_lm;
+  static constexpr int kLdW = 257;        // staged am / lm rows: 256 columns of the n-tile, odd stride
+  static constexpr int kMaxStaged = 64;   // (am + lm bucket rows) that fit the operand ring next to dj
   struct Scratch {
     float dj[128 * kLd];
-    float amS[128 * kLd];  // am / lm rows of the tile's buckets, current 32-column chunk
-    float lmS[128 * kLd];
+    float rows[kMaxStaged * kLdW];  // am rows of the buckets, then lm rows, this tile's 256 columns
     int64_t red[8];
     int cnt[2][128], start[2][128];
     int order[2][128];
@@ -397,7 +398,7 @@ struct DJointEpi {
     int64_t ao, lo;
     int64_t a_row0, l_row0;
     int sa, sl;
-    bool live, direct;
+    bool live, direct, staged;
   };
   __device__ void begin(State& st, const EpiCtx& ctx) const {
     Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
@@ -456,31 +457,49 @@ struct DJointEpi {
       sc.order[0][sc.start[0][(int)sa] + pa] = ctx.t;
       sc.order[1][sc.start[1][(int)sl] + pl] = ctx.t;
     }
+    // stage the bucket rows of am and lm for the 256 columns of this n-tile: one burst of coalesced
+    // loads per tile (all in flight together) instead of a dependent L2 round trip per row and chunk
+    const int na = sc.n_slots[0], nl = sc.n_slots[1];
+    st.staged = (na + nl) <= kMaxStaged;
+    if (st.staged) {
+      const int n0 = ctx.n_tile * 256;
+      const int total = (na + nl) * 256;
+      for (int i0 = ctx.t; i0 < total; i0 += 128 * 8) {
+        float tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 128;
+          const int row = i >> 8, col = i & 255;
+          float x = 0.f;
+          if (i < total && n0 + col < V) {
+            x = row < na ? __ldg(am + (st.a_row0 + row) * V + n0 + col)
+                         : __ldg(lm + (st.l_row0 + row - na) * V + n0 + col);
+          }
+          tmp[u] = x;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 128;
+          if (i < total) sc.rows[(i >> 8) * kLdW + (i & 255)] = tmp[u];
+        }
+      }
+      st.sl += na;  // lm rows follow the am rows
+    }
     epi_sync();
   }
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
     float* mine = sc.dj + ctx.t * kLd;
-    // stage the am / lm rows of the buckets for these 32 columns (coalesced 128-byte reads)
-    {
-      const int na = sc.n_slots[0], nl = sc.n_slots[1];
-      for (int i = ctx.t; i < (na + nl) * 32; i += 128) {
-        const int slot = i >> 5, j = i & 31;
-        if (n + j < V) {
-          if (slot < na) sc.amS[slot * kLd + j] = __ldg(am + (st.a_row0 + slot) * V + n + j);
-          else sc.lmS[(slot - na) * kLd + j] = __ldg(lm + (st.l_row0 + slot - na) * V + n + j);
-        }
-      }
-    }
-    epi_sync();
+    const int c0 = n - ctx.n_tile * 256;  // first column of this chunk inside the staged rows
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int v = n + j;
       float dj = 0.f;
       if (st.live && v < V && acc[j] != 0.f) {
-        const float x = st.direct ? __ldg(am + st.ao + v) + __ldg(lm + st.lo + v)
-                                  : sc.amS[st.sa * kLd + j] + sc.lmS[st.sl * kLd + j];
+        const float x = (st.direct || !st.staged)
+                            ? __ldg(am + st.ao + v) + __ldg(lm + st.lo + v)
+                            : sc.rows[st.sa * kLdW + c0 + j] + sc.rows[st.sl * kLdW + c0 + j];
         dj = acc[j] * act_bwd_fast(x, act);
         if (st.direct && dj != 0.f) {
           atomicAdd(d_am + st.ao + v, dj);
@@ -631,7 +650,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     JointRowProducer a{p.am, p.lm, w.am_off, w.lm_off, M, p.V, p.act};
     HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt};
-    if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
+    if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
                                             "tc_joiner_hidden_gemm"))
       return rc;
   }
@@ -639,7 +658,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     BulkA a{w.Hp, d.Mt};
     LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_tiles_v, M, w.part, w.sym_logit, w.blank_logit};
-    if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
+    if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                    "tc_joiner_logits_lse_gemm"))
       return rc;
   }
@@ -671,7 +690,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
-      if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                      "tc_joiner_grad_logits_gemm"))
         return rc;
     }
@@ -679,7 +698,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Gp, ct};
       DHiddenEpi ep{p.I, w.DHp, ct, db1};
-      if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
+      if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
                                                      "tc_joiner_dhidden_gemm"))
         return rc;
     }
@@ -688,7 +707,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Gp, ct};
       StoreRowMajorEpi ep{dW2, p.I, p.V, p.I, true};
-      if (int rc = launch_gemm_stream<256, 3, true, 0>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / 256,
+      if (int rc = launch_gemm_stream<256, 2, true, 0>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / 256,
                                                     kbM, splits, ep, stream, "tc_joiner_dW2_gemm"))
         return rc;
     }
@@ -696,7 +715,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       JointMnProducer a{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act};
       StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
-      if (int rc = launch_gemm_stream<256, 3, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
+      if (int rc = launch_gemm_stream<256, 2, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
                                                     "tc_joiner_dW1_gemm"))
         return rc;
     }
@@ -704,7 +723,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       DJointEpi ep{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act, d_am, d_lm};
-      if (int rc = launch_gemm_stream<256, 3, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                      "tc_joiner_djoint_gemm"))
         return rc;
     }
