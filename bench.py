@@ -107,18 +107,33 @@ def kernel_work(cfg):
     simple = 2.0 * B * S1 * T * V
     lat_cells = B * (S1 * (T + 1))
     band_cells = B * T * R
+    proj_enc = 2.0 * B * T * D * V
+    proj_pred = 2.0 * B * S1 * D * V
     w = {
         # name: (bound, algorithmic flops or bytes per launch)
+        # strict-fp32 SIMT mode
         "joiner_hidden_gemm": ("tensor", gemm), "joiner_logits_gemm": ("tensor", gemm),
         "joiner_dhidden_gemm": ("tensor", gemm), "joiner_dW2_gemm": ("tensor", gemm),
         "joiner_dW1_gemm": ("tensor", gemm), "joiner_djoint_gemm": ("tensor", gemm),
         "simple_normaliser_gemm": ("tensor", simple), "simple_d_am_gemm": ("tensor", simple),
         "simple_d_lm_gemm": ("tensor", simple),
+        # bf16 tensor-core mode (tcgen05): every joiner contraction is 2*M*V*I
+        "tc_joiner_hidden_gemm": ("tensor", gemm), "tc_joiner_logits_lse_gemm": ("tensor", gemm),
+        "tc_joiner_grad_logits_gemm": ("tensor", gemm), "tc_joiner_dhidden_gemm": ("tensor", gemm),
+        "tc_joiner_dW2_gemm": ("tensor", gemm), "tc_joiner_dW1_gemm": ("tensor", gemm),
+        "tc_joiner_djoint_gemm": ("tensor", gemm),
+        # projections: two launches per step (encoder and predictor side); average of the two
+        "tc_linear_fwd_gemm_3xtf32": ("tensor", (proj_enc + proj_pred) / 2),
+        "tc_linear_dx_gemm": ("tensor", (proj_enc + proj_pred) / 2),
+        "tc_linear_dW_gemm": ("tensor", (proj_enc + proj_pred) / 2),
         "lse_gather_kernel": ("hbm", M * V * 4.0), "logits_grad_kernel": ("hbm", 2.0 * M * V * 4),
         "joint_act_kernel": ("hbm", M * V * 4.0 * 3), "joint_grad_kernel": ("hbm", M * V * 4.0 * 5),
-        # simple lattice: alpha reads px,py, writes alpha; beta reads px,py,alpha, writes 2 occupations
+        # lattices: alpha reads px,py and writes alpha; beta the same; occupation reads 4, writes 2
         "lattice_alpha_kernel": ("hbm", 12.0 * (lat_cells + band_cells) / 2),
         "lattice_beta_kernel": ("hbm", 20.0 * (lat_cells + band_cells) / 2),
+        "simple_lattice_kernel": ("hbm", 2 * 12.0 * lat_cells),
+        "simple_occupation_kernel": ("hbm", 24.0 * lat_cells),
+        "band_lattice_kernel": ("hbm", 20.0 * band_cells),
         "prune_ranges_kernel": ("hbm", B * ((U * (T + 1) + S1 * T) * 4.0 + T * R * 8.0)),
     }
     return w
@@ -219,7 +234,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
-    ap.add_argument("--mode", default=os.environ.get("S2T_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("S2T_BENCH_MODE", "bf16"), choices=["fp32", "bf16"],
+                    help="joiner arithmetic: bf16 tensor cores (BASELINE config 3: 'bf16 joiner') or strict fp32")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-utts", type=int, default=4, help="utterances per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -259,6 +275,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the CUDA library is missing
 
