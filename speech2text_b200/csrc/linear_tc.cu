@@ -17,13 +17,27 @@ namespace {
 
 using namespace tc;
 
+// out[n] += sum over a 64-row slab of x[r, n]; block = 32 columns x 8 row lanes
 __global__ void linear_col_sum_kernel(const float* __restrict__ x, int64_t rows, int ld, int N, float* __restrict__ out) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  int64_t r0 = (int64_t)blockIdx.y * 512, r1 = min(rows, r0 + 512);
+  __shared__ float part[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * 64;
   float acc = 0.f;
-  for (int64_t r = r0; r < r1; ++r) acc += x[r * ld + n];
-  atomicAdd(out + n, acc);
+  if (n < N) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = r0 + threadIdx.y + 8 * i;
+      if (r < rows) acc += x[r * ld + n];
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
 }
 
 struct LinDims {
@@ -107,8 +121,8 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
                                                       "tc_linear_dW_gemm"))
       return rc;
     ProfScope prof("linear_col_sum_kernel", st);
-    dim3 grid((N + 127) / 128, (unsigned)((M + 511) / 512));
-    linear_col_sum_kernel<<<grid, 128, 0, st>>>(dy, M, N, N, db);
+    dim3 grid((N + 31) / 32, (unsigned)((M + 63) / 64));
+    linear_col_sum_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, M, N, N, db);
   }
   return check_launch("linear_bwd");
 }

@@ -69,37 +69,74 @@ prune_ranges_kernel(const float* __restrict__ px_grad, const float* __restrict__
   const int pad = max(Sb - R + 1, 0);
   const int ncand = S1 - R + 1;
 
-  // phase 1: argmax_s of the window score, one frame per thread
+  // phase 1: argmax_s of the window score, one frame per thread.  The window of R occupation values
+  // slides through registers (one new py_grad load + one px_grad load per candidate); the sum is
+  // still formed left to right over the window, which is the bit-exactness contract.
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     int best = 0;
     if (t < Tb - 1) {
       float best_v = kNegInf;
-      for (int s = 0; s < ncand; ++s) {
-        float v;
-        if (VARIANT == 0) {
-          // A: sum_k py_grad[s+k, t] (left to right) - px_grad[s-1, t]
-          float acc = __ldg(pyg + (int64_t)s * T + t);
-          for (int k = 1; k < R; ++k) acc += __ldg(pyg + (int64_t)(s + k) * T + t);
-          float pxp = (s == 0) ? 0.f : __ldg(pxg + (int64_t)(s - 1) * T1 + t);
-          v = acc - pxp;
+      if (VARIANT == 0) {
+        constexpr int kMaxR = 8;
+        if (R <= kMaxR) {
+          float w[kMaxR];
+#pragma unroll
+          for (int k = 0; k < kMaxR; ++k) w[k] = (k < R - 1) ? __ldg(pyg + (int64_t)k * T + t) : 0.f;
+          const float* py_in = pyg + (int64_t)(R - 1) * T + t;
+          const float* px_in = pxg + t - T1;  // px_grad[s-1, t]
+#pragma unroll 4
+          for (int s = 0; s < ncand; ++s) {
+            const float newest = __ldg(py_in + (int64_t)s * T);
+            const float pxp = (s == 0) ? 0.f : __ldg(px_in + (int64_t)s * T1);
+            float acc = w[0];
+#pragma unroll
+            for (int k = 1; k < kMaxR; ++k) {
+              if (k < R - 1) acc += w[k];
+            }
+            if (R > 1) acc += newest; else acc = newest;
+            const float v = acc - pxp;
+            if (v > best_v) {
+              best_v = v;
+              best = s;
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxR - 1; ++k) w[k] = w[k + 1];
+            if (R >= 2) {
+#pragma unroll
+              for (int k = 0; k < kMaxR; ++k)
+                if (k == R - 2) w[k] = newest;
+            }
+          }
         } else {
-          // B: cs[s+R] - cs[s] with cs the running sum over s of px_grad + py_grad
-          // (evaluated as the two prefix sums k2 would form, sequentially from 0)
-          float cs_lo = 0.f;
-          for (int j = 0; j < s; ++j) {
-            float tot = (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
-            cs_lo += tot;
+          for (int s = 0; s < ncand; ++s) {
+            float acc = __ldg(pyg + (int64_t)s * T + t);
+            for (int k = 1; k < R; ++k) acc += __ldg(pyg + (int64_t)(s + k) * T + t);
+            float pxp = (s == 0) ? 0.f : __ldg(pxg + (int64_t)(s - 1) * T1 + t);
+            const float v = acc - pxp;
+            if (v > best_v) {
+              best_v = v;
+              best = s;
+            }
           }
-          float cs_hi = cs_lo;
-          for (int j = s; j < s + R; ++j) {
-            float tot = (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
-            cs_hi += tot;
-          }
-          v = cs_hi - cs_lo;
         }
-        if (v > best_v) {  // strict: first maximum wins
-          best_v = v;
-          best = s;
+      } else {
+        // B: cs[s+R] - cs[s] with cs the running sum over s of px_grad + py_grad, formed sequentially
+        // from 0 exactly as the oracle does: cs_lo and cs_hi are two pointers into the same running sum.
+        float cs_hi = 0.f;
+        for (int j = 0; j < R; ++j)
+          cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+        float cs_lo = 0.f;
+        for (int s = 0; s < ncand; ++s) {
+          const float v = cs_hi - cs_lo;
+          if (v > best_v) {
+            best_v = v;
+            best = s;
+          }
+          if (s + 1 < ncand) {
+            cs_lo += (s < S ? __ldg(pxg + (int64_t)s * T1 + t) : 0.f) + __ldg(pyg + (int64_t)s * T + t);
+            const int j = s + R;
+            cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+          }
         }
       }
     } else {

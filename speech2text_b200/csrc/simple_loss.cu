@@ -120,24 +120,25 @@ struct GradAmEpilogue {  // d_am[b,t,c] = -exp(am - am_max) * acc
   }
 };
 
-// one thread per (b, t): add the one-hot terms of the occupation probabilities to d_am
+// one-hot terms of d_am: thread per (b, s, t), t fastest (coalesced occupation reads), scattered atomics
 __global__ void simple_scatter_am_kernel(const float* __restrict__ occ_px, const float* __restrict__ occ_py,
                                          const int64_t* __restrict__ sym, const float* __restrict__ coef,
                                          int B, int S, int T, int V, int blank, float* __restrict__ d_am) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)B * T) return;
-  int t = (int)(i % T), b = (int)(i / T);
-  float* row = d_am + i * V;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * (S + 1) * T;
+  if (i >= total) return;
+  const int t = (int)(i % T);
+  const int64_t bs = i / T;
+  const int s = (int)(bs % (S + 1));
+  const int b = (int)(bs / (S + 1));
   const float cf = coef[b];
-  float ysum = 0.f;
-  for (int s = 0; s <= S; ++s) {
-    ysum += occ_py[((int64_t)b * (S + 1) + s) * T + t];
-    if (s < S) {
-      float ox = occ_px[((int64_t)b * S + s) * (T + 1) + t];
-      if (ox != 0.f) row[sym[(int64_t)b * S + s]] += cf * ox;
-    }
+  float* row = d_am + ((int64_t)b * T + t) * V;
+  const float oy = occ_py[i];
+  if (oy != 0.f) atomicAdd(row + blank, cf * oy);
+  if (s < S) {
+    const float ox = occ_px[((int64_t)b * S + s) * (T + 1) + t];
+    if (ox != 0.f) atomicAdd(row + sym[(int64_t)b * S + s], cf * ox);
   }
-  row[blank] += cf * ysum;
 }
 
 // one warp per (b, s): add the one-hot terms to d_lm
@@ -210,10 +211,9 @@ int simple_backward(const float* am, const float* lm, const int64_t* sym, const 
     GradAmEpilogue ep{lm, lm_max, S + 1, V, d_lm};
     if (int rc = launch_sgemm<true, false>(B, S + 1, V, T, 1, a, bop, ep, stream, "simple_d_lm_gemm")) return rc;
   }
-  int64_t nbt = (int64_t)B * T;
   ProfScope prof2("simple_scatter_kernels", stream, 2);
-  simple_scatter_am_kernel<<<(unsigned)((nbt + 127) / 128), 128, 0, stream>>>(occ_px, occ_py, sym, coef, B, S,
-                                                                               T, V, blank, d_am);
+  simple_scatter_am_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(occ_px, occ_py, sym, coef, B, S,
+                                                                                 T, V, blank, d_am);
   int64_t nbs = (int64_t)B * (S + 1);
   simple_scatter_lm_kernel<<<(unsigned)((nbs + 7) / 8), 256, 0, stream>>>(occ_px, occ_py, sym, coef, B, S, T,
                                                                            V, blank, d_lm);
