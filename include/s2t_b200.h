@@ -79,17 +79,22 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
  * px_grad (B,S,T+1), py_grad (B,S+1,T).
  * lm_only_scale / am_only_scale must be 0 in this ABI version (the reference's
  * configs never set them; non-zero returns an error).
+ * mode: S2T_MODE_FP32_SIMT = fp32 FMA contraction; S2T_MODE_BF16_TC = 3xTF32 tensor-core
+ * normaliser (fp32-level accuracy) and bf16 tensor-core backward contractions.
+ * workspace: s2t_simple_workspace_bytes(mode,B,T,S,V) bytes.
  */
-int s2t_simple_loss_fwd(const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
+size_t s2t_simple_workspace_bytes(int mode, int B, int T, int S, int V);
+int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
                         int B, int T, int S, int V, int blank, float lm_only_scale, float am_only_scale,
-                        float* am_max, float* lm_max, float* px, float* py, float* nrm, float* alpha_ws,
-                        float* scores, float* px_grad, float* py_grad, void* stream);
+                        float* am_max, float* lm_max, float* px, float* py, float* nrm, void* alpha_ws,
+                        float* scores, float* px_grad, float* py_grad, void* workspace, void* stream);
 
 /* Backward of the above: grad_scores (B) = d loss / d scores[b].
- * wbuf: scratch (B,S+1,T).  d_am (B,T,V), d_lm (B,S+1,V) are overwritten. */
-int s2t_simple_loss_bwd(const float* am, const float* lm, const int64_t* symbols, const float* am_max,
+ * workspace: s2t_simple_workspace_bytes(mode,...) bytes (may be a fresh buffer).
+ * d_am (B,T,V), d_lm (B,S+1,V) are overwritten. */
+int s2t_simple_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols, const float* am_max,
                         const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,
-                        const float* grad_scores, int B, int T, int S, int V, int blank, float* wbuf,
+                        const float* grad_scores, int B, int T, int S, int V, int blank, void* workspace,
                         float* d_am, float* d_lm, void* stream);
 
 /* ---------------------------------------------------------------------------

@@ -36,6 +36,14 @@ int simple_backward(const float* am, const float* lm, const int64_t* sym, const 
                     const float* lm_max, const float* nrm, const float* occ_px, const float* occ_py,
                     const float* coef, int B, int T, int S, int V, int blank, float* wbuf, float* d_am,
                     float* d_lm, cudaStream_t stream);
+size_t simple_tc_workspace_bytes(int B, int T, int S, int V);
+int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
+                       int S, int V, int blank, float* am_max, float* lm_max, float* px, float* py, float* nrm,
+                       void* ws, cudaStream_t stream);
+int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, const float* am_max,
+                       const float* lm_max, const float* nrm, const float* occ_px, const float* occ_py,
+                       const float* coef, int B, int T, int S, int V, int blank, void* ws, float* d_am, float* d_lm,
+                       cudaStream_t stream);
 int prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boundary, int B, int S, int T, int R,
                  int variant, int64_t* ranges, cudaStream_t stream);
 int lse_gather(const void* logits, int dtype, const int64_t* sym, const int64_t* ranges, const int64_t* boundary,
@@ -144,25 +152,41 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
   return launch_lattice_fwd_bwd(v, scores, px_grad, py_grad, st);
 }
 
-int s2t_simple_loss_fwd(const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
+size_t s2t_simple_workspace_bytes(int mode, int B, int T, int S, int V) {
+  if (mode == S2T_MODE_BF16_TC) return simple_tc_workspace_bytes(B, T, S, V);
+  return (size_t)B * (S + 1) * T * sizeof(float) + 256;  // W scratch of the fp32 backward
+}
+
+int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
                         int B, int T, int S, int V, int blank, float lm_only_scale, float am_only_scale,
-                        float* am_max, float* lm_max, float* px, float* py, float* nrm, float* alpha_ws,
-                        float* scores, float* px_grad, float* py_grad, void* stream) {
+                        float* am_max, float* lm_max, float* px, float* py, float* nrm, void* alpha_ws,
+                        float* scores, float* px_grad, float* py_grad, void* workspace, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(lm_only_scale == 0.f && am_only_scale == 0.f,
               "simple_loss: non-zero lm_only_scale/am_only_scale (%g, %g) not supported by ABI v%d",
               lm_only_scale, am_only_scale, S2T_ABI_VERSION);
   S2T_REQUIRE(B > 0 && T > 0 && S >= 0 && V > 0, "simple_loss: bad dims B=%d T=%d S=%d V=%d", B, T, S, V);
   S2T_REQUIRE(blank >= 0 && blank < V, "simple_loss: blank %d out of range", blank);
-  if (int rc = simple_logprobs(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm, st))
-    return rc;
+  if (mode == S2T_MODE_BF16_TC) {
+    if (int rc = simple_logprobs_tc(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm,
+                                    workspace, st))
+      return rc;
+  } else {
+    if (int rc = simple_logprobs(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm, st))
+      return rc;
+  }
   return s2t_mutual_information(px, py, boundary, B, S, T, alpha_ws, scores, px_grad, py_grad, stream);
 }
 
-int s2t_simple_loss_bwd(const float* am, const float* lm, const int64_t* symbols, const float* am_max,
+int s2t_simple_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols, const float* am_max,
                         const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,
-                        const float* grad_scores, int B, int T, int S, int V, int blank, float* wbuf,
+                        const float* grad_scores, int B, int T, int S, int V, int blank, void* workspace,
                         float* d_am, float* d_lm, void* stream) {
+  if (mode == S2T_MODE_BF16_TC) {
+    return simple_backward_tc(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, grad_scores, B, T, S, V, blank,
+                              workspace, d_am, d_lm, (cudaStream_t)stream);
+  }
+  float* wbuf = (float*)workspace;
   return simple_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, grad_scores, B, T, S, V, blank,
                          wbuf, d_am, d_lm, (cudaStream_t)stream);
 }

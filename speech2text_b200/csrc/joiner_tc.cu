@@ -120,7 +120,7 @@ struct JointRowProducer {
   int64_t M;
   int V, act;
   template <class W, class A>
-  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t,
+  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t, int,
                       W wait_empty, A arrive_full) const {
     const int64_t m = (int64_t)m_tile * 128 + t;
     const bool live = m < M;
@@ -152,7 +152,7 @@ struct JointMnProducer {
   int64_t row0, M;
   int V, act;
   template <class W, class A>
-  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int v_tile, int ks0, int n_it, int t,
+  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int v_tile, int ks0, int n_it, int t, int,
                       W wait_empty, A arrive_full) const {
     const int r = t >> 1, g = t & 1;
     const int v_base = v_tile * 128 + g * 64;

@@ -168,6 +168,9 @@ __global__ void simple_scatter_lm_kernel(const float* __restrict__ occ_px, const
 
 }  // namespace
 
+int simple_scatter_onehot(const float* occ_px, const float* occ_py, const int64_t* sym, const float* coef, int B,
+                          int S, int T, int V, int blank, float* d_am, float* d_lm, cudaStream_t stream);
+
 int simple_logprobs(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary,
                     int B, int T, int S, int V, int blank, float* am_max, float* lm_max, float* px,
                     float* py, float* nrm, cudaStream_t stream) {
@@ -211,6 +214,14 @@ int simple_backward(const float* am, const float* lm, const int64_t* sym, const 
     GradAmEpilogue ep{lm, lm_max, S + 1, V, d_lm};
     if (int rc = launch_sgemm<true, false>(B, S + 1, V, T, 1, a, bop, ep, stream, "simple_d_lm_gemm")) return rc;
   }
+  return simple_scatter_onehot(occ_px, occ_py, sym, coef, B, S, T, V, blank, d_am, d_lm, stream);
+}
+
+// adds the one-hot terms of the occupation probabilities to d_am and d_lm
+int simple_scatter_onehot(const float* occ_px, const float* occ_py, const int64_t* sym, const float* coef, int B,
+                          int S, int T, int V, int blank, float* d_am, float* d_lm, cudaStream_t stream) {
+  const int64_t total = (int64_t)B * (S + 1) * T;
+  if (total == 0) return 0;
   ProfScope prof2("simple_scatter_kernels", stream, 2);
   simple_scatter_am_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(occ_px, occ_py, sym, coef, B, S,
                                                                                  T, V, blank, d_am);

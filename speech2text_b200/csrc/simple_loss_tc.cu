@@ -1,0 +1,302 @@
+// Tensor-core version of the simple-loss contractions (same maths as simple_loss.cu; replaces the
+// bmm inside k2.rnnt_loss_smoothed, /root/reference/model/joiner/joiner.py:100-110).
+//
+//   forward   acc[b, t, s] = sum_c exp(am[b,t,c] - am_max) * exp(lm[b,s,c] - lm_max)
+//             3xTF32 (fp32-level accuracy: these normalisers decide the prune ranges by an argmax);
+//             A = exp(am - max) built on the fly (big | small), B = packed exp(lm - max) (big, small);
+//             the epilogue thread owns one frame t and writes nrm / px / py columns s with the
+//             k2 (B,S,T) layout, i.e. coalesced along t across the warp.
+//   backward  d_am[b,t,c] = -exp(am - max) * sum_s W[b,s,t] exp(lm[b,s,c] - max)
+//             d_lm[b,s,c] = -exp(lm - max) * sum_t W[b,s,t] exp(am[b,t,c] - max)
+//             bf16 operands, MN-major (the contraction index is the row index of every packed operand),
+//             batched over b; the one-hot terms are added by the scatter kernels of simple_loss.cu.
+#include "tc_gemm.cuh"
+
+namespace s2t {
+
+int simple_scatter_onehot(const float* occ_px, const float* occ_py, const int64_t* sym, const float* coef, int B,
+                          int S, int T, int V, int blank, float* d_am, float* d_lm, cudaStream_t stream);
+
+namespace {
+
+using namespace tc;
+
+// one warp per row: max over V (shared with simple_loss.cu's kernel in spirit; kept local for the TC path)
+__global__ void tc_row_max_kernel(const float* __restrict__ x, int64_t rows, int V, float* __restrict__ out) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (row >= rows) return;
+  const int lane = threadIdx.x % 32;
+  const float* p = x + row * V;
+  float m = kNegInf;
+  for (int c = lane; c < V; c += 32) m = fmaxf(m, __ldg(p + c));
+  m = warp_max(m);
+  if (lane == 0) out[row] = m;
+}
+
+// K-major 3xTF32 A: rows = frames t of batch b, 32 vocabulary entries per k-step, value exp(am - am_max)
+struct ExpRowProducerF32 {
+  static constexpr bool kBulk = false;
+  const float* x;   // (B, rows, V)
+  const float* mx;  // (B, rows)
+  int rows, V;
+  template <class W, class A>
+  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t, int batch,
+                      W wait_empty, A arrive_full) const {
+    const int r = m_tile * 128 + t;
+    const bool live = r < rows;
+    const float* row = x + ((int64_t)batch * rows + (live ? r : 0)) * V;
+    const float sub = live ? __ldg(mx + (int64_t)batch * rows + r) : 0.f;
+    const bool vec = ((V & 3) == 0);
+    float4 cur[8], nxt[8];
+    auto load = [&](float4 (&dst)[8], int ks) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = ks * 32 + c * 4;
+        if (live && vec && k + 4 <= V) {
+          dst[c] = __ldg(reinterpret_cast<const float4*>(row + k));
+        } else {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = (live && k + j < V) ? __ldg(row + k + j) : kNegInf;
+          dst[c] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    };
+    load(cur, ks0);
+    for (int it = 0; it < n_it; ++it) {
+      if (it + 1 < n_it) load(nxt, ks0 + it + 1);
+      wait_empty(it);
+      uint8_t* dst = smem + (it % stages) * stage_bytes + t * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = (ks0 + it) * 32 + c * 4;
+        float e[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
+        float4 big, small;
+        float* pb = &big.x;
+        float* ps = &small.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float p = (live && k + j < V) ? expf(e[j] - sub) : 0.f;
+          pb[j] = round_tf32(p);
+          ps[j] = round_tf32(p - pb[j]);
+        }
+        const int off = ((c ^ (t & 7)) & 7) << 4;
+        *reinterpret_cast<float4*>(dst + off) = big;
+        *reinterpret_cast<float4*>(dst + kBlockBytes + off) = small;
+      }
+      arrive_full(it);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+    }
+  }
+};
+
+// accumulator rows = frames t (ctx.m inside batch ctx.batch), columns = symbol positions s
+struct SimpleEmitTcEpi {
+  const float* am;
+  const float* lm;
+  const float* am_max;
+  const float* lm_max;
+  const int64_t* sym;
+  const int64_t* boundary;
+  int T, S, V, blank;
+  float* px;   // (B, S, T+1)
+  float* py;   // (B, S+1, T)
+  float* nrm;  // (B, S+1, T)
+  struct State {
+    const float* am_row;
+    float amx, am_blank;
+    int Tb;
+    bool live;
+  };
+  __device__ void begin(State& st, const EpiCtx& ctx) const {
+    const int b = ctx.batch, t = ctx.m;
+    st.live = t < T;
+    st.am_row = am + ((int64_t)b * T + (st.live ? t : 0)) * V;
+    st.amx = st.live ? am_max[(int64_t)b * T + t] : 0.f;
+    st.am_blank = st.live ? __ldg(st.am_row + blank) : 0.f;
+    st.Tb = boundary ? (int)boundary[4 * b + 3] : T;
+  }
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    if (!st.live) return;
+    const int b = ctx.batch, t = ctx.m;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int s = n + j;
+      if (s > S) break;
+      const float* lm_row = lm + ((int64_t)b * (S + 1) + s) * V;
+      const float nv = logf(acc[j] + FLT_MIN) + __ldg(lm_max + (int64_t)b * (S + 1) + s) + st.amx;
+      const int64_t o = ((int64_t)b * (S + 1) + s) * T + t;
+      nrm[o] = nv;
+      py[o] = st.am_blank + __ldg(lm_row + blank) - nv;
+      if (s < S) {
+        const int c = (int)sym[(int64_t)b * S + s];
+        float* px_row = px + ((int64_t)b * S + s) * (T + 1);
+        const float v = __ldg(st.am_row + c) + __ldg(lm_row + c) - nv;
+        px_row[t] = (t == st.Tb) ? kNegInf : v;
+        if (t == T - 1) px_row[T] = kNegInf;
+      }
+    }
+  }
+};
+
+// W[b,s,t] = coef_b (occ_px + occ_py) exp(am_max + lm_max - nrm) -> bf16 packed twice:
+//   Wst: rows (b, s) cols t        Wts: rows (b, t) cols s
+__global__ void simple_w_packed_kernel(const float* __restrict__ occ_px, const float* __restrict__ occ_py,
+                                       const float* __restrict__ nrm, const float* __restrict__ am_max,
+                                       const float* __restrict__ lm_max, const float* __restrict__ coef, int B, int S,
+                                       int T, int Spad, int Tpad, uint8_t* __restrict__ Wst,
+                                       uint8_t* __restrict__ Wts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Spad * Tpad;
+  if (i >= total) return;
+  const int t = (int)(i % Tpad);
+  const int64_t bs = i / Tpad;
+  const int s = (int)(bs % Spad);
+  const int b = (int)(bs / Spad);
+  float w = 0.f;
+  if (s <= S && t < T) {
+    const int64_t o = ((int64_t)b * (S + 1) + s) * T + t;
+    float g = occ_py[o];
+    if (s < S) g += occ_px[((int64_t)b * S + s) * (T + 1) + t];
+    if (g != 0.f) w = coef[b] * g * expf(am_max[(int64_t)b * T + t] + lm_max[(int64_t)b * (S + 1) + s] - nrm[o]);
+  }
+  const __nv_bfloat16 wb = __float2bfloat16(w);
+  {
+    const int64_t r = (int64_t)b * Spad + s;  // row of Wst, column t
+    uint8_t* blk = Wst + packed_block_index((int)(r >> 7), t >> 6, (int)(((int64_t)B * Spad) >> 7)) * kBlockBytes;
+    *reinterpret_cast<__nv_bfloat16*>(blk + block_elem_offset((int)(r & 127), t & 63)) = wb;
+  }
+  {
+    const int64_t r = (int64_t)b * Tpad + t;  // row of Wts, column s
+    uint8_t* blk = Wts + packed_block_index((int)(r >> 7), s >> 6, (int)(((int64_t)B * Tpad) >> 7)) * kBlockBytes;
+    *reinterpret_cast<__nv_bfloat16*>(blk + block_elem_offset((int)(r & 127), s & 63)) = wb;
+  }
+}
+
+// out[b, r, c] = -exp(x[b, r, c] - max[b, r]) * acc      accumulator rows r (inside batch), cols c
+struct GradExpEpi {
+  const float* x;
+  const float* mx;
+  int rows, V;
+  float* out;
+  struct State { const float* xr; float* orow; float sub; bool live; };
+  __device__ void begin(State& st, const EpiCtx& ctx) const {
+    st.live = ctx.m < rows;
+    const int64_t r = (int64_t)ctx.batch * rows + (st.live ? ctx.m : 0);
+    st.xr = x + r * V;
+    st.orow = out + r * V;
+    st.sub = st.live ? mx[r] : 0.f;
+  }
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State& st, const EpiCtx&, int n, const float (&acc)[32]) const {
+    if (!st.live) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = n + j;
+      if (c < V) st.orow[c] = -expf(__ldg(st.xr + c) - st.sub) * acc[j];
+    }
+  }
+};
+
+struct SimpleTcDims {
+  int Spad, Tpad, Vp;  // S+1 and T padded to 128, V padded to 256
+  int kb32, kb64;      // vocabulary blocks of 32 (fp32) / 64 (bf16, = Vp / 64)
+  size_t lm_f32, am_bf16, lm_bf16, wst, wts;
+};
+
+SimpleTcDims simple_tc_dims(int B, int T, int S, int V) {
+  SimpleTcDims d;
+  d.Spad = ((S + 1 + 127) / 128) * 128;
+  d.Tpad = ((T + 127) / 128) * 128;
+  d.Vp = ((V + 255) / 256) * 256;
+  d.kb32 = (V + 31) / 32;
+  d.kb64 = d.Vp / 64;
+  d.lm_f32 = (size_t)B * (d.Spad / 128) * d.kb32 * kBlockBytes;
+  d.am_bf16 = (size_t)B * (d.Tpad / 128) * d.kb64 * kBlockBytes;
+  d.lm_bf16 = (size_t)B * (d.Spad / 128) * d.kb64 * kBlockBytes;
+  d.wst = (size_t)B * (d.Spad / 128) * (d.Tpad / 64) * kBlockBytes;
+  d.wts = (size_t)B * (d.Tpad / 128) * (d.Spad / 64) * kBlockBytes;
+  return d;
+}
+
+}  // namespace
+
+size_t simple_tc_workspace_bytes(int B, int T, int S, int V) {
+  SimpleTcDims d = simple_tc_dims(B, T, S, V);
+  return 2 * d.lm_f32 + d.am_bf16 + d.lm_bf16 + d.wst + d.wts + 4096;
+}
+
+int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
+                       int S, int V, int blank, float* am_max, float* lm_max, float* px, float* py, float* nrm,
+                       void* ws, cudaStream_t stream) {
+  SimpleTcDims d = simple_tc_dims(B, T, S, V);
+  uint8_t* lm_big = (uint8_t*)ws;
+  uint8_t* lm_small = lm_big + d.lm_f32;
+  const int wpb = 8;
+  const int64_t rows_am = (int64_t)B * T, rows_lm = (int64_t)B * (S + 1);
+  {
+    ProfScope prof("row_max_kernel", stream, 2);
+    tc_row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max);
+    tc_row_max_kernel<<<(unsigned)((rows_lm + wpb - 1) / wpb), wpb * 32, 0, stream>>>(lm, rows_lm, V, lm_max);
+  }
+  if (int rc = check_launch("row_max_kernel")) return rc;
+  PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
+  if (int rc = pack_f32_split(ps, lm_big, lm_small, stream)) return rc;
+  ExpRowProducerF32 a{am, am_max, T, V};
+  SimpleEmitTcEpi ep{am, lm, am_max, lm_max, sym, boundary, T, S, V, blank, px, py, nrm};
+  MnDebug extra;
+  extra.b_small = lm_small;
+  extra.b_batch_off = d.Spad / 128;
+  return launch_gemm_stream<128, 3, false, 2>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32, 1, ep,
+                                              stream, "tc_simple_normaliser_gemm_3xtf32", extra, B);
+}
+
+int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, const float* am_max,
+                       const float* lm_max, const float* nrm, const float* occ_px, const float* occ_py,
+                       const float* coef, int B, int T, int S, int V, int blank, void* ws, float* d_am, float* d_lm,
+                       cudaStream_t stream) {
+  SimpleTcDims d = simple_tc_dims(B, T, S, V);
+  uint8_t* p = (uint8_t*)ws + 2 * d.lm_f32;
+  uint8_t* am_p = p; p += d.am_bf16;
+  uint8_t* lm_p = p; p += d.lm_bf16;
+  uint8_t* Wst = p; p += d.wst;
+  uint8_t* Wts = p;
+  {
+    const int64_t total = (int64_t)B * d.Spad * d.Tpad;
+    ProfScope prof("simple_w_kernel", stream);
+    simple_w_packed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(occ_px, occ_py, nrm, am_max, lm_max,
+                                                                                coef, B, S, T, d.Spad, d.Tpad, Wst, Wts);
+  }
+  if (int rc = check_launch("simple_w_packed_kernel")) return rc;
+  PackSpec pa{am, (int64_t)T * V, V, B, T, d.Tpad, V, d.kb64, am_max};
+  if (int rc = pack_bf16(pa, am_p, stream)) return rc;
+  PackSpec pl{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb64, lm_max};
+  if (int rc = pack_bf16(pl, lm_p, stream)) return rc;
+  // d_am: rows t, cols c, contraction over s (rows of Wst and of lm_p)
+  {
+    BulkA a{Wst, B * (d.Spad / 128)};
+    GradExpEpi ep{am, am_max, T, V, d_am};
+    MnDebug extra;
+    extra.a_batch_off = d.Spad / 64;
+    extra.b_batch_off = d.Spad / 64;
+    if (int rc = launch_gemm_stream<256, 2, true, 0>(a, lm_p, B * (d.Spad / 128), d.Tpad / 128, d.Vp / 256, d.Spad / 64, 1,
+                                                     ep, stream, "tc_simple_d_am_gemm", extra, B))
+      return rc;
+  }
+  // d_lm: rows s, cols c, contraction over t (rows of Wts and of am_p)
+  {
+    BulkA a{Wts, B * (d.Tpad / 128)};
+    GradExpEpi ep{lm, lm_max, S + 1, V, d_lm};
+    MnDebug extra;
+    extra.a_batch_off = d.Tpad / 64;
+    extra.b_batch_off = d.Tpad / 64;
+    if (int rc = launch_gemm_stream<256, 2, true, 0>(a, am_p, B * (d.Tpad / 128), d.Spad / 128, d.Vp / 256, d.Tpad / 64, 1,
+                                                     ep, stream, "tc_simple_d_lm_gemm", extra, B))
+      return rc;
+  }
+  return simple_scatter_onehot(occ_px, occ_py, sym, coef, B, S, T, V, blank, d_am, d_lm, stream);
+}
+
+}  // namespace s2t

@@ -28,7 +28,7 @@
 //   struct ASrc { static constexpr bool kBulk;
 //       // kBulk : const uint8_t* packed; int row_blocks;   (row blocks of the packed array)
 //       // !kBulk: template <class W, class A> __device__ void run(uint8_t* smem, int stage_bytes, int stages,
-//       //             int m_tile, int ks0, int n_it, int t, W wait_empty, A arrive_full) const;
+//       //             int m_tile, int ks0, int n_it, int t, int batch, W wait_empty, A arrive_full) const;
 //       //         must, for it in [0, n_it): wait_empty(it); fill stage it % stages; arrive_full(it).
 //   };
 //   struct Epi {
@@ -51,7 +51,7 @@ struct EpiCtx {
   int m;        // global output row of this thread
   int t;        // epilogue thread index, 0..127
   int row;      // row inside the 128-row tile
-  int m_tile, n_tile, split;
+  int m_tile, n_tile, split, batch;
   uint8_t* scratch;
   int scratch_bytes;
 };
@@ -92,6 +92,10 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
   uint32_t sbo_bytes = 1024;
   uint32_t k_advance_bytes = 2048;  // 16 k-rows
   const uint8_t* b_small = nullptr;  // kKind == 2: packed residuals of B
+  // batched launches (blockIdx.z = batch * k_splits + split): operand offsets per batch, in 128-row
+  // blocks for K-major operands and in 64-row k-steps for MN-major operands
+  int a_batch_off = 0;
+  int b_batch_off = 0;
 };
 
 template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
@@ -114,7 +118,8 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int batch = blockIdx.z / k_splits, split = blockIdx.z % k_splits;
   const int per = (k_steps + k_splits - 1) / k_splits;
   const int ks0 = split * per;
   const int ks1 = min(k_steps, ks0 + per);
@@ -145,30 +150,32 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         mbar_arrive_expect_tx(&full[s], (ASrc::kBulk ? kABytes : 0) + kBBytes);
         if constexpr (!kMn) {
           if constexpr (ASrc::kBulk) {
-            bulk_copy_g2s(sa, asrc.packed + packed_block_index(m_tile, ks, asrc.row_blocks) * kBlockBytes, kABytes,
-                          &full[s]);
+            bulk_copy_g2s(sa, asrc.packed + packed_block_index(m_tile + batch * mn.a_batch_off, ks, asrc.row_blocks) *
+                                                kBlockBytes,
+                          kABytes, &full[s]);
           }
-          bulk_copy_g2s(sb, b_packed + packed_block_index(n_tile * (BN / 128), ks, b_row_blocks) * kBlockBytes,
-                        kBPart, &full[s]);
-          if constexpr (kKind == 2) {
-            bulk_copy_g2s(sb + kBPart, mn.b_small + packed_block_index(n_tile * (BN / 128), ks, b_row_blocks) * kBlockBytes,
-                          kBPart, &full[s]);
-          }
+          const size_t boff = packed_block_index(n_tile * (BN / 128) + batch * mn.b_batch_off, ks, b_row_blocks) *
+                              kBlockBytes;
+          bulk_copy_g2s(sb, b_packed + boff, kBPart, &full[s]);
+          if constexpr (kKind == 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
         } else {
           // k-step ks = 64 contraction rows = half of row block ks >> 1; group g = 64 columns = column block
-          const size_t half = (size_t)(ks & 1) * kGroupBytes;
           if constexpr (ASrc::kBulk) {
+            const int ka = ks + batch * mn.a_batch_off;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               bulk_copy_g2s(sa + g * kGroupBytes,
-                            asrc.packed + packed_block_index(ks >> 1, m_tile * 2 + g, asrc.row_blocks) * kBlockBytes + half,
+                            asrc.packed + packed_block_index(ka >> 1, m_tile * 2 + g, asrc.row_blocks) * kBlockBytes +
+                                (size_t)(ka & 1) * kGroupBytes,
                             kGroupBytes, &full[s]);
             }
           }
+          const int kb2 = ks + batch * mn.b_batch_off;
 #pragma unroll
           for (int g = 0; g < BN / 64; ++g) {
             bulk_copy_g2s(sb + g * kGroupBytes,
-                          b_packed + packed_block_index(ks >> 1, n_tile * (BN / 64) + g, b_row_blocks) * kBlockBytes + half,
+                          b_packed + packed_block_index(kb2 >> 1, n_tile * (BN / 64) + g, b_row_blocks) * kBlockBytes +
+                              (size_t)(kb2 & 1) * kGroupBytes,
                           kGroupBytes, &full[s]);
           }
         }
@@ -216,7 +223,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     const int t = (warp - 2) * 32 + lane;
     if constexpr (!ASrc::kBulk) {
       asrc.run(
-          smem, kStageBytes, kStages, m_tile, ks0, n_it, t,
+          smem, kStageBytes, kStages, m_tile, ks0, n_it, t, batch,
           [&](int it) { mbar_wait(&empty[it % kStages], ((it / kStages) & 1) ^ 1); },
           [&](int it) {
             fence_proxy_async_smem();
@@ -233,6 +240,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     ctx.m_tile = m_tile;
     ctx.n_tile = n_tile;
     ctx.split = split;
+    ctx.batch = batch;
     ctx.scratch = smem;
     ctx.scratch_bytes = kStages * kStageBytes;
     typename Epi::State st;
@@ -253,7 +261,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
 template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
 int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                        int k_steps, int k_splits, const Epi& epi, cudaStream_t stream, const char* what,
-                       MnDebug mn = MnDebug()) {
+                       MnDebug mn = MnDebug(), int batches = 1) {
   if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0) return 0;
   if (k_splits < 1) k_splits = 1;
   if (k_splits > k_steps) k_splits = k_steps;
@@ -268,7 +276,7 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
     }
     configured = true;
   }
-  dim3 grid(n_tiles, m_tiles, k_splits);
+  dim3 grid(n_tiles, m_tiles, k_splits * batches);
   S2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", what);
   ProfScope prof(what, stream);
   kern<<<grid, kGemmThreads, smem, stream>>>(asrc, b_packed, b_row_blocks, k_steps, k_splits, epi, mn);
@@ -310,6 +318,19 @@ int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int r
 int pack_operand_f32(const float* src, int64_t row_stride, int rows, int K, int row_blocks, int k_blocks,
                      int part, uint8_t* dst, cudaStream_t stream);
 
+// Batched packing with an optional fused exp: element (batch, r, k) = f(src[batch*batch_stride + r*row_stride + k])
+// with f(x) = exp(x - row_sub[batch*rows + r]) when row_sub != nullptr.  Every batch is padded to rows_pad
+// (a multiple of 128) rows, so the batches form one tall packed operand and never share a block.
+struct PackSpec {
+  const float* src;
+  int64_t batch_stride, row_stride;
+  int batches, rows, rows_pad, K;
+  int k_blocks;          // column blocks of the packed operand (64 bf16 / 32 fp32 elements each)
+  const float* row_sub;  // optional per-row value subtracted before exp
+};
+int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream);
+int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream);
+
 // On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage.
 struct RowCopyProducerF32 {
   static constexpr bool kBulk = false;
@@ -319,7 +340,7 @@ struct RowCopyProducerF32 {
   int K;
   bool split;  // also write the residual block right after the big block (3xTF32)
   template <class W, class A>
-  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t,
+  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t, int,
                       W wait_empty, A arrive_full) const {
     const int64_t m = (int64_t)m_tile * 128 + t;
     const bool live = m < M;

@@ -60,7 +60,71 @@ __global__ void pack_operand_f32_kernel(const float* __restrict__ src, int64_t r
   *reinterpret_cast<float4*>(blk + block_chunk_offset((int)(r % 128), (k0 % 32) / 4)) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// batched, optionally exponentiated packing: one thread per 16-byte chunk
+template <bool kF32>
+__global__ void pack_batched_kernel(PackSpec p, uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_small) {
+  constexpr int kPer = kF32 ? 4 : 8;  // elements per chunk
+  const int chunks_per_row = p.k_blocks * 8;
+  const int64_t total = (int64_t)p.batches * p.rows_pad * chunks_per_row;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ck = (int)(i % chunks_per_row);
+  const int64_t rp = i / chunks_per_row;  // padded global row
+  const int batch = (int)(rp / p.rows_pad), r = (int)(rp % p.rows_pad);
+  const int k0 = ck * kPer;
+  float v[kPer];
+  const bool row_ok = r < p.rows;
+  const float* src = p.src + (int64_t)batch * p.batch_stride + (int64_t)r * p.row_stride;
+  const float sub = (row_ok && p.row_sub) ? __ldg(p.row_sub + (int64_t)batch * p.rows + r) : 0.f;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    float x = 0.f;
+    if (row_ok && k0 + j < p.K) {
+      x = __ldg(src + k0 + j);
+      if (p.row_sub) x = expf(x - sub);
+    }
+    v[j] = x;
+  }
+  const int64_t rb = rp >> 7;
+  const int kb = ck >> 3;
+  const size_t off = packed_block_index((int)rb, kb, (int)(((int64_t)p.batches * p.rows_pad) >> 7)) * kBlockBytes +
+                     block_chunk_offset((int)(rp & 127), ck & 7);
+  if constexpr (kF32) {
+    float4 big, small;
+    big.x = round_tf32(v[0]); big.y = round_tf32(v[1]); big.z = round_tf32(v[2]); big.w = round_tf32(v[3]);
+    small.x = round_tf32(v[0] - big.x); small.y = round_tf32(v[1] - big.y);
+    small.z = round_tf32(v[2] - big.z); small.w = round_tf32(v[3] - big.w);
+    *reinterpret_cast<float4*>(dst + off) = big;
+    *reinterpret_cast<float4*>(dst_small + off) = small;
+  } else {
+    uint4 out;
+    out.x = pack_bf16x2(v[0], v[1]);
+    out.y = pack_bf16x2(v[2], v[3]);
+    out.z = pack_bf16x2(v[4], v[5]);
+    out.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + off) = out;
+  }
+}
+
 }  // namespace
+
+int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream) {
+  S2T_REQUIRE(p.rows_pad % 128 == 0 && p.rows_pad >= p.rows && p.k_blocks * 64 >= p.K, "pack_bf16: bad padding");
+  const int64_t total = (int64_t)p.batches * p.rows_pad * p.k_blocks * 8;
+  if (total == 0) return 0;
+  ProfScope prof("pack_operand_kernel", stream);
+  pack_batched_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, dst, nullptr);
+  return check_launch("pack_batched_kernel<bf16>");
+}
+
+int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream) {
+  S2T_REQUIRE(p.rows_pad % 128 == 0 && p.rows_pad >= p.rows && p.k_blocks * 32 >= p.K, "pack_f32_split: bad padding");
+  const int64_t total = (int64_t)p.batches * p.rows_pad * p.k_blocks * 8;
+  if (total == 0) return 0;
+  ProfScope prof("pack_operand_kernel", stream);
+  pack_batched_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, dst_big, dst_small);
+  return check_launch("pack_batched_kernel<f32>");
+}
 
 int pack_operand_f32(const float* src, int64_t row_stride, int rows, int K, int row_blocks, int k_blocks,
                      int part, uint8_t* dst, cudaStream_t stream) {

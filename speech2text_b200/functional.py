@@ -69,7 +69,7 @@ class _SimpleLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, am: Tensor, lm: Tensor, symbols: Tensor, boundary: Tensor, blank: int,
-                lm_only_scale: float, am_only_scale: float):
+                lm_only_scale: float, am_only_scale: float, mode: int):
         am, lm = _f32c(am), _f32c(lm)
         symbols, boundary = _i64c(symbols), _i64c(boundary)
         B, T, V = am.shape
@@ -86,12 +86,14 @@ class _SimpleLoss(torch.autograd.Function):
         scores = torch.empty((B,), **f32)
         px_grad = torch.empty((B, S, T + 1), **f32)
         py_grad = torch.empty((B, S + 1, T), **f32)
-        check(lib().s2t_simple_loss_fwd(ptr(am), ptr(lm), ptr(symbols), ptr(boundary), B, T, S, V, blank,
+        ws = torch.empty((lib().s2t_simple_workspace_bytes(mode, B, T, S, V),), dtype=torch.uint8, device=dev)
+        check(lib().s2t_simple_loss_fwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(boundary), B, T, S, V, blank,
                                         float(lm_only_scale), float(am_only_scale), ptr(am_max), ptr(lm_max),
                                         ptr(px), ptr(py), ptr(nrm), ptr(alpha), ptr(scores), ptr(px_grad),
-                                        ptr(py_grad), stream()))
+                                        ptr(py_grad), ptr(ws), stream()))
         ctx.save_for_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad)
         ctx.blank = blank
+        ctx.mode = mode
         ctx.mark_non_differentiable(px_grad, py_grad)
         return scores, px_grad, py_grad
 
@@ -101,27 +103,29 @@ class _SimpleLoss(torch.autograd.Function):
         B, T, V = am.shape
         S = lm.shape[1] - 1
         grad_scores = _f32c(grad_scores)
-        wbuf = torch.empty((B, S + 1, T), dtype=torch.float32, device=am.device)
+        ws = torch.empty((lib().s2t_simple_workspace_bytes(ctx.mode, B, T, S, V),), dtype=torch.uint8,
+                         device=am.device)
         d_am = torch.empty_like(am)
         d_lm = torch.empty_like(lm)
-        check(lib().s2t_simple_loss_bwd(ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
+        check(lib().s2t_simple_loss_bwd(ctx.mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
                                         ptr(px_grad), ptr(py_grad), ptr(grad_scores), B, T, S, V, ctx.blank,
-                                        ptr(wbuf), ptr(d_am), ptr(d_lm), stream()))
-        return d_am, d_lm, None, None, None, None, None
+                                        ptr(ws), ptr(d_am), ptr(d_lm), stream()))
+        return d_am, d_lm, None, None, None, None, None, None
 
 
 def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                        lm_only_scale: float = 0.0, am_only_scale: float = 0.0,
                        boundary: Optional[Tensor] = None, reduction: str = "mean",
-                       return_grad: bool = False):
-    """Drop-in for ``k2.rnnt_loss_smoothed`` (rnnt_type='regular')."""
+                       return_grad: bool = False, mode: int = _lib.MODE_FP32_SIMT):
+    """Drop-in for ``k2.rnnt_loss_smoothed`` (rnnt_type='regular').  ``mode`` picks the arithmetic of
+    the normaliser contraction: fp32 FMA, or tensor cores (3xTF32 forward, bf16 backward)."""
     if boundary is None:
         B, T = am.shape[0], am.shape[1]
         boundary = torch.zeros((B, 4), dtype=torch.int64, device=am.device)
         boundary[:, 2] = lm.shape[1] - 1
         boundary[:, 3] = T
     scores, px_grad, py_grad = _SimpleLoss.apply(am, lm, symbols, boundary, termination_symbol,
-                                                 lm_only_scale, am_only_scale)
+                                                 lm_only_scale, am_only_scale, mode)
     loss = _reduce(scores, reduction)
     return (loss, (px_grad, py_grad)) if return_grad else loss
 

@@ -154,7 +154,7 @@ class Joiner(nn.Module):
 
     @torch.jit.unused
     def _simple_loss_and_ranges(self, am: torch.Tensor, encoder_out_lengths: torch.Tensor, lm: torch.Tensor,
-                                target_lengths: torch.Tensor, target: torch.Tensor):
+                                target_lengths: torch.Tensor, target: torch.Tensor, mode: int = 0):
         """joiner.py:74-117 without the pruning gather: boundary, simple loss, ranges."""
         boundary = F2.make_boundary(target_lengths, encoder_out_lengths, am.device)
         assert len(target.shape) == 2  # (B, U)
@@ -172,6 +172,7 @@ class Joiner(nn.Module):
             boundary=boundary,
             reduction="mean",
             return_grad=True,
+            mode=mode,
         )
         ranges = F2.get_rnnt_prune_ranges(px_grad=px_grad, py_grad=py_grad, boundary=boundary,
                                           s_range=self.prune_range)
@@ -208,7 +209,7 @@ class Joiner(nn.Module):
         if self.prune_range > 0:
             assert target.shape[0] == target_lengths.shape[0]
             boundary, ranges, simple_loss = self._simple_loss_and_ranges(am, encoder_out_lengths, lm,
-                                                                         target_lengths, target)
+                                                                         target_lengths, target, mode)
         else:
             # For API consistency
             boundary = None
