@@ -24,6 +24,13 @@ using namespace tc;
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// CTA tile width (columns of the TMEM accumulator) and smem ring depth of the joiner contractions.
+// 256 columns x 2 stages = 96 KB + 256 TMEM columns: two CTAs per SM, whose prologue / mainloop /
+// epilogue phases overlap each other.  (128-wide tiles were measured slower: the on-the-fly A
+// operand is then produced once per 128 instead of once per 256 output columns.)
+constexpr int kBN = 256;
+constexpr int kNStages = 2;
+
 __device__ __forceinline__ float act_fwd_fast(float x, int act) { return act == kRelu ? fmaxf(x, 0.f) : tanh_fast(x); }
 __device__ __forceinline__ float act_bwd_fast(float x, int act) {
   if (act == kRelu) return x > 0.f ? 1.f : 0.f;
@@ -384,7 +391,7 @@ struct DJointEpi {
   int V, act;
   float* d_am;
   float* d_lm;
-  static constexpr int kLdW = 257;        // staged am / lm rows: 256 columns of the n-tile, odd stride
+  static constexpr int kLdW = kBN + 1;    // staged am / lm rows: the kBN columns of the n-tile, odd stride
   static constexpr int kMaxStaged = 64;   // (am + lm bucket rows) that fit the operand ring next to dj
   struct Scratch {
     float dj[128 * kLd];
@@ -462,14 +469,14 @@ struct DJointEpi {
     const int na = sc.n_slots[0], nl = sc.n_slots[1];
     st.staged = (na + nl) <= kMaxStaged;
     if (st.staged) {
-      const int n0 = ctx.n_tile * 256;
-      const int total = (na + nl) * 256;
+      const int n0 = ctx.n_tile * kBN;
+      const int total = (na + nl) * kBN;
       for (int i0 = ctx.t; i0 < total; i0 += 128 * 8) {
         float tmp[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
-          const int row = i >> 8, col = i & 255;
+          const int row = i / kBN, col = i % kBN;
           float x = 0.f;
           if (i < total && n0 + col < V) {
             x = row < na ? __ldg(am + (st.a_row0 + row) * V + n0 + col)
@@ -480,7 +487,7 @@ struct DJointEpi {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
-          if (i < total) sc.rows[(i >> 8) * kLdW + (i & 255)] = tmp[u];
+          if (i < total) sc.rows[(i / kBN) * kLdW + (i % kBN)] = tmp[u];
         }
       }
       st.sl += na;  // lm rows follow the am rows
@@ -491,7 +498,7 @@ struct DJointEpi {
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
     float* mine = sc.dj + ctx.t * kLd;
-    const int c0 = n - ctx.n_tile * 256;  // first column of this chunk inside the staged rows
+    const int c0 = n - ctx.n_tile * kBN;  // first column of this chunk inside the staged rows
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int v = n + j;
@@ -562,7 +569,7 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.Ip = ((I + 255) / 256) * 256;
   d.kbV = (V + 63) / 64;
   d.kbI = d.Ip / 64;
-  d.n_tiles_v = d.Vp / 256;
+  d.n_tiles_v = d.Vp / kBN;
   const size_t budget = (size_t)1 << 30;  // bytes of one orientation of the chunk's G
   int64_t rows = (int64_t)(budget / ((size_t)d.Vp * 2));
   rows = (rows / 128) * 128;
@@ -650,7 +657,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     JointRowProducer a{p.am, p.lm, w.am_off, w.lm_off, M, p.V, p.act};
     HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt};
-    if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / 256, d.kbV, 1, ep, stream,
+    if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
                                             "tc_joiner_hidden_gemm"))
       return rc;
   }
@@ -658,7 +665,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     BulkA a{w.Hp, d.Mt};
     LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_tiles_v, M, w.part, w.sym_logit, w.blank_logit};
-    if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
+    if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                    "tc_joiner_logits_lse_gemm"))
       return rc;
   }
@@ -690,7 +697,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
-      if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                      "tc_joiner_grad_logits_gemm"))
         return rc;
     }
@@ -698,16 +705,16 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Gp, ct};
       DHiddenEpi ep{p.I, w.DHp, ct, db1};
-      if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / 256, d.kbV, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / kBN, d.kbV, 1, ep, stream,
                                                      "tc_joiner_dhidden_gemm"))
         return rc;
     }
-    const int splits = max(1, min(kbM, sms / max(1, (d.Vp / 128) * (d.Ip / 256))));
+    const int splits = max(1, min(kbM, sms / max(1, (d.Vp / 128) * (d.Ip / kBN))));
     // dW2[v, i] += sum_m G[m, v] hidden[m, i]: both operands MN-major (contraction over the rows m)
     {
       BulkA a{w.Gp, ct};
       StoreRowMajorEpi ep{dW2, p.I, p.V, p.I, true};
-      if (int rc = launch_gemm_stream<256, 2, true, 0>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / 256,
+      if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / kBN,
                                                     kbM, splits, ep, stream, "tc_joiner_dW2_gemm"))
         return rc;
     }
@@ -715,7 +722,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       JointMnProducer a{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act};
       StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
-      if (int rc = launch_gemm_stream<256, 2, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / 256, kbM, splits, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, stream,
                                                     "tc_joiner_dW1_gemm"))
         return rc;
     }
@@ -723,7 +730,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       DJointEpi ep{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act, d_am, d_lm};
-      if (int rc = launch_gemm_stream<256, 2, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                      "tc_joiner_djoint_gemm"))
         return rc;
     }

@@ -99,7 +99,7 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
 };
 
 template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, kKind == 2 ? 1 : 2)
+__global__ void __launch_bounds__(kGemmThreads, kKind == 2 ? 1 : ((BN == 128 && ASrc::kBulk) ? 3 : 2))
 gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int k_steps, int k_splits,
                    Epi epi, MnDebug mn) {
   static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
