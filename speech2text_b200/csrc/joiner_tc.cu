@@ -25,11 +25,12 @@ using namespace tc;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // CTA tile width (columns of the TMEM accumulator) and smem ring depth of the joiner contractions.
-// 256 columns x 2 stages = 96 KB + 256 TMEM columns: two CTAs per SM, whose prologue / mainloop /
-// epilogue phases overlap each other.  (128-wide tiles were measured slower: the on-the-fly A
-// operand is then produced once per 128 instead of once per 256 output columns.)
+// 256 columns = both 256-column TMEM accumulator buffers of the persistent kernel; 48 KB per stage.
+// (128-wide tiles were measured slower: the on-the-fly A operand is then produced once per 128
+// instead of once per 256 output columns.)
 constexpr int kBN = 256;
-constexpr int kNStages = 2;
+constexpr int kNStages = 4;   // 192 KB ring
+constexpr int kNStagesDj = 2; // dJ epilogue keeps 84 KB of reduction scratch next to the ring
 
 __device__ __forceinline__ float act_fwd_fast(float x, int act) { return act == kRelu ? fmaxf(x, 0.f) : tanh_fast(x); }
 __device__ __forceinline__ float act_bwd_fast(float x, int act) {
@@ -117,7 +118,8 @@ __device__ __forceinline__ void joint_emit_half(const JointHalf& h, uint8_t* row
   }
 }
 
-// K-major A: block rows = joiner rows m of the tile, K = vocabulary.
+// K-major A: block rows = joiner rows m of the tile, K = vocabulary.  Two producer threads per row,
+// each owning one half (32 entries) of every 64-entry k-step.
 struct JointRowProducer {
   static constexpr bool kBulk = false;
   const float* am;
@@ -126,30 +128,27 @@ struct JointRowProducer {
   const int64_t* lm_off;
   int64_t M;
   int V, act;
-  template <class W, class A>
-  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t, int,
-                      W wait_empty, A arrive_full) const {
-    const int64_t m = (int64_t)m_tile * 128 + t;
+  __device__ void run(const ProdCtx& pc) const {
+    const int r = pc.t >> 1, half = pc.t & 1;
+    const int64_t m = (int64_t)pc.m_tile * 128 + r;
     const bool live = m < M;
     const float* a = am + (live ? am_off[m] : 0);
     const float* l = lm + (live ? lm_off[m] : 0);
     const bool vec = ((V & 3) == 0);
-    const int H = 2 * n_it;
     JointHalf cur, nxt;
-    joint_load_half(cur, a, l, ks0 * 64, V, live, vec);
-    for (int h = 0; h < H; ++h) {
-      const int it = h >> 1, half = h & 1;
-      if (h + 1 < H) joint_load_half(nxt, a, l, (ks0 + ((h + 1) >> 1)) * 64 + ((h + 1) & 1) * 32, V, live, vec);
-      if (half == 0) wait_empty(it);
-      uint8_t* row = smem + (it % stages) * stage_bytes + t * 128;
-      joint_emit_half(cur, row, t & 7, half * 4, act);
-      if (half == 1) arrive_full(it);
+    joint_load_half(cur, a, l, pc.ks0 * 64 + half * 32, V, live, vec);
+    for (int it = 0; it < pc.n_it; ++it) {
+      if (it + 1 < pc.n_it) joint_load_half(nxt, a, l, (pc.ks0 + it + 1) * 64 + half * 32, V, live, vec);
+      pc.wait_empty(it);
+      joint_emit_half(cur, pc.stage(it) + r * 128, r & 7, half * 4, act);
+      pc.arrive_full(it);
       cur = nxt;
     }
   }
 };
 
-// MN-major A: stage = 2 groups x [64 contraction rows (joiner rows m) x 64 vocabulary entries].
+// MN-major A: stage = 2 groups x [64 contraction rows (joiner rows m) x 64 vocabulary entries]; four
+// producer threads per contraction row (group x half).
 struct JointMnProducer {
   static constexpr bool kBulk = false;
   const float* am;
@@ -158,13 +157,10 @@ struct JointMnProducer {
   const int64_t* lm_off;
   int64_t row0, M;
   int V, act;
-  template <class W, class A>
-  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int v_tile, int ks0, int n_it, int t, int,
-                      W wait_empty, A arrive_full) const {
-    const int r = t >> 1, g = t & 1;
-    const int v_base = v_tile * 128 + g * 64;
+  __device__ void run(const ProdCtx& pc) const {
+    const int r = pc.t >> 2, g = (pc.t >> 1) & 1, half = pc.t & 1;
+    const int v_base = pc.m_tile * 128 + g * 64 + half * 32;
     const bool vec = ((V & 3) == 0);
-    const int H = 2 * n_it;
     auto row_ptrs = [&](int ks, const float*& a, const float*& l, bool& live) {
       const int64_t m = row0 + (int64_t)ks * 64 + r;
       live = m < M;
@@ -175,21 +171,19 @@ struct JointMnProducer {
     {
       const float *a, *l;
       bool live;
-      row_ptrs(ks0, a, l, live);
+      row_ptrs(pc.ks0, a, l, live);
       joint_load_half(cur, a, l, v_base, V, live, vec);
     }
-    for (int h = 0; h < H; ++h) {
-      const int it = h >> 1, half = h & 1;
-      if (h + 1 < H) {
+    for (int it = 0; it < pc.n_it; ++it) {
+      if (it + 1 < pc.n_it) {
         const float *a, *l;
         bool live;
-        row_ptrs(ks0 + ((h + 1) >> 1), a, l, live);
-        joint_load_half(nxt, a, l, v_base + ((h + 1) & 1) * 32, V, live, vec);
+        row_ptrs(pc.ks0 + it + 1, a, l, live);
+        joint_load_half(nxt, a, l, v_base, V, live, vec);
       }
-      if (half == 0) wait_empty(it);
-      uint8_t* row = smem + (it % stages) * stage_bytes + g * kGroupBytes + r * 128;
-      joint_emit_half(cur, row, r & 7, half * 4, act);
-      if (half == 1) arrive_full(it);
+      pc.wait_empty(it);
+      joint_emit_half(cur, pc.stage(it) + g * kGroupBytes + r * 128, r & 7, half * 4, act);
+      pc.arrive_full(it);
       cur = nxt;
     }
   }
@@ -211,6 +205,7 @@ __device__ __forceinline__ void store_packed_row32(uint8_t* packed, int row_bloc
 }
 // hidden = acc + b1 -> Hp (rows m, cols i)
 struct HiddenEpi {
+  static constexpr int kScratchBytes = 0;
   const float* b1;
   int I;
   int64_t M;
@@ -230,6 +225,7 @@ struct HiddenEpi {
 
 // logits = acc + b2: per-tile (max, sum exp) and the gathered sym / blank logits
 struct LseEpi {
+  static constexpr int kScratchBytes = 0;
   const float* b2;
   const int* row_sym;
   int V, blank, n_tiles;
@@ -305,6 +301,7 @@ __global__ void lse_combine_kernel(const float* __restrict__ part, const float* 
 
 // G = coef * clip(occ_px [v == sym] + occ_py [v == blank] - (occ_px + occ_py) softmax) for a row chunk
 struct GradEpi {
+  static constexpr int kScratchBytes = 0;
   const float* b2;
   const int* row_sym;
   const float* lse;
@@ -357,6 +354,7 @@ struct GradEpi {
 
 // dhidden -> DHp (rows chunk-local m, cols i), db1
 struct DHiddenEpi {
+  static constexpr int kScratchBytes = 0;
   int I;
   uint8_t* DHp;
   int dh_row_blocks;
@@ -401,6 +399,7 @@ struct DJointEpi {
     int order[2][128];
     int n_slots[2];
   };
+  static constexpr int kScratchBytes = sizeof(Scratch);
   struct State {
     int64_t ao, lo;
     int64_t a_row0, l_row0;
@@ -538,6 +537,7 @@ struct DJointEpi {
 
 // C^T accumulate: out[(n + j) * ld + m] += acc[j]     (dW1[i, v] from the (v, i) accumulator)
 struct StoreTransposedAtomicEpi {
+  static constexpr int kScratchBytes = 0;
   float* out;
   int64_t ld;
   int M, N;  // valid rows (v) and columns (i) of the accumulator
@@ -730,8 +730,8 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       DJointEpi ep{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act, d_am, d_lm};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
-                                                     "tc_joiner_djoint_gemm"))
+      if (int rc = launch_gemm_stream<kBN, kNStagesDj, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep,
+                                                                 stream, "tc_joiner_djoint_gemm"))
         return rc;
     }
   }

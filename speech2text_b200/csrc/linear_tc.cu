@@ -104,7 +104,7 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
   if (dx) {
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dx, K, (int)M, K, false, nullptr};
-    if (int rc = tc::launch_gemm_stream<256, 2, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
+    if (int rc = tc::launch_gemm_stream<256, 4, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
                                                        "tc_linear_dx_gemm"))
       return rc;
   }
@@ -117,7 +117,7 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
     if (splits < 1) splits = 1;
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dW, K, N, K, true, nullptr};
-    if (int rc = tc::launch_gemm_stream<256, 2, true, 0>(a, px, d.Mt, d.Np / 128, d.Kp / 256, k_steps, splits, ep, st,
+    if (int rc = tc::launch_gemm_stream<256, 4, true, 0>(a, px, d.Mt, d.Np / 128, d.Kp / 256, k_steps, splits, ep, st,
                                                       "tc_linear_dW_gemm"))
       return rc;
     ProfScope prof("linear_col_sum_kernel", st);

@@ -39,19 +39,18 @@ struct ExpRowProducerF32 {
   const float* x;   // (B, rows, V)
   const float* mx;  // (B, rows)
   int rows, V;
-  template <class W, class A>
-  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t, int batch,
-                      W wait_empty, A arrive_full) const {
-    const int r = m_tile * 128 + t;
+  __device__ void run(const ProdCtx& pc) const {
+    const int rr = pc.t >> 1, half = pc.t & 1;  // two producer threads per row, four chunks each
+    const int r = pc.m_tile * 128 + rr;
     const bool live = r < rows;
-    const float* row = x + ((int64_t)batch * rows + (live ? r : 0)) * V;
-    const float sub = live ? __ldg(mx + (int64_t)batch * rows + r) : 0.f;
+    const float* row = x + ((int64_t)pc.batch * rows + (live ? r : 0)) * V;
+    const float sub = live ? __ldg(mx + (int64_t)pc.batch * rows + r) : 0.f;
     const bool vec = ((V & 3) == 0);
-    float4 cur[8], nxt[8];
-    auto load = [&](float4 (&dst)[8], int ks) {
+    float4 cur[4], nxt[4];
+    auto load = [&](float4 (&dst)[4], int ks) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int k = ks * 32 + c * 4;
+      for (int c = 0; c < 4; ++c) {
+        const int k = ks * 32 + (half * 4 + c) * 4;
         if (live && vec && k + 4 <= V) {
           dst[c] = __ldg(reinterpret_cast<const float4*>(row + k));
         } else {
@@ -62,37 +61,38 @@ struct ExpRowProducerF32 {
         }
       }
     };
-    load(cur, ks0);
-    for (int it = 0; it < n_it; ++it) {
-      if (it + 1 < n_it) load(nxt, ks0 + it + 1);
-      wait_empty(it);
-      uint8_t* dst = smem + (it % stages) * stage_bytes + t * 128;
+    load(cur, pc.ks0);
+    for (int it = 0; it < pc.n_it; ++it) {
+      if (it + 1 < pc.n_it) load(nxt, pc.ks0 + it + 1);
+      pc.wait_empty(it);
+      uint8_t* dst = pc.stage(it) + rr * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int k = (ks0 + it) * 32 + c * 4;
+      for (int c = 0; c < 4; ++c) {
+        const int k = (pc.ks0 + it) * 32 + (half * 4 + c) * 4;
         float e[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
         float4 big, small;
         float* pb = &big.x;
         float* ps = &small.x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float p = (live && k + j < V) ? expf(e[j] - sub) : 0.f;
+          const float p = (live && k + j < V) ? __expf(e[j] - sub) : 0.f;
           pb[j] = round_tf32(p);
           ps[j] = round_tf32(p - pb[j]);
         }
-        const int off = ((c ^ (t & 7)) & 7) << 4;
+        const int off = (((half * 4 + c) ^ (rr & 7)) & 7) << 4;
         *reinterpret_cast<float4*>(dst + off) = big;
         *reinterpret_cast<float4*>(dst + kBlockBytes + off) = small;
       }
-      arrive_full(it);
+      pc.arrive_full(it);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+      for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
     }
   }
 };
 
 // accumulator rows = frames t (ctx.m inside batch ctx.batch), columns = symbol positions s
 struct SimpleEmitTcEpi {
+  static constexpr int kScratchBytes = 0;
   const float* am;
   const float* lm;
   const float* am_max;
@@ -177,6 +177,7 @@ __global__ void simple_w_packed_kernel(const float* __restrict__ occ_px, const f
 
 // out[b, r, c] = -exp(x[b, r, c] - max[b, r]) * acc      accumulator rows r (inside batch), cols c
 struct GradExpEpi {
+  static constexpr int kScratchBytes = 0;
   const float* x;
   const float* mx;
   int rows, V;
@@ -281,7 +282,7 @@ int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, con
     MnDebug extra;
     extra.a_batch_off = d.Spad / 64;
     extra.b_batch_off = d.Spad / 64;
-    if (int rc = launch_gemm_stream<256, 2, true, 0>(a, lm_p, B * (d.Spad / 128), d.Tpad / 128, d.Vp / 256, d.Spad / 64, 1,
+    if (int rc = launch_gemm_stream<256, 4, true, 0>(a, lm_p, B * (d.Spad / 128), d.Tpad / 128, d.Vp / 256, d.Spad / 64, 1,
                                                      ep, stream, "tc_simple_d_am_gemm", extra, B))
       return rc;
   }
@@ -292,7 +293,7 @@ int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, con
     MnDebug extra;
     extra.a_batch_off = d.Tpad / 64;
     extra.b_batch_off = d.Tpad / 64;
-    if (int rc = launch_gemm_stream<256, 2, true, 0>(a, am_p, B * (d.Tpad / 128), d.Spad / 128, d.Vp / 256, d.Tpad / 64, 1,
+    if (int rc = launch_gemm_stream<256, 4, true, 0>(a, am_p, B * (d.Tpad / 128), d.Spad / 128, d.Vp / 256, d.Tpad / 64, 1,
                                                      ep, stream, "tc_simple_d_lm_gemm", extra, B))
       return rc;
   }

@@ -3,15 +3,18 @@
 //     K-major  (kMn = false):  C[m, n] (+)= sum_k A[m, k]  * B[n, k]     operands stored (rows, K)
 //     MN-major (kMn = true):   C[m, n] (+)= sum_k At[k, m] * Bt[k, n]    operands stored (K, rows)
 //
-// One CTA owns a 128 x BN output tile whose accumulator lives in TMEM; a single elected thread
-// issues tcgen05.mma (M=128, N=BN, K=16) over 64-deep K steps that arrive in shared memory
-// through a kStages-deep mbarrier ring.  Warp roles (192 threads):
-//   warp 0      bulk-copy issuer (cp.async.bulk, TMA engine) for the packed operands
-//   warp 1      TMEM allocation + MMA issue + commits
-//   warps 2..5  (a) optional on-the-fly A producer -- the threads build the A stage (e.g.
-//               act(am + lm[ranges]) -> bf16) directly in the swizzled smem image, so the operand
-//               never exists in HBM;  (b) epilogue: tcgen05.ld the accumulator (one TMEM lane = one
-//               output row per thread) and hand 32-column chunks to the epilogue functor.
+// Persistent kernel, one CTA per SM, looping over 128 x BN output tiles.  The accumulators live in
+// TMEM (two buffers); a single elected thread issues tcgen05.mma (M=128, N=BN, K=16) over 64-deep
+// K steps that arrive in shared memory through a kStages-deep mbarrier ring which keeps running
+// across tile boundaries.  Warp roles:
+//   warp 0       bulk-copy issuer (cp.async.bulk, TMA engine) for the packed operands
+//   warp 1       TMEM allocation + MMA issue + commits
+//   warps 4..7   epilogue: tcgen05.ld the finished accumulator (one TMEM lane = one output row per
+//                thread) and hand 32-column chunks to the epilogue functor, while the MMA warp is
+//                already filling the other TMEM buffer with the next tile
+//   warps 8..15  (only with an on-the-fly A source) producers: build the A stage, e.g.
+//                act(am + lm[ranges]) -> bf16, directly in the swizzled smem image, so the operand
+//                never exists in HBM
 //
 // Both modes read the SAME packed format (tc_prims.cuh): 128 x 64 blocks, 128 B per row, 16-byte
 // chunks XOR-swizzled by (row & 7).  For a K-major operand the block rows are the operand's
@@ -27,9 +30,8 @@
 // Functor contracts
 //   struct ASrc { static constexpr bool kBulk;
 //       // kBulk : const uint8_t* packed; int row_blocks;   (row blocks of the packed array)
-//       // !kBulk: template <class W, class A> __device__ void run(uint8_t* smem, int stage_bytes, int stages,
-//       //             int m_tile, int ks0, int n_it, int t, int batch, W wait_empty, A arrive_full) const;
-//       //         must, for it in [0, n_it): wait_empty(it); fill stage it % stages; arrive_full(it).
+//       // !kBulk: __device__ void run(const ProdCtx&) const;  called by kProdThreads threads per tile; must,
+//       //         for it in [0, n_it): pc.wait_empty(it); fill pc.stage(it); pc.arrive_full(it).
 //   };
 //   struct Epi {
 //     struct State {...};                       // per-thread (= per output row) running state
@@ -37,9 +39,8 @@
 //     __device__ void chunk(State&, const EpiCtx&, int n, const float (&acc)[32]) const;   // 32 columns from n
 //     __device__ void end(State&, const EpiCtx&) const;
 //   };
-// During the epilogue all MMAs of the CTA have completed, so the operand ring is free:
-// EpiCtx::scratch points at it (kStages * stage bytes) for CTA-level reductions; epi_sync()
-// is a barrier over the 128 epilogue threads.
+// Epi::kScratchBytes of shared memory are reserved for CTA-level reductions of the epilogue
+// (EpiCtx::scratch); epi_sync() is a barrier over the 128 epilogue threads.
 #pragma once
 #include "common.cuh"
 #include "tc_prims.cuh"
@@ -64,15 +65,29 @@ struct BulkA {
   int row_blocks;
 };
 
-constexpr int kGemmThreads = 192;
+// Warp roles of the persistent kernel.  Epilogue warps are 4..7 so that (warp & 3) is the TMEM lane
+// quarter each may read; warps 2..3 only take part in the CTA-wide barriers.
+constexpr int kCtrlWarps = 4;
+constexpr int kEpiWarps = 4;
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kGroupBytes = 64 * 128;  // one MN-major group: 64 k-rows x 64 elements
+
+template <class ASrc>
+constexpr int gemm_threads() {
+  return 32 * (kCtrlWarps + kEpiWarps + (ASrc::kBulk ? 0 : kProdWarps));
+}
 
 // kKind: 0 = bf16 operands; 1 = tf32 (fp32 in smem, single pass); 2 = 3xTF32: every fp32 operand is held
 // as big = rn_tf32(x) and small = x - big, and D += A_big B_big + A_big B_small + A_small B_big, which
 // recovers fp32-level accuracy (error ~2^-21) on the tensor cores.
-template <int BN, int kStages, int kKind = 0>
+template <int BN, int kKind>
+constexpr int gemm_stage_bytes() {
+  return (kKind == 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
+}
+template <int BN, int kStages, int kKind, class Epi>
 constexpr size_t gemm_stream_smem_bytes() {
-  return (size_t)kStages * (kKind == 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes) + 1024 /*align*/ +
+  return (size_t)kStages * gemm_stage_bytes<BN, kKind>() + ((Epi::kScratchBytes + 127) / 128) * 128 + 1024 /*align*/ +
          256 /*barriers*/;
 }
 
@@ -92,181 +107,276 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
   uint32_t sbo_bytes = 1024;
   uint32_t k_advance_bytes = 2048;  // 16 k-rows
   const uint8_t* b_small = nullptr;  // kKind == 2: packed residuals of B
-  // batched launches (blockIdx.z = batch * k_splits + split): operand offsets per batch, in 128-row
-  // blocks for K-major operands and in 64-row k-steps for MN-major operands
+  // batched launches: operand offsets per batch, in 128-row blocks for K-major operands and in
+  // 64-row k-steps for MN-major operands
   int a_batch_off = 0;
   int b_batch_off = 0;
 };
 
+// What an on-the-fly A producer sees for one tile: kProdThreads threads fill stage(it) for it in [0, n_it).
+struct ProdCtx {
+  int m_tile, batch, ks0, n_it;
+  int t;  // producer thread index, 0 .. kProdThreads-1
+  uint8_t* smem;
+  int stage_bytes, stages;
+  uint32_t it0;  // ring position of the tile's first k-step
+  uint64_t* full;
+  uint64_t* empty;
+  __device__ __forceinline__ uint8_t* stage(int it) const { return smem + ((it0 + it) % stages) * stage_bytes; }
+  __device__ __forceinline__ void wait_empty(int it) const {
+    const uint32_t g = it0 + it;
+    mbar_wait(&empty[g % stages], ((g / stages) & 1) ^ 1);
+  }
+  __device__ __forceinline__ void arrive_full(int it) const {
+    fence_proxy_async_smem();
+    mbar_arrive(&full[(it0 + it) % stages]);
+  }
+};
+
+struct TileCoord {
+  int n_tile, m_tile, batch, split, ks0, n_it;
+};
+
+// Persistent, warp-specialised contraction kernel: one CTA per SM loops over output tiles
+// (n fastest, so the CTAs running together share A rows in L2).  The smem operand ring and the
+// two TMEM accumulator buffers run across tile boundaries: while the epilogue warps drain tile i
+// from one TMEM buffer, the MMA warp already accumulates tile i+1 into the other and the copy /
+// producer warps fill the ring for it.
 template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, kKind == 2 ? 1 : ((BN == 128 && ASrc::kBulk) ? 3 : 2))
-gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int k_steps, int k_splits,
-                   Epi epi, MnDebug mn) {
+__global__ void __launch_bounds__(gemm_threads<ASrc>(), 1)
+gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int m_tiles, int n_tiles,
+                   int batches, int k_steps, int k_splits, Epi epi, MnDebug mn) {
   static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
   constexpr int kParts = kKind == 2 ? 2 : 1;
   constexpr int kABytes = kParts * kBlockBytes;
   constexpr int kBPart = (BN / 128) * kBlockBytes;
   constexpr int kBBytes = kParts * kBPart;
   constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kScratch = ((Epi::kScratchBytes + 127) / 128) * 128;
+  constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
   static_assert(kKind != 2 || !ASrc::kBulk, "3xTF32 expects an on-the-fly A producer that writes big|small");
+  static_assert(kKind == 0 || !kMn, "tf32 operands are K-major only");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* scratch = smem + kStages * kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(scratch + kScratch);
   uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-  const int batch = blockIdx.z / k_splits, split = blockIdx.z % k_splits;
+  const int num_tiles = n_tiles * m_tiles * batches * k_splits;
   const int per = (k_steps + k_splits - 1) / k_splits;
-  const int ks0 = split * per;
-  const int ks1 = min(k_steps, ks0 + per);
-  const int n_it = ks1 - ks0;
-  if (n_it <= 0) return;
+  auto decode = [&](int tile) {
+    TileCoord c;
+    c.n_tile = tile % n_tiles;
+    int rest = tile / n_tiles;
+    c.m_tile = rest % m_tiles;
+    rest /= m_tiles;
+    c.split = rest % k_splits;
+    c.batch = rest / k_splits;
+    c.ks0 = c.split * per;
+    c.n_it = min(k_steps, c.ks0 + per) - c.ks0;
+    return c;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + 128);
+      mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + kProdThreads);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 32 * kEpiWarps);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ---------------- bulk-copy issuer ----------------
     if (lane == 0) {
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1, ks = ks0 + it;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sa = smem + s * kStageBytes;
-        uint8_t* sb = sa + kABytes;
-        mbar_arrive_expect_tx(&full[s], (ASrc::kBulk ? kABytes : 0) + kBBytes);
-        if constexpr (!kMn) {
-          if constexpr (ASrc::kBulk) {
-            bulk_copy_g2s(sa, asrc.packed + packed_block_index(m_tile + batch * mn.a_batch_off, ks, asrc.row_blocks) *
-                                                kBlockBytes,
-                          kABytes, &full[s]);
-          }
-          const size_t boff = packed_block_index(n_tile * (BN / 128) + batch * mn.b_batch_off, ks, b_row_blocks) *
-                              kBlockBytes;
-          bulk_copy_g2s(sb, b_packed + boff, kBPart, &full[s]);
-          if constexpr (kKind == 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
-        } else {
-          // k-step ks = 64 contraction rows = half of row block ks >> 1; group g = 64 columns = column block
-          if constexpr (ASrc::kBulk) {
-            const int ka = ks + batch * mn.a_batch_off;
+      uint32_t git = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord c = decode(tile);
+        for (int it = 0; it < c.n_it; ++it, ++git) {
+          const int s = git % kStages, ks = c.ks0 + it;
+          mbar_wait(&empty[s], ((git / kStages) & 1) ^ 1);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full[s], (ASrc::kBulk ? kABytes : 0) + kBBytes);
+          if constexpr (!kMn) {
+            if constexpr (ASrc::kBulk) {
+              bulk_copy_g2s(sa,
+                            asrc.packed + packed_block_index(c.m_tile + c.batch * mn.a_batch_off, ks, asrc.row_blocks) *
+                                              kBlockBytes,
+                            kABytes, &full[s]);
+            }
+            const size_t boff =
+                packed_block_index(c.n_tile * (BN / 128) + c.batch * mn.b_batch_off, ks, b_row_blocks) * kBlockBytes;
+            bulk_copy_g2s(sb, b_packed + boff, kBPart, &full[s]);
+            if constexpr (kKind == 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
+          } else {
+            // k-step = 64 contraction rows = half of a 128-row block; group = 64 columns = one column block
+            if constexpr (ASrc::kBulk) {
+              const int ka = ks + c.batch * mn.a_batch_off;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              bulk_copy_g2s(sa + g * kGroupBytes,
-                            asrc.packed + packed_block_index(ka >> 1, m_tile * 2 + g, asrc.row_blocks) * kBlockBytes +
-                                (size_t)(ka & 1) * kGroupBytes,
+              for (int g = 0; g < 2; ++g) {
+                bulk_copy_g2s(sa + g * kGroupBytes,
+                              asrc.packed + packed_block_index(ka >> 1, c.m_tile * 2 + g, asrc.row_blocks) * kBlockBytes +
+                                  (size_t)(ka & 1) * kGroupBytes,
+                              kGroupBytes, &full[s]);
+              }
+            }
+            const int kb2 = ks + c.batch * mn.b_batch_off;
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) {
+              bulk_copy_g2s(sb + g * kGroupBytes,
+                            b_packed + packed_block_index(kb2 >> 1, c.n_tile * (BN / 64) + g, b_row_blocks) * kBlockBytes +
+                                (size_t)(kb2 & 1) * kGroupBytes,
                             kGroupBytes, &full[s]);
             }
-          }
-          const int kb2 = ks + batch * mn.b_batch_off;
-#pragma unroll
-          for (int g = 0; g < BN / 64; ++g) {
-            bulk_copy_g2s(sb + g * kGroupBytes,
-                          b_packed + packed_block_index(kb2 >> 1, n_tile * (BN / 64) + g, b_row_blocks) * kBlockBytes +
-                              (size_t)(kb2 & 1) * kGroupBytes,
-                          kGroupBytes, &full[s]);
           }
         }
       }
     }
   } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      // kKind 0: bf16 operands (64 per 128-byte row);  1: tf32 (fp32 in smem, 32 per row, K-major only)
-      static_assert(kKind == 0 || !kMn, "tf32 operands are K-major only");
       uint32_t idesc = kKind == 0 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
       if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t git = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord c = decode(tile);
+        if (c.n_it <= 0) continue;
+        const uint32_t buf = lt & 1;
+        mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * kStageBytes);
-        const uint32_t sb = sa + kABytes;
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int it = 0; it < c.n_it; ++it, ++git) {
+          const int s = git % kStages;
+          mbar_wait(&full[s], (git / kStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * kStageBytes);
+          const uint32_t sb = sa + kABytes;
 #pragma unroll
-        for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-          uint64_t da, db;
-          if constexpr (!kMn) {
-            da = umma_smem_desc(sa + k4 * kUmmaK * 2);
-            db = umma_smem_desc(sb + k4 * kUmmaK * 2);
-          } else {
-            da = umma_smem_desc_mn(sa + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
-            db = umma_smem_desc_mn(sb + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
+          for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+            uint64_t da, db;
+            if constexpr (!kMn) {
+              da = umma_smem_desc(sa + k4 * kUmmaK * 2);
+              db = umma_smem_desc(sb + k4 * kUmmaK * 2);
+            } else {
+              da = umma_smem_desc_mn(sa + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
+              db = umma_smem_desc_mn(sb + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
+            }
+            const bool accum = (it > 0) || (k4 > 0);
+            if constexpr (kKind == 0) {
+              umma_bf16(acc, da, db, idesc, accum);
+            } else if constexpr (kKind == 1) {
+              umma_tf32(acc, da, db, idesc, accum);
+            } else {
+              const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
+              const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
+              umma_tf32(acc, da_s, db, idesc, accum);  // small terms first
+              umma_tf32(acc, da, db_s, idesc, true);
+              umma_tf32(acc, da, db, idesc, true);
+            }
           }
-          if constexpr (kKind == 0) {
-            umma_bf16(tmem_base, da, db, idesc, (it > 0) || (k4 > 0));
-          } else if constexpr (kKind == 1) {
-            umma_tf32(tmem_base, da, db, idesc, (it > 0) || (k4 > 0));
-          } else {
-            const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
-            const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
-            umma_tf32(tmem_base, da_s, db, idesc, (it > 0) || (k4 > 0));  // small terms first
-            umma_tf32(tmem_base, da, db_s, idesc, true);
-            umma_tf32(tmem_base, da, db, idesc, true);
-          }
+          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&tfull[buf]);
+        ++lt;
       }
-      umma_commit(tmem_full);
     }
-  } else {
-    const int t = (warp - 2) * 32 + lane;
-    if constexpr (!ASrc::kBulk) {
-      asrc.run(
-          smem, kStageBytes, kStages, m_tile, ks0, n_it, t, batch,
-          [&](int it) { mbar_wait(&empty[it % kStages], ((it / kStages) & 1) ^ 1); },
-          [&](int it) {
-            fence_proxy_async_smem();
-            mbar_arrive(&full[it % kStages]);
-          });
-    }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+  } else if (warp >= kCtrlWarps && warp < kCtrlWarps + kEpiWarps) {
+    // ---------------- epilogue ----------------
     const int quarter = warp & 3;  // TMEM lanes this warp may read
-    EpiCtx ctx;
-    ctx.row = quarter * 32 + lane;
-    ctx.m = m_tile * 128 + ctx.row;
-    ctx.t = t;
-    ctx.m_tile = m_tile;
-    ctx.n_tile = n_tile;
-    ctx.split = split;
-    ctx.batch = batch;
-    ctx.scratch = smem;
-    ctx.scratch_bytes = kStages * kStageBytes;
-    typename Epi::State st;
-    epi.begin(st, ctx);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord c = decode(tile);
+      if (c.n_it <= 0) continue;
+      const uint32_t buf = lt & 1;
+      mbar_wait(&tfull[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      EpiCtx ctx;
+      ctx.row = quarter * 32 + lane;
+      ctx.m = c.m_tile * 128 + ctx.row;
+      ctx.t = (warp - kCtrlWarps) * 32 + lane;
+      ctx.m_tile = c.m_tile;
+      ctx.n_tile = c.n_tile;
+      ctx.split = c.split;
+      ctx.batch = c.batch;
+      ctx.scratch = scratch;
+      ctx.scratch_bytes = kScratch;
+      typename Epi::State st;
+      epi.begin(st, ctx);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
-      epi.chunk(st, ctx, n_tile * BN + c * 32, v);
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + cc * 32, v);
+        epi.chunk(st, ctx, c.n_tile * BN + cc * 32, v);
+      }
+      epi.end(st, ctx);
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+      ++lt;
     }
-    epi.end(st, ctx);
+  } else if (warp >= kCtrlWarps + kEpiWarps) {
+    // ---------------- on-the-fly A producers ----------------
+    if constexpr (!ASrc::kBulk) {
+      uint32_t git = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord c = decode(tile);
+        if (c.n_it <= 0) continue;
+        ProdCtx pc;
+        pc.m_tile = c.m_tile;
+        pc.batch = c.batch;
+        pc.ks0 = c.ks0;
+        pc.n_it = c.n_it;
+        pc.t = (warp - kCtrlWarps - kEpiWarps) * 32 + lane;
+        pc.smem = smem;
+        pc.stage_bytes = kStageBytes;
+        pc.stages = kStages;
+        pc.it0 = git;
+        pc.full = full;
+        pc.empty = empty;
+        asrc.run(pc);
+        git += c.n_it;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+inline int gemm_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
 }
 
 template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
 int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                        int k_steps, int k_splits, const Epi& epi, cudaStream_t stream, const char* what,
                        MnDebug mn = MnDebug(), int batches = 1) {
-  if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0) return 0;
+  if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0 || batches <= 0) return 0;
   if (k_splits < 1) k_splits = 1;
   if (k_splits > k_steps) k_splits = k_steps;
   auto kern = gemm_stream_kernel<BN, kStages, kMn, kKind, ASrc, Epi>;
-  constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, kKind>();
+  constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, kKind, Epi>();
+  static_assert(smem <= 227 * 1024, "stage ring + epilogue scratch exceed the 227 KB of one CTA");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -276,10 +386,11 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
     }
     configured = true;
   }
-  dim3 grid(n_tiles, m_tiles, k_splits * batches);
-  S2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", what);
+  const long long tiles = (long long)m_tiles * n_tiles * batches * k_splits;
+  const int grid = (int)(tiles < gemm_sm_count() ? tiles : gemm_sm_count());
   ProfScope prof(what, stream);
-  kern<<<grid, kGemmThreads, smem, stream>>>(asrc, b_packed, b_row_blocks, k_steps, k_splits, epi, mn);
+  kern<<<grid, gemm_threads<ASrc>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
+                                                     k_splits, epi, mn);
   return check_launch(what);
 }
 
@@ -291,6 +402,7 @@ struct StoreRowMajorEpi {
   int M, N;
   bool atomic;
   const float* bias = nullptr;  // added per column when not atomic
+  static constexpr int kScratchBytes = 0;
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
   __device__ void end(State&, const EpiCtx&) const {}
@@ -331,7 +443,8 @@ struct PackSpec {
 int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream);
 int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream);
 
-// On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage.
+// On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage;
+// two producer threads per row (four 16-byte chunks each).
 struct RowCopyProducerF32 {
   static constexpr bool kBulk = false;
   const float* x;
@@ -339,18 +452,17 @@ struct RowCopyProducerF32 {
   int64_t M;
   int K;
   bool split;  // also write the residual block right after the big block (3xTF32)
-  template <class W, class A>
-  __device__ void run(uint8_t* smem, int stage_bytes, int stages, int m_tile, int ks0, int n_it, int t, int,
-                      W wait_empty, A arrive_full) const {
-    const int64_t m = (int64_t)m_tile * 128 + t;
+  __device__ void run(const ProdCtx& pc) const {
+    const int r = pc.t >> 1, half = pc.t & 1;
+    const int64_t m = (int64_t)pc.m_tile * 128 + r;
     const bool live = m < M;
     const float* row = x + (live ? m * ld : 0);
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    float4 cur[8], nxt[8];
-    auto load = [&](float4 (&dst)[8], int ks) {
+    float4 cur[4], nxt[4];
+    auto load = [&](float4 (&dst)[4], int ks) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int k = ks * 32 + c * 4;
+      for (int c = 0; c < 4; ++c) {
+        const int k = ks * 32 + (half * 4 + c) * 4;
         if (live && vec && k + 4 <= K) {
           dst[c] = __ldg(reinterpret_cast<const float4*>(row + k));
         } else {
@@ -361,27 +473,28 @@ struct RowCopyProducerF32 {
         }
       }
     };
-    load(cur, ks0);
-    for (int it = 0; it < n_it; ++it) {
-      if (it + 1 < n_it) load(nxt, ks0 + it + 1);
-      wait_empty(it);
-      uint8_t* dst = smem + (it % stages) * stage_bytes + t * 128;
+    load(cur, pc.ks0);
+    for (int it = 0; it < pc.n_it; ++it) {
+      if (it + 1 < pc.n_it) load(nxt, pc.ks0 + it + 1);
+      pc.wait_empty(it);
+      uint8_t* dst = pc.stage(it) + r * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const float4 x4 = cur[c];
         float4 v;
         v.x = round_tf32(x4.x); v.y = round_tf32(x4.y); v.z = round_tf32(x4.z); v.w = round_tf32(x4.w);
-        *reinterpret_cast<float4*>(dst + (((c ^ (t & 7)) & 7) << 4)) = v;
+        const int off = (((half * 4 + c) ^ (r & 7)) & 7) << 4;
+        *reinterpret_cast<float4*>(dst + off) = v;
         if (split) {
-          float4 r;
-          r.x = round_tf32(x4.x - v.x); r.y = round_tf32(x4.y - v.y); r.z = round_tf32(x4.z - v.z);
-          r.w = round_tf32(x4.w - v.w);
-          *reinterpret_cast<float4*>(dst + kBlockBytes + (((c ^ (t & 7)) & 7) << 4)) = r;
+          float4 q;
+          q.x = round_tf32(x4.x - v.x); q.y = round_tf32(x4.y - v.y); q.z = round_tf32(x4.z - v.z);
+          q.w = round_tf32(x4.w - v.w);
+          *reinterpret_cast<float4*>(dst + kBlockBytes + off) = q;
         }
       }
-      arrive_full(it);
+      pc.arrive_full(it);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+      for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
     }
   }
 };

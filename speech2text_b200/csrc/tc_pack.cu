@@ -181,7 +181,7 @@ extern "C" int s2t_tc_gemm(const float* A, const float* B, float* C, int M, int 
     return tc::launch_gemm_stream<128, 4, false, 0>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
                                           "tc_gemm_debug_128");
   }
-  return tc::launch_gemm_stream<256, 3, false, 0>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
+  return tc::launch_gemm_stream<256, 4, false, 0>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
                                         "tc_gemm_debug_256");
 }
 
@@ -207,6 +207,6 @@ extern "C" int s2t_tc_gemm_mn(const float* At, const float* Bt, float* C, int M,
   if (lbo) mn.lbo_bytes = lbo;
   if (sbo) mn.sbo_bytes = sbo;
   if (kadv) mn.k_advance_bytes = kadv;
-  return tc::launch_gemm_stream<256, 3, true, 0>(a, pb, rb, (M + 127) / 128, (N + 255) / 256, (K + 63) / 64, k_splits, epi,
+  return tc::launch_gemm_stream<256, 4, true, 0>(a, pb, rb, (M + 127) / 128, (N + 255) / 256, (K + 63) / 64, k_splits, epi,
                                               st, "tc_gemm_mn_debug", mn);
 }
