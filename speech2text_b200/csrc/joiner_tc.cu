@@ -32,6 +32,12 @@ constexpr int kBN = 256;
 constexpr int kNStages = 4;   // 192 KB ring
 constexpr int kNStagesDj = 2; // dJ epilogue keeps 84 KB of reduction scratch next to the ring
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float act_fwd_fast(float x, int act) { return act == kRelu ? fmaxf(x, 0.f) : tanh_fast(x); }
 __device__ __forceinline__ float act_bwd_fast(float x, int act) {
   if (act == kRelu) return x > 0.f ? 1.f : 0.f;
@@ -269,7 +275,7 @@ struct LseEpi {
   }
   __device__ void end(State& st, const EpiCtx& ctx) const {
     if (ctx.m >= M) return;
-    float* p = part + ((int64_t)ctx.m * n_tiles + ctx.n_tile) * 2;
+    float* p = part + ((int64_t)ctx.m * n_tiles + ctx.part) * 2;  // n_tiles counts (n_tile, group) partials
     p[0] = st.mx;
     p[1] = st.sum;
   }
@@ -327,23 +333,42 @@ struct GradEpi {
       st.csym = row_sym[m];
       if (st.ox + st.oy == 0.f || st.cf == 0.f) st.live = false;
     }
+    if (!st.live) {
+      st.ox = 0.f;
+      st.oy = 0.f;
+    }
   }
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     float x[32];
-    const float g = st.ox + st.oy;
+    // softmax term: -cf (occ_px + occ_py) exp(logit - lse); dead rows use -inf so that it is exactly 0
+    const float gneg = st.live ? -(st.ox + st.oy) * st.cf : 0.f;
+    const float nl2 = st.live ? -st.l * kLog2e : kNegInf;
+    const float oxc = st.ox * st.cf, oyc = st.oy * st.cf;
+    if (clamp > 0.f) {
+      // torchaudio's gradient clamp acts on the per-utterance gradient before the upstream scale
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int v = n + j;
-      float val = 0.f;
-      if (st.live && v < V) {
-        val = -g * exp2f((acc[j] + __ldg(b2 + v) - st.l) * kLog2e);
-        if (v == st.csym) val += st.ox;
-        if (v == blank) val += st.oy;
-        if (clamp > 0.f) val = fminf(fmaxf(val, -clamp), clamp);
-        val *= st.cf;
+      for (int j = 0; j < 32; ++j) {
+        const int v = n + j;
+        float val = 0.f;
+        if (st.live && v < V) {
+          val = -(st.ox + st.oy) * exp2f(fmaf(acc[j] + __ldg(b2 + v), kLog2e, nl2));
+          if (v == st.csym) val += st.ox;
+          if (v == blank) val += st.oy;
+          val = fminf(fmaxf(val, -clamp), clamp) * st.cf;
+        }
+        x[j] = val;
       }
-      x[j] = val;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int v = n + j;
+        const float b = (v < V) ? __ldg(b2 + v) : 0.f;
+        float val = gneg * ex2_approx(fmaf(acc[j] + b, kLog2e, nl2));
+        if (v == st.csym) val += oxc;
+        if (v == blank) val += oyc;
+        x[j] = (v < V) ? val : 0.f;
+      }
     }
     store_packed_row32(Gp, g_row_blocks, ctx.m, n, x);
     const float cs = warp_column_sums(x);
@@ -389,7 +414,8 @@ struct DJointEpi {
   int V, act;
   float* d_am;
   float* d_lm;
-  static constexpr int kLdW = kBN + 1;    // staged am / lm rows: the kBN columns of the n-tile, odd stride
+  static constexpr int kColsG = kBN / 2;   // columns drained by one epilogue group (bulk-fed kernel: 2 groups)
+  static constexpr int kLdW = kColsG + 1;  // staged am / lm rows: this group's columns, odd stride
   static constexpr int kMaxStaged = 64;   // (am + lm bucket rows) that fit the operand ring next to dj
   struct Scratch {
     float dj[128 * kLd];
@@ -428,7 +454,7 @@ struct DJointEpi {
     }
     sc.cnt[0][ctx.t] = 0;
     sc.cnt[1][ctx.t] = 0;
-    epi_sync();
+    epi_sync(ctx);
     ra = sc.red[0];
     rl = sc.red[4];
 #pragma unroll
@@ -448,7 +474,7 @@ struct DJointEpi {
       pa = atomicAdd(&sc.cnt[0][(int)sa], 1);
       pl = atomicAdd(&sc.cnt[1][(int)sl], 1);
     }
-    epi_sync();
+    epi_sync(ctx);
     if (ctx.t < 2) {  // exclusive scans (128 entries each, once per tile)
       int run = 0, last = 0;
       for (int i = 0; i < 128; ++i) {
@@ -458,7 +484,7 @@ struct DJointEpi {
       }
       sc.n_slots[ctx.t] = last;
     }
-    epi_sync();
+    epi_sync(ctx);
     if (bucket) {
       sc.order[0][sc.start[0][(int)sa] + pa] = ctx.t;
       sc.order[1][sc.start[1][(int)sl] + pl] = ctx.t;
@@ -468,14 +494,14 @@ struct DJointEpi {
     const int na = sc.n_slots[0], nl = sc.n_slots[1];
     st.staged = (na + nl) <= kMaxStaged;
     if (st.staged) {
-      const int n0 = ctx.n_tile * kBN;
-      const int total = (na + nl) * kBN;
+      const int n0 = ctx.col0;
+      const int total = (na + nl) * kColsG;
       for (int i0 = ctx.t; i0 < total; i0 += 128 * 8) {
         float tmp[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
-          const int row = i / kBN, col = i % kBN;
+          const int row = i / kColsG, col = i % kColsG;
           float x = 0.f;
           if (i < total && n0 + col < V) {
             x = row < na ? __ldg(am + (st.a_row0 + row) * V + n0 + col)
@@ -486,18 +512,18 @@ struct DJointEpi {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
-          if (i < total) sc.rows[(i / kBN) * kLdW + (i % kBN)] = tmp[u];
+          if (i < total) sc.rows[(i / kColsG) * kLdW + (i % kColsG)] = tmp[u];
         }
       }
       st.sl += na;  // lm rows follow the am rows
     }
-    epi_sync();
+    epi_sync(ctx);
   }
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
     float* mine = sc.dj + ctx.t * kLd;
-    const int c0 = n - ctx.n_tile * kBN;  // first column of this chunk inside the staged rows
+    const int c0 = n - ctx.col0;  // first column of this chunk inside the staged rows
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int v = n + j;
@@ -515,7 +541,7 @@ struct DJointEpi {
       }
       mine[j] = dj;
     }
-    epi_sync();
+    epi_sync(ctx);
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const int ns = sc.n_slots[which];
@@ -531,7 +557,7 @@ struct DJointEpi {
         if (sum != 0.f) atomicAdd(dst + (base_row + slot) * V + n + j, sum);
       }
     }
-    epi_sync();
+    epi_sync(ctx);
   }
 };
 
@@ -557,7 +583,8 @@ struct TcDims {
   int Mt;          // row tiles of 128
   int Vp, Ip;      // V, I padded to multiples of 256
   int kbV, kbI;    // K blocks of 64 covering V, Ip
-  int n_tiles_v;   // Vp / 256
+  int n_tiles_v;   // Vp / kBN
+  int n_parts_v;   // LSE partials per row
   int64_t chunk;   // rows per backward chunk (multiple of 128)
 };
 
@@ -570,6 +597,7 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.kbV = (V + 63) / 64;
   d.kbI = d.Ip / 64;
   d.n_tiles_v = d.Vp / kBN;
+  d.n_parts_v = 2 * d.n_tiles_v;  // the logits kernel is bulk-fed: two epilogue groups per tile
   const size_t budget = (size_t)1 << 30;  // bytes of one orientation of the chunk's G
   int64_t rows = (int64_t)(budget / ((size_t)d.Vp * 2));
   rows = (rows / 128) * 128;
@@ -604,7 +632,7 @@ TcWs tc_carve(void* ws, const TcDims& d) {
   w.am_off = (int64_t*)take(d.M * sizeof(int64_t));
   w.lm_off = (int64_t*)take(d.M * sizeof(int64_t));
   w.row_sym = (int*)take(d.M * sizeof(int));
-  w.part = (float*)take((size_t)d.M * d.n_tiles_v * 2 * sizeof(float));
+  w.part = (float*)take((size_t)d.M * d.n_parts_v * 2 * sizeof(float));
   w.sym_logit = (float*)take(d.M * sizeof(float));
   w.blank_logit = (float*)take(d.M * sizeof(float));
   w.W1p = (uint8_t*)take((size_t)(d.Ip / 128) * d.kbV * kBlockBytes);
@@ -664,7 +692,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   // logits -> lse partials: M x Vp, K = Ip
   {
     BulkA a{w.Hp, d.Mt};
-    LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_tiles_v, M, w.part, w.sym_logit, w.blank_logit};
+    LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_parts_v, M, w.part, w.sym_logit, w.blank_logit};
     if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                    "tc_joiner_logits_lse_gemm"))
       return rc;
@@ -672,7 +700,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     ProfScope prof("lse_combine_kernel", stream);
     lse_combine_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(w.part, w.sym_logit, w.blank_logit, p.boundary,
-                                                                       M, d.n_tiles_v, p.T, p.R, p.delay_penalty, lse,
+                                                                       M, d.n_parts_v, p.T, p.R, p.delay_penalty, lse,
                                                                        px, py);
   }
   return check_launch("lse_combine_kernel");

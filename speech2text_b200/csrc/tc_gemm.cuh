@@ -9,10 +9,11 @@
 // across tile boundaries.  Warp roles:
 //   warp 0       bulk-copy issuer (cp.async.bulk, TMA engine) for the packed operands
 //   warp 1       TMEM allocation + MMA issue + commits
-//   warps 4..7   epilogue: tcgen05.ld the finished accumulator (one TMEM lane = one output row per
-//                thread) and hand 32-column chunks to the epilogue functor, while the MMA warp is
-//                already filling the other TMEM buffer with the next tile
-//   warps 8..15  (only with an on-the-fly A source) producers: build the A stage, e.g.
+//   warps 4..    epilogue groups of 4 warps: tcgen05.ld the finished accumulator (one TMEM lane = one
+//                output row per thread) and hand 32-column chunks to the epilogue functor, while the
+//                MMA warp is already filling the other TMEM buffer with the next tile; bulk-fed
+//                kernels run two groups (half of the columns each), producer-fed kernels one
+//   last 8 warps (only with an on-the-fly A source) producers: build the A stage, e.g.
 //                act(am + lm[ranges]) -> bf16, directly in the swizzled smem image, so the operand
 //                never exists in HBM
 //
@@ -40,7 +41,7 @@
 //     __device__ void end(State&, const EpiCtx&) const;
 //   };
 // Epi::kScratchBytes of shared memory are reserved for CTA-level reductions of the epilogue
-// (EpiCtx::scratch); epi_sync() is a barrier over the 128 epilogue threads.
+// per epilogue group (EpiCtx::scratch); epi_sync(ctx) is a barrier over the 128 threads of a group.
 #pragma once
 #include "common.cuh"
 #include "tc_prims.cuh"
@@ -53,11 +54,18 @@ struct EpiCtx {
   int t;        // epilogue thread index, 0..127
   int row;      // row inside the 128-row tile
   int m_tile, n_tile, split, batch;
-  uint8_t* scratch;
+  int group;   // epilogue group: each group of 128 threads drains its own range of accumulator columns
+  int col0;    // first output column of this group's range
+  int ncols;   // columns in the range (BN / groups)
+  int part;    // n_tile * groups + group: index of the (row, column-range) partial
+  uint8_t* scratch;  // this group's Epi::kScratchBytes
   int scratch_bytes;
 };
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// barrier over the 128 threads of one epilogue group
+__device__ __forceinline__ void epi_sync(const EpiCtx& ctx) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + ctx.group) : "memory");
+}
 
 struct BulkA {
   static constexpr bool kBulk = true;
@@ -73,9 +81,15 @@ constexpr int kProdWarps = 8;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kGroupBytes = 64 * 128;  // one MN-major group: 64 k-rows x 64 elements
 
+// Epilogue groups: kernels fed purely by bulk copies have no producer warps and spend the thread
+// budget on a second epilogue group (each group drains half of the accumulator columns).
+template <class ASrc>
+constexpr int gemm_epi_groups() {
+  return ASrc::kBulk ? 2 : 1;
+}
 template <class ASrc>
 constexpr int gemm_threads() {
-  return 32 * (kCtrlWarps + kEpiWarps + (ASrc::kBulk ? 0 : kProdWarps));
+  return 32 * (kCtrlWarps + kEpiWarps * gemm_epi_groups<ASrc>() + (ASrc::kBulk ? 0 : kProdWarps));
 }
 
 // kKind: 0 = bf16 operands; 1 = tf32 (fp32 in smem, single pass); 2 = 3xTF32: every fp32 operand is held
@@ -85,10 +99,10 @@ template <int BN, int kKind>
 constexpr int gemm_stage_bytes() {
   return (kKind == 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
 }
-template <int BN, int kStages, int kKind, class Epi>
+template <int BN, int kStages, int kKind, class ASrc, class Epi>
 constexpr size_t gemm_stream_smem_bytes() {
-  return (size_t)kStages * gemm_stage_bytes<BN, kKind>() + ((Epi::kScratchBytes + 127) / 128) * 128 + 1024 /*align*/ +
-         256 /*barriers*/;
+  return (size_t)kStages * gemm_stage_bytes<BN, kKind>() +
+         (size_t)gemm_epi_groups<ASrc>() * (((Epi::kScratchBytes + 127) / 128) * 128) + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 // MN-major smem descriptor: 8-row (K) groups 1024 B apart, 64-element (MN) groups lbo_bytes apart
@@ -152,7 +166,8 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   constexpr int kBPart = (BN / 128) * kBlockBytes;
   constexpr int kBBytes = kParts * kBPart;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kScratch = ((Epi::kScratchBytes + 127) / 128) * 128;
+  constexpr int kGroups = gemm_epi_groups<ASrc>();
+  constexpr int kScratch = ((Epi::kScratchBytes + 127) / 128) * 128;  // per epilogue group
   constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
   static_assert(kKind != 2 || !ASrc::kBulk, "3xTF32 expects an on-the-fly A producer that writes big|small");
   static_assert(kKind == 0 || !kMn, "tf32 operands are K-major only");
@@ -160,7 +175,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   uint8_t* scratch = smem + kStages * kStageBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(scratch + kScratch);
+  uint64_t* full = reinterpret_cast<uint64_t*>(scratch + kGroups * kScratch);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
@@ -189,7 +204,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 32 * kEpiWarps);
+      mbar_init(&tempty[i], 32 * kEpiWarps * kGroups);
     }
     fence_mbar_init();
   }
@@ -294,9 +309,11 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         ++lt;
       }
     }
-  } else if (warp >= kCtrlWarps && warp < kCtrlWarps + kEpiWarps) {
+  } else if (warp >= kCtrlWarps && warp < kCtrlWarps + kEpiWarps * kGroups) {
     // ---------------- epilogue ----------------
     const int quarter = warp & 3;  // TMEM lanes this warp may read
+    const int group = (warp - kCtrlWarps) / kEpiWarps;
+    constexpr int kCols = BN / kGroups;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord c = decode(tile);
@@ -307,27 +324,31 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       EpiCtx ctx;
       ctx.row = quarter * 32 + lane;
       ctx.m = c.m_tile * 128 + ctx.row;
-      ctx.t = (warp - kCtrlWarps) * 32 + lane;
+      ctx.t = ((warp - kCtrlWarps) % kEpiWarps) * 32 + lane;
       ctx.m_tile = c.m_tile;
       ctx.n_tile = c.n_tile;
       ctx.split = c.split;
       ctx.batch = c.batch;
-      ctx.scratch = scratch;
+      ctx.group = group;
+      ctx.col0 = c.n_tile * BN + group * kCols;
+      ctx.ncols = kCols;
+      ctx.part = c.n_tile * kGroups + group;
+      ctx.scratch = scratch + group * kScratch;
       ctx.scratch_bytes = kScratch;
       typename Epi::State st;
       epi.begin(st, ctx);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
+      for (int cc = 0; cc < kCols / 32; ++cc) {
         float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + cc * 32, v);
-        epi.chunk(st, ctx, c.n_tile * BN + cc * 32, v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + group * kCols + cc * 32, v);
+        epi.chunk(st, ctx, ctx.col0 + cc * 32, v);
       }
       epi.end(st, ctx);
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
       ++lt;
     }
-  } else if (warp >= kCtrlWarps + kEpiWarps) {
+  } else if (warp >= kCtrlWarps + kEpiWarps * kGroups) {
     // ---------------- on-the-fly A producers ----------------
     if constexpr (!ASrc::kBulk) {
       uint32_t git = 0;
@@ -339,7 +360,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         pc.batch = c.batch;
         pc.ks0 = c.ks0;
         pc.n_it = c.n_it;
-        pc.t = (warp - kCtrlWarps - kEpiWarps) * 32 + lane;
+        pc.t = (warp - kCtrlWarps - kEpiWarps * kGroups) * 32 + lane;
         pc.smem = smem;
         pc.stage_bytes = kStageBytes;
         pc.stages = kStages;
@@ -375,7 +396,7 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
   if (k_splits < 1) k_splits = 1;
   if (k_splits > k_steps) k_splits = k_steps;
   auto kern = gemm_stream_kernel<BN, kStages, kMn, kKind, ASrc, Epi>;
-  constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, kKind, Epi>();
+  constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, kKind, ASrc, Epi>();
   static_assert(smem <= 227 * 1024, "stage ring + epilogue scratch exceed the 227 KB of one CTA");
   static bool configured = false;
   if (!configured) {
