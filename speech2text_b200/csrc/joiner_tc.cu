@@ -14,6 +14,8 @@
 // Row-chunking bounds the only (B,T,R,V)-sized scratch (the bf16 G of one chunk, kept in both
 // orientations for the two contractions that consume it).
 // TODO(perf): chain logits -> G -> dhidden inside one kernel so G stays in smem.
+#include <stdlib.h>
+#include <limits.h>
 #include "joiner.cuh"
 #include "tc_gemm.cuh"
 
@@ -30,7 +32,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 // instead of once per 256 output columns.)
 constexpr int kBN = 256;
 constexpr int kNStages = 4;   // 192 KB ring
-constexpr int kNStagesDj = 2; // dJ epilogue keeps 84 KB of reduction scratch next to the ring
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -398,168 +399,158 @@ struct DHiddenEpi {
   }
 };
 
-// dJ = (dhidden W1)[m, v] * act'(am + lm) reduced into d_am / d_lm.
-// The 128 rows of a tile touch few distinct am rows (128/R frames) and lm rows (the band moves
-// slowly).  Once per tile the rows are bucketed by am-row and by lm-row (counting sort in the idle
-// operand ring); every 32-column chunk is then staged in shared memory, summed per bucket without
-// atomics, and only the per-bucket sums go to global memory: ~(128/R + band rows) * 32 atomics
-// per chunk instead of 2 * 128 * 32.
-struct DJointEpi {
-  static constexpr int kSlotsA = 128, kSlotsL = 128, kLd = 33;
-  const float* am;
-  const float* lm;
-  const int64_t* am_off;
-  const int64_t* lm_off;
-  int64_t row0, M;
-  int V, act;
-  float* d_am;
-  float* d_lm;
-  static constexpr int kColsG = kBN / 2;   // columns drained by one epilogue group (bulk-fed kernel: 2 groups)
-  static constexpr int kLdW = kColsG + 1;  // staged am / lm rows: this group's columns, odd stride
-  static constexpr int kMaxStaged = 64;   // (am + lm bucket rows) that fit the operand ring next to dj
-  struct Scratch {
-    float dj[128 * kLd];
-    float rows[kMaxStaged * kLdW];  // am rows of the buckets, then lm rows, this tile's 256 columns
-    int64_t red[8];
-    int cnt[2][128], start[2][128];
-    int order[2][128];
-    int n_slots[2];
-  };
-  static constexpr int kScratchBytes = sizeof(Scratch);
-  struct State {
-    int64_t ao, lo;
-    int64_t a_row0, l_row0;
-    int sa, sl;
-    bool live, direct, staged;
-  };
-  __device__ void begin(State& st, const EpiCtx& ctx) const {
-    Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
-    const int64_t m = row0 + ctx.m;
-    const int lane = ctx.t & 31, w = ctx.t >> 5;
-    st.live = m < M;
-    st.ao = st.live ? am_off[m] : 0;
-    st.lo = st.live ? lm_off[m] : 0;
-    // tile-wide minimum am / lm row ids
-    int64_t ka = st.live ? st.ao / V : INT64_MAX, kl = st.live ? st.lo / V : INT64_MAX;
-    int64_t ra = ka, rl = kl;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      int64_t oa = __shfl_xor_sync(0xffffffffu, ra, o), ol = __shfl_xor_sync(0xffffffffu, rl, o);
-      ra = oa < ra ? oa : ra;
-      rl = ol < rl ? ol : rl;
-    }
-    if (lane == 0) {
-      sc.red[w] = ra;
-      sc.red[4 + w] = rl;
-    }
-    sc.cnt[0][ctx.t] = 0;
-    sc.cnt[1][ctx.t] = 0;
-    epi_sync(ctx);
-    ra = sc.red[0];
-    rl = sc.red[4];
-#pragma unroll
-    for (int i = 1; i < 4; ++i) {
-      ra = sc.red[i] < ra ? sc.red[i] : ra;
-      rl = sc.red[4 + i] < rl ? sc.red[4 + i] : rl;
-    }
-    st.a_row0 = ra;
-    st.l_row0 = rl;
-    const int64_t sa = st.live ? ka - ra : 0, sl = st.live ? kl - rl : 0;
-    st.direct = st.live && (sa >= kSlotsA || sl >= kSlotsL);  // far-apart rows: straight to global
-    st.sa = (int)(sa < kSlotsA ? sa : 0);
-    st.sl = (int)(sl < kSlotsL ? sl : 0);
-    int pa = 0, pl = 0;
-    const bool bucket = st.live && !st.direct;
-    if (bucket) {
-      pa = atomicAdd(&sc.cnt[0][(int)sa], 1);
-      pl = atomicAdd(&sc.cnt[1][(int)sl], 1);
-    }
-    epi_sync(ctx);
-    if (ctx.t < 2) {  // exclusive scans (128 entries each, once per tile)
-      int run = 0, last = 0;
-      for (int i = 0; i < 128; ++i) {
-        sc.start[ctx.t][i] = run;
-        run += sc.cnt[ctx.t][i];
-        if (sc.cnt[ctx.t][i]) last = i + 1;
-      }
-      sc.n_slots[ctx.t] = last;
-    }
-    epi_sync(ctx);
-    if (bucket) {
-      sc.order[0][sc.start[0][(int)sa] + pa] = ctx.t;
-      sc.order[1][sc.start[1][(int)sl] + pl] = ctx.t;
-    }
-    // stage the bucket rows of am and lm for the 256 columns of this n-tile: one burst of coalesced
-    // loads per tile (all in flight together) instead of a dependent L2 round trip per row and chunk
-    const int na = sc.n_slots[0], nl = sc.n_slots[1];
-    st.staged = (na + nl) <= kMaxStaged;
-    if (st.staged) {
-      const int n0 = ctx.col0;
-      const int total = (na + nl) * kColsG;
-      for (int i0 = ctx.t; i0 < total; i0 += 128 * 8) {
-        float tmp[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * 128;
-          const int row = i / kColsG, col = i % kColsG;
-          float x = 0.f;
-          if (i < total && n0 + col < V) {
-            x = row < na ? __ldg(am + (st.a_row0 + row) * V + n0 + col)
-                         : __ldg(lm + (st.l_row0 + row - na) * V + n0 + col);
-          }
-          tmp[u] = x;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * 128;
-          if (i < total) sc.rows[(i / kColsG) * kLdW + (i % kColsG)] = tmp[u];
-        }
-      }
-      st.sl += na;  // lm rows follow the am rows
-    }
-    epi_sync(ctx);
-  }
+// dh = dhidden W1 (before the activation derivative), bf16 row-major (chunk rows, Vp): the GEMM epilogue
+// is a plain store; the segmented reductions into d_am / d_lm run as two fully parallel kernels below.
+struct StoreRowsBf16Epi {
+  static constexpr int kScratchBytes = 0;
+  __nv_bfloat16* out;
+  int ld;
+  struct State {};
+  __device__ void begin(State&, const EpiCtx&) const {}
   __device__ void end(State&, const EpiCtx&) const {}
-  __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
-    Scratch& sc = *reinterpret_cast<Scratch*>(ctx.scratch);
-    float* mine = sc.dj + ctx.t * kLd;
-    const int c0 = n - ctx.col0;  // first column of this chunk inside the staged rows
+  __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)ctx.m * ld + n);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int v = n + j;
-      float dj = 0.f;
-      if (st.live && v < V && acc[j] != 0.f) {
-        const float x = (st.direct || !st.staged)
-                            ? __ldg(am + st.ao + v) + __ldg(lm + st.lo + v)
-                            : sc.rows[st.sa * kLdW + c0 + j] + sc.rows[st.sl * kLdW + c0 + j];
-        dj = acc[j] * act_bwd_fast(x, act);
-        if (st.direct && dj != 0.f) {
-          atomicAdd(d_am + st.ao + v, dj);
-          atomicAdd(d_lm + st.lo + v, dj);
-          dj = 0.f;
-        }
-      }
-      mine[j] = dj;
+    for (int c = 0; c < 4; ++c) {
+      dst[c] = make_uint4(pack_bf16x2(acc[c * 8 + 0], acc[c * 8 + 1]), pack_bf16x2(acc[c * 8 + 2], acc[c * 8 + 3]),
+                          pack_bf16x2(acc[c * 8 + 4], acc[c * 8 + 5]), pack_bf16x2(acc[c * 8 + 6], acc[c * 8 + 7]));
     }
-    epi_sync(ctx);
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const int ns = sc.n_slots[which];
-      float* dst = which == 0 ? d_am : d_lm;
-      const int64_t base_row = which == 0 ? st.a_row0 : st.l_row0;
-      for (int i = ctx.t; i < ns * 32; i += 128) {
-        const int slot = i >> 5, j = i & 31;
-        const int c = sc.cnt[which][slot];
-        if (c == 0 || n + j >= V) continue;
-        const int s0 = sc.start[which][slot];
-        float sum = 0.f;
-        for (int k = 0; k < c; ++k) sum += sc.dj[sc.order[which][s0 + k] * kLd + j];
-        if (sum != 0.f) atomicAdd(dst + (base_row + slot) * V + n + j, sum);
-      }
-    }
-    epi_sync(ctx);
   }
 };
+
+// d_am[b,t,v] += sum_r dh[(b,t,r), v] * act'(am[b,t,v] + lm[b, s(t,r), v])      (A.5: sum over the band slots)
+// one thread per (frame, 4 consecutive v): every read and the write are coalesced 8/16-byte accesses, no atomics.
+__global__ void djoint_am_kernel(const __nv_bfloat16* __restrict__ dh, int ld, const float* __restrict__ am,
+                                 const float* __restrict__ lm, const int64_t* __restrict__ lm_off, int64_t row0,
+                                 int64_t rows, int64_t M, int R, int V, int act, float* __restrict__ d_am) {
+  const int64_t f0 = row0 / R, f1 = (min(row0 + rows, M) + R - 1) / R;  // frames touched by this chunk
+  const int vq = (V + 3) / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (f1 - f0) * vq) return;
+  const int v = (int)(i % vq) * 4;
+  const int64_t bt = f0 + i / vq;
+  const bool vec = ((V & 3) == 0);
+  float a[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (vec) {
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(am + bt * V + v));
+    a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(am + bt * V + v + j) : 0.f;
+  }
+#pragma unroll 4
+  for (int r = 0; r < R; ++r) {
+    const int64_t m = bt * R + r;
+    if (m < row0 || m >= row0 + rows || m >= M) continue;
+    const uint2 raw = *reinterpret_cast<const uint2*>(dh + (m - row0) * ld + v);  // ld and v are multiples of 4
+    const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&raw);
+    const float* lrow = lm + lm_off[m] + v;
+    float l[4];
+    if (vec) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
+      l[0] = t4.x; l[1] = t4.y; l[2] = t4.z; l[3] = t4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) l[j] = (v + j < V) ? __ldg(lrow + j) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[j], act);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (v + j < V) d_am[bt * V + v + j] += acc[j];
+}
+
+// d_lm[b,s,v] += sum over the frames t whose band holds s of dh[(b,t,s-sb[t]), v] * act'(am[b,t,v] + lm[b,s,v]).
+// sb[] is non-decreasing, so those frames are one interval; the block finds its two ends with one parallel
+// sweep over sb[], stages the dh row of every frame of the interval in shared memory, and then two half-blocks
+// take alternate frames, four columns per thread, with independent coalesced 8/16-byte loads only.
+template <bool kVec>
+__global__ void __launch_bounds__(256) djoint_lm_kernel(const __nv_bfloat16* __restrict__ dh, int ld,
+                                                        const float* __restrict__ am, const float* __restrict__ lm,
+                                                        const int64_t* __restrict__ ranges,
+                                                        const int64_t* __restrict__ boundary, int64_t row0,
+                                                        int64_t rows, int64_t M, int T, int S, int R, int V, int act,
+                                                        float* __restrict__ d_lm) {
+  __shared__ int t_range[2];
+  __shared__ int dh_row[64];
+  __shared__ float red[128][4];
+  const int64_t bs = blockIdx.x;  // (b, s)
+  const int b = (int)(bs / (S + 1)), s = (int)(bs % (S + 1));
+  const int Tb = boundary ? min((int)boundary[4 * b + 3], T) : T;  // padding frames carry no gradient
+  if (threadIdx.x == 0) {
+    t_range[0] = (ranges || s >= R) ? Tb : 0;  // unpruned: slot r is symbol position r in every frame
+    t_range[1] = Tb;
+  }
+  __syncthreads();
+  if (ranges) {
+    const int64_t* rg = ranges + (int64_t)b * T * R;  // sb[t] = rg[t * R]
+    for (int t = threadIdx.x; t < Tb; t += 256) {
+      const int sb = (int)rg[(int64_t)t * R];
+      const int prev = t ? (int)rg[(int64_t)(t - 1) * R] : INT_MIN / 2;
+      if (sb + R - 1 >= s && prev + R - 1 < s) t_range[0] = t;  // first frame whose band reaches s
+      if (sb > s && prev <= s) t_range[1] = t;                  // first frame whose band has left s
+    }
+    __syncthreads();
+  }
+  const int t_lo = t_range[0], t_hi = t_range[1];
+  const int half = threadIdx.x >> 7, q = threadIdx.x & 127;
+  for (int vb = 0; vb < V; vb += 512) {
+    const int v = vb + q * 4;
+    float l[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kVec) {
+      const float4 t4 = (v < V) ? __ldg(reinterpret_cast<const float4*>(lm + bs * V + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      l[0] = t4.x; l[1] = t4.y; l[2] = t4.z; l[3] = t4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) l[j] = (v + j < V) ? __ldg(lm + bs * V + v + j) : 0.f;
+    }
+    for (int tb = t_lo; tb < t_hi; tb += 64) {
+      const int nt = min(64, t_hi - tb);
+      __syncthreads();
+      if (threadIdx.x < nt) {
+        const int t = tb + threadIdx.x;
+        const int r = ranges ? s - (int)ranges[((int64_t)b * T + t) * R] : s;
+        const int64_t m = ((int64_t)b * T + t) * R + r;
+        dh_row[threadIdx.x] = (r >= 0 && r < R && m >= row0 && m < row0 + rows && m < M) ? (int)(m - row0) : -1;
+      }
+      __syncthreads();
+      if (v < V) {
+#pragma unroll 4
+        for (int k = half; k < nt; k += 2) {
+          const int row = dh_row[k];
+          const float wgt = row >= 0 ? 1.f : 0.f;
+          const uint2 raw = *reinterpret_cast<const uint2*>(dh + (int64_t)max(row, 0) * ld + v);  // ld, v multiples of 4
+          const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&raw);
+          const float* arow = am + ((int64_t)b * T + tb + k) * V + v;
+          float a[4];
+          if (kVec) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow));
+            a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(arow + j) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] += wgt * __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[j], act);
+        }
+      }
+    }
+    __syncthreads();
+    if (half) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[q][j] = acc[j];
+    }
+    __syncthreads();
+    if (!half && v < V) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = acc[j] + red[q][j];
+        if (v + j < V && x != 0.f) d_lm[bs * V + v + j] += x;
+      }
+    }
+  }
+}
 
 // C^T accumulate: out[(n + j) * ld + m] += acc[j]     (dW1[i, v] from the (v, i) accumulator)
 struct StoreTransposedAtomicEpi {
@@ -617,6 +608,7 @@ struct TcWs {
   uint8_t *W1p, *W2p, *W2Tp, *W1Tp;
   uint8_t* Hp;
   uint8_t *Gp, *DHp;
+  __nv_bfloat16* dh;  // (chunk rows, Vp) d loss / d (joint pre-activation) before act'
   size_t bytes;
 };
 
@@ -642,6 +634,7 @@ TcWs tc_carve(void* ws, const TcDims& d) {
   w.Hp = (uint8_t*)take((size_t)d.Mt * d.kbI * kBlockBytes);
   w.Gp = (uint8_t*)take((size_t)ct * (d.Vp / 64) * kBlockBytes);
   w.DHp = (uint8_t*)take((size_t)ct * d.kbI * kBlockBytes);
+  w.dh = (__nv_bfloat16*)take((size_t)d.chunk * d.Vp * sizeof(__nv_bfloat16));
   w.bytes = (size_t)(p - (char*)ws);
   return w;
 }
@@ -754,13 +747,32 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
                                                     "tc_joiner_dW1_gemm"))
         return rc;
     }
-    // dJ = (dhidden W1) * act' -> d_am, d_lm: rows m, N = Vp, K = Ip
+    // dh = dhidden W1: rows m, N = Vp, K = Ip  ->  bf16 rows; then the two segmented reductions
     {
       BulkA a{w.DHp, ct};
-      DJointEpi ep{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act, d_am, d_lm};
-      if (int rc = launch_gemm_stream<kBN, kNStagesDj, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep,
-                                                                 stream, "tc_joiner_djoint_gemm"))
+      StoreRowsBf16Epi ep{w.dh, d.Vp};
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+                                                               "tc_joiner_dh_gemm"))
         return rc;
+      const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;
+      {
+        const int64_t f0 = row0 / p.R, f1 = (row0 + rows_live + p.R - 1) / p.R;
+        const int64_t n = (f1 - f0) * ((p.V + 3) / 4);
+        ProfScope prof("djoint_am_kernel", stream);
+        djoint_am_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, w.lm_off, row0, rows_live,
+                                                                         M, p.R, p.V, p.act, d_am);
+      }
+      {
+        ProfScope prof("djoint_lm_kernel", stream);
+        const unsigned nbs = (unsigned)((int64_t)p.B * (p.S + 1));
+        if (p.V % 4 == 0)
+          djoint_lm_kernel<true><<<nbs, 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0, rows_live, M,
+                                                          p.T, p.S, p.R, p.V, p.act, d_lm);
+        else
+          djoint_lm_kernel<false><<<nbs, 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0, rows_live,
+                                                           M, p.T, p.S, p.R, p.V, p.act, d_lm);
+      }
+      if (int rc = check_launch("djoint reduce kernels")) return rc;
     }
   }
   return 0;
