@@ -121,7 +121,15 @@ def kernel_work(cfg):
         "tc_joiner_hidden_gemm": ("tensor", gemm), "tc_joiner_logits_lse_gemm": ("tensor", gemm),
         "tc_joiner_grad_logits_gemm": ("tensor", gemm), "tc_joiner_dhidden_gemm": ("tensor", gemm),
         "tc_joiner_dW2_gemm": ("tensor", gemm), "tc_joiner_dW1_gemm": ("tensor", gemm),
-        "tc_joiner_djoint_gemm": ("tensor", gemm),
+        "tc_joiner_djoint_gemm": ("tensor", gemm), "tc_joiner_dh_gemm": ("tensor", gemm),
+        # segmented reductions of dh (bf16 rows) into d_am / d_lm: dh once, am once, lm once, grads read+write
+        "djoint_am_kernel": ("hbm", M * V * 2.0 + 3 * B * T * V * 4.0 + B * S1 * V * 4.0),
+        "djoint_lm_kernel": ("hbm", M * V * 2.0 + B * T * V * 4.0 + 3 * B * S1 * V * 4.0),
+        # simple (smoothed) loss on tensor cores: exp(am - max) built on the fly, 3xTF32 contraction with exp(lm - max)
+        # over V, px/py emitted from the epilogue: am and lm read once, px/py written once
+        "tc_simple_normaliser_gemm_3xtf32": ("hbm", 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
+        "tc_simple_d_am_gemm": ("tensor", simple), "tc_simple_d_lm_gemm": ("tensor", simple),
+        "simple_w_kernel": ("hbm", 12.0 * B * S1 * T), "row_max_kernel": ("hbm", 4.0 * (B * T * V + B * S1 * V)),
         # projections: two launches per step (encoder and predictor side); average of the two
         "tc_linear_fwd_gemm_3xtf32": ("tensor", (proj_enc + proj_pred) / 2),
         "tc_linear_dx_gemm": ("tensor", (proj_enc + proj_pred) / 2),

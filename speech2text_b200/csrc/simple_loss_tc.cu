@@ -33,59 +33,68 @@ __global__ void tc_row_max_kernel(const float* __restrict__ x, int64_t rows, int
   if (lane == 0) out[row] = m;
 }
 
-// K-major 3xTF32 A: rows = frames t of batch b, 32 vocabulary entries per k-step, value exp(am - am_max)
+// K-major 3xTF32 A: rows = frames t of batch b, 32 vocabulary entries per k-step, value exp(am - am_max).
+// Same thread mapping as RowCopyProducerF32: eight lanes read the 128 contiguous bytes of one row.
 struct ExpRowProducerF32 {
   static constexpr bool kBulk = false;
   const float* x;   // (B, rows, V)
   const float* mx;  // (B, rows)
   int rows, V;
   __device__ void run(const ProdCtx& pc) const {
-    const int rr = pc.t >> 1, half = pc.t & 1;  // two producer threads per row, four chunks each
-    const int r = pc.m_tile * 128 + rr;
-    const bool live = r < rows;
-    const float* row = x + ((int64_t)pc.batch * rows + (live ? r : 0)) * V;
-    const float sub = live ? __ldg(mx + (int64_t)pc.batch * rows + r) : 0.f;
+    const int warp = pc.t >> 5, lane = pc.t & 31;
+    const int c = lane & 7, rbase = warp * 4 + (lane >> 3);
     const bool vec = ((V & 3) == 0);
+    const float* rowp[4];
+    float sub[4];
+    bool live[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = pc.m_tile * 128 + rbase + 32 * i;
+      live[i] = r < rows;
+      const int64_t g = (int64_t)pc.batch * rows + (live[i] ? r : 0);
+      rowp[i] = x + g * V;
+      sub[i] = live[i] ? __ldg(mx + g) : 0.f;
+    }
     float4 cur[4], nxt[4];
     auto load = [&](float4 (&dst)[4], int ks) {
+      const int k = ks * 32 + c * 4;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int k = ks * 32 + (half * 4 + c) * 4;
-        if (live && vec && k + 4 <= V) {
-          dst[c] = __ldg(reinterpret_cast<const float4*>(row + k));
+      for (int i = 0; i < 4; ++i) {
+        if (live[i] && vec && k + 4 <= V) {
+          dst[i] = __ldg(reinterpret_cast<const float4*>(rowp[i] + k));
         } else {
           float v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = (live && k + j < V) ? __ldg(row + k + j) : kNegInf;
-          dst[c] = make_float4(v[0], v[1], v[2], v[3]);
+          for (int j = 0; j < 4; ++j) v[j] = (live[i] && k + j < V) ? __ldg(rowp[i] + k + j) : kNegInf;
+          dst[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
     };
+    const int off = ((c ^ (rbase & 7)) & 7) << 4;
     load(cur, pc.ks0);
     for (int it = 0; it < pc.n_it; ++it) {
       if (it + 1 < pc.n_it) load(nxt, pc.ks0 + it + 1);
       pc.wait_empty(it);
-      uint8_t* dst = pc.stage(it) + rr * 128;
+      uint8_t* dst = pc.stage(it) + rbase * 128 + off;
+      const int k = (pc.ks0 + it) * 32 + c * 4;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int k = (pc.ks0 + it) * 32 + (half * 4 + c) * 4;
-        float e[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
+      for (int i = 0; i < 4; ++i) {
+        const float e[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
         float4 big, small;
         float* pb = &big.x;
         float* ps = &small.x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float p = (live && k + j < V) ? __expf(e[j] - sub) : 0.f;
+          const float p = (live[i] && k + j < V) ? __expf(e[j] - sub[i]) : 0.f;
           pb[j] = round_tf32(p);
           ps[j] = round_tf32(p - pb[j]);
         }
-        const int off = (((half * 4 + c) ^ (rr & 7)) & 7) << 4;
-        *reinterpret_cast<float4*>(dst + off) = big;
-        *reinterpret_cast<float4*>(dst + kBlockBytes + off) = small;
+        *reinterpret_cast<float4*>(dst + i * 32 * 128) = big;
+        *reinterpret_cast<float4*>(dst + kBlockBytes + i * 32 * 128) = small;
       }
       pc.arrive_full(it);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
     }
   }
 };

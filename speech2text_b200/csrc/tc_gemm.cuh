@@ -416,27 +416,63 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
 }
 
 // ---- epilogues --------------------------------------------------------------------------------
-// C[m * ldc + n] = acc (or += with atomics when partial sums from several splits / CTAs meet)
+// C[m * ldc + n] = acc (or += with atomics when partial sums from several splits / CTAs meet).
+// An epilogue thread owns one output ROW (one TMEM lane), so storing its 32 columns directly would make
+// every store instruction of the warp touch 32 different lines.  Each warp instead transposes 32 x 16
+// sub-tiles through a padded shared-memory tile (row stride 20 words: conflict-free for the 16-byte
+// writes by row and the 16-byte reads by 8 rows x 4 column groups) and writes 64 contiguous bytes per row.
 struct StoreRowMajorEpi {
   float* C;
   int64_t ldc;
   int M, N;
   bool atomic;
   const float* bias = nullptr;  // added per column when not atomic
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kRowWords = 20;
+  static constexpr int kScratchBytes = 4 * 32 * kRowWords * 4;
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
-    const int m = ctx.m;
-    if (m >= M) return;
-    float* row = C + (int64_t)m * ldc;
+    float* tile = reinterpret_cast<float*>(ctx.scratch) + (ctx.t >> 5) * (32 * kRowWords);
+    const int lane = ctx.t & 31;
+    const int m0 = ctx.m - lane;  // first row of this warp
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (n + j < N) {
-        if (atomic) atomicAdd(row + n + j, acc[j]);
-        else row[n + j] = acc[j] + (bias ? __ldg(bias + n + j) : 0.f);
+    for (int h = 0; h < 2; ++h) {
+      if (n + h * 16 >= N) break;  // uniform over the warp
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(tile + lane * kRowWords + q * 4) =
+            make_float4(acc[h * 16 + q * 4 + 0], acc[h * 16 + q * 4 + 1], acc[h * 16 + q * 4 + 2], acc[h * 16 + q * 4 + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int r = pass * 8 + (lane & 7), cg = lane >> 3;
+        float4 v = *reinterpret_cast<const float4*>(tile + r * kRowWords + cg * 4);
+        const int m = m0 + r, col = n + h * 16 + cg * 4;
+        if (m >= M || col >= N) continue;
+        float* dst = C + (int64_t)m * ldc + col;
+        if (vec_ok && col + 4 <= N) {
+          if (atomic) {
+            atomicAdd(reinterpret_cast<float4*>(dst), v);
+          } else {
+            if (bias) {
+              v.x += __ldg(bias + col); v.y += __ldg(bias + col + 1); v.z += __ldg(bias + col + 2); v.w += __ldg(bias + col + 3);
+            }
+            *reinterpret_cast<float4*>(dst) = v;
+          }
+        } else {
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (col + j < N) {
+              if (atomic) atomicAdd(dst + j, e[j]);
+              else dst[j] = e[j] + (bias ? __ldg(bias + col + j) : 0.f);
+            }
+          }
+        }
       }
+      __syncwarp();
     }
   }
 };
@@ -464,8 +500,9 @@ struct PackSpec {
 int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream);
 int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream);
 
-// On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage;
-// two producer threads per row (four 16-byte chunks each).
+// On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage.
+// Eight lanes cover the 128 bytes one row contributes to a k-step, so a warp-wide load instruction reads
+// four whole 128-byte lines; thread (warp w, lane l) serves rows 4w + l/8 + 32 i, i = 0..3.
 struct RowCopyProducerF32 {
   static constexpr bool kBulk = false;
   const float* x;
@@ -474,48 +511,54 @@ struct RowCopyProducerF32 {
   int K;
   bool split;  // also write the residual block right after the big block (3xTF32)
   __device__ void run(const ProdCtx& pc) const {
-    const int r = pc.t >> 1, half = pc.t & 1;
-    const int64_t m = (int64_t)pc.m_tile * 128 + r;
-    const bool live = m < M;
-    const float* row = x + (live ? m * ld : 0);
+    const int warp = pc.t >> 5, lane = pc.t & 31;
+    const int c = lane & 7, rbase = warp * 4 + (lane >> 3);
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const float* rowp[4];
+    bool live[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = (int64_t)pc.m_tile * 128 + rbase + 32 * i;
+      live[i] = m < M;
+      rowp[i] = x + (live[i] ? m * ld : 0);
+    }
     float4 cur[4], nxt[4];
     auto load = [&](float4 (&dst)[4], int ks) {
+      const int k = ks * 32 + c * 4;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int k = ks * 32 + (half * 4 + c) * 4;
-        if (live && vec && k + 4 <= K) {
-          dst[c] = __ldg(reinterpret_cast<const float4*>(row + k));
+      for (int i = 0; i < 4; ++i) {
+        if (live[i] && vec && k + 4 <= K) {
+          dst[i] = __ldg(reinterpret_cast<const float4*>(rowp[i] + k));
         } else {
           float v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = (live && k + j < K) ? __ldg(row + k + j) : 0.f;
-          dst[c] = make_float4(v[0], v[1], v[2], v[3]);
+          for (int j = 0; j < 4; ++j) v[j] = (live[i] && k + j < K) ? __ldg(rowp[i] + k + j) : 0.f;
+          dst[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
     };
+    const int off = ((c ^ (rbase & 7)) & 7) << 4;
     load(cur, pc.ks0);
     for (int it = 0; it < pc.n_it; ++it) {
       if (it + 1 < pc.n_it) load(nxt, pc.ks0 + it + 1);
       pc.wait_empty(it);
-      uint8_t* dst = pc.stage(it) + r * 128;
+      uint8_t* dst = pc.stage(it) + rbase * 128 + off;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 x4 = cur[c];
+      for (int i = 0; i < 4; ++i) {
+        const float4 x4 = cur[i];
         float4 v;
         v.x = round_tf32(x4.x); v.y = round_tf32(x4.y); v.z = round_tf32(x4.z); v.w = round_tf32(x4.w);
-        const int off = (((half * 4 + c) ^ (r & 7)) & 7) << 4;
-        *reinterpret_cast<float4*>(dst + off) = v;
+        *reinterpret_cast<float4*>(dst + i * 32 * 128) = v;
         if (split) {
           float4 q;
           q.x = round_tf32(x4.x - v.x); q.y = round_tf32(x4.y - v.y); q.z = round_tf32(x4.z - v.z);
           q.w = round_tf32(x4.w - v.w);
-          *reinterpret_cast<float4*>(dst + kBlockBytes + off) = q;
+          *reinterpret_cast<float4*>(dst + kBlockBytes + i * 32 * 128) = q;
         }
       }
       pc.arrive_full(it);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
     }
   }
 };
