@@ -21,8 +21,10 @@ namespace {
 
 using namespace tc;
 
-// one warp per row: max over V (shared with simple_loss.cu's kernel in spirit; kept local for the TC path)
-__global__ void tc_row_max_kernel(const float* __restrict__ x, int64_t rows, int V, float* __restrict__ out) {
+// one warp per row: max over V.  For the lm rows (info != nullptr) lane 0 also records what the
+// normaliser epilogue needs per symbol position: {max, lm[blank], lm[sym[b, s]]} as one 16-byte record.
+__global__ void tc_row_max_kernel(const float* __restrict__ x, int64_t rows, int V, float* __restrict__ out,
+                                  const int64_t* __restrict__ sym, int S, int blank, float4* __restrict__ info) {
   int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   if (row >= rows) return;
   const int lane = threadIdx.x % 32;
@@ -30,7 +32,15 @@ __global__ void tc_row_max_kernel(const float* __restrict__ x, int64_t rows, int
   float m = kNegInf;
   for (int c = lane; c < V; c += 32) m = fmaxf(m, __ldg(p + c));
   m = warp_max(m);
-  if (lane == 0) out[row] = m;
+  if (lane == 0) {
+    out[row] = m;
+    if (info) {
+      const int64_t b = row / (S + 1);
+      const int s = (int)(row % (S + 1));
+      const float ls = (s < S) ? __ldg(p + (int)sym[b * S + s]) : 0.f;
+      info[row] = make_float4(m, __ldg(p + blank), ls, 0.f);
+    }
+  }
 }
 
 // K-major 3xTF32 A: rows = frames t of batch b, 32 vocabulary entries per k-step, value exp(am - am_max).
@@ -99,56 +109,68 @@ struct ExpRowProducerF32 {
   }
 };
 
-// accumulator rows = frames t (ctx.m inside batch ctx.batch), columns = symbol positions s
+// accumulator rows = frames t (ctx.m inside batch ctx.batch), columns = symbol positions s.
+// Writes nrm and py (lane = frame, so every store instruction is one contiguous 128-byte row segment of the
+// k2 (B, S+1, T) layout); px needs the gather am[b, t, sym[b, s]] and is finished by simple_px_kernel with
+// the whole GPU instead of the four epilogue warps.
 struct SimpleEmitTcEpi {
   static constexpr int kScratchBytes = 0;
   const float* am;
-  const float* lm;
   const float* am_max;
-  const float* lm_max;
-  const int64_t* sym;
-  const int64_t* boundary;
+  const float4* lm_info;  // (B, S+1): {lm_max, lm[blank], lm[sym], -}
   int T, S, V, blank;
-  float* px;   // (B, S, T+1)
   float* py;   // (B, S+1, T)
   float* nrm;  // (B, S+1, T)
   struct State {
-    const float* am_row;
     float amx, am_blank;
-    int Tb;
     bool live;
   };
   __device__ void begin(State& st, const EpiCtx& ctx) const {
     const int b = ctx.batch, t = ctx.m;
     st.live = t < T;
-    st.am_row = am + ((int64_t)b * T + (st.live ? t : 0)) * V;
-    st.amx = st.live ? am_max[(int64_t)b * T + t] : 0.f;
-    st.am_blank = st.live ? __ldg(st.am_row + blank) : 0.f;
-    st.Tb = boundary ? (int)boundary[4 * b + 3] : T;
+    const int64_t r = (int64_t)b * T + (st.live ? t : 0);
+    st.amx = st.live ? am_max[r] : 0.f;
+    st.am_blank = st.live ? __ldg(am + r * V + blank) : 0.f;
   }
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
-    if (!st.live) return;
+    if (!st.live || n > S) return;
     const int b = ctx.batch, t = ctx.m;
-#pragma unroll 4
+    const float4* info = lm_info + (int64_t)b * (S + 1);
+    float* nrow = nrm + ((int64_t)b * (S + 1) + n) * T + t;
+    float* prow = py + ((int64_t)b * (S + 1) + n) * T + t;
+#pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int s = n + j;
-      if (s > S) break;
-      const float* lm_row = lm + ((int64_t)b * (S + 1) + s) * V;
-      const float nv = logf(acc[j] + FLT_MIN) + __ldg(lm_max + (int64_t)b * (S + 1) + s) + st.amx;
-      const int64_t o = ((int64_t)b * (S + 1) + s) * T + t;
-      nrm[o] = nv;
-      py[o] = st.am_blank + __ldg(lm_row + blank) - nv;
-      if (s < S) {
-        const int c = (int)sym[(int64_t)b * S + s];
-        float* px_row = px + ((int64_t)b * S + s) * (T + 1);
-        const float v = __ldg(st.am_row + c) + __ldg(lm_row + c) - nv;
-        px_row[t] = (t == st.Tb) ? kNegInf : v;
-        if (t == T - 1) px_row[T] = kNegInf;
+      if (n + j <= S) {
+        const float4 li = __ldg(info + n + j);
+        const float nv = logf(acc[j] + FLT_MIN) + li.x + st.amx;
+        nrow[(int64_t)j * T] = nv;
+        prow[(int64_t)j * T] = st.am_blank + li.y - nv;
       }
     }
   }
 };
+
+// px[b, s, t] = am[b, t, sym[b, s]] + lm[b, s, sym[b, s]] - nrm[b, s, t]   (-inf at t = T_b and in column T)
+__global__ void simple_px_kernel(const float* __restrict__ am, const float4* __restrict__ lm_info,
+                                 const float* __restrict__ nrm, const int64_t* __restrict__ sym,
+                                 const int64_t* __restrict__ boundary, int B, int T, int S, int V,
+                                 float* __restrict__ px) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * S * (T + 1);
+  if (i >= total) return;
+  const int t = (int)(i % (T + 1));
+  const int64_t bs = i / (T + 1);
+  const int s = (int)(bs % S), b = (int)(bs / S);
+  float v = kNegInf;
+  const int Tb = boundary ? (int)boundary[4 * b + 3] : T;
+  if (t < T && t != Tb) {
+    const int c = (int)sym[bs];
+    const int64_t row = (int64_t)b * (S + 1) + s;
+    v = __ldg(am + ((int64_t)b * T + t) * V + c) + __ldg(lm_info + row).z - __ldg(nrm + row * T + t);
+  }
+  px[i] = v;
+}
 
 // W[b,s,t] = coef_b (occ_px + occ_py) exp(am_max + lm_max - nrm) -> bf16 packed twice:
 //   Wst: rows (b, s) cols t        Wts: rows (b, t) cols s
@@ -184,36 +206,50 @@ __global__ void simple_w_packed_kernel(const float* __restrict__ occ_px, const f
   }
 }
 
-// out[b, r, c] = -exp(x[b, r, c] - max[b, r]) * acc      accumulator rows r (inside batch), cols c
+// out[b, r, c] = -exp(x[b, r, c] - max[b, r]) * acc      accumulator rows r (inside batch), cols c.
+// Transposed through shared memory so that x is read and out written in 64-byte row segments.
 struct GradExpEpi {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = kTransposeScratchBytes;
   const float* x;
   const float* mx;
   int rows, V;
   float* out;
-  struct State { const float* xr; float* orow; float sub; bool live; };
+  struct State { float sub[4]; };  // row maxima of the four rows this lane serves after the transpose
   __device__ void begin(State& st, const EpiCtx& ctx) const {
-    st.live = ctx.m < rows;
-    const int64_t r = (int64_t)ctx.batch * rows + (st.live ? ctx.m : 0);
-    st.xr = x + r * V;
-    st.orow = out + r * V;
-    st.sub = st.live ? mx[r] : 0.f;
+    const int lane = ctx.t & 31, m0 = ctx.m - lane;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int r = m0 + pass * 8 + (lane & 7);
+      st.sub[pass] = r < rows ? mx[(int64_t)ctx.batch * rows + r] : 0.f;
+    }
   }
   __device__ void end(State&, const EpiCtx&) const {}
-  __device__ void chunk(State& st, const EpiCtx&, int n, const float (&acc)[32]) const {
-    if (!st.live) return;
+  __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    const int m0 = ctx.m - (ctx.t & 31);
+    const bool vec = ((V & 3) == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    warp_transposed_chunk(ctx, acc, V - n, [&](int r, int c, float4 v) {
+      const int m = m0 + r, col = n + c;
+      if (m >= rows || col >= V) return;
+      const float sub = st.sub[r >> 3];
+      const int64_t o = ((int64_t)ctx.batch * rows + m) * V + col;
+      if (vec) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + o));
+        *reinterpret_cast<float4*>(out + o) = make_float4(-__expf(xv.x - sub) * v.x, -__expf(xv.y - sub) * v.y,
+                                                          -__expf(xv.z - sub) * v.z, -__expf(xv.w - sub) * v.w);
+      } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = n + j;
-      if (c < V) st.orow[c] = -expf(__ldg(st.xr + c) - st.sub) * acc[j];
-    }
+        for (int j = 0; j < 4; ++j)
+          if (col + j < V) out[o + j] = -__expf(__ldg(x + o + j) - sub) * e[j];
+      }
+    });
   }
 };
 
 struct SimpleTcDims {
   int Spad, Tpad, Vp;  // S+1 and T padded to 128, V padded to 256
   int kb32, kb64;      // vocabulary blocks of 32 (fp32) / 64 (bf16, = Vp / 64)
-  size_t lm_f32, am_bf16, lm_bf16, wst, wts;
+  size_t lm_f32, am_bf16, lm_bf16, wst, wts, info;
 };
 
 SimpleTcDims simple_tc_dims(int B, int T, int S, int V) {
@@ -228,6 +264,7 @@ SimpleTcDims simple_tc_dims(int B, int T, int S, int V) {
   d.lm_bf16 = (size_t)B * (d.Spad / 128) * d.kb64 * kBlockBytes;
   d.wst = (size_t)B * (d.Spad / 128) * (d.Tpad / 64) * kBlockBytes;
   d.wts = (size_t)B * (d.Tpad / 128) * (d.Spad / 64) * kBlockBytes;
+  d.info = (((size_t)B * (S + 1) * sizeof(float4)) + 1023) / 1024 * 1024;
   return d;
 }
 
@@ -235,7 +272,7 @@ SimpleTcDims simple_tc_dims(int B, int T, int S, int V) {
 
 size_t simple_tc_workspace_bytes(int B, int T, int S, int V) {
   SimpleTcDims d = simple_tc_dims(B, T, S, V);
-  return 2 * d.lm_f32 + d.am_bf16 + d.lm_bf16 + d.wst + d.wts + 4096;
+  return 2 * d.lm_f32 + d.am_bf16 + d.lm_bf16 + d.wst + d.wts + d.info + 4096;
 }
 
 int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
@@ -244,23 +281,33 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   SimpleTcDims d = simple_tc_dims(B, T, S, V);
   uint8_t* lm_big = (uint8_t*)ws;
   uint8_t* lm_small = lm_big + d.lm_f32;
+  float4* lm_info = (float4*)((uint8_t*)ws + 2 * d.lm_f32 + d.am_bf16 + d.lm_bf16 + d.wst + d.wts);
   const int wpb = 8;
   const int64_t rows_am = (int64_t)B * T, rows_lm = (int64_t)B * (S + 1);
   {
     ProfScope prof("row_max_kernel", stream, 2);
-    tc_row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max);
-    tc_row_max_kernel<<<(unsigned)((rows_lm + wpb - 1) / wpb), wpb * 32, 0, stream>>>(lm, rows_lm, V, lm_max);
+    tc_row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max, nullptr, S,
+                                                                                      blank, nullptr);
+    tc_row_max_kernel<<<(unsigned)((rows_lm + wpb - 1) / wpb), wpb * 32, 0, stream>>>(lm, rows_lm, V, lm_max, sym, S,
+                                                                                      blank, lm_info);
   }
   if (int rc = check_launch("row_max_kernel")) return rc;
   PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
   if (int rc = pack_f32_split(ps, lm_big, lm_small, stream)) return rc;
   ExpRowProducerF32 a{am, am_max, T, V};
-  SimpleEmitTcEpi ep{am, lm, am_max, lm_max, sym, boundary, T, S, V, blank, px, py, nrm};
+  SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm};
   MnDebug extra;
   extra.b_small = lm_small;
   extra.b_batch_off = d.Spad / 128;
-  return launch_gemm_stream<128, 3, false, 2>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32, 1, ep,
-                                              stream, "tc_simple_normaliser_gemm_3xtf32", extra, B);
+  if (int rc = launch_gemm_stream<128, 3, false, 2>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32, 1,
+                                                    ep, stream, "tc_simple_normaliser_gemm_3xtf32", extra, B))
+    return rc;
+  const int64_t total = (int64_t)B * S * (T + 1);
+  if (total > 0) {
+    ProfScope prof("simple_px_kernel", stream);
+    simple_px_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(am, lm_info, nrm, sym, boundary, B, T, S, V, px);
+  }
+  return check_launch("simple_px_kernel");
 }
 
 int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, const float* am_max,

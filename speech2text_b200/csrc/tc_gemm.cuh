@@ -421,59 +421,71 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
 // every store instruction of the warp touch 32 different lines.  Each warp instead transposes 32 x 16
 // sub-tiles through a padded shared-memory tile (row stride 20 words: conflict-free for the 16-byte
 // writes by row and the 16-byte reads by 8 rows x 4 column groups) and writes 64 contiguous bytes per row.
+constexpr int kTransposeRowWords = 20;
+constexpr int kTransposeScratchBytes = 4 * 32 * kTransposeRowWords * 4;  // per epilogue group
+
+// Hands the warp's 32 x 32 accumulator chunk (thread = row) back as f(r, c, v): v = columns c .. c+3 of the
+// warp's row r, with the eight lanes l, l+8, l+16, l+24 ... of a call covering 64 contiguous bytes of a row.
+// f is called 8 times per thread; `cols` (uniform over the warp) limits the columns that are needed.
+template <class F>
+__device__ __forceinline__ void warp_transposed_chunk(const EpiCtx& ctx, const float (&acc)[32], int cols, F&& f) {
+  float* tile = reinterpret_cast<float*>(ctx.scratch) + (ctx.t >> 5) * (32 * kTransposeRowWords);
+  const int lane = ctx.t & 31;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (h * 16 >= cols) break;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(tile + lane * kTransposeRowWords + q * 4) =
+          make_float4(acc[h * 16 + q * 4 + 0], acc[h * 16 + q * 4 + 1], acc[h * 16 + q * 4 + 2], acc[h * 16 + q * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int r = pass * 8 + (lane & 7), cg = lane >> 3;
+      const float4 v = *reinterpret_cast<const float4*>(tile + r * kTransposeRowWords + cg * 4);
+      f(r, h * 16 + cg * 4, v);
+    }
+    __syncwarp();
+  }
+}
+
 struct StoreRowMajorEpi {
   float* C;
   int64_t ldc;
   int M, N;
   bool atomic;
   const float* bias = nullptr;  // added per column when not atomic
-  static constexpr int kRowWords = 20;
-  static constexpr int kScratchBytes = 4 * 32 * kRowWords * 4;
+  static constexpr int kScratchBytes = kTransposeScratchBytes;
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
-    float* tile = reinterpret_cast<float*>(ctx.scratch) + (ctx.t >> 5) * (32 * kRowWords);
-    const int lane = ctx.t & 31;
-    const int m0 = ctx.m - lane;  // first row of this warp
+    const int m0 = ctx.m - (ctx.t & 31);  // first row of this warp
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (n + h * 16 >= N) break;  // uniform over the warp
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(tile + lane * kRowWords + q * 4) =
-            make_float4(acc[h * 16 + q * 4 + 0], acc[h * 16 + q * 4 + 1], acc[h * 16 + q * 4 + 2], acc[h * 16 + q * 4 + 3]);
-      __syncwarp();
-#pragma unroll
-      for (int pass = 0; pass < 4; ++pass) {
-        const int r = pass * 8 + (lane & 7), cg = lane >> 3;
-        float4 v = *reinterpret_cast<const float4*>(tile + r * kRowWords + cg * 4);
-        const int m = m0 + r, col = n + h * 16 + cg * 4;
-        if (m >= M || col >= N) continue;
-        float* dst = C + (int64_t)m * ldc + col;
-        if (vec_ok && col + 4 <= N) {
-          if (atomic) {
-            atomicAdd(reinterpret_cast<float4*>(dst), v);
-          } else {
-            if (bias) {
-              v.x += __ldg(bias + col); v.y += __ldg(bias + col + 1); v.z += __ldg(bias + col + 2); v.w += __ldg(bias + col + 3);
-            }
-            *reinterpret_cast<float4*>(dst) = v;
-          }
+    warp_transposed_chunk(ctx, acc, N - n, [&](int r, int c, float4 v) {
+      const int m = m0 + r, col = n + c;
+      if (m >= M || col >= N) return;
+      float* dst = C + (int64_t)m * ldc + col;
+      if (vec_ok && col + 4 <= N) {
+        if (atomic) {
+          atomicAdd(reinterpret_cast<float4*>(dst), v);
         } else {
-          const float e[4] = {v.x, v.y, v.z, v.w};
+          if (bias) {
+            v.x += __ldg(bias + col); v.y += __ldg(bias + col + 1); v.z += __ldg(bias + col + 2); v.w += __ldg(bias + col + 3);
+          }
+          *reinterpret_cast<float4*>(dst) = v;
+        }
+      } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (col + j < N) {
-              if (atomic) atomicAdd(dst + j, e[j]);
-              else dst[j] = e[j] + (bias ? __ldg(bias + col + j) : 0.f);
-            }
+        for (int j = 0; j < 4; ++j) {
+          if (col + j < N) {
+            if (atomic) atomicAdd(dst + j, e[j]);
+            else dst[j] = e[j] + (bias ? __ldg(bias + col + j) : 0.f);
           }
         }
       }
-      __syncwarp();
-    }
+    });
   }
 };
 
