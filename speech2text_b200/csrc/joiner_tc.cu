@@ -63,10 +63,10 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32]) {
 }
 
 // ---- per-row metadata -----------------------------------------------------------------------
+// am_row[m] = b * T + t and lm_row[m] = b * (S+1) + s(t, r): the rows of am / lm that joiner row m adds up
 __global__ void tc_row_meta_kernel(const int64_t* __restrict__ ranges, const int64_t* __restrict__ sym,
-                                   int64_t rows, int T, int R, int S, int V, int blank,
-                                   int64_t* __restrict__ am_off, int64_t* __restrict__ lm_off,
-                                   int* __restrict__ row_sym) {
+                                   int64_t rows, int T, int R, int S, int blank, int* __restrict__ am_row,
+                                   int* __restrict__ lm_row, int* __restrict__ row_sym) {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= rows) return;
   int64_t bt = m / R;
@@ -74,124 +74,139 @@ __global__ void tc_row_meta_kernel(const int64_t* __restrict__ ranges, const int
   int64_t b = bt / T;
   int s = ranges ? (int)ranges[m] : r;
   int sc = min(max(s, 0), S);
-  am_off[m] = bt * V;
-  lm_off[m] = (b * (S + 1) + sc) * V;
+  am_row[m] = (int)bt;
+  lm_row[m] = (int)(b * (S + 1) + sc);
   if (row_sym) row_sym[m] = (sym && s >= 0 && s < S) ? (int)sym[b * S + s] : blank;
 }
 
 // ---- A producers ----------------------------------------------------------------------------
-// Both producers turn 64 consecutive vocabulary entries of one joiner row m into eight 16-byte
-// chunks act(am[m, v] + lm[m, v]) -> bf16.  Work is pipelined in half rows (32 entries): the
-// global loads of the next half are issued before the current half is converted, so one L2
-// round trip is exposed per pipeline fill, not per chunk.
-struct JointHalf {
-  float4 a[8], l[8];
+// Both producers build act(am[m, v] + lm[m, v]) -> bf16 straight into the swizzled stage.  Sixteen lanes
+// cover the 64 vocabulary entries (256 contiguous bytes of am and of lm) that one joiner row contributes
+// to a k-step, so every warp-wide load reads whole 128-byte lines; a k-step is pipelined in two halves
+// of four rows per thread, the loads of the next half in flight while the current one is converted.
+__device__ int g_exp_noload = 0;
+struct JointQuad {
+  float4 a[4], l[4];
 };
 
-__device__ __forceinline__ void joint_load_half(JointHalf& h, const float* a, const float* l, int v0, int V,
-                                                bool live, bool vec) {
+// loads entries v .. v+3 of the four rows (am_row[j], lm_row[j]); a negative row index marks a dead row
+__device__ __forceinline__ void joint_load_quad(JointQuad& q, const float* am, const float* lm, const int (&ar)[4],
+                                                const int (&lr)[4], int v, int V, bool vec) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int v = v0 + q * 4;
+  for (int j = 0; j < 4; ++j) {
+    const bool live = ar[j] >= 0;
+    if (g_exp_noload) { q.a[j] = make_float4(0.1f * v, 0.2f, 0.3f, 0.4f); q.l[j] = make_float4(0.1f, 0.2f * lr[j], 0.3f, 0.4f); continue; }
+    const float* a = am + (int64_t)(live ? ar[j] : 0) * V + v;
+    const float* l = lm + (int64_t)(live ? lr[j] : 0) * V + v;
     if (live && vec && v + 4 <= V) {
-      h.a[q] = __ldg(reinterpret_cast<const float4*>(a + v));
-      h.l[q] = __ldg(reinterpret_cast<const float4*>(l + v));
+      q.a[j] = __ldg(reinterpret_cast<const float4*>(a));
+      q.l[j] = __ldg(reinterpret_cast<const float4*>(l));
     } else {
       float xa[4], xl[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = live && (v + j < V);
-        xa[j] = ok ? __ldg(a + v + j) : 0.f;
-        xl[j] = ok ? __ldg(l + v + j) : 0.f;
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = live && (v + e < V);
+        xa[e] = ok ? __ldg(a + e) : 0.f;
+        xl[e] = ok ? __ldg(l + e) : 0.f;
       }
-      h.a[q] = make_float4(xa[0], xa[1], xa[2], xa[3]);
-      h.l[q] = make_float4(xl[0], xl[1], xl[2], xl[3]);
+      q.a[j] = make_float4(xa[0], xa[1], xa[2], xa[3]);
+      q.l[j] = make_float4(xl[0], xl[1], xl[2], xl[3]);
     }
   }
 }
 
-// writes chunks c0 .. c0+3 of the 128-byte row at `row_base`; r7 = (row index & 7) for the swizzle.
-// Padding (v >= V or dead row) must come out as exact zeros: act(0) = 0 for relu and tanh.
-__device__ __forceinline__ void joint_emit_half(const JointHalf& h, uint8_t* row_base, int r7, int c0, int act) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float4 a0 = h.a[2 * c], a1 = h.a[2 * c + 1], l0 = h.l[2 * c], l1 = h.l[2 * c + 1];
-    uint4 out;
-    out.x = pack_bf16x2(act_fwd_fast(a0.x + l0.x, act), act_fwd_fast(a0.y + l0.y, act));
-    out.y = pack_bf16x2(act_fwd_fast(a0.z + l0.z, act), act_fwd_fast(a0.w + l0.w, act));
-    out.z = pack_bf16x2(act_fwd_fast(a1.x + l1.x, act), act_fwd_fast(a1.y + l1.y, act));
-    out.w = pack_bf16x2(act_fwd_fast(a1.z + l1.z, act), act_fwd_fast(a1.w + l1.w, act));
-    *reinterpret_cast<uint4*>(row_base + ((((c0 + c) ^ r7) & 7) << 4)) = out;
-  }
+// 4 entries -> 8 bytes.  Padding (v >= V or dead row) must come out as exact zeros: act(0) = 0 for relu and tanh.
+__device__ __forceinline__ uint2 joint_act4(const float4& a, const float4& l, int act) {
+  return make_uint2(pack_bf16x2(act_fwd_fast(a.x + l.x, act), act_fwd_fast(a.y + l.y, act)),
+                    pack_bf16x2(act_fwd_fast(a.z + l.z, act), act_fwd_fast(a.w + l.w, act)));
 }
 
-// K-major A: block rows = joiner rows m of the tile, K = vocabulary.  Two producer threads per row,
-// each owning one half (32 entries) of every 64-entry k-step.
+// K-major A: block rows = joiner rows m of the tile, K = vocabulary.  Thread (warp w, lane l) serves rows
+// 2w + l/16 + 16 i (i = 0..7) and the four entries 4 (l % 16) .. +3 of every 64-entry k-step.
 struct JointRowProducer {
   static constexpr bool kBulk = false;
   const float* am;
   const float* lm;
-  const int64_t* am_off;
-  const int64_t* lm_off;
+  const int* am_row;
+  const int* lm_row;
   int64_t M;
   int V, act;
   __device__ void run(const ProdCtx& pc) const {
-    const int r = pc.t >> 1, half = pc.t & 1;
-    const int64_t m = (int64_t)pc.m_tile * 128 + r;
-    const bool live = m < M;
-    const float* a = am + (live ? am_off[m] : 0);
-    const float* l = lm + (live ? lm_off[m] : 0);
+    const int warp = pc.t >> 5, lane = pc.t & 31;
+    const int c = lane & 15, rbase = warp * 2 + (lane >> 4);
     const bool vec = ((V & 3) == 0);
-    JointHalf cur, nxt;
-    joint_load_half(cur, a, l, pc.ks0 * 64 + half * 32, V, live, vec);
+    int ar[2][4], lr[2][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t m = (int64_t)pc.m_tile * 128 + rbase + 16 * i;
+      ar[i >> 2][i & 3] = m < M ? __ldg(am_row + m) : -1;
+      lr[i >> 2][i & 3] = m < M ? __ldg(lm_row + m) : 0;
+    }
+    // byte offset inside the stage of this thread's 8 bytes in row rbase (+ 16 i rows: the swizzle only sees row & 7)
+    const int off = rbase * 128 + ((((c >> 1) ^ (rbase & 7)) & 7) << 4) + (c & 1) * 8;
+    JointQuad q0, q1;
+    joint_load_quad(q0, am, lm, ar[0], lr[0], pc.ks0 * 64 + c * 4, V, vec);
     for (int it = 0; it < pc.n_it; ++it) {
-      if (it + 1 < pc.n_it) joint_load_half(nxt, a, l, (pc.ks0 + it + 1) * 64 + half * 32, V, live, vec);
+      const int v = (pc.ks0 + it) * 64 + c * 4;
+      joint_load_quad(q1, am, lm, ar[1], lr[1], v, V, vec);
       pc.wait_empty(it);
-      joint_emit_half(cur, pc.stage(it) + r * 128, r & 7, half * 4, act);
+      uint8_t* dst = pc.stage(it) + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(dst + j * 16 * 128) = joint_act4(q0.a[j], q0.l[j], act);
+      if (it + 1 < pc.n_it) joint_load_quad(q0, am, lm, ar[0], lr[0], v + 64, V, vec);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(dst + (4 + j) * 16 * 128) = joint_act4(q1.a[j], q1.l[j], act);
       pc.arrive_full(it);
-      cur = nxt;
     }
   }
 };
 
-// MN-major A: stage = 2 groups x [64 contraction rows (joiner rows m) x 64 vocabulary entries]; four
-// producer threads per contraction row (group x half).
+// MN-major A: stage = 2 groups x [64 contraction rows (joiner rows m) x 64 vocabulary entries].  A warp
+// covers the 128 entries of one contraction row (512 contiguous bytes of am and of lm): lane l owns entries
+// 4 l .. +3 (group l / 16), thread (warp w) serves contraction rows w + 8 i (i = 0..7) of every k-step.
 struct JointMnProducer {
   static constexpr bool kBulk = false;
   const float* am;
   const float* lm;
-  const int64_t* am_off;
-  const int64_t* lm_off;
+  const int* am_row;
+  const int* lm_row;
   int64_t row0, M;
   int V, act;
   __device__ void run(const ProdCtx& pc) const {
-    const int r = pc.t >> 2, g = (pc.t >> 1) & 1, half = pc.t & 1;
-    const int v_base = pc.m_tile * 128 + g * 64 + half * 32;
+    const int warp = pc.t >> 5, lane = pc.t & 31;
+    const int g = lane >> 4, c = lane & 15;
+    const int v = pc.m_tile * 128 + lane * 4;
     const bool vec = ((V & 3) == 0);
-    auto row_ptrs = [&](int ks, const float*& a, const float*& l, bool& live) {
-      const int64_t m = row0 + (int64_t)ks * 64 + r;
-      live = m < M;
-      a = am + (live ? am_off[m] : 0);
-      l = lm + (live ? lm_off[m] : 0);
-    };
-    JointHalf cur, nxt;
-    {
-      const float *a, *l;
-      bool live;
-      row_ptrs(pc.ks0, a, l, live);
-      joint_load_half(cur, a, l, v_base, V, live, vec);
-    }
-    for (int it = 0; it < pc.n_it; ++it) {
-      if (it + 1 < pc.n_it) {
-        const float *a, *l;
-        bool live;
-        row_ptrs(pc.ks0 + it + 1, a, l, live);
-        joint_load_half(nxt, a, l, v_base, V, live, vec);
+    auto load_rows = [&](int (&ar)[2][4], int (&lr)[2][4], int ks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = row0 + (int64_t)ks * 64 + warp + 8 * i;
+        ar[i >> 2][i & 3] = m < M ? __ldg(am_row + m) : -1;
+        lr[i >> 2][i & 3] = m < M ? __ldg(lm_row + m) : 0;
       }
+    };
+    const int off = g * kGroupBytes + warp * 128 + ((((c >> 1) ^ (warp & 7)) & 7) << 4) + (c & 1) * 8;
+    int ar[2][4], lr[2][4], ar_n[2][4], lr_n[2][4];
+    load_rows(ar, lr, pc.ks0);
+    JointQuad q0, q1;
+    joint_load_quad(q0, am, lm, ar[0], lr[0], v, V, vec);
+    for (int it = 0; it < pc.n_it; ++it) {
+      const bool more = it + 1 < pc.n_it;
+      if (more) load_rows(ar_n, lr_n, pc.ks0 + it + 1);
+      joint_load_quad(q1, am, lm, ar[1], lr[1], v, V, vec);
       pc.wait_empty(it);
-      joint_emit_half(cur, pc.stage(it) + g * kGroupBytes + r * 128, r & 7, half * 4, act);
+      uint8_t* dst = pc.stage(it) + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(dst + j * 8 * 128) = joint_act4(q0.a[j], q0.l[j], act);
+      if (more) joint_load_quad(q0, am, lm, ar_n[0], lr_n[0], v, V, vec);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(dst + (4 + j) * 8 * 128) = joint_act4(q1.a[j], q1.l[j], act);
       pc.arrive_full(it);
-      cur = nxt;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ar[i >> 2][i & 3] = ar_n[i >> 2][i & 3];
+        lr[i >> 2][i & 3] = lr_n[i >> 2][i & 3];
+      }
     }
   }
 };
@@ -421,7 +436,7 @@ struct StoreRowsBf16Epi {
 // d_am[b,t,v] += sum_r dh[(b,t,r), v] * act'(am[b,t,v] + lm[b, s(t,r), v])      (A.5: sum over the band slots)
 // one thread per (frame, 4 consecutive v): every read and the write are coalesced 8/16-byte accesses, no atomics.
 __global__ void djoint_am_kernel(const __nv_bfloat16* __restrict__ dh, int ld, const float* __restrict__ am,
-                                 const float* __restrict__ lm, const int64_t* __restrict__ lm_off, int64_t row0,
+                                 const float* __restrict__ lm, const int* __restrict__ lm_row, int64_t row0,
                                  int64_t rows, int64_t M, int R, int V, int act, float* __restrict__ d_am) {
   const int64_t f0 = row0 / R, f1 = (min(row0 + rows, M) + R - 1) / R;  // frames touched by this chunk
   const int vq = (V + 3) / 4;
@@ -444,7 +459,7 @@ __global__ void djoint_am_kernel(const __nv_bfloat16* __restrict__ dh, int ld, c
     if (m < row0 || m >= row0 + rows || m >= M) continue;
     const uint2 raw = *reinterpret_cast<const uint2*>(dh + (m - row0) * ld + v);  // ld and v are multiples of 4
     const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&raw);
-    const float* lrow = lm + lm_off[m] + v;
+    const float* lrow = lm + (int64_t)lm_row[m] * V + v;
     float l[4];
     if (vec) {
       const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
@@ -599,8 +614,8 @@ TcDims tc_dims(int64_t M, int V, int I) {
 }
 
 struct TcWs {
-  int64_t* am_off;
-  int64_t* lm_off;
+  int* am_row;
+  int* lm_row;
   int* row_sym;
   float* part;
   float* sym_logit;
@@ -621,8 +636,8 @@ TcWs tc_carve(void* ws, const TcDims& d) {
     return q;
   };
   const int ct = (int)(d.chunk / 128);
-  w.am_off = (int64_t*)take(d.M * sizeof(int64_t));
-  w.lm_off = (int64_t*)take(d.M * sizeof(int64_t));
+  w.am_row = (int*)take(d.M * sizeof(int));
+  w.lm_row = (int*)take(d.M * sizeof(int));
   w.row_sym = (int*)take(d.M * sizeof(int));
   w.part = (float*)take((size_t)d.M * d.n_parts_v * 2 * sizeof(float));
   w.sym_logit = (float*)take(d.M * sizeof(float));
@@ -669,14 +684,22 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   TcWs w = tc_carve(workspace, d);
   {
     ProfScope prof("tc_row_meta_kernel", stream);
-    tc_row_meta_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(p.ranges, p.sym, M, p.T, p.R, p.S, p.V, p.blank,
-                                                                       w.am_off, w.lm_off, w.row_sym);
+    tc_row_meta_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(p.ranges, p.sym, M, p.T, p.R, p.S, p.blank,
+                                                                       w.am_row, w.lm_row, w.row_sym);
   }
   if (int rc = check_launch("tc_row_meta_kernel")) return rc;
+  {
+    static int exp_flag = -1;
+    if (exp_flag < 0) {
+      const char* e = getenv("S2T_EXP");
+      exp_flag = e ? atoi(e) : 0;
+      cudaMemcpyToSymbol(g_exp_noload, &exp_flag, sizeof(int));
+    }
+  }
   if (int rc = pack_weights(p, d, w, false, stream)) return rc;
   // hidden: M x Ip, K = V
   {
-    JointRowProducer a{p.am, p.lm, w.am_off, w.lm_off, M, p.V, p.act};
+    JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act};
     HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt};
     if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
                                             "tc_joiner_hidden_gemm"))
@@ -741,7 +764,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     }
     // dW1[i, v] += sum_m dhidden[m, i] act(.)[m, v]: accumulator rows v (A built on the fly), cols i
     {
-      JointMnProducer a{p.am, p.lm, w.am_off, w.lm_off, row0, M, p.V, p.act};
+      JointMnProducer a{p.am, p.lm, w.am_row, w.lm_row, row0, M, p.V, p.act};
       StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
       if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, stream,
                                                     "tc_joiner_dW1_gemm"))
@@ -759,7 +782,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
         const int64_t f0 = row0 / p.R, f1 = (row0 + rows_live + p.R - 1) / p.R;
         const int64_t n = (f1 - f0) * ((p.V + 3) / 4);
         ProfScope prof("djoint_am_kernel", stream);
-        djoint_am_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, w.lm_off, row0, rows_live,
+        djoint_am_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, w.lm_row, row0, rows_live,
                                                                          M, p.R, p.V, p.act, d_am);
       }
       {

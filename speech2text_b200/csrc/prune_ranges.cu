@@ -7,14 +7,16 @@
 // Integer output, bit-exact contract: identical (px_grad, py_grad) inputs, fp32
 // left-to-right summation over the window, first-maximum tie-break.
 //
-// One CTA per utterance:
-//   phase 1  thread-per-frame argmax over s (reads are coalesced along t: the
-//            occupation arrays are t-contiguous),
-//   phase 2  padding fix-up + two suffix-min scans (k2.monotonic_lower_bound)
-//            with the +-(R-1)*t transform between them, done in shared memory,
-//   phase 3  coalesced int64 store of ranges[b, t, 0..R).
-// HBM-bound integer/compare work: reads (S*(T+1) + (S+1)*T)*4 B, writes T*R*8 B
-// per utterance.
+// Two launches:
+//   prune_argmax_kernel  thread (frame t, candidate segment): argmax over s of the window score.  Reads
+//            are coalesced along t (the occupation arrays are t-contiguous); the candidates of a frame
+//            are split over 8 segments so that B*T*8 threads share the latency-bound scan, and merged in
+//            segment order with a strict '>' (first maximum wins, as in a serial scan).  The raw window
+//            starts are parked in ranges[b, t, 0].
+//   prune_adjust_kernel  one CTA per utterance: padding fix-up + two suffix-min scans
+//            (k2.monotonic_lower_bound) with the +-(R-1)*t transform between them in shared memory, then
+//            the coalesced int64 store of ranges[b, t, 0..R).
+// HBM-bound integer/compare work: reads (S*(T+1) + (S+1)*T)*4 B, writes T*R*8 B per utterance.
 #include "common.cuh"
 
 namespace s2t {
@@ -53,109 +55,132 @@ __device__ void suffix_min_inplace(int* sm, int* tmp, int T) {
   }
 }
 
+constexpr int kSegs = 8;
+
 template <int VARIANT>
-__global__ void __launch_bounds__(kThreads)
-prune_ranges_kernel(const float* __restrict__ px_grad, const float* __restrict__ py_grad,
-                    const int64_t* __restrict__ boundary, int S, int T, int R,
-                    int64_t* __restrict__ ranges) {
-  extern __shared__ int sm[];  // T ints + blockDim scratch
-  int* sbeg = sm;
-  int* tmp = sm + T;
-  const int b = blockIdx.x;
+__global__ void __launch_bounds__(32 * kSegs)
+prune_argmax_kernel(const float* __restrict__ px_grad, const float* __restrict__ py_grad,
+                    const int64_t* __restrict__ boundary, int S, int T, int R, int64_t* __restrict__ ranges) {
+  __shared__ float seg_v[kSegs][32];
+  __shared__ int seg_s[kSegs][32];
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 32 + threadIdx.x;
+  const int seg = threadIdx.y;
   const int S1 = S + 1, T1 = T + 1;
   const float* pxg = px_grad + (int64_t)b * S * T1;
   const float* pyg = py_grad + (int64_t)b * S1 * T;
   const int Sb = (int)boundary[4 * b + 2], Tb = (int)boundary[4 * b + 3];
-  const int pad = max(Sb - R + 1, 0);
   const int ncand = S1 - R + 1;
-
-  // phase 1: argmax_s of the window score, one frame per thread.  The window of R occupation values
-  // slides through registers (one new py_grad load + one px_grad load per candidate); the sum is
-  // still formed left to right over the window, which is the bit-exactness contract.
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    int best = 0;
-    if (t < Tb - 1) {
-      float best_v = kNegInf;
-      if (VARIANT == 0) {
-        constexpr int kMaxR = 8;
-        if (R <= kMaxR) {
-          float w[kMaxR];
+  // variant B carries a running sum from s = 0 (sequential by contract): one segment does all of it
+  const int per = VARIANT == 0 ? (ncand + kSegs - 1) / kSegs : ncand;
+  const int s0 = min(seg * per, ncand), s1 = min(s0 + per, ncand);
+  float best_v = kNegInf;
+  int best = s0;
+  if (t < Tb - 1 && t < T && s0 < s1) {
+    if (VARIANT == 0) {
+      // The window of R occupation values slides through registers (one new py_grad load + one px_grad
+      // load per candidate); the sum is still formed left to right over the window, which is the
+      // bit-exactness contract.
+      constexpr int kMaxR = 8;
+      if (R <= kMaxR) {
+        float w[kMaxR];
 #pragma unroll
-          for (int k = 0; k < kMaxR; ++k) w[k] = (k < R - 1) ? __ldg(pyg + (int64_t)k * T + t) : 0.f;
-          const float* py_in = pyg + (int64_t)(R - 1) * T + t;
-          const float* px_in = pxg + t - T1;  // px_grad[s-1, t]
+        for (int k = 0; k < kMaxR; ++k) w[k] = (k < R - 1) ? __ldg(pyg + (int64_t)(s0 + k) * T + t) : 0.f;
+        const float* py_in = pyg + (int64_t)(R - 1) * T + t;
+        const float* px_in = pxg + t - T1;  // px_grad[s-1, t]
 #pragma unroll 4
-          for (int s = 0; s < ncand; ++s) {
-            const float newest = __ldg(py_in + (int64_t)s * T);
-            const float pxp = (s == 0) ? 0.f : __ldg(px_in + (int64_t)s * T1);
-            float acc = w[0];
+        for (int s = s0; s < s1; ++s) {
+          const float newest = __ldg(py_in + (int64_t)s * T);
+          const float pxp = (s == 0) ? 0.f : __ldg(px_in + (int64_t)s * T1);
+          float acc = w[0];
 #pragma unroll
-            for (int k = 1; k < kMaxR; ++k) {
-              if (k < R - 1) acc += w[k];
-            }
-            if (R > 1) acc += newest; else acc = newest;
-            const float v = acc - pxp;
-            if (v > best_v) {
-              best_v = v;
-              best = s;
-            }
-#pragma unroll
-            for (int k = 0; k < kMaxR - 1; ++k) w[k] = w[k + 1];
-            if (R >= 2) {
-#pragma unroll
-              for (int k = 0; k < kMaxR; ++k)
-                if (k == R - 2) w[k] = newest;
-            }
+          for (int k = 1; k < kMaxR; ++k) {
+            if (k < R - 1) acc += w[k];
           }
-        } else {
-          for (int s = 0; s < ncand; ++s) {
-            float acc = __ldg(pyg + (int64_t)s * T + t);
-            for (int k = 1; k < R; ++k) acc += __ldg(pyg + (int64_t)(s + k) * T + t);
-            float pxp = (s == 0) ? 0.f : __ldg(pxg + (int64_t)(s - 1) * T1 + t);
-            const float v = acc - pxp;
-            if (v > best_v) {
-              best_v = v;
-              best = s;
-            }
-          }
-        }
-      } else {
-        // B: cs[s+R] - cs[s] with cs the running sum over s of px_grad + py_grad, formed sequentially
-        // from 0 exactly as the oracle does: cs_lo and cs_hi are two pointers into the same running sum.
-        float cs_hi = 0.f;
-        for (int j = 0; j < R; ++j)
-          cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
-        float cs_lo = 0.f;
-        for (int s = 0; s < ncand; ++s) {
-          const float v = cs_hi - cs_lo;
+          if (R > 1) acc += newest; else acc = newest;
+          const float v = acc - pxp;
           if (v > best_v) {
             best_v = v;
             best = s;
           }
-          if (s + 1 < ncand) {
-            cs_lo += (s < S ? __ldg(pxg + (int64_t)s * T1 + t) : 0.f) + __ldg(pyg + (int64_t)s * T + t);
-            const int j = s + R;
-            cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+#pragma unroll
+          for (int k = 0; k < kMaxR - 1; ++k) w[k] = w[k + 1];
+          if (R >= 2) {
+#pragma unroll
+            for (int k = 0; k < kMaxR; ++k)
+              if (k == R - 2) w[k] = newest;
+          }
+        }
+      } else {
+        for (int s = s0; s < s1; ++s) {
+          float acc = __ldg(pyg + (int64_t)s * T + t);
+          for (int k = 1; k < R; ++k) acc += __ldg(pyg + (int64_t)(s + k) * T + t);
+          float pxp = (s == 0) ? 0.f : __ldg(pxg + (int64_t)(s - 1) * T1 + t);
+          const float v = acc - pxp;
+          if (v > best_v) {
+            best_v = v;
+            best = s;
           }
         }
       }
     } else {
-      best = pad;  // last real frame and padding frames
+      // B: cs[s+R] - cs[s] with cs the running sum over s of px_grad + py_grad, formed sequentially
+      // from 0 exactly as the oracle does: cs_lo and cs_hi are two pointers into the same running sum.
+      float cs_hi = 0.f;
+      for (int j = 0; j < R; ++j)
+        cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+      float cs_lo = 0.f;
+      for (int s = 0; s < ncand; ++s) {
+        const float v = cs_hi - cs_lo;
+        if (v > best_v) {
+          best_v = v;
+          best = s;
+        }
+        if (s + 1 < ncand) {
+          cs_lo += (s < S ? __ldg(pxg + (int64_t)s * T1 + t) : 0.f) + __ldg(pyg + (int64_t)s * T + t);
+          const int j = s + R;
+          cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+        }
+      }
     }
-    sbeg[t] = best;
   }
+  seg_v[seg][threadIdx.x] = best_v;
+  seg_s[seg][threadIdx.x] = best;
   __syncthreads();
+  if (seg == 0 && t < T) {
+    int out;
+    if (t < Tb - 1) {
+      out = 0;
+      float bv = kNegInf;
+#pragma unroll
+      for (int g = 0; g < kSegs; ++g) {
+        if (seg_v[g][threadIdx.x] > bv) {
+          bv = seg_v[g][threadIdx.x];
+          out = seg_s[g][threadIdx.x];
+        }
+      }
+    } else {
+      out = max(Sb - R + 1, 0);  // last real frame and padding frames
+    }
+    ranges[((int64_t)b * T + t) * R] = out;
+  }
+}
 
-  // phase 2: _adjust_pruning_lower_bound
+__global__ void __launch_bounds__(kThreads)
+prune_adjust_kernel(int T, int R, int64_t* __restrict__ ranges) {
+  extern __shared__ int sm[];  // T ints + blockDim scratch
+  int* sbeg = sm;
+  int* tmp = sm + T;
+  int64_t* out = ranges + (int64_t)blockIdx.x * T * R;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) sbeg[t] = (int)out[(int64_t)t * R];
+  __syncthreads();
+  // _adjust_pruning_lower_bound
   suffix_min_inplace(sbeg, tmp, T);
   for (int t = threadIdx.x; t < T; t += blockDim.x) sbeg[t] = -(sbeg[t] - (R - 1) * t);
   __syncthreads();
   suffix_min_inplace(sbeg, tmp, T);
   for (int t = threadIdx.x; t < T; t += blockDim.x) sbeg[t] = -(max(sbeg[t], 0) - (R - 1) * t);
   __syncthreads();
-
-  // phase 3
-  int64_t* out = ranges + (int64_t)b * T * R;
   for (int i = threadIdx.x; i < T * R; i += blockDim.x) out[i] = (int64_t)sbeg[i / R] + (i % R);
 }
 
@@ -168,12 +193,14 @@ int prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boun
   if (B == 0 || T == 0) return 0;
   size_t smem = (size_t)(T + kThreads) * sizeof(int);
   S2T_REQUIRE(smem <= 200 * 1024, "prune_ranges: T=%d too long for one CTA", T);
-  auto kern = variant == 0 ? prune_ranges_kernel<0> : prune_ranges_kernel<1>;
   if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(prune_adjust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  ProfScope prof("prune_ranges_kernel", stream);
-  kern<<<B, kThreads, smem, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
+  ProfScope prof("prune_ranges_kernel", stream, 2);
+  const dim3 grid((unsigned)((T + 31) / 32), (unsigned)B), block(32, kSegs);
+  if (variant == 0) prune_argmax_kernel<0><<<grid, block, 0, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
+  else prune_argmax_kernel<1><<<grid, block, 0, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
+  prune_adjust_kernel<<<B, kThreads, smem, stream>>>(T, R, ranges);
   return check_launch("prune_ranges_kernel");
 }
 
