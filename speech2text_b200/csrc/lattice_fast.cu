@@ -36,12 +36,18 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kMinLog2Diff = kMinLogDiff * kLog2e;  // k2's LogAdd cut-off, in the log2 domain
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // log2(2^x + 2^y): the recursions run in the log2 domain so that a log-add is MAX, SUB, EX2, ADD, LG2, ADD.
 // Both -inf gives NaN in d, the compare fails and -inf (the max) comes back, as in k2's LogAdd.
 __device__ __forceinline__ float log2_add(float x, float y) {
   const float mx = fmaxf(x, y), mn = fminf(x, y);
   const float d = mn - mx;
-  return (d >= kMinLog2Diff) ? mx + __log2f(1.f + exp2f(d)) : mx;
+  return (d >= kMinLog2Diff) ? mx + __log2f(1.f + ex2_fast(d)) : mx;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -112,23 +118,34 @@ __global__ void __launch_bounds__(kSimpleThreads, 1) simple_lattice_kernel(Simpl
       const int d = 32 * D + lane;
       float* rx = ringX + (slot * 32 + lane) * RS;
       float* ry = ringY + (slot * 32 + lane) * RS;
-#pragma unroll 8
-      for (int s = pw; s < ROWS; s += kSimpleProducerWarps) {
+      // all global loads of the block first (registers), then the shared-memory scatter: the compiler must
+      // not be made to order a load behind a shared store it cannot prove independent
+      constexpr int kRowsPerWarp = ROWS / kSimpleProducerWarps;
+      float xs[kRowsPerWarp], ys[kRowsPerWarp];
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int s = pw + i * kSimpleProducerWarps;
         const int t = d - s;
         float xv = kNegInf, yv = kNegInf;
         if (s <= Sb) {
           if (!is_beta) {
             // alpha step into (s, t): X = px(s-1, t), Y = py(s, t-1)
-            if (s >= 1 && t >= 0 && t <= Tb) xv = kLog2e * __ldg(px + (int64_t)(s - 1) * (a.T + 1) + t);
-            if (t >= 1 && t <= Tb) yv = kLog2e * __ldg(py + (int64_t)s * a.T + t - 1);
+            if (s >= 1 && t >= 0 && t <= Tb) xv = __ldg(px + (int64_t)(s - 1) * (a.T + 1) + t);
+            if (t >= 1 && t <= Tb) yv = __ldg(py + (int64_t)s * a.T + t - 1);
           } else {
             // beta step out of (s, t): X = px(s, t), Y = py(s, t)
-            if (s < Sb && t >= 0 && t <= Tb) xv = kLog2e * __ldg(px + (int64_t)s * (a.T + 1) + t);
-            if (t >= 0 && t < Tb) yv = kLog2e * __ldg(py + (int64_t)s * a.T + t);
+            if (s < Sb && t >= 0 && t <= Tb) xv = __ldg(px + (int64_t)s * (a.T + 1) + t);
+            if (t >= 0 && t < Tb) yv = __ldg(py + (int64_t)s * a.T + t);
           }
         }
-        rx[s] = xv;
-        ry[s] = yv;
+        xs[i] = xv;
+        ys[i] = yv;
+      }
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int s = pw + i * kSimpleProducerWarps;
+        rx[s] = kLog2e * xs[i];
+        ry[s] = kLog2e * ys[i];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[slot]);
@@ -296,8 +313,9 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
   float* pys = pxs + T * R;
   float* als = pys + T * R;   // alpha / beta relative to the offset of their diagonal
   float* bes = als + T * R;
-  int* sbs = reinterpret_cast<int*>(bes + T * R);  // sb[t], T + 2 entries (padding frames repeat the last)
-  double* offs = reinterpret_cast<double*>(sbs + ((T + 3) & ~1));
+  float* yis = bes + T * R;   // alpha's incoming blank move: py(t-1, r + sb[t] - sb[t-1]) or -inf
+  int* sbs = reinterpret_cast<int*>(yis + T * R);  // sb[t], T + 2 entries (padding frames repeat the last)
+  double* offs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sbs + T + 2) + 7) & ~(uintptr_t)7);
   const int n_off = ((a.S + T + R) >> kRebaseShift) + 2;
   double* aoff = offs;
   double* boff = offs + n_off;
@@ -326,6 +344,16 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
   }
   if (threadIdx.x == 0) s_logp2 = -INFINITY;
   __syncthreads();
+  for (int i = threadIdx.x; i < Tb * R; i += blockDim.x) {
+    const int t = i / R, r = i - t * R;
+    float v = kNegInf;
+    if (t > 0) {
+      const int r2 = r + sbs[t] - sbs[t - 1];
+      if (r2 < R) v = pys[(t - 1) * R + r2];
+    }
+    yis[i] = v;
+  }
+  __syncthreads();
 
   constexpr int kDone = 1 << 29;
   const int last_d = (Tb > 0) ? (Tb - 1 + sbs[Tb - 1] + R - 1) : -1;  // last diagonal that holds a band cell
@@ -334,11 +362,18 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
     // ---- alpha: lane r owns slot r and walks the frames upwards.  Per frame it pre-loads the two
     // incoming log-probs (already -inf when the move or the cell does not exist), so a step is two
     // shuffles and one log2-add.
+    // Everything a frame needs is fetched one frame ahead (independent shared-memory loads), so the only
+    // dependent chain of a step is shuffle -> log2-add.
     int t = 0, sb_cur = sbs[0];
     int f = (lane < R) ? sb_cur + lane : kDone;  // diagonal of this lane's next cell
     int delta = 0;
-    float xin = (lane > 0 && lane < R) ? pxs[lane - 1] : kNegInf;  // px(t, r-1)
-    float yin = kNegInf;                                            // py(t-1, r+delta): none for t = 0
+    const bool act = lane < R;
+    float xin = (lane > 0 && act) ? pxs[lane - 1] : kNegInf;  // px(t, r-1)
+    float yin = kNegInf;                                       // py(t-1, r+delta): none for t = 0
+    int tn = min(1, Tb - 1);
+    int sb_n = sbs[tn];
+    float xin_n = (lane > 0 && act) ? pxs[tn * R + lane - 1] : kNegInf;
+    float yin_n = act ? yis[tn * R + lane] : kNegInf;
     float* ap = als + lane;
     float last = kNegInf;
     double off = 0.0;
@@ -358,12 +393,15 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
           ap += R;
           ++t;
           if (t < Tb) {
-            const int sb_next = sbs[t];
-            delta = sb_next - sb_cur;
-            sb_cur = sb_next;
+            delta = sb_n - sb_cur;
+            sb_cur = sb_n;
             f = t + sb_cur + lane;
-            xin = (lane > 0) ? pxs[t * R + lane - 1] : kNegInf;
-            yin = (lane + delta < R) ? pys[(t - 1) * R + lane + delta] : kNegInf;
+            xin = xin_n;
+            yin = yin_n;
+            tn = min(t + 1, Tb - 1);
+            sb_n = sbs[tn];
+            xin_n = (lane > 0) ? pxs[tn * R + lane - 1] : kNegInf;
+            yin_n = yis[tn * R + lane];
           } else {
             f = kDone;
           }
@@ -381,10 +419,15 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
     int t = Tb - 1, sb_cur = sbs[Tb - 1];
     int f = (lane < R) ? t + sb_cur + lane : -kDone;
     int delta = 0;  // sb[t+1] - sb[t]
+    const bool act = lane < R;
     const int s0 = sb_cur + lane;
     float xout = (lane + 1 < R && s0 < Sb) ? pxs[t * R + lane] : kNegInf;  // px(t, r) -> slot r+1
-    float yout = (lane < R && s0 == Sb) ? pys[t * R + lane] : kNegInf;    // last frame: beta(s, T_b) = [s == S_b]
+    float yout = (act && s0 == Sb) ? pys[t * R + lane] : kNegInf;         // last frame: beta(s, T_b) = [s == S_b]
     bool term = true;  // the blank move of the last frame ends the lattice
+    int tp = max(t - 1, 0);  // frame fetched ahead
+    int sb_p = sbs[tp];
+    float xraw_p = act ? pxs[tp * R + lane] : kNegInf;
+    float yraw_p = act ? pys[tp * R + lane] : kNegInf;
     float* bp = bes + t * R + lane;
     float last = kNegInf;
     double off = 0.0;
@@ -404,13 +447,15 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
           --t;
           term = false;
           if (t >= 0) {
-            const int sb_prev = sbs[t];
-            delta = sb_cur - sb_prev;
-            sb_cur = sb_prev;
+            delta = sb_cur - sb_p;
+            sb_cur = sb_p;
             f = t + sb_cur + lane;
-            const int s = sb_cur + lane;
-            xout = (lane + 1 < R && s < Sb) ? pxs[t * R + lane] : kNegInf;
-            yout = (lane - delta >= 0) ? pys[t * R + lane] : kNegInf;
+            xout = (lane + 1 < R && sb_cur + lane < Sb) ? xraw_p : kNegInf;
+            yout = (lane - delta >= 0) ? yraw_p : kNegInf;
+            tp = max(t - 1, 0);
+            sb_p = sbs[tp];
+            xraw_p = pxs[tp * R + lane];
+            yraw_p = pys[tp * R + lane];
           } else {
             f = -kDone;
           }
@@ -542,7 +587,7 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
 
 static size_t band_smem_bytes(int S, int T, int R) {
   const size_t n_off = ((S + T + R) >> kRebaseShift) + 2;
-  return (size_t)4 * T * R * sizeof(float) + (size_t)((T + 3) & ~1) * sizeof(int) + 2 * n_off * sizeof(double) + 16;
+  return (size_t)5 * T * R * sizeof(float) + (size_t)(T + 2) * sizeof(int) + 8 + 2 * n_off * sizeof(double) + 16;
 }
 
 bool band_lattice_fast_ok(int S, int T, int R) { return R <= 32 && band_smem_bytes(S, T, R) <= 200 * 1024; }
