@@ -140,7 +140,7 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
                            void* alpha_ws, float* scores, float* px_grad, float* py_grad, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(B >= 0 && S >= 0 && T >= 0, "mutual_information: negative dimension");
-  if (simple_lattice_fast_ok(S) && !getenv("S2T_B200_GENERIC_DP")) {
+  if (simple_lattice_fast_ok(S, T) && !getenv("S2T_B200_GENERIC_DP")) {
     const bool grads = px_grad != nullptr && py_grad != nullptr;
     return launch_simple_lattice_fast(px, py, boundary, B, S, T, alpha_ws, scores, grads ? px_grad : nullptr,
                                       grads ? py_grad : nullptr, st);

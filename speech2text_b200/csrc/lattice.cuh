@@ -50,7 +50,7 @@ int launch_lattice_fwd_bwd(const LatticeView& v, float* logp, float* occ_px, flo
 int launch_lattice_fwd(const LatticeView& v, float* logp, cudaStream_t stream);
 
 // warp-synchronous fast paths (lattice_fast.cu)
-bool simple_lattice_fast_ok(int S);
+bool simple_lattice_fast_ok(int S, int T);
 size_t simple_lattice_fast_workspace_bytes(int B, int S, int T);
 // occ_px / occ_py may both be nullptr (scores only); otherwise every element of them is written
 int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,

@@ -30,7 +30,6 @@ using tc::mbar_init;
 using tc::mbar_wait;
 
 constexpr int kRebaseShift = 4;  // offsets are constant over 16 consecutive diagonals
-constexpr int kRingBlocks = 3;   // 32-diagonal blocks in the shared-memory ring
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -58,11 +57,12 @@ struct SimpleArgs {
   const float* py;  // (B, S+1, T)
   const int64_t* boundary;
   int B, S, T;
-  int rows_pad;       // 32 * RPL
+  int groups;         // row groups of 32 symbol positions (= recursion warps)
+  int rows_pad;       // 32 * groups
   int diag_rows;      // diagonals allocated per utterance (multiple of 32)
-  float* alpha_diag;  // (B, diag_rows, rows_pad), log2 domain, relative to aoff
+  float* alpha_diag;  // (B, diag_rows, rows_pad), log2 domain, relative to aoff of the row's group
   float* beta_diag;
-  double* aoff;  // (B, n_off), log2 domain
+  double* aoff;  // (B, groups, n_off), log2 domain
   double* boff;
   int n_off;
   double* logp_d;  // (B), natural log
@@ -70,18 +70,149 @@ struct SimpleArgs {
 };
 
 constexpr int kSimpleProducerWarps = 8;
-constexpr int kSimpleThreads = 32 * (1 + kSimpleProducerWarps);
 
-template <int RPL>
-__global__ void __launch_bounds__(kSimpleThreads, 1) simple_lattice_kernel(SimpleArgs a) {
-  constexpr int ROWS = 32 * RPL;
-  constexpr int RS = ROWS + 1;  // odd stride: the producers' diagonal scatter is conflict-free
-  constexpr int W = 32 * kRingBlocks;
+// Systolic layout: recursion warp g owns symbol positions 32 g .. 32 g + 31 (one per lane), so a diagonal
+// step is ONE shuffle + ONE log2-add per warp.  The value a group needs from its neighbour group (row
+// 32 g - 1 for alpha, 32 g + 32 for beta, one diagonal earlier) travels through a small shared-memory
+// array; group g runs one 32-diagonal block behind the neighbour it depends on (mbarrier per block), so
+// the G warps work on G different blocks at once, like a pipeline.  Every group keeps its own fp64 offset
+// (re-based every 16 diagonals by the group's maximum); boundary values are converted between the offsets
+// of the two groups.  Producer warps (8 / G per group) stream px / py from HBM into a per-group
+// diagonal-major ring.
+struct SimpleSmem {
+  float* ringX;   // [G][W * RS]
+  float* ringY;   // [G][W * RS]
+  float* bnd;     // [G + 1][bnd_stride]: boundary-row value per diagonal at index d + 1; array G stays -inf
+  double* offs;   // [G][n_off]
+  uint64_t* full;   // [G][kRing]
+  uint64_t* empty;  // [G][kRing]
+  uint64_t* bfull;  // [G][nblk_max]
+  int bnd_stride;
+};
+
+template <int G, bool kBeta>
+__device__ __forceinline__ void simple_recursion(const SimpleArgs& a, const SimpleSmem& sh, int b, int g, int lane,
+                                                 int Sb, int nd, int nblk) {
+  constexpr int ROWS = 32 * G;
+  constexpr int RS = 33;
+  constexpr int kRing = G <= 4 ? 3 : 2;
+  constexpr int W = 32 * kRing;
+  constexpr int kYOff = G * W * RS;  // ringY - ringX
+  const int nblk_max = a.diag_rows / 32;
+  const int dep = kBeta ? g + 1 : g - 1;  // the group whose boundary row feeds this one
+  const bool has_dep = dep >= 0 && dep < G;
+  const int edge_lane = kBeta ? 31 : 0;   // lane that takes its neighbour from the other group
+  const int send_lane = kBeta ? 0 : 31;   // lane whose value the next group needs
+  const float* gx = sh.ringX + g * W * RS + lane;
+  float* my_bnd = sh.bnd + g * sh.bnd_stride + 1;
+  const float* dep_bnd = sh.bnd + (has_dep ? dep : G) * sh.bnd_stride + 1;
+  double* my_offs = sh.offs + g * a.n_off;
+  const double* dep_offs = sh.offs + (has_dep ? dep : 0) * a.n_off;
+  double* g_offs = (kBeta ? a.boff : a.aoff) + ((int64_t)b * G + g) * a.n_off;
+  float* out0 = (kBeta ? a.beta_diag : a.alpha_diag) + (int64_t)b * a.diag_rows * ROWS + 32 * g + lane;
+  const int src_lane = kBeta ? ((lane + 1) & 31) : ((lane + 31) & 31);
+  const bool fin_mine = (Sb >> 5) == g;
+  const int fin_lane = Sb & 31;
+  constexpr int kStep = kBeta ? -1 : 1;
+  float v = kNegInf;
+  double off = 0.0;
+
+  for (int k = 0; k < nblk; ++k) {
+    const int D = kBeta ? (nblk - 1 - k) : k;
+    const int slot = k % kRing;
+    mbar_wait(&sh.full[g * kRing + slot], (k / kRing) & 1);
+    if (has_dep) mbar_wait(&sh.bfull[dep * nblk_max + k], 0);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {  // two 16-diagonal periods per block
+      const int dh = kBeta ? (32 * D + 31 - 16 * h) : (32 * D + 16 * h);  // first diagonal of the period
+      const int p = dh >> kRebaseShift;
+      if (lane == 0) {
+        my_offs[p] = off;
+        g_offs[p] = off;
+      }
+      // Boundary values of this period, one per lane (lane i serves step i), converted from the neighbour
+      // group's offset of the period they were computed in to this group's current offset.
+      float bvals = kNegInf;
+      if (has_dep && lane < 16) {
+        const int pp = kBeta ? p + 1 : p - 1;
+        const bool pp_ok = kBeta ? (16 * pp < 32 * nblk) : (pp >= 0);
+        const double o = (lane == 0) ? (pp_ok ? dep_offs[pp] : off) : dep_offs[p];
+        const int dp = kBeta ? dh - lane + 1 : dh + lane - 1;
+        bvals = dep_bnd[dp] + (float)(o - off);
+      }
+      const float* rx = gx + (slot * 32 + (dh & 31)) * RS;
+      float* out = out0 + (int64_t)dh * ROWS;
+      float* bp = my_bnd + dh;
+      const bool special = kBeta ? (nd <= dh && nd > dh - 16) : (dh == 0 || (nd >= dh && nd < dh + 16));
+      if (!special) {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) {
+          const float rot = __shfl_sync(0xffffffffu, v, src_lane);
+          const float bv = __shfl_sync(0xffffffffu, bvals, ii);
+          const float nb = (lane == edge_lane) ? bv : rot;
+          v = log2_add(nb + rx[kStep * ii * RS], v + rx[kStep * ii * RS + kYOff]);
+          out[kStep * ii * ROWS] = v;
+          if (lane == send_lane) bp[kStep * ii] = v;
+        }
+      } else {
+#pragma unroll 4
+        for (int ii = 0; ii < 16; ++ii) {
+          const int d = dh + kStep * ii;
+          const float rot = __shfl_sync(0xffffffffu, v, src_lane);
+          const float bv = __shfl_sync(0xffffffffu, bvals, ii);
+          const float nb = (lane == edge_lane) ? bv : rot;
+          float nv = log2_add(nb + rx[kStep * ii * RS], v + rx[kStep * ii * RS + kYOff]);
+          // the single source cell: alpha(0, 0) = 0 on diagonal 0, beta(S_b, T_b) = 0 on diagonal nd
+          if (!kBeta) {
+            if (d == 0 && g == 0 && lane == 0) nv = 0.f;
+          } else if (d == nd && fin_mine && lane == fin_lane) {
+            nv = 0.f;
+          }
+          v = nv;
+          out[kStep * ii * ROWS] = v;
+          if (lane == send_lane) bp[kStep * ii] = v;
+          if (!kBeta && d == nd && fin_mine) {  // log P(y|x) = alpha(S_b, T_b)
+            const float fin = __shfl_sync(0xffffffffu, v, fin_lane);
+            if (lane == 0) {
+              const double lp = ((double)fin + off) * (double)kLn2;
+              a.logp_d[b] = lp;
+              a.logp[b] = (float)lp;
+            }
+          }
+        }
+      }
+      const float m = warp_max(v);
+      if (m - m == 0.f) {
+        v -= m;
+        off += (double)m;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&sh.empty[g * kRing + slot]);
+      mbar_arrive(&sh.bfull[g * nblk_max + k]);
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(32 * (G + kSimpleProducerWarps), 1) simple_lattice_kernel(SimpleArgs a) {
+  constexpr int RS = 33;                 // odd row stride: the producers' diagonal scatter is conflict-free
+  constexpr int kRing = G <= 4 ? 3 : 2;  // 32-diagonal blocks per group ring
+  constexpr int W = 32 * kRing;
+  constexpr int kProdPerGroup = kSimpleProducerWarps / G;
+  constexpr int kRowsPerProd = 32 / kProdPerGroup;
   extern __shared__ float sm[];
-  float* ringX = sm;
-  float* ringY = sm + W * RS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ringY + W * RS);  // 2 * W * RS floats: 8-byte aligned
-  uint64_t* empty = full + kRingBlocks;
+  const int nblk_max = a.diag_rows / 32;
+  SimpleSmem sh;
+  sh.bnd_stride = a.diag_rows + 2;
+  sh.ringX = sm;
+  sh.ringY = sh.ringX + G * W * RS;
+  sh.bnd = sh.ringY + G * W * RS;
+  sh.offs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sh.bnd + (G + 1) * sh.bnd_stride) + 7) & ~(uintptr_t)7);
+  sh.full = reinterpret_cast<uint64_t*>(sh.offs + G * a.n_off);
+  sh.empty = sh.full + G * kRing;
+  sh.bfull = sh.empty + G * kRing;
 
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
@@ -98,33 +229,35 @@ __global__ void __launch_bounds__(kSimpleThreads, 1) simple_lattice_kernel(Simpl
   const float* px = a.px + (int64_t)b * a.S * (a.T + 1);
   const float* py = a.py + (int64_t)b * (a.S + 1) * a.T;
 
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kRingBlocks; ++i) {
-      mbar_init(&full[i], kSimpleProducerWarps);
-      mbar_init(&empty[i], 1);
-    }
-    tc::fence_mbar_init();
+  for (int i = threadIdx.x; i < G * kRing; i += blockDim.x) {
+    mbar_init(&sh.full[i], kProdPerGroup);
+    mbar_init(&sh.empty[i], 1);
   }
+  for (int i = threadIdx.x; i < G * nblk_max; i += blockDim.x) mbar_init(&sh.bfull[i], 1);
+  for (int i = threadIdx.x; i < (G + 1) * sh.bnd_stride; i += blockDim.x) sh.bnd[i] = kNegInf;
+  for (int i = threadIdx.x; i < G * a.n_off; i += blockDim.x) sh.offs[i] = 0.0;
+  tc::fence_mbar_init();
   __syncthreads();
 
-  if (warp > 0) {
-    // ---- producers: rows s = pw, pw + 8, ...; lane = diagonal inside the block.  They write EVERY
-    // row of the ring (-inf outside the lattice) so that the recursion needs no masks.
-    const int pw = warp - 1;
+  if (warp >= G) {
+    // ---- producers: lane = diagonal inside the block.  They write EVERY row of the ring (-inf outside
+    // the lattice) so that the recursion needs no masks.
+    const int pw = warp - G;
+    const int g = pw % G, sub = pw / G;
+    float* gx = sh.ringX + g * W * RS;
+    float* gy = sh.ringY + g * W * RS;
     for (int k = 0; k < nblk; ++k) {
       const int D = is_beta ? (nblk - 1 - k) : k;
-      const int slot = k % kRingBlocks;
-      mbar_wait(&empty[slot], ((k / kRingBlocks) & 1) ^ 1);
+      const int slot = k % kRing;
+      mbar_wait(&sh.empty[g * kRing + slot], ((k / kRing) & 1) ^ 1);
       const int d = 32 * D + lane;
-      float* rx = ringX + (slot * 32 + lane) * RS;
-      float* ry = ringY + (slot * 32 + lane) * RS;
-      // all global loads of the block first (registers), then the shared-memory scatter: the compiler must
-      // not be made to order a load behind a shared store it cannot prove independent
-      constexpr int kRowsPerWarp = ROWS / kSimpleProducerWarps;
-      float xs[kRowsPerWarp], ys[kRowsPerWarp];
+      float* rx = gx + (slot * 32 + lane) * RS;
+      float* ry = gy + (slot * 32 + lane) * RS;
+      // all global loads of the block first (registers), then the shared-memory scatter
+      float xs[kRowsPerProd], ys[kRowsPerProd];
 #pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) {
-        const int s = pw + i * kSimpleProducerWarps;
+      for (int i = 0; i < kRowsPerProd; ++i) {
+        const int s = 32 * g + sub + i * kProdPerGroup;
         const int t = d - s;
         float xv = kNegInf, yv = kNegInf;
         if (s <= Sb) {
@@ -142,94 +275,19 @@ __global__ void __launch_bounds__(kSimpleThreads, 1) simple_lattice_kernel(Simpl
         ys[i] = yv;
       }
 #pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) {
-        const int s = pw + i * kSimpleProducerWarps;
-        rx[s] = kLog2e * xs[i];
-        ry[s] = kLog2e * ys[i];
+      for (int i = 0; i < kRowsPerProd; ++i) {
+        const int r = sub + i * kProdPerGroup;
+        rx[r] = kLog2e * xs[i];
+        ry[r] = kLog2e * ys[i];
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[slot]);
+      if (lane == 0) mbar_arrive(&sh.full[g * kRing + slot]);
     }
     return;
   }
-
-  // ---- recursion warp: lane l holds rows l, l + 32, ... ----
-  float v[RPL];
-#pragma unroll
-  for (int j = 0; j < RPL; ++j) v[j] = kNegInf;
-  double off = 0.0;
-  float* out = (is_beta ? a.beta_diag : a.alpha_diag) + (int64_t)b * a.diag_rows * ROWS;
-  double* offs = (is_beta ? a.boff : a.aoff) + (int64_t)b * a.n_off;
-  const int src_lane = is_beta ? ((lane + 1) & 31) : ((lane + 31) & 31);
-  const int fin_j = Sb >> 5, fin_lane = Sb & 31;
-  float fin = kNegInf;
-  double fin_off = 0.0;
-
-  for (int k = 0; k < nblk; ++k) {
-    const int D = is_beta ? (nblk - 1 - k) : k;
-    const int slot = k % kRingBlocks;
-    mbar_wait(&full[slot], (k / kRingBlocks) & 1);
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {  // two 16-diagonal periods per block
-      const int dh = is_beta ? (32 * D + 31 - 16 * h) : (32 * D + 16 * h);  // first diagonal of the period
-      if (lane == 0) offs[dh >> kRebaseShift] = off;
-#pragma unroll 4
-      for (int ii = 0; ii < 16; ++ii) {
-        const int d = is_beta ? dh - ii : dh + ii;
-        const float* rx = ringX + (slot * 32 + (d & 31)) * RS;
-        const float* ry = ringY + (slot * 32 + (d & 31)) * RS;
-        float rot[RPL];
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) rot[j] = __shfl_sync(0xffffffffu, v[j], src_lane);
-        float nv[RPL];
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) {
-          float nb;  // neighbour row s-1 (alpha) / s+1 (beta) on the previous diagonal
-          if (!is_beta) nb = (lane > 0) ? rot[j] : (j > 0 ? rot[j - 1] : kNegInf);
-          else nb = (lane < 31) ? rot[j] : (j < RPL - 1 ? rot[j + 1] : kNegInf);
-          nv[j] = log2_add(nb + rx[j * 32 + lane], v[j] + ry[j * 32 + lane]);
-        }
-        // the single source cell: alpha(0, 0) = 0 on diagonal 0, beta(S_b, T_b) = 0 on diagonal nd
-        if (!is_beta) {
-          if (d == 0 && lane == 0) nv[0] = 0.f;
-        } else if (d == nd && lane == fin_lane) {
-#pragma unroll
-          for (int j = 0; j < RPL; ++j)
-            if (j == fin_j) nv[j] = 0.f;
-        }
-        float* o = out + (int64_t)d * ROWS + lane;
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) {
-          v[j] = nv[j];
-          o[j * 32] = nv[j];
-        }
-        if (!is_beta && d == nd) {  // log P(y|x) = alpha(S_b, T_b)
-          float mine = kNegInf;
-#pragma unroll
-          for (int j = 0; j < RPL; ++j)
-            if (j == fin_j) mine = v[j];
-          fin = __shfl_sync(0xffffffffu, mine, fin_lane);
-          fin_off = off;
-        }
-      }
-      float m = v[0];
-#pragma unroll
-      for (int j = 1; j < RPL; ++j) m = fmaxf(m, v[j]);
-      m = warp_max(m);
-      if (m - m == 0.f) {
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) v[j] -= m;
-        off += (double)m;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);
-  }
-  if (!is_beta && lane == 0) {
-    const double lp = ((double)fin + fin_off) * (double)kLn2;
-    a.logp_d[b] = lp;
-    a.logp[b] = (float)lp;
-  }
+  // ---- recursion warp g: lane l holds symbol position 32 g + l ----
+  if (is_beta) simple_recursion<G, true>(a, sh, b, warp, lane, Sb, nd, nblk);
+  else simple_recursion<G, false>(a, sh, b, warp, lane, Sb, nd, nblk);
 }
 
 // occupation probabilities in k2 layout from diagonal-major alpha / beta; writes EVERY element of
@@ -266,25 +324,25 @@ __global__ void __launch_bounds__(256) simple_occupation_kernel(SimpleArgs a, fl
   __syncthreads();
   const double lp = a.logp_d[b];
   const bool lp_ok = (lp - lp == 0.0);
-  const double* aoff = a.aoff + (int64_t)b * a.n_off;
-  const double* boff = a.boff + (int64_t)b * a.n_off;
+  const double* aoff = a.aoff + (int64_t)b * a.groups * a.n_off;  // [group][period]
+  const double* boff = a.boff + (int64_t)b * a.groups * a.n_off;
   for (int rs = ty; rs < 32; rs += 8) {
     const int s = s0 + rs, t = t0 + tx;
     if (s > a.S || t > a.T) continue;
     float ox = 0.f, oy = 0.f;
     if (tile_live && lp_ok && s <= Sb && t <= Tb) {
       const int d = s + t;
-      // alpha / beta and their offsets are in the log2 domain
-      const float cst = (float)(aoff[d >> kRebaseShift] + boff[(d + 1 <= nd ? d + 1 : nd) >> kRebaseShift] -
-                                lp * (double)kLog2e);
+      // alpha / beta and the offsets of their row groups are in the log2 domain
+      const int pb = (d + 1 <= nd ? d + 1 : nd) >> kRebaseShift;
+      const double ca = aoff[(s >> 5) * a.n_off + (d >> kRebaseShift)] - lp * (double)kLog2e;
       const float av = sA[rs + tx][rs];
       if (t < Tb) {
         const float yv = kLog2e * __ldg(a.py + ((int64_t)b * (a.S + 1) + s) * a.T + t);
-        oy = exp2f(av + yv + sB[rs + tx][rs] + cst);
+        oy = exp2f(av + yv + sB[rs + tx][rs] + (float)(ca + boff[(s >> 5) * a.n_off + pb]));
       }
       if (s < Sb) {
         const float xv = kLog2e * __ldg(a.px + ((int64_t)b * a.S + s) * (a.T + 1) + t);
-        ox = exp2f(av + xv + sB[rs + tx][rs + 1] + cst);
+        ox = exp2f(av + xv + sB[rs + tx][rs + 1] + (float)(ca + boff[((s + 1) >> 5) * a.n_off + pb]));
       }
     }
     if (s < a.S) occ_px[((int64_t)b * a.S + s) * (a.T + 1) + t] = ox;
@@ -531,7 +589,6 @@ static int simple_rpl(int S) {
   return 0;
 }
 
-bool simple_lattice_fast_ok(int S) { return simple_rpl(S) > 0; }
 
 size_t simple_lattice_fast_workspace_bytes(int B, int S, int T) {
   const int rpl = simple_rpl(S);
@@ -539,7 +596,20 @@ size_t simple_lattice_fast_workspace_bytes(int B, int S, int T) {
   const size_t diag_rows = (size_t)((S + T) / 32 + 1) * 32;
   const size_t diag = (size_t)B * diag_rows * 32 * rpl * sizeof(float);
   const size_t n_off = diag_rows / 16 + 2;
-  return 2 * diag + (2 * (size_t)B * n_off + B) * sizeof(double) + 64;
+  return 2 * diag + (2 * (size_t)B * rpl * n_off + B) * sizeof(double) + 64;
+}
+
+static size_t simple_smem_bytes(int G, int diag_rows, int n_off) {
+  const int ring = G <= 4 ? 3 : 2;
+  return (size_t)2 * G * 32 * ring * 33 * sizeof(float) + (size_t)(G + 1) * (diag_rows + 2) * sizeof(float) + 8 +
+         (size_t)G * n_off * sizeof(double) + (size_t)(2 * G * ring + G * (diag_rows / 32)) * 8 + 16;
+}
+
+bool simple_lattice_fast_ok(int S, int T) {
+  const int g = simple_rpl(S);
+  if (!g) return false;
+  const int diag_rows = ((S + T) / 32 + 1) * 32;
+  return simple_smem_bytes(g, diag_rows, diag_rows / 16 + 2) <= 227 * 1024;
 }
 
 int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,
@@ -550,6 +620,7 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
   SimpleArgs a{};
   a.px = px; a.py = py; a.boundary = boundary;
   a.B = B; a.S = S; a.T = T;
+  a.groups = rpl;
   a.rows_pad = 32 * rpl;
   a.diag_rows = ((S + T) / 32 + 1) * 32;
   const size_t diag = (size_t)B * a.diag_rows * a.rows_pad;
@@ -557,22 +628,23 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
   a.alpha_diag = (float*)ws;
   a.beta_diag = a.alpha_diag + diag;
   a.aoff = (double*)(a.beta_diag + diag + ((2 * diag) & 1));
-  a.boff = a.aoff + (size_t)B * a.n_off;
-  a.logp_d = a.boff + (size_t)B * a.n_off;
+  a.boff = a.aoff + (size_t)B * rpl * a.n_off;
+  a.logp_d = a.boff + (size_t)B * rpl * a.n_off;
   a.logp = logp;
-  const size_t smem = (size_t)2 * 32 * kRingBlocks * (a.rows_pad + 1) * sizeof(float) + 8 + 2 * kRingBlocks * 8 + 16;
+  const size_t smem = simple_smem_bytes(rpl, a.diag_rows, a.n_off);
+  S2T_REQUIRE(smem <= 227 * 1024, "simple_lattice_fast: S+T = %d needs %zu B of shared memory", S + T, smem);
   {
     ProfScope prof("simple_lattice_kernel", stream);
     dim3 grid(B, occ_px ? 2 : 1);
-    auto launch = [&](auto kern) {
+    auto launch = [&](auto kern, int threads) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<grid, kSimpleThreads, smem, stream>>>(a);
+      kern<<<grid, threads, smem, stream>>>(a);
     };
     switch (rpl) {
-      case 1: launch(simple_lattice_kernel<1>); break;
-      case 2: launch(simple_lattice_kernel<2>); break;
-      case 4: launch(simple_lattice_kernel<4>); break;
-      default: launch(simple_lattice_kernel<8>); break;
+      case 1: launch(simple_lattice_kernel<1>, 32 * (1 + kSimpleProducerWarps)); break;
+      case 2: launch(simple_lattice_kernel<2>, 32 * (2 + kSimpleProducerWarps)); break;
+      case 4: launch(simple_lattice_kernel<4>, 32 * (4 + kSimpleProducerWarps)); break;
+      default: launch(simple_lattice_kernel<8>, 32 * (8 + kSimpleProducerWarps)); break;
     }
   }
   if (int rc = check_launch("simple_lattice_kernel")) return rc;
