@@ -364,6 +364,17 @@ struct BandArgs {
   float* occ_py;
 };
 
+// One step record per band cell and direction, built in parallel before the recursions start:
+//   x, y   incoming (alpha) / outgoing (beta) log2-probabilities, -inf where the move or the cell does not exist
+//   f      diagonal t + sb[t] + r of the cell (kBandDone / -kBandDone after the last cell of the lane)
+//   w      bits 0..7: lane distance delta to the blank-move neighbour; bit 8: the blank-move term is a
+//          constant 0 (alpha(0,0) = 0 and the lattice exit of the last frame) instead of a neighbour value
+struct __align__(16) BandStep {
+  float x, y;
+  int f, w;
+};
+constexpr int kBandDone = 1 << 29;
+
 __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
   extern __shared__ float sm[];
   const int T = a.T, R = a.R;
@@ -371,8 +382,9 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
   float* pys = pxs + T * R;
   float* als = pys + T * R;   // alpha / beta relative to the offset of their diagonal
   float* bes = als + T * R;
-  float* yis = bes + T * R;   // alpha's incoming blank move: py(t-1, r + sb[t] - sb[t-1]) or -inf
-  int* sbs = reinterpret_cast<int*>(yis + T * R);  // sb[t], T + 2 entries (padding frames repeat the last)
+  BandStep* arec = reinterpret_cast<BandStep*>((reinterpret_cast<uintptr_t>(bes + T * R) + 15) & ~(uintptr_t)15);  // (T + 1) * R
+  BandStep* brec = arec + (T + 1) * R + 3 * R;  // frame t at brec + t * R; frames -3..-1 are padding / terminator
+  int* sbs = reinterpret_cast<int*>(brec + (T + 1) * R);  // sb[t], T + 2 entries (padding frames repeat the last)
   double* offs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sbs + T + 2) + 7) & ~(uintptr_t)7);
   const int n_off = ((a.S + T + R) >> kRebaseShift) + 2;
   double* aoff = offs;
@@ -402,36 +414,57 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
   }
   if (threadIdx.x == 0) s_logp2 = -INFINITY;
   __syncthreads();
-  for (int i = threadIdx.x; i < Tb * R; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (Tb + 1) * R; i += blockDim.x) {
     const int t = i / R, r = i - t * R;
-    float v = kNegInf;
-    if (t > 0) {
-      const int r2 = r + sbs[t] - sbs[t - 1];
-      if (r2 < R) v = pys[(t - 1) * R + r2];
+    BandStep ra{kNegInf, kNegInf, kBandDone, 0}, rb{kNegInf, kNegInf, -kBandDone, 0};
+    if (t < Tb) {
+      const int sb = sbs[t], s = sb + r;
+      const bool in = s <= Sb;
+      // alpha into (t, r): symbol move from (t, r-1), blank move from (t-1, r + sb[t] - sb[t-1])
+      const int da = t > 0 ? sb - sbs[t - 1] : 0;
+      ra.f = t + sb + r;
+      ra.w = da & 255;
+      if (in) {
+        if (r > 0) ra.x = pxs[i - 1];
+        if (t > 0 && r + da < R) ra.y = pys[(t - 1) * R + r + da];
+        if (t == 0 && s == 0) {  // alpha(0, 0) = 0
+          ra.x = kNegInf;
+          ra.y = 0.f;
+          ra.w |= 256;
+        }
+      }
+      // beta out of (t, r): symbol move to (t, r+1), blank move to (t+1, r - (sb[t+1] - sb[t])) or out of the lattice
+      const int db = t + 1 < Tb ? sbs[t + 1] - sb : 0;
+      rb.f = t + sb + r;
+      rb.w = db & 255;
+      if (in) {
+        if (r + 1 < R && s < Sb) rb.x = pxs[i];
+        if (t + 1 < Tb) {
+          if (r - db >= 0) rb.y = pys[i];
+        } else {
+          rb.w |= 256;  // last frame: beta(s, T_b) = [s == S_b]
+          if (s == Sb) rb.y = pys[i];
+        }
+      }
     }
-    yis[i] = v;
+    arec[i] = ra;
+    brec[i] = rb;
   }
+  for (int i = threadIdx.x; i < 3 * R; i += blockDim.x) brec[i - 3 * R] = BandStep{kNegInf, kNegInf, -kBandDone, 0};
   __syncthreads();
 
-  constexpr int kDone = 1 << 29;
   const int last_d = (Tb > 0) ? (Tb - 1 + sbs[Tb - 1] + R - 1) : -1;  // last diagonal that holds a band cell
   const int n_periods = (last_d >> kRebaseShift) + 1;
   if (warp == 0 && Tb > 0) {
-    // ---- alpha: lane r owns slot r and walks the frames upwards.  Per frame it pre-loads the two
-    // incoming log-probs (already -inf when the move or the cell does not exist), so a step is two
-    // shuffles and one log2-add.
-    // Everything a frame needs is fetched one frame ahead (independent shared-memory loads), so the only
-    // dependent chain of a step is shuffle -> log2-add.
-    int t = 0, sb_cur = sbs[0];
-    int f = (lane < R) ? sb_cur + lane : kDone;  // diagonal of this lane's next cell
-    int delta = 0;
+    // ---- alpha: lane r owns slot r and walks the frames upwards; the record of the next cell is fetched
+    // one cell ahead, so the dependent chain of a step is shuffle -> log2-add.
     const bool act = lane < R;
-    float xin = (lane > 0 && act) ? pxs[lane - 1] : kNegInf;  // px(t, r-1)
-    float yin = kNegInf;                                       // py(t-1, r+delta): none for t = 0
-    int tn = min(1, Tb - 1);
-    int sb_n = sbs[tn];
-    float xin_n = (lane > 0 && act) ? pxs[tn * R + lane - 1] : kNegInf;
-    float yin_n = act ? yis[tn * R + lane] : kNegInf;
+    const BandStep* rp = arec + (act ? lane : 0);
+    BandStep cur = *rp;
+    if (!act) cur.f = kBandDone;
+    rp += R;
+    BandStep nxt = *rp;  // frame 1 (or the terminator written for t = T_b)
+    rp += R;             // rp always points one record past nxt (reads beyond the terminator are never used)
     float* ap = als + lane;
     float last = kNegInf;
     double off = 0.0;
@@ -441,29 +474,15 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
       for (int ii = 0; ii < 16; ++ii) {
         const int d = 16 * p + ii;
         const float up_src = __shfl_up_sync(0xffffffffu, last, 1);
-        const float left_src = __shfl_sync(0xffffffffu, last, (lane + delta) & 31);
-        float val = kNegInf;
-        if (f == d) {
-          val = log2_add(up_src + xin, left_src + yin);
-          if (d == 0) val = (lane == 0) ? 0.f : kNegInf;  // alpha(0, 0) = 0
-          if (sb_cur + lane > Sb) val = kNegInf;
-          *ap = val;
-          ap += R;
-          ++t;
-          if (t < Tb) {
-            delta = sb_n - sb_cur;
-            sb_cur = sb_n;
-            f = t + sb_cur + lane;
-            xin = xin_n;
-            yin = yin_n;
-            tn = min(t + 1, Tb - 1);
-            sb_n = sbs[tn];
-            xin_n = (lane > 0) ? pxs[tn * R + lane - 1] : kNegInf;
-            yin_n = yis[tn * R + lane];
-          } else {
-            f = kDone;
-          }
-        }
+        const float left_src = __shfl_sync(0xffffffffu, last, (lane + cur.w) & 31);
+        const BandStep cand = *rp;  // branch-free: fetched every step, consumed only when the lane advances
+        const bool on = cur.f == d;
+        const float val = on ? log2_add(up_src + cur.x, ((cur.w & 256) ? 0.f : left_src) + cur.y) : kNegInf;
+        if (on) *ap = val;
+        ap += on ? R : 0;
+        rp += on ? R : 0;
+        cur.x = on ? nxt.x : cur.x; cur.y = on ? nxt.y : cur.y; cur.f = on ? nxt.f : cur.f; cur.w = on ? nxt.w : cur.w;
+        nxt.x = on ? cand.x : nxt.x; nxt.y = on ? cand.y : nxt.y; nxt.f = on ? cand.f : nxt.f; nxt.w = on ? cand.w : nxt.w;
         last = val;
       }
       const float m = warp_max(last);  // cells older than this diagonal already sit in als[]
@@ -474,19 +493,14 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
     }
   } else if (warp == 1 && Tb > 0) {
     // ---- beta: lane r owns slot r and walks the frames downwards ----
-    int t = Tb - 1, sb_cur = sbs[Tb - 1];
-    int f = (lane < R) ? t + sb_cur + lane : -kDone;
-    int delta = 0;  // sb[t+1] - sb[t]
     const bool act = lane < R;
-    const int s0 = sb_cur + lane;
-    float xout = (lane + 1 < R && s0 < Sb) ? pxs[t * R + lane] : kNegInf;  // px(t, r) -> slot r+1
-    float yout = (act && s0 == Sb) ? pys[t * R + lane] : kNegInf;         // last frame: beta(s, T_b) = [s == S_b]
-    bool term = true;  // the blank move of the last frame ends the lattice
-    int tp = max(t - 1, 0);  // frame fetched ahead
-    int sb_p = sbs[tp];
-    float xraw_p = act ? pxs[tp * R + lane] : kNegInf;
-    float yraw_p = act ? pys[tp * R + lane] : kNegInf;
-    float* bp = bes + t * R + lane;
+    const BandStep* rp = brec + (Tb - 1) * R + (act ? lane : 0);
+    BandStep cur = *rp;
+    if (!act) cur.f = -kBandDone;
+    rp -= R;
+    BandStep nxt = *rp;  // frame T_b - 2, or the terminator stored as frame -1
+    rp -= R;             // rp always points one record past nxt
+    float* bp = bes + (Tb - 1) * R + lane;
     float last = kNegInf;
     double off = 0.0;
     for (int p = n_periods - 1; p >= 0; --p) {
@@ -495,29 +509,15 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
       for (int ii = 15; ii >= 0; --ii) {
         const int d = 16 * p + ii;
         const float down_src = __shfl_down_sync(0xffffffffu, last, 1);
-        const float right_src = __shfl_sync(0xffffffffu, last, (lane - delta) & 31);
-        float val = kNegInf;
-        if (f == d) {
-          val = log2_add(down_src + xout, term ? yout : right_src + yout);
-          if (sb_cur + lane > Sb) val = kNegInf;
-          *bp = val;
-          bp -= R;
-          --t;
-          term = false;
-          if (t >= 0) {
-            delta = sb_cur - sb_p;
-            sb_cur = sb_p;
-            f = t + sb_cur + lane;
-            xout = (lane + 1 < R && sb_cur + lane < Sb) ? xraw_p : kNegInf;
-            yout = (lane - delta >= 0) ? yraw_p : kNegInf;
-            tp = max(t - 1, 0);
-            sb_p = sbs[tp];
-            xraw_p = pxs[tp * R + lane];
-            yraw_p = pys[tp * R + lane];
-          } else {
-            f = -kDone;
-          }
-        }
+        const float right_src = __shfl_sync(0xffffffffu, last, (lane - cur.w) & 31);
+        const BandStep cand = *rp;
+        const bool on = cur.f == d;
+        const float val = on ? log2_add(down_src + cur.x, ((cur.w & 256) ? 0.f : right_src) + cur.y) : kNegInf;
+        if (on) *bp = val;
+        bp -= on ? R : 0;
+        rp -= on ? R : 0;
+        cur.x = on ? nxt.x : cur.x; cur.y = on ? nxt.y : cur.y; cur.f = on ? nxt.f : cur.f; cur.w = on ? nxt.w : cur.w;
+        nxt.x = on ? cand.x : nxt.x; nxt.y = on ? cand.y : nxt.y; nxt.f = on ? cand.f : nxt.f; nxt.w = on ? cand.w : nxt.w;
         last = val;
       }
       const float m = warp_max(last);
@@ -659,7 +659,8 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
 
 static size_t band_smem_bytes(int S, int T, int R) {
   const size_t n_off = ((S + T + R) >> kRebaseShift) + 2;
-  return (size_t)5 * T * R * sizeof(float) + (size_t)(T + 2) * sizeof(int) + 8 + 2 * n_off * sizeof(double) + 16;
+  return (size_t)4 * T * R * sizeof(float) + 16 + (size_t)(2 * (T + 1) + 3) * R * 16 + (size_t)(T + 2) * sizeof(int) + 8 +
+         2 * n_off * sizeof(double) + 16;
 }
 
 bool band_lattice_fast_ok(int S, int T, int R) { return R <= 32 && band_smem_bytes(S, T, R) <= 200 * 1024; }
