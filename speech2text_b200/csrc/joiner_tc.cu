@@ -654,16 +654,18 @@ TcWs tc_carve(void* ws, const TcDims& d) {
   return w;
 }
 
-int pack_weights(const JoinerProblem& p, const TcDims& d, const TcWs& w, bool for_backward, cudaStream_t st) {
-  // W1 (I, V): rows i, K v          W2 (V, I): rows v, K i
-  if (int rc = pack_operand(p.W1, p.V, 1, p.I, p.V, d.Ip / 128, d.kbV, w.W1p, st)) return rc;
-  if (int rc = pack_operand(p.W2, p.I, 1, p.V, p.I, d.Vp / 128, d.kbI, w.W2p, st)) return rc;
-  if (for_backward) {
-    // W2^T: rows i, K v -> element (i, v) = W2[v * I + i]     W1^T: rows v, K i -> W1[i * V + v]
-    if (int rc = pack_operand(p.W2, 1, p.I, p.I, p.V, d.Ip / 128, d.kbV, w.W2Tp, st)) return rc;
-    if (int rc = pack_operand(p.W1, 1, p.V, p.V, p.I, d.Vp / 128, d.kbI, w.W1Tp, st)) return rc;
-  }
-  return 0;
+// All four operand images of the two weight matrices in one launch (the backward call reuses them: the
+// workspace travels unchanged from forward to backward).
+int pack_weights(const JoinerProblem& p, const TcDims& d, const TcWs& w, cudaStream_t st) {
+  const PackJob jobs[4] = {
+      // W1 (I, V): rows i, K v          W2 (V, I): rows v, K i
+      {p.W1, p.V, 1, p.I, p.V, d.Ip / 128, d.kbV, w.W1p, 0},
+      {p.W2, p.I, 1, p.V, p.I, d.Vp / 128, d.kbI, w.W2p, 0},
+      // W2^T: rows i, K v -> element (i, v) = W2[v * I + i]     W1^T: rows v, K i -> W1[i * V + v]
+      {p.W2, 1, p.I, p.I, p.V, d.Ip / 128, d.kbV, w.W2Tp, 0},
+      {p.W1, 1, p.V, p.V, p.I, d.Vp / 128, d.kbI, w.W1Tp, 0},
+  };
+  return pack_jobs(jobs, 4, st);
 }
 
 }  // namespace
@@ -696,7 +698,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
       cudaMemcpyToSymbol(g_exp_noload, &exp_flag, sizeof(int));
     }
   }
-  if (int rc = pack_weights(p, d, w, false, stream)) return rc;
+  if (int rc = pack_weights(p, d, w, stream)) return rc;
   // hidden: M x Ip, K = V
   {
     JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act};
@@ -730,7 +732,6 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
   if (M == 0) return 0;
   TcDims d = tc_dims(M, p.V, p.I);
   TcWs w = tc_carve(workspace, d);
-  if (int rc = pack_weights(p, d, w, true, stream)) return rc;
   const int sms = 148;
   for (int64_t row0 = 0; row0 < (int64_t)d.Mt * 128; row0 += d.chunk) {
     const int64_t rows_pad = ((int64_t)d.Mt * 128 - row0 < d.chunk) ? ((int64_t)d.Mt * 128 - row0) : d.chunk;

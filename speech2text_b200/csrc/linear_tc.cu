@@ -8,7 +8,7 @@
 //   forward   y = x W^T + b          K-major tf32: A = x copied on the fly, B = fp32 pack(W) (rows n, cols k)
 //   backward  dx = dy W              K-major:  A = pack(dy) (rows m, cols n), B = pack(W^T) (rows k, cols n)
 //             dW = dy^T x            MN-major: the SAME pack(dy) and pack(x), contraction over the rows m
-//             db = column sums of dy
+//             db = column sums of dy (a by-product of packing dy)
 // pack(x) is written once in the forward call and reused by the backward call (workspace).
 #include "tc_gemm.cuh"
 
@@ -16,29 +16,6 @@ namespace s2t {
 namespace {
 
 using namespace tc;
-
-// out[n] += sum over a 64-row slab of x[r, n]; block = 32 columns x 8 row lanes
-__global__ void linear_col_sum_kernel(const float* __restrict__ x, int64_t rows, int ld, int N, float* __restrict__ out) {
-  __shared__ float part[8][33];
-  const int n = blockIdx.x * 32 + threadIdx.x;
-  const int64_t r0 = (int64_t)blockIdx.y * 64;
-  float acc = 0.f;
-  if (n < N) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t r = r0 + threadIdx.y + 8 * i;
-      if (r < rows) acc += x[r * ld + n];
-    }
-  }
-  part[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
-    atomicAdd(out + n, s);
-  }
-}
 
 struct LinDims {
   int Mt, Np, Kp;       // row tiles of x; N, K padded to multiples of 256
@@ -64,7 +41,7 @@ using namespace s2t;
 
 extern "C" {
 
-// workspace = [pack(x) | pack(W) | pack(dy) | pack(W^T)]; only pack(x) must survive until backward
+// workspace = [pack(x) | pack(W) | pack(dy) | pack(W^T)]; pack(x) and pack(W^T) must survive until backward
 size_t s2t_linear_workspace_bytes(int64_t M, int N, int K) {
   LinDims d = lin_dims(M, N, K);
   return d.px + d.pw + d.pdy + d.pwt + 1024;
@@ -79,8 +56,16 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
   uint8_t* pw = px + d.px;
   if (int rc = tc::pack_operand(x, K, 1, (int)M, K, d.Mt, d.Kp / 64, px, st)) return rc;  // for dW in backward
   uint8_t* pw_small = pw + d.pw / 2;
-  if (int rc = tc::pack_operand_f32(W, K, N, K, d.Np / 128, d.Kp / 32, 0, pw, st)) return rc;
-  if (int rc = tc::pack_operand_f32(W, K, N, K, d.Np / 128, d.Kp / 32, 1, pw_small, st)) return rc;
+  uint8_t* pwt = pw + d.pw + d.pdy;
+  {
+    const tc::PackJob jobs[3] = {
+        {W, K, 1, N, K, d.Np / 128, d.Kp / 32, pw, 1},
+        {W, K, 1, N, K, d.Np / 128, d.Kp / 32, pw_small, 2},
+        // W^T for dx in backward: rows k, cols n -> element (k, n) = W[n * K + k]
+        {W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, 0},
+    };
+    if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
+  }
   tc::RowCopyProducerF32 a{x, K, M, K, true};
   tc::StoreRowMajorEpi ep{y, N, (int)M, N, false, b};
   tc::MnDebug extra;
@@ -98,9 +83,9 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
   uint8_t* px = (uint8_t*)ws;
   uint8_t* pdy = px + d.px + d.pw;
   uint8_t* pwt = pdy + d.pdy;
-  if (int rc = tc::pack_operand(dy, N, 1, (int)M, N, d.Mt, d.Np / 64, pdy, st)) return rc;
-  // W^T: rows k, cols n -> element (k, n) = W[n * K + k]
-  if (int rc = tc::pack_operand(W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, st)) return rc;
+  // pack(dy) also yields db = column sums of dy
+  cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
+  if (int rc = tc::pack_rows_colsum(dy, N, (int)M, N, d.Mt, d.Np / 64, pdy, db, st)) return rc;
   if (dx) {
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dx, K, (int)M, K, false, nullptr};
@@ -110,7 +95,6 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
   }
   {
     cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), st);
-    cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
     const int k_steps = d.Mt * 2;
     const int tiles = (d.Np / 128) * (d.Kp / 256);
     int splits = 148 / (tiles > 0 ? tiles : 1);
@@ -120,9 +104,6 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
     if (int rc = tc::launch_gemm_stream<256, 4, true, 0>(a, px, d.Mt, d.Np / 128, d.Kp / 256, k_steps, splits, ep, st,
                                                       "tc_linear_dW_gemm"))
       return rc;
-    ProfScope prof("linear_col_sum_kernel", st);
-    dim3 grid((N + 31) / 32, (unsigned)((M + 63) / 64));
-    linear_col_sum_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, M, N, N, db);
   }
   return check_launch("linear_bwd");
 }

@@ -499,6 +499,27 @@ int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int r
 int pack_operand_f32(const float* src, int64_t row_stride, int rows, int K, int row_blocks, int k_blocks,
                      int part, uint8_t* dst, cudaStream_t stream);
 
+// Row-major fp32 (rows, K) -> bf16 packed operand; col_sum (may be null) += the column sums of src.
+int pack_rows_colsum(const float* src, int64_t ld, int rows, int K, int row_blocks, int k_blocks, uint8_t* dst,
+                     float* col_sum, cudaStream_t stream);
+
+// Several pack jobs in one launch (weights of a module).  kind 0: bf16 (k_blocks of 64); kind 1 / 2: the
+// big / residual tf32 part of an fp32 operand (k_blocks of 32).  src(r, k) = src[r * row_stride + k * col_stride].
+struct PackJob {
+  const float* src;
+  int64_t row_stride, col_stride;
+  int rows, K, row_blocks, k_blocks;
+  uint8_t* dst;
+  int kind;
+};
+struct PackJobs {
+  static constexpr int kMax = 6;
+  PackJob job[kMax];
+  int64_t first[kMax + 1];  // first chunk (thread) of every job
+  int n;
+};
+int pack_jobs(const PackJob* list, int n, cudaStream_t stream);
+
 // Batched packing with an optional fused exp: element (batch, r, k) = f(src[batch*batch_stride + r*row_stride + k])
 // with f(x) = exp(x - row_sub[batch*rows + r]) when row_sub != nullptr.  Every batch is padded to rows_pad
 // (a multiple of 128) rows, so the batches form one tall packed operand and never share a block.

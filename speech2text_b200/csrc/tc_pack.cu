@@ -60,6 +60,97 @@ __global__ void pack_operand_f32_kernel(const float* __restrict__ src, int64_t r
   *reinterpret_cast<float4*>(blk + block_chunk_offset((int)(r % 128), (k0 % 32) / 4)) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// Row-major fp32 (rows, K) -> bf16 packed operand, one 128 x 64 block per CTA, plus the column sums of the
+// source (the bias gradient of a linear layer falls out of packing dy).  16 threads cover the 64 columns
+// of a row (one float4 each), 16 rows per pass; the block's column sums meet in shared memory and leave
+// as 64 atomics.
+__global__ void __launch_bounds__(256) pack_rows_colsum_kernel(const float* __restrict__ src, int64_t ld, int rows, int K,
+                                                               int row_blocks, uint8_t* __restrict__ dst,
+                                                               float* __restrict__ col_sum) {
+  __shared__ float part[16][65];
+  const int rb = blockIdx.x, kb = blockIdx.y;
+  const int c = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int k = kb * 64 + c * 4;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  uint8_t* blk = dst + packed_block_index(rb, kb, row_blocks) * kBlockBytes;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const int rr = pass * 16 + rl;
+    const int64_t r = (int64_t)rb * 128 + rr;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+      const float* p = src + r * ld + k;
+      if (vec && k + 4 <= K) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (k + e < K) ? __ldg(p + e) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += v[e];
+    *reinterpret_cast<uint2*>(blk + block_chunk_offset(rr, c >> 1) + (c & 1) * 8) =
+        make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  }
+  if (col_sum == nullptr) return;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) part[rl][c * 4 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += part[i][threadIdx.x];
+    const int col = kb * 64 + threadIdx.x;
+    if (col < K && t != 0.f) atomicAdd(col_sum + col, t);
+  }
+}
+
+// several small matrices (the weights of one module) in ONE launch: one thread per 16-byte chunk of any job
+__global__ void pack_jobs_kernel(PackJobs jobs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= jobs.first[jobs.n]) return;
+  int j = 0;
+#pragma unroll
+  for (int q = 1; q < PackJobs::kMax; ++q)
+    if (q < jobs.n && i >= jobs.first[q]) j = q;
+  const PackJob& job = jobs.job[j];
+  const int64_t li = i - jobs.first[j];
+  const int64_t rows_pad = (int64_t)job.row_blocks * 128, chunks = (int64_t)job.k_blocks * 8;
+  int64_t r, ck;
+  if (job.col_stride == 1) {  // consecutive threads along K
+    ck = li % chunks;
+    r = li / chunks;
+  } else {  // transposed source: consecutive threads along the rows
+    r = li % rows_pad;
+    ck = li / rows_pad;
+  }
+  const int per = job.kind == 0 ? 8 : 4;  // elements per 16-byte chunk
+  const int k0 = (int)ck * per;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    v[e] = (e < per && r < job.rows && k < job.K) ? __ldg(job.src + r * job.row_stride + (int64_t)k * job.col_stride) : 0.f;
+  }
+  const int rb = (int)(r >> 7), kb = (int)(ck >> 3);
+  uint8_t* out = job.dst + packed_block_index(rb, kb, job.row_blocks) * kBlockBytes + block_chunk_offset((int)(r & 127), (int)(ck & 7));
+  if (job.kind == 0) {
+    *reinterpret_cast<uint4*>(out) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  } else {
+    float4 o;
+    float* po = &o.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float big = round_tf32(v[e]);
+      po[e] = job.kind == 1 ? big : round_tf32(v[e] - big);
+    }
+    *reinterpret_cast<float4*>(out) = o;
+  }
+}
+
 // batched, optionally exponentiated packing: one thread per 16-byte chunk
 template <bool kF32>
 __global__ void pack_batched_kernel(PackSpec p, uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_small) {
@@ -115,6 +206,35 @@ int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream) {
   ProfScope prof("pack_operand_kernel", stream);
   pack_batched_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, dst, nullptr);
   return check_launch("pack_batched_kernel<bf16>");
+}
+
+int pack_rows_colsum(const float* src, int64_t ld, int rows, int K, int row_blocks, int k_blocks, uint8_t* dst,
+                     float* col_sum, cudaStream_t stream) {
+  S2T_REQUIRE(row_blocks * 128 >= rows && k_blocks * 64 >= K, "pack_rows_colsum: padded dims too small");
+  if (row_blocks == 0 || k_blocks == 0) return 0;
+  S2T_REQUIRE(k_blocks <= 65535, "pack_rows_colsum: K too large");
+  ProfScope prof("pack_operand_kernel", stream);
+  pack_rows_colsum_kernel<<<dim3((unsigned)row_blocks, (unsigned)k_blocks), 256, 0, stream>>>(src, ld, rows, K, row_blocks, dst,
+                                                                                            col_sum);
+  return check_launch("pack_rows_colsum_kernel");
+}
+
+int pack_jobs(const PackJob* list, int n, cudaStream_t stream) {
+  S2T_REQUIRE(n >= 1 && n <= PackJobs::kMax, "pack_jobs: %d jobs", n);
+  PackJobs jobs;
+  jobs.n = n;
+  jobs.first[0] = 0;
+  for (int j = 0; j < n; ++j) {
+    const PackJob& q = list[j];
+    S2T_REQUIRE(q.row_blocks * 128 >= q.rows && q.k_blocks * (q.kind == 0 ? 64 : 32) >= q.K, "pack_jobs: padded dims too small");
+    jobs.job[j] = q;
+    jobs.first[j + 1] = jobs.first[j] + (int64_t)q.row_blocks * 128 * q.k_blocks * 8;
+  }
+  const int64_t total = jobs.first[n];
+  if (total == 0) return 0;
+  ProfScope prof("pack_operand_kernel", stream);
+  pack_jobs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(jobs);
+  return check_launch("pack_jobs_kernel");
 }
 
 int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream) {
