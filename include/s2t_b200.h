@@ -90,7 +90,8 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
                         float* scores, float* px_grad, float* py_grad, void* workspace, void* stream);
 
 /* Backward of the above: grad_scores (B) = d loss / d scores[b].
- * workspace: s2t_simple_workspace_bytes(mode,...) bytes (may be a fresh buffer).
+ * workspace: THE buffer the forward call wrote (in S2T_MODE_BF16_TC it holds the bf16 exp(am - max) /
+ * exp(lm - max) operands that the forward pass produced as a by-product), unchanged.
  * d_am (B,T,V), d_lm (B,S+1,V) are overwritten. */
 int s2t_simple_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols, const float* am_max,
                         const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,

@@ -54,7 +54,8 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
   LinDims d = lin_dims(M, N, K);
   uint8_t* px = (uint8_t*)ws;
   uint8_t* pw = px + d.px;
-  if (int rc = tc::pack_operand(x, K, 1, (int)M, K, d.Mt, d.Kp / 64, px, st)) return rc;  // for dW in backward
+  // pack(x) for dW in backward is a by-product of the forward producer; only K padding it never visits needs zeros
+  if (((K + 31) / 32) * 32 < d.Kp) cudaMemsetAsync(px, 0, d.px, st);
   uint8_t* pw_small = pw + d.pw / 2;
   uint8_t* pwt = pw + d.pw + d.pdy;
   {
@@ -66,7 +67,7 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
     };
     if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
   }
-  tc::RowCopyProducerF32 a{x, K, M, K, true};
+  tc::RowCopyProducerF32 a{x, K, M, K, true, px, d.Mt};
   tc::StoreRowMajorEpi ep{y, N, (int)M, N, false, b};
   tc::MnDebug extra;
   extra.b_small = pw_small;

@@ -50,10 +50,15 @@ struct ExpRowProducerF32 {
   const float* x;   // (B, rows, V)
   const float* mx;  // (B, rows)
   int rows, V;
+  // by-product for the backward contractions: exp(x - max) as a bf16 packed operand, batch b / row tile m at
+  // row block b * tiles_per_batch + m, 64 columns per block (written while column tile 0 streams by)
+  uint8_t* bf16_pack;
+  int tiles_per_batch, pack_row_blocks;
   __device__ void run(const ProdCtx& pc) const {
     const int warp = pc.t >> 5, lane = pc.t & 31;
     const int c = lane & 7, rbase = warp * 4 + (lane >> 3);
     const bool vec = ((V & 3) == 0);
+    const bool emit = bf16_pack != nullptr && pc.n_tile == 0;
     const float* rowp[4];
     float sub[4];
     bool live[4];
@@ -101,6 +106,13 @@ struct ExpRowProducerF32 {
         }
         *reinterpret_cast<float4*>(dst + i * 32 * 128) = big;
         *reinterpret_cast<float4*>(dst + kBlockBytes + i * 32 * 128) = small;
+        if (emit) {
+          const int ks = pc.ks0 + it;
+          uint8_t* blk = bf16_pack +
+                         packed_block_index(pc.batch * tiles_per_batch + pc.m_tile, ks >> 1, pack_row_blocks) * kBlockBytes;
+          *reinterpret_cast<uint2*>(blk + block_chunk_offset(rbase + 32 * i, (ks & 1) * 4 + (c >> 1)) + (c & 1) * 8) =
+              make_uint2(pack_bf16x2(pb[0] + ps[0], pb[1] + ps[1]), pack_bf16x2(pb[2] + ps[2], pb[3] + ps[3]));
+        }
       }
       pc.arrive_full(it);
 #pragma unroll
@@ -292,9 +304,15 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
                                                                                       blank, lm_info);
   }
   if (int rc = check_launch("row_max_kernel")) return rc;
+  // exp(am - max) and exp(lm - max) as bf16 operands of the backward contractions are by-products of this pass
+  uint8_t* am_p = lm_small + d.lm_f32;
+  uint8_t* lm_p = am_p + d.am_bf16;
+  if (d.kb32 * 32 < d.Vp) {  // vocabulary padding the fp32 k-steps never visit
+    cudaMemsetAsync(am_p, 0, d.am_bf16 + d.lm_bf16, stream);
+  }
   PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
-  if (int rc = pack_f32_split(ps, lm_big, lm_small, stream)) return rc;
-  ExpRowProducerF32 a{am, am_max, T, V};
+  if (int rc = pack_f32_split(ps, lm_big, lm_small, stream, lm_p, d.kb64)) return rc;
+  ExpRowProducerF32 a{am, am_max, T, V, am_p, d.Tpad / 128, B * (d.Tpad / 128)};
   SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm};
   MnDebug extra;
   extra.b_small = lm_small;
@@ -327,10 +345,7 @@ int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, con
                                                                                 coef, B, S, T, d.Spad, d.Tpad, Wst, Wts);
   }
   if (int rc = check_launch("simple_w_packed_kernel")) return rc;
-  PackSpec pa{am, (int64_t)T * V, V, B, T, d.Tpad, V, d.kb64, am_max};
-  if (int rc = pack_bf16(pa, am_p, stream)) return rc;
-  PackSpec pl{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb64, lm_max};
-  if (int rc = pack_bf16(pl, lm_p, stream)) return rc;
+  // am_p / lm_p = bf16 exp(am - max), exp(lm - max): written by simple_logprobs_tc into the SAME workspace
   // d_am: rows t, cols c, contraction over s (rows of Wst and of lm_p)
   {
     BulkA a{Wst, B * (d.Spad / 128)};

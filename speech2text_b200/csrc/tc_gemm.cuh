@@ -129,7 +129,7 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
 
 // What an on-the-fly A producer sees for one tile: kProdThreads threads fill stage(it) for it in [0, n_it).
 struct ProdCtx {
-  int m_tile, batch, ks0, n_it;
+  int m_tile, n_tile, batch, ks0, n_it;
   int t;  // producer thread index, 0 .. kProdThreads-1
   uint8_t* smem;
   int stage_bytes, stages;
@@ -357,6 +357,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         if (c.n_it <= 0) continue;
         ProdCtx pc;
         pc.m_tile = c.m_tile;
+        pc.n_tile = c.n_tile;
         pc.batch = c.batch;
         pc.ks0 = c.ks0;
         pc.n_it = c.n_it;
@@ -531,7 +532,10 @@ struct PackSpec {
   const float* row_sub;  // optional per-row value subtracted before exp
 };
 int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream);
-int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream);
+// dst_bf16 (optional): the same values once more as a bf16 operand of bf16_k_blocks 64-column blocks; columns the
+// fp32 operand does not cover must already be zero there
+int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream,
+                   uint8_t* dst_bf16 = nullptr, int bf16_k_blocks = 0);
 
 // On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage.
 // Eight lanes cover the 128 bytes one row contributes to a k-step, so a warp-wide load instruction reads
@@ -543,9 +547,14 @@ struct RowCopyProducerF32 {
   int64_t M;
   int K;
   bool split;  // also write the residual block right after the big block (3xTF32)
+  // optional by-product: the bf16 packed image of x (row_blocks = m tiles, 64-column blocks), written while
+  // the first column tile of every row tile streams by -- the weight-gradient contraction reads it later
+  uint8_t* bf16_pack = nullptr;
+  int pack_row_blocks = 0;
   __device__ void run(const ProdCtx& pc) const {
     const int warp = pc.t >> 5, lane = pc.t & 31;
     const int c = lane & 7, rbase = warp * 4 + (lane >> 3);
+    const bool emit = bf16_pack != nullptr && pc.n_tile == 0;
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const float* rowp[4];
     bool live[4];
@@ -587,6 +596,12 @@ struct RowCopyProducerF32 {
           q.x = round_tf32(x4.x - v.x); q.y = round_tf32(x4.y - v.y); q.z = round_tf32(x4.z - v.z);
           q.w = round_tf32(x4.w - v.w);
           *reinterpret_cast<float4*>(dst + kBlockBytes + i * 32 * 128) = q;
+        }
+        if (emit) {
+          const int ks = pc.ks0 + it;
+          uint8_t* blk = bf16_pack + packed_block_index(pc.m_tile, ks >> 1, pack_row_blocks) * kBlockBytes;
+          *reinterpret_cast<uint2*>(blk + block_chunk_offset(rbase + 32 * i, (ks & 1) * 4 + (c >> 1)) + (c & 1) * 8) =
+              make_uint2(pack_bf16x2(x4.x, x4.y), pack_bf16x2(x4.z, x4.w));
         }
       }
       pc.arrive_full(it);

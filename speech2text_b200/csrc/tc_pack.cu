@@ -153,7 +153,8 @@ __global__ void pack_jobs_kernel(PackJobs jobs) {
 
 // batched, optionally exponentiated packing: one thread per 16-byte chunk
 template <bool kF32>
-__global__ void pack_batched_kernel(PackSpec p, uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_small) {
+__global__ void pack_batched_kernel(PackSpec p, uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_small,
+                                    uint8_t* __restrict__ dst_bf16, int bf16_k_blocks) {
   constexpr int kPer = kF32 ? 4 : 8;  // elements per chunk
   const int chunks_per_row = p.k_blocks * 8;
   const int64_t total = (int64_t)p.batches * p.rows_pad * chunks_per_row;
@@ -187,6 +188,12 @@ __global__ void pack_batched_kernel(PackSpec p, uint8_t* __restrict__ dst, uint8
     small.z = round_tf32(v[2] - big.z); small.w = round_tf32(v[3] - big.w);
     *reinterpret_cast<float4*>(dst + off) = big;
     *reinterpret_cast<float4*>(dst_small + off) = small;
+    if (dst_bf16) {  // the same values as a bf16 operand (64 per block row): this thread owns half a 16-byte chunk
+      const size_t o16 = packed_block_index((int)rb, ck >> 4, (int)(((int64_t)p.batches * p.rows_pad) >> 7)) * kBlockBytes +
+                         block_chunk_offset((int)(rp & 127), (ck >> 1) & 7) + (ck & 1) * 8;
+      if ((ck >> 4) < bf16_k_blocks)
+        *reinterpret_cast<uint2*>(dst_bf16 + o16) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
   } else {
     uint4 out;
     out.x = pack_bf16x2(v[0], v[1]);
@@ -204,7 +211,7 @@ int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream) {
   const int64_t total = (int64_t)p.batches * p.rows_pad * p.k_blocks * 8;
   if (total == 0) return 0;
   ProfScope prof("pack_operand_kernel", stream);
-  pack_batched_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, dst, nullptr);
+  pack_batched_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, dst, nullptr, nullptr, 0);
   return check_launch("pack_batched_kernel<bf16>");
 }
 
@@ -237,12 +244,14 @@ int pack_jobs(const PackJob* list, int n, cudaStream_t stream) {
   return check_launch("pack_jobs_kernel");
 }
 
-int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream) {
+int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream, uint8_t* dst_bf16,
+                   int bf16_k_blocks) {
   S2T_REQUIRE(p.rows_pad % 128 == 0 && p.rows_pad >= p.rows && p.k_blocks * 32 >= p.K, "pack_f32_split: bad padding");
   const int64_t total = (int64_t)p.batches * p.rows_pad * p.k_blocks * 8;
   if (total == 0) return 0;
   ProfScope prof("pack_operand_kernel", stream);
-  pack_batched_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, dst_big, dst_small);
+  pack_batched_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, dst_big, dst_small, dst_bf16,
+                                                                                 bf16_k_blocks);
   return check_launch("pack_batched_kernel<f32>");
 }
 

@@ -91,7 +91,9 @@ class _SimpleLoss(torch.autograd.Function):
                                         float(lm_only_scale), float(am_only_scale), ptr(am_max), ptr(lm_max),
                                         ptr(px), ptr(py), ptr(nrm), ptr(alpha), ptr(scores), ptr(px_grad),
                                         ptr(py_grad), ptr(ws), stream()))
-        ctx.save_for_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad)
+        # the workspace travels to backward: in tensor-core mode it holds the bf16 exp(am - max) / exp(lm - max)
+        # operands the forward pass produced on the side
+        ctx.save_for_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws)
         ctx.blank = blank
         ctx.mode = mode
         ctx.mark_non_differentiable(px_grad, py_grad)
@@ -99,12 +101,10 @@ class _SimpleLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_scores, _gx, _gy):
-        am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad = ctx.saved_tensors
+        am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws = ctx.saved_tensors
         B, T, V = am.shape
         S = lm.shape[1] - 1
         grad_scores = _f32c(grad_scores)
-        ws = torch.empty((lib().s2t_simple_workspace_bytes(ctx.mode, B, T, S, V),), dtype=torch.uint8,
-                         device=am.device)
         d_am = torch.empty_like(am)
         d_lm = torch.empty_like(lm)
         check(lib().s2t_simple_loss_bwd(ctx.mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
