@@ -131,6 +131,10 @@ struct JointRowProducer {
   const int* lm_row;
   int64_t M;
   int V, act;
+  // optional by-product: the stage image is also the packed operand block (row tile, k-step) of
+  // J = act(am + lm[ranges]); kept for the weight-gradient contraction of the backward pass
+  uint8_t* Jp;
+  int j_row_blocks;
   __device__ void run(const ProdCtx& pc) const {
     const int warp = pc.t >> 5, lane = pc.t & 31;
     const int c = lane & 15, rbase = warp * 2 + (lane >> 4);
@@ -151,11 +155,22 @@ struct JointRowProducer {
       joint_load_quad(q1, am, lm, ar[1], lr[1], v, V, vec);
       pc.wait_empty(it);
       uint8_t* dst = pc.stage(it) + off;
+      uint8_t* jdst = (Jp != nullptr && pc.n_tile == 0)
+                          ? Jp + packed_block_index(pc.m_tile, pc.ks0 + it, j_row_blocks) * kBlockBytes + off
+                          : nullptr;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(dst + j * 16 * 128) = joint_act4(q0.a[j], q0.l[j], act);
+      for (int j = 0; j < 4; ++j) {
+        const uint2 o = joint_act4(q0.a[j], q0.l[j], act);
+        *reinterpret_cast<uint2*>(dst + j * 16 * 128) = o;
+        if (jdst) *reinterpret_cast<uint2*>(jdst + j * 16 * 128) = o;
+      }
       if (it + 1 < pc.n_it) joint_load_quad(q0, am, lm, ar[0], lr[0], v + 64, V, vec);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(dst + (4 + j) * 16 * 128) = joint_act4(q1.a[j], q1.l[j], act);
+      for (int j = 0; j < 4; ++j) {
+        const uint2 o = joint_act4(q1.a[j], q1.l[j], act);
+        *reinterpret_cast<uint2*>(dst + (4 + j) * 16 * 128) = o;
+        if (jdst) *reinterpret_cast<uint2*>(jdst + (4 + j) * 16 * 128) = o;
+      }
       pc.arrive_full(it);
     }
   }
@@ -592,6 +607,7 @@ struct TcDims {
   int n_tiles_v;   // Vp / kBN
   int n_parts_v;   // LSE partials per row
   int64_t chunk;   // rows per backward chunk (multiple of 128)
+  bool keep_joint; // keep act(am + lm[ranges]) as a bf16 operand from forward to backward
 };
 
 TcDims tc_dims(int64_t M, int V, int I) {
@@ -610,6 +626,7 @@ TcDims tc_dims(int64_t M, int V, int I) {
   if (rows < 128) rows = 128;
   int64_t all = (int64_t)d.Mt * 128;
   d.chunk = rows < all ? rows : all;
+  d.keep_joint = (size_t)d.Mt * (d.Vp / 64) * kBlockBytes <= ((size_t)4 << 30) && !getenv("S2T_B200_NO_KEEP_JOINT");
   return d;
 }
 
@@ -622,6 +639,7 @@ struct TcWs {
   float* blank_logit;
   uint8_t *W1p, *W2p, *W2Tp, *W1Tp;
   uint8_t* Hp;
+  uint8_t* Jp;  // packed act(am + lm[ranges]) (rows m, cols v) or nullptr when it would not fit the budget
   uint8_t *Gp, *DHp;
   __nv_bfloat16* dh;  // (chunk rows, Vp) d loss / d (joint pre-activation) before act'
   size_t bytes;
@@ -647,6 +665,7 @@ TcWs tc_carve(void* ws, const TcDims& d) {
   w.W2p = (uint8_t*)take((size_t)(d.Vp / 128) * d.kbI * kBlockBytes);
   w.W1Tp = (uint8_t*)take((size_t)(d.Vp / 128) * d.kbI * kBlockBytes);
   w.Hp = (uint8_t*)take((size_t)d.Mt * d.kbI * kBlockBytes);
+  w.Jp = d.keep_joint ? (uint8_t*)take((size_t)d.Mt * (d.Vp / 64) * kBlockBytes) : nullptr;
   w.Gp = (uint8_t*)take((size_t)ct * (d.Vp / 64) * kBlockBytes);
   w.DHp = (uint8_t*)take((size_t)ct * d.kbI * kBlockBytes);
   w.dh = (__nv_bfloat16*)take((size_t)d.chunk * d.Vp * sizeof(__nv_bfloat16));
@@ -701,7 +720,8 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   if (int rc = pack_weights(p, d, w, stream)) return rc;
   // hidden: M x Ip, K = V
   {
-    JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act};
+    if (w.Jp && d.kbV < d.Vp / 64) cudaMemsetAsync(w.Jp, 0, (size_t)d.Mt * (d.Vp / 64) * kBlockBytes, stream);
+    JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act, w.Jp, d.Mt};
     HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt};
     if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
                                             "tc_joiner_hidden_gemm"))
@@ -763,13 +783,21 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
                                                     kbM, splits, ep, stream, "tc_joiner_dW2_gemm"))
         return rc;
     }
-    // dW1[i, v] += sum_m dhidden[m, i] act(.)[m, v]: accumulator rows v (A built on the fly), cols i
+    // dW1[i, v] += sum_m dhidden[m, i] act(.)[m, v]: accumulator rows v, cols i; A = the J kept by the forward
+    // pass (bulk copies) or, when it was too large to keep, rebuilt on the fly
     {
-      JointMnProducer a{p.am, p.lm, w.am_row, w.lm_row, row0, M, p.V, p.act};
       StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
-      if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, stream,
-                                                    "tc_joiner_dW1_gemm"))
-        return rc;
+      if (w.Jp) {
+        BulkA a{w.Jp + (size_t)tile0 * kBlockBytes, d.Mt};
+        if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, stream,
+                                                                "tc_joiner_dW1_gemm"))
+          return rc;
+      } else {
+        JointMnProducer a{p.am, p.lm, w.am_row, w.lm_row, row0, M, p.V, p.act};
+        if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, stream,
+                                                                "tc_joiner_dW1_gemm"))
+          return rc;
+      }
     }
     // dh = dhidden W1: rows m, N = Vp, K = Ip  ->  bf16 rows; then the two segmented reductions
     {
