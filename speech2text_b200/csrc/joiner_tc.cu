@@ -448,135 +448,122 @@ struct StoreRowsBf16Epi {
   }
 };
 
-// d_am[b,t,v] += sum_r dh[(b,t,r), v] * act'(am[b,t,v] + lm[b, s(t,r), v])      (A.5: sum over the band slots)
-// one thread per (frame, 4 consecutive v): every read and the write are coalesced 8/16-byte accesses, no atomics.
-__global__ void djoint_am_kernel(const __nv_bfloat16* __restrict__ dh, int ld, const float* __restrict__ am,
-                                 const float* __restrict__ lm, const int* __restrict__ lm_row, int64_t row0,
-                                 int64_t rows, int64_t M, int R, int V, int act, float* __restrict__ d_am) {
-  const int64_t f0 = row0 / R, f1 = (min(row0 + rows, M) + R - 1) / R;  // frames touched by this chunk
-  const int vq = (V + 3) / 4;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (f1 - f0) * vq) return;
-  const int v = (int)(i % vq) * 4;
-  const int64_t bt = f0 + i / vq;
-  const bool vec = ((V & 3) == 0);
-  float a[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (vec) {
-    const float4 t4 = __ldg(reinterpret_cast<const float4*>(am + bt * V + v));
-    a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(am + bt * V + v + j) : 0.f;
-  }
-#pragma unroll 4
-  for (int r = 0; r < R; ++r) {
-    const int64_t m = bt * R + r;
-    if (m < row0 || m >= row0 + rows || m >= M) continue;
-    const uint2 raw = *reinterpret_cast<const uint2*>(dh + (m - row0) * ld + v);  // ld and v are multiples of 4
-    const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&raw);
-    const float* lrow = lm + (int64_t)lm_row[m] * V + v;
-    float l[4];
-    if (vec) {
-      const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
-      l[0] = t4.x; l[1] = t4.y; l[2] = t4.z; l[3] = t4.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) l[j] = (v + j < V) ? __ldg(lrow + j) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] += __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[j], act);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (v + j < V) d_am[bt * V + v + j] += acc[j];
-}
+// dJ = dh * act'(am + lm[ranges]) reduced both ways in one pass over dh:
+//   d_am[b,t,v] += sum_r dJ[(b,t,r), v]                       (A.5: sum over the band slots of a frame)
+//   d_lm[b,s,v] += sum over the (t, r) with sb[t] + r = s of dJ[(b,t,r), v]
+// One CTA owns kFrames consecutive frames of one utterance; every thread owns four vocabulary columns, so
+// the frame sums live in registers and the per-symbol-position sums in thread-private columns of a
+// shared-memory tile (no barrier, no shared atomics).  The band of kFrames frames spans only a few symbol
+// positions; the tile is flushed to d_lm with 16-byte reductions, since neighbouring frame chunks meet in
+// the same rows.  Wider spans (unpruned lattices) are processed in windows of kMaxSpan positions.
+constexpr int kDjFrames = 16;
+constexpr int kDjMaxSpan = 16;
+constexpr int kDjCols = 512;  // columns per pass: 128 threads x 4
 
-// d_lm[b,s,v] += sum over the frames t whose band holds s of dh[(b,t,s-sb[t]), v] * act'(am[b,t,v] + lm[b,s,v]).
-// sb[] is non-decreasing, so those frames are one interval; the block finds its two ends with one parallel
-// sweep over sb[], stages the dh row of every frame of the interval in shared memory, and then two half-blocks
-// take alternate frames, four columns per thread, with independent coalesced 8/16-byte loads only.
 template <bool kVec>
-__global__ void __launch_bounds__(256) djoint_lm_kernel(const __nv_bfloat16* __restrict__ dh, int ld,
-                                                        const float* __restrict__ am, const float* __restrict__ lm,
-                                                        const int64_t* __restrict__ ranges,
-                                                        const int64_t* __restrict__ boundary, int64_t row0,
-                                                        int64_t rows, int64_t M, int T, int S, int R, int V, int act,
-                                                        float* __restrict__ d_lm) {
-  __shared__ int t_range[2];
-  __shared__ int dh_row[64];
-  __shared__ float red[128][4];
-  const int64_t bs = blockIdx.x;  // (b, s)
-  const int b = (int)(bs / (S + 1)), s = (int)(bs % (S + 1));
+__global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16* __restrict__ dh, int ld,
+                                                            const float* __restrict__ am, const float* __restrict__ lm,
+                                                            const int64_t* __restrict__ ranges,
+                                                            const int64_t* __restrict__ boundary, int64_t row0,
+                                                            int64_t rows, int64_t M, int T, int S, int R, int V, int act,
+                                                            float* __restrict__ d_am, float* __restrict__ d_lm) {
+  extern __shared__ float acc[];  // [kDjMaxSpan][kDjCols]
+  __shared__ int sbs[kDjFrames];
+  const int b = blockIdx.y, t0 = blockIdx.x * kDjFrames;
   const int Tb = boundary ? min((int)boundary[4 * b + 3], T) : T;  // padding frames carry no gradient
-  if (threadIdx.x == 0) {
-    t_range[0] = (ranges || s >= R) ? Tb : 0;  // unpruned: slot r is symbol position r in every frame
-    t_range[1] = Tb;
-  }
+  const int t1 = min(t0 + kDjFrames, Tb);
+  if (t0 >= t1) return;
+  const int64_t bt0 = (int64_t)b * T;
+  const int64_t row_end = min(row0 + rows, M);
+  if ((bt0 + t1) * R <= row0 || (bt0 + t0) * R >= row_end) return;  // no row of this chunk
+  if (threadIdx.x < t1 - t0) sbs[threadIdx.x] = ranges ? (int)ranges[(bt0 + t0 + threadIdx.x) * R] : 0;
   __syncthreads();
-  if (ranges) {
-    const int64_t* rg = ranges + (int64_t)b * T * R;  // sb[t] = rg[t * R]
-    for (int t = threadIdx.x; t < Tb; t += 256) {
-      const int sb = (int)rg[(int64_t)t * R];
-      const int prev = t ? (int)rg[(int64_t)(t - 1) * R] : INT_MIN / 2;
-      if (sb + R - 1 >= s && prev + R - 1 < s) t_range[0] = t;  // first frame whose band reaches s
-      if (sb > s && prev <= s) t_range[1] = t;                  // first frame whose band has left s
-    }
-    __syncthreads();
-  }
-  const int t_lo = t_range[0], t_hi = t_range[1];
-  const int half = threadIdx.x >> 7, q = threadIdx.x & 127;
-  for (int vb = 0; vb < V; vb += 512) {
-    const int v = vb + q * 4;
-    float l[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (kVec) {
-      const float4 t4 = (v < V) ? __ldg(reinterpret_cast<const float4*>(lm + bs * V + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      l[0] = t4.x; l[1] = t4.y; l[2] = t4.z; l[3] = t4.w;
-    } else {
+  const int s_lo = min(max(sbs[0], 0), S), s_hi = min(max(sbs[t1 - t0 - 1] + R - 1, 0), S);
+  float* mine = acc + threadIdx.x * 4;
+  for (int w_lo = s_lo; w_lo <= s_hi; w_lo += kDjMaxSpan) {
+    const int w_hi = min(w_lo + kDjMaxSpan - 1, s_hi);
+    for (int vb = 0; vb < V; vb += kDjCols) {
+      const int v = vb + threadIdx.x * 4;
+      if (v >= V) continue;
+      for (int i = 0; i <= w_hi - w_lo; ++i) *reinterpret_cast<float4*>(mine + i * kDjCols) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = t0; t < t1; ++t) {
+        const int sbt = sbs[t - t0];
+        const int r_lo = max(0, w_lo - sbt), r_hi = min(R - 1, w_hi - sbt);
+        const int64_t m_base = (bt0 + t) * R;
+        if (r_lo > r_hi || m_base + r_hi < row0 || m_base + r_lo >= row_end) continue;
+        float a[4], dsum[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* arow = am + (bt0 + t) * V + v;
+        if (kVec) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow));
+          a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) l[j] = (v + j < V) ? __ldg(lm + bs * V + v + j) : 0.f;
-    }
-    for (int tb = t_lo; tb < t_hi; tb += 64) {
-      const int nt = min(64, t_hi - tb);
-      __syncthreads();
-      if (threadIdx.x < nt) {
-        const int t = tb + threadIdx.x;
-        const int r = ranges ? s - (int)ranges[((int64_t)b * T + t) * R] : s;
-        const int64_t m = ((int64_t)b * T + t) * R + r;
-        dh_row[threadIdx.x] = (r >= 0 && r < R && m >= row0 && m < row0 + rows && m < M) ? (int)(m - row0) : -1;
-      }
-      __syncthreads();
-      if (v < V) {
-#pragma unroll 4
-        for (int k = half; k < nt; k += 2) {
-          const int row = dh_row[k];
-          const float wgt = row >= 0 ? 1.f : 0.f;
-          const uint2 raw = *reinterpret_cast<const uint2*>(dh + (int64_t)max(row, 0) * ld + v);  // ld, v multiples of 4
-          const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&raw);
-          const float* arow = am + ((int64_t)b * T + tb + k) * V + v;
-          float a[4];
-          if (kVec) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow));
-            a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
-          } else {
+          for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(arow + j) : 0.f;
+        }
+        for (int rb = r_lo; rb <= r_hi; rb += 8) {
+          // all loads of up to eight band slots first, so their latencies overlap
+          uint2 graw[8];
+          float l[8][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(arow + j) : 0.f;
+          for (int q = 0; q < 8; ++q) {
+            const int r = rb + q;
+            const int64_t m = m_base + r;
+            const bool ok = r <= r_hi && m >= row0 && m < row_end;
+            graw[q] = make_uint2(0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) l[q][j] = 0.f;
+            if (ok) {
+              graw[q] = *reinterpret_cast<const uint2*>(dh + (m - row0) * ld + v);  // ld and v are multiples of 4
+              const float* lrow = lm + ((int64_t)b * (S + 1) + sbt + r) * V + v;
+              if (kVec) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
+                l[q][0] = t4.x; l[q][1] = t4.y; l[q][2] = t4.z; l[q][3] = t4.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) l[q][j] = (v + j < V) ? __ldg(lrow + j) : 0.f;
+              }
+            }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] += wgt * __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[j], act);
+          for (int q = 0; q < 8; ++q) {
+            const int r = rb + q;
+            if (r > r_hi) break;
+            const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&graw[q]);
+            float4* cell = reinterpret_cast<float4*>(mine + (sbt + r - w_lo) * kDjCols);  // sbt + r in [w_lo, w_hi]
+            float4 c = *cell;
+            float x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[j] = __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[q][j], act);  // rows outside the chunk: dh read as 0
+              dsum[j] += x[j];
+            }
+            c.x += x[0]; c.y += x[1]; c.z += x[2]; c.w += x[3];
+            *cell = c;
+          }
+        }
+        float* drow = d_am + (bt0 + t) * V + v;
+        if (kVec) {
+          float4 o = *reinterpret_cast<float4*>(drow);
+          o.x += dsum[0]; o.y += dsum[1]; o.z += dsum[2]; o.w += dsum[3];
+          *reinterpret_cast<float4*>(drow) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (v + j < V) drow[j] += dsum[j];
         }
       }
-    }
-    __syncthreads();
-    if (half) {
+      for (int i = 0; i <= w_hi - w_lo; ++i) {
+        const float4 c = *reinterpret_cast<const float4*>(mine + i * kDjCols);
+        if (c.x == 0.f && c.y == 0.f && c.z == 0.f && c.w == 0.f) continue;
+        float* lrow = d_lm + ((int64_t)b * (S + 1) + w_lo + i) * V + v;
+        if (kVec) {
+          atomicAdd(reinterpret_cast<float4*>(lrow), c);
+        } else {
+          const float e[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) red[q][j] = acc[j];
-    }
-    __syncthreads();
-    if (!half && v < V) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = acc[j] + red[q][j];
-        if (v + j < V && x != 0.f) d_lm[bs * V + v + j] += x;
+          for (int j = 0; j < 4; ++j)
+            if (v + j < V && e[j] != 0.f) atomicAdd(lrow + j, e[j]);
+        }
       }
     }
   }
@@ -808,21 +795,19 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
         return rc;
       const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;
       {
-        const int64_t f0 = row0 / p.R, f1 = (row0 + rows_live + p.R - 1) / p.R;
-        const int64_t n = (f1 - f0) * ((p.V + 3) / 4);
-        ProfScope prof("djoint_am_kernel", stream);
-        djoint_am_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, w.lm_row, row0, rows_live,
-                                                                         M, p.R, p.V, p.act, d_am);
-      }
-      {
-        ProfScope prof("djoint_lm_kernel", stream);
-        const unsigned nbs = (unsigned)((int64_t)p.B * (p.S + 1));
-        if (p.V % 4 == 0)
-          djoint_lm_kernel<true><<<nbs, 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0, rows_live, M,
-                                                          p.T, p.S, p.R, p.V, p.act, d_lm);
-        else
-          djoint_lm_kernel<false><<<nbs, 256, 0, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0, rows_live,
-                                                           M, p.T, p.S, p.R, p.V, p.act, d_lm);
+        ProfScope prof("djoint_reduce_kernel", stream);
+        const dim3 grid((unsigned)((p.T + kDjFrames - 1) / kDjFrames), (unsigned)p.B);
+        const size_t smem = (size_t)kDjMaxSpan * kDjCols * sizeof(float);
+        const bool vec = (p.V % 4 == 0) && (((uintptr_t)p.am | (uintptr_t)p.lm | (uintptr_t)d_am | (uintptr_t)d_lm) % 16 == 0);
+        if (vec) {
+          cudaFuncSetAttribute(djoint_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          djoint_reduce_kernel<true><<<grid, 128, smem, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0,
+                                                                 rows_live, M, p.T, p.S, p.R, p.V, p.act, d_am, d_lm);
+        } else {
+          cudaFuncSetAttribute(djoint_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          djoint_reduce_kernel<false><<<grid, 128, smem, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0,
+                                                                  rows_live, M, p.T, p.S, p.R, p.V, p.act, d_am, d_lm);
+        }
       }
       if (int rc = check_launch("djoint reduce kernels")) return rc;
     }
