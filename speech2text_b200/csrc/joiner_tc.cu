@@ -460,13 +460,14 @@ constexpr int kDjFrames = 16;
 constexpr int kDjMaxSpan = 16;
 constexpr int kDjCols = 512;  // columns per pass: 128 threads x 4
 
-template <bool kVec>
+template <bool kVec, int kRB>
 __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16* __restrict__ dh, int ld,
                                                             const float* __restrict__ am, const float* __restrict__ lm,
                                                             const int64_t* __restrict__ ranges,
                                                             const int64_t* __restrict__ boundary, int64_t row0,
                                                             int64_t rows, int64_t M, int T, int S, int R, int V, int act,
-                                                            float* __restrict__ d_am, float* __restrict__ d_lm) {
+                                                            bool am_accumulate, float* __restrict__ d_am,
+                                                            float* __restrict__ d_lm) {
   extern __shared__ float acc[];  // [kDjMaxSpan][kDjCols]
   __shared__ int sbs[kDjFrames];
   const int b = blockIdx.y, t0 = blockIdx.x * kDjFrames;
@@ -500,41 +501,37 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
 #pragma unroll
           for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(arow + j) : 0.f;
         }
-        for (int rb = r_lo; rb <= r_hi; rb += 8) {
-          // all loads of up to eight band slots first, so their latencies overlap
-          uint2 graw[8];
-          float l[8][4];
+        for (int rb = r_lo; rb <= r_hi; rb += kRB) {
+          // all loads of up to kRB band slots first, unconditionally (slots outside the band or the chunk read a
+          // valid dummy row and are weighted by 0), so that their latencies overlap
+          uint2 graw[kRB];
+          float l[kRB][4], wgt[kRB];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < kRB; ++q) {
             const int r = rb + q;
             const int64_t m = m_base + r;
             const bool ok = r <= r_hi && m >= row0 && m < row_end;
-            graw[q] = make_uint2(0u, 0u);
+            wgt[q] = ok ? 1.f : 0.f;
+            graw[q] = *reinterpret_cast<const uint2*>(dh + (ok ? (m - row0) * ld : 0) + v);  // ld, v multiples of 4
+            const float* lrow = lm + ((int64_t)b * (S + 1) + (ok ? sbt + r : 0)) * V + v;
+            if (kVec) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
+              l[q][0] = t4.x; l[q][1] = t4.y; l[q][2] = t4.z; l[q][3] = t4.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) l[q][j] = 0.f;
-            if (ok) {
-              graw[q] = *reinterpret_cast<const uint2*>(dh + (m - row0) * ld + v);  // ld and v are multiples of 4
-              const float* lrow = lm + ((int64_t)b * (S + 1) + sbt + r) * V + v;
-              if (kVec) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
-                l[q][0] = t4.x; l[q][1] = t4.y; l[q][2] = t4.z; l[q][3] = t4.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) l[q][j] = (v + j < V) ? __ldg(lrow + j) : 0.f;
-              }
+              for (int j = 0; j < 4; ++j) l[q][j] = (v + j < V) ? __ldg(lrow + j) : 0.f;
             }
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = rb + q;
-            if (r > r_hi) break;
+          for (int q = 0; q < kRB; ++q) {
+            const int r = min(rb + q, r_hi);  // a clamped duplicate slot adds 0
             const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&graw[q]);
             float4* cell = reinterpret_cast<float4*>(mine + (sbt + r - w_lo) * kDjCols);  // sbt + r in [w_lo, w_hi]
             float4 c = *cell;
             float x[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              x[j] = __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[q][j], act);  // rows outside the chunk: dh read as 0
+              x[j] = wgt[q] * __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[q][j], act);
               dsum[j] += x[j];
             }
             c.x += x[0]; c.y += x[1]; c.z += x[2]; c.w += x[3];
@@ -543,13 +540,16 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
         }
         float* drow = d_am + (bt0 + t) * V + v;
         if (kVec) {
-          float4 o = *reinterpret_cast<float4*>(drow);
-          o.x += dsum[0]; o.y += dsum[1]; o.z += dsum[2]; o.w += dsum[3];
+          float4 o = make_float4(dsum[0], dsum[1], dsum[2], dsum[3]);
+          if (am_accumulate) {
+            const float4 old = *reinterpret_cast<float4*>(drow);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
           *reinterpret_cast<float4*>(drow) = o;
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (v + j < V) drow[j] += dsum[j];
+            if (v + j < V) drow[j] = (am_accumulate ? drow[j] : 0.f) + dsum[j];
         }
       }
       for (int i = 0; i <= w_hi - w_lo; ++i) {
@@ -567,6 +567,17 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
       }
     }
   }
+}
+
+template <bool kVec, int kRB>
+void launch_djoint_reduce(const JoinerProblem& p, const __nv_bfloat16* dh, int ld, int64_t row0, int64_t rows, int64_t M,
+                          bool am_accumulate, float* d_am, float* d_lm, cudaStream_t stream) {
+  const dim3 grid((unsigned)((p.T + kDjFrames - 1) / kDjFrames), (unsigned)p.B);
+  const size_t smem = (size_t)kDjMaxSpan * kDjCols * sizeof(float);
+  auto kern = djoint_reduce_kernel<kVec, kRB>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, 128, smem, stream>>>(dh, ld, p.am, p.lm, p.ranges, p.boundary, row0, rows, M, p.T, p.S, p.R, p.V, p.act,
+                                    am_accumulate, d_am, d_lm);
 }
 
 // C^T accumulate: out[(n + j) * ld + m] += acc[j]     (dW1[i, v] from the (v, i) accumulator)
@@ -796,18 +807,15 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;
       {
         ProfScope prof("djoint_reduce_kernel", stream);
-        const dim3 grid((unsigned)((p.T + kDjFrames - 1) / kDjFrames), (unsigned)p.B);
-        const size_t smem = (size_t)kDjMaxSpan * kDjCols * sizeof(float);
         const bool vec = (p.V % 4 == 0) && (((uintptr_t)p.am | (uintptr_t)p.lm | (uintptr_t)d_am | (uintptr_t)d_lm) % 16 == 0);
-        if (vec) {
-          cudaFuncSetAttribute(djoint_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          djoint_reduce_kernel<true><<<grid, 128, smem, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0,
-                                                                 rows_live, M, p.T, p.S, p.R, p.V, p.act, d_am, d_lm);
-        } else {
-          cudaFuncSetAttribute(djoint_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          djoint_reduce_kernel<false><<<grid, 128, smem, stream>>>(w.dh, d.Vp, p.am, p.lm, p.ranges, p.boundary, row0,
-                                                                  rows_live, M, p.T, p.S, p.R, p.V, p.act, d_am, d_lm);
-        }
+        // a frame whose band slots straddle two row chunks is finished by the second launch
+        const bool am_acc = d.chunk < (int64_t)d.Mt * 128;
+        const int rb = p.R <= 4 ? 4 : (p.R == 5 ? 5 : (p.R == 6 ? 6 : 8));
+        if (!vec) launch_djoint_reduce<false, 4>(p, w.dh, d.Vp, row0, rows_live, M, am_acc, d_am, d_lm, stream);
+        else if (rb == 4) launch_djoint_reduce<true, 4>(p, w.dh, d.Vp, row0, rows_live, M, am_acc, d_am, d_lm, stream);
+        else if (rb == 5) launch_djoint_reduce<true, 5>(p, w.dh, d.Vp, row0, rows_live, M, am_acc, d_am, d_lm, stream);
+        else if (rb == 6) launch_djoint_reduce<true, 6>(p, w.dh, d.Vp, row0, rows_live, M, am_acc, d_am, d_lm, stream);
+        else launch_djoint_reduce<true, 8>(p, w.dh, d.Vp, row0, rows_live, M, am_acc, d_am, d_lm, stream);
       }
       if (int rc = check_launch("djoint reduce kernels")) return rc;
     }
