@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
         float* drow = d_am + (bt0 + t) * V + v;
         if (kVec) {
           float4 o = make_float4(dsum[0], dsum[1], dsum[2], dsum[3]);
-          if (am_accumulate) {
+          if (am_accumulate || w_lo > s_lo) {  // later windows add to what the first one stored
             const float4 old = *reinterpret_cast<float4*>(drow);
             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
           }
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (v + j < V) drow[j] = (am_accumulate ? drow[j] : 0.f) + dsum[j];
+            if (v + j < V) drow[j] = ((am_accumulate || w_lo > s_lo) ? drow[j] : 0.f) + dsum[j];
         }
       }
       for (int i = 0; i <= w_hi - w_lo; ++i) {
@@ -620,6 +620,7 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.n_parts_v = 2 * d.n_tiles_v;  // the logits kernel is bulk-fed: two epilogue groups per tile
   const size_t budget = (size_t)1 << 30;  // bytes of one orientation of the chunk's G
   int64_t rows = (int64_t)(budget / ((size_t)d.Vp * 2));
+  if (const char* e = getenv("S2T_B200_CHUNK_ROWS")) rows = atoll(e);  // test hook: force the multi-chunk backward
   rows = (rows / 128) * 128;
   if (rows < 128) rows = 128;
   int64_t all = (int64_t)d.Mt * 128;
