@@ -123,8 +123,9 @@ def kernel_work(cfg):
         "tc_joiner_dW2_gemm": ("tensor", gemm), "tc_joiner_dW1_gemm": ("tensor", gemm),
         "tc_joiner_djoint_gemm": ("tensor", gemm), "tc_joiner_dh_gemm": ("tensor", gemm),
         # segmented reductions of dh (bf16 rows) into d_am / d_lm: dh once, am once, lm once, grads read+write
-        "djoint_am_kernel": ("hbm", M * V * 2.0 + 3 * B * T * V * 4.0 + B * S1 * V * 4.0),
-        "djoint_lm_kernel": ("hbm", M * V * 2.0 + B * T * V * 4.0 + 3 * B * S1 * V * 4.0),
+        # one pass over dh (bf16 rows): dh, am and lm read once, d_am written once, d_lm read-modify-write
+        "djoint_reduce_kernel": ("hbm", M * V * 2.0 + 2 * B * T * V * 4.0 + 3 * B * S1 * V * 4.0),
+        "simple_px_kernel": ("hbm", 4.0 * (2 * B * U * (T + 1) + B * U * T)),
         # simple (smoothed) loss on tensor cores: exp(am - max) built on the fly, 3xTF32 contraction with exp(lm - max)
         # over V, px/py emitted from the epilogue: am and lm read once, px/py written once
         "tc_simple_normaliser_gemm_3xtf32": ("hbm", 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
@@ -245,7 +246,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("S2T_BENCH_MODE", "bf16"), choices=["fp32", "bf16"],
                     help="joiner arithmetic: bf16 tensor cores (BASELINE config 3: 'bf16 joiner') or strict fp32")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-utts", type=int, default=4, help="utterances per CPU-baseline step")
+    ap.add_argument("--cpu-utts", type=int, default=64, help="utterances per CPU-baseline step")
+    ap.add_argument("--cpu-steps", type=int, default=8, help="timed CPU-baseline steps (about 10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -263,7 +265,7 @@ def main():
         if rank != 0:
             return
         batch = make_batch(cfg, 1234)
-        steps = max(1, min(args.steps, 3))
+        steps = max(1, min(args.steps, args.cpu_steps))
         base, sec = cpu_arm(cfg, batch, args.cpu_utts, steps, min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "utt/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
@@ -346,19 +348,24 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in h_in.values())
     loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
+    # the copy of step i+1 travels on the prefetcher's stream while step i computes (every step still copies
+    # its own inputs from pinned memory inside the timed region and reads its losses back)
+    from speech2text_b200.prefetch import HostBatchPrefetcher
+    pf = HostBatchPrefetcher(dev)
+
     def e2e_step():
-        e = h_in["enc"].to(dev, non_blocking=True).requires_grad_(True)
-        p = h_in["pred"].to(dev, non_blocking=True).requires_grad_(True)
-        t_len = h_in["t_len"].to(dev, non_blocking=True)
-        s_len = h_in["s_len"].to(dev, non_blocking=True)
-        labels = h_in["labels"].to(dev, non_blocking=True)
+        d = pf.get()
+        pf.put(h_in)
+        e = d["enc"].detach().requires_grad_(True)  # fresh autograd leaves over the slot's storage
+        p = d["pred"].detach().requires_grad_(True)
         bucket.zero()
-        total, simple, pruned = hot_path_step(joiner, loss_mod, e, t_len, p, s_len, labels)
+        total, simple, pruned = hot_path_step(joiner, loss_mod, e, d["t_len"], p, d["s_len"], d["labels"])
         if world > 1:
             bucket.all_reduce(average=True)
         vec = reduce_scalars([total, simple, pruned])
         loss_host.copy_(vec, non_blocking=True)
 
+    pf.put(h_in)
     for _ in range(2):
         e2e_step()
     barrier()
@@ -401,10 +408,12 @@ def main():
                 "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset, untimed)",
                                                     joiner_mode=args.mode),
                 "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps},
+                        "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps,
+                        "h2d": "pinned host -> device on a copy stream, one step ahead of the compute stream "
+                               "(speech2text_b200.prefetch.HostBatchPrefetcher)"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels_ms_per_step": kernels}
         if not args.no_cpu_baseline and world == 1:
-            base, _ = cpu_arm(cfg, batch, args.cpu_utts, 2, 1,
+            base, _ = cpu_arm(cfg, batch, args.cpu_utts, args.cpu_steps, 1,
                               joiner_state={k: v.detach().cpu() for k, v in joiner.state_dict().items()})
             line["cpu_baseline"] = base
         elif not args.no_cpu_baseline:

@@ -402,3 +402,22 @@ def test_full_size_properties_c3():
     last = torch.gather(s0, 1, (Tl - 1)[:, None]).squeeze(1)
     assert torch.equal(last, torch.clamp(Sl - R + 1, min=0))
     assert torch.equal(ranges[:, :, 1:] - ranges[:, :, :-1], torch.ones_like(ranges[:, :, 1:]))
+
+
+def test_host_batch_prefetcher_delivers_batches_in_order():
+    from speech2text_b200.prefetch import HostBatchPrefetcher
+    pf = HostBatchPrefetcher(_dev())
+    host = [{"x": torch.full((1 << 20,), float(i)).pin_memory(), "n": torch.tensor([i]).pin_memory()} for i in range(4)]
+    pf.put(host[0])
+    for i in range(4):
+        d = pf.get()
+        if i + 1 < 4:
+            pf.put(host[i + 1])
+        assert d["x"].is_cuda and float(d["x"].sum().item()) == float(i) * (1 << 20)
+        assert int(d["n"].item()) == i
+    assert len(pf) == 0
+    with pytest.raises(ValueError):
+        pf.put({"x": torch.zeros(4)})
+    pf.put(host[0])
+    with pytest.raises(RuntimeError):  # depth 2: one batch in use, one in flight
+        pf.put(host[1])
