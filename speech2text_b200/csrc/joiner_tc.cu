@@ -84,7 +84,6 @@ __global__ void tc_row_meta_kernel(const int64_t* __restrict__ ranges, const int
 // cover the 64 vocabulary entries (256 contiguous bytes of am and of lm) that one joiner row contributes
 // to a k-step, so every warp-wide load reads whole 128-byte lines; a k-step is pipelined in two halves
 // of four rows per thread, the loads of the next half in flight while the current one is converted.
-__device__ int g_exp_noload = 0;
 struct JointQuad {
   float4 a[4], l[4];
 };
@@ -95,7 +94,6 @@ __device__ __forceinline__ void joint_load_quad(JointQuad& q, const float* am, c
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const bool live = ar[j] >= 0;
-    if (g_exp_noload) { q.a[j] = make_float4(0.1f * v, 0.2f, 0.3f, 0.4f); q.l[j] = make_float4(0.1f, 0.2f * lr[j], 0.3f, 0.4f); continue; }
     const float* a = am + (int64_t)(live ? ar[j] : 0) * V + v;
     const float* l = lm + (int64_t)(live ? lr[j] : 0) * V + v;
     if (live && vec && v + 4 <= V) {
@@ -227,22 +225,24 @@ struct JointMnProducer {
 };
 
 // ---- epilogue helpers -----------------------------------------------------------------------
-// write 32 consecutive K-elements (columns n..n+31 of the accumulator) of row `r_glob` of a packed operand
-__device__ __forceinline__ void store_packed_row32(uint8_t* packed, int row_blocks, int64_t r_glob, int n,
+// write 32 consecutive K-elements (columns n..n+31 of the accumulator) of every row of the warp into a packed
+// operand; transposed through shared memory so that four lanes write the 64 contiguous bytes a row owns
+// inside its (swizzled) 128-byte block row.  ctx.m is the thread's own row (rows of a warp are consecutive).
+__device__ __forceinline__ void store_packed_row32(const EpiCtx& ctx, uint8_t* packed, int row_blocks, int n,
                                                    const float (&x)[32]) {
-  const int rb = (int)(r_glob >> 7), r = (int)(r_glob & 127);
-  uint8_t* blk = packed + packed_block_index(rb, n >> 6, row_blocks) * kBlockBytes;
-  const int c0 = (n & 63) >> 3;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 out = make_uint4(pack_bf16x2(x[c * 8 + 0], x[c * 8 + 1]), pack_bf16x2(x[c * 8 + 2], x[c * 8 + 3]),
-                           pack_bf16x2(x[c * 8 + 4], x[c * 8 + 5]), pack_bf16x2(x[c * 8 + 6], x[c * 8 + 7]));
-    *reinterpret_cast<uint4*>(blk + block_chunk_offset(r, c0 + c)) = out;
-  }
+  uint4 mine[4];
+  pack_row32_bf16(x, mine);
+  const int64_t m0 = (int64_t)ctx.m - (ctx.t & 31);
+  const int kb = n >> 6, c0 = (n & 63) >> 3;
+  warp_transposed_chunk_b16(ctx, mine, [&](int r, int q, uint4 v) {
+    const int64_t rg = m0 + r;
+    uint8_t* blk = packed + packed_block_index((int)(rg >> 7), kb, row_blocks) * kBlockBytes;
+    *reinterpret_cast<uint4*>(blk + block_chunk_offset((int)(rg & 127), c0 + q)) = v;
+  });
 }
 // hidden = acc + b1 -> Hp (rows m, cols i)
 struct HiddenEpi {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = kTransposeScratchBytes;
   const float* b1;
   int I;
   int64_t M;
@@ -256,7 +256,7 @@ struct HiddenEpi {
     const bool live = ctx.m < M;
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = (live && n + j < I) ? acc[j] + __ldg(b1 + n + j) : 0.f;
-    store_packed_row32(Hp, h_row_blocks, ctx.m, n, x);
+    store_packed_row32(ctx, Hp, h_row_blocks, n, x);
   }
 };
 
@@ -338,7 +338,7 @@ __global__ void lse_combine_kernel(const float* __restrict__ part, const float* 
 
 // G = coef * clip(occ_px [v == sym] + occ_py [v == blank] - (occ_px + occ_py) softmax) for a row chunk
 struct GradEpi {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = kTransposeScratchBytes;
   const float* b2;
   const int* row_sym;
   const float* lse;
@@ -401,7 +401,7 @@ struct GradEpi {
         x[j] = (v < V) ? val : 0.f;
       }
     }
-    store_packed_row32(Gp, g_row_blocks, ctx.m, n, x);
+    store_packed_row32(ctx, Gp, g_row_blocks, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
     if (n + lane < V && cs != 0.f) atomicAdd(db2 + n + lane, cs);
@@ -410,7 +410,7 @@ struct GradEpi {
 
 // dhidden -> DHp (rows chunk-local m, cols i), db1
 struct DHiddenEpi {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = kTransposeScratchBytes;
   int I;
   uint8_t* DHp;
   int dh_row_blocks;
@@ -422,7 +422,7 @@ struct DHiddenEpi {
     float x[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = (n + j < I) ? acc[j] : 0.f;
-    store_packed_row32(DHp, dh_row_blocks, ctx.m, n, x);
+    store_packed_row32(ctx, DHp, dh_row_blocks, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
     if (n + lane < I && cs != 0.f) atomicAdd(db1 + n + lane, cs);
@@ -432,19 +432,19 @@ struct DHiddenEpi {
 // dh = dhidden W1 (before the activation derivative), bf16 row-major (chunk rows, Vp): the GEMM epilogue
 // is a plain store; the segmented reductions into d_am / d_lm run as two fully parallel kernels below.
 struct StoreRowsBf16Epi {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = kTransposeScratchBytes;
   __nv_bfloat16* out;
   int ld;
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
-    uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)ctx.m * ld + n);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      dst[c] = make_uint4(pack_bf16x2(acc[c * 8 + 0], acc[c * 8 + 1]), pack_bf16x2(acc[c * 8 + 2], acc[c * 8 + 3]),
-                          pack_bf16x2(acc[c * 8 + 4], acc[c * 8 + 5]), pack_bf16x2(acc[c * 8 + 6], acc[c * 8 + 7]));
-    }
+    uint4 mine[4];
+    pack_row32_bf16(acc, mine);
+    const int64_t m0 = (int64_t)ctx.m - (ctx.t & 31);
+    warp_transposed_chunk_b16(ctx, mine, [&](int r, int q, uint4 v) {
+      *reinterpret_cast<uint4*>(out + (m0 + r) * ld + n + q * 8) = v;
+    });
   }
 };
 
@@ -708,14 +708,6 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
                                                                        w.am_row, w.lm_row, w.row_sym);
   }
   if (int rc = check_launch("tc_row_meta_kernel")) return rc;
-  {
-    static int exp_flag = -1;
-    if (exp_flag < 0) {
-      const char* e = getenv("S2T_EXP");
-      exp_flag = e ? atoi(e) : 0;
-      cudaMemcpyToSymbol(g_exp_noload, &exp_flag, sizeof(int));
-    }
-  }
   if (int rc = pack_weights(p, d, w, stream)) return rc;
   // hidden: M x Ip, K = V
   {

@@ -70,7 +70,8 @@ struct ExpRowProducerF32 {
       rowp[i] = x + g * V;
       sub[i] = live[i] ? __ldg(mx + g) : 0.f;
     }
-    float4 cur[4], nxt[4];
+    // three register buffers: the loads of k-steps it+1 and it+2 are in flight while step it is converted
+    float4 buf[3][4];
     auto load = [&](float4 (&dst)[4], int ks) {
       const int k = ks * 32 + c * 4;
 #pragma unroll
@@ -86,9 +87,7 @@ struct ExpRowProducerF32 {
       }
     };
     const int off = ((c ^ (rbase & 7)) & 7) << 4;
-    load(cur, pc.ks0);
-    for (int it = 0; it < pc.n_it; ++it) {
-      if (it + 1 < pc.n_it) load(nxt, pc.ks0 + it + 1);
+    auto emit_stage = [&](const float4 (&cur)[4], int it) {
       pc.wait_empty(it);
       uint8_t* dst = pc.stage(it) + rbase * 128 + off;
       const int k = (pc.ks0 + it) * 32 + c * 4;
@@ -115,8 +114,17 @@ struct ExpRowProducerF32 {
         }
       }
       pc.arrive_full(it);
+    };
+    load(buf[0], pc.ks0);
+    if (pc.n_it > 1) load(buf[1], pc.ks0 + 1);
+    for (int it = 0; it < pc.n_it; it += 3) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      for (int u = 0; u < 3; ++u) {
+        if (it + u < pc.n_it) {
+          if (it + u + 2 < pc.n_it) load(buf[(u + 2) % 3], pc.ks0 + it + u + 2);
+          emit_stage(buf[u], it + u);
+        }
+      }
     }
   }
 };
@@ -237,15 +245,25 @@ struct GradExpEpi {
   }
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
-    const int m0 = ctx.m - (ctx.t & 31);
+    const int lane = ctx.t & 31, m0 = ctx.m - lane;
     const bool vec = ((V & 3) == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    // the eight x pieces this lane will need after the transpose, all requested before the first one is used
+    float4 xs[8];
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i & 3) * 8 + (lane & 7), col = n + (i >> 2) * 16 + (lane >> 3) * 4;
+        xs[i] = (m < rows && col < V) ? __ldg(reinterpret_cast<const float4*>(x + ((int64_t)ctx.batch * rows + m) * V + col))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     warp_transposed_chunk(ctx, acc, V - n, [&](int r, int c, float4 v) {
       const int m = m0 + r, col = n + c;
       if (m >= rows || col >= V) return;
       const float sub = st.sub[r >> 3];
       const int64_t o = ((int64_t)ctx.batch * rows + m) * V + col;
       if (vec) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + o));
+        const float4 xv = xs[(c >> 4) * 4 + (r >> 3)];
         *reinterpret_cast<float4*>(out + o) = make_float4(-__expf(xv.x - sub) * v.x, -__expf(xv.y - sub) * v.y,
                                                           -__expf(xv.z - sub) * v.z, -__expf(xv.w - sub) * v.w);
       } else {

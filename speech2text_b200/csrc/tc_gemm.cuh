@@ -125,6 +125,7 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
   // 64-row k-steps for MN-major operands
   int a_batch_off = 0;
   int b_batch_off = 0;
+  int dbg = 0;  // experiment flags (S2T_DBG): 1 skip epilogue functor, 2 only the big x big MMA, 4 skip the MMA
 };
 
 // What an on-the-fly A producer sees for one tile: kProdThreads threads fill stage(it) for it in [0, n_it).
@@ -141,9 +142,12 @@ struct ProdCtx {
     const uint32_t g = it0 + it;
     mbar_wait(&empty[g % stages], ((g / stages) & 1) ^ 1);
   }
+  // every producer thread publishes its generic-proxy writes to the async proxy; one arrival per warp
+  // (256 per-thread arrivals on one mbarrier serialise on the shared-memory atomic unit)
   __device__ __forceinline__ void arrive_full(int it) const {
     fence_proxy_async_smem();
-    mbar_arrive(&full[(it0 + it) % stages]);
+    __syncwarp();
+    if ((t & 31) == 0) mbar_arrive(&full[(it0 + it) % stages]);
   }
 };
 
@@ -199,7 +203,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + kProdThreads);
+      mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + kProdWarps);
       mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -298,9 +302,13 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
             } else {
               const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
               const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
-              umma_tf32(acc, da_s, db, idesc, accum);  // small terms first
-              umma_tf32(acc, da, db_s, idesc, true);
-              umma_tf32(acc, da, db, idesc, true);
+              if (!(mn.dbg & 2)) {
+                umma_tf32(acc, da_s, db, idesc, accum);  // small terms first
+                umma_tf32(acc, da, db_s, idesc, true);
+                umma_tf32(acc, da, db, idesc, true);
+              } else {
+                umma_tf32(acc, da, db, idesc, accum);
+              }
             }
           }
           umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
@@ -341,7 +349,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       for (int cc = 0; cc < kCols / 32; ++cc) {
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + group * kCols + cc * 32, v);
-        epi.chunk(st, ctx, ctx.col0 + cc * 32, v);
+        if (!(mn.dbg & 1)) epi.chunk(st, ctx, ctx.col0 + cc * 32, v);
       }
       epi.end(st, ctx);
       tc_fence_before();
@@ -410,6 +418,11 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
   }
   const long long tiles = (long long)m_tiles * n_tiles * batches * k_splits;
   const int grid = (int)(tiles < gemm_sm_count() ? tiles : gemm_sm_count());
+  {
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("S2T_DBG") ? atoi(getenv("S2T_DBG")) : 0;
+    mn.dbg = dbg;
+  }
   ProfScope prof(what, stream);
   kern<<<grid, gemm_threads<ASrc>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
                                                      k_splits, epi, mn);
@@ -448,6 +461,31 @@ __device__ __forceinline__ void warp_transposed_chunk(const EpiCtx& ctx, const f
     }
     __syncwarp();
   }
+}
+
+// Same idea for 2-byte outputs: the thread's 32 columns are 64 bytes (four 16-byte pieces).  f(r, q, v) hands
+// piece q (columns 8 q .. 8 q + 7) of the warp's row r back; the four lanes l, l+8, l+16, l+24 of a call cover the
+// 64 contiguous bytes of one row, so a warp-wide 16-byte store writes whole 32-byte sectors of eight rows.
+template <class F>
+__device__ __forceinline__ void warp_transposed_chunk_b16(const EpiCtx& ctx, const uint4 (&mine)[4], F&& f) {
+  uint32_t* tile = reinterpret_cast<uint32_t*>(ctx.scratch) + (ctx.t >> 5) * (32 * kTransposeRowWords);
+  const int lane = ctx.t & 31;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(tile + lane * kTransposeRowWords + q * 4) = mine[q];
+  __syncwarp();
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 8 + (lane & 7), q = lane >> 3;
+    f(r, q, *reinterpret_cast<const uint4*>(tile + r * kTransposeRowWords + q * 4));
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void pack_row32_bf16(const float (&x)[32], uint4 (&out)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    out[c] = make_uint4(pack_bf16x2(x[c * 8 + 0], x[c * 8 + 1]), pack_bf16x2(x[c * 8 + 2], x[c * 8 + 3]),
+                        pack_bf16x2(x[c * 8 + 4], x[c * 8 + 5]), pack_bf16x2(x[c * 8 + 6], x[c * 8 + 7]));
 }
 
 struct StoreRowMajorEpi {
@@ -564,7 +602,8 @@ struct RowCopyProducerF32 {
       live[i] = m < M;
       rowp[i] = x + (live[i] ? m * ld : 0);
     }
-    float4 cur[4], nxt[4];
+    // three register buffers: the loads of k-steps it+1 and it+2 are in flight while step it is converted
+    float4 buf[3][4];
     auto load = [&](float4 (&dst)[4], int ks) {
       const int k = ks * 32 + c * 4;
 #pragma unroll
@@ -580,9 +619,7 @@ struct RowCopyProducerF32 {
       }
     };
     const int off = ((c ^ (rbase & 7)) & 7) << 4;
-    load(cur, pc.ks0);
-    for (int it = 0; it < pc.n_it; ++it) {
-      if (it + 1 < pc.n_it) load(nxt, pc.ks0 + it + 1);
+    auto emit_stage = [&](const float4 (&cur)[4], int it) {
       pc.wait_empty(it);
       uint8_t* dst = pc.stage(it) + rbase * 128 + off;
 #pragma unroll
@@ -605,8 +642,17 @@ struct RowCopyProducerF32 {
         }
       }
       pc.arrive_full(it);
+    };
+    load(buf[0], pc.ks0);
+    if (pc.n_it > 1) load(buf[1], pc.ks0 + 1);
+    for (int it = 0; it < pc.n_it; it += 3) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      for (int u = 0; u < 3; ++u) {
+        if (it + u < pc.n_it) {
+          if (it + u + 2 < pc.n_it) load(buf[(u + 2) % 3], pc.ks0 + it + u + 2);
+          emit_stage(buf[u], it + u);
+        }
+      }
     }
   }
 };
