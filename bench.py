@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--cpu-utts", type=int, default=64, help="utterances per CPU-baseline step")
     ap.add_argument("--cpu-steps", type=int, default=8, help="timed CPU-baseline steps (about 10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
 
     cfg = WORKLOADS[args.workload]
@@ -297,16 +298,20 @@ def main():
     pred = d_in["pred"].requires_grad_(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step():
+    def step_core():
         bucket.zero()
         enc.grad = None
         pred.grad = None
-        total, simple, pruned = hot_path_step(joiner, loss_mod, enc, d_in["t_len"], pred, d_in["s_len"],
-                                              d_in["labels"])
+        return hot_path_step(joiner, loss_mod, enc, d_in["t_len"], pred, d_in["s_len"], d_in["labels"])
+
+    def finish(losses):
         if world > 1:
             bucket.all_reduce(average=True)
-            reduce_scalars([total, simple, pruned])
-        return total, simple, pruned
+            reduce_scalars(list(losses))
+        return losses
+
+    def step():  # eager: every kernel issued from Python
+        return finish(step_core())
 
     def barrier():
         torch.cuda.synchronize()
@@ -328,13 +333,31 @@ def main():
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs)
 
+    # the step is a fixed sequence of ~350 short kernels: capture it once, replay it (speech2text_b200.graph)
+    execution = "eager"
+    run_step = step
+    launches0 = _lib.launch_count()
+    step()
+    launches_per_step = _lib.launch_count() - launches0
+    if not args.eager:
+        try:
+            from speech2text_b200.graph import GraphedStep
+            graphed = GraphedStep(step_core)
+            run_step = lambda: finish(graphed())
+            execution = "cuda graph replay of the eager step (forward + backward), all-reduce issued after it"
+        except Exception as exc:  # keep measuring, but say what happened
+            execution = f"eager (graph capture failed: {type(exc).__name__}: {exc})"
+            torch.cuda.synchronize()
+    for _ in range(3):
+        run_step()
+    barrier()
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = _lib.launch_count()
     barrier()
-    total_ms = timed(args.steps, step)
+    total_ms = timed(args.steps, run_step)
     barrier()
-    launches = _lib.launch_count() - launches0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop()
 
     # per-kernel device time, same steps again with the library's event timer on
@@ -353,20 +376,30 @@ def main():
     from speech2text_b200.prefetch import HostBatchPrefetcher
     pf = HostBatchPrefetcher(dev)
 
-    def e2e_step():
-        d = pf.get()
-        pf.put(h_in)
+    def e2e_core(d):
         e = d["enc"].detach().requires_grad_(True)  # fresh autograd leaves over the slot's storage
         p = d["pred"].detach().requires_grad_(True)
         bucket.zero()
-        total, simple, pruned = hot_path_step(joiner, loss_mod, e, d["t_len"], p, d["s_len"], d["labels"])
+        return hot_path_step(joiner, loss_mod, e, d["t_len"], p, d["s_len"], d["labels"])
+
+    slot_graphs = {}
+
+    def e2e_step():
+        d = pf.get()
+        pf.put(h_in)
+        key = d["enc"].data_ptr()
+        if execution.startswith("cuda graph") and key not in slot_graphs:
+            # one graph per device slot of the prefetcher (a graph reads fixed addresses)
+            from speech2text_b200.graph import GraphedStep
+            slot_graphs[key] = GraphedStep(lambda: e2e_core(d), warmup=1, pool=graphed.pool())
+        losses = slot_graphs[key]() if key in slot_graphs else e2e_core(d)
         if world > 1:
             bucket.all_reduce(average=True)
-        vec = reduce_scalars([total, simple, pruned])
+        vec = reduce_scalars(list(losses))
         loss_host.copy_(vec, non_blocking=True)
 
     pf.put(h_in)
-    for _ in range(2):
+    for _ in range(4):
         e2e_step()
     barrier()
     e2e_ms = timed(args.steps, e2e_step)
@@ -405,7 +438,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16",
-                "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset, untimed)",
+                "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset, untimed)", execution=execution,
                                                     joiner_mode=args.mode),
                 "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps,

@@ -60,6 +60,7 @@ struct EpiCtx {
   int part;    // n_tile * groups + group: index of the (row, column-range) partial
   uint8_t* scratch;  // this group's Epi::kScratchBytes
   int scratch_bytes;
+  int dbg;
 };
 
 // barrier over the 128 threads of one epilogue group
@@ -343,6 +344,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       ctx.part = c.n_tile * kGroups + group;
       ctx.scratch = scratch + group * kScratch;
       ctx.scratch_bytes = kScratch;
+      ctx.dbg = mn.dbg;
       typename Epi::State st;
       epi.begin(st, ctx);
 #pragma unroll 1

@@ -421,3 +421,58 @@ def test_host_batch_prefetcher_delivers_batches_in_order():
     pf.put(host[0])
     with pytest.raises(RuntimeError):  # depth 2: one batch in use, one in flight
         pf.put(host[1])
+
+
+def test_graphed_step_replays_the_eager_step(monkeypatch):
+    """speech2text_b200.graph.GraphedStep: the captured forward + backward gives the eager results."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    from speech2text_b200.graph import GraphedStep
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", "bf16")
+    name = "pruned_loss_test"
+    spec, case = CASES[name], make_case(name)
+    dev = _dev()
+    joiner = Joiner(JoinerConfig(**spec["joiner"]))
+    joiner.load_state_dict({k: torch.from_numpy(v) for k, v in case["weights"].items()})
+    joiner = joiner.to(dev)
+    loss_mod = Loss({"model": "Pruned_Rnnt", "config": spec["loss"]})
+    enc = torch.from_numpy(case["encoder_out"]).to(dev).requires_grad_(True)
+    pred = torch.from_numpy(case["predict_out"]).to(dev).requires_grad_(True)
+    enc_len = torch.from_numpy(case["encoder_out_lengths"]).float().to(dev)
+    tgt_len = torch.from_numpy(case["target_lengths"]).float().to(dev)
+    tgt = torch.from_numpy(case["target"]).to(dev)
+
+    def step():
+        joiner.zero_grad(set_to_none=False)
+        enc.grad = None
+        pred.grad = None
+        logits, boundary, ranges, simple = joiner(enc, enc_len, pred, tgt_len, tgt)
+        pruned = loss_mod({"logits": logits, "logits_length": enc_len, "targets": tgt, "targets_length": tgt_len,
+                           "boundary": boundary, "ranges": ranges})
+        total = (0.5 * simple + pruned).mean()
+        total.backward()
+        return total
+
+    for p in joiner.parameters():
+        p.grad = torch.zeros_like(p)
+    ref = step().detach().clone()
+    torch.cuda.synchronize()
+    ref_enc = enc.grad.clone()
+    ref_w = {k: p.grad.clone() for k, p in joiner.named_parameters()}
+    g = GraphedStep(step)
+    enc.data.mul_(1.0)  # same data: replay must reproduce the eager numbers
+    out = g()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-6
+    assert rel_err(enc.grad, ref_enc) < 2e-3  # atomics order + bf16 operands
+    for k, p in joiner.named_parameters():
+        assert rel_err(p.grad, ref_w[k]) < 2e-3, k
+    # new data through the same graph
+    with torch.no_grad():
+        enc.mul_(0.5)
+    out2 = g()
+    torch.cuda.synchronize()
+    eager2 = step().detach()
+    torch.cuda.synchronize()
+    assert rel_err(out2, eager2) < 1e-6
