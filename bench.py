@@ -428,8 +428,16 @@ def main():
             else:
                 achieved = per_launch / avg_s / 1e9
                 peak, unit = pk["hbm"], "GB/s"
+            traffic = None
+            try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+                    rec = json.load(f).get(name)
+                if rec:
+                    traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+            except OSError:
+                pass
             roof = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit,
-                    "frac": achieved / peak, "traffic": None, "peak_source": pk["source"],
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": pk["source"],
                     "avg_launch_ms": ms / cnt, "launches_timed": cnt,
                     "share_of_step": ms / prof_ms,
                     "how": "library CUDA-event timer around every launch, second pass of the same steps"}
