@@ -224,6 +224,75 @@ struct JointMnProducer {
   }
 };
 
+// J = act(am + lm[ranges]) for every joiner row -> bf16 packed operand (rows m, cols v).  A CTA owns 32 rows:
+// their am / lm row indices are staged once, then every warp converts (row, 128-column segment) tasks, four at
+// a time so that their loads are in flight together.  A lane owns four consecutive vocabulary entries, so each
+// warp-wide load reads 512 contiguous bytes of one am (lm) row and each 8-byte store instruction fills two whole
+// 128-byte block rows.  Rows beyond M and columns beyond V come out as zeros.  Used when J is kept for the
+// backward pass: the hidden contraction is then fed by bulk copies like every other one.
+constexpr int kJpRows = 32;
+
+template <int kAct>
+__global__ void __launch_bounds__(256) joint_pack_kernel(const float* __restrict__ am, const float* __restrict__ lm,
+                                                         const int* __restrict__ am_row, const int* __restrict__ lm_row,
+                                                         int64_t M, int V, int row_blocks, int k_blocks,
+                                                         uint8_t* __restrict__ Jp) {
+  __shared__ int ar[kJpRows], lr[kJpRows];
+  const int64_t m0 = (int64_t)blockIdx.x * kJpRows;
+  if (threadIdx.x < kJpRows) {
+    const int64_t m = m0 + threadIdx.x;
+    ar[threadIdx.x] = m < M ? __ldg(am_row + m) : -1;
+    lr[threadIdx.x] = m < M ? __ldg(lm_row + m) : 0;
+  }
+  __syncthreads();
+  const bool vec = (V & 3) == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = (int)(m0 >> 7), r_in = (int)(m0 & 127);  // the 32 rows sit in one 128-row block
+  const int segs = k_blocks / 2;                           // 128-column segments per row (Vp is a multiple of 256)
+  const int tasks = kJpRows * segs;                        // task = seg * 32 + row: a warp walks down the rows
+  for (int base = warp; base < tasks; base += 8 * 4) {
+    float4 a[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int task = base + 8 * u;
+      const int r = task & (kJpRows - 1), v = (task / kJpRows) * 128 + lane * 4;
+      const bool live = task < tasks && ar[r] >= 0 && v < V;
+      const float* pa = am + (int64_t)max(ar[r], 0) * V + v;
+      const float* pl = lm + (int64_t)lr[r] * V + v;
+      if (live && vec && v + 4 <= V) {
+        a[u] = __ldg(reinterpret_cast<const float4*>(pa));
+        l[u] = __ldg(reinterpret_cast<const float4*>(pl));
+      } else {
+        float xa[4], xl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = live && v + j < V;
+          xa[j] = ok ? __ldg(pa + j) : 0.f;
+          xl[j] = ok ? __ldg(pl + j) : 0.f;
+        }
+        a[u] = make_float4(xa[0], xa[1], xa[2], xa[3]);
+        l[u] = make_float4(xl[0], xl[1], xl[2], xl[3]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int task = base + 8 * u;
+      if (task >= tasks) break;
+      const int r = task & (kJpRows - 1), seg = task / kJpRows;
+      const float x0 = a[u].x + l[u].x, x1 = a[u].y + l[u].y, x2 = a[u].z + l[u].z, x3 = a[u].w + l[u].w;
+      uint2 o;
+      if (kAct == kRelu) {
+        o = make_uint2(pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)), pack_bf16x2(fmaxf(x2, 0.f), fmaxf(x3, 0.f)));
+      } else {
+        o = make_uint2(pack_bf16x2(tanh_fast(x0), tanh_fast(x1)), pack_bf16x2(tanh_fast(x2), tanh_fast(x3)));
+      }
+      // lane -> k-block seg * 2 + lane / 16, 16-byte chunk (lane % 16) / 2, half lane % 2
+      uint8_t* blk = Jp + packed_block_index(rb, seg * 2 + (lane >> 4), row_blocks) * kBlockBytes;
+      *reinterpret_cast<uint2*>(blk + block_chunk_offset(r_in + r, (lane & 15) >> 1) + (lane & 1) * 8) = o;
+    }
+  }
+}
+
 // ---- epilogue helpers -----------------------------------------------------------------------
 // write 32 consecutive K-elements (columns n..n+31 of the accumulator) of every row of the warp into a packed
 // operand; transposed through shared memory so that four lanes write the 64 contiguous bytes a row owns
@@ -709,14 +778,30 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   }
   if (int rc = check_launch("tc_row_meta_kernel")) return rc;
   if (int rc = pack_weights(p, d, w, stream)) return rc;
-  // hidden: M x Ip, K = V
+  // hidden: M x Ip, K = V.  With J kept for the backward pass it is written once by a fully parallel kernel and the
+  // contraction streams it like any packed operand; otherwise the producer warps build it on the fly.
   {
-    if (w.Jp && d.kbV < d.Vp / 64) cudaMemsetAsync(w.Jp, 0, (size_t)d.Mt * (d.Vp / 64) * kBlockBytes, stream);
-    JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act, w.Jp, d.Mt};
     HiddenEpi ep{p.b1, p.I, M, w.Hp, d.Mt};
-    if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
-                                            "tc_joiner_hidden_gemm"))
-      return rc;
+    if (w.Jp) {
+      {
+        ProfScope prof("joint_pack_kernel", stream);
+        const unsigned grid = (unsigned)(d.Mt * (128 / kJpRows));
+        if (p.act == kRelu)
+          joint_pack_kernel<kRelu><<<grid, 256, 0, stream>>>(p.am, p.lm, w.am_row, w.lm_row, M, p.V, d.Mt, d.Vp / 64, w.Jp);
+        else
+          joint_pack_kernel<kTanh><<<grid, 256, 0, stream>>>(p.am, p.lm, w.am_row, w.lm_row, M, p.V, d.Mt, d.Vp / 64, w.Jp);
+      }
+      if (int rc = check_launch("joint_pack_kernel")) return rc;
+      BulkA a{w.Jp, d.Mt};
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
+                                                               "tc_joiner_hidden_gemm"))
+        return rc;
+    } else {
+      JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act, nullptr, d.Mt};
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
+                                                               "tc_joiner_hidden_gemm"))
+        return rc;
+    }
   }
   // logits -> lse partials: M x Vp, K = Ip
   {
