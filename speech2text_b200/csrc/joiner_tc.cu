@@ -355,13 +355,17 @@ struct LseEpi {
       cm = fmaxf(cm, x[j]);
     }
     if (cm > st.mx) {
-      st.sum *= exp2f((st.mx - cm) * kLog2e);
+      st.sum *= ex2_approx((st.mx - cm) * kLog2e);  // (-inf - finite) -> 0 on the first chunk
       st.mx = cm;
     }
-    float s = 0.f;
+    const float nm = -st.mx * kLog2e;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s += exp2f((x[j] - st.mx) * kLog2e);
-    st.sum += s;
+    for (int j = 0; j < 32; j += 2) {  // arguments <= 0; padding columns hold -inf -> 0
+      s0 += ex2_approx(fmaf(x[j], kLog2e, nm));
+      s1 += ex2_approx(fmaf(x[j + 1], kLog2e, nm));
+    }
+    st.sum += s0 + s1;
     if (st.csym >= n && st.csym < n + 32) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)

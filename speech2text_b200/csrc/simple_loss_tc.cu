@@ -194,35 +194,62 @@ __global__ void simple_px_kernel(const float* __restrict__ am, const float4* __r
 
 // W[b,s,t] = coef_b (occ_px + occ_py) exp(am_max + lm_max - nrm) -> bf16 packed twice:
 //   Wst: rows (b, s) cols t        Wts: rows (b, t) cols s
-__global__ void simple_w_packed_kernel(const float* __restrict__ occ_px, const float* __restrict__ occ_py,
-                                       const float* __restrict__ nrm, const float* __restrict__ am_max,
-                                       const float* __restrict__ lm_max, const float* __restrict__ coef, int B, int S,
-                                       int T, int Spad, int Tpad, uint8_t* __restrict__ Wst,
-                                       uint8_t* __restrict__ Wts) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * Spad * Tpad;
-  if (i >= total) return;
-  const int t = (int)(i % Tpad);
-  const int64_t bs = i / Tpad;
-  const int s = (int)(bs % Spad);
-  const int b = (int)(bs / Spad);
-  float w = 0.f;
-  if (s <= S && t < T) {
-    const int64_t o = ((int64_t)b * (S + 1) + s) * T + t;
-    float g = occ_py[o];
-    if (s < S) g += occ_px[((int64_t)b * S + s) * (T + 1) + t];
-    if (g != 0.f) w = coef[b] * g * expf(am_max[(int64_t)b * T + t] + lm_max[(int64_t)b * (S + 1) + s] - nrm[o]);
+// One CTA per (b, 64 x 64 tile): the tile is computed once (reads coalesced along t), parked in shared memory
+// as bf16 and written out in both orientations as whole 16-byte chunks.
+__global__ void __launch_bounds__(256) simple_w_packed_kernel(const float* __restrict__ occ_px,
+                                                              const float* __restrict__ occ_py,
+                                                              const float* __restrict__ nrm,
+                                                              const float* __restrict__ am_max,
+                                                              const float* __restrict__ lm_max,
+                                                              const float* __restrict__ coef, int B, int S, int T,
+                                                              int Spad, int Tpad, uint8_t* __restrict__ Wst,
+                                                              uint8_t* __restrict__ Wts) {
+  __shared__ __nv_bfloat16 w[64][66];  // odd word stride: column reads are conflict-free
+  const int b = blockIdx.z, s0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // t lane, s lane
+  const float cf = coef[b];
+  const int t = t0 + tx;
+  const float amx = t < T ? am_max[(int64_t)b * T + t] : 0.f;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int sl = ty + 4 * i, s = s0 + sl;
+    float v = 0.f;
+    if (s <= S && t < T) {
+      const int64_t o = ((int64_t)b * (S + 1) + s) * T + t;
+      float g = occ_py[o];
+      if (s < S) g += occ_px[((int64_t)b * S + s) * (T + 1) + t];
+      if (g != 0.f) v = cf * g * expf(amx + lm_max[(int64_t)b * (S + 1) + s] - nrm[o]);
+    }
+    w[sl][tx] = __float2bfloat16(v);
   }
-  const __nv_bfloat16 wb = __float2bfloat16(w);
-  {
-    const int64_t r = (int64_t)b * Spad + s;  // row of Wst, column t
-    uint8_t* blk = Wst + packed_block_index((int)(r >> 7), t >> 6, (int)(((int64_t)B * Spad) >> 7)) * kBlockBytes;
-    *reinterpret_cast<__nv_bfloat16*>(blk + block_elem_offset((int)(r & 127), t & 63)) = wb;
-  }
-  {
-    const int64_t r = (int64_t)b * Tpad + t;  // row of Wts, column s
-    uint8_t* blk = Wts + packed_block_index((int)(r >> 7), s >> 6, (int)(((int64_t)B * Tpad) >> 7)) * kBlockBytes;
-    *reinterpret_cast<__nv_bfloat16*>(blk + block_elem_offset((int)(r & 127), s & 63)) = wb;
+  __syncthreads();
+  // 64 rows x 8 chunks per orientation: two chunks per thread and orientation
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = threadIdx.x + 256 * i;  // 0..511
+    const int row = q >> 3, ck = q & 7;
+    {
+      // Wst: row (b, s0 + row), columns t0 + 8 ck .. + 7
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = *reinterpret_cast<const uint32_t*>(&w[row][ck * 8 + 2 * j]);
+      const int64_t r = (int64_t)b * Spad + s0 + row;
+      uint8_t* blk = Wst + packed_block_index((int)(r >> 7), t0 >> 6, (int)(((int64_t)B * Spad) >> 7)) * kBlockBytes;
+      *reinterpret_cast<uint4*>(blk + block_chunk_offset((int)(r & 127), ck)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    {
+      // Wts: row (b, t0 + row), columns s0 + 8 ck .. + 7 (a column of the tile)
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint16_t lo = *reinterpret_cast<const uint16_t*>(&w[ck * 8 + 2 * j][row]);
+        const uint16_t hi = *reinterpret_cast<const uint16_t*>(&w[ck * 8 + 2 * j + 1][row]);
+        o[j] = (uint32_t)lo | ((uint32_t)hi << 16);
+      }
+      const int64_t r = (int64_t)b * Tpad + t0 + row;
+      uint8_t* blk = Wts + packed_block_index((int)(r >> 7), s0 >> 6, (int)(((int64_t)B * Tpad) >> 7)) * kBlockBytes;
+      *reinterpret_cast<uint4*>(blk + block_chunk_offset((int)(r & 127), ck)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -357,10 +384,10 @@ int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, con
   uint8_t* Wst = p; p += d.wst;
   uint8_t* Wts = p;
   {
-    const int64_t total = (int64_t)B * d.Spad * d.Tpad;
     ProfScope prof("simple_w_kernel", stream);
-    simple_w_packed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(occ_px, occ_py, nrm, am_max, lm_max,
-                                                                                coef, B, S, T, d.Spad, d.Tpad, Wst, Wts);
+    const dim3 grid((unsigned)(d.Tpad / 64), (unsigned)(d.Spad / 64), (unsigned)B);
+    simple_w_packed_kernel<<<grid, 256, 0, stream>>>(occ_px, occ_py, nrm, am_max, lm_max, coef, B, S, T, d.Spad, d.Tpad,
+                                                     Wst, Wts);
   }
   if (int rc = check_launch("simple_w_packed_kernel")) return rc;
   // am_p / lm_p = bf16 exp(am - max), exp(lm - max): written by simple_logprobs_tc into the SAME workspace
