@@ -560,69 +560,130 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
       const int v = vb + threadIdx.x * 4;
       if (v >= V) continue;
       for (int i = 0; i <= w_hi - w_lo; ++i) *reinterpret_cast<float4*>(mine + i * kDjCols) = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int t = t0; t < t1; ++t) {
-        const int sbt = sbs[t - t0];
-        const int r_lo = max(0, w_lo - sbt), r_hi = min(R - 1, w_hi - sbt);
-        const int64_t m_base = (bt0 + t) * R;
-        if (r_lo > r_hi || m_base + r_hi < row0 || m_base + r_lo >= row_end) continue;
-        float a[4], dsum[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* arow = am + (bt0 + t) * V + v;
-        if (kVec) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow));
-          a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(arow + j) : 0.f;
-        }
-        for (int rb = r_lo; rb <= r_hi; rb += kRB) {
-          // all loads of up to kRB band slots first, unconditionally (slots outside the band or the chunk read a
-          // valid dummy row and are weighted by 0), so that their latencies overlap
-          uint2 graw[kRB];
-          float l[kRB][4], wgt[kRB];
+      // Common case: the CTA's frames lie inside this row chunk and their band fits one window.  Then every
+      // slot of every frame is live, the dh rows of a frame are R consecutive rows and its lm rows R consecutive
+      // symbol positions: no predicates, no index arithmetic beyond two running pointers.  The loads of frame
+      // t+1 are in flight while frame t is reduced (two register sets used alternately).
+      const bool lean = kVec && R == kRB && s_hi - s_lo < kDjMaxSpan && (bt0 + t0) * R >= row0 &&
+                        (bt0 + t1) * R <= row_end && sbs[t1 - t0 - 1] + R - 1 <= S && sbs[0] >= 0;
+      if (lean) {
+        struct Frame {
+          uint2 g[kRB];
+          float4 l[kRB];
+          float4 a;
+        };
+        const __nv_bfloat16* dhp = dh + ((bt0 + t0) * R - row0) * ld + v;
+        const float* amp = am + (bt0 + t0) * V + v;
+        const float* lmb = lm + (int64_t)b * (S + 1) * V + v;
+        const int64_t frame_stride = (int64_t)R * ld;
+        auto load_frame = [&](Frame& f, int i) {  // i = t - t0
+          const __nv_bfloat16* gp = dhp + i * frame_stride;
+          const float* lp = lmb + (int64_t)sbs[i] * V;
+          f.a = __ldg(reinterpret_cast<const float4*>(amp + (int64_t)i * V));
 #pragma unroll
           for (int q = 0; q < kRB; ++q) {
-            const int r = rb + q;
-            const int64_t m = m_base + r;
-            const bool ok = r <= r_hi && m >= row0 && m < row_end;
-            wgt[q] = ok ? 1.f : 0.f;
-            graw[q] = *reinterpret_cast<const uint2*>(dh + (ok ? (m - row0) * ld : 0) + v);  // ld, v multiples of 4
-            const float* lrow = lm + ((int64_t)b * (S + 1) + (ok ? sbt + r : 0)) * V + v;
-            if (kVec) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
-              l[q][0] = t4.x; l[q][1] = t4.y; l[q][2] = t4.z; l[q][3] = t4.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) l[q][j] = (v + j < V) ? __ldg(lrow + j) : 0.f;
-            }
+            f.g[q] = *reinterpret_cast<const uint2*>(gp + (int64_t)q * ld);
+            f.l[q] = __ldg(reinterpret_cast<const float4*>(lp + (int64_t)q * V));
           }
+        };
+        auto reduce_frame = [&](const Frame& f, int i) {
+          float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+          float* cell0 = mine + (sbs[i] - w_lo) * kDjCols;
 #pragma unroll
           for (int q = 0; q < kRB; ++q) {
-            const int r = min(rb + q, r_hi);  // a clamped duplicate slot adds 0
-            const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&graw[q]);
-            float4* cell = reinterpret_cast<float4*>(mine + (sbt + r - w_lo) * kDjCols);  // sbt + r in [w_lo, w_hi]
+            float4* cell = reinterpret_cast<float4*>(cell0 + q * kDjCols);
             float4 c = *cell;
-            float x[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              x[j] = wgt[q] * __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[q][j], act);
-              dsum[j] += x[j];
-            }
-            c.x += x[0]; c.y += x[1]; c.z += x[2]; c.w += x[3];
+            const float x0 = __uint_as_float(f.g[q].x << 16) * act_bwd_fast(f.a.x + f.l[q].x, act);
+            const float x1 = __uint_as_float(f.g[q].x & 0xffff0000u) * act_bwd_fast(f.a.y + f.l[q].y, act);
+            const float x2 = __uint_as_float(f.g[q].y << 16) * act_bwd_fast(f.a.z + f.l[q].z, act);
+            const float x3 = __uint_as_float(f.g[q].y & 0xffff0000u) * act_bwd_fast(f.a.w + f.l[q].w, act);
+            ds.x += x0; ds.y += x1; ds.z += x2; ds.w += x3;
+            c.x += x0; c.y += x1; c.z += x2; c.w += x3;
             *cell = c;
           }
-        }
-        float* drow = d_am + (bt0 + t) * V + v;
-        if (kVec) {
-          float4 o = make_float4(dsum[0], dsum[1], dsum[2], dsum[3]);
-          if (am_accumulate || w_lo > s_lo) {  // later windows add to what the first one stored
+          float* drow = d_am + (bt0 + t0 + i) * V + v;
+          if (am_accumulate) {
             const float4 old = *reinterpret_cast<float4*>(drow);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            ds.x += old.x; ds.y += old.y; ds.z += old.z; ds.w += old.w;
           }
-          *reinterpret_cast<float4*>(drow) = o;
-        } else {
+          *reinterpret_cast<float4*>(drow) = ds;
+        };
+        const int nf = t1 - t0;
+        Frame fa, fb;
+        load_frame(fa, 0);
+        for (int i = 0; i < nf; i += 2) {
+          if (i + 1 < nf) load_frame(fb, i + 1);
+          reduce_frame(fa, i);
+          if (i + 1 < nf) {
+            if (i + 2 < nf) load_frame(fa, i + 2);
+            reduce_frame(fb, i + 1);
+          }
+        }
+      } else {
+      for (int t = t0; t < t1; ++t) {
+          const int sbt = sbs[t - t0];
+          const int r_lo = max(0, w_lo - sbt), r_hi = min(R - 1, w_hi - sbt);
+          const int64_t m_base = (bt0 + t) * R;
+          if (r_lo > r_hi || m_base + r_hi < row0 || m_base + r_lo >= row_end) continue;
+          float a[4], dsum[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* arow = am + (bt0 + t) * V + v;
+          if (kVec) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow));
+            a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (v + j < V) drow[j] = ((am_accumulate || w_lo > s_lo) ? drow[j] : 0.f) + dsum[j];
+            for (int j = 0; j < 4; ++j) a[j] = (v + j < V) ? __ldg(arow + j) : 0.f;
+          }
+          for (int rb = r_lo; rb <= r_hi; rb += kRB) {
+            // all loads of up to kRB band slots first, unconditionally (slots outside the band or the chunk read a
+            // valid dummy row and are weighted by 0), so that their latencies overlap
+            uint2 graw[kRB];
+            float l[kRB][4], wgt[kRB];
+#pragma unroll
+            for (int q = 0; q < kRB; ++q) {
+              const int r = rb + q;
+              const int64_t m = m_base + r;
+              const bool ok = r <= r_hi && m >= row0 && m < row_end;
+              wgt[q] = ok ? 1.f : 0.f;
+              graw[q] = *reinterpret_cast<const uint2*>(dh + (ok ? (m - row0) * ld : 0) + v);  // ld, v multiples of 4
+              const float* lrow = lm + ((int64_t)b * (S + 1) + (ok ? sbt + r : 0)) * V + v;
+              if (kVec) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(lrow));
+                l[q][0] = t4.x; l[q][1] = t4.y; l[q][2] = t4.z; l[q][3] = t4.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) l[q][j] = (v + j < V) ? __ldg(lrow + j) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < kRB; ++q) {
+              const int r = min(rb + q, r_hi);  // a clamped duplicate slot adds 0
+              const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(&graw[q]);
+              float4* cell = reinterpret_cast<float4*>(mine + (sbt + r - w_lo) * kDjCols);  // sbt + r in [w_lo, w_hi]
+              float4 c = *cell;
+              float x[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                x[j] = wgt[q] * __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[q][j], act);
+                dsum[j] += x[j];
+              }
+              c.x += x[0]; c.y += x[1]; c.z += x[2]; c.w += x[3];
+              *cell = c;
+            }
+          }
+          float* drow = d_am + (bt0 + t) * V + v;
+          if (kVec) {
+            float4 o = make_float4(dsum[0], dsum[1], dsum[2], dsum[3]);
+            if (am_accumulate || w_lo > s_lo) {  // later windows add to what the first one stored
+              const float4 old = *reinterpret_cast<float4*>(drow);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(drow) = o;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (v + j < V) drow[j] = ((am_accumulate || w_lo > s_lo) ? drow[j] : 0.f) + dsum[j];
+          }
         }
       }
       for (int i = 0; i <= w_hi - w_lo; ++i) {
