@@ -32,6 +32,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // instead of once per 256 output columns.)
 constexpr int kBN = 256;
 constexpr int kNStages = 4;   // 192 KB ring
+constexpr int kLseGroups = S2T_BULK_EPI_GROUPS;  // epilogue groups of the (bulk-fed) logits -> LSE kernel
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -412,6 +413,7 @@ __global__ void lse_combine_kernel(const float* __restrict__ part, const float* 
 // G = coef * clip(occ_px [v == sym] + occ_py [v == blank] - (occ_px + occ_py) softmax) for a row chunk
 struct GradEpi {
   static constexpr int kScratchBytes = kTransposeScratchBytes;
+  static constexpr int kBulkGroups = 2;  // needs > 96 registers per thread: two groups (384 threads), not four
   const float* b2;
   const int* row_sym;
   const float* lse;
@@ -751,7 +753,7 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.kbV = (V + 63) / 64;
   d.kbI = d.Ip / 64;
   d.n_tiles_v = d.Vp / kBN;
-  d.n_parts_v = 2 * d.n_tiles_v;  // the logits kernel is bulk-fed: two epilogue groups per tile
+  d.n_parts_v = kLseGroups * d.n_tiles_v;  // one partial per (column tile, epilogue group)
   const size_t budget = (size_t)1 << 30;  // bytes of one orientation of the chunk's G
   int64_t rows = (int64_t)(budget / ((size_t)d.Vp * 2));
   if (const char* e = getenv("S2T_B200_CHUNK_ROWS")) rows = atoll(e);  // test hook: force the multi-chunk backward

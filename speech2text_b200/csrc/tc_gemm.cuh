@@ -82,15 +82,27 @@ constexpr int kProdWarps = 8;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kGroupBytes = 64 * 128;  // one MN-major group: 64 k-rows x 64 elements
 
+#ifndef S2T_BULK_EPI_GROUPS
+#define S2T_BULK_EPI_GROUPS 4
+#endif
 // Epilogue groups: kernels fed purely by bulk copies have no producer warps and spend the thread
 // budget on a second epilogue group (each group drains half of the accumulator columns).
-template <class ASrc>
+// An epilogue functor may ask for fewer groups (static constexpr int kBulkGroups) when it needs the registers.
+template <class Epi, class = void>
+struct EpiBulkGroups {
+  static constexpr int value = S2T_BULK_EPI_GROUPS;
+};
+template <class Epi>
+struct EpiBulkGroups<Epi, decltype((void)Epi::kBulkGroups)> {
+  static constexpr int value = Epi::kBulkGroups;
+};
+template <class ASrc, class Epi>
 constexpr int gemm_epi_groups() {
-  return ASrc::kBulk ? 2 : 1;
+  return ASrc::kBulk ? EpiBulkGroups<Epi>::value : 1;
 }
-template <class ASrc>
+template <class ASrc, class Epi>
 constexpr int gemm_threads() {
-  return 32 * (kCtrlWarps + kEpiWarps * gemm_epi_groups<ASrc>() + (ASrc::kBulk ? 0 : kProdWarps));
+  return 32 * (kCtrlWarps + kEpiWarps * gemm_epi_groups<ASrc, Epi>() + (ASrc::kBulk ? 0 : kProdWarps));
 }
 
 // kKind: 0 = bf16 operands; 1 = tf32 (fp32 in smem, single pass); 2 = 3xTF32: every fp32 operand is held
@@ -101,9 +113,20 @@ constexpr int gemm_stage_bytes() {
   return (kKind == 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
 }
 template <int BN, int kStages, int kKind, class ASrc, class Epi>
+constexpr size_t gemm_stream_smem_bytes_for(int stages) {
+  return (size_t)stages * gemm_stage_bytes<BN, kKind>() +
+         (size_t)gemm_epi_groups<ASrc, Epi>() * (((Epi::kScratchBytes + 127) / 128) * 128) + 1024 /*align*/ + 256 /*barriers*/;
+}
+// ring depth actually used: the requested one, less when the epilogue scratch of all groups would not fit
+template <int BN, int kStages, int kKind, class ASrc, class Epi>
+constexpr int gemm_eff_stages() {
+  int s = kStages;
+  while (s > 2 && gemm_stream_smem_bytes_for<BN, kStages, kKind, ASrc, Epi>(s) > 227 * 1024) --s;
+  return s;
+}
+template <int BN, int kStages, int kKind, class ASrc, class Epi>
 constexpr size_t gemm_stream_smem_bytes() {
-  return (size_t)kStages * gemm_stage_bytes<BN, kKind>() +
-         (size_t)gemm_epi_groups<ASrc>() * (((Epi::kScratchBytes + 127) / 128) * 128) + 1024 /*align*/ + 256 /*barriers*/;
+  return gemm_stream_smem_bytes_for<BN, kStages, kKind, ASrc, Epi>(gemm_eff_stages<BN, kStages, kKind, ASrc, Epi>());
 }
 
 // MN-major smem descriptor: 8-row (K) groups 1024 B apart, 64-element (MN) groups lbo_bytes apart
@@ -161,17 +184,18 @@ struct TileCoord {
 // two TMEM accumulator buffers run across tile boundaries: while the epilogue warps drain tile i
 // from one TMEM buffer, the MMA warp already accumulates tile i+1 into the other and the copy /
 // producer warps fill the ring for it.
-template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
-__global__ void __launch_bounds__(gemm_threads<ASrc>(), 1)
+template <int BN, int kStagesReq, bool kMn, int kKind, class ASrc, class Epi>
+__global__ void __launch_bounds__(gemm_threads<ASrc, Epi>(), 1)
 gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                    int batches, int k_steps, int k_splits, Epi epi, MnDebug mn) {
   static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
+  constexpr int kStages = gemm_eff_stages<BN, kStagesReq, kKind, ASrc, Epi>();
   constexpr int kParts = kKind == 2 ? 2 : 1;
   constexpr int kABytes = kParts * kBlockBytes;
   constexpr int kBPart = (BN / 128) * kBlockBytes;
   constexpr int kBBytes = kParts * kBPart;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kGroups = gemm_epi_groups<ASrc>();
+  constexpr int kGroups = gemm_epi_groups<ASrc, Epi>();
   constexpr int kScratch = ((Epi::kScratchBytes + 127) / 128) * 128;  // per epilogue group
   constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
   static_assert(kKind != 2 || !ASrc::kBulk, "3xTF32 expects an on-the-fly A producer that writes big|small");
@@ -426,7 +450,7 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
     mn.dbg = dbg;
   }
   ProfScope prof(what, stream);
-  kern<<<grid, gemm_threads<ASrc>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
+  kern<<<grid, gemm_threads<ASrc, Epi>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
                                                      k_splits, epi, mn);
   return check_launch(what);
 }
