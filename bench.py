@@ -237,7 +237,20 @@ def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None)
                        f"{steps} steps after {warmup} warm-up, {sec:.2f} s/step"), sec
 
 
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else this process (or NCCL's version banner,
+    which is written to fd 1 from C) prints is diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -274,7 +287,7 @@ def main():
                 "data": "synthetic", "config": config, "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "utt/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ----------------------------------------------------------------------------- our arm
@@ -459,7 +472,7 @@ def main():
             line["cpu_baseline"] = base
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
