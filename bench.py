@@ -37,8 +37,12 @@ METRIC = "pruned RNN-T loss fwd+bwd utterances/sec"
 WORKLOADS = {
     "c1": dict(B=4, T=327, U=123, V=128, D=256, R=5, I=0, act="relu",
                desc="zipformer_stateless_pruned_rnnt.yaml joiner, sample_data-shaped lengths"),
+    "c2": dict(B=32, T=250, U=50, V=500, D=512, R=-1, I=256, act="tanh",
+               desc="vanilla Rnnt full-lattice loss, synthetic B=32 T=250 U=50 V=500 joiner D=512"),
     "c3": dict(B=64, T=400, U=100, V=500, D=512, R=5, I=256, act="tanh",
                desc="pruned RNN-T prune_range=5, synthetic B=64 T=400 U=100 V=500 D=512"),
+    "c4": dict(B=128, T=500, U=100, V=2000, D=512, R=5, I=256, act="tanh",
+               desc="CTC_Hybrid_Rnnt, the pruned RNN-T half: B=128 T=500 U=100 V=2000 D=512 prune_range=5"),
     "c5": dict(B=256, T=1000, U=250, V=5000, D=1024, R=5, I=256, act="tanh",
                desc="large-vocab pruned RNN-T V=5000 D=1024 prune_range=5, B=256/GPU"),
 }
@@ -82,12 +86,20 @@ def build_modules(cfg, device, mode: str):
     joiner = Joiner(JoinerConfig(input_dim=cfg["D"], output_dim=cfg["V"], inner_dim=max(cfg["I"], 1),
                                  activation=cfg["act"], prune_range=cfg["R"],
                                  use_out_project=cfg["I"] > 0)).to(device)
-    loss = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
+    if cfg["R"] > 0:
+        loss = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
+    else:
+        loss = Loss({"model": "Rnnt", "config": {"blank_label": 0, "clamp": -1, "reduction": "mean"}})
     return joiner, loss
 
 
 def hot_path_step(joiner, loss_mod, enc, t_len, pred, s_len, labels):
     """rnnt_task.py:469-499 through the reference-facing module API."""
+    if joiner.prune_range <= 0:  # vanilla full-lattice loss (rnnt_task.py:326-339)
+        logits, _, _, _ = joiner(enc, t_len, pred, s_len)
+        total = loss_mod({"logits": logits, "logits_length": t_len, "targets": labels, "targets_length": s_len})
+        total.backward()
+        return total, total.detach(), total.detach()
     logits, boundary, ranges, simple = joiner(enc, t_len, pred, s_len, labels)
     pruned = loss_mod({"logits": logits, "logits_length": t_len, "targets": labels, "targets_length": s_len,
                        "boundary": boundary, "ranges": ranges})
@@ -220,6 +232,10 @@ def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None)
         w = {k: v.clone().float().requires_grad_(True) for k, v in joiner_state.items()}
         e = enc.clone().requires_grad_(True)
         p = pred.clone().requires_grad_(True)
+        if cfg["R"] <= 0:
+            logits, _, _, _ = port.joiner_forward(w, jc, e, t_len, p, s_len, None)
+            port.rnnt_loss(logits, labels, t_len, s_len).backward()
+            return
         logits, boundary, ranges, simple = port.joiner_forward(w, jc, e, t_len, p, s_len, labels)
         pruned = port.pruned_rnnt_loss(logits, labels, boundary, ranges)
         (0.5 * simple + 0.5 * pruned).backward()

@@ -476,3 +476,63 @@ def test_graphed_step_replays_the_eager_step(monkeypatch):
     eager2 = step().detach()
     torch.cuda.synchronize()
     assert rel_err(out2, eager2) < 1e-6
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", (LOSS_RTOL, GRAD_RTOL)), ("bf16", (BF16_RTOL, 2 * BF16_RTOL))])
+def test_vanilla_full_size_c2_matches_torchaudio(mode, tol, monkeypatch):
+    """BASELINE config 2 (vanilla full-lattice RNN-T, B=32 T=250 U=50 V=500 D=512): the fused joiner + loss against
+    torchaudio's compiled rnnt_loss (the reference's vanilla back end, rnnt_loss.py:42-44) on the logits the
+    reference's joiner ops produce from the same weights."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    B, T, U, V, D, I = 32, 250, 50, 500, 512, 256
+    g = torch.Generator().manual_seed(21)
+    enc0 = torch.randn(B, T, D, generator=g) * 0.5
+    pred0 = torch.randn(B, U + 1, D, generator=g) * 0.5
+    tgt = torch.randint(1, V, (B, U), generator=g)
+    t_len = torch.randint(int(0.6 * T), T + 1, (B,), generator=g)
+    s_len = torch.clamp((t_len.float() * U / T * 0.9).long(), 1, U)
+    t_len[0], s_len[0] = T, U
+    torch.manual_seed(5)
+    joiner = Joiner(JoinerConfig(input_dim=D, output_dim=V, inner_dim=I, activation="tanh", prune_range=-1,
+                                 use_out_project=True)).to(_dev())
+    # reference chain in plain torch on the GPU (projections, add, tanh, out-projection), torchaudio loss on the CPU
+    enc_r = enc0.to(_dev()).requires_grad_(True)
+    pred_r = pred0.to(_dev()).requires_grad_(True)
+    am = joiner._enc_proj(enc_r).unsqueeze(2)
+    lm = joiner._pre_proj(pred_r).unsqueeze(1)
+    logits = joiner._out_projection(torch.tanh(am + lm))
+    # torchaudio's fp32 recursion carries ~1e-3 relative noise in the gradients at |log P| ~ 1500: it pins the loss;
+    # the gradient reference is the oracle's k2 restatement run in fp64 with a range that covers the lattice
+    logits_cpu = logits.detach().cpu().double().requires_grad_(True)
+    ta = torchaudio.functional.rnnt_loss(logits_cpu.detach().float(), tgt.int(), t_len.int(), s_len.int(), blank=0,
+                                         clamp=-1, reduction="mean")
+    from oracle import k2_shim
+    bnd = torch.zeros(B, 4, dtype=torch.int64)
+    bnd[:, 2], bnd[:, 3] = s_len, t_len
+    full = torch.arange(U + 1).expand(B, T, U + 1).contiguous()
+    ref = k2_shim.rnnt_loss_pruned(logits_cpu, tgt, full, 0, bnd, reduction="mean")
+    assert rel_err(ref, ta) < LOSS_RTOL
+    ref.backward()
+    logits.backward(logits_cpu.grad.float().to(_dev()))
+    ref_grads = {"d_enc": enc_r.grad.clone(), "d_pred": pred_r.grad.clone(),
+                 **{"d" + k: p.grad.clone() for k, p in joiner.named_parameters()}}
+    joiner.zero_grad(set_to_none=True)
+    del logits, am, lm
+    # the drop-in path
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", mode)
+    enc = enc0.to(_dev()).requires_grad_(True)
+    pred = pred0.to(_dev()).requires_grad_(True)
+    loss_mod = Loss({"model": "Rnnt", "config": {"blank_label": 0, "clamp": -1, "reduction": "mean"}})
+    out, boundary, ranges, simple = joiner(enc, t_len.to(_dev()), pred, s_len.to(_dev()))
+    assert boundary is None and ranges is None and simple is None and tuple(out.shape) == (B, T, U + 1, V)
+    loss = loss_mod({"logits": out, "logits_length": t_len.to(_dev()), "targets": tgt.to(_dev()),
+                     "targets_length": s_len.to(_dev())})
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(loss, ref) < tol[0]
+    got = {"d_enc": enc.grad, "d_pred": pred.grad, **{"d" + k: p.grad for k, p in joiner.named_parameters()}}
+    for k, v in ref_grads.items():
+        assert rel_err(got[k], v) < tol[1], k
