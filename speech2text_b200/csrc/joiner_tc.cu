@@ -24,6 +24,9 @@ namespace {
 
 using namespace tc;
 
+// K-major contractions run as 2-CTA clusters: the B operand of a stage is loaded half by each CTA and multicast
+constexpr int kPair = 1;  // 2 (B multicast across a CTA pair) measured equal within noise on the same box: L2 reads are not what bounds the ring
+
 constexpr float kLog2e = 1.4426950408889634f;
 
 // CTA tile width (columns of the TMEM accumulator) and smem ring depth of the joiner contractions.
@@ -154,7 +157,7 @@ struct JointRowProducer {
       joint_load_quad(q1, am, lm, ar[1], lr[1], v, V, vec);
       pc.wait_empty(it);
       uint8_t* dst = pc.stage(it) + off;
-      uint8_t* jdst = (Jp != nullptr && pc.n_tile == 0)
+      uint8_t* jdst = (Jp != nullptr && pc.n_tile == 0 && pc.valid)
                           ? Jp + packed_block_index(pc.m_tile, pc.ks0 + it, j_row_blocks) * kBlockBytes + off
                           : nullptr;
 #pragma unroll
@@ -860,12 +863,12 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
       }
       if (int rc = check_launch("joint_pack_kernel")) return rc;
       BulkA a{w.Jp, d.Mt};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
                                                                "tc_joiner_hidden_gemm"))
         return rc;
     } else {
       JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act, nullptr, d.Mt};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
                                                                "tc_joiner_hidden_gemm"))
         return rc;
     }
@@ -874,7 +877,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     BulkA a{w.Hp, d.Mt};
     LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_parts_v, M, w.part, w.sym_logit, w.blank_logit};
-    if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
+    if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                    "tc_joiner_logits_lse_gemm"))
       return rc;
   }
@@ -905,7 +908,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                      "tc_joiner_grad_logits_gemm"))
         return rc;
     }
@@ -913,7 +916,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Gp, ct};
       DHiddenEpi ep{p.I, w.DHp, ct, db1};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / kBN, d.kbV, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / kBN, d.kbV, 1, ep, stream,
                                                      "tc_joiner_dhidden_gemm"))
         return rc;
     }
@@ -946,7 +949,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       StoreRowsBf16Epi ep{w.dh, d.Vp};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
                                                                "tc_joiner_dh_gemm"))
         return rc;
       const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;

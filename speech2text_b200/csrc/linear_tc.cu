@@ -17,6 +17,9 @@ namespace {
 
 using namespace tc;
 
+// K-major contractions run as 2-CTA clusters: the B operand of a stage is loaded half by each CTA and multicast
+constexpr int kPair = 1;  // 2 (B multicast across a CTA pair) measured equal within noise on the same box: L2 reads are not what bounds the ring
+
 struct LinDims {
   int Mt, Np, Kp;       // row tiles of x; N, K padded to multiples of 256
   size_t px, pw, pdy, pwt;  // bf16 pack(x), fp32 pack(W), bf16 pack(dy), bf16 pack(W^T)
@@ -71,7 +74,7 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
   tc::StoreRowMajorEpi ep{y, N, (int)M, N, false, b};
   tc::MnDebug extra;
   extra.b_small = pw_small;
-  return tc::launch_gemm_stream<256, 2, false, 2>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 31) / 32, 1, ep, st,
+  return tc::launch_gemm_stream<256, 2, false, 2, kPair>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 31) / 32, 1, ep, st,
                                                   "tc_linear_fwd_gemm_3xtf32", extra);
 }
 
@@ -90,7 +93,7 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
   if (dx) {
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dx, K, (int)M, K, false, nullptr};
-    if (int rc = tc::launch_gemm_stream<256, 4, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
+    if (int rc = tc::launch_gemm_stream<256, 4, false, 0, kPair>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
                                                        "tc_linear_dx_gemm"))
       return rc;
   }

@@ -21,6 +21,9 @@ namespace {
 
 using namespace tc;
 
+// K-major contractions run as 2-CTA clusters: the B operand of a stage is loaded half by each CTA and multicast
+constexpr int kPair = 1;  // 2 (B multicast across a CTA pair) measured equal within noise on the same box: L2 reads are not what bounds the ring
+
 // one warp per row: max over V.  For the lm rows (info != nullptr) lane 0 also records what the
 // normaliser epilogue needs per symbol position: {max, lm[blank], lm[sym[b, s]]} as one 16-byte record.
 __global__ void tc_row_max_kernel(const float* __restrict__ x, int64_t rows, int V, float* __restrict__ out,
@@ -58,7 +61,7 @@ struct ExpRowProducerF32 {
     const int warp = pc.t >> 5, lane = pc.t & 31;
     const int c = lane & 7, rbase = warp * 4 + (lane >> 3);
     const bool vec = ((V & 3) == 0);
-    const bool emit = bf16_pack != nullptr && pc.n_tile == 0;
+    const bool emit = bf16_pack != nullptr && pc.n_tile == 0 && pc.valid;
     const float* rowp[4];
     float sub[4];
     bool live[4];
@@ -362,7 +365,7 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   MnDebug extra;
   extra.b_small = lm_small;
   extra.b_batch_off = d.Spad / 128;
-  if (int rc = launch_gemm_stream<128, 3, false, 2>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32, 1,
+  if (int rc = launch_gemm_stream<128, 3, false, 2, kPair>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32, 1,
                                                     ep, stream, "tc_simple_normaliser_gemm_3xtf32", extra, B))
     return rc;
   const int64_t total = (int64_t)B * S * (T + 1);

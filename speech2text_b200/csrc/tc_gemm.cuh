@@ -155,6 +155,7 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
 // What an on-the-fly A producer sees for one tile: kProdThreads threads fill stage(it) for it in [0, n_it).
 struct ProdCtx {
   int m_tile, n_tile, batch, ks0, n_it;
+  bool valid;  // false: row tile past the end (odd CTA of a cluster): fill zeros, write no by-product
   int t;  // producer thread index, 0 .. kProdThreads-1
   uint8_t* smem;
   int stage_bytes, stages;
@@ -177,6 +178,7 @@ struct ProdCtx {
 
 struct TileCoord {
   int n_tile, m_tile, batch, split, ks0, n_it;
+  bool valid;  // false: the odd CTA of a cluster past the last row tile (runs the protocol, produces nothing)
 };
 
 // Persistent, warp-specialised contraction kernel: one CTA per SM loops over output tiles
@@ -184,7 +186,10 @@ struct TileCoord {
 // two TMEM accumulator buffers run across tile boundaries: while the epilogue warps drain tile i
 // from one TMEM buffer, the MMA warp already accumulates tile i+1 into the other and the copy /
 // producer warps fill the ring for it.
-template <int BN, int kStagesReq, bool kMn, int kKind, class ASrc, class Epi>
+// kCluster = 2: the two CTAs of a cluster work on neighbouring row tiles of the same column tile and k range; each
+// loads half of every B stage and multicasts it into both shared memories, so the B operand crosses L2 -> SM
+// once per CTA pair.  A stage is released only when the MMAs of BOTH CTAs have read it (multicast commit).
+template <int BN, int kStagesReq, bool kMn, int kKind, class ASrc, class Epi, int kCluster = 1>
 __global__ void __launch_bounds__(gemm_threads<ASrc, Epi>(), 1)
 gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                    int batches, int k_steps, int k_splits, Epi epi, MnDebug mn) {
@@ -210,15 +215,22 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  static_assert(kCluster == 1 || kCluster == 2, "clusters of one or two CTAs");
+  static_assert(kCluster == 1 || !kMn, "B multicast is built for K-major operands");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = n_tiles * m_tiles * batches * k_splits;
+  const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
+  const int first_tile = blockIdx.x / kCluster, tile_stride = gridDim.x / kCluster;
+  const int m_groups = (m_tiles + kCluster - 1) / kCluster;
+  const int num_tiles = n_tiles * m_groups * batches * k_splits;
   const int per = (k_steps + k_splits - 1) / k_splits;
+  constexpr uint16_t kCtaMask = (1u << kCluster) - 1;
   auto decode = [&](int tile) {
     TileCoord c;
     c.n_tile = tile % n_tiles;
     int rest = tile / n_tiles;
-    c.m_tile = rest % m_tiles;
-    rest /= m_tiles;
+    c.m_tile = (rest % m_groups) * kCluster + crank;
+    c.valid = c.m_tile < m_tiles;
+    rest /= m_groups;
     c.split = rest % k_splits;
     c.batch = rest / k_splits;
     c.ks0 = c.split * per;
@@ -229,7 +241,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + kProdWarps);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], kCluster);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -240,6 +252,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -247,7 +260,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     // ---------------- bulk-copy issuer ----------------
     if (lane == 0) {
       uint32_t git = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const TileCoord c = decode(tile);
         for (int it = 0; it < c.n_it; ++it, ++git) {
           const int s = git % kStages, ks = c.ks0 + it;
@@ -257,15 +270,22 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
           mbar_arrive_expect_tx(&full[s], (ASrc::kBulk ? kABytes : 0) + kBBytes);
           if constexpr (!kMn) {
             if constexpr (ASrc::kBulk) {
-              bulk_copy_g2s(sa,
-                            asrc.packed + packed_block_index(c.m_tile + c.batch * mn.a_batch_off, ks, asrc.row_blocks) *
-                                              kBlockBytes,
+              const int mt = c.valid ? c.m_tile : m_tiles - 1;  // keep the byte count; the result is discarded
+              bulk_copy_g2s(sa, asrc.packed + packed_block_index(mt + c.batch * mn.a_batch_off, ks, asrc.row_blocks) * kBlockBytes,
                             kABytes, &full[s]);
             }
             const size_t boff =
                 packed_block_index(c.n_tile * (BN / 128) + c.batch * mn.b_batch_off, ks, b_row_blocks) * kBlockBytes;
-            bulk_copy_g2s(sb, b_packed + boff, kBPart, &full[s]);
-            if constexpr (kKind == 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
+            if constexpr (kCluster == 1) {
+              bulk_copy_g2s(sb, b_packed + boff, kBPart, &full[s]);
+              if constexpr (kKind == 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
+            } else {
+              constexpr int kShare = kBPart / kCluster;  // this CTA's share of the stage, delivered to every CTA
+              const size_t off = (size_t)crank * kShare;
+              bulk_copy_g2s_multicast(sb + off, b_packed + boff + off, kShare, &full[s], kCtaMask);
+              if constexpr (kKind == 2)
+                bulk_copy_g2s_multicast(sb + kBPart + off, mn.b_small + boff + off, kShare, &full[s], kCtaMask);
+            }
           } else {
             // k-step = 64 contraction rows = half of a 128-row block; group = 64 columns = one column block
             if constexpr (ASrc::kBulk) {
@@ -296,7 +316,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       uint32_t idesc = kKind == 0 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
       if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       uint32_t git = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const TileCoord c = decode(tile);
         if (c.n_it <= 0) continue;
         const uint32_t buf = lt & 1;
@@ -336,7 +356,8 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
               }
             }
           }
-          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          if constexpr (kCluster == 1) umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          else umma_commit_multicast(&empty[s], kCtaMask);    // ... in both CTAs: the peer multicasts into it
         }
         umma_commit(&tfull[buf]);
         ++lt;
@@ -348,7 +369,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     const int group = (warp - kCtrlWarps) / kEpiWarps;
     constexpr int kCols = BN / kGroups;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
       const TileCoord c = decode(tile);
       if (c.n_it <= 0) continue;
       const uint32_t buf = lt & 1;
@@ -369,15 +390,17 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       ctx.scratch = scratch + group * kScratch;
       ctx.scratch_bytes = kScratch;
       ctx.dbg = mn.dbg;
-      typename Epi::State st;
-      epi.begin(st, ctx);
+      if (c.valid) {
+        typename Epi::State st;
+        epi.begin(st, ctx);
 #pragma unroll 1
-      for (int cc = 0; cc < kCols / 32; ++cc) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + group * kCols + cc * 32, v);
-        if (!(mn.dbg & 1)) epi.chunk(st, ctx, ctx.col0 + cc * 32, v);
+        for (int cc = 0; cc < kCols / 32; ++cc) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + group * kCols + cc * 32, v);
+          if (!(mn.dbg & 1)) epi.chunk(st, ctx, ctx.col0 + cc * 32, v);
+        }
+        epi.end(st, ctx);
       }
-      epi.end(st, ctx);
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
       ++lt;
@@ -386,11 +409,12 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     // ---------------- on-the-fly A producers ----------------
     if constexpr (!ASrc::kBulk) {
       uint32_t git = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const TileCoord c = decode(tile);
         if (c.n_it <= 0) continue;
         ProdCtx pc;
         pc.m_tile = c.m_tile;
+        pc.valid = c.valid;
         pc.n_tile = c.n_tile;
         pc.batch = c.batch;
         pc.ks0 = c.ks0;
@@ -409,6 +433,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();  // nobody leaves while the peer may still signal or multicast
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
@@ -423,14 +448,14 @@ inline int gemm_sm_count() {
   return sms;
 }
 
-template <int BN, int kStages, bool kMn, int kKind, class ASrc, class Epi>
+template <int BN, int kStages, bool kMn, int kKind, int kCluster = 1, class ASrc, class Epi>
 int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                        int k_steps, int k_splits, const Epi& epi, cudaStream_t stream, const char* what,
                        MnDebug mn = MnDebug(), int batches = 1) {
   if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0 || batches <= 0) return 0;
   if (k_splits < 1) k_splits = 1;
   if (k_splits > k_steps) k_splits = k_steps;
-  auto kern = gemm_stream_kernel<BN, kStages, kMn, kKind, ASrc, Epi>;
+  auto kern = gemm_stream_kernel<BN, kStages, kMn, kKind, ASrc, Epi, kCluster>;
   constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, kKind, ASrc, Epi>();
   static_assert(smem <= 227 * 1024, "stage ring + epilogue scratch exceed the 227 KB of one CTA");
   static bool configured = false;
@@ -442,16 +467,38 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
     }
     configured = true;
   }
-  const long long tiles = (long long)m_tiles * n_tiles * batches * k_splits;
-  const int grid = (int)(tiles < gemm_sm_count() ? tiles : gemm_sm_count());
+  const long long tiles = (long long)((m_tiles + kCluster - 1) / kCluster) * n_tiles * batches * k_splits;  // per cluster
+  const int max_clusters = gemm_sm_count() / kCluster;
+  const int grid = kCluster * (int)(tiles < max_clusters ? tiles : max_clusters);
   {
     static int dbg = -1;
     if (dbg < 0) dbg = getenv("S2T_DBG") ? atoi(getenv("S2T_DBG")) : 0;
     mn.dbg = dbg;
   }
   ProfScope prof(what, stream);
-  kern<<<grid, gemm_threads<ASrc, Epi>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
-                                                     k_splits, epi, mn);
+  if constexpr (kCluster == 1) {
+    kern<<<grid, gemm_threads<ASrc, Epi>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
+                                                            k_splits, epi, mn);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)gemm_threads<ASrc, Epi>());
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps, k_splits,
+                                       epi, mn);
+    if (e != cudaSuccess) {
+      set_error("%s: cluster launch: %s", what, cudaGetErrorString(e));
+      return 2;
+    }
+  }
   return check_launch(what);
 }
 
@@ -618,7 +665,7 @@ struct RowCopyProducerF32 {
   __device__ void run(const ProdCtx& pc) const {
     const int warp = pc.t >> 5, lane = pc.t & 31;
     const int c = lane & 7, rbase = warp * 4 + (lane >> 3);
-    const bool emit = bf16_pack != nullptr && pc.n_tile == 0;
+    const bool emit = bf16_pack != nullptr && pc.n_tile == 0 && pc.valid;
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const float* rowp[4];
     bool live[4];

@@ -306,10 +306,17 @@ extern "C" int s2t_tc_gemm(const float* A, const float* B, float* C, int M, int 
   tc::BulkA a{pa, m_tiles};
   if (k_splits > 1) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
   tc::StoreRowMajorEpi epi{C, N, M, N, k_splits > 1};
+  const bool pair = getenv("S2T_GEMM_CLUSTER") && atoi(getenv("S2T_GEMM_CLUSTER")) == 2;  // 2-CTA clusters, B multicast
   if (bn == 128) {
+    if (pair)
+      return tc::launch_gemm_stream<128, 4, false, 0, 2>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi,
+                                                         st, "tc_gemm_debug_128_pair");
     return tc::launch_gemm_stream<128, 4, false, 0>(a, pb, b_row_blocks, m_tiles, (N + 127) / 128, k_blocks, k_splits, epi, st,
                                           "tc_gemm_debug_128");
   }
+  if (pair)
+    return tc::launch_gemm_stream<256, 4, false, 0, 2>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
+                                                       "tc_gemm_debug_256_pair");
   return tc::launch_gemm_stream<256, 4, false, 0>(a, pb, b_row_blocks, m_tiles, (N + 255) / 256, k_blocks, k_splits, epi, st,
                                         "tc_gemm_debug_256");
 }
