@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed; see speech2text_b200/lib/build.log")
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH, *objs])
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs])
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB_PATH

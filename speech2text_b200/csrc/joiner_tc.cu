@@ -521,7 +521,7 @@ struct StoreRowsBf16Epi {
     pack_row32_bf16(acc, mine);
     const int64_t m0 = (int64_t)ctx.m - (ctx.t & 31);
     warp_transposed_chunk_b16(ctx, mine, [&](int r, int q, uint4 v) {
-      if (!(ctx.dbg & 8) || v.x == 0x12345678u) *reinterpret_cast<uint4*>(out + (m0 + r) * ld + n + q * 8) = v;
+      *reinterpret_cast<uint4*>(out + (m0 + r) * ld + n + q * 8) = v;
     });
   }
 };
