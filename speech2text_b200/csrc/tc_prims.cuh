@@ -215,11 +215,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// round-to-nearest fp32 -> tf32 (the MMA itself would truncate the low 13 mantissa bits: biased)
+// round-to-nearest (ties away from zero) fp32 -> tf32; the MMA itself would truncate the low 13 mantissa bits,
+// which is biased.  Same result as cvt.rna.tf32.f32 for finite values, but two full-rate integer instructions
+// (the cvt issues on a narrow pipe: "math pipe throttle" was the producers' top stall reason in ncu).
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 __device__ __forceinline__ float tanh_fast(float x) {
