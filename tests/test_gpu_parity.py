@@ -536,3 +536,63 @@ def test_vanilla_full_size_c2_matches_torchaudio(mode, tol, monkeypatch):
     got = {"d_enc": enc.grad, "d_pred": pred.grad, **{"d" + k: p.grad for k, p in joiner.named_parameters()}}
     for k, v in ref_grads.items():
         assert rel_err(got[k], v) < tol[1], k
+
+
+ODD_SHAPES = [
+    # B, T, U, V, D, I, R, act
+    (2, 7, 3, 33, 16, 24, 2, "tanh"),        # tiny, V % 4 != 0
+    (3, 50, 20, 130, 64, 96, 5, "relu"),     # V % 4 != 0, I not a multiple of 64
+    (2, 300, 260, 64, 32, 64, 5, "tanh"),    # S + 1 > 256: generic simple lattice
+    (2, 64, 40, 72, 32, 40, 33, "relu"),     # R > 32: generic band lattice, several symbol-position windows
+    (4, 128, 30, 257, 48, 300, 4, "tanh"),   # I > 256 (two 256-column tiles of the hidden layer), odd V
+    (1, 700, 20, 40, 16, 32, 8, "relu"),     # one long utterance
+    (5, 96, 95, 48, 24, 16, 3, "tanh"),      # U close to T: the band moves almost every frame
+]
+
+
+@pytest.mark.parametrize("shape", ODD_SHAPES, ids=lambda s: "x".join(str(v) for v in s))
+def test_bf16_path_agrees_with_fp32_path_on_odd_shapes(shape, monkeypatch):
+    """Shapes that leave the fast paths (odd vocabulary sizes, wide ranges, long transcripts, inner dimensions
+    that need padding): the tensor-core path against the strict-fp32 path of the same library."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    B, T, U, V, D, I, R, act = shape
+    g = torch.Generator().manual_seed(sum(shape[:7]))
+    enc0 = torch.randn(B, T, D, generator=g)
+    pred0 = torch.randn(B, U + 1, D, generator=g)
+    tgt = torch.randint(1, V, (B, U), generator=g)
+    t_len = torch.randint(max(U, int(0.7 * T)), T + 1, (B,), generator=g)
+    t_len[0] = T
+    s_len = torch.minimum(torch.randint(max(1, U // 2), U + 1, (B,), generator=g), t_len)
+    s_len[0] = U
+    torch.manual_seed(3)
+    joiner = Joiner(JoinerConfig(input_dim=D, output_dim=V, inner_dim=I, activation=act, prune_range=R,
+                                 use_out_project=True)).to(_dev())
+    res = {}
+    for mode in ("fp32", "bf16"):
+        monkeypatch.setenv("S2T_B200_FUSED", "1")
+        monkeypatch.setenv("S2T_B200_JOINER_MODE", mode)
+        joiner.zero_grad(set_to_none=True)
+        enc = enc0.to(_dev()).requires_grad_(True)
+        pred = pred0.to(_dev()).requires_grad_(True)
+        loss_mod = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
+        logits, boundary, ranges, simple = joiner(enc, t_len.to(_dev()), pred, s_len.to(_dev()), tgt.to(_dev()))
+        pruned = loss_mod({"logits": logits, "logits_length": t_len.to(_dev()), "targets": tgt.to(_dev()),
+                           "targets_length": s_len.to(_dev()), "boundary": boundary, "ranges": ranges})
+        (0.5 * simple + pruned).backward()
+        torch.cuda.synchronize()
+        res[mode] = dict(simple=simple.detach(), pruned=pruned.detach(), ranges=ranges, d_enc=enc.grad, d_pred=pred.grad,
+                         **{"d" + k: p.grad.clone() for k, p in joiner.named_parameters()})
+    a, b = res["fp32"], res["bf16"]
+    assert torch.isfinite(b["pruned"]).all() and torch.isfinite(b["simple"]).all()
+    assert rel_err(b["simple"], a["simple"]) < 1e-4
+    same = (a["ranges"] == b["ranges"]).all(dim=2).all(dim=1)
+    if bool(same.all()):
+        assert rel_err(b["pruned"], a["pruned"]) < BF16_RTOL
+        for k in a:
+            if k.startswith("d"):
+                assert rel_err(b[k], a[k]) < 3 * BF16_RTOL, k
+    else:  # a near-tie frame picked the neighbouring window: compare what is comparable
+        assert rel_err(b["pruned"], a["pruned"]) < 5 * BF16_RTOL
+        if bool(same.any()):
+            assert rel_err(b["d_enc"][same], a["d_enc"][same]) < 3 * BF16_RTOL
