@@ -35,6 +35,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 // instead of once per 256 output columns.)
 constexpr int kBN = 256;
 constexpr int kNStages = 4;   // 192 KB ring
+// contractions over the inner dimension (K = Ip <= 256: logits, their gradient, dh) keep B resident in shared memory
+constexpr int kResSteps = 4;    // resident k-steps of B: 4 x 32 KB
+constexpr int kNStagesRes = 4;  // A-only ring of 16 KB stages next to it
 constexpr int kLseGroups = S2T_BULK_EPI_GROUPS;  // epilogue groups of the (bulk-fed) logits -> LSE kernel
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -877,8 +880,8 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   {
     BulkA a{w.Hp, d.Mt};
     LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_parts_v, M, w.part, w.sym_logit, w.blank_logit};
-    if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, 1, ep, stream,
-                                                   "tc_joiner_logits_lse_gemm"))
+    if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, ep, stream,
+                                                                     "tc_joiner_logits_lse_gemm"))
       return rc;
   }
   {
@@ -908,8 +911,8 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
-                                                     "tc_joiner_grad_logits_gemm"))
+      if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
+                                                                       "tc_joiner_grad_logits_gemm"))
         return rc;
     }
     // dhidden = G W2: rows m, N = Ip, K = V
@@ -949,8 +952,8 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       StoreRowsBf16Epi ep{w.dh, d.Vp};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, 1, ep, stream,
-                                                               "tc_joiner_dh_gemm"))
+      if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
+                                                                       "tc_joiner_dh_gemm"))
         return rc;
       const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;
       {

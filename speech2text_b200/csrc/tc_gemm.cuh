@@ -112,21 +112,25 @@ template <int BN, int kKind>
 constexpr int gemm_stage_bytes() {
   return (kKind == 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
 }
-template <int BN, int kStages, int kKind, class ASrc, class Epi>
+// kBRes > 0: the B operand of the CTA's column tile (kBRes k-steps) stays resident in shared memory and the ring
+// carries A stages only
+template <int BN, int kStages, int kKind, class ASrc, class Epi, int kBRes = 0>
 constexpr size_t gemm_stream_smem_bytes_for(int stages) {
-  return (size_t)stages * gemm_stage_bytes<BN, kKind>() +
+  return (size_t)stages * (kBRes > 0 ? kBlockBytes : gemm_stage_bytes<BN, kKind>()) +
+         (size_t)kBRes * (BN / 128) * kBlockBytes +
          (size_t)gemm_epi_groups<ASrc, Epi>() * (((Epi::kScratchBytes + 127) / 128) * 128) + 1024 /*align*/ + 256 /*barriers*/;
 }
 // ring depth actually used: the requested one, less when the epilogue scratch of all groups would not fit
-template <int BN, int kStages, int kKind, class ASrc, class Epi>
+template <int BN, int kStages, int kKind, class ASrc, class Epi, int kBRes = 0>
 constexpr int gemm_eff_stages() {
   int s = kStages;
-  while (s > 2 && gemm_stream_smem_bytes_for<BN, kStages, kKind, ASrc, Epi>(s) > 227 * 1024) --s;
+  while (s > 2 && gemm_stream_smem_bytes_for<BN, kStages, kKind, ASrc, Epi, kBRes>(s) > 227 * 1024) --s;
   return s;
 }
-template <int BN, int kStages, int kKind, class ASrc, class Epi>
+template <int BN, int kStages, int kKind, class ASrc, class Epi, int kBRes = 0>
 constexpr size_t gemm_stream_smem_bytes() {
-  return gemm_stream_smem_bytes_for<BN, kStages, kKind, ASrc, Epi>(gemm_eff_stages<BN, kStages, kKind, ASrc, Epi>());
+  return gemm_stream_smem_bytes_for<BN, kStages, kKind, ASrc, Epi, kBRes>(
+      gemm_eff_stages<BN, kStages, kKind, ASrc, Epi, kBRes>());
 }
 
 // MN-major smem descriptor: 8-row (K) groups 1024 B apart, 64-element (MN) groups lbo_bytes apart
@@ -189,17 +193,22 @@ struct TileCoord {
 // kCluster = 2: the two CTAs of a cluster work on neighbouring row tiles of the same column tile and k range; each
 // loads half of every B stage and multicasts it into both shared memories, so the B operand crosses L2 -> SM
 // once per CTA pair.  A stage is released only when the MMAs of BOTH CTAs have read it (multicast commit).
-template <int BN, int kStagesReq, bool kMn, int kKind, class ASrc, class Epi, int kCluster = 1>
+// kBRes > 0 (B-stationary): a CTA keeps ONE column tile for its whole life, loads that tile's B operand (k_steps <= kBRes
+// k-steps) into shared memory once and streams only A through the ring: a short-K contraction then pulls 16 KB instead
+// of 48 KB per k-step through the L2 -> SM path, which is what bounds the streaming mainloop (profiles/README.md).
+template <int BN, int kStagesReq, bool kMn, int kKind, class ASrc, class Epi, int kCluster = 1, int kBRes = 0>
 __global__ void __launch_bounds__(gemm_threads<ASrc, Epi>(), 1)
 gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                    int batches, int k_steps, int k_splits, Epi epi, MnDebug mn) {
   static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
-  constexpr int kStages = gemm_eff_stages<BN, kStagesReq, kKind, ASrc, Epi>();
+  static_assert(kBRes == 0 || (!kMn && kKind == 0 && ASrc::kBulk && kCluster == 1),
+                "B-stationary mode: K-major bf16, bulk-fed, no cluster");
+  constexpr int kStages = gemm_eff_stages<BN, kStagesReq, kKind, ASrc, Epi, kBRes>();
   constexpr int kParts = kKind == 2 ? 2 : 1;
   constexpr int kABytes = kParts * kBlockBytes;
   constexpr int kBPart = (BN / 128) * kBlockBytes;
   constexpr int kBBytes = kParts * kBPart;
-  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kStageBytes = kBRes > 0 ? kABytes : kABytes + kBBytes;
   constexpr int kGroups = gemm_epi_groups<ASrc, Epi>();
   constexpr int kScratch = ((Epi::kScratchBytes + 127) / 128) * 128;  // per epilogue group
   constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
@@ -208,24 +217,38 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  uint8_t* scratch = smem + kStages * kStageBytes;
+  uint8_t* bres = smem + kStages * kStageBytes;  // resident B (kBRes k-steps), empty in streaming mode
+  uint8_t* scratch = bres + kBRes * kBPart;
   uint64_t* full = reinterpret_cast<uint64_t*>(scratch + kGroups * kScratch);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bres_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
 
   static_assert(kCluster == 1 || kCluster == 2, "clusters of one or two CTAs");
   static_assert(kCluster == 1 || !kMn, "B multicast is built for K-major operands");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
-  const int first_tile = blockIdx.x / kCluster, tile_stride = gridDim.x / kCluster;
+  // streaming: tiles of all (n, m, split, batch), n fastest; B-stationary: the CTA's own column tile, row tiles strided
+  const int first_tile = kBRes > 0 ? (int)blockIdx.x / n_tiles : (int)blockIdx.x / kCluster;
+  const int tile_stride = kBRes > 0 ? (int)gridDim.x / n_tiles : (int)gridDim.x / kCluster;
   const int m_groups = (m_tiles + kCluster - 1) / kCluster;
-  const int num_tiles = n_tiles * m_groups * batches * k_splits;
+  const int num_tiles = kBRes > 0 ? m_tiles : n_tiles * m_groups * batches * k_splits;
   const int per = (k_steps + k_splits - 1) / k_splits;
   constexpr uint16_t kCtaMask = (1u << kCluster) - 1;
   auto decode = [&](int tile) {
     TileCoord c;
+    if constexpr (kBRes > 0) {
+      c.n_tile = (int)blockIdx.x % n_tiles;
+      c.m_tile = tile;
+      c.valid = true;
+      c.split = 0;
+      c.batch = 0;
+      c.ks0 = 0;
+      c.n_it = k_steps;
+      return c;
+    }
     c.n_tile = tile % n_tiles;
     int rest = tile / n_tiles;
     c.m_tile = (rest % m_groups) * kCluster + crank;
@@ -247,6 +270,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 32 * kEpiWarps * kGroups);
     }
+    mbar_init(bres_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -260,6 +284,15 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     // ---------------- bulk-copy issuer ----------------
     if (lane == 0) {
       uint32_t git = 0;
+      if constexpr (kBRes > 0) {
+        if (first_tile < num_tiles) {
+          mbar_arrive_expect_tx(bres_full, (uint32_t)k_steps * kBPart);
+          const int nt = (int)blockIdx.x % n_tiles;
+          for (int ks = 0; ks < k_steps; ++ks)
+            bulk_copy_g2s(bres + ks * kBPart,
+                          b_packed + packed_block_index(nt * (BN / 128), ks, b_row_blocks) * kBlockBytes, kBPart, bres_full);
+        }
+      }
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const TileCoord c = decode(tile);
         for (int it = 0; it < c.n_it; ++it, ++git) {
@@ -267,6 +300,11 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
           mbar_wait(&empty[s], ((git / kStages) & 1) ^ 1);
           uint8_t* sa = smem + s * kStageBytes;
           uint8_t* sb = sa + kABytes;
+          if constexpr (kBRes > 0) {
+            mbar_arrive_expect_tx(&full[s], kABytes);
+            bulk_copy_g2s(sa, asrc.packed + packed_block_index(c.m_tile, ks, asrc.row_blocks) * kBlockBytes, kABytes, &full[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&full[s], (ASrc::kBulk ? kABytes : 0) + kBBytes);
           if constexpr (!kMn) {
             if constexpr (ASrc::kBulk) {
@@ -316,6 +354,9 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       uint32_t idesc = kKind == 0 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
       if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       uint32_t git = 0, lt = 0;
+      if constexpr (kBRes > 0) {
+        if (first_tile < num_tiles) mbar_wait(bres_full, 0);
+      }
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const TileCoord c = decode(tile);
         if (c.n_it <= 0) continue;
@@ -328,7 +369,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
           mbar_wait(&full[s], (git / kStages) & 1);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sb = kBRes > 0 ? smem_u32(bres + (c.ks0 + it) * kBPart) : sa + kABytes;
 #pragma unroll
           for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
             uint64_t da, db;
@@ -499,6 +540,42 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
       return 2;
     }
   }
+  return check_launch(what);
+}
+
+// B-stationary launch of a K-major bf16 bulk-fed contraction with k_steps <= kBRes (e.g. K = inner dim = 256: four
+// k-steps, 128 KB of resident B per 256-column tile); anything else goes to the streaming kernel.
+template <int BN, int kStages, int kBRes, class ASrc, class Epi>
+int launch_gemm_bstationary(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
+                            int k_steps, const Epi& epi, cudaStream_t stream, const char* what) {
+  constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, 0, ASrc, Epi, kBRes>();
+  static_assert(smem <= 227 * 1024, "resident B + A ring + epilogue scratch exceed the 227 KB of one CTA");
+  const int sms = gemm_sm_count();
+  if (k_steps > kBRes || n_tiles > sms || getenv("S2T_B200_NO_BSTATIONARY"))
+    return launch_gemm_stream<BN, kStages, false, 0>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, k_steps, 1, epi, stream, what);
+  if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0) return 0;
+  auto kern = gemm_stream_kernel<BN, kStages, false, 0, ASrc, Epi, 1, kBRes>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
+      return 2;
+    }
+    configured = true;
+  }
+  // every CTA owns one column tile: grid = column tiles x (CTAs per column tile)
+  int per_tile = sms / n_tiles;
+  if (per_tile > m_tiles) per_tile = m_tiles;
+  const int grid = per_tile * n_tiles;
+  MnDebug mn;
+  {
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("S2T_DBG") ? atoi(getenv("S2T_DBG")) : 0;
+    mn.dbg = dbg;
+  }
+  ProfScope prof(what, stream);
+  kern<<<grid, gemm_threads<ASrc, Epi>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, 1, k_steps, 1, epi, mn);
   return check_launch(what);
 }
 
