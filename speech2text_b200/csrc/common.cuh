@@ -32,6 +32,23 @@ class ProfScope {
   bool on_;
 };
 
+// Fork / join of independent kernel chains inside one library call: the caller's stream forks into up to two
+// library-owned side streams (events only, no host synchronisation, legal under CUDA-graph capture) so that the tail
+// of one persistent kernel overlaps the start of an independent one.  S2T_B200_NO_FORK=1 keeps everything on the
+// caller's stream.
+class ForkJoin {
+ public:
+  explicit ForkJoin(cudaStream_t main);
+  cudaStream_t side(int i);  // i in {0, 1}; forks on first use
+  void join();               // the main stream waits for every side stream that was used
+  ~ForkJoin() { join(); }
+
+ private:
+  cudaStream_t main_;
+  bool used_[2];
+  bool enabled_;
+};
+
 #define S2T_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

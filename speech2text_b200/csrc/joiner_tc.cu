@@ -915,6 +915,10 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
                                                                        "tc_joiner_grad_logits_gemm"))
         return rc;
     }
+    // Three independent chains follow G: dW2 (needs G and the hidden activations), and after dhidden, dW1 and dh -> dJ.
+    // The weight-gradient contractions run on side streams so that their CTAs fill the tails of the main chain.
+    ForkJoin fj(stream);
+    cudaStream_t s_dw2 = fj.side(0);  // forked here: after G, before dhidden
     // dhidden = G W2: rows m, N = Ip, K = V
     {
       BulkA a{w.Gp, ct};
@@ -929,21 +933,22 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       BulkA a{w.Gp, ct};
       StoreRowMajorEpi ep{dW2, p.I, p.V, p.I, true};
       if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / kBN,
-                                                    kbM, splits, ep, stream, "tc_joiner_dW2_gemm"))
+                                                    kbM, splits, ep, s_dw2, "tc_joiner_dW2_gemm"))
         return rc;
     }
+    cudaStream_t s_dw1 = fj.side(1);  // forked here: after dhidden
     // dW1[i, v] += sum_m dhidden[m, i] act(.)[m, v]: accumulator rows v, cols i; A = the J kept by the forward
     // pass (bulk copies) or, when it was too large to keep, rebuilt on the fly
     {
       StoreTransposedAtomicEpi ep{dW1, p.V, p.V, p.I};
       if (w.Jp) {
         BulkA a{w.Jp + (size_t)tile0 * kBlockBytes, d.Mt};
-        if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, stream,
+        if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, s_dw1,
                                                                 "tc_joiner_dW1_gemm"))
           return rc;
       } else {
         JointMnProducer a{p.am, p.lm, w.am_row, w.lm_row, row0, M, p.V, p.act};
-        if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, stream,
+        if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, s_dw1,
                                                                 "tc_joiner_dW1_gemm"))
           return rc;
       }
@@ -970,6 +975,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       }
       if (int rc = check_launch("djoint reduce kernels")) return rc;
     }
+    fj.join();  // the next chunk overwrites G and dhidden
   }
   return 0;
 }

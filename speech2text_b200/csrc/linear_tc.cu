@@ -90,6 +90,8 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
   // pack(dy) also yields db = column sums of dy
   cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
   if (int rc = tc::pack_rows_colsum(dy, N, (int)M, N, d.Mt, d.Np / 64, pdy, db, st)) return rc;
+  ForkJoin fj(st);  // dx and dW only share the packed dy: the weight gradient runs on a side stream
+  cudaStream_t s_dw = dx ? fj.side(0) : st;
   if (dx) {
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dx, K, (int)M, K, false, nullptr};
@@ -98,17 +100,18 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
       return rc;
   }
   {
-    cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), st);
+    cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s_dw);
     const int k_steps = d.Mt * 2;
     const int tiles = (d.Np / 128) * (d.Kp / 256);
     int splits = 148 / (tiles > 0 ? tiles : 1);
     if (splits < 1) splits = 1;
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dW, K, N, K, true, nullptr};
-    if (int rc = tc::launch_gemm_stream<256, 4, true, 0>(a, px, d.Mt, d.Np / 128, d.Kp / 256, k_steps, splits, ep, st,
+    if (int rc = tc::launch_gemm_stream<256, 4, true, 0>(a, px, d.Mt, d.Np / 128, d.Kp / 256, k_steps, splits, ep, s_dw,
                                                       "tc_linear_dW_gemm"))
       return rc;
   }
+  fj.join();
   return check_launch("linear_bwd");
 }
 

@@ -13,6 +13,7 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace s2t {
 
@@ -42,6 +43,57 @@ ProfScope::~ProfScope() {
   cudaEventRecord(stop_, stream_);
   std::lock_guard<std::mutex> lk(g_mu);
   g_entries.push_back(Entry{name_, start_, stop_});
+}
+
+// ---- ForkJoin -------------------------------------------------------------------------------------
+namespace {
+struct SideStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+SideStreams& side_streams() {
+  static thread_local SideStreams per_device[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStreams& st = per_device[dev & 63];
+  if (!st.ok) {
+    for (int i = 0; i < 2; ++i) {
+      cudaStreamCreateWithFlags(&st.s[i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&st.fork, cudaEventDisableTiming);
+    st.ok = true;
+  }
+  return st;
+}
+}  // namespace
+
+ForkJoin::ForkJoin(cudaStream_t main) : main_(main), used_{false, false} {
+  static const bool disabled = getenv("S2T_B200_NO_FORK") != nullptr;
+  enabled_ = !disabled;
+}
+
+cudaStream_t ForkJoin::side(int i) {
+  if (!enabled_) return main_;
+  SideStreams& st = side_streams();
+  if (!used_[i]) {
+    cudaEventRecord(st.fork, main_);
+    cudaStreamWaitEvent(st.s[i], st.fork, 0);
+    used_[i] = true;
+  }
+  return st.s[i];
+}
+
+void ForkJoin::join() {
+  if (!enabled_) return;
+  SideStreams& st = side_streams();
+  for (int i = 0; i < 2; ++i) {
+    if (!used_[i]) continue;
+    cudaEventRecord(st.done[i], st.s[i]);
+    cudaStreamWaitEvent(main_, st.done[i], 0);
+    used_[i] = false;
+  }
 }
 
 }  // namespace s2t

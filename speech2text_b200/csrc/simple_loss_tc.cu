@@ -394,6 +394,8 @@ int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, con
   }
   if (int rc = check_launch("simple_w_packed_kernel")) return rc;
   // am_p / lm_p = bf16 exp(am - max), exp(lm - max): written by simple_logprobs_tc into the SAME workspace
+  ForkJoin fj(stream);  // the two gradient contractions are independent: d_lm runs on a side stream
+  cudaStream_t s_lm = fj.side(0);
   // d_am: rows t, cols c, contraction over s (rows of Wst and of lm_p)
   {
     BulkA a{Wst, B * (d.Spad / 128)};
@@ -413,9 +415,10 @@ int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, con
     extra.a_batch_off = d.Tpad / 64;
     extra.b_batch_off = d.Tpad / 64;
     if (int rc = launch_gemm_stream<256, 4, true, 0>(a, am_p, B * (d.Tpad / 128), d.Spad / 128, d.Vp / 256, d.Tpad / 64, 1,
-                                                     ep, stream, "tc_simple_d_lm_gemm", extra, B))
+                                                     ep, s_lm, "tc_simple_d_lm_gemm", extra, B))
       return rc;
   }
+  fj.join();
   return simple_scatter_onehot(occ_px, occ_py, sym, coef, B, S, T, V, blank, d_am, d_lm, stream);
 }
 
