@@ -71,7 +71,7 @@ SideStreams& side_streams() {
 
 ForkJoin::ForkJoin(cudaStream_t main) : main_(main), used_{false, false} {
   static const bool disabled = getenv("S2T_B200_NO_FORK") != nullptr;
-  enabled_ = !disabled;
+  enabled_ = !disabled && !g_enabled.load();  // the per-kernel timer wants exclusive kernel times: no overlap
 }
 
 cudaStream_t ForkJoin::side(int i) {
