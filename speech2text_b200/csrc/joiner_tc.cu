@@ -419,7 +419,6 @@ __global__ void lse_combine_kernel(const float* __restrict__ part, const float* 
 // G = coef * clip(occ_px [v == sym] + occ_py [v == blank] - (occ_px + occ_py) softmax) for a row chunk
 struct GradEpi {
   static constexpr int kScratchBytes = kTransposeScratchBytes;
-  static constexpr int kBulkGroups = 2;  // needs > 96 registers per thread: two groups (384 threads), not four
   const float* b2;
   const int* row_sym;
   const float* lse;
