@@ -160,15 +160,18 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
 /* ---------------------------------------------------------------------------
  * nn.Linear for the joiner's projections in bf16 tensor-core mode
  *   reference: self._enc_proj / self._pre_proj, model/joiner/joiner.py:41-42, 148-149.
- * x (M,K), W (N,K), b (N) fp32 -> y (M,N) fp32 = x W^T + b with bf16 operands, fp32 accumulation.
+ * x (M,K), W (N,K), b (N) fp32 -> y (M,N) fp32 = x W^T + b: 3xTF32 forward (fp32-level accuracy), bf16 operands in
+ * the backward contractions, fp32 accumulation.
  * workspace: s2t_linear_workspace_bytes(M,N,K) bytes, the same buffer for fwd and bwd
- * (it carries the packed bf16 x).  bwd overwrites dx (may be NULL), dW, db.
+ * (it carries the packed bf16 x and W^T).  bwd overwrites dx (may be NULL), dW, db.  The upstream gradient is
+ * dy + dy2 (dy2 may be NULL): y feeds two consumers in this path (simple loss and joiner) and their two gradient
+ * terms are added while dy is packed instead of by a separate pass over (M,N).
  */
 size_t s2t_linear_workspace_bytes(int64_t M, int N, int K);
 int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, int N, int K, void* workspace,
                    float* y, void* stream);
-int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, void* workspace, float* dx, float* dW,
-                   float* db, void* stream);
+int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M, int N, int K, void* workspace,
+                   float* dx, float* dW, float* db, void* stream);
 
 /* Debug / materialised mode: write the logits (B,T,R,V) fp32 the fused path never stores. */
 int s2t_joiner_materialize(int mode, const float* am, const float* lm, const int64_t* ranges, const float* W1,

@@ -48,7 +48,7 @@ _SIGNATURES = {
                                     P, P, P, P, P]),
     "s2t_linear_workspace_bytes": (c_size_t, [ctypes.c_int64, I, I]),
     "s2t_linear_fwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P]),
-    "s2t_linear_bwd": (c_int, [P, P, ctypes.c_int64, I, I, P, P, P, P, P]),
+    "s2t_linear_bwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P, P, P]),
     "s2t_joiner_materialize": (c_int, [I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P]),
 }
 

@@ -78,9 +78,9 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
                                                   "tc_linear_fwd_gemm_3xtf32", extra);
 }
 
-// dx (M,K), dW (N,K), db (N) are overwritten
-int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, void* ws, float* dx, float* dW,
-                   float* db, void* stream) {
+// dx (M,K), dW (N,K), db (N) are overwritten; the upstream gradient is dy (+ dy2 when not null)
+int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M, int N, int K, void* ws, float* dx,
+                   float* dW, float* db, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
   LinDims d = lin_dims(M, N, K);
@@ -89,7 +89,7 @@ int s2t_linear_bwd(const float* dy, const float* W, int64_t M, int N, int K, voi
   uint8_t* pwt = pdy + d.pdy;
   // pack(dy) also yields db = column sums of dy
   cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
-  if (int rc = tc::pack_rows_colsum(dy, N, (int)M, N, d.Mt, d.Np / 64, pdy, db, st)) return rc;
+  if (int rc = tc::pack_rows_colsum(dy, dy2, N, (int)M, N, d.Mt, d.Np / 64, pdy, db, st)) return rc;
   ForkJoin fj(st);  // dx and dW only share the packed dy: the weight gradient runs on a side stream
   cudaStream_t s_dw = dx ? fj.side(0) : st;
   if (dx) {

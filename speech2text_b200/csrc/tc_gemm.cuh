@@ -688,9 +688,9 @@ int pack_operand(const float* src, int64_t row_stride, int64_t col_stride, int r
 int pack_operand_f32(const float* src, int64_t row_stride, int rows, int K, int row_blocks, int k_blocks,
                      int part, uint8_t* dst, cudaStream_t stream);
 
-// Row-major fp32 (rows, K) -> bf16 packed operand; col_sum (may be null) += the column sums of src.
-int pack_rows_colsum(const float* src, int64_t ld, int rows, int K, int row_blocks, int k_blocks, uint8_t* dst,
-                     float* col_sum, cudaStream_t stream);
+// Row-major fp32 (rows, K) -> bf16 packed operand of src (+ src2 when not null); col_sum (may be null) += its column sums.
+int pack_rows_colsum(const float* src, const float* src2, int64_t ld, int rows, int K, int row_blocks, int k_blocks,
+                     uint8_t* dst, float* col_sum, cudaStream_t stream);
 
 // Several pack jobs in one launch (weights of a module).  kind 0: bf16 (k_blocks of 64); kind 1 / 2: the
 // big / residual tf32 part of an fp32 operand (k_blocks of 32).  src(r, k) = src[r * row_stride + k * col_stride].

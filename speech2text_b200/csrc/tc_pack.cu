@@ -64,14 +64,15 @@ __global__ void pack_operand_f32_kernel(const float* __restrict__ src, int64_t r
 // source (the bias gradient of a linear layer falls out of packing dy).  16 threads cover the 64 columns
 // of a row (one float4 each), 16 rows per pass; the block's column sums meet in shared memory and leave
 // as 64 atomics.
-__global__ void __launch_bounds__(256) pack_rows_colsum_kernel(const float* __restrict__ src, int64_t ld, int rows, int K,
+__global__ void __launch_bounds__(256) pack_rows_colsum_kernel(const float* __restrict__ src,
+                                                               const float* __restrict__ src2, int64_t ld, int rows, int K,
                                                                int row_blocks, uint8_t* __restrict__ dst,
                                                                float* __restrict__ col_sum) {
   __shared__ float part[16][65];
   const int rb = blockIdx.x, kb = blockIdx.y;
   const int c = threadIdx.x & 15, rl = threadIdx.x >> 4;
   const int k = kb * 64 + c * 4;
-  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const bool vec = ((ld & 3) == 0) && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(src2)) & 15) == 0);
   uint8_t* blk = dst + packed_block_index(rb, kb, row_blocks) * kBlockBytes;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -84,9 +85,13 @@ __global__ void __launch_bounds__(256) pack_rows_colsum_kernel(const float* __re
       if (vec && k + 4 <= K) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        if (src2) {  // the operand is the sum of two gradient terms that were never added in memory
+          const float4 u = __ldg(reinterpret_cast<const float4*>(src2 + r * ld + k));
+          v[0] += u.x; v[1] += u.y; v[2] += u.z; v[3] += u.w;
+        }
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (k + e < K) ? __ldg(p + e) : 0.f;
+        for (int e = 0; e < 4; ++e) v[e] = (k + e < K) ? __ldg(p + e) + (src2 ? __ldg(src2 + r * ld + k + e) : 0.f) : 0.f;
       }
     }
 #pragma unroll
@@ -215,13 +220,13 @@ int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream) {
   return check_launch("pack_batched_kernel<bf16>");
 }
 
-int pack_rows_colsum(const float* src, int64_t ld, int rows, int K, int row_blocks, int k_blocks, uint8_t* dst,
-                     float* col_sum, cudaStream_t stream) {
+int pack_rows_colsum(const float* src, const float* src2, int64_t ld, int rows, int K, int row_blocks, int k_blocks,
+                     uint8_t* dst, float* col_sum, cudaStream_t stream) {
   S2T_REQUIRE(row_blocks * 128 >= rows && k_blocks * 64 >= K, "pack_rows_colsum: padded dims too small");
   if (row_blocks == 0 || k_blocks == 0) return 0;
   S2T_REQUIRE(k_blocks <= 65535, "pack_rows_colsum: K too large");
   ProfScope prof("pack_operand_kernel", stream);
-  pack_rows_colsum_kernel<<<dim3((unsigned)row_blocks, (unsigned)k_blocks), 256, 0, stream>>>(src, ld, rows, K, row_blocks, dst,
+  pack_rows_colsum_kernel<<<dim3((unsigned)row_blocks, (unsigned)k_blocks), 256, 0, stream>>>(src, src2, ld, rows, K, row_blocks, dst,
                                                                                             col_sum);
   return check_launch("pack_rows_colsum_kernel");
 }

@@ -318,6 +318,10 @@ def joiner_materialize(am: Tensor, lm: Tensor, W1, b1, W2, b2, ranges: Optional[
 # nn.Linear on the tensor cores (joiner projections, bf16 mode)
 # ---------------------------------------------------------------------------
 class _LinearTC(torch.autograd.Function):
+    """y = x W^T + b, returned twice (the second output is an alias of the first): the path feeds y to two
+    consumers -- the simple loss and the joiner -- and with one output each their gradients arrive here
+    separately, so that the sum is formed while dy is packed for the backward contractions instead of by a
+    separate pass of autograd over two (M, N) tensors."""
 
     @staticmethod
     def forward(ctx, x: Tensor, W: Tensor, b: Tensor):
@@ -331,20 +335,31 @@ class _LinearTC(torch.autograd.Function):
         check(lib().s2t_linear_fwd(ptr(x2), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y), stream()))
         ctx.save_for_backward(W, ws)
         ctx.dims = (M, N, K, lead, x.requires_grad)
-        return y.reshape(*lead, N)
+        y = y.reshape(*lead, N)
+        return y, y.view_as(y)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dy_alias):
         W, ws = ctx.saved_tensors
         M, N, K, lead, need_dx = ctx.dims
+        if dy is None:
+            dy, dy_alias = dy_alias, None
+        if dy is None:
+            return None, None, None
         dy2 = _f32c(dy).reshape(M, N)
+        dy3 = _f32c(dy_alias).reshape(M, N) if dy_alias is not None else None
         dx = torch.empty((M, K), dtype=torch.float32, device=dy.device) if need_dx else None
         dW = torch.empty_like(W)
         db = torch.empty((N,), dtype=torch.float32, device=dy.device)
-        check(lib().s2t_linear_bwd(ptr(dy2), ptr(W), M, N, K, ptr(ws), ptr(dx), ptr(dW), ptr(db), stream()))
+        check(lib().s2t_linear_bwd(ptr(dy2), ptr(dy3), ptr(W), M, N, K, ptr(ws), ptr(dx), ptr(dW), ptr(db), stream()))
         return (dx.reshape(*lead, K) if need_dx else None), dW, db
 
 
 def linear_tc(x: Tensor, W: Tensor, b: Tensor) -> Tensor:
-    """``F.linear(x, W, b)`` with bf16 operands / fp32 accumulation on tcgen05; fp32 in, fp32 out."""
+    """``F.linear(x, W, b)`` on tcgen05 (3xTF32 forward, bf16 backward); fp32 in, fp32 out."""
+    return _LinearTC.apply(x, W, b)[0]
+
+
+def linear_tc_pair(x: Tensor, W: Tensor, b: Tensor) -> Tuple[Tensor, Tensor]:
+    """Same, as two aliases of the result for two consumers (see _LinearTC)."""
     return _LinearTC.apply(x, W, b)

@@ -200,11 +200,12 @@ class Joiner(nn.Module):
         # Project both encoder_out and predictor_out into vocab_size
         mode = _mode_from_env()
         if mode == _lib.MODE_BF16_TC and os.environ.get("S2T_B200_PROJ_TC", "1") != "0":
-            am = F2.linear_tc(encoder_out, self._enc_proj.weight, self._enc_proj.bias)
-            lm = F2.linear_tc(predict_out, self._pre_proj.weight, self._pre_proj.bias)
+            # two aliases of each projection: one for the simple loss, one for the joiner (functional._LinearTC)
+            am, am_j = F2.linear_tc_pair(encoder_out, self._enc_proj.weight, self._enc_proj.bias)
+            lm, lm_j = F2.linear_tc_pair(predict_out, self._pre_proj.weight, self._pre_proj.bias)
         else:
-            am = self._enc_proj(encoder_out)
-            lm = self._pre_proj(predict_out)
+            am = am_j = self._enc_proj(encoder_out)
+            lm = lm_j = self._pre_proj(predict_out)
 
         if self.prune_range > 0:
             assert target.shape[0] == target_lengths.shape[0]
@@ -219,18 +220,18 @@ class Joiner(nn.Module):
         W1, b1, W2, b2 = self._out_proj_params()
         fused = os.environ.get("S2T_B200_FUSED", "1") != "0"
         if fused:
-            output = LazyJoinerLogits(am, lm, W1, b1, W2, b2, ranges, self._act_code, mode)
+            output = LazyJoinerLogits(am_j, lm_j, W1, b1, W2, b2, ranges, self._act_code, mode)
         else:
             # the reference's own materialising ops (joiner.py:121-123, 166-178)
             if ranges is not None:
                 B, T, R = ranges.shape
                 S1, C = lm.shape[1], lm.shape[2]
-                am_p = am.unsqueeze(2).expand((B, T, R, am.shape[-1]))
-                lm_p = torch.gather(lm.unsqueeze(1).expand((B, T, S1, C)), dim=2,
+                am_p = am_j.unsqueeze(2).expand((B, T, R, am.shape[-1]))
+                lm_p = torch.gather(lm_j.unsqueeze(1).expand((B, T, S1, C)), dim=2,
                                     index=ranges.reshape((B, T, R, 1)).expand((B, T, R, C)))
             else:
-                am_p = am.unsqueeze(2).contiguous()
-                lm_p = lm.unsqueeze(1).contiguous()
+                am_p = am_j.unsqueeze(2).contiguous()
+                lm_p = lm_j.unsqueeze(1).contiguous()
             output = self._out_projection(self._activation(am_p + lm_p))
 
         # Use raw output of joiner for rnnt_loss compute since log_softmax will be
