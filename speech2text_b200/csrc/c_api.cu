@@ -108,6 +108,9 @@ static int band_dp(const float* px, const float* py, const int64_t* ranges, cons
   if (band_lattice_fast_ok(S, T, R) && !getenv("S2T_B200_GENERIC_DP")) {
     return launch_band_lattice_fast(px, py, ranges, boundary, B, S, T, R, scores, occ_px, occ_py, st);
   }
+  if (ranges == nullptr && R == S + 1 && full_lattice_fast_ok(S, T) && !getenv("S2T_B200_GENERIC_DP")) {
+    return launch_full_lattice_fast(px, py, boundary, B, S, T, alpha, scores, occ_px, occ_py, st);
+  }
   LatticeView v = band_view(px, py, ranges, boundary, B, S, T, R, alpha);
   size_t n = (size_t)B * T * R * sizeof(float);
   cudaMemsetAsync(occ_px, 0, n, st);
@@ -219,7 +222,9 @@ int s2t_logits_loss_bwd(const void* logits, int dtype, const int64_t* symbols, c
 size_t s2t_lattice_workspace_bytes(int B, int S, int T, int slots) {
   size_t generic = lattice_workspace_bytes(B, S, T, slots);
   size_t fast = simple_lattice_fast_workspace_bytes(B, S, T);
-  return generic > fast ? generic : fast;
+  size_t full = slots == S + 1 ? full_lattice_fast_workspace_bytes(B, S, T) : 0;
+  size_t best = generic > fast ? generic : fast;
+  return best > full ? best : full;
 }
 
 size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {

@@ -51,6 +51,11 @@ int launch_lattice_fwd(const LatticeView& v, float* logp, cudaStream_t stream);
 
 // warp-synchronous fast paths (lattice_fast.cu)
 bool simple_lattice_fast_ok(int S, int T);
+// unpruned lattice handed over in band layout (B, T, S+1): transposed onto the systolic full-lattice kernel
+bool full_lattice_fast_ok(int S, int T);
+size_t full_lattice_fast_workspace_bytes(int B, int S, int T);
+int launch_full_lattice_fast(const float* px, const float* py, const int64_t* boundary, int B, int S, int T, void* ws,
+                             float* logp, float* occ_px, float* occ_py, cudaStream_t stream);
 size_t simple_lattice_fast_workspace_bytes(int B, int S, int T);
 // occ_px / occ_py may both be nullptr (scores only); otherwise every element of them is written
 int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* boundary, int B, int S, int T,

@@ -657,6 +657,95 @@ int launch_simple_lattice_fast(const float* px, const float* py, const int64_t* 
   return 0;
 }
 
+// ---- unpruned lattice in band layout -> the systolic full-lattice kernel ---------------------------------------
+// The vanilla RNN-T loss hands px / py over as (B, T, S+1) (frame-major, ranges == NULL): a full lattice.  Its
+// recursion runs on simple_lattice_kernel after a tiled transpose into the k2 layout, and the occupation
+// probabilities are transposed back.
+namespace {
+
+// in (B, T, R=S+1) -> px_k2 (B, S, T+1) [-inf in column T_b and beyond the symbols], py_k2 (B, S+1, T)
+__global__ void __launch_bounds__(256) full_to_k2_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                         const int64_t* __restrict__ boundary, int S, int T,
+                                                         float* __restrict__ px_k2, float* __restrict__ py_k2) {
+  __shared__ float tx[32][33], ty[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, s0 = blockIdx.y * 32, R = S + 1;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8
+  const int Tb = boundary ? (int)boundary[4 * b + 3] : T;
+  for (int i = ly; i < 32; i += 8) {  // rows t, columns s (s contiguous in the source)
+    const int t = t0 + i, s = s0 + lx;
+    const bool ok = t < T && s < R;
+    tx[i][lx] = ok ? px[((int64_t)b * T + t) * R + s] : kNegInf;
+    ty[i][lx] = ok ? py[((int64_t)b * T + t) * R + s] : kNegInf;
+  }
+  __syncthreads();
+  for (int i = ly; i < 32; i += 8) {  // rows s, columns t (t contiguous in the destination)
+    const int s = s0 + i, t = t0 + lx;
+    if (s >= R) continue;
+    if (t < T) py_k2[((int64_t)b * R + s) * T + t] = ty[lx][i];
+    if (s < S && t < T) px_k2[((int64_t)b * S + s) * (T + 1) + t] = (t == Tb) ? kNegInf : tx[lx][i];
+    if (s < S && t == T - 1) px_k2[((int64_t)b * S + s) * (T + 1) + T] = kNegInf;
+  }
+}
+
+// occupation probabilities back: k2 layout -> (B, T, R)
+__global__ void __launch_bounds__(256) k2_to_full_kernel(const float* __restrict__ ox_k2, const float* __restrict__ oy_k2,
+                                                         int S, int T, float* __restrict__ occ_px,
+                                                         float* __restrict__ occ_py) {
+  __shared__ float tx[32][33], ty[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, s0 = blockIdx.y * 32, R = S + 1;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (int i = ly; i < 32; i += 8) {  // rows s, columns t
+    const int s = s0 + i, t = t0 + lx;
+    tx[i][lx] = (s < S && t < T) ? ox_k2[((int64_t)b * S + s) * (T + 1) + t] : 0.f;
+    ty[i][lx] = (s < R && t < T) ? oy_k2[((int64_t)b * R + s) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ly; i < 32; i += 8) {  // rows t, columns s
+    const int t = t0 + i, s = s0 + lx;
+    if (t >= T || s >= R) continue;
+    occ_px[((int64_t)b * T + t) * R + s] = tx[lx][i];
+    occ_py[((int64_t)b * T + t) * R + s] = ty[lx][i];
+  }
+}
+
+size_t full_k2_floats(int B, int S, int T) {
+  return 2 * ((size_t)B * S * (T + 1) + (size_t)B * (S + 1) * T);  // px, py, occ_px, occ_py in k2 layout
+}
+
+}  // namespace
+
+bool full_lattice_fast_ok(int S, int T) { return S >= 1 && simple_lattice_fast_ok(S, T); }
+
+size_t full_lattice_fast_workspace_bytes(int B, int S, int T) {
+  if (!full_lattice_fast_ok(S, T)) return 0;
+  return ((full_k2_floats(B, S, T) * sizeof(float) + 255) / 256) * 256 + simple_lattice_fast_workspace_bytes(B, S, T);
+}
+
+int launch_full_lattice_fast(const float* px, const float* py, const int64_t* boundary, int B, int S, int T, void* ws,
+                             float* logp, float* occ_px, float* occ_py, cudaStream_t stream) {
+  if (B == 0 || T == 0) return 0;
+  float* px_k2 = (float*)ws;
+  float* py_k2 = px_k2 + (size_t)B * S * (T + 1);
+  float* ox_k2 = py_k2 + (size_t)B * (S + 1) * T;
+  float* oy_k2 = ox_k2 + (size_t)B * S * (T + 1);
+  void* ws2 = (char*)ws + ((full_k2_floats(B, S, T) * sizeof(float) + 255) / 256) * 256;
+  const dim3 grid((unsigned)((T + 31) / 32), (unsigned)((S + 1 + 31) / 32), (unsigned)B);
+  {
+    ProfScope prof("full_lattice_transpose_kernels", stream);
+    full_to_k2_kernel<<<grid, 256, 0, stream>>>(px, py, boundary, S, T, px_k2, py_k2);
+  }
+  if (int rc = check_launch("full_to_k2_kernel")) return rc;
+  if (int rc = launch_simple_lattice_fast(px_k2, py_k2, boundary, B, S, T, ws2, logp, occ_px ? ox_k2 : nullptr,
+                                          occ_px ? oy_k2 : nullptr, stream))
+    return rc;
+  if (occ_px) {
+    ProfScope prof("full_lattice_transpose_kernels", stream);
+    k2_to_full_kernel<<<grid, 256, 0, stream>>>(ox_k2, oy_k2, S, T, occ_px, occ_py);
+    return check_launch("k2_to_full_kernel");
+  }
+  return 0;
+}
+
 static size_t band_smem_bytes(int S, int T, int R) {
   const size_t n_off = ((S + T + R) >> kRebaseShift) + 2;
   return (size_t)4 * T * R * sizeof(float) + 16 + (size_t)(2 * (T + 1) + 3) * R * 16 + (size_t)(T + 2) * sizeof(int) + 8 +

