@@ -77,8 +77,8 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
  * nrm (B,S+1,T) [log-normalisers, kept for the backward], alpha_ws (scratch, as above),
  * scores (B) = log P(y|x) per utterance (reduction is the caller's),
  * px_grad (B,S,T+1), py_grad (B,S+1,T).
- * lm_only_scale / am_only_scale must be 0 in this ABI version (the reference's
- * configs never set them; non-zero returns an error).
+ * lm_only_scale / am_only_scale: k2's lm-only / am-only interpolation (JoinerConfig.lm_scale / am_scale);
+ * both >= 0, sum < 1; 0 drops the term.
  * mode: S2T_MODE_FP32_SIMT = fp32 FMA contraction; S2T_MODE_BF16_TC = 3xTF32 tensor-core
  * normaliser (fp32-level accuracy) and bf16 tensor-core backward contractions.
  * workspace: s2t_simple_workspace_bytes(mode,B,T,S,V) bytes.
@@ -95,8 +95,8 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
  * d_am (B,T,V), d_lm (B,S+1,V) are overwritten. */
 int s2t_simple_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols, const float* am_max,
                         const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,
-                        const float* grad_scores, int B, int T, int S, int V, int blank, void* workspace,
-                        float* d_am, float* d_lm, void* stream);
+                        const float* grad_scores, int B, int T, int S, int V, int blank, float lm_only_scale,
+                        float am_only_scale, void* workspace, float* d_am, float* d_lm, void* stream);
 
 /* ---------------------------------------------------------------------------
  * k2.get_rnnt_prune_ranges(px_grad, py_grad, boundary, s_range)

@@ -37,7 +37,7 @@ _SIGNATURES = {
     "s2t_mutual_information": (c_int, [P, P, P, I, I, I, P, P, P, P, P]),
     "s2t_simple_workspace_bytes": (c_size_t, [I, I, I, I, I]),
     "s2t_simple_loss_fwd": (c_int, [I, P, P, P, P, I, I, I, I, I, F, F, P, P, P, P, P, P, P, P, P, P, P]),
-    "s2t_simple_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, P]),
+    "s2t_simple_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, F, P, P, P, P]),
     "s2t_prune_ranges": (c_int, [P, P, P, I, I, I, I, I, P, P]),
     "s2t_logits_loss_fwd": (c_int, [P, I, P, P, P, I, I, I, I, I, I, F, P, P, P, P, P, P, P, P]),
     "s2t_logits_loss_bwd": (c_int, [P, I, P, P, P, P, P, P, I, I, I, I, I, I, F, P, P]),

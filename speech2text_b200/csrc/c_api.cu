@@ -44,6 +44,19 @@ int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, con
                        const float* lm_max, const float* nrm, const float* occ_px, const float* occ_py,
                        const float* coef, int B, int T, int S, int V, int blank, void* ws, float* d_am, float* d_lm,
                        cudaStream_t stream);
+size_t simple_smooth_workspace_bytes(int B, int T, int S, int V);
+int simple_smooth_forward(const float* am, const float* lm, const int64_t* sym, const float* am_max,
+                          const float* lm_max, const float* nrm, int B, int T, int S, int V, int blank, float ls,
+                          float as, void* ws, float* px, float* py, cudaStream_t st);
+float* simple_smooth_scaled_coef(const float* coef, int B, int T, int S, int V, float k, int slot, void* ws,
+                                 cudaStream_t st);
+int simple_smooth_backward(const float* am, const float* lm, const int64_t* sym, const float* am_max,
+                           const float* lm_max, const float* occ_px, const float* occ_py, const float* coef, int B,
+                           int T, int S, int V, int blank, float ls, float as, void* ws, float* d_am, float* d_lm,
+                           cudaStream_t st);
+int simple_scatter_onehot_split(const float* occ_px, const float* occ_py, const int64_t* sym, const float* coef_am,
+                                const float* coef_lm, int B, int S, int T, int V, int blank, float* d_am, float* d_lm,
+                                cudaStream_t stream);
 int prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boundary, int B, int S, int T, int R,
                  int variant, int64_t* ranges, cudaStream_t stream);
 int lse_gather(const void* logits, int dtype, const int64_t* sym, const int64_t* ranges, const int64_t* boundary,
@@ -155,9 +168,14 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
   return launch_lattice_fwd_bwd(v, scores, px_grad, py_grad, st);
 }
 
+static size_t simple_base_workspace_bytes(int mode, int B, int T, int S, int V) {
+  size_t n = mode == S2T_MODE_BF16_TC ? simple_tc_workspace_bytes(B, T, S, V)
+                                      : (size_t)B * (S + 1) * T * sizeof(float) + 256;  // W scratch of the fp32 backward
+  return (n + 255) / 256 * 256;
+}
+
 size_t s2t_simple_workspace_bytes(int mode, int B, int T, int S, int V) {
-  if (mode == S2T_MODE_BF16_TC) return simple_tc_workspace_bytes(B, T, S, V);
-  return (size_t)B * (S + 1) * T * sizeof(float) + 256;  // W scratch of the fp32 backward
+  return simple_base_workspace_bytes(mode, B, T, S, V) + simple_smooth_workspace_bytes(B, T, S, V);
 }
 
 int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
@@ -165,9 +183,9 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
                         float* am_max, float* lm_max, float* px, float* py, float* nrm, void* alpha_ws,
                         float* scores, float* px_grad, float* py_grad, void* workspace, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  S2T_REQUIRE(lm_only_scale == 0.f && am_only_scale == 0.f,
-              "simple_loss: non-zero lm_only_scale/am_only_scale (%g, %g) not supported by ABI v%d",
-              lm_only_scale, am_only_scale, S2T_ABI_VERSION);
+  S2T_REQUIRE(lm_only_scale >= 0.f && am_only_scale >= 0.f && lm_only_scale + am_only_scale < 1.f,
+              "simple_loss: lm_only_scale/am_only_scale (%g, %g) must be >= 0 and sum to less than 1", lm_only_scale,
+              am_only_scale);
   S2T_REQUIRE(B > 0 && T > 0 && S >= 0 && V > 0, "simple_loss: bad dims B=%d T=%d S=%d V=%d", B, T, S, V);
   S2T_REQUIRE(blank >= 0 && blank < V, "simple_loss: blank %d out of range", blank);
   if (mode == S2T_MODE_BF16_TC) {
@@ -178,20 +196,43 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
     if (int rc = simple_logprobs(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm, st))
       return rc;
   }
+  if (lm_only_scale != 0.f || am_only_scale != 0.f) {
+    void* sws = (char*)workspace + simple_base_workspace_bytes(mode, B, T, S, V);
+    if (int rc = simple_smooth_forward(am, lm, symbols, am_max, lm_max, nrm, B, T, S, V, blank, lm_only_scale,
+                                       am_only_scale, sws, px, py, st))
+      return rc;
+  }
   return s2t_mutual_information(px, py, boundary, B, S, T, alpha_ws, scores, px_grad, py_grad, stream);
 }
 
 int s2t_simple_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols, const float* am_max,
                         const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,
-                        const float* grad_scores, int B, int T, int S, int V, int blank, void* workspace,
-                        float* d_am, float* d_lm, void* stream) {
+                        const float* grad_scores, int B, int T, int S, int V, int blank, float lm_only_scale,
+                        float am_only_scale, void* workspace, float* d_am, float* d_lm, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool smooth = lm_only_scale != 0.f || am_only_scale != 0.f;
+  void* sws = (char*)workspace + simple_base_workspace_bytes(mode, B, T, S, V);
+  // px_i holds the plain term with weight c0 and the am / lm one-hots with c0 + am_only_scale / c0 + lm_only_scale
+  const float* coef = grad_scores;
+  if (smooth)
+    coef = simple_smooth_scaled_coef(grad_scores, B, T, S, V, 1.f - lm_only_scale - am_only_scale, 0, sws, st);
+  int rc;
   if (mode == S2T_MODE_BF16_TC) {
-    return simple_backward_tc(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, grad_scores, B, T, S, V, blank,
-                              workspace, d_am, d_lm, (cudaStream_t)stream);
+    rc = simple_backward_tc(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, coef, B, T, S, V, blank, workspace,
+                            d_am, d_lm, st);
+  } else {
+    rc = simple_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, coef, B, T, S, V, blank,
+                         (float*)workspace, d_am, d_lm, st);
   }
-  float* wbuf = (float*)workspace;
-  return simple_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, grad_scores, B, T, S, V, blank,
-                         wbuf, d_am, d_lm, (cudaStream_t)stream);
+  if (rc || !smooth) return rc;
+  const float* ca = am_only_scale != 0.f ? simple_smooth_scaled_coef(grad_scores, B, T, S, V, am_only_scale, 1, sws, st)
+                                         : nullptr;
+  const float* cl = lm_only_scale != 0.f ? simple_smooth_scaled_coef(grad_scores, B, T, S, V, lm_only_scale, 2, sws, st)
+                                         : nullptr;
+  if (int rc2 = simple_scatter_onehot_split(px_grad, py_grad, symbols, ca, cl, B, S, T, V, blank, d_am, d_lm, st))
+    return rc2;
+  return simple_smooth_backward(am, lm, symbols, am_max, lm_max, px_grad, py_grad, grad_scores, B, T, S, V, blank,
+                                lm_only_scale, am_only_scale, sws, d_am, d_lm, st);
 }
 
 int s2t_prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boundary, int B, int S, int T,

@@ -231,4 +231,21 @@ int simple_scatter_onehot(const float* occ_px, const float* occ_py, const int64_
   return check_launch("simple_scatter kernels");
 }
 
+// the same scatter with separate per-utterance factors for the am and the lm side (either may be null: skipped)
+int simple_scatter_onehot_split(const float* occ_px, const float* occ_py, const int64_t* sym, const float* coef_am,
+                                const float* coef_lm, int B, int S, int T, int V, int blank, float* d_am, float* d_lm,
+                                cudaStream_t stream) {
+  const int64_t total = (int64_t)B * (S + 1) * T;
+  if (total == 0) return 0;
+  ProfScope prof2("simple_scatter_kernels", stream, 2);
+  if (coef_am)
+    simple_scatter_am_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(occ_px, occ_py, sym, coef_am, B, S, T, V,
+                                                                                   blank, d_am);
+  const int64_t nbs = (int64_t)B * (S + 1);
+  if (coef_lm)
+    simple_scatter_lm_kernel<<<(unsigned)((nbs + 7) / 8), 256, 0, stream>>>(occ_px, occ_py, sym, coef_lm, B, S, T, V, blank,
+                                                                             d_lm);
+  return check_launch("simple_scatter kernels");
+}
+
 }  // namespace s2t

@@ -96,6 +96,7 @@ class _SimpleLoss(torch.autograd.Function):
         ctx.save_for_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws)
         ctx.blank = blank
         ctx.mode = mode
+        ctx.scales = (float(lm_only_scale), float(am_only_scale))
         ctx.mark_non_differentiable(px_grad, py_grad)
         return scores, px_grad, py_grad
 
@@ -109,7 +110,7 @@ class _SimpleLoss(torch.autograd.Function):
         d_lm = torch.empty_like(lm)
         check(lib().s2t_simple_loss_bwd(ctx.mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
                                         ptr(px_grad), ptr(py_grad), ptr(grad_scores), B, T, S, V, ctx.blank,
-                                        ptr(ws), ptr(d_am), ptr(d_lm), stream()))
+                                        ctx.scales[0], ctx.scales[1], ptr(ws), ptr(d_am), ptr(d_lm), stream()))
         return d_am, d_lm, None, None, None, None, None, None
 
 

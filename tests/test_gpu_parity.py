@@ -215,7 +215,7 @@ def _run_modules(name, fused: bool, monkeypatch, mode: str = "fp32"):
     return out
 
 
-SUPPORTED = [n for n in CASES if CASES[n]["joiner"].get("lm_scale", 0.0) == 0.0]
+SUPPORTED = list(CASES)  # includes tanh_smoothed: non-zero lm_scale / am_scale (k2's lm-only / am-only interpolation)
 
 
 @pytest.mark.parametrize("fused", [True, False])
@@ -358,16 +358,38 @@ def test_lazy_logits_materialize_matches_port(name, monkeypatch):
     assert rel_err(simple, ref_simple) < LOSS_RTOL
 
 
-def test_smoothing_scales_raise_loudly(monkeypatch):
-    """Non-zero lm_scale / am_scale are not built in ABI v1: the call must fail, not fall back."""
-    from speech2text_b200._lib import S2TError
-    from speech2text_b200.joiner import Joiner, JoinerConfig
-    spec, case = CASES["tanh_smoothed"], make_case("tanh_smoothed")
-    joiner = Joiner(JoinerConfig(**spec["joiner"])).to(_dev())
-    args = [torch.from_numpy(case[k]).to(_dev()) for k in
-            ("encoder_out", "encoder_out_lengths", "predict_out", "target_lengths", "target")]
-    with pytest.raises(S2TError):
-        joiner(*args)
+@pytest.mark.parametrize("scales", [(0.25, 0.1), (0.3, 0.0), (0.0, 0.2)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_smoothed_simple_loss_matches_oracle(scales, mode):
+    """k2.rnnt_loss_smoothed with non-zero lm_only_scale / am_only_scale: loss, occupation probabilities and the
+    gradients w.r.t. am / lm (including the terms through the batch-wide unigram) against the fp64 oracle."""
+    from speech2text_b200 import _lib
+    from speech2text_b200 import functional as F2
+    B, T, S, V = 3, 37, 11, 29
+    g = torch.Generator().manual_seed(99)
+    am = torch.randn(B, T, V, generator=g)
+    lm = torch.randn(B, S + 1, V, generator=g)
+    sym = torch.randint(1, V, (B, S), generator=g)
+    boundary = torch.tensor([[0, 0, S, T], [0, 0, 7, 30], [0, 0, 3, 12]], dtype=torch.int64)
+    am_r = am.double().requires_grad_(True)
+    lm_r = lm.double().requires_grad_(True)
+    loss_r, (gx_r, gy_r) = k2.rnnt_loss_smoothed(lm=lm_r, am=am_r, symbols=sym, termination_symbol=0,
+                                                 lm_only_scale=scales[0], am_only_scale=scales[1], boundary=boundary,
+                                                 reduction="mean", return_grad=True)
+    loss_r.backward()
+    am_g = am.to(_dev()).requires_grad_(True)
+    lm_g = lm.to(_dev()).requires_grad_(True)
+    m = _lib.MODE_BF16_TC if mode == "bf16" else _lib.MODE_FP32_SIMT
+    loss_g, (gx, gy) = F2.rnnt_loss_smoothed(lm=lm_g, am=am_g, symbols=sym.to(_dev()), termination_symbol=0,
+                                             lm_only_scale=scales[0], am_only_scale=scales[1],
+                                             boundary=boundary.to(_dev()), reduction="mean", return_grad=True, mode=m)
+    loss_g.backward()
+    torch.cuda.synchronize()
+    gtol = GRAD_RTOL if mode == "fp32" else BF16_RTOL
+    assert rel_err(loss_g, loss_r) < LOSS_RTOL
+    assert rel_err(gx, gx_r) < GRAD_RTOL and rel_err(gy, gy_r) < GRAD_RTOL
+    assert rel_err(am_g.grad, am_r.grad) < gtol
+    assert rel_err(lm_g.grad, lm_r.grad) < gtol
 
 
 def test_full_size_properties_c3():
