@@ -141,10 +141,12 @@ def kernel_work(cfg):
         # simple (smoothed) loss on tensor cores: exp(am - max) built on the fly, 3xTF32 contraction with exp(lm - max)
         # over V, px/py emitted from the epilogue: am and lm read once, px/py written once
         "tc_simple_normaliser_gemm_3xtf32": ("hbm", 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
+        "tc_simple_normaliser_gemm_3xf16": ("hbm", 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
         "tc_simple_d_am_gemm": ("tensor", simple), "tc_simple_d_lm_gemm": ("tensor", simple),
         "simple_w_kernel": ("hbm", 12.0 * B * S1 * T), "row_max_kernel": ("hbm", 4.0 * (B * T * V + B * S1 * V)),
         # projections: two launches per step (encoder and predictor side); average of the two
         "tc_linear_fwd_gemm_3xtf32": ("tensor", (proj_enc + proj_pred) / 2),
+        "tc_linear_fwd_gemm_3xf16": ("tensor", (proj_enc + proj_pred) / 2),
         "tc_linear_dx_gemm": ("tensor", (proj_enc + proj_pred) / 2),
         "tc_linear_dW_gemm": ("tensor", (proj_enc + proj_pred) / 2),
         "lse_gather_kernel": ("hbm", M * V * 4.0), "logits_grad_kernel": ("hbm", 2.0 * M * V * 4),
@@ -475,6 +477,9 @@ def main():
                 # fp32-level accuracy costs three tf32 MMAs (half the bf16 rate) per algorithmic product
                 roof["issued_mma_frac"] = roof["frac"] * 6.0
                 roof["note"] = "3xTF32: issued tensor work = 6x the algorithmic bf16-equivalent FLOPs"
+            if name.endswith("3xf16"):
+                roof["issued_mma_frac"] = roof["frac"] * 3.0
+                roof["note"] = "3xF16 (hi/lo split, fp32-level accuracy): issued tensor work = 3x the algorithmic FLOPs"
         kernels = {k: {"launches": c, "ms_per_step": ms / args.steps} for k, (c, ms) in
                    sorted(report.items(), key=lambda kv: -kv[1][1])}
         line = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,

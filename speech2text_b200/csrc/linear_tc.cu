@@ -10,6 +10,7 @@
 //             dW = dy^T x            MN-major: the SAME pack(dy) and pack(x), contraction over the rows m
 //             db = column sums of dy (a by-product of packing dy)
 // pack(x) is written once in the forward call and reused by the backward call (workspace).
+#include <stdlib.h>
 #include "tc_gemm.cuh"
 
 namespace s2t {
@@ -31,7 +32,7 @@ LinDims lin_dims(int64_t M, int N, int K) {
   d.Np = ((N + 255) / 256) * 256;
   d.Kp = ((K + 255) / 256) * 256;
   d.px = (size_t)d.Mt * (d.Kp / 64) * kBlockBytes;
-  d.pw = 2 * (size_t)(d.Np / 128) * (d.Kp / 32) * kBlockBytes;  // big | small
+  d.pw = 2 * (size_t)(d.Np / 128) * (d.Kp / 32) * kBlockBytes;  // big | small (sized for the tf32 split; the f16 split needs half)
   d.pdy = (size_t)d.Mt * (d.Np / 64) * kBlockBytes;
   d.pwt = (size_t)(d.Kp / 128) * (d.Np / 64) * kBlockBytes;
   return d;
@@ -58,22 +59,39 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
   uint8_t* px = (uint8_t*)ws;
   uint8_t* pw = px + d.px;
   // pack(x) for dW in backward is a by-product of the forward producer; only K padding it never visits needs zeros
-  if (((K + 31) / 32) * 32 < d.Kp) cudaMemsetAsync(px, 0, d.px, st);
+  const bool f16 = getenv("S2T_B200_LINEAR_TF32") == nullptr;  // default: 3xF16 split; the 3xTF32 path stays selectable
+  const int kstep = f16 ? 64 : 32;
+  if (((K + kstep - 1) / kstep) * kstep < d.Kp) cudaMemsetAsync(px, 0, d.px, st);
   uint8_t* pw_small = pw + d.pw / 2;
   uint8_t* pwt = pw + d.pw + d.pdy;
+  tc::StoreRowMajorEpi ep{y, N, (int)M, N, false, b};
+  tc::MnDebug extra;
+  extra.b_small = pw_small;
+  if (f16) {
+    // W is pre-scaled by 2^6 so that the lo halves of typical weights (|w| ~ 1e-2) stay normal f16 numbers; the
+    // epilogue multiplies the accumulator by 2^-6 (exact).  |w| < 1023 and |x| < 65504 are representable.
+    constexpr float kWScale = 64.f;
+    const tc::PackJob jobs[3] = {
+        {W, K, 1, N, K, d.Np / 128, d.Kp / 64, pw, 3, kWScale},
+        {W, K, 1, N, K, d.Np / 128, d.Kp / 64, pw_small, 4, kWScale},
+        // W^T for dx in backward: rows k, cols n -> element (k, n) = W[n * K + k]
+        {W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, 0},
+    };
+    if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
+    tc::RowSplitProducerF16 a{x, K, M, K, px, d.Mt};
+    ep.scale = 1.f / kWScale;
+    return tc::launch_gemm_stream<256, 2, false, 3, kPair>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 63) / 64, 1, ep, st,
+                                                           "tc_linear_fwd_gemm_3xf16", extra);
+  }
   {
     const tc::PackJob jobs[3] = {
         {W, K, 1, N, K, d.Np / 128, d.Kp / 32, pw, 1},
         {W, K, 1, N, K, d.Np / 128, d.Kp / 32, pw_small, 2},
-        // W^T for dx in backward: rows k, cols n -> element (k, n) = W[n * K + k]
         {W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, 0},
     };
     if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
   }
   tc::RowCopyProducerF32 a{x, K, M, K, true, px, d.Mt};
-  tc::StoreRowMajorEpi ep{y, N, (int)M, N, false, b};
-  tc::MnDebug extra;
-  extra.b_small = pw_small;
   return tc::launch_gemm_stream<256, 2, false, 2, kPair>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 31) / 32, 1, ep, st,
                                                   "tc_linear_fwd_gemm_3xtf32", extra);
 }

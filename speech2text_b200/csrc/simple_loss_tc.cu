@@ -10,6 +10,7 @@
 //             d_lm[b,s,c] = -exp(lm - max) * sum_t W[b,s,t] exp(am[b,t,c] - max)
 //             bf16 operands, MN-major (the contraction index is the row index of every packed operand),
 //             batched over b; the one-hot terms are added by the scatter kernels of simple_loss.cu.
+#include <stdlib.h>
 #include "tc_gemm.cuh"
 
 namespace s2t {
@@ -132,6 +133,76 @@ struct ExpRowProducerF32 {
   }
 };
 
+// The same A operand for the 3xF16 contraction: 64 vocabulary entries per k-step, hi | lo f16 halves of
+// scale * exp(am - am_max) (thread mapping of tc::RowSplitProducerF16), bf16 by-product unscaled.
+struct ExpRowSplitProducerF16 {
+  static constexpr bool kBulk = false;
+  const float* x;   // (B, rows, V)
+  const float* mx;  // (B, rows)
+  int rows, V;
+  float scale;
+  uint8_t* bf16_pack;
+  int tiles_per_batch, pack_row_blocks;
+  __device__ void run(const ProdCtx& pc) const {
+    const int warp = pc.t >> 5, lane = pc.t & 31;
+    const int c = lane & 15, rbase = warp * 2 + (lane >> 4);
+    const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const bool emit = bf16_pack != nullptr && pc.n_tile == 0 && pc.valid;
+    const int off = rbase * 128 + ((((c >> 1) ^ (rbase & 7)) & 7) << 4) + (c & 1) * 8;
+    float sub[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = pc.m_tile * 128 + rbase + 16 * i;
+      sub[i] = r < rows ? __ldg(mx + (int64_t)pc.batch * rows + r) : 0.f;
+    }
+    auto load = [&](float4 (&dst)[4], int ks, int half) {
+      const int k = ks * 64 + c * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = pc.m_tile * 128 + rbase + 16 * (half * 4 + j);
+        const float* row = x + ((int64_t)pc.batch * rows + r) * V;
+        if (r < rows && vec && k + 4 <= V) {
+          dst[j] = __ldg(reinterpret_cast<const float4*>(row + k));
+        } else {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (r < rows && k + e < V) ? __ldg(row + k + e) : kNegInf;
+          dst[j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    };
+    auto emit_half = [&](const float4 (&src)[4], int it, int half) {
+      uint8_t* dst = pc.stage(it) + off;
+      const int ks = pc.ks0 + it;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float s = sub[half * 4 + j];  // padding holds -inf -> exp = 0
+        const float p[4] = {__expf(src[j].x - s), __expf(src[j].y - s), __expf(src[j].z - s), __expf(src[j].w - s)};
+        const float v[4] = {p[0] * scale, p[1] * scale, p[2] * scale, p[3] * scale};
+        uint2 hi, lo;
+        split_f16x4(v, hi, lo);
+        const int ro = (half * 4 + j) * 16 * 128;
+        *reinterpret_cast<uint2*>(dst + ro) = hi;
+        *reinterpret_cast<uint2*>(dst + kBlockBytes + ro) = lo;
+        if (emit) {
+          uint8_t* blk = bf16_pack + packed_block_index(pc.batch * tiles_per_batch + pc.m_tile, ks, pack_row_blocks) * kBlockBytes;
+          *reinterpret_cast<uint2*>(blk + off + ro) = make_uint2(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]));
+        }
+      }
+    };
+    float4 q0[4], q1[4];
+    load(q0, pc.ks0, 0);
+    for (int it = 0; it < pc.n_it; ++it) {
+      load(q1, pc.ks0 + it, 1);
+      pc.wait_empty(it);
+      emit_half(q0, it, 0);
+      if (it + 1 < pc.n_it) load(q0, pc.ks0 + it + 1, 0);
+      emit_half(q1, it, 1);
+      pc.arrive_full(it);
+    }
+  }
+};
+
 // accumulator rows = frames t (ctx.m inside batch ctx.batch), columns = symbol positions s.
 // Writes nrm and py (lane = frame, so every store instruction is one contiguous 128-byte row segment of the
 // k2 (B, S+1, T) layout); px needs the gather am[b, t, sym[b, s]] and is finished by simple_px_kernel with
@@ -144,6 +215,7 @@ struct SimpleEmitTcEpi {
   int T, S, V, blank;
   float* py;   // (B, S+1, T)
   float* nrm;  // (B, S+1, T)
+  float acc_scale;  // undoes the power-of-two pre-scale of the two operands
   struct State {
     float amx, am_blank;
     bool live;
@@ -166,7 +238,7 @@ struct SimpleEmitTcEpi {
     for (int j = 0; j < 32; ++j) {
       if (n + j <= S) {
         const float4 li = __ldg(info + n + j);
-        const float nv = logf(acc[j] + FLT_MIN) + li.x + st.amx;
+        const float nv = logf(acc[j] * acc_scale + FLT_MIN) + li.x + st.amx;
         nrow[(int64_t)j * T] = nv;
         prow[(int64_t)j * T] = st.am_blank + li.y - nv;
       }
@@ -355,19 +427,35 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   // exp(am - max) and exp(lm - max) as bf16 operands of the backward contractions are by-products of this pass
   uint8_t* am_p = lm_small + d.lm_f32;
   uint8_t* lm_p = am_p + d.am_bf16;
-  if (d.kb32 * 32 < d.Vp) {  // vocabulary padding the fp32 k-steps never visit
+  const bool f16 = getenv("S2T_B200_SIMPLE_TF32") == nullptr;  // default: 3xF16 split; 3xTF32 stays selectable
+  const int kstep = f16 ? 64 : 32;
+  const int ksteps = (V + kstep - 1) / kstep;
+  if (ksteps * kstep < d.Vp) {  // vocabulary padding the k-steps never visit
     cudaMemsetAsync(am_p, 0, d.am_bf16 + d.lm_bf16, stream);
   }
-  PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
-  if (int rc = pack_f32_split(ps, lm_big, lm_small, stream, lm_p, d.kb64)) return rc;
-  ExpRowProducerF32 a{am, am_max, T, V, am_p, d.Tpad / 128, B * (d.Tpad / 128)};
-  SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm};
   MnDebug extra;
   extra.b_small = lm_small;
   extra.b_batch_off = d.Spad / 128;
-  if (int rc = launch_gemm_stream<128, 3, false, 2, kPair>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32, 1,
-                                                    ep, stream, "tc_simple_normaliser_gemm_3xtf32", extra, B))
-    return rc;
+  if (f16) {
+    // both operands are in (0, 1]: scaled by 2^12 so that entries down to ~3e-5 keep a normal lo half; the product
+    // is scaled back (2^-24, exact) before the log
+    constexpr float kScale = 4096.f;
+    PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, ksteps, lm_max};
+    if (int rc = pack_f16_split(ps, kScale, lm_big, lm_small, lm_p, stream)) return rc;
+    ExpRowSplitProducerF16 a{am, am_max, T, V, kScale, am_p, d.Tpad / 128, B * (d.Tpad / 128)};
+    SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm, 1.f / (kScale * kScale)};
+    if (int rc = launch_gemm_stream<128, 3, false, 3, kPair>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, ksteps,
+                                                             1, ep, stream, "tc_simple_normaliser_gemm_3xf16", extra, B))
+      return rc;
+  } else {
+    PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
+    if (int rc = pack_f32_split(ps, lm_big, lm_small, stream, lm_p, d.kb64)) return rc;
+    ExpRowProducerF32 a{am, am_max, T, V, am_p, d.Tpad / 128, B * (d.Tpad / 128)};
+    SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm, 1.f};
+    if (int rc = launch_gemm_stream<128, 3, false, 2, kPair>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32,
+                                                             1, ep, stream, "tc_simple_normaliser_gemm_3xtf32", extra, B))
+      return rc;
+  }
   const int64_t total = (int64_t)B * S * (T + 1);
   if (total > 0) {
     ProfScope prof("simple_px_kernel", stream);

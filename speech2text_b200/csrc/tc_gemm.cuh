@@ -105,12 +105,15 @@ constexpr int gemm_threads() {
   return 32 * (kCtrlWarps + kEpiWarps * gemm_epi_groups<ASrc, Epi>() + (ASrc::kBulk ? 0 : kProdWarps));
 }
 
+// kKind 3 = 3xF16: every fp32 operand is held as hi = f16(x) and lo = f16(x - hi) (two 64-column blocks per stage),
+// D += A_lo B_hi + A_hi B_lo + A_hi B_hi: the same ~2^-21 accuracy as 3xTF32 at twice the tensor rate and half the
+// operand bytes (operands must fit the f16 range: callers pre-scale by powers of two and undo it in the epilogue).
 // kKind: 0 = bf16 operands; 1 = tf32 (fp32 in smem, single pass); 2 = 3xTF32: every fp32 operand is held
 // as big = rn_tf32(x) and small = x - big, and D += A_big B_big + A_big B_small + A_small B_big, which
 // recovers fp32-level accuracy (error ~2^-21) on the tensor cores.
 template <int BN, int kKind>
 constexpr int gemm_stage_bytes() {
-  return (kKind == 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
+  return (kKind >= 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
 }
 // kBRes > 0: the B operand of the CTA's column tile (kBRes k-steps) stays resident in shared memory and the ring
 // carries A stages only
@@ -204,7 +207,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   static_assert(kBRes == 0 || (!kMn && kKind == 0 && ASrc::kBulk && kCluster == 1),
                 "B-stationary mode: K-major bf16, bulk-fed, no cluster");
   constexpr int kStages = gemm_eff_stages<BN, kStagesReq, kKind, ASrc, Epi, kBRes>();
-  constexpr int kParts = kKind == 2 ? 2 : 1;
+  constexpr int kParts = kKind >= 2 ? 2 : 1;
   constexpr int kABytes = kParts * kBlockBytes;
   constexpr int kBPart = (BN / 128) * kBlockBytes;
   constexpr int kBBytes = kParts * kBPart;
@@ -212,8 +215,8 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   constexpr int kGroups = gemm_epi_groups<ASrc, Epi>();
   constexpr int kScratch = ((Epi::kScratchBytes + 127) / 128) * 128;  // per epilogue group
   constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
-  static_assert(kKind != 2 || !ASrc::kBulk, "3xTF32 expects an on-the-fly A producer that writes big|small");
-  static_assert(kKind == 0 || !kMn, "tf32 operands are K-major only");
+  static_assert(kKind < 2 || !ASrc::kBulk, "split operands expect an on-the-fly A producer that writes big|small");
+  static_assert(kKind == 0 || !kMn, "tf32 / split operands are K-major only");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -316,12 +319,12 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
                 packed_block_index(c.n_tile * (BN / 128) + c.batch * mn.b_batch_off, ks, b_row_blocks) * kBlockBytes;
             if constexpr (kCluster == 1) {
               bulk_copy_g2s(sb, b_packed + boff, kBPart, &full[s]);
-              if constexpr (kKind == 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
+              if constexpr (kKind >= 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
             } else {
               constexpr int kShare = kBPart / kCluster;  // this CTA's share of the stage, delivered to every CTA
               const size_t off = (size_t)crank * kShare;
               bulk_copy_g2s_multicast(sb + off, b_packed + boff + off, kShare, &full[s], kCtaMask);
-              if constexpr (kKind == 2)
+              if constexpr (kKind >= 2)
                 bulk_copy_g2s_multicast(sb + kBPart + off, mn.b_small + boff + off, kShare, &full[s], kCtaMask);
             }
           } else {
@@ -351,7 +354,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      uint32_t idesc = kKind == 0 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
+      uint32_t idesc = kKind == 0 ? umma_idesc_bf16(128, BN) : (kKind == 3 ? umma_idesc_f16(128, BN) : umma_idesc_tf32(128, BN));
       if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       uint32_t git = 0, lt = 0;
       if constexpr (kBRes > 0) {
@@ -385,6 +388,12 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
               umma_bf16(acc, da, db, idesc, accum);
             } else if constexpr (kKind == 1) {
               umma_tf32(acc, da, db, idesc, accum);
+            } else if constexpr (kKind == 3) {
+              const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
+              const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
+              umma_bf16(acc, da_s, db, idesc, accum);  // small terms first
+              umma_bf16(acc, da, db_s, idesc, true);
+              umma_bf16(acc, da, db, idesc, true);
             } else {
               const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
               const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
@@ -644,6 +653,7 @@ struct StoreRowMajorEpi {
   int M, N;
   bool atomic;
   const float* bias = nullptr;  // added per column when not atomic
+  float scale = 1.f;            // applied to the accumulator first (undoes a power-of-two operand pre-scale)
   static constexpr int kScratchBytes = kTransposeScratchBytes;
   struct State {};
   __device__ void begin(State&, const EpiCtx&) const {}
@@ -654,6 +664,7 @@ struct StoreRowMajorEpi {
     warp_transposed_chunk(ctx, acc, N - n, [&](int r, int c, float4 v) {
       const int m = m0 + r, col = n + c;
       if (m >= M || col >= N) return;
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
       float* dst = C + (int64_t)m * ldc + col;
       if (vec_ok && col + 4 <= N) {
         if (atomic) {
@@ -693,13 +704,15 @@ int pack_rows_colsum(const float* src, const float* src2, int64_t ld, int rows, 
                      uint8_t* dst, float* col_sum, cudaStream_t stream);
 
 // Several pack jobs in one launch (weights of a module).  kind 0: bf16 (k_blocks of 64); kind 1 / 2: the
-// big / residual tf32 part of an fp32 operand (k_blocks of 32).  src(r, k) = src[r * row_stride + k * col_stride].
+// big / residual tf32 part of an fp32 operand (k_blocks of 32); kind 3 / 4: the hi / lo f16 part of scale * x
+// (k_blocks of 64).  src(r, k) = src[r * row_stride + k * col_stride].
 struct PackJob {
   const float* src;
   int64_t row_stride, col_stride;
   int rows, K, row_blocks, k_blocks;
   uint8_t* dst;
   int kind;
+  float scale = 1.f;
 };
 struct PackJobs {
   static constexpr int kMax = 6;
@@ -724,6 +737,9 @@ int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream);
 // fp32 operand does not cover must already be zero there
 int pack_f32_split(const PackSpec& p, uint8_t* dst_big, uint8_t* dst_small, cudaStream_t stream,
                    uint8_t* dst_bf16 = nullptr, int bf16_k_blocks = 0);
+// hi / lo f16 halves of scale * f(x) (k_blocks of 64) and, optionally, bf16 f(x) in the same block geometry
+int pack_f16_split(const PackSpec& p, float scale, uint8_t* dst_hi, uint8_t* dst_lo, uint8_t* dst_bf16,
+                   cudaStream_t stream);
 
 // On-the-fly K-major A for tf32: copies 128 rows x 32 fp32 of a row-major matrix into the swizzled stage.
 // Eight lanes cover the 128 bytes one row contributes to a k-step, so a warp-wide load instruction reads
@@ -803,6 +819,69 @@ struct RowCopyProducerF32 {
           emit_stage(buf[u], it + u);
         }
       }
+    }
+  }
+};
+
+// On-the-fly K-major A for the 3xF16 contraction: 128 rows x 64 fp32 of a row-major matrix -> hi | lo half blocks of
+// the stage.  Sixteen lanes cover the 256 bytes one row contributes to a k-step; thread (warp w, lane l) serves rows
+// 2w + l/16 + 16 i, i = 0..7.  Optional by-product: the bf16 packed image of x (same block geometry).
+struct RowSplitProducerF16 {
+  static constexpr bool kBulk = false;
+  const float* x;
+  int64_t ld;
+  int64_t M;
+  int K;
+  uint8_t* bf16_pack = nullptr;
+  int pack_row_blocks = 0;
+  __device__ void run(const ProdCtx& pc) const {
+    const int warp = pc.t >> 5, lane = pc.t & 31;
+    const int c = lane & 15, rbase = warp * 2 + (lane >> 4);
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const bool emit = bf16_pack != nullptr && pc.n_tile == 0 && pc.valid;
+    const int off = rbase * 128 + ((((c >> 1) ^ (rbase & 7)) & 7) << 4) + (c & 1) * 8;
+    auto load = [&](float4 (&dst)[4], int ks, int half) {
+      const int k = ks * 64 + c * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t m = (int64_t)pc.m_tile * 128 + rbase + 16 * (half * 4 + j);
+        const float* row = x + m * ld;
+        if (m < M && vec && k + 4 <= K) {
+          dst[j] = __ldg(reinterpret_cast<const float4*>(row + k));
+        } else {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (m < M && k + e < K) ? __ldg(row + k + e) : 0.f;
+          dst[j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    };
+    auto emit_half = [&](const float4 (&src)[4], int it, int half) {
+      uint8_t* dst = pc.stage(it) + off;
+      const int ks = pc.ks0 + it;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v[4] = {src[j].x, src[j].y, src[j].z, src[j].w};
+        uint2 hi, lo;
+        split_f16x4(v, hi, lo);
+        const int ro = (half * 4 + j) * 16 * 128;
+        *reinterpret_cast<uint2*>(dst + ro) = hi;
+        *reinterpret_cast<uint2*>(dst + kBlockBytes + ro) = lo;
+        if (emit) {
+          uint8_t* blk = bf16_pack + packed_block_index(pc.m_tile, ks, pack_row_blocks) * kBlockBytes;
+          *reinterpret_cast<uint2*>(blk + off + ro) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+        }
+      }
+    };
+    float4 q0[4], q1[4];
+    load(q0, pc.ks0, 0);
+    for (int it = 0; it < pc.n_it; ++it) {
+      load(q1, pc.ks0 + it, 1);
+      pc.wait_empty(it);
+      emit_half(q0, it, 0);
+      if (it + 1 < pc.n_it) load(q0, pc.ks0 + it + 1, 0);
+      emit_half(q1, it, 1);
+      pc.arrive_full(it);
     }
   }
 };

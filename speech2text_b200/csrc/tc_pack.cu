@@ -131,7 +131,7 @@ __global__ void pack_jobs_kernel(PackJobs jobs) {
     r = li % rows_pad;
     ck = li / rows_pad;
   }
-  const int per = job.kind == 0 ? 8 : 4;  // elements per 16-byte chunk
+  const int per = (job.kind == 0 || job.kind >= 3) ? 8 : 4;  // elements per 16-byte chunk
   const int k0 = (int)ck * per;
   float v[8];
 #pragma unroll
@@ -144,6 +144,13 @@ __global__ void pack_jobs_kernel(PackJobs jobs) {
   if (job.kind == 0) {
     *reinterpret_cast<uint4*>(out) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  } else if (job.kind >= 3) {
+    const float a[4] = {v[0] * job.scale, v[1] * job.scale, v[2] * job.scale, v[3] * job.scale};
+    const float b[4] = {v[4] * job.scale, v[5] * job.scale, v[6] * job.scale, v[7] * job.scale};
+    uint2 h0, l0, h1, l1;
+    split_f16x4(a, h0, l0);
+    split_f16x4(b, h1, l1);
+    *reinterpret_cast<uint4*>(out) = job.kind == 3 ? make_uint4(h0.x, h0.y, h1.x, h1.y) : make_uint4(l0.x, l0.y, l1.x, l1.y);
   } else {
     float4 o;
     float* po = &o.x;
@@ -209,7 +216,55 @@ __global__ void pack_batched_kernel(PackSpec p, uint8_t* __restrict__ dst, uint8
   }
 }
 
+// batched hi / lo f16 split of scale * f(x) with the optional exp, plus bf16 f(x): one thread per 16-byte chunk
+__global__ void pack_batched_f16split_kernel(PackSpec p, float scale, uint8_t* __restrict__ dst_hi,
+                                             uint8_t* __restrict__ dst_lo, uint8_t* __restrict__ dst_bf16) {
+  const int chunks_per_row = p.k_blocks * 8;
+  const int64_t total = (int64_t)p.batches * p.rows_pad * chunks_per_row;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ck = (int)(i % chunks_per_row);
+  const int64_t rp = i / chunks_per_row;
+  const int batch = (int)(rp / p.rows_pad), r = (int)(rp % p.rows_pad);
+  const int k0 = ck * 8;
+  const bool row_ok = r < p.rows;
+  const float* src = p.src + (int64_t)batch * p.batch_stride + (int64_t)r * p.row_stride;
+  const float sub = (row_ok && p.row_sub) ? __ldg(p.row_sub + (int64_t)batch * p.rows + r) : 0.f;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = 0.f;
+    if (row_ok && k0 + j < p.K) {
+      x = __ldg(src + k0 + j);
+      if (p.row_sub) x = expf(x - sub);
+    }
+    v[j] = x;
+  }
+  const size_t off = packed_block_index((int)(rp >> 7), ck >> 3, (int)(((int64_t)p.batches * p.rows_pad) >> 7)) * kBlockBytes +
+                     block_chunk_offset((int)(rp & 127), ck & 7);
+  const float a[4] = {v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale};
+  const float b[4] = {v[4] * scale, v[5] * scale, v[6] * scale, v[7] * scale};
+  uint2 h0, l0, h1, l1;
+  split_f16x4(a, h0, l0);
+  split_f16x4(b, h1, l1);
+  *reinterpret_cast<uint4*>(dst_hi + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *reinterpret_cast<uint4*>(dst_lo + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+  if (dst_bf16)
+    *reinterpret_cast<uint4*>(dst_bf16 + off) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
 }  // namespace
+
+int pack_f16_split(const PackSpec& p, float scale, uint8_t* dst_hi, uint8_t* dst_lo, uint8_t* dst_bf16,
+                   cudaStream_t stream) {
+  S2T_REQUIRE(p.rows_pad % 128 == 0 && p.rows_pad >= p.rows && p.k_blocks * 64 >= p.K, "pack_f16_split: bad padding");
+  const int64_t total = (int64_t)p.batches * p.rows_pad * p.k_blocks * 8;
+  if (total == 0) return 0;
+  ProfScope prof("pack_operand_kernel", stream);
+  pack_batched_f16split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, scale, dst_hi, dst_lo, dst_bf16);
+  return check_launch("pack_batched_f16split_kernel");
+}
 
 int pack_bf16(const PackSpec& p, uint8_t* dst, cudaStream_t stream) {
   S2T_REQUIRE(p.rows_pad % 128 == 0 && p.rows_pad >= p.rows && p.k_blocks * 64 >= p.K, "pack_bf16: bad padding");
@@ -238,7 +293,8 @@ int pack_jobs(const PackJob* list, int n, cudaStream_t stream) {
   jobs.first[0] = 0;
   for (int j = 0; j < n; ++j) {
     const PackJob& q = list[j];
-    S2T_REQUIRE(q.row_blocks * 128 >= q.rows && q.k_blocks * (q.kind == 0 ? 64 : 32) >= q.K, "pack_jobs: padded dims too small");
+    S2T_REQUIRE(q.row_blocks * 128 >= q.rows && q.k_blocks * ((q.kind == 0 || q.kind >= 3) ? 64 : 32) >= q.K,
+                "pack_jobs: padded dims too small");
     jobs.job[j] = q;
     jobs.first[j + 1] = jobs.first[j] + (int64_t)q.row_blocks * 128 * q.k_blocks * 8;
   }

@@ -163,7 +163,16 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
   d |= (uint32_t)(M >> 4) << 24;     // M
   return d;
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+// same instruction kind with IEEE half operands (11 significant bits): used for the hi/lo split that carries
+// fp32-level accuracy through three MMAs at the full 16-bit rate
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // D format: f32; A / B format fields 0 = f16
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread (kind::f16 covers f16 and bf16 operands)
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           bool accumulate) {
   asm volatile(
@@ -208,6 +217,23 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
+}
+
+// fp32 -> (hi, lo) halves with hi + lo = x to ~22 significant bits (|x| clamped to the f16 range)
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+// four floats -> four hi halves and four lo halves (8 bytes each)
+__device__ __forceinline__ void split_f16x4(const float (&x)[4], uint2& hi, uint2& lo) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_f16(x[j], h[j], l[j]);
+  hi = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                  (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+  lo = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                  (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
