@@ -234,13 +234,26 @@ struct SimpleEmitTcEpi {
     const float4* info = lm_info + (int64_t)b * (S + 1);
     float* nrow = nrm + ((int64_t)b * (S + 1) + n) * T + t;
     float* prow = py + ((int64_t)b * (S + 1) + n) * T + t;
+    // the per-column lm terms are fetched sixteen at a time ahead of the stores they feed: interleaved with the
+    // stores every load would expose its own L2 round trip (the producers' streaming loads own the small L1)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (n + j <= S) {
-        const float4 li = __ldg(info + n + j);
-        const float nv = logf(acc[j] * acc_scale + FLT_MIN) + li.x + st.amx;
-        nrow[(int64_t)j * T] = nv;
-        prow[(int64_t)j * T] = st.am_blank + li.y - nv;
+    for (int g = 0; g < 2; ++g) {
+      float lx[16], ly[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = n + g * 16 + j;
+        const float4 li = __ldg(info + (c <= S ? c : S));
+        lx[j] = li.x;
+        ly[j] = li.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int jj = g * 16 + j;
+        if (n + jj <= S) {
+          const float nv = logf(acc[jj] * acc_scale + FLT_MIN) + lx[j] + st.amx;
+          nrow[(int64_t)jj * T] = nv;
+          prow[(int64_t)jj * T] = st.am_blank + ly[j] - nv;
+        }
       }
     }
   }

@@ -655,33 +655,52 @@ struct StoreRowMajorEpi {
   const float* bias = nullptr;  // added per column when not atomic
   float scale = 1.f;            // applied to the accumulator first (undoes a power-of-two operand pre-scale)
   static constexpr int kScratchBytes = kTransposeScratchBytes;
-  struct State {};
-  __device__ void begin(State&, const EpiCtx&) const {}
+  // The lane's bias values for the NEXT 32-column chunk (two 16-column halves x 4 columns) are fetched while the
+  // current chunk is transposed: a bias load inside the store callback exposes one L2 round trip per pass, because
+  // the producers' streaming loads leave nothing of the small L1 carve-out.
+  struct State {
+    float4 nb[2];
+  };
+  __device__ __forceinline__ void load_bias(float4 (&b)[2], int n, int lane) const {
+    const bool vec = (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = n + h * 16 + (lane >> 3) * 4;
+      if (bias == nullptr || atomic || col >= N) {
+        b[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (vec && col + 4 <= N) {
+        b[h] = __ldg(reinterpret_cast<const float4*>(bias + col));
+      } else {
+        b[h].x = __ldg(bias + col);
+        b[h].y = col + 1 < N ? __ldg(bias + col + 1) : 0.f;
+        b[h].z = col + 2 < N ? __ldg(bias + col + 2) : 0.f;
+        b[h].w = col + 3 < N ? __ldg(bias + col + 3) : 0.f;
+      }
+    }
+  }
+  __device__ void begin(State& st, const EpiCtx& ctx) const { load_bias(st.nb, ctx.col0, ctx.t & 31); }
   __device__ void end(State&, const EpiCtx&) const {}
-  __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+  __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     const int m0 = ctx.m - (ctx.t & 31);  // first row of this warp
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const float4 cur[2] = {st.nb[0], st.nb[1]};
+    if (n + 32 < ctx.col0 + ctx.ncols) load_bias(st.nb, n + 32, ctx.t & 31);
     warp_transposed_chunk(ctx, acc, N - n, [&](int r, int c, float4 v) {
       const int m = m0 + r, col = n + c;
       if (m >= M || col >= N) return;
-      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      const float4 b = cur[c >> 4];
+      v.x = v.x * scale + b.x; v.y = v.y * scale + b.y; v.z = v.z * scale + b.z; v.w = v.w * scale + b.w;
       float* dst = C + (int64_t)m * ldc + col;
       if (vec_ok && col + 4 <= N) {
-        if (atomic) {
-          atomicAdd(reinterpret_cast<float4*>(dst), v);
-        } else {
-          if (bias) {
-            v.x += __ldg(bias + col); v.y += __ldg(bias + col + 1); v.z += __ldg(bias + col + 2); v.w += __ldg(bias + col + 3);
-          }
-          *reinterpret_cast<float4*>(dst) = v;
-        }
+        if (atomic) atomicAdd(reinterpret_cast<float4*>(dst), v);
+        else *reinterpret_cast<float4*>(dst) = v;
       } else {
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (col + j < N) {
             if (atomic) atomicAdd(dst + j, e[j]);
-            else dst[j] = e[j] + (bias ? __ldg(bias + col + j) : 0.f);
+            else dst[j] = e[j];
           }
         }
       }
