@@ -859,11 +859,13 @@ struct RowSplitProducerF16 {
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const bool emit = bf16_pack != nullptr && pc.n_tile == 0 && pc.valid;
     const int off = rbase * 128 + ((((c >> 1) ^ (rbase & 7)) & 7) << 4) + (c & 1) * 8;
-    auto load = [&](float4 (&dst)[4], int ks, int half) {
+    // Two whole k-steps of raw fp32 (2 x 8 float4 per lane, 64 KB per CTA) are kept in flight: with one k-step
+    // every iteration costs a full DRAM round trip, Little's law then caps the CTA at ~32 KB per microsecond.
+    auto load = [&](float4 (&dst)[8], int ks) {
       const int k = ks * 64 + c * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t m = (int64_t)pc.m_tile * 128 + rbase + 16 * (half * 4 + j);
+      for (int j = 0; j < 8; ++j) {
+        const int64_t m = (int64_t)pc.m_tile * 128 + rbase + 16 * j;
         const float* row = x + m * ld;
         if (m < M && vec && k + 4 <= K) {
           dst[j] = __ldg(reinterpret_cast<const float4*>(row + k));
@@ -875,32 +877,34 @@ struct RowSplitProducerF16 {
         }
       }
     };
-    auto emit_half = [&](const float4 (&src)[4], int it, int half) {
+    auto emit_step = [&](const float4 (&src)[8], int it) {
       uint8_t* dst = pc.stage(it) + off;
       const int ks = pc.ks0 + it;
+      uint8_t* blk = emit ? bf16_pack + packed_block_index(pc.m_tile, ks, pack_row_blocks) * kBlockBytes + off : nullptr;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const float v[4] = {src[j].x, src[j].y, src[j].z, src[j].w};
         uint2 hi, lo;
         split_f16x4(v, hi, lo);
-        const int ro = (half * 4 + j) * 16 * 128;
+        const int ro = j * 16 * 128;
         *reinterpret_cast<uint2*>(dst + ro) = hi;
         *reinterpret_cast<uint2*>(dst + kBlockBytes + ro) = lo;
-        if (emit) {
-          uint8_t* blk = bf16_pack + packed_block_index(pc.m_tile, ks, pack_row_blocks) * kBlockBytes;
-          *reinterpret_cast<uint2*>(blk + off + ro) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-        }
+        if (emit) *reinterpret_cast<uint2*>(blk + ro) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
       }
     };
-    float4 q0[4], q1[4];
-    load(q0, pc.ks0, 0);
-    for (int it = 0; it < pc.n_it; ++it) {
-      load(q1, pc.ks0 + it, 1);
+    float4 qa[8], qb[8];
+    load(qa, pc.ks0);
+    for (int it = 0; it < pc.n_it; it += 2) {
+      if (it + 1 < pc.n_it) load(qb, pc.ks0 + it + 1);
       pc.wait_empty(it);
-      emit_half(q0, it, 0);
-      if (it + 1 < pc.n_it) load(q0, pc.ks0 + it + 1, 0);
-      emit_half(q1, it, 1);
+      emit_step(qa, it);
       pc.arrive_full(it);
+      if (it + 2 < pc.n_it) load(qa, pc.ks0 + it + 2);
+      if (it + 1 < pc.n_it) {
+        pc.wait_empty(it + 1);
+        emit_step(qb, it + 1);
+        pc.arrive_full(it + 1);
+      }
     }
   }
 };
