@@ -24,8 +24,9 @@ namespace {
 
 using namespace tc;
 
-// K-major contractions run as 2-CTA clusters: the B operand of a stage is loaded half by each CTA and multicast
-constexpr int kPair = 1;  // 2 (B multicast across a CTA pair) measured equal within noise on the same box: L2 reads are not what bounds the ring
+// The hidden contraction runs on CTA pairs (tcgen05 cta_group::2: one M = 256 MMA over the two row tiles of a pair,
+// each CTA holding half of the W1 rows of a stage).  Same-box A/B: a shade faster there, a shade slower for dhidden.
+constexpr int kPair = S2T_PAIR;
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -922,8 +923,8 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Gp, ct};
       DHiddenEpi ep{p.I, w.DHp, ct, db1};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / kBN, d.kbV, 1, ep, stream,
-                                                     "tc_joiner_dhidden_gemm"))
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / kBN, d.kbV, 1, ep, stream,
+                                                               "tc_joiner_dhidden_gemm"))
         return rc;
     }
     const int splits = max(1, min(kbM, sms / max(1, (d.Vp / 128) * (d.Ip / kBN))));

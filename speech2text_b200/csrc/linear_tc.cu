@@ -19,7 +19,7 @@ namespace {
 using namespace tc;
 
 // K-major contractions run as 2-CTA clusters: the B operand of a stage is loaded half by each CTA and multicast
-constexpr int kPair = 1;  // 2 (B multicast across a CTA pair) measured equal within noise on the same box: L2 reads are not what bounds the ring
+constexpr int kPair = S2T_PAIR;  // the forward projection runs on CTA pairs (cta_group::2); dx measured better on single CTAs
 
 struct LinDims {
   int Mt, Np, Kp;       // row tiles of x; N, K padded to multiples of 256
@@ -113,7 +113,7 @@ int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M,
   if (dx) {
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dx, K, (int)M, K, false, nullptr};
-    if (int rc = tc::launch_gemm_stream<256, 4, false, 0, kPair>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
+    if (int rc = tc::launch_gemm_stream<256, 4, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
                                                        "tc_linear_dx_gemm"))
       return rc;
   }

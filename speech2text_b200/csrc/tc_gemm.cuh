@@ -82,6 +82,9 @@ constexpr int kProdWarps = 8;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kGroupBytes = 64 * 128;  // one MN-major group: 64 k-rows x 64 elements
 
+#ifndef S2T_PAIR
+#define S2T_PAIR 2
+#endif
 #ifndef S2T_BULK_EPI_GROUPS
 #define S2T_BULK_EPI_GROUPS 4
 #endif
@@ -193,9 +196,13 @@ struct TileCoord {
 // two TMEM accumulator buffers run across tile boundaries: while the epilogue warps drain tile i
 // from one TMEM buffer, the MMA warp already accumulates tile i+1 into the other and the copy /
 // producer warps fill the ring for it.
-// kCluster = 2: the two CTAs of a cluster work on neighbouring row tiles of the same column tile and k range; each
-// loads half of every B stage and multicasts it into both shared memories, so the B operand crosses L2 -> SM
-// once per CTA pair.  A stage is released only when the MMAs of BOTH CTAs have read it (multicast commit).
+// kCluster = 2 (CTA pair, tcgen05 cta_group::2): the two CTAs of a cluster own neighbouring row tiles of the same
+// column tile and k range.  Each keeps its own 128 A rows and only HALF of the B rows of every stage; the leader
+// CTA (rank 0) issues one M = 256 MMA that reads both shared memories and writes 128 accumulator lanes into each
+// CTA's TMEM, so a stage pulls a third less through the L2 -> SM path that bounds the mainloop.  The peer forwards
+// "my half of stage s has landed" to the leader's pfull barrier; the leader's commits release the stage (empty) and
+// publish the accumulator (tfull) in both CTAs; both CTAs' epilogue warps hand the TMEM buffer back on the leader's
+// tempty barrier.
 // kBRes > 0 (B-stationary): a CTA keeps ONE column tile for its whole life, loads that tile's B operand (k_steps <= kBRes
 // k-steps) into shared memory once and streams only A through the ring: a short-K contraction then pulls 16 KB instead
 // of 48 KB per k-step through the L2 -> SM path, which is what bounds the streaming mainloop (profiles/README.md).
@@ -206,12 +213,15 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
   static_assert(kBRes == 0 || (!kMn && kKind == 0 && ASrc::kBulk && kCluster == 1),
                 "B-stationary mode: K-major bf16, bulk-fed, no cluster");
-  constexpr int kStages = gemm_eff_stages<BN, kStagesReq, kKind, ASrc, Epi, kBRes>();
   constexpr int kParts = kKind >= 2 ? 2 : 1;
   constexpr int kABytes = kParts * kBlockBytes;
-  constexpr int kBPart = (BN / 128) * kBlockBytes;
+  constexpr int kBPart = (BN / 128) * kBlockBytes / kCluster;  // this CTA's rows of one B part
   constexpr int kBBytes = kParts * kBPart;
   constexpr int kStageBytes = kBRes > 0 ? kABytes : kABytes + kBBytes;
+  // a pair's stages are smaller (half of B): the ring the launcher sized for single CTAs holds more of them, which the
+  // longer peer -> leader -> commit round trip of a stage needs
+  constexpr int kStages1 = gemm_eff_stages<BN, kStagesReq, kKind, ASrc, Epi, kBRes>();
+  constexpr int kStages = kCluster == 1 ? kStages1 : (kStages1 * gemm_stage_bytes<BN, kKind>()) / kStageBytes;
   constexpr int kGroups = gemm_epi_groups<ASrc, Epi>();
   constexpr int kScratch = ((Epi::kScratchBytes + 127) / 128) * 128;  // per epilogue group
   constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
@@ -227,10 +237,11 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* bres_full = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
+  uint64_t* pfull = bres_full + 1;  // leader of a pair: the peer's half of stage s has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + kStages);
 
   static_assert(kCluster == 1 || kCluster == 2, "clusters of one or two CTAs");
-  static_assert(kCluster == 1 || !kMn, "B multicast is built for K-major operands");
+  static_assert(kCluster == 1 || !kMn, "CTA pairs are built for K-major operands");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
   // streaming: tiles of all (n, m, split, batch), n fastest; B-stationary: the CTA's own column tile, row tiles strided
@@ -267,16 +278,21 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + kProdWarps);
-      mbar_init(&empty[s], kCluster);
+      mbar_init(&empty[s], 1);
+      mbar_init(&pfull[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 32 * kEpiWarps * kGroups);
+      // one CTA: every epilogue thread arrives; pair: one lane per epilogue warp of both CTAs, on the leader's barrier
+      mbar_init(&tempty[i], kCluster == 1 ? 32 * kEpiWarps * kGroups : kCluster * kEpiWarps * kGroups);
     }
     mbar_init(bres_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (kCluster == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    else tmem_alloc_pair<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (kCluster > 1) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
@@ -285,7 +301,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
 
   if (warp == 0) {
     // ---------------- bulk-copy issuer ----------------
-    if (lane == 0) {
+    if (lane == 0 && !(mn.dbg & 16)) {
       uint32_t git = 0;
       if constexpr (kBRes > 0) {
         if (first_tile < num_tiles) {
@@ -317,16 +333,10 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
             }
             const size_t boff =
                 packed_block_index(c.n_tile * (BN / 128) + c.batch * mn.b_batch_off, ks, b_row_blocks) * kBlockBytes;
-            if constexpr (kCluster == 1) {
-              bulk_copy_g2s(sb, b_packed + boff, kBPart, &full[s]);
-              if constexpr (kKind >= 2) bulk_copy_g2s(sb + kBPart, mn.b_small + boff, kBPart, &full[s]);
-            } else {
-              constexpr int kShare = kBPart / kCluster;  // this CTA's share of the stage, delivered to every CTA
-              const size_t off = (size_t)crank * kShare;
-              bulk_copy_g2s_multicast(sb + off, b_packed + boff + off, kShare, &full[s], kCtaMask);
-              if constexpr (kKind >= 2)
-                bulk_copy_g2s_multicast(sb + kBPart + off, mn.b_small + boff + off, kShare, &full[s], kCtaMask);
-            }
+            // a pair: this CTA's half of the column tile's rows (contiguous in the packed layout)
+            const size_t roff = boff + (size_t)crank * kBPart;
+            bulk_copy_g2s(sb, b_packed + roff, kBPart, &full[s]);
+            if constexpr (kKind >= 2) bulk_copy_g2s(sb + kBPart, mn.b_small + roff, kBPart, &full[s]);
           } else {
             // k-step = 64 contraction rows = half of a 128-row block; group = 64 columns = one column block
             if constexpr (ASrc::kBulk) {
@@ -353,9 +363,29 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      uint32_t idesc = kKind == 0 ? umma_idesc_bf16(128, BN) : (kKind == 3 ? umma_idesc_f16(128, BN) : umma_idesc_tf32(128, BN));
+    if (lane == 0 && kCluster > 1 && crank != 0) {
+      // peer of a pair: no MMA of its own; tells the leader when its half of each stage is in shared memory
+      uint32_t git = 0;
+      for (int tile = first_tile; tile < num_tiles && !(mn.dbg & 16); tile += tile_stride) {
+        const TileCoord c = decode(tile);
+        for (int it = 0; it < c.n_it; ++it, ++git) {
+          const int s = git % kStages;
+          mbar_wait(&full[s], (git / kStages) & 1);
+          mbar_arrive_cluster(&pfull[s], 0);
+        }
+      }
+    } else if (lane == 0) {
+      constexpr int kM = 128 * kCluster;
+      uint32_t idesc = kKind == 0 ? umma_idesc_bf16(kM, BN) : (kKind == 3 ? umma_idesc_f16(kM, BN) : umma_idesc_tf32(kM, BN));
       if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
+      auto mma16 = [](uint32_t acc, uint64_t da, uint64_t db, uint32_t id, bool accum) {
+        if constexpr (kCluster == 1) umma_bf16(acc, da, db, id, accum);
+        else umma_f16_pair(acc, da, db, id, accum);
+      };
+      auto mma32 = [](uint32_t acc, uint64_t da, uint64_t db, uint32_t id, bool accum) {
+        if constexpr (kCluster == 1) umma_tf32(acc, da, db, id, accum);
+        else umma_tf32_pair(acc, da, db, id, accum);
+      };
       uint32_t git = 0, lt = 0;
       if constexpr (kBRes > 0) {
         if (first_tile < num_tiles) mbar_wait(bres_full, 0);
@@ -364,12 +394,17 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         const TileCoord c = decode(tile);
         if (c.n_it <= 0) continue;
         const uint32_t buf = lt & 1;
-        mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        // epilogue (of both CTAs of a pair) has drained this accumulator
+        if constexpr (kCluster == 1) mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
+        else mbar_wait_cluster(&tempty[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * BN;
         for (int it = 0; it < c.n_it; ++it, ++git) {
           const int s = git % kStages;
-          mbar_wait(&full[s], (git / kStages) & 1);
+          if (!(mn.dbg & 16)) {
+            mbar_wait(&full[s], (git / kStages) & 1);
+            if constexpr (kCluster > 1) mbar_wait_cluster(&pfull[s], (git / kStages) & 1);
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint32_t sb = kBRes > 0 ? smem_u32(bres + (c.ks0 + it) * kBPart) : sa + kABytes;
@@ -385,31 +420,33 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
             }
             const bool accum = (it > 0) || (k4 > 0);
             if constexpr (kKind == 0) {
-              umma_bf16(acc, da, db, idesc, accum);
+              mma16(acc, da, db, idesc, accum);
             } else if constexpr (kKind == 1) {
-              umma_tf32(acc, da, db, idesc, accum);
+              mma32(acc, da, db, idesc, accum);
             } else if constexpr (kKind == 3) {
               const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
               const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
-              umma_bf16(acc, da_s, db, idesc, accum);  // small terms first
-              umma_bf16(acc, da, db_s, idesc, true);
-              umma_bf16(acc, da, db, idesc, true);
+              mma16(acc, da_s, db, idesc, accum);  // small terms first
+              mma16(acc, da, db_s, idesc, true);
+              mma16(acc, da, db, idesc, true);
             } else {
               const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
               const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
               if (!(mn.dbg & 2)) {
-                umma_tf32(acc, da_s, db, idesc, accum);  // small terms first
-                umma_tf32(acc, da, db_s, idesc, true);
-                umma_tf32(acc, da, db, idesc, true);
+                mma32(acc, da_s, db, idesc, accum);  // small terms first
+                mma32(acc, da, db_s, idesc, true);
+                mma32(acc, da, db, idesc, true);
               } else {
-                umma_tf32(acc, da, db, idesc, accum);
+                mma32(acc, da, db, idesc, accum);
               }
             }
           }
-          if constexpr (kCluster == 1) umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
-          else umma_commit_multicast(&empty[s], kCtaMask);    // ... in both CTAs: the peer multicasts into it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (kCluster == 1) umma_commit(&empty[s]);
+          else umma_commit_pair(&empty[s], kCtaMask);
         }
-        umma_commit(&tfull[buf]);
+        if constexpr (kCluster == 1) umma_commit(&tfull[buf]);
+        else umma_commit_pair(&tfull[buf], kCtaMask);
         ++lt;
       }
     }
@@ -452,7 +489,12 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         epi.end(st, ctx);
       }
       tc_fence_before();
-      mbar_arrive(&tempty[buf]);
+      if constexpr (kCluster == 1) {
+        mbar_arrive(&tempty[buf]);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty[buf], 0);
+      }
       ++lt;
     }
   } else if (warp >= kCtrlWarps + kEpiWarps * kGroups) {
@@ -484,7 +526,10 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   tc_fence_before();
   __syncthreads();
   if constexpr (kCluster > 1) cluster_sync_all();  // nobody leaves while the peer may still signal or multicast
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 1) {
+    if constexpr (kCluster == 1) tmem_dealloc<kTmemCols>(tmem_base);
+    else tmem_dealloc_pair<kTmemCols>(tmem_base);
+  }
 }
 
 inline int gemm_sm_count() {

@@ -621,3 +621,33 @@ def test_bf16_path_agrees_with_fp32_path_on_odd_shapes(shape, monkeypatch):
         assert rel_err(b["pruned"], a["pruned"]) < 5 * BF16_RTOL
         if bool(same.any()):
             assert rel_err(b["d_enc"][same], a["d_enc"][same]) < 3 * BF16_RTOL
+
+
+@pytest.mark.parametrize("pair", [False, True], ids=["single_cta", "cta_pair"])
+@pytest.mark.parametrize("shape", [(128, 128, 64, 128, 1), (300, 200, 100, 128, 1), (1000, 500, 300, 256, 1),
+                                   (130, 256, 8192, 256, 7), (4096, 512, 512, 256, 1)],
+                         ids=lambda s: "x".join(str(v) for v in s))
+def test_streaming_contraction_kernel_single_cta_and_cta_pair(shape, pair, monkeypatch):
+    """The tcgen05 contraction kernel behind every projection of the path, through its debug entry
+    (s2t_tc_gemm: C = A B^T with bf16-rounded operands, fp32 accumulation): one CTA per tile and the
+    cta_group::2 pair mode (M = 256 MMA across two SMs, half of B per CTA) against torch on the same
+    bf16-rounded operands.  Odd sizes exercise the row / column / k tails and the odd last row tile of a pair."""
+    import ctypes
+    from speech2text_b200 import _lib
+    L = _lib.lib()
+    L.s2t_tc_gemm_workspace_bytes.restype = ctypes.c_size_t
+    L.s2t_tc_gemm_workspace_bytes.argtypes = [ctypes.c_int] * 3
+    L.s2t_tc_gemm.restype = ctypes.c_int
+    L.s2t_tc_gemm.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 2
+    monkeypatch.setenv("S2T_GEMM_CLUSTER", "2" if pair else "1")
+    M, N, K, bn, splits = shape
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g).to(_dev())
+    B = torch.randn(N, K, generator=g).to(_dev())
+    C = torch.full((M, N), float("nan"), device=_dev())
+    ws = torch.empty(L.s2t_tc_gemm_workspace_bytes(M, N, K), dtype=torch.uint8, device=_dev())
+    _lib.check(L.s2t_tc_gemm(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, bn, splits, _lib.ptr(ws), _lib.stream()))
+    torch.cuda.synchronize()
+    ref = A.bfloat16().double() @ B.bfloat16().double().t()
+    assert not torch.isnan(C).any()
+    assert ((C.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
