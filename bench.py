@@ -113,7 +113,7 @@ def hot_path_step(joiner, loss_mod, enc, t_len, pred, s_len, labels):
 # ---------------------------------------------------------------------------------------------
 def kernel_work(cfg):
     B, T, U, V, D, R, I = (cfg[k] for k in ("B", "T", "U", "V", "D", "R", "I"))
-    M = B * T * R
+    M = B * T * (R if R > 0 else U + 1)  # joiner rows: pruned band, or the full lattice of the vanilla loss
     S1 = U + 1
     gemm = 2.0 * M * V * max(I, 1)
     simple = 2.0 * B * S1 * T * V
@@ -121,43 +121,55 @@ def kernel_work(cfg):
     band_cells = B * T * R
     proj_enc = 2.0 * B * T * D * V
     proj_pred = 2.0 * B * S1 * D * V
+    rows = float(B * T + B * S1)  # projections: encoder-side and predictor-side launch together
+    Ii = max(I, 1)
+    # name: (algorithmic FLOPs, algorithmic HBM bytes) per STEP, summed over the kernel's launches in it (two for the
+    # projections, one per row chunk when the joiner backward is chunked).  Bytes = every operand the kernel must read once
+    # plus every result it must write once, in the dtype it is stored in (packed bf16 operands 2 B, fp32 4 B); weights
+    # and per-row scalars are left out.  The roofline that bounds a kernel is whichever of FLOPs / tensor peak and
+    # bytes / HBM peak takes longer: every contraction of this path is short and wide (K <= 512 against 10^5 rows),
+    # which puts most of them on the HBM side even at the bf16 tensor rate.
     w = {
-        # name: (bound, algorithmic flops or bytes per launch)
         # strict-fp32 SIMT mode
-        "joiner_hidden_gemm": ("tensor", gemm), "joiner_logits_gemm": ("tensor", gemm),
-        "joiner_dhidden_gemm": ("tensor", gemm), "joiner_dW2_gemm": ("tensor", gemm),
-        "joiner_dW1_gemm": ("tensor", gemm), "joiner_djoint_gemm": ("tensor", gemm),
-        "simple_normaliser_gemm": ("tensor", simple), "simple_d_am_gemm": ("tensor", simple),
-        "simple_d_lm_gemm": ("tensor", simple),
+        "joiner_hidden_gemm": (gemm, 4.0 * M * (V + Ii)), "joiner_logits_gemm": (gemm, 4.0 * M * (V + Ii)),
+        "joiner_dhidden_gemm": (gemm, 4.0 * M * (V + Ii)), "joiner_dW2_gemm": (gemm, 4.0 * M * (V + Ii)),
+        "joiner_dW1_gemm": (gemm, 4.0 * M * (V + Ii)), "joiner_djoint_gemm": (gemm, 4.0 * M * (V + Ii)),
+        "simple_normaliser_gemm": (simple, 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
+        "simple_d_am_gemm": (simple, 4.0 * (B * S1 * T + B * S1 * V + B * T * V)),
+        "simple_d_lm_gemm": (simple, 4.0 * (B * S1 * T + B * S1 * V + B * T * V)),
         # bf16 tensor-core mode (tcgen05): every joiner contraction is 2*M*V*I
-        "tc_joiner_hidden_gemm": ("tensor", gemm), "tc_joiner_logits_lse_gemm": ("tensor", gemm),
-        "tc_joiner_grad_logits_gemm": ("tensor", gemm), "tc_joiner_dhidden_gemm": ("tensor", gemm),
-        "tc_joiner_dW2_gemm": ("tensor", gemm), "tc_joiner_dW1_gemm": ("tensor", gemm),
-        "tc_joiner_djoint_gemm": ("tensor", gemm), "tc_joiner_dh_gemm": ("tensor", gemm),
-        # segmented reductions of dh (bf16 rows) into d_am / d_lm: dh once, am once, lm once, grads read+write
-        # one pass over dh (bf16 rows): dh, am and lm read once, d_am written once, d_lm read-modify-write
-        "djoint_reduce_kernel": ("hbm", M * V * 2.0 + 2 * B * T * V * 4.0 + 3 * B * S1 * V * 4.0),
-        "simple_px_kernel": ("hbm", 4.0 * (2 * B * U * (T + 1) + B * U * T)),
-        # simple (smoothed) loss on tensor cores: exp(am - max) built on the fly, 3xTF32 contraction with exp(lm - max)
-        # over V, px/py emitted from the epilogue: am and lm read once, px/py written once
-        "tc_simple_normaliser_gemm_3xtf32": ("hbm", 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
-        "tc_simple_normaliser_gemm_3xf16": ("hbm", 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
-        "tc_simple_d_am_gemm": ("tensor", simple), "tc_simple_d_lm_gemm": ("tensor", simple),
-        "simple_w_kernel": ("hbm", 12.0 * B * S1 * T), "row_max_kernel": ("hbm", 4.0 * (B * T * V + B * S1 * V)),
-        # projections: two launches per step (encoder and predictor side); average of the two
-        "tc_linear_fwd_gemm_3xtf32": ("tensor", (proj_enc + proj_pred) / 2),
-        "tc_linear_fwd_gemm_3xf16": ("tensor", (proj_enc + proj_pred) / 2),
-        "tc_linear_dx_gemm": ("tensor", (proj_enc + proj_pred) / 2),
-        "tc_linear_dW_gemm": ("tensor", (proj_enc + proj_pred) / 2),
-        "lse_gather_kernel": ("hbm", M * V * 4.0), "logits_grad_kernel": ("hbm", 2.0 * M * V * 4),
-        "joint_act_kernel": ("hbm", M * V * 4.0 * 3), "joint_grad_kernel": ("hbm", M * V * 4.0 * 5),
+        "tc_joiner_hidden_gemm": (gemm, 2.0 * M * V + 2.0 * M * Ii),            # act(am+lm) rows in, hidden rows out
+        "tc_joiner_logits_lse_gemm": (gemm, 2.0 * M * Ii + 12.0 * M),            # hidden in, lse / px / py out
+        "tc_joiner_grad_logits_gemm": (gemm, 2.0 * M * Ii + 2.0 * M * V),        # hidden in, d logits (bf16) out
+        "tc_joiner_dhidden_gemm": (gemm, 2.0 * M * V + 2.0 * M * Ii),            # d logits in, d hidden out
+        "tc_joiner_dW2_gemm": (gemm, 2.0 * M * V + 2.0 * M * Ii),                # d logits and hidden in
+        "tc_joiner_dW1_gemm": (gemm, 2.0 * M * V + 2.0 * M * Ii),                # d hidden and act rows in
+        "tc_joiner_djoint_gemm": (gemm, 2.0 * M * V + 2.0 * M * Ii),
+        "tc_joiner_dh_gemm": (gemm, 2.0 * M * Ii + 2.0 * M * V),                 # d hidden in, d act rows (bf16) out
+        "joint_pack_kernel": (0.0, 4.0 * (B * T * V + B * S1 * V) + 2.0 * M * V),
+        # one pass over the d act rows (bf16): those, am and lm read once, d_am written once, d_lm read-modify-write
+        "djoint_reduce_kernel": (0.0, M * V * 2.0 + 2 * B * T * V * 4.0 + 3 * B * S1 * V * 4.0),
+        "simple_px_kernel": (0.0, 4.0 * (2 * B * U * (T + 1) + B * U * T)),
+        # simple (smoothed) loss on tensor cores: exp(am - max) built on the fly, contraction with exp(lm - max)
+        # over V, nrm/py emitted from the epilogue: am and lm read once, nrm/py written once
+        "tc_simple_normaliser_gemm_3xtf32": (simple, 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
+        "tc_simple_normaliser_gemm_3xf16": (simple, 4.0 * (B * T * V + B * S1 * V) + 8.0 * B * S1 * T),
+        "tc_simple_d_am_gemm": (simple, 2.0 * (B * S1 * T + B * S1 * V) + 8.0 * B * T * V),
+        "tc_simple_d_lm_gemm": (simple, 2.0 * (B * S1 * T + B * T * V) + 8.0 * B * S1 * V),
+        "simple_w_kernel": (0.0, 12.0 * B * S1 * T), "row_max_kernel": (0.0, 4.0 * (B * T * V + B * S1 * V)),
+        "tc_linear_fwd_gemm_3xtf32": (2.0 * rows * D * V, 4.0 * rows * (D + V)),
+        "tc_linear_fwd_gemm_3xf16": (2.0 * rows * D * V, 4.0 * rows * (D + V)),
+        "tc_linear_dx_gemm": (2.0 * rows * D * V, rows * (2.0 * V + 4.0 * D)),
+        "tc_linear_dW_gemm": (2.0 * rows * D * V, 2.0 * rows * (V + D)),
+        "lse_gather_kernel": (0.0, M * V * 4.0), "logits_grad_kernel": (0.0, 2.0 * M * V * 4),
+        "joint_act_kernel": (0.0, M * V * 4.0 * 3), "joint_grad_kernel": (0.0, M * V * 4.0 * 5),
         # lattices: alpha reads px,py and writes alpha; beta the same; occupation reads 4, writes 2
-        "lattice_alpha_kernel": ("hbm", 12.0 * (lat_cells + band_cells) / 2),
-        "lattice_beta_kernel": ("hbm", 20.0 * (lat_cells + band_cells) / 2),
-        "simple_lattice_kernel": ("hbm", 2 * 12.0 * lat_cells),
-        "simple_occupation_kernel": ("hbm", 24.0 * lat_cells),
-        "band_lattice_kernel": ("hbm", 20.0 * band_cells),
-        "prune_ranges_kernel": ("hbm", B * ((U * (T + 1) + S1 * T) * 4.0 + T * R * 8.0)),
+        "lattice_alpha_kernel": (0.0, 12.0 * (lat_cells + band_cells) / 2),
+        "lattice_beta_kernel": (0.0, 20.0 * (lat_cells + band_cells) / 2),
+        "simple_lattice_kernel": (0.0, 2 * 12.0 * lat_cells),
+        "simple_occupation_kernel": (0.0, 24.0 * lat_cells),
+        "band_lattice_kernel": (0.0, 20.0 * band_cells),
+        "prune_ranges_kernel": (0.0, B * ((U * (T + 1) + S1 * T) * 4.0 + T * R * 8.0)),
     }
     return w
 
@@ -315,6 +327,14 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
     torch.cuda.set_device(local_rank)
+    cpus_before = os.sched_getaffinity(0)
+    try:  # run (and first-touch the pinned staging buffers) on the CPUs next to this rank's GPU: a host buffer on the
+        # far socket costs a third of the host -> device bandwidth the end-to-end number is bound by
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:  # pragma: no cover - affinity is an optimisation, never a requirement
+        pass
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
@@ -323,7 +343,7 @@ def main():
 
     batch = make_batch(cfg, 1234 + rank)
     joiner, loss_mod = build_modules(cfg, dev, args.mode)
-    bucket = FlatGradBucket(joiner.parameters())
+    bucket = FlatGradBucket(joiner.parameters()).bind()  # dW kernels write straight into the all-reduce buffer
     d_in = {k: v.to(dev) for k, v in batch.items()}
     enc = d_in["enc"].requires_grad_(True)
     pred = d_in["pred"].requires_grad_(True)
@@ -448,17 +468,27 @@ def main():
         pk = peaks()
         work = kernel_work(cfg)
         roof = None
+        kernel_roofs = {}
+
+        def kernel_roof(name, cnt, ms):
+            # work of all launches of this kernel in one step / their time in one step  (= per-launch work / average
+            # launch duration, the launches of a step being equal shares of it)
+            flops, nbytes = work.get(name, (0.0, 0.0))
+            step_s = ms / args.steps / 1e3
+            t_tc, t_hbm = flops / (pk["tc_sustained"] * 1e12), nbytes / (pk["hbm"] * 1e9)
+            if t_tc > t_hbm:
+                return {"bound": "tensor", "achieved": flops / step_s / 1e12, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
+                        "frac": t_tc / step_s}
+            return {"bound": "hbm", "achieved": nbytes / step_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": t_hbm / step_s}
+
         if report:
+            for kname, (kcnt, kms) in report.items():
+                kr = kernel_roof(kname, kcnt, kms)
+                kernel_roofs[kname] = {"bound": kr["bound"], "frac": round(kr["frac"], 4)}
             top = max(report.items(), key=lambda kv: kv[1][1])
             name, (cnt, ms) = top
-            bound, per_launch = work.get(name, ("hbm", 0.0))
-            avg_s = ms / cnt / 1e3
-            if bound == "tensor":
-                achieved = per_launch / avg_s / 1e12
-                peak, unit = pk["tc_sustained"], "TFLOP/s"
-            else:
-                achieved = per_launch / avg_s / 1e9
-                peak, unit = pk["hbm"], "GB/s"
+            kr = kernel_roof(name, cnt, ms)
             traffic = None
             try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
                 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
@@ -467,19 +497,29 @@ def main():
                     traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
             except OSError:
                 pass
-            roof = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit,
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": pk["source"],
+            roof = {"bound": kr["bound"], "kernel": name, "achieved": kr["achieved"], "peak": kr["peak"], "unit": kr["unit"],
+                    "frac": kr["frac"], "traffic": traffic, "peak_source": pk["source"],
                     "avg_launch_ms": ms / cnt, "launches_timed": cnt,
                     "share_of_step": ms / max(sum(v[1] for v in report.values()), 1e-9),
                     "how": "library CUDA-event timer around every launch, eager second pass of the same steps; "
-                           "share_of_step = this kernel's time / the sum over all of the library's kernels"}
-            if name.endswith("3xtf32"):
-                # fp32-level accuracy costs three tf32 MMAs (half the bf16 rate) per algorithmic product
-                roof["issued_mma_frac"] = roof["frac"] * 6.0
-                roof["note"] = "3xTF32: issued tensor work = 6x the algorithmic bf16-equivalent FLOPs"
-            if name.endswith("3xf16"):
-                roof["issued_mma_frac"] = roof["frac"] * 3.0
-                roof["note"] = "3xF16 (hi/lo split, fp32-level accuracy): issued tensor work = 3x the algorithmic FLOPs"
+                           "share_of_step = this kernel's time / the sum over all of the library's kernels; bound = the "
+                           "slower of algorithmic FLOPs / tensor peak and algorithmic bytes / HBM peak for this kernel"}
+            # the whole step against SURVEY.md section 8(d)'s algorithmic work per utterance
+            Bc, Tc, Sc, Vc, Dc, Rc, Ic = (cfg[k] for k in ("B", "T", "U", "V", "D", "R", "I"))
+            if Rc > 0:
+                fl = 6.0 * (Tc + Sc + 1) * Dc * Vc + 6.0 * (Sc + 1) * Tc * Vc + (12.0 * Tc * Rc * Vc * Ic if Ic > 0 else 0.0)
+                by = (3.0 * (Tc + Sc + 1) * Dc * 4 + 6.0 * (Tc + Sc + 1) * Vc * 4 + 4.0 * (Sc * (Tc + 1) + (Sc + 1) * Tc) * 4
+                      + 2.0 * Tc * Rc * 8 + 4.0 * Tc * Rc * 2 * 4)
+            else:
+                fl = 6.0 * (Tc + Sc + 1) * Dc * Vc + 12.0 * Tc * (Sc + 1) * Vc * max(Ic, 1)
+                by = 3.0 * (Tc + Sc + 1) * Dc * 4 + 6.0 * (Tc + Sc + 1) * Vc * 4
+            t_tc, t_hbm = Bc * fl / (pk["tc_sustained"] * 1e12), Bc * by / (pk["hbm"] * 1e9)
+            step_s = total_ms / args.steps / 1e3
+            roof["step"] = {"algorithmic_gflop_per_utt": fl / 1e9, "algorithmic_mb_per_utt": by / 1e6,
+                            "bound": "tensor" if t_tc > t_hbm else "hbm", "roofline_ms": max(t_tc, t_hbm) * 1e3,
+                            "frac": max(t_tc, t_hbm) / step_s,
+                            "note": "SURVEY.md 8(d): padded T and S, logits never counted; the step is spread over "
+                                    "~26 kernels (kernel_rooflines), none above a tenth of it"}
         kernels = {k: {"launches": c, "ms_per_step": ms / args.steps} for k, (c, ms) in
                    sorted(report.items(), key=lambda kv: -kv[1][1])}
         line = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
@@ -491,8 +531,14 @@ def main():
                         "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps,
                         "h2d": "pinned host -> device on a copy stream, one step ahead of the compute stream "
                                "(speech2text_b200.prefetch.HostBatchPrefetcher)"},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels_ms_per_step": kernels}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels_ms_per_step": kernels,
+                "kernel_rooflines": kernel_roofs}
         if not args.no_cpu_baseline and world == 1:
+            for tid in os.listdir("/proc/self/task"):  # the CPU arm gets every host core back
+                try:
+                    os.sched_setaffinity(int(tid), cpus_before)
+                except OSError:
+                    pass
             base, _ = cpu_arm(cfg, batch, args.cpu_utts, args.cpu_steps, 1,
                               joiner_state={k: v.detach().cpu() for k, v in joiner.state_dict().items()})
             line["cpu_baseline"] = base

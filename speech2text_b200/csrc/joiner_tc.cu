@@ -471,6 +471,22 @@ struct GradEpi {
         }
         x[j] = val;
       }
+    } else if (n + 32 <= V) {
+      // whole chunk inside the vocabulary (all but the last one): no per-element range test, the bias folded into
+      // the exponent offset, the blank column fixed up under a warp-uniform branch -- the epilogue is issue-bound
+      const int cj = st.csym - n;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float t = fmaf(__ldg(b2 + n + j), kLog2e, nl2);
+        float val = gneg * ex2_approx(fmaf(acc[j], kLog2e, t));
+        if (j == cj) val += oxc;
+        x[j] = val;
+      }
+      if (blank >= n && blank < n + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n + j == blank) x[j] += oyc;
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

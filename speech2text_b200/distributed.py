@@ -42,6 +42,24 @@ class FlatGradBucket:
             p.grad = self.flat[off:off + n].view_as(p)
             off += n
 
+    def bind(self) -> "FlatGradBucket":
+        """Let the path's backward kernels write each gradient straight into its slice of the flat buffer
+        (the dW kernels write into the buffer NCCL sends, no extra copy).  A bound parameter's
+        gradient is OVERWRITTEN by every backward pass of the tensor-core path and autograd's accumulate is
+        skipped for it (eight read-modify-write passes per step less); parameters that reach autograd through plain
+        torch ops (strict-fp32 mode projections) still accumulate, so ``zero()`` stays a real zero.  Gradient
+        accumulation over several backward passes must use an unbound bucket."""
+        for p in self.params:
+            p._s2t_grad_sink = p.grad
+        self.bound = True
+        return self
+
+    def unbind(self) -> None:
+        for p in self.params:
+            if hasattr(p, "_s2t_grad_sink"):
+                del p._s2t_grad_sink
+        self.bound = False
+
     def zero(self) -> None:
         self.flat.zero_()
 

@@ -98,6 +98,7 @@ class _SimpleLoss(torch.autograd.Function):
         ctx.mode = mode
         ctx.scales = (float(lm_only_scale), float(am_only_scale))
         ctx.mark_non_differentiable(px_grad, py_grad)
+        ctx.set_materialize_grads(False)  # no zero-filled (B,S,T+1) / (B,S+1,T) gradients for the two lattices
         return scores, px_grad, py_grad
 
     @staticmethod
@@ -105,6 +106,8 @@ class _SimpleLoss(torch.autograd.Function):
         am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws = ctx.saved_tensors
         B, T, V = am.shape
         S = lm.shape[1] - 1
+        if grad_scores is None:
+            return (None,) * 8
         grad_scores = _f32c(grad_scores)
         d_am = torch.empty_like(am)
         d_lm = torch.empty_like(lm)
@@ -131,14 +134,23 @@ def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symb
     return (loss, (px_grad, py_grad)) if return_grad else loss
 
 
+_REDUCE_WEIGHTS: dict = {}
+
+
 def _reduce(scores: Tensor, reduction: str) -> Tensor:
+    """-scores / -mean / -sum.  mean and sum are ONE dot product with a cached constant vector (-1/B or -1): the
+    step is a chain of short kernels, and ``-torch.mean(x)`` is two of them forward and two more backward."""
     if reduction == "none":
         return -scores
-    if reduction == "mean":
-        return -torch.mean(scores)
-    if reduction == "sum":
-        return -torch.sum(scores)
-    raise ValueError(f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+    if reduction not in ("mean", "sum"):
+        raise ValueError(f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+    n = scores.numel()
+    key = (reduction, n, scores.device, scores.dtype)
+    w = _REDUCE_WEIGHTS.get(key)
+    if w is None:
+        w = torch.full((n,), -1.0 / n if reduction == "mean" else -1.0, dtype=scores.dtype, device=scores.device)
+        _REDUCE_WEIGHTS[key] = w
+    return torch.dot(scores.reshape(-1), w)
 
 
 # ---------------------------------------------------------------------------
@@ -224,7 +236,9 @@ class _JoinerLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, am: Tensor, lm: Tensor, W1, b1, W2, b2, symbols: Tensor, ranges: Optional[Tensor],
-                boundary: Tensor, act: int, blank: int, delay_penalty: float, clamp: float, mode: int):
+                boundary: Tensor, act: int, blank: int, delay_penalty: float, clamp: float, mode: int,
+                sinks=None):
+        ctx.sinks = sinks  # (dW1, db1, dW2, db2) buffers written in place by backward, or None
         am, lm = _f32c(am), _f32c(lm)
         symbols, boundary = _i64c(symbols), _i64c(boundary)
         B, T, V = am.shape
@@ -271,7 +285,10 @@ class _JoinerLoss(torch.autograd.Function):
         B, T, V = am.shape
         d_am = torch.empty_like(am)
         d_lm = torch.empty_like(lm)
-        if has_proj:
+        sinks = ctx.sinks if (has_proj and ctx.sinks is not None and all(t is not None for t in ctx.sinks)) else None
+        if sinks is not None:
+            dW1, db1, dW2, db2 = sinks
+        elif has_proj:
             dW1, db1, dW2, db2 = (torch.empty_like(W1), torch.empty_like(b1), torch.empty_like(W2),
                                   torch.empty_like(b2))
         else:
@@ -281,15 +298,18 @@ class _JoinerLoss(torch.autograd.Function):
                                         blank, float(clamp), ptr(workspace), ptr(lse), ptr(occ_px), ptr(occ_py),
                                         ptr(_f32c(grad_scores)), ptr(d_am), ptr(d_lm), ptr(dW1), ptr(db1),
                                         ptr(dW2), ptr(db2), stream()))
-        return (d_am, d_lm, dW1, db1, dW2, db2, None, None, None, None, None, None, None, None)
+        if sinks is not None:
+            dW1 = db1 = dW2 = db2 = None  # already where the optimizer / all-reduce reads them
+        return (d_am, d_lm, dW1, db1, dW2, db2, None, None, None, None, None, None, None, None, None)
 
 
 def joiner_scores(am: Tensor, lm: Tensor, W1, b1, W2, b2, symbols: Tensor, ranges: Optional[Tensor],
                   boundary: Tensor, act: int, blank: int = 0, delay_penalty: float = 0.0,
                   clamp: float = -1.0, mode: int = _lib.MODE_FP32_SIMT) -> Tensor:
     """log P(y|x) per utterance of the (pruned or full) joiner lattice, fused."""
+    sinks = tuple(grad_sink(p) for p in (W1, b1, W2, b2))
     return _JoinerLoss.apply(am, lm, W1, b1, W2, b2, symbols, ranges, boundary, act, blank, delay_penalty,
-                             clamp, mode)
+                             clamp, mode, sinks if all(t is not None for t in sinks) else None)
 
 
 def joiner_materialize(am: Tensor, lm: Tensor, W1, b1, W2, b2, ranges: Optional[Tensor], act: int,
@@ -325,7 +345,8 @@ class _LinearTC(torch.autograd.Function):
     separate pass of autograd over two (M, N) tensors."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, W: Tensor, b: Tensor):
+    def forward(ctx, x: Tensor, W: Tensor, b: Tensor, sink_W: Optional[Tensor] = None, sink_b: Optional[Tensor] = None):
+        ctx.sinks = (sink_W, sink_b)
         lead = x.shape[:-1]
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
@@ -346,21 +367,34 @@ class _LinearTC(torch.autograd.Function):
         if dy is None:
             dy, dy_alias = dy_alias, None
         if dy is None:
-            return None, None, None
+            return None, None, None, None, None
+        sink_W, sink_b = ctx.sinks
         dy2 = _f32c(dy).reshape(M, N)
         dy3 = _f32c(dy_alias).reshape(M, N) if dy_alias is not None else None
         dx = torch.empty((M, K), dtype=torch.float32, device=dy.device) if need_dx else None
-        dW = torch.empty_like(W)
-        db = torch.empty((N,), dtype=torch.float32, device=dy.device)
+        # a bound gradient buffer (FlatGradBucket.bind) is written in place and autograd gets no gradient to add
+        dW = sink_W if sink_W is not None else torch.empty_like(W)
+        db = sink_b if sink_b is not None else torch.empty((N,), dtype=torch.float32, device=dy.device)
         check(lib().s2t_linear_bwd(ptr(dy2), ptr(dy3), ptr(W), M, N, K, ptr(ws), ptr(dx), ptr(dW), ptr(db), stream()))
-        return (dx.reshape(*lead, K) if need_dx else None), dW, db
+        return ((dx.reshape(*lead, K) if need_dx else None), None if sink_W is not None else dW,
+                None if sink_b is not None else db, None, None)
+
+
+def grad_sink(p: Optional[Tensor]) -> Optional[Tensor]:
+    """The buffer ``FlatGradBucket.bind`` attached to a parameter (a view of the flat all-reduce buffer), if any:
+    the backward kernels then write the gradient there instead of handing a temporary to autograd's accumulate."""
+    sink = getattr(p, "_s2t_grad_sink", None) if p is not None else None
+    if sink is not None and (sink.shape != p.shape or sink.dtype != torch.float32 or not sink.is_contiguous()
+                             or sink.device != p.device):
+        raise ValueError("gradient sink must be a contiguous fp32 tensor of the parameter's shape on its device")
+    return sink
 
 
 def linear_tc(x: Tensor, W: Tensor, b: Tensor) -> Tensor:
-    """``F.linear(x, W, b)`` on tcgen05 (3xTF32 forward, bf16 backward); fp32 in, fp32 out."""
-    return _LinearTC.apply(x, W, b)[0]
+    """``F.linear(x, W, b)`` on tcgen05 (3xF16 split forward, bf16 backward); fp32 in, fp32 out."""
+    return _LinearTC.apply(x, W, b, grad_sink(W), grad_sink(b))[0]
 
 
 def linear_tc_pair(x: Tensor, W: Tensor, b: Tensor) -> Tuple[Tensor, Tensor]:
     """Same, as two aliases of the result for two consumers (see _LinearTC)."""
-    return _LinearTC.apply(x, W, b)
+    return _LinearTC.apply(x, W, b, grad_sink(W), grad_sink(b))

@@ -651,3 +651,54 @@ def test_streaming_contraction_kernel_single_cta_and_cta_pair(shape, pair, monke
     ref = A.bfloat16().double() @ B.bfloat16().double().t()
     assert not torch.isnan(C).any()
     assert ((C.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_bound_gradient_bucket_receives_the_same_gradients(monkeypatch):
+    """FlatGradBucket.bind(): the weight-gradient kernels write straight into the flat all-reduce buffer
+     and autograd's accumulate is skipped; the buffer must hold what autograd would have
+    produced, also when the step is repeated (overwrite, not accumulate)."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    from speech2text_b200.distributed import FlatGradBucket
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", "bf16")
+    name = "pruned_loss_test"
+    spec, case = CASES[name], make_case(name)
+    dev = _dev()
+    joiner = Joiner(JoinerConfig(**spec["joiner"]))
+    joiner.load_state_dict({k: torch.from_numpy(v) for k, v in case["weights"].items()})
+    joiner = joiner.to(dev)
+    loss_mod = Loss({"model": "Pruned_Rnnt", "config": spec["loss"]})
+    enc = torch.from_numpy(case["encoder_out"]).to(dev).requires_grad_(True)
+    pred = torch.from_numpy(case["predict_out"]).to(dev).requires_grad_(True)
+    enc_len = torch.from_numpy(case["encoder_out_lengths"]).float().to(dev)
+    tgt_len = torch.from_numpy(case["target_lengths"]).float().to(dev)
+    tgt = torch.from_numpy(case["target"]).to(dev)
+
+    def step():
+        enc.grad = None
+        pred.grad = None
+        logits, boundary, ranges, simple = joiner(enc, enc_len, pred, tgt_len, tgt)
+        pruned = loss_mod({"logits": logits, "logits_length": enc_len, "targets": tgt, "targets_length": tgt_len,
+                           "boundary": boundary, "ranges": ranges})
+        total = 0.5 * simple + 0.5 * pruned
+        total.backward()
+        return total.detach()
+
+    joiner.zero_grad(set_to_none=True)
+    ref_loss = step()
+    ref = {k: p.grad.clone() for k, p in joiner.named_parameters()}
+    ref_enc = enc.grad.clone()
+    bucket = FlatGradBucket(joiner.parameters()).bind()
+    for _ in range(2):  # second pass: overwritten, not accumulated
+        bucket.zero()
+        out = step()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref_loss) < 1e-6
+    assert rel_err(enc.grad, ref_enc) < 2e-3  # atomics order
+    off = 0
+    for k, p in joiner.named_parameters():
+        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off, k  # still the bucket view
+        assert rel_err(p.grad, ref[k]) < 2e-3, k
+        off += p.numel()
+    bucket.unbind()
