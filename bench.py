@@ -484,6 +484,8 @@ def main():
 
         if report:
             for kname, (kcnt, kms) in report.items():
+                if kname not in work:
+                    continue  # small helper kernels (operand packs, row metadata, scatters) carry no work model
                 kr = kernel_roof(kname, kcnt, kms)
                 kernel_roofs[kname] = {"bound": kr["bound"], "frac": round(kr["frac"], 4)}
             top = max(report.items(), key=lambda kv: kv[1][1])

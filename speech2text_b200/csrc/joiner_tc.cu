@@ -783,7 +783,14 @@ TcDims tc_dims(int64_t M, int V, int I) {
   if (rows < 128) rows = 128;
   int64_t all = (int64_t)d.Mt * 128;
   d.chunk = rows < all ? rows : all;
-  d.keep_joint = (size_t)d.Mt * (d.Vp / 64) * kBlockBytes <= ((size_t)4 << 30) && !getenv("S2T_B200_NO_KEEP_JOINT");
+  // Jp is kept while it fits an eighth of the device memory (22 GB of a B200's 180 GB: c5's 13 GB fits); beyond that
+  // the hidden and dW1 contractions rebuild it on the fly in their producer warps
+  static size_t jp_budget = 0;
+  if (jp_budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    jp_budget = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0 ? total_b / 8 : (size_t)4 << 30;
+  }
+  d.keep_joint = (size_t)d.Mt * (d.Vp / 64) * kBlockBytes <= jp_budget && !getenv("S2T_B200_NO_KEEP_JOINT");
   return d;
 }
 
