@@ -506,6 +506,11 @@ def main():
                     "how": "library CUDA-event timer around every launch, eager second pass of the same steps; "
                            "share_of_step = this kernel's time / the sum over all of the library's kernels; bound = the "
                            "slower of algorithmic FLOPs / tensor peak and algorithmic bytes / HBM peak for this kernel"}
+            if name.endswith("3xf16"):
+                fl3 = 3.0 * work[name][0]
+                roof["issued_tensor_frac"] = fl3 / (pk["tc_sustained"] * 1e12) / (ms / args.steps / 1e3)
+                roof["note"] = ("3xF16 (hi/lo half split for fp32-level accuracy): the kernel issues 3x the algorithmic "
+                                "MMA work; issued_tensor_frac = that work / tensor peak / time")
             # the whole step against SURVEY.md section 8(d)'s algorithmic work per utterance
             Bc, Tc, Sc, Vc, Dc, Rc, Ic = (cfg[k] for k in ("B", "T", "U", "V", "D", "R", "I"))
             if Rc > 0:

@@ -43,6 +43,9 @@
 // Epi::kScratchBytes of shared memory are reserved for CTA-level reductions of the epilogue
 // per epilogue group (EpiCtx::scratch); epi_sync(ctx) is a barrier over the 128 threads of a group.
 #pragma once
+#include <cstdio>
+#include <cstring>
+
 #include "common.cuh"
 #include "tc_prims.cuh"
 
@@ -159,8 +162,19 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
   // 64-row k-steps for MN-major operands
   int a_batch_off = 0;
   int b_batch_off = 0;
-  int dbg = 0;  // experiment flags (S2T_DBG): 1 skip epilogue functor, 2 only the big x big MMA, 4 skip the MMA
+  int dbg = 0;  // experiment flags (S2T_DBG): 1 skip epilogue functor, 2 only the big x big MMA, 16 no loads (MMA only)
+  // S2T_TRACE=<kernel label>: CTA 0 records (clock, role event, index) words here; the launcher prints them
+  unsigned long long* trace = nullptr;
 };
+
+constexpr int kTraceCap = 4096;
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int code, int idx) {
+  if (trace != nullptr && blockIdx.x == 0) {
+    const unsigned long long slot = atomicAdd(trace, 1ull);
+    if (slot < (unsigned long long)kTraceCap)
+      trace[1 + slot] = ((unsigned long long)clock64() << 16) | ((unsigned long long)(code & 15) << 12) | (unsigned)(idx & 0xfff);
+  }
+}
 
 // What an on-the-fly A producer sees for one tile: kProdThreads threads fill stage(it) for it in [0, n_it).
 struct ProdCtx {
@@ -172,6 +186,10 @@ struct ProdCtx {
   uint32_t it0;  // ring position of the tile's first k-step
   uint64_t* full;
   uint64_t* empty;
+  unsigned long long* trace = nullptr;
+  __device__ __forceinline__ void mark(int code, int it) const {
+    if (t == 0) trace_mark(trace, code, (int)(it0 + it));
+  }
   __device__ __forceinline__ uint8_t* stage(int it) const { return smem + ((it0 + it) % stages) * stage_bytes; }
   __device__ __forceinline__ void wait_empty(int it) const {
     const uint32_t g = it0 + it;
@@ -337,6 +355,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
             const size_t roff = boff + (size_t)crank * kBPart;
             bulk_copy_g2s(sb, b_packed + roff, kBPart, &full[s]);
             if constexpr (kKind >= 2) bulk_copy_g2s(sb + kBPart, mn.b_small + roff, kBPart, &full[s]);
+            trace_mark(mn.trace, 7, (int)git);
           } else {
             // k-step = 64 contraction rows = half of a 128-row block; group = 64 columns = one column block
             if constexpr (ASrc::kBulk) {
@@ -405,6 +424,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
             mbar_wait(&full[s], (git / kStages) & 1);
             if constexpr (kCluster > 1) mbar_wait_cluster(&pfull[s], (git / kStages) & 1);
           }
+          trace_mark(mn.trace, 3, (int)git);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint32_t sb = kBRes > 0 ? smem_u32(bres + (c.ks0 + it) * kBPart) : sa + kABytes;
@@ -447,6 +467,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         }
         if constexpr (kCluster == 1) umma_commit(&tfull[buf]);
         else umma_commit_pair(&tfull[buf], kCtaMask);
+        trace_mark(mn.trace, 4, (int)lt);
         ++lt;
       }
     }
@@ -461,6 +482,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       if (c.n_it <= 0) continue;
       const uint32_t buf = lt & 1;
       mbar_wait(&tfull[buf], (lt >> 1) & 1);
+      if (warp == kCtrlWarps && lane == 0) trace_mark(mn.trace, 5, (int)lt);
       tc_fence_after();
       EpiCtx ctx;
       ctx.row = quarter * 32 + lane;
@@ -488,6 +510,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         }
         epi.end(st, ctx);
       }
+      if (warp == kCtrlWarps && lane == 0) trace_mark(mn.trace, 6, (int)lt);
       tc_fence_before();
       if constexpr (kCluster == 1) {
         mbar_arrive(&tempty[buf]);
@@ -518,6 +541,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         pc.it0 = git;
         pc.full = full;
         pc.empty = empty;
+        pc.trace = mn.trace;
         asrc.run(pc);
         git += c.n_it;
       }
@@ -570,6 +594,32 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
     if (dbg < 0) dbg = getenv("S2T_DBG") ? atoi(getenv("S2T_DBG")) : 0;
     mn.dbg = dbg;
   }
+  static unsigned long long* trace_buf = nullptr;
+  static int trace_left = 2;  // launches to trace
+  const char* trace_env = getenv("S2T_TRACE");
+  static int trace_seen = 0;  // the first launches of a process are cold: trace the third and fourth
+  const bool tracing = trace_env && strstr(what, trace_env) && trace_seen++ >= 2 && trace_left > 0;
+  if (tracing) {
+    if (!trace_buf) cudaMalloc(&trace_buf, (kTraceCap + 1) * sizeof(unsigned long long));
+    cudaMemsetAsync(trace_buf, 0, (kTraceCap + 1) * sizeof(unsigned long long), stream);
+    mn.trace = trace_buf;
+  }
+  struct TraceDump {
+    unsigned long long* buf; cudaStream_t st; const char* what; int* left;
+    ~TraceDump() {
+      if (!buf) return;
+      cudaStreamSynchronize(st);
+      static unsigned long long host[kTraceCap + 1];
+      cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
+      const unsigned long long n = host[0] < (unsigned long long)kTraceCap ? host[0] : kTraceCap;
+      unsigned long long t0 = ~0ull;
+      for (unsigned long long i = 0; i < n; ++i) if ((host[1 + i] >> 16) < t0) t0 = host[1 + i] >> 16;
+      fprintf(stderr, "S2T_TRACE %s events=%llu\n", what, n);
+      for (unsigned long long i = 0; i < n; ++i)
+        fprintf(stderr, "T %llu %d %d\n", (host[1 + i] >> 16) - t0, (int)((host[1 + i] >> 12) & 15), (int)(host[1 + i] & 0xfff));
+      --*left;
+    }
+  } trace_dump{tracing ? trace_buf : nullptr, stream, what, &trace_left};
   ProfScope prof(what, stream);
   if constexpr (kCluster == 1) {
     kern<<<grid, gemm_threads<ASrc, Epi>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
@@ -941,9 +991,12 @@ struct RowSplitProducerF16 {
     load(qa, pc.ks0);
     for (int it = 0; it < pc.n_it; it += 2) {
       if (it + 1 < pc.n_it) load(qb, pc.ks0 + it + 1);
+      pc.mark(9, it);
       pc.wait_empty(it);
+      pc.mark(1, it);
       emit_step(qa, it);
       pc.arrive_full(it);
+      pc.mark(2, it);
       if (it + 2 < pc.n_it) load(qa, pc.ks0 + it + 2);
       if (it + 1 < pc.n_it) {
         pc.wait_empty(it + 1);

@@ -287,15 +287,18 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }
-// four floats -> four hi halves and four lo halves (8 bytes each)
+// four floats -> four hi halves and four lo halves (8 bytes each).  Packed conversions only (cvt.rn.f16x2.f32 and the
+// half2 -> float2 widening): the scalar cvt.f16.f32 issues on the narrow conversion pipe and made the producers that
+// split a whole operand stage per k-step the slowest role of their kernels (role timeline, profiles/README.md).
 __device__ __forceinline__ void split_f16x4(const float (&x)[4], uint2& hi, uint2& lo) {
-  __half h[4], l[4];
+  float c[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) split_f16(x[j], h[j], l[j]);
-  hi = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-                  (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-  lo = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-                  (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+  for (int j = 0; j < 4; ++j) c[j] = fminf(fmaxf(x[j], -65504.f), 65504.f);
+  const __half2 h01 = __floats2half2_rn(c[0], c[1]), h23 = __floats2half2_rn(c[2], c[3]);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(c[0] - f01.x, c[1] - f01.y), l23 = __floats2half2_rn(c[2] - f23.x, c[3] - f23.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
