@@ -553,7 +553,7 @@ struct StoreRowsBf16Epi {
 // shared-memory tile (no barrier, no shared atomics).  The band of kFrames frames spans only a few symbol
 // positions; the tile is flushed to d_lm with 16-byte reductions, since neighbouring frame chunks meet in
 // the same rows.  Wider spans (unpruned lattices) are processed in windows of kMaxSpan positions.
-constexpr int kDjFrames = 16;
+constexpr int kDjFrames = 8;  // 16 left 2.2 waves of CTAs at c3 (three rounds of 28 us): wave quantisation, not bandwidth, set the time
 constexpr int kDjMaxSpan = 16;
 constexpr int kDjCols = 512;  // columns per pass: 128 threads x 4
 
@@ -633,13 +633,27 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
           *reinterpret_cast<float4*>(drow) = ds;
         };
         const int nf = t1 - t0;
+        // the two register sets keep the loads of one frame in flight, which is less than a DRAM round trip of
+        // work: the dh / am lines of the frames after that are pulled into L2 ahead of their loads
+        auto prefetch_frame = [&](int i) {
+          if (i < nf) {
+            const __nv_bfloat16* gp = dhp + i * frame_stride;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(amp + (int64_t)i * V));
+#pragma unroll
+            for (int q = 0; q < kRB; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + (int64_t)q * ld));
+          }
+        };
+        prefetch_frame(2);
+        prefetch_frame(3);
         Frame fa, fb;
         load_frame(fa, 0);
         for (int i = 0; i < nf; i += 2) {
           if (i + 1 < nf) load_frame(fb, i + 1);
+          prefetch_frame(i + 4);
           reduce_frame(fa, i);
           if (i + 1 < nf) {
             if (i + 2 < nf) load_frame(fa, i + 2);
+            prefetch_frame(i + 5);
             reduce_frame(fb, i + 1);
           }
         }
