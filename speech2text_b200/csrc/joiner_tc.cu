@@ -240,13 +240,48 @@ struct JointMnProducer {
 // backward pass: the hidden contraction is then fed by bulk copies like every other one.
 constexpr int kJpRows = 32;
 
+// tile_live[i] = 1 when any of the rows 128 i .. 128 i + 127 belongs to a frame t < T_b of its utterance.  Padding
+// frames occupy the tail of every utterance's (T R)-row block: at c3 a sixth of the row tiles hold nothing else,
+// and no kernel of the path computes, stores or reads them.
+__global__ void tc_tile_live_kernel(const int64_t* __restrict__ boundary, int64_t M, int T, int R,
+                                    uint8_t* __restrict__ tile_live) {
+  const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  int live = 0;
+  if (m < M) {
+    const int64_t bt = m / R;
+    const int b = (int)(bt / T), t = (int)(bt % T);
+    const int Tb = boundary ? min(max((int)boundary[4 * b + 3], 0), T) : T;
+    live = t < Tb;
+  }
+  live = __syncthreads_or(live);
+  if (threadIdx.x == 0) tile_live[blockIdx.x] = live ? 1 : 0;
+}
+
+// live tiles in ascending order and the exclusive prefix counts (one warp: a ballot per 32 tiles)
+__global__ void tc_live_list_kernel(const uint8_t* __restrict__ tile_live, int Mt, int* __restrict__ live_idx,
+                                    int* __restrict__ live_prefix) {
+  const int lane = threadIdx.x;
+  int count = 0;
+  for (int base = 0; base < Mt; base += 32) {
+    const int i = base + lane;
+    const bool l = i < Mt && tile_live[i] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, l);
+    const int pos = count + __popc(b & ((1u << lane) - 1));
+    if (i < Mt) live_prefix[i] = pos;
+    if (l) live_idx[pos] = i;
+    count += __popc(b);
+  }
+  if (lane == 0) live_prefix[Mt] = count;
+}
+
 template <int kAct>
 __global__ void __launch_bounds__(256) joint_pack_kernel(const float* __restrict__ am, const float* __restrict__ lm,
                                                          const int* __restrict__ am_row, const int* __restrict__ lm_row,
                                                          int64_t M, int V, int row_blocks, int k_blocks,
-                                                         uint8_t* __restrict__ Jp) {
+                                                         uint8_t* __restrict__ Jp, const uint8_t* __restrict__ tile_live) {
   __shared__ int ar[kJpRows], lr[kJpRows];
   const int64_t m0 = (int64_t)blockIdx.x * kJpRows;
+  if (tile_live != nullptr && tile_live[m0 >> 7] == 0) return;  // padding frames only: nobody reads this block
   if (threadIdx.x < kJpRows) {
     const int64_t m = m0 + threadIdx.x;
     ar[threadIdx.x] = m < M ? __ldg(am_row + m) : -1;
@@ -399,6 +434,16 @@ __global__ void lse_combine_kernel(const float* __restrict__ part, const float* 
                                    float* __restrict__ lse, float* __restrict__ px, float* __restrict__ py) {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= rows) return;
+  if (boundary) {  // padding frame: its row tile may never have been computed; the lattice ignores these entries
+    const int64_t bt = m / R;
+    const int b = (int)(bt / T), t = (int)(bt % T);
+    if (t >= min(max((int)boundary[4 * b + 3], 0), T)) {
+      lse[m] = 0.f;
+      px[m] = 0.f;
+      py[m] = 0.f;
+      return;
+    }
+  }
   const float* p = part + m * n_tiles * 2;
   float mx = kNegInf;
   for (int i = 0; i < n_tiles; ++i) mx = fmaxf(mx, p[2 * i]);
@@ -702,7 +747,8 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
               float x[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                x[j] = wgt[q] * __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[q][j], act);
+                // select, not multiply: the dummy row of a skipped slot may sit in a never-written (padding) block
+                x[j] = wgt[q] != 0.f ? __bfloat162float(gb[j]) * act_bwd_fast(a[j] + l[q][j], act) : 0.f;
                 dsum[j] += x[j];
               }
               c.x += x[0]; c.y += x[1]; c.z += x[2]; c.w += x[3];
@@ -820,6 +866,9 @@ struct TcWs {
   uint8_t* Jp;  // packed act(am + lm[ranges]) (rows m, cols v) or nullptr when it would not fit the budget
   uint8_t *Gp, *DHp;
   __nv_bfloat16* dh;  // (chunk rows, Vp) d loss / d (joint pre-activation) before act'
+  uint8_t* tile_live;  // one byte per 128-row tile, or nullptr (J rebuilt on the fly / S2T_B200_NO_DEAD_SKIP)
+  int* live_idx;       // the live tiles, ascending
+  int* live_prefix;    // live tiles before tile i (Mt + 1 entries)
   size_t bytes;
 };
 
@@ -847,6 +896,13 @@ TcWs tc_carve(void* ws, const TcDims& d) {
   w.Gp = (uint8_t*)take((size_t)ct * (d.Vp / 64) * kBlockBytes);
   w.DHp = (uint8_t*)take((size_t)ct * d.kbI * kBlockBytes);
   w.dh = (__nv_bfloat16*)take((size_t)d.chunk * d.Vp * sizeof(__nv_bfloat16));
+  w.tile_live = (uint8_t*)take((size_t)d.Mt);
+  w.live_idx = (int*)take((size_t)d.Mt * sizeof(int));
+  w.live_prefix = (int*)take((size_t)(d.Mt + 1) * sizeof(int));
+  if (!d.keep_joint || getenv("S2T_B200_NO_DEAD_SKIP")) {  // producer-fed paths touch every row
+    w.tile_live = nullptr;
+    w.live_idx = w.live_prefix = nullptr;
+  }
   w.bytes = (size_t)(p - (char*)ws);
   return w;
 }
@@ -887,7 +943,15 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
                                                                        w.am_row, w.lm_row, w.row_sym);
   }
   if (int rc = check_launch("tc_row_meta_kernel")) return rc;
+  if (w.tile_live) {
+    ProfScope prof("tc_row_meta_kernel", stream);
+    tc_tile_live_kernel<<<(unsigned)d.Mt, 128, 0, stream>>>(p.boundary, M, p.T, p.R, w.tile_live);
+    tc_live_list_kernel<<<1, 32, 0, stream>>>(w.tile_live, d.Mt, w.live_idx, w.live_prefix);
+  }
   if (int rc = pack_weights(p, d, w, stream)) return rc;
+  MnDebug live;
+  live.live_idx = w.live_idx;
+  live.live_prefix = w.live_prefix;
   // hidden: M x Ip, K = V.  With J kept for the backward pass it is written once by a fully parallel kernel and the
   // contraction streams it like any packed operand; otherwise the producer warps build it on the fly.
   {
@@ -897,14 +961,16 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
         ProfScope prof("joint_pack_kernel", stream);
         const unsigned grid = (unsigned)(d.Mt * (128 / kJpRows));
         if (p.act == kRelu)
-          joint_pack_kernel<kRelu><<<grid, 256, 0, stream>>>(p.am, p.lm, w.am_row, w.lm_row, M, p.V, d.Mt, d.Vp / 64, w.Jp);
+          joint_pack_kernel<kRelu><<<grid, 256, 0, stream>>>(p.am, p.lm, w.am_row, w.lm_row, M, p.V, d.Mt, d.Vp / 64, w.Jp,
+                                                             w.tile_live);
         else
-          joint_pack_kernel<kTanh><<<grid, 256, 0, stream>>>(p.am, p.lm, w.am_row, w.lm_row, M, p.V, d.Mt, d.Vp / 64, w.Jp);
+          joint_pack_kernel<kTanh><<<grid, 256, 0, stream>>>(p.am, p.lm, w.am_row, w.lm_row, M, p.V, d.Mt, d.Vp / 64, w.Jp,
+                                                             w.tile_live);
       }
       if (int rc = check_launch("joint_pack_kernel")) return rc;
       BulkA a{w.Jp, d.Mt};
-      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0, kPair>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
-                                                               "tc_joiner_hidden_gemm"))
+      if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W1p, d.Ip / 128, d.Mt, d.Ip / kBN, d.kbV, 1, ep, stream,
+                                                               "tc_joiner_hidden_gemm", live))
         return rc;
     } else {
       JointRowProducer a{p.am, p.lm, w.am_row, w.lm_row, M, p.V, p.act, nullptr, d.Mt};
@@ -918,7 +984,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
     BulkA a{w.Hp, d.Mt};
     LseEpi ep{p.b2, w.row_sym, p.V, p.blank, d.n_parts_v, M, w.part, w.sym_logit, w.blank_logit};
     if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, d.Mt, d.n_tiles_v, d.kbI, ep, stream,
-                                                                     "tc_joiner_logits_lse_gemm"))
+                                                                     "tc_joiner_logits_lse_gemm", live))
       return rc;
   }
   {
@@ -944,12 +1010,16 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     const int ct = (int)(rows_pad / 128);       // row tiles of this chunk
     const int kbM = (int)(rows_pad / 64);       // K blocks when rows are the contraction index
     const int tile0 = (int)(row0 / 128);
+    MnDebug live;  // live row tiles of this chunk
+    live.live_idx = w.live_idx;
+    live.live_prefix = w.live_prefix;
+    live.live_off = tile0;
     // G = d loss / d logits of the chunk (+ db2)
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
       if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
-                                                                       "tc_joiner_grad_logits_gemm"))
+                                                                       "tc_joiner_grad_logits_gemm", live))
         return rc;
     }
     // Three independent chains follow G: dW2 (needs G and the hidden activations), and after dhidden, dW1 and dh -> dJ.
@@ -961,7 +1031,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       BulkA a{w.Gp, ct};
       DHiddenEpi ep{p.I, w.DHp, ct, db1};
       if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / kBN, d.kbV, 1, ep, stream,
-                                                               "tc_joiner_dhidden_gemm"))
+                                                               "tc_joiner_dhidden_gemm", live))
         return rc;
     }
     const int splits = max(1, min(kbM, sms / max(1, (d.Vp / 128) * (d.Ip / kBN))));
@@ -970,7 +1040,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       BulkA a{w.Gp, ct};
       StoreRowMajorEpi ep{dW2, p.I, p.V, p.I, true};
       if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.Hp + (size_t)tile0 * kBlockBytes, d.Mt, d.Vp / 128, d.Ip / kBN,
-                                                    kbM, splits, ep, s_dw2, "tc_joiner_dW2_gemm"))
+                                                    kbM, splits, ep, s_dw2, "tc_joiner_dW2_gemm", live))
         return rc;
     }
     cudaStream_t s_dw1 = fj.side(1);  // forked here: after dhidden
@@ -981,7 +1051,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       if (w.Jp) {
         BulkA a{w.Jp + (size_t)tile0 * kBlockBytes, d.Mt};
         if (int rc = launch_gemm_stream<kBN, kNStages, true, 0>(a, w.DHp, ct, d.Vp / 128, d.Ip / kBN, kbM, splits, ep, s_dw1,
-                                                                "tc_joiner_dW1_gemm"))
+                                                                "tc_joiner_dW1_gemm", live))
           return rc;
       } else {
         JointMnProducer a{p.am, p.lm, w.am_row, w.lm_row, row0, M, p.V, p.act};
@@ -995,7 +1065,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       BulkA a{w.DHp, ct};
       StoreRowsBf16Epi ep{w.dh, d.Vp};
       if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
-                                                                       "tc_joiner_dh_gemm"))
+                                                                       "tc_joiner_dh_gemm", live))
         return rc;
       const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;
       {

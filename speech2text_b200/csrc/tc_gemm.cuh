@@ -165,6 +165,15 @@ struct MnDebug {  // descriptor knobs (kept as kernel arguments so a test can pr
   int dbg = 0;  // experiment flags (S2T_DBG): 1 skip epilogue functor, 2 only the big x big MMA, 16 no loads (MMA only)
   // S2T_TRACE=<kernel label>: CTA 0 records (clock, role event, index) words here; the launcher prints them
   unsigned long long* trace = nullptr;
+  // Live row blocks, or null.  Padding frames fill whole 128-row blocks of the joiner lattice; live_idx lists the
+  // blocks that hold at least one real frame (ascending), live_prefix[i] counts the live blocks before block i.  With
+  // the list a row-wise (K-major) contraction walks the live row tiles of [live_off, live_off + m_tiles) only and a
+  // reduction over the rows (MN-major, bulk-fed) walks the k-steps of the live blocks only, both evenly spread over
+  // the CTAs / the k-splits (a static round-robin over all tiles leaves the makespan where it was), and nothing ever
+  // reads or writes a dead block.  Single CTAs only (kCluster == 1).
+  const int* live_idx = nullptr;
+  const int* live_prefix = nullptr;
+  int live_off = 0;
 };
 
 constexpr int kTraceCap = 4096;
@@ -265,15 +274,24 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   // streaming: tiles of all (n, m, split, batch), n fastest; B-stationary: the CTA's own column tile, row tiles strided
   const int first_tile = kBRes > 0 ? (int)blockIdx.x / n_tiles : (int)blockIdx.x / kCluster;
   const int tile_stride = kBRes > 0 ? (int)gridDim.x / n_tiles : (int)gridDim.x / kCluster;
-  const int m_groups = (m_tiles + kCluster - 1) / kCluster;
-  const int num_tiles = kBRes > 0 ? m_tiles : n_tiles * m_groups * batches * k_splits;
-  const int per = (k_steps + k_splits - 1) / k_splits;
+  // live-block list: lo = first list entry of this launch's block range, n_live = live blocks in it
+  const bool listed = kCluster == 1 && (kMn ? ASrc::kBulk : true) && mn.live_idx != nullptr;
+  const int live_lo = listed ? mn.live_prefix[mn.live_off] : 0;
+  const int n_live = listed ? mn.live_prefix[mn.live_off + (kMn ? (k_steps + 1) / 2 : m_tiles)] - live_lo : 0;
+  const int m_rows = (listed && !kMn) ? n_live : m_tiles;      // row tiles to walk
+  const int k_live = (listed && kMn) ? 2 * n_live : k_steps;    // k-steps to walk (two per live 128-row block)
+  const int m_groups = (m_rows + kCluster - 1) / kCluster;
+  const int num_tiles = kBRes > 0 ? m_rows : n_tiles * m_groups * batches * k_splits;
+  const int per = (k_live + k_splits - 1) / k_splits;
+  // position in the walk -> row tile / k-step of the launch
+  auto row_tile = [&](int j) { return (listed && !kMn) ? mn.live_idx[live_lo + j] - mn.live_off : j; };
+  auto k_step = [&](int j) { return (listed && kMn) ? 2 * (mn.live_idx[live_lo + (j >> 1)] - mn.live_off) + (j & 1) : j; };
   constexpr uint16_t kCtaMask = (1u << kCluster) - 1;
   auto decode = [&](int tile) {
     TileCoord c;
     if constexpr (kBRes > 0) {
       c.n_tile = (int)blockIdx.x % n_tiles;
-      c.m_tile = tile;
+      c.m_tile = row_tile(tile);
       c.valid = true;
       c.split = 0;
       c.batch = 0;
@@ -283,13 +301,14 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     }
     c.n_tile = tile % n_tiles;
     int rest = tile / n_tiles;
-    c.m_tile = (rest % m_groups) * kCluster + crank;
-    c.valid = c.m_tile < m_tiles;
+    const int walk_m = (rest % m_groups) * kCluster + crank;
+    c.valid = walk_m < m_rows;
+    c.m_tile = c.valid ? row_tile(walk_m) : walk_m;
     rest /= m_groups;
     c.split = rest % k_splits;
     c.batch = rest / k_splits;
-    c.ks0 = c.split * per;
-    c.n_it = min(k_steps, c.ks0 + per) - c.ks0;
+    c.ks0 = c.split * per;  // in walk positions: the bulk issuer maps them to k-steps
+    c.n_it = min(k_live, c.ks0 + per) - c.ks0;
     return c;
   };
 
@@ -332,9 +351,11 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       }
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const TileCoord c = decode(tile);
-        for (int it = 0; it < c.n_it; ++it, ++git) {
-          const int s = git % kStages, ks = c.ks0 + it;
-          mbar_wait(&empty[s], ((git / kStages) & 1) ^ 1);
+        for (int it = 0; it < c.n_it; ++it) {
+          const int ks = k_step(c.ks0 + it);
+          const int s = git % kStages;
+          const uint32_t g_now = git++;
+          mbar_wait(&empty[s], ((g_now / kStages) & 1) ^ 1);
           uint8_t* sa = smem + s * kStageBytes;
           uint8_t* sb = sa + kABytes;
           if constexpr (kBRes > 0) {
@@ -418,13 +439,15 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         else mbar_wait_cluster(&tempty[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * BN;
-        for (int it = 0; it < c.n_it; ++it, ++git) {
+        bool first = true;  // the first k-step actually issued overwrites the accumulator
+        for (int it = 0; it < c.n_it; ++it) {
           const int s = git % kStages;
+          const uint32_t g_now = git++;
           if (!(mn.dbg & 16)) {
-            mbar_wait(&full[s], (git / kStages) & 1);
-            if constexpr (kCluster > 1) mbar_wait_cluster(&pfull[s], (git / kStages) & 1);
+            mbar_wait(&full[s], (g_now / kStages) & 1);
+            if constexpr (kCluster > 1) mbar_wait_cluster(&pfull[s], (g_now / kStages) & 1);
           }
-          trace_mark(mn.trace, 3, (int)git);
+          trace_mark(mn.trace, 3, (int)g_now);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint32_t sb = kBRes > 0 ? smem_u32(bres + (c.ks0 + it) * kBPart) : sa + kABytes;
@@ -438,7 +461,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
               da = umma_smem_desc_mn(sa + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
               db = umma_smem_desc_mn(sb + k4 * mn.k_advance_bytes, mn.lbo_bytes, mn.sbo_bytes);
             }
-            const bool accum = (it > 0) || (k4 > 0);
+            const bool accum = !first || (k4 > 0);
             if constexpr (kKind == 0) {
               mma16(acc, da, db, idesc, accum);
             } else if constexpr (kKind == 1) {
@@ -461,6 +484,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
               }
             }
           }
+          first = false;
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
           if constexpr (kCluster == 1) umma_commit(&empty[s]);
           else umma_commit_pair(&empty[s], kCtaMask);
@@ -651,12 +675,15 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
 // k-steps, 128 KB of resident B per 256-column tile); anything else goes to the streaming kernel.
 template <int BN, int kStages, int kBRes, class ASrc, class Epi>
 int launch_gemm_bstationary(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
-                            int k_steps, const Epi& epi, cudaStream_t stream, const char* what) {
+                            int k_steps, const Epi& epi, cudaStream_t stream, const char* what,
+                            const MnDebug& live = MnDebug()) {
   constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, 0, ASrc, Epi, kBRes>();
   static_assert(smem <= 227 * 1024, "resident B + A ring + epilogue scratch exceed the 227 KB of one CTA");
   const int sms = gemm_sm_count();
-  if (k_steps > kBRes || n_tiles > sms || getenv("S2T_B200_NO_BSTATIONARY"))
-    return launch_gemm_stream<BN, kStages, false, 0>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, k_steps, 1, epi, stream, what);
+  if (k_steps > kBRes || n_tiles > sms || getenv("S2T_B200_NO_BSTATIONARY")) {
+    return launch_gemm_stream<BN, kStages, false, 0>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, k_steps, 1, epi, stream, what,
+                                                     live);
+  }
   if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0) return 0;
   auto kern = gemm_stream_kernel<BN, kStages, false, 0, ASrc, Epi, 1, kBRes>;
   static bool configured = false;
@@ -672,7 +699,7 @@ int launch_gemm_bstationary(const ASrc& asrc, const uint8_t* b_packed, int b_row
   int per_tile = sms / n_tiles;
   if (per_tile > m_tiles) per_tile = m_tiles;
   const int grid = per_tile * n_tiles;
-  MnDebug mn;
+  MnDebug mn = live;
   {
     static int dbg = -1;
     if (dbg < 0) dbg = getenv("S2T_DBG") ? atoi(getenv("S2T_DBG")) : 0;
