@@ -702,3 +702,53 @@ def test_bound_gradient_bucket_receives_the_same_gradients(monkeypatch):
         assert rel_err(p.grad, ref[k]) < 2e-3, k
         off += p.numel()
     bucket.unbind()
+
+
+def test_padding_tiles_are_skipped_without_changing_results(monkeypatch):
+    """Row tiles of the joiner lattice that hold padding frames only are never computed (live-tile list).
+    Same step with the skip disabled (S2T_B200_NO_DEAD_SKIP) must give the same losses and gradients; the
+    lengths leave most of some utterances' frames as padding and the backward runs in several row chunks."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", "bf16")
+    monkeypatch.setenv("S2T_B200_CHUNK_ROWS", "1024")
+    dev = _dev()
+    B, T, U, V, D = 6, 230, 40, 200, 128
+    g = torch.Generator().manual_seed(77)
+    torch.manual_seed(5)
+    joiner = Joiner(JoinerConfig(input_dim=D, output_dim=V, inner_dim=64, activation="tanh", prune_range=5)).to(dev)
+    loss_mod = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
+    enc = (torch.randn(B, T, D, generator=g) * 0.5).to(dev).requires_grad_(True)
+    pred = (torch.randn(B, U + 1, D, generator=g) * 0.5).to(dev).requires_grad_(True)
+    t_len = torch.tensor([230, 60, 200, 33, 128, 129], device=dev)
+    s_len = torch.tensor([40, 12, 31, 7, 40, 25], device=dev)
+    labels = torch.randint(1, V - 1, (B, U), generator=g)
+    for b in range(B):
+        labels[b, s_len[b]:] = 0
+    labels = labels.to(dev)
+
+    def step():
+        joiner.zero_grad(set_to_none=True)
+        enc.grad = None
+        pred.grad = None
+        logits, boundary, ranges, simple = joiner(enc, t_len, pred, s_len, labels)
+        pruned = loss_mod({"logits": logits, "logits_length": t_len, "targets": labels, "targets_length": s_len,
+                           "boundary": boundary, "ranges": ranges})
+        (0.5 * simple + 0.5 * pruned).backward()
+        torch.cuda.synchronize()
+        return (simple.detach().clone(), pruned.detach().clone(), enc.grad.clone(), pred.grad.clone(),
+                {k: p.grad.clone() for k, p in joiner.named_parameters()})
+
+    skip = step()
+    monkeypatch.setenv("S2T_B200_NO_DEAD_SKIP", "1")
+    full = step()
+    assert torch.isfinite(skip[2]).all() and torch.isfinite(skip[3]).all()
+    assert rel_err(skip[0], full[0]) < 1e-6 and rel_err(skip[1], full[1]) < 1e-6
+    assert rel_err(skip[2], full[2]) < 1e-4 and rel_err(skip[3], full[3]) < 1e-4  # summation order of the reductions
+    for k in skip[4]:
+        assert torch.isfinite(skip[4][k]).all(), k
+        assert rel_err(skip[4][k], full[4][k]) < 1e-4, k
+    # padding frames receive exactly zero gradient
+    for b in range(B):
+        assert float(skip[2][b, int(t_len[b]):].abs().max()) == 0.0 if int(t_len[b]) < T else True
