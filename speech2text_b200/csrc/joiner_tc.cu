@@ -242,36 +242,46 @@ constexpr int kJpRows = 32;
 
 // tile_live[i] = 1 when any of the rows 128 i .. 128 i + 127 belongs to a frame t < T_b of its utterance.  Padding
 // frames occupy the tail of every utterance's (T R)-row block: at c3 a sixth of the row tiles hold nothing else,
-// and no kernel of the path computes, stores or reads them.
-__global__ void tc_tile_live_kernel(const int64_t* __restrict__ boundary, int64_t M, int T, int R,
-                                    uint8_t* __restrict__ tile_live) {
-  const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  int live = 0;
-  if (m < M) {
-    const int64_t bt = m / R;
-    const int b = (int)(bt / T), t = (int)(bt % T);
-    const int Tb = boundary ? min(max((int)boundary[4 * b + 3], 0), T) : T;
-    live = t < Tb;
+// and no kernel of the path computes, stores or reads them.  live_idx lists the live tiles in ascending order,
+// live_prefix[i] counts the live tiles before tile i (Mt + 1 entries).  One block: flags, block scan, lists.
+__global__ void __launch_bounds__(1024) tc_live_tiles_kernel(const int64_t* __restrict__ boundary, int64_t M, int T, int R,
+                                                            int Mt, uint8_t* __restrict__ tile_live,
+                                                            int* __restrict__ live_idx, int* __restrict__ live_prefix) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < Mt; base += 1024) {
+    const int i = base + threadIdx.x;
+    int live = 0;
+    if (i < Mt) {
+      const int64_t m0 = (int64_t)i * 128, m1 = min(M, m0 + 128) - 1;
+      const int64_t f0 = m0 / R, f1 = m1 / R;  // first and last frame (b T + t) of the tile
+      for (int64_t b = f0 / T; b <= f1 / T && !live; ++b) {
+        const int ts = (int)(max(f0, b * T) - b * T);  // first frame of the tile inside utterance b
+        const int Tb = boundary ? min(max((int)boundary[4 * b + 3], 0), T) : T;
+        live = ts < Tb;
+      }
+      tile_live[i] = (uint8_t)live;
+    }
+    // exclusive scan of the flags over the block
+    const unsigned bal = __ballot_sync(0xffffffffu, live != 0);
+    const int in_warp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < warp; ++w) before += warp_sums[w];
+    const int pos = before + in_warp;
+    if (i < Mt) {
+      live_prefix[i] = pos;
+      if (live) live_idx[pos] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + (live ? 1 : 0);
+    __syncthreads();
   }
-  live = __syncthreads_or(live);
-  if (threadIdx.x == 0) tile_live[blockIdx.x] = live ? 1 : 0;
-}
-
-// live tiles in ascending order and the exclusive prefix counts (one warp: a ballot per 32 tiles)
-__global__ void tc_live_list_kernel(const uint8_t* __restrict__ tile_live, int Mt, int* __restrict__ live_idx,
-                                    int* __restrict__ live_prefix) {
-  const int lane = threadIdx.x;
-  int count = 0;
-  for (int base = 0; base < Mt; base += 32) {
-    const int i = base + lane;
-    const bool l = i < Mt && tile_live[i] != 0;
-    const unsigned b = __ballot_sync(0xffffffffu, l);
-    const int pos = count + __popc(b & ((1u << lane) - 1));
-    if (i < Mt) live_prefix[i] = pos;
-    if (l) live_idx[pos] = i;
-    count += __popc(b);
-  }
-  if (lane == 0) live_prefix[Mt] = count;
+  if (threadIdx.x == 0) live_prefix[Mt] = carry;
 }
 
 template <int kAct>
@@ -937,18 +947,19 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   if (M == 0) return 0;
   TcDims d = tc_dims(M, p.V, p.I);
   TcWs w = tc_carve(workspace, d);
+  ForkJoin fj(stream);
+  if (w.tile_live) {
+    // one small block, needed first by the J pre-pass: runs beside the row metadata and the weight packs
+    tc_live_tiles_kernel<<<1, 1024, 0, fj.side(0)>>>(p.boundary, M, p.T, p.R, d.Mt, w.tile_live, w.live_idx, w.live_prefix);
+  }
   {
     ProfScope prof("tc_row_meta_kernel", stream);
     tc_row_meta_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(p.ranges, p.sym, M, p.T, p.R, p.S, p.blank,
                                                                        w.am_row, w.lm_row, w.row_sym);
   }
   if (int rc = check_launch("tc_row_meta_kernel")) return rc;
-  if (w.tile_live) {
-    ProfScope prof("tc_row_meta_kernel", stream);
-    tc_tile_live_kernel<<<(unsigned)d.Mt, 128, 0, stream>>>(p.boundary, M, p.T, p.R, w.tile_live);
-    tc_live_list_kernel<<<1, 32, 0, stream>>>(w.tile_live, d.Mt, w.live_idx, w.live_prefix);
-  }
   if (int rc = pack_weights(p, d, w, stream)) return rc;
+  fj.join();
   MnDebug live;
   live.live_idx = w.live_idx;
   live.live_prefix = w.live_prefix;
