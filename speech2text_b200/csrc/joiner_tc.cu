@@ -376,8 +376,13 @@ struct HiddenEpi {
   __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     float x[32];
     const bool live = ctx.m < M;
+    if (n + 32 <= I) {  // interior chunk: one select per row instead of a range test per element
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = (live && n + j < I) ? acc[j] + __ldg(b1 + n + j) : 0.f;
+      for (int j = 0; j < 32; ++j) x[j] = live ? acc[j] + __ldg(b1 + n + j) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = (live && n + j < I) ? acc[j] + __ldg(b1 + n + j) : 0.f;
+    }
     store_packed_row32(ctx, Hp, h_row_blocks, n, x);
   }
 };
@@ -402,10 +407,18 @@ struct LseEpi {
     if (ctx.m >= M || n >= V) return;
     float x[32];
     float cm = kNegInf;
+    if (n + 32 <= V) {  // interior chunk: no per-element range test (the epilogue is issue-bound)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      x[j] = (n + j < V) ? acc[j] + __ldg(b2 + n + j) : kNegInf;
-      cm = fmaxf(cm, x[j]);
+      for (int j = 0; j < 32; ++j) {
+        x[j] = acc[j] + __ldg(b2 + n + j);
+        cm = fmaxf(cm, x[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        x[j] = (n + j < V) ? acc[j] + __ldg(b2 + n + j) : kNegInf;
+        cm = fmaxf(cm, x[j]);
+      }
     }
     if (cm > st.mx) {
       st.sum *= ex2_approx((st.mx - cm) * kLog2e);  // (-inf - finite) -> 0 on the first chunk
@@ -572,8 +585,13 @@ struct DHiddenEpi {
   __device__ void end(State&, const EpiCtx&) const {}
   __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     float x[32];
+    if (n + 32 <= I) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = (n + j < I) ? acc[j] : 0.f;
+      for (int j = 0; j < 32; ++j) x[j] = acc[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = (n + j < I) ? acc[j] : 0.f;
+    }
     store_packed_row32(ctx, DHp, dh_row_blocks, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
