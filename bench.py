@@ -111,9 +111,11 @@ def hot_path_step(joiner, loss_mod, enc, t_len, pred, s_len, labels):
 # ---------------------------------------------------------------------------------------------
 # algorithmic work of each kernel (per launch group), for the roofline of the dominant one
 # ---------------------------------------------------------------------------------------------
-def kernel_work(cfg):
+def kernel_work(cfg, live_frames: float = 1.0):
+    """live_frames = real frames / padded frames of the batch: the joiner kernels skip the row tiles of padding
+    frames, so their work is counted on the real frames only (the padded count would flatter them)."""
     B, T, U, V, D, R, I = (cfg[k] for k in ("B", "T", "U", "V", "D", "R", "I"))
-    M = B * T * (R if R > 0 else U + 1)  # joiner rows: pruned band, or the full lattice of the vanilla loss
+    M = B * T * (R if R > 0 else U + 1) * live_frames  # joiner rows: pruned band, or the vanilla full lattice
     S1 = U + 1
     gemm = 2.0 * M * V * max(I, 1)
     simple = 2.0 * B * S1 * T * V
@@ -466,7 +468,7 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        work = kernel_work(cfg)
+        work = kernel_work(cfg, float(batch["t_len"].sum()) / (cfg["B"] * cfg["T"]))
         roof = None
         kernel_roofs = {}
 
