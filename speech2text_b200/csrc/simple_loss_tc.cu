@@ -429,10 +429,9 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   float4* lm_info = (float4*)((uint8_t*)ws + 2 * d.lm_f32 + d.am_bf16 + d.lm_bf16 + d.wst + d.wts);
   const int wpb = 8;
   const int64_t rows_am = (int64_t)B * T, rows_lm = (int64_t)B * (S + 1);
+  // lm first: its hi/lo split (the B operand of the normaliser) then runs on a side stream next to the am row maxima
   {
-    ProfScope prof("row_max_kernel", stream, 2);
-    tc_row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max, nullptr, S,
-                                                                                      blank, nullptr);
+    ProfScope prof("row_max_kernel", stream);
     tc_row_max_kernel<<<(unsigned)((rows_lm + wpb - 1) / wpb), wpb * 32, 0, stream>>>(lm, rows_lm, V, lm_max, sym, S,
                                                                                       blank, lm_info);
   }
@@ -449,12 +448,22 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   MnDebug extra;
   extra.b_small = lm_small;
   extra.b_batch_off = d.Spad / 128;
+  auto row_max_am = [&]() {
+    ProfScope prof("row_max_kernel", stream);
+    tc_row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max, nullptr, S,
+                                                                                      blank, nullptr);
+  };
   if (f16) {
     // both operands are in (0, 1]: scaled by 2^12 so that entries down to ~3e-5 keep a normal lo half; the product
     // is scaled back (2^-24, exact) before the log
     constexpr float kScale = 4096.f;
     PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, ksteps, lm_max};
-    if (int rc = pack_f16_split(ps, kScale, lm_big, lm_small, lm_p, stream)) return rc;
+    {
+      ForkJoin fj(stream);
+      if (int rc = pack_f16_split(ps, kScale, lm_big, lm_small, lm_p, fj.side(0))) return rc;
+      row_max_am();
+    }  // joined
+    if (int rc = check_launch("row_max_kernel")) return rc;
     ExpRowSplitProducerF16 a{am, am_max, T, V, kScale, am_p, d.Tpad / 128, B * (d.Tpad / 128)};
     SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm, 1.f / (kScale * kScale)};
     if (int rc = launch_gemm_stream<128, 3, false, 3, kPair>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, ksteps,
@@ -462,6 +471,8 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
       return rc;
   } else {
     PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
+    row_max_am();
+    if (int rc = check_launch("row_max_kernel")) return rc;
     if (int rc = pack_f32_split(ps, lm_big, lm_small, stream, lm_p, d.kb64)) return rc;
     ExpRowProducerF32 a{am, am_max, T, V, am_p, d.Tpad / 128, B * (d.Tpad / 128)};
     SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm, 1.f};
