@@ -24,8 +24,8 @@ namespace {
 
 using namespace tc;
 
-// The hidden contraction runs on CTA pairs (tcgen05 cta_group::2: one M = 256 MMA over the two row tiles of a pair,
-// each CTA holding half of the W1 rows of a stage).  Same-box A/B: a shade faster there, a shade slower for dhidden.
+// CTA pairs (tcgen05 cta_group::2) remain for the producer-fed hidden contraction of the no-keep path; the bulk-fed
+// contractions walk the live-tile list (padding frames skipped), which is a single-CTA schedule.
 constexpr int kPair = S2T_PAIR;
 
 constexpr float kLog2e = 1.4426950408889634f;
