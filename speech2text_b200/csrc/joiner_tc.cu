@@ -864,7 +864,14 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.kbI = d.Ip / 64;
   d.n_tiles_v = d.Vp / kBN;
   d.n_parts_v = kLseGroups * d.n_tiles_v;  // one partial per (column tile, epilogue group)
-  const size_t budget = (size_t)1 << 30;  // bytes of one orientation of the chunk's G
+  // device-memory budgets (queried once): an eighth of the memory for the kept J, a 48th (3.7 GB of a B200's 180 GB,
+  // at least 1 GiB) for each of the two (chunk rows x Vp) bf16 buffers of the backward pass
+  static size_t jp_budget = 0;
+  if (jp_budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    jp_budget = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0 ? total_b / 8 : (size_t)4 << 30;
+  }
+  const size_t budget = jp_budget / 6 > ((size_t)1 << 30) ? jp_budget / 6 : (size_t)1 << 30;
   int64_t rows = (int64_t)(budget / ((size_t)d.Vp * 2));
   if (const char* e = getenv("S2T_B200_CHUNK_ROWS")) rows = atoll(e);  // test hook: force the multi-chunk backward
   rows = (rows / 128) * 128;
@@ -873,11 +880,6 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.chunk = rows < all ? rows : all;
   // Jp is kept while it fits an eighth of the device memory (22 GB of a B200's 180 GB: c5's 13 GB fits); beyond that
   // the hidden and dW1 contractions rebuild it on the fly in their producer warps
-  static size_t jp_budget = 0;
-  if (jp_budget == 0) {
-    size_t free_b = 0, total_b = 0;
-    jp_budget = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0 ? total_b / 8 : (size_t)4 << 30;
-  }
   d.keep_joint = (size_t)d.Mt * (d.Vp / 64) * kBlockBytes <= jp_budget && !getenv("S2T_B200_NO_KEEP_JOINT");
   return d;
 }
