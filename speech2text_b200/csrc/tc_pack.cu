@@ -75,8 +75,11 @@ __global__ void __launch_bounds__(256) pack_rows_colsum_kernel(const float* __re
   const bool vec = ((ld & 3) == 0) && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(src2)) & 15) == 0);
   uint8_t* blk = dst + packed_block_index(rb, kb, row_blocks) * kBlockBytes;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // blockIdx.z = upper / lower 64 rows of the block: 128 x 64 tiles gave 1600 CTAs for the encoder-side dy of c3,
+  // 1.35 waves of the 1184 resident ones, i.e. two rounds for 1.35 rounds of work
 #pragma unroll
-  for (int pass = 0; pass < 8; ++pass) {
+  for (int pp = 0; pp < 4; ++pp) {
+    const int pass = (int)blockIdx.z * 4 + pp;
     const int rr = pass * 16 + rl;
     const int64_t r = (int64_t)rb * 128 + rr;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -281,7 +284,7 @@ int pack_rows_colsum(const float* src, const float* src2, int64_t ld, int rows, 
   if (row_blocks == 0 || k_blocks == 0) return 0;
   S2T_REQUIRE(k_blocks <= 65535, "pack_rows_colsum: K too large");
   ProfScope prof("pack_operand_kernel", stream);
-  pack_rows_colsum_kernel<<<dim3((unsigned)row_blocks, (unsigned)k_blocks), 256, 0, stream>>>(src, src2, ld, rows, K, row_blocks, dst,
+  pack_rows_colsum_kernel<<<dim3((unsigned)row_blocks, (unsigned)k_blocks, 2), 256, 0, stream>>>(src, src2, ld, rows, K, row_blocks, dst,
                                                                                             col_sum);
   return check_launch("pack_rows_colsum_kernel");
 }
