@@ -39,10 +39,12 @@ WORKLOADS = {
                desc="zipformer_stateless_pruned_rnnt.yaml joiner, sample_data-shaped lengths"),
     "c2": dict(B=32, T=250, U=50, V=500, D=512, R=-1, I=256, act="tanh",
                desc="vanilla Rnnt full-lattice loss, synthetic B=32 T=250 U=50 V=500 joiner D=512"),
-    "c3": dict(B=64, T=400, U=100, V=500, D=512, R=5, I=256, act="tanh",
-               desc="pruned RNN-T prune_range=5, synthetic B=64 T=400 U=100 V=500 D=512"),
-    "c4": dict(B=128, T=500, U=100, V=2000, D=512, R=5, I=256, act="tanh",
-               desc="CTC_Hybrid_Rnnt, the pruned RNN-T half: B=128 T=500 U=100 V=2000 D=512 prune_range=5"),
+    # "bf16 joiner" (BASELINE config 3, SURVEY 8(d) e = 2): the activations arrive as bf16 in tensor-core mode
+    "c3": dict(B=64, T=400, U=100, V=500, D=512, R=5, I=256, act="tanh", in_dtype="bf16",
+               desc="pruned RNN-T prune_range=5, synthetic B=64 T=400 U=100 V=500 D=512, bf16 joiner"),
+    "c4": dict(B=128, T=500, U=125, V=2000, D=512, R=5, I=256, act="tanh", ctc=True,
+               desc="CTC + pruned RNN-T loss on shared encoder output (PrunedRnntTask enable_ctc, rnnt_task.py:485-496): "
+                    "B=128 T=500 U=125 V=2000 D=512 prune_range=5"),
     "c5": dict(B=256, T=1000, U=250, V=5000, D=1024, R=5, I=256, act="tanh",
                desc="large-vocab pruned RNN-T V=5000 D=1024 prune_range=5, B=256/GPU"),
 }
@@ -61,8 +63,9 @@ def peaks():
 # ---------------------------------------------------------------------------------------------
 # synthetic inputs
 # ---------------------------------------------------------------------------------------------
-def make_batch(cfg, seed: int):
-    """Host tensors.  Longest item full length, others T_b ~ U[0.6T, T], S_b ~ T_b*U/T*U[0.8,1]."""
+def make_batch(cfg, seed: int, in_dtype: str = "f32"):
+    """Host tensors.  Longest item full length, others T_b ~ U[0.6T, T], S_b ~ T_b*U/T*U[0.8,1].
+    in_dtype "bf16": encoder_out / predict_out are rounded to bf16 (both arms start from the same rounded values)."""
     g = torch.Generator().manual_seed(seed)
     B, T, U, V, D = cfg["B"], cfg["T"], cfg["U"], cfg["V"], cfg["D"]
     enc = torch.randn(B, T, D, generator=g) * 0.5
@@ -75,7 +78,13 @@ def make_batch(cfg, seed: int):
     labels = torch.randint(1, V - 1, (B, U), generator=g)
     for b in range(B):
         labels[b, s_len[b]:] = 0  # pad_sequence(padding_value=0), dataset/utils.py:189-191
+    if in_dtype == "bf16":
+        enc, pred = enc.bfloat16(), pred.bfloat16()
     return dict(enc=enc, pred=pred, t_len=t_len, s_len=s_len, labels=labels)
+
+
+def input_dtype(cfg, mode: str) -> str:
+    return cfg.get("in_dtype", "f32") if mode == "bf16" else "f32"
 
 
 def build_modules(cfg, device, mode: str):
@@ -229,20 +238,24 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's own CPU path (oracle port over the k2 restatement + torch CPU ops)
 # ---------------------------------------------------------------------------------------------
-def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None):
+def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None, threads: int = 0):
+    """Times the reference's CPU path (oracle port) on the first n utterances of the batch.  Returns (baseline dict,
+    seconds per step, results of the last step) -- the results feed the bench line's ``parity`` block."""
     from oracle import reference_port as port
     n = min(n_utts, cfg["B"])
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads if threads > 0 else (os.cpu_count() or 1))
     jc = dict(input_dim=cfg["D"], output_dim=cfg["V"], inner_dim=max(cfg["I"], 1), activation=cfg["act"],
               prune_range=cfg["R"], use_out_project=cfg["I"] > 0)
     if joiner_state is None:
         from oracle.cases import make_weights
         import numpy as np
         joiner_state = {k: torch.from_numpy(v) for k, v in make_weights(jc, np.random.RandomState(1234)).items()}
-    enc = batch["enc"][:n].clone()
-    pred = batch["pred"][:n].clone()
+    enc = batch["enc"][:n].float().clone()
+    pred = batch["pred"][:n].float().clone()
     t_len, s_len, labels = batch["t_len"][:n].clone(), batch["s_len"][:n].clone(), batch["labels"][:n].clone()
     # torchaudio-style constraint of the sample: keep padded shapes of the full batch
+
+    last = {}
 
     def one():
         w = {k: v.clone().float().requires_grad_(True) for k, v in joiner_state.items()}
@@ -250,11 +263,16 @@ def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None)
         p = pred.clone().requires_grad_(True)
         if cfg["R"] <= 0:
             logits, _, _, _ = port.joiner_forward(w, jc, e, t_len, p, s_len, None)
-            port.rnnt_loss(logits, labels, t_len, s_len).backward()
+            total = port.rnnt_loss(logits, labels, t_len, s_len)
+            total.backward()
+            last.update(total=total.detach(), d_enc=e.grad, d_pred=p.grad)
             return
         logits, boundary, ranges, simple = port.joiner_forward(w, jc, e, t_len, p, s_len, labels)
         pruned = port.pruned_rnnt_loss(logits, labels, boundary, ranges)
-        (0.5 * simple + 0.5 * pruned).backward()
+        total = 0.5 * simple + 0.5 * pruned
+        total.backward()
+        last.update(total=total.detach(), simple=simple.detach(), pruned=pruned.detach(), ranges=ranges, d_enc=e.grad,
+                    d_pred=p.grad)
 
     for _ in range(warmup):
         one()
@@ -266,7 +284,49 @@ def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None)
     sec = sum(times) / len(times)
     return dict(value=n / sec, unit="utt/s", cores=torch.get_num_threads(), kind="port",
                 sample=f"{n} of {cfg['B']} utterances per step (same shapes/lengths as the GPU batch), "
-                       f"{steps} steps after {warmup} warm-up, {sec:.2f} s/step"), sec
+                       f"{steps} steps after {warmup} warm-up, {sec:.2f} s/step"), sec, last
+
+
+def parity_block(cfg, batch, ref, n, joiner, loss_mod, dev, mode):
+    """The timed configuration checked against the CPU baseline's results on the SAME batch and weights (first n
+    utterances, one eager step): relative loss errors, the rate of prune-range entries that differ, and the
+    gradient of encoder_out over the utterances whose windows all agree (max |diff| / max |ref|)."""
+    sub = {k: v[:n].to(dev) for k, v in batch.items()}
+    enc = sub["enc"].detach().requires_grad_(True)
+    pred = sub["pred"].detach().requires_grad_(True)
+    joiner.zero_grad(set_to_none=True)  # drops the bucket aliases: this step goes through plain autograd
+    ranges = None
+    if joiner.prune_range > 0:
+        logits, boundary, ranges, simple = joiner(enc, sub["t_len"], pred, sub["s_len"], sub["labels"])
+        pruned = loss_mod({"logits": logits, "logits_length": sub["t_len"], "targets": sub["labels"],
+                           "targets_length": sub["s_len"], "boundary": boundary, "ranges": ranges})
+        total = 0.5 * simple + 0.5 * pruned
+    else:
+        logits, _, _, _ = joiner(enc, sub["t_len"], pred, sub["s_len"])
+        total = loss_mod({"logits": logits, "logits_length": sub["t_len"], "targets": sub["labels"],
+                          "targets_length": sub["s_len"]})
+    total.backward()
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    out = {"utterances": n, "against": "cpu_baseline (oracle/reference_port.py, fp32) on the same batch and weights",
+           "loss_rel": rel(total, ref["total"]), "tolerance": "fp32 1e-5 loss / 1e-4 gradients, bf16 joiner 1e-2 (north_star)",
+           "mode": mode}
+    g, gr = enc.grad.float().cpu(), ref["d_enc"]
+    if "ranges" in ref:
+        same = (ranges.cpu() == ref["ranges"]).all(dim=2).all(dim=1)
+        out["ranges_mismatch"] = float((ranges.cpu() != ref["ranges"]).float().mean())
+        out["utterances_with_identical_ranges"] = float(same.float().mean())
+        out["simple_loss_rel"] = rel(simple, ref["simple"])
+        out["pruned_loss_rel"] = rel(pruned, ref["pruned"])
+        out["grad_rel"] = rel(g[same], gr[same]) if bool(same.any()) else None
+        out["grad_rel_all_utterances"] = rel(g, gr)
+    else:
+        out["grad_rel"] = rel(g, gr)
+    return out
 
 
 def emit(line: dict) -> None:
@@ -310,9 +370,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        batch = make_batch(cfg, 1234)
+        batch = make_batch(cfg, 1234, input_dtype(cfg, args.mode))
         steps = max(1, min(args.steps, args.cpu_steps))
-        base, sec = cpu_arm(cfg, batch, args.cpu_utts, steps, min(args.warmup, 1))
+        base, sec, _ = cpu_arm(cfg, batch, args.cpu_utts, steps, min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "utt/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -325,7 +385,7 @@ def main():
     # ----------------------------------------------------------------------------- our arm
     import torch.distributed as dist
     from speech2text_b200 import _lib
-    from speech2text_b200.distributed import FlatGradBucket, reduce_scalars
+    from speech2text_b200.distributed import FlatGradBucket
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
     torch.cuda.set_device(local_rank)
@@ -343,9 +403,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the CUDA library is missing
 
-    batch = make_batch(cfg, 1234 + rank)
+    in_dtype = input_dtype(cfg, args.mode)
+    config["input_dtype"] = in_dtype
+    batch = make_batch(cfg, 1234 + rank, in_dtype)
     joiner, loss_mod = build_modules(cfg, dev, args.mode)
-    bucket = FlatGradBucket(joiner.parameters()).bind()  # dW kernels write straight into the all-reduce buffer
+    # dW kernels write straight into the all-reduce buffer; its three tail slots carry the logged losses
+    bucket = FlatGradBucket(joiner.parameters(), extra_scalars=3).bind()
     d_in = {k: v.to(dev) for k, v in batch.items()}
     enc = d_in["enc"].requires_grad_(True)
     pred = d_in["pred"].requires_grad_(True)
@@ -358,9 +421,10 @@ def main():
         return hot_path_step(joiner, loss_mod, enc, d_in["t_len"], pred, d_in["s_len"], d_in["labels"])
 
     def finish(losses):
+        # ONE collective per step (gradients + logged scalars, averaged inside NCCL), part of the captured graph
         if world > 1:
+            bucket.put_scalars(list(losses))
             bucket.all_reduce(average=True)
-            reduce_scalars(list(losses))
         return losses
 
     def step():  # eager: every kernel issued from Python
@@ -392,15 +456,29 @@ def main():
     launches0 = _lib.launch_count()
     step()
     launches_per_step = _lib.launch_count() - launches0
+    graphed = None
     if not args.eager:
-        try:
-            from speech2text_b200.graph import GraphedStep
-            graphed = GraphedStep(step_core)
-            run_step = lambda: finish(graphed())
-            execution = "cuda graph replay of the eager step (forward + backward), all-reduce issued after it"
-        except Exception as exc:  # keep measuring, but say what happened
-            execution = f"eager (graph capture failed: {type(exc).__name__}: {exc})"
-            torch.cuda.synchronize()
+        from speech2text_b200.graph import GraphedStep
+        if world > 1 and os.environ.get("S2T_BENCH_GRAPH_COLLECTIVE", "1") != "0":
+            try:  # the all-reduce inside the graph: no launch gap between the last dW kernel and NCCL
+                graphed = GraphedStep(step)
+                run_step = graphed
+                execution = "cuda graph replay of the step (forward + backward + the gradient/scalar all-reduce)"
+            except Exception as exc:
+                graphed = None
+                torch.cuda.synchronize()
+                sys.stderr.write(f"graph capture with the collective failed ({type(exc).__name__}: {exc}); "
+                                 "capturing the compute part only\n")
+        if graphed is None:
+            try:
+                graphed = GraphedStep(step_core)
+                run_step = lambda: finish(graphed())
+                execution = "cuda graph replay of the eager step (forward + backward)" + (
+                    ", all-reduce issued after it" if world > 1 else "")
+            except Exception as exc:  # keep measuring, but say what happened
+                graphed = None
+                execution = f"eager (graph capture failed: {type(exc).__name__}: {exc})"
+                torch.cuda.synchronize()
     for _ in range(3):
         run_step()
     barrier()
@@ -444,11 +522,11 @@ def main():
         if execution.startswith("cuda graph") and key not in slot_graphs:
             # one graph per device slot of the prefetcher (a graph reads fixed addresses)
             from speech2text_b200.graph import GraphedStep
-            slot_graphs[key] = GraphedStep(lambda: e2e_core(d), warmup=1, pool=graphed.pool())
+            slot_graphs[key] = GraphedStep(lambda: e2e_core(d), warmup=1, pool=graphed.pool() if graphed else None)
         losses = slot_graphs[key]() if key in slot_graphs else e2e_core(d)
+        vec = bucket.put_scalars(list(losses))
         if world > 1:
             bucket.all_reduce(average=True)
-        vec = reduce_scalars(list(losses))
         loss_host.copy_(vec, non_blocking=True)
 
     pf.put(h_in)
@@ -495,8 +573,12 @@ def main():
             kr = kernel_roof(name, cnt, ms)
             traffic = None
             try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
-                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
-                    rec = json.load(f).get(name)
+                rec = None
+                for fname in ("r2_traffic.json", "r1_traffic.json"):
+                    fpath = os.path.join(ROOT, "profiles", fname)
+                    if rec is None and os.path.exists(fpath):
+                        with open(fpath) as f:
+                            rec = json.load(f).get(name)
                 if rec:
                     traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
             except OSError:
@@ -517,7 +599,7 @@ def main():
             Bc, Tc, Sc, Vc, Dc, Rc, Ic = (cfg[k] for k in ("B", "T", "U", "V", "D", "R", "I"))
             if Rc > 0:
                 fl = 6.0 * (Tc + Sc + 1) * Dc * Vc + 6.0 * (Sc + 1) * Tc * Vc + (12.0 * Tc * Rc * Vc * Ic if Ic > 0 else 0.0)
-                by = (3.0 * (Tc + Sc + 1) * Dc * 4 + 6.0 * (Tc + Sc + 1) * Vc * 4 + 4.0 * (Sc * (Tc + 1) + (Sc + 1) * Tc) * 4
+                by = (3.0 * (Tc + Sc + 1) * Dc * (2 if in_dtype == "bf16" else 4) + 6.0 * (Tc + Sc + 1) * Vc * 4 + 4.0 * (Sc * (Tc + 1) + (Sc + 1) * Tc) * 4
                       + 2.0 * Tc * Rc * 8 + 4.0 * Tc * Rc * 2 * 4)
             else:
                 fl = 6.0 * (Tc + Sc + 1) * Dc * Vc + 12.0 * Tc * (Sc + 1) * Vc * max(Ic, 1)
@@ -548,9 +630,14 @@ def main():
                     os.sched_setaffinity(int(tid), cpus_before)
                 except OSError:
                     pass
-            base, _ = cpu_arm(cfg, batch, args.cpu_utts, args.cpu_steps, 1,
-                              joiner_state={k: v.detach().cpu() for k, v in joiner.state_dict().items()})
+            state = {k: v.detach().cpu() for k, v in joiner.state_dict().items()}
+            base, _, ref = cpu_arm(cfg, batch, args.cpu_utts, args.cpu_steps, 1, joiner_state=state)
+            # k2's own CPU schedule is serial over the batch: the 1-thread figure beside the all-thread one
+            base1, sec1, _ = cpu_arm(cfg, batch, args.cpu_utts, 1, 0, joiner_state=state, threads=1)
+            base["value_1thread"] = base1["value"]
+            base["sample_1thread"] = f"1 step, {sec1:.2f} s"
             line["cpu_baseline"] = base
+            line["parity"] = parity_block(cfg, batch, ref, min(args.cpu_utts, cfg["B"]), joiner, loss_mod, dev, args.mode)
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = None
         emit(line)

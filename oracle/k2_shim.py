@@ -75,6 +75,20 @@ def _ptr(t: Optional[Tensor]):
 # --------------------------------------------------------------------------
 # mutual_information.py
 # --------------------------------------------------------------------------
+def _over_utterances(call, B: int) -> None:
+    """k2's CPU kernel is one serial loop over the batch; utterances are independent, so the all-thread figure of
+    the CPU baseline splits [0, B) over ``torch.get_num_threads()`` host threads (ctypes releases
+    the GIL).  ``torch.set_num_threads(1)`` gives k2's own serial schedule.  Results do not depend on the split."""
+    n = max(1, min(B, torch.get_num_threads()))
+    if n == 1:
+        call(0, B)
+        return
+    import concurrent.futures
+    per = -(-B // n)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=n) as pool:
+        list(pool.map(lambda lo: call(lo, min(B, lo + per)), range(0, B, per)))
+
+
 def _mi_forward(px: Tensor, py: Tensor, boundary: Optional[Tensor],
                 p: Tensor) -> Tensor:
     B, S, T1 = px.shape
@@ -83,9 +97,8 @@ def _mi_forward(px: Tensor, py: Tensor, boundary: Optional[Tensor],
     ans = torch.empty(B, dtype=px.dtype)
     sfx = {torch.float32: "f32", torch.float64: "f64"}[px.dtype]
     fn = getattr(_native(), f"s2t_oracle_mi_forward_{sfx}")
-    fn(_ptr(px), _ptr(py), _ptr(boundary), _ptr(p), _ptr(ans),
-       ctypes.c_int(B), ctypes.c_int(S), ctypes.c_int(T), ctypes.c_int(0),
-       ctypes.c_int(B))
+    _over_utterances(lambda lo, hi: fn(_ptr(px), _ptr(py), _ptr(boundary), _ptr(p), _ptr(ans), ctypes.c_int(B),
+                                       ctypes.c_int(S), ctypes.c_int(T), ctypes.c_int(lo), ctypes.c_int(hi)), B)
     return ans
 
 
@@ -98,9 +111,9 @@ def _mi_backward(px: Tensor, py: Tensor, boundary: Optional[Tensor], p: Tensor,
     py_grad = torch.zeros_like(py)
     sfx = {torch.float32: "f32", torch.float64: "f64"}[px.dtype]
     fn = getattr(_native(), f"s2t_oracle_mi_backward_{sfx}")
-    fn(_ptr(px), _ptr(py), _ptr(boundary), _ptr(p), _ptr(ans_grad),
-       _ptr(p_grad), _ptr(px_grad), _ptr(py_grad), ctypes.c_int(B),
-       ctypes.c_int(S), ctypes.c_int(T), ctypes.c_int(0), ctypes.c_int(B))
+    _over_utterances(lambda lo, hi: fn(_ptr(px), _ptr(py), _ptr(boundary), _ptr(p), _ptr(ans_grad), _ptr(p_grad),
+                                       _ptr(px_grad), _ptr(py_grad), ctypes.c_int(B), ctypes.c_int(S),
+                                       ctypes.c_int(T), ctypes.c_int(lo), ctypes.c_int(hi)), B)
     return px_grad, py_grad
 
 
@@ -369,9 +382,14 @@ def _adjust_pruning_lower_bound(s_begin: Tensor, s_range: int) -> Tensor:
 
 
 #: which published variant of get_rnnt_prune_ranges to use:
-#: "A" = sliding-window sum of py_grad minus padded px_grad (k2.get_rnnt_prune_ranges
-#: at tag v1.24.3), "B" = cumulative symmetric px+py window.
-PRUNE_RANGES_VARIANT = "A"
+#: "B" = cumulative symmetric px+py window: upstream's ``get_rnnt_prune_ranges`` since early 2023, i.e. what
+#:       both of the reference's pins resolve to (requirements.txt:4 ``k2==1.24.3.dev20240615``, a 2024 build of
+#:       the 1.24.3 sources; Dockerfile.build:28-35 tag v1.24.3, mid 2023) -- the default;
+#: "A" = sliding-window sum of py_grad minus padded px_grad (upstream's older function, kept there as
+#:       ``get_rnnt_prune_ranges_deprecated``).
+#: k2 is not installable offline, so the choice cannot be verified here: both are built,
+#: both have golden vectors (tests/golden/<case>.{A,B}.*.npz) and every parity test runs under both.
+PRUNE_RANGES_VARIANT = "B"
 
 
 def get_rnnt_prune_ranges(

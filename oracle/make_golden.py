@@ -20,7 +20,6 @@ Usage (build container only):  python -m oracle.make_golden
 """
 from __future__ import annotations
 
-import importlib
 import os
 import sys
 import types
@@ -35,24 +34,23 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def _import_reference():
+    """The three reference modules, loaded from their files under /root/reference (the reference's ``model`` is a
+    namespace package, so with this repo's import-path mirror on sys.path ``import model.joiner.joiner`` would
+    resolve to the mirror; none of the three imports anything from ``model.*``)."""
+    import importlib.util
     from oracle import k2_shim
     sys.modules["k2"] = k2_shim
     sys.modules.setdefault("onnx", types.ModuleType("onnx"))
-    # make sure `model.*` resolves to the reference, not to this repo's mirror
-    for name in [m for m in sys.modules if m == "model" or m.startswith("model.")]:
-        del sys.modules[name]
-    sys.path.insert(0, REFERENCE)
-    try:
-        joiner = importlib.import_module("model.joiner.joiner")
-        pruned = importlib.import_module("model.loss.pruned_rnnt_loss")
-        rnnt = importlib.import_module("model.loss.rnnt_loss")
-        assert joiner.__file__.startswith(REFERENCE), joiner.__file__
-        assert pruned.__file__.startswith(REFERENCE), pruned.__file__
-    finally:
-        sys.path.remove(REFERENCE)
-        for name in [m for m in sys.modules if m == "model" or m.startswith("model.")]:
-            del sys.modules[name]
-    return joiner, pruned, rnnt
+
+    def load(rel):
+        path = os.path.join(REFERENCE, rel)
+        spec = importlib.util.spec_from_file_location("_reference_" + os.path.basename(rel)[:-3], path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert mod.__file__.startswith(REFERENCE), mod.__file__
+        return mod
+
+    return (load("model/joiner/joiner.py"), load("model/loss/pruned_rnnt_loss.py"), load("model/loss/rnnt_loss.py"))
 
 
 def summarize(t: torch.Tensor, max_elems: int = 16384):
@@ -72,8 +70,10 @@ def summarize(t: torch.Tensor, max_elems: int = 16384):
     return out
 
 
-def run_case(name, joiner_mod, pruned_mod, rnnt_mod, dtype=torch.float32):
+def run_case(name, joiner_mod, pruned_mod, rnnt_mod, dtype=torch.float32, variant="B"):
     from oracle.cases import CASES, make_case
+    from oracle import k2_shim
+    k2_shim.PRUNE_RANGES_VARIANT = variant  # the reference calls k2.get_rnnt_prune_ranges without a variant
     spec = CASES[name]
     case = make_case(name)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -129,15 +129,19 @@ def main():
     joiner_mod, pruned_mod, rnnt_mod = _import_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, spec in CASES.items():
-        for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
-            if dt == torch.float64 and spec["joiner"].get("prune_range", 5) <= 0:
-                continue  # torchaudio's rnnt_loss has no fp64 kernel
-            res = run_case(name, joiner_mod, pruned_mod, rnnt_mod, dt)
-            path = os.path.join(OUT, f"{name}.{tag}.npz")
-            np.savez_compressed(path, **res)
-            keys = [k for k in ("simple_loss", "pruned_loss", "rnnt_loss") if k in res]
-            print(f"{name}.{tag}: " + ", ".join(f"{k}={res[k]}" for k in keys),
-                  f"-> {os.path.getsize(path) / 1024:.0f} KiB")
+        pruned = spec["joiner"].get("prune_range", 5) > 0
+        # both published variants of k2.get_rnnt_prune_ranges for every pruned case
+        for variant in (("A", "B") if pruned else (None,)):
+            for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+                if dt == torch.float64 and not pruned:
+                    continue  # torchaudio's rnnt_loss has no fp64 kernel
+                res = run_case(name, joiner_mod, pruned_mod, rnnt_mod, dt, variant or "B")
+                stem = f"{name}.{variant}.{tag}" if variant else f"{name}.{tag}"
+                path = os.path.join(OUT, stem + ".npz")
+                np.savez_compressed(path, **res)
+                keys = [k for k in ("simple_loss", "pruned_loss", "rnnt_loss") if k in res]
+                print(f"{stem}: " + ", ".join(f"{k}={res[k]}" for k in keys),
+                      f"-> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":

@@ -268,8 +268,13 @@ size_t s2t_lattice_workspace_bytes(int B, int S, int T, int slots) {
   return best > full ? best : full;
 }
 
+// use_out_project=False (the reference's zipformer yaml): the joiner has no contraction, its "logits" are
+// act(am + lm[ranges]) -- an HBM-bound elementwise + log-sum-exp pass that is the same code in both modes (the
+// tensor-core mode then still covers the projections and the simple loss)
+static bool joiner_uses_tc(int mode, int I) { return mode == S2T_MODE_BF16_TC && I > 0; }
+
 size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {
-  if (mode == S2T_MODE_BF16_TC) return joiner_tc_workspace_bytes((int64_t)B * T * R, V, I);
+  if (joiner_uses_tc(mode, I)) return joiner_tc_workspace_bytes((int64_t)B * T * R, V, I);
   return joiner_simt_workspace_bytes((int64_t)B * T * R, V, I, nullptr);
 }
 
@@ -284,7 +289,7 @@ int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_
   S2T_REQUIRE(I == 0 || (W1 && b1 && W2 && b2), "joiner_loss: out-projection weights missing");
   JoinerProblem p = make_problem(am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
                                  delay_penalty);
-  if (mode == S2T_MODE_BF16_TC) {
+  if (joiner_uses_tc(mode, I)) {
     if (int rc = joiner_tc_forward(p, workspace, lse, px, py, st)) return rc;
   } else {
     if (int rc = joiner_simt_forward(p, workspace, lse, px, py, st)) return rc;
@@ -310,7 +315,7 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
     cudaMemsetAsync(dW2, 0, (size_t)V * I * sizeof(float), st);
     cudaMemsetAsync(db2, 0, (size_t)V * sizeof(float), st);
   }
-  if (mode == S2T_MODE_BF16_TC) {
+  if (joiner_uses_tc(mode, I)) {
     return joiner_tc_backward(p, workspace, lse, occ_px, occ_py, grad_scores, clamp, d_am, d_lm, dW1, db1, dW2, db2,
                               st);
   }

@@ -49,6 +49,15 @@ class ForkJoin {
   bool enabled_;
 };
 
+// Per-device facts the launchers size their grids and scratch buffers from (queried once per device, cached).
+struct DeviceInfo {
+  int device;
+  int sms;            // multiprocessors
+  size_t total_mem;   // bytes of device memory
+};
+const DeviceInfo& device_info();  // of the CURRENT device
+constexpr int kMaxDevices = 64;
+
 #define S2T_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

@@ -866,11 +866,7 @@ TcDims tc_dims(int64_t M, int V, int I) {
   d.n_parts_v = kLseGroups * d.n_tiles_v;  // one partial per (column tile, epilogue group)
   // device-memory budgets (queried once): an eighth of the memory for the kept J, a 48th (3.7 GB of a B200's 180 GB,
   // at least 1 GiB) for each of the two (chunk rows x Vp) bf16 buffers of the backward pass
-  static size_t jp_budget = 0;
-  if (jp_budget == 0) {
-    size_t free_b = 0, total_b = 0;
-    jp_budget = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0 ? total_b / 8 : (size_t)4 << 30;
-  }
+  const size_t jp_budget = device_info().total_mem / 8;  // per device: forward and backward of a step agree on the layout
   const size_t budget = jp_budget / 6 > ((size_t)1 << 30) ? jp_budget / 6 : (size_t)1 << 30;
   int64_t rows = (int64_t)(budget / ((size_t)d.Vp * 2));
   if (const char* e = getenv("S2T_B200_CHUNK_ROWS")) rows = atoll(e);  // test hook: force the multi-chunk backward
@@ -1035,7 +1031,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
   if (M == 0) return 0;
   TcDims d = tc_dims(M, p.V, p.I);
   TcWs w = tc_carve(workspace, d);
-  const int sms = 148;
+  const int sms = device_info().sms;
   for (int64_t row0 = 0; row0 < (int64_t)d.Mt * 128; row0 += d.chunk) {
     const int64_t rows_pad = ((int64_t)d.Mt * 128 - row0 < d.chunk) ? ((int64_t)d.Mt * 128 - row0) : d.chunk;
     const int ct = (int)(rows_pad / 128);       // row tiles of this chunk

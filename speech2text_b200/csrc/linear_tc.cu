@@ -121,7 +121,7 @@ int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M,
     cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s_dw);
     const int k_steps = d.Mt * 2;
     const int tiles = (d.Np / 128) * (d.Kp / 256);
-    int splits = 148 / (tiles > 0 ? tiles : 1);
+    int splits = device_info().sms / (tiles > 0 ? tiles : 1);
     if (splits < 1) splits = 1;
     tc::BulkA a{pdy, d.Mt};
     tc::StoreRowMajorEpi ep{dW, K, N, K, true, nullptr};

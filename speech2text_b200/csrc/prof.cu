@@ -45,6 +45,30 @@ ProfScope::~ProfScope() {
   g_entries.push_back(Entry{name_, start_, stop_});
 }
 
+// ---- DeviceInfo ----------------------------------------------------------------------------------
+const DeviceInfo& device_info() {
+  static DeviceInfo info[kMaxDevices];
+  static std::atomic<int> ready[kMaxDevices];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= (kMaxDevices - 1);
+  if (ready[dev].load(std::memory_order_acquire) == 0) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (ready[dev].load(std::memory_order_relaxed) == 0) {
+      DeviceInfo d{};
+      d.device = dev;
+      cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+      if (d.sms <= 0) d.sms = 148;
+      size_t free_b = 0, total_b = 0;
+      d.total_mem = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) ? total_b : ((size_t)32 << 30);
+      info[dev] = d;
+      ready[dev].store(1, std::memory_order_release);
+    }
+  }
+  return info[dev];
+}
+
 // ---- ForkJoin -------------------------------------------------------------------------------------
 namespace {
 struct SideStreams {

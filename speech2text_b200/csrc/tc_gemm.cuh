@@ -580,15 +580,21 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   }
 }
 
-inline int gemm_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+inline int gemm_sm_count() { return device_info().sms; }
+
+// cudaFuncSetAttribute(max dynamic shared memory) once per kernel instantiation AND device
+template <class Kern>
+inline int configure_smem_once(Kern kern, size_t smem, bool (&done)[kMaxDevices], const char* what) {
+  const int dev = device_info().device;
+  if (!done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
+      return 2;
+    }
+    done[dev] = true;
   }
-  return sms;
+  return 0;
 }
 
 template <int BN, int kStages, bool kMn, int kKind, int kCluster = 1, class ASrc, class Epi>
@@ -601,15 +607,8 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
   auto kern = gemm_stream_kernel<BN, kStages, kMn, kKind, ASrc, Epi, kCluster>;
   constexpr size_t smem = gemm_stream_smem_bytes<BN, kStages, kKind, ASrc, Epi>();
   static_assert(smem <= 227 * 1024, "stage ring + epilogue scratch exceed the 227 KB of one CTA");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
-      return 2;
-    }
-    configured = true;
-  }
+  static bool configured[kMaxDevices] = {};
+  if (int rc = configure_smem_once(kern, smem, configured, what)) return rc;
   const long long tiles = (long long)((m_tiles + kCluster - 1) / kCluster) * n_tiles * batches * k_splits;  // per cluster
   const int max_clusters = gemm_sm_count() / kCluster;
   const int grid = kCluster * (int)(tiles < max_clusters ? tiles : max_clusters);
@@ -686,15 +685,8 @@ int launch_gemm_bstationary(const ASrc& asrc, const uint8_t* b_packed, int b_row
   }
   if (m_tiles <= 0 || n_tiles <= 0 || k_steps <= 0) return 0;
   auto kern = gemm_stream_kernel<BN, kStages, false, 0, ASrc, Epi, 1, kBRes>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
-      return 2;
-    }
-    configured = true;
-  }
+  static bool configured[kMaxDevices] = {};
+  if (int rc = configure_smem_once(kern, smem, configured, what)) return rc;
   // every CTA owns one column tile: grid = column tiles x (CTAs per column tile)
   int per_tile = sms / n_tiles;
   if (per_tile > m_tiles) per_tile = m_tiles;

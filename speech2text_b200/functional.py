@@ -18,6 +18,30 @@ from ._lib import check, lib, ptr, stream
 PRUNE_VARIANTS = {"A": 0, "B": 1}
 
 
+def _on_tensor_device(fn):
+    """Run an autograd.Function's forward / backward with the device of its first CUDA tensor current: the C ABI
+    takes raw pointers plus ``torch.cuda.current_stream()``, and the library's side streams are keyed by
+    ``cudaGetDevice`` -- with tensors on a non-current device (one process driving several GPUs, or before
+    ``torch.cuda.set_device``) the kernels would otherwise be launched on the wrong device and stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        dev = None
+        for a in args + tuple(getattr(ctx, "saved_tensors", ()) or ()):
+            if isinstance(a, Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise _lib.S2TError(f"tensors on different devices handed to one call: {dev} and {a.device}")
+        if dev is None:
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+
+    return wrapped
+
+
 def _f32c(t: Tensor) -> Tensor:
     return t.to(torch.float32).contiguous()
 
@@ -68,6 +92,7 @@ def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tens
 class _SimpleLoss(torch.autograd.Function):
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, am: Tensor, lm: Tensor, symbols: Tensor, boundary: Tensor, blank: int,
                 lm_only_scale: float, am_only_scale: float, mode: int):
         am, lm = _f32c(am), _f32c(lm)
@@ -102,6 +127,7 @@ class _SimpleLoss(torch.autograd.Function):
         return scores, px_grad, py_grad
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, grad_scores, _gx, _gy):
         am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws = ctx.saved_tensors
         B, T, V = am.shape
@@ -158,7 +184,9 @@ def _reduce(scores: Tensor, reduction: str) -> Tensor:
 # ---------------------------------------------------------------------------
 def get_rnnt_prune_ranges(px_grad: Tensor, py_grad: Tensor, boundary: Tensor, s_range: int,
                           variant: Optional[str] = None) -> Tensor:
-    variant = variant or os.environ.get("S2T_B200_PRUNE_VARIANT", "A")
+    variant = variant or os.environ.get("S2T_B200_PRUNE_VARIANT", "B")
+    if variant not in PRUNE_VARIANTS:
+        raise ValueError(f"S2T_B200_PRUNE_VARIANT must be A or B, got {variant}")
     px_grad, py_grad, boundary = _f32c(px_grad), _f32c(py_grad), _i64c(boundary)
     B, S, T1 = px_grad.shape
     T = py_grad.shape[-1]
@@ -183,6 +211,7 @@ def get_rnnt_prune_ranges(px_grad: Tensor, py_grad: Tensor, boundary: Tensor, s_
 class _LogitsLoss(torch.autograd.Function):
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, logits: Tensor, symbols: Tensor, ranges: Optional[Tensor], boundary: Tensor,
                 blank: int, delay_penalty: float, clamp: float):
         logits = logits.contiguous()
@@ -212,6 +241,7 @@ class _LogitsLoss(torch.autograd.Function):
         return scores
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, grad_scores):
         logits, symbols, ranges, lse, occ_px, occ_py = ctx.saved_tensors
         B, T, R, V = logits.shape
@@ -235,10 +265,11 @@ def logits_scores(logits: Tensor, symbols: Tensor, ranges: Optional[Tensor], bou
 class _JoinerLoss(torch.autograd.Function):
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, am: Tensor, lm: Tensor, W1, b1, W2, b2, symbols: Tensor, ranges: Optional[Tensor],
                 boundary: Tensor, act: int, blank: int, delay_penalty: float, clamp: float, mode: int,
                 sinks=None):
-        ctx.sinks = sinks  # (dW1, db1, dW2, db2) buffers written in place by backward, or None
+        ctx.sink_params = sinks  # the four out-projection parameters when they may carry a bound gradient sink
         am, lm = _f32c(am), _f32c(lm)
         symbols, boundary = _i64c(symbols), _i64c(boundary)
         B, T, V = am.shape
@@ -279,13 +310,14 @@ class _JoinerLoss(torch.autograd.Function):
         return scores
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, grad_scores):
         (am, lm, W1, b1, W2, b2, symbols, ranges, boundary, workspace, lse, occ_px, occ_py) = ctx.saved_tensors
         has_proj, has_ranges, S, R, I, act, blank, clamp, mode = ctx.meta
         B, T, V = am.shape
         d_am = torch.empty_like(am)
         d_lm = torch.empty_like(lm)
-        sinks = ctx.sinks if (has_proj and ctx.sinks is not None and all(t is not None for t in ctx.sinks)) else None
+        sinks = claim_grad_sinks(ctx.sink_params) if has_proj else None
         if sinks is not None:
             dW1, db1, dW2, db2 = sinks
         elif has_proj:
@@ -307,9 +339,9 @@ def joiner_scores(am: Tensor, lm: Tensor, W1, b1, W2, b2, symbols: Tensor, range
                   boundary: Tensor, act: int, blank: int = 0, delay_penalty: float = 0.0,
                   clamp: float = -1.0, mode: int = _lib.MODE_FP32_SIMT) -> Tensor:
     """log P(y|x) per utterance of the (pruned or full) joiner lattice, fused."""
-    sinks = tuple(grad_sink(p) for p in (W1, b1, W2, b2))
+    params = (W1, b1, W2, b2)
     return _JoinerLoss.apply(am, lm, W1, b1, W2, b2, symbols, ranges, boundary, act, blank, delay_penalty,
-                             clamp, mode, sinks if all(t is not None for t in sinks) else None)
+                             clamp, mode, params if all(grad_sink(p) is not None for p in params) else None)
 
 
 def joiner_materialize(am: Tensor, lm: Tensor, W1, b1, W2, b2, ranges: Optional[Tensor], act: int,
@@ -345,8 +377,9 @@ class _LinearTC(torch.autograd.Function):
     separate pass of autograd over two (M, N) tensors."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, W: Tensor, b: Tensor, sink_W: Optional[Tensor] = None, sink_b: Optional[Tensor] = None):
-        ctx.sinks = (sink_W, sink_b)
+    @_on_tensor_device
+    def forward(ctx, x: Tensor, W: Tensor, b: Tensor, sink_params=None):
+        ctx.sink_params = sink_params  # (W, b) parameters when they may carry a bound gradient sink
         lead = x.shape[:-1]
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
@@ -356,19 +389,21 @@ class _LinearTC(torch.autograd.Function):
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         check(lib().s2t_linear_fwd(ptr(x2), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y), stream()))
         ctx.save_for_backward(W, ws)
-        ctx.dims = (M, N, K, lead, x.requires_grad)
+        ctx.dims = (M, N, K, lead, x.requires_grad, x.dtype)
         y = y.reshape(*lead, N)
         return y, y.view_as(y)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy, dy_alias):
         W, ws = ctx.saved_tensors
-        M, N, K, lead, need_dx = ctx.dims
+        M, N, K, lead, need_dx, x_dtype = ctx.dims
         if dy is None:
             dy, dy_alias = dy_alias, None
         if dy is None:
-            return None, None, None, None, None
-        sink_W, sink_b = ctx.sinks
+            return None, None, None, None
+        sinks = claim_grad_sinks(ctx.sink_params)
+        sink_W, sink_b = sinks if sinks is not None else (None, None)
         dy2 = _f32c(dy).reshape(M, N)
         dy3 = _f32c(dy_alias).reshape(M, N) if dy_alias is not None else None
         dx = torch.empty((M, K), dtype=torch.float32, device=dy.device) if need_dx else None
@@ -376,25 +411,56 @@ class _LinearTC(torch.autograd.Function):
         dW = sink_W if sink_W is not None else torch.empty_like(W)
         db = sink_b if sink_b is not None else torch.empty((N,), dtype=torch.float32, device=dy.device)
         check(lib().s2t_linear_bwd(ptr(dy2), ptr(dy3), ptr(W), M, N, K, ptr(ws), ptr(dx), ptr(dW), ptr(db), stream()))
+        if need_dx and x_dtype != torch.float32:
+            dx = dx.to(x_dtype)  # bf16 activations in (BASELINE config 3's "bf16 joiner"): their gradient goes back as bf16
         return ((dx.reshape(*lead, K) if need_dx else None), None if sink_W is not None else dW,
-                None if sink_b is not None else db, None, None)
+                None if sink_b is not None else db, None)
 
 
 def grad_sink(p: Optional[Tensor]) -> Optional[Tensor]:
     """The buffer ``FlatGradBucket.bind`` attached to a parameter (a view of the flat all-reduce buffer), if any:
     the backward kernels then write the gradient there instead of handing a temporary to autograd's accumulate."""
-    sink = getattr(p, "_s2t_grad_sink", None) if p is not None else None
-    if sink is not None and (sink.shape != p.shape or sink.dtype != torch.float32 or not sink.is_contiguous()
-                             or sink.device != p.device):
+    rec = getattr(p, "_s2t_grad_sink", None) if p is not None else None
+    if rec is None:
+        return None
+    sink = rec[0]
+    if sink.shape != p.shape or sink.dtype != torch.float32 or not sink.is_contiguous() or sink.device != p.device:
         raise ValueError("gradient sink must be a contiguous fp32 tensor of the parameter's shape on its device")
     return sink
 
 
+def claim_grad_sinks(params):
+    """Called by a backward pass that wants to OVERWRITE the bound gradient buffers of ``params``.  Returns the
+    sinks only if that is what autograd's accumulate would have produced: every ``p.grad`` still aliases its
+    sink (``optimizer.zero_grad(set_to_none=True)`` drops the alias: the kernels would then write into an orphaned
+    buffer and the optimizer would skip the parameter) and no earlier backward pass has written the sink since the
+    last ``FlatGradBucket.zero()`` (gradient accumulation, a second joiner call in one step).  Otherwise None: the
+    caller returns its gradients to autograd, which accumulates them as usual."""
+    if params is None:
+        return None
+    recs = []
+    for p in params:
+        rec = getattr(p, "_s2t_grad_sink", None) if p is not None else None
+        if rec is None:
+            return None
+        sink, bucket = rec
+        if p.grad is None or p.grad.data_ptr() != sink.data_ptr() or p.grad.shape != sink.shape:
+            return None
+        if bucket is not None and id(p) in bucket.written:
+            return None
+        recs.append((p, sink, bucket))
+    for p, _, bucket in recs:
+        if bucket is not None:
+            bucket.written.add(id(p))
+    return tuple(sink for _, sink, _ in recs)
+
+
 def linear_tc(x: Tensor, W: Tensor, b: Tensor) -> Tensor:
     """``F.linear(x, W, b)`` on tcgen05 (3xF16 split forward, bf16 backward); fp32 in, fp32 out."""
-    return _LinearTC.apply(x, W, b, grad_sink(W), grad_sink(b))[0]
+    return linear_tc_pair(x, W, b)[0]
 
 
 def linear_tc_pair(x: Tensor, W: Tensor, b: Tensor) -> Tuple[Tensor, Tensor]:
     """Same, as two aliases of the result for two consumers (see _LinearTC)."""
-    return _LinearTC.apply(x, W, b, grad_sink(W), grad_sink(b))
+    params = (W, b)
+    return _LinearTC.apply(x, W, b, params if all(grad_sink(p) is not None for p in params) else None)

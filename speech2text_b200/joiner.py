@@ -16,7 +16,8 @@ what happens inside ``forward`` on a CUDA device:
 Environment knobs (no new required config keys -- JoinerConfig(**yaml) must keep working):
   S2T_B200_FUSED=0          materialise logits like the reference (default 1)
   S2T_B200_JOINER_MODE      "fp32" (strict, default) | "bf16" (tensor cores)
-  S2T_B200_PRUNE_VARIANT    "A" (default, k2 v1.24.3) | "B"
+  S2T_B200_PRUNE_VARIANT    "B" (default: upstream's get_rnnt_prune_ranges since early 2023, what the reference's
+                            k2 pins resolve to) | "A" (the older sliding-window function)
 """
 from __future__ import annotations
 

@@ -39,7 +39,11 @@ class HostBatchPrefetcher:
         slot = self._slots[idx]
         if slot is None or any(k not in slot or slot[k].shape != v.shape or slot[k].dtype != v.dtype
                                for k, v in host_batch.items()):
-            slot = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_batch.items()}
+            # allocated ON the copy stream (the stream that writes them first): a block the caching allocator hands
+            # back from the compute stream could still have queued readers there; get() records the compute stream
+            # as a user, so a later reallocation (shapes change every step for real speech batches) waits for it
+            with torch.cuda.stream(self.copy_stream):
+                slot = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_batch.items()}
             self._slots[idx] = slot
         return slot
 
@@ -70,6 +74,8 @@ class HostBatchPrefetcher:
         idx, done = self._queue.popleft()
         cur.wait_event(done)
         self._in_use = idx
+        for t in self._slots[idx].values():
+            t.record_stream(cur)
         return self._slots[idx]
 
     def __len__(self) -> int:

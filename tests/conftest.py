@@ -25,8 +25,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-def load_golden(name: str, tag: str = "f32"):
-    return dict(np.load(os.path.join(GOLDEN, f"{name}.{tag}.npz")))
+VARIANTS = ("A", "B")  # published variants of k2.get_rnnt_prune_ranges; B is the default
+
+
+def load_golden(name: str, tag: str = "f32", variant: str = "B"):
+    """Golden vectors of a case: <name>.<variant>.<tag>.npz for the pruned cases (one file per variant of the
+    prune-range selection), <name>.<tag>.npz for the vanilla one."""
+    path = os.path.join(GOLDEN, f"{name}.{variant}.{tag}.npz")
+    if not os.path.exists(path):
+        path = os.path.join(GOLDEN, f"{name}.{tag}.npz")
+    return dict(np.load(path))
 
 
 def check_summary(t: torch.Tensor, gold: dict, key: str, rtol: float, what: str = ""):

@@ -5,23 +5,26 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import check_summary, load_golden
+from conftest import VARIANTS, check_summary, load_golden
 from oracle import k2_shim as k2
 from oracle import reference_port as port
 from oracle.cases import CASES, make_case
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("tag", ["f32", "f64"])
-def test_port_matches_reference_goldens(name, tag):
+def test_port_matches_reference_goldens(name, tag, variant):
     spec = CASES[name]
     pruned = spec["joiner"].get("prune_range", 5) > 0
     if tag == "f64" and not pruned:
         pytest.skip("torchaudio has no fp64 kernel")
-    gold = load_golden(name, tag)
+    if not pruned and variant != VARIANTS[-1]:
+        pytest.skip("the vanilla path has no prune ranges")
+    gold = load_golden(name, tag, variant)
     case = make_case(name)
     dtype = torch.float32 if tag == "f32" else torch.float64
-    out = port.training_step_loss(case["weights"], spec, case, dtype=dtype)
+    out = port.training_step_loss(case["weights"], spec, case, dtype=dtype, prune_variant=variant)
     tol = 2e-6 if tag == "f32" else 1e-12
     if pruned:
         assert np.array_equal(out["ranges"].numpy(), gold["ranges"])
@@ -37,10 +40,10 @@ def test_port_matches_reference_goldens(name, tag):
 def test_f32_and_f64_goldens_agree():
     """fp32 reference run vs fp64 reference run: the tolerance budget of north_star
     (1e-5 loss, 1e-4 grads) has to be achievable by fp32 arithmetic at all."""
-    for name, spec in CASES.items():
+    for variant, (name, spec) in [(v, c) for v in VARIANTS for c in CASES.items()]:
         if spec["joiner"].get("prune_range", 5) <= 0:
             continue
-        g32, g64 = load_golden(name, "f32"), load_golden(name, "f64")
+        g32, g64 = load_golden(name, "f32", variant), load_golden(name, "f64", variant)
         np.testing.assert_allclose(g32["pruned_loss"], g64["pruned_loss"], rtol=1e-5)
         np.testing.assert_allclose(g32["simple_loss"], g64["simple_loss"], rtol=1e-5)
         mism = (g32["ranges"] != g64["ranges"]).mean()
