@@ -99,6 +99,11 @@ def build_modules(cfg, device, mode: str):
         loss = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
     else:
         loss = Loss({"model": "Rnnt", "config": {"blank_label": 0, "clamp": -1, "reduction": "mean"}})
+    if cfg.get("ctc"):
+        # PrunedRnntTask with loss.enable_ctc (rnnt_task.py:434-445): a Projector head (model/decoder/projector.py:
+        # Linear D -> V; its dropout is switched off here so that both arms see the same numbers) and the CTC loss
+        joiner.ctc_proj = torch.nn.Linear(cfg["D"], cfg["V"]).to(device)
+        joiner.ctc_loss = Loss({"model": "CTC", "config": {"blank_label": 0, "reduction": "mean", "zero_infinity": True}})
     return joiner, loss
 
 
@@ -113,8 +118,20 @@ def hot_path_step(joiner, loss_mod, enc, t_len, pred, s_len, labels):
     pruned = loss_mod({"logits": logits, "logits_length": t_len, "targets": labels, "targets_length": s_len,
                        "boundary": boundary, "ranges": ranges})
     total = 0.5 * simple + 0.5 * pruned
+    if hasattr(joiner, "ctc_proj"):  # rnnt_task.py:485-496: loss = simple_scale * simple + pruned_scale * pruned + ctc
+        total = total + ctc_branch(joiner, enc, t_len, labels, s_len)
     total.backward()
     return total, simple, pruned
+
+
+def ctc_branch(joiner, enc, t_len, labels, s_len):
+    from speech2text_b200 import functional as F2
+    proj = joiner.ctc_proj
+    if os.environ.get("S2T_B200_JOINER_MODE", "fp32") == "bf16":
+        ctc_logits = F2.linear_tc(enc, proj.weight, proj.bias)  # the Projector's Linear on tcgen05 as well
+    else:
+        ctc_logits = proj(enc)
+    return joiner.ctc_loss({"logits": ctc_logits, "logits_length": t_len, "targets": labels, "targets_length": s_len})
 
 
 # ---------------------------------------------------------------------------------------------
@@ -181,6 +198,10 @@ def kernel_work(cfg, live_frames: float = 1.0):
         "simple_occupation_kernel": (0.0, 24.0 * lat_cells),
         "band_lattice_kernel": (0.0, 20.0 * band_cells),
         "prune_ranges_kernel": (0.0, B * ((U * (T + 1) + S1 * T) * 4.0 + T * R * 8.0)),
+        # CTC branch (config 4): logits read once for lse + emissions, once more with the gradient write; the lattice
+        # reads the emissions and writes alpha / beta~ (2U+1 states each)
+        "ctc_emit_kernel": (0.0, 4.0 * B * T * (V + S1)), "ctc_grad_kernel": (0.0, 4.0 * B * T * (2 * V + 2 * (2 * U + 1))),
+        "ctc_lattice_kernel": (0.0, 4.0 * B * T * (2 * S1 + 2 * (2 * U + 1))),
     }
     return w
 
@@ -238,41 +259,52 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's own CPU path (oracle port over the k2 restatement + torch CPU ops)
 # ---------------------------------------------------------------------------------------------
+def port_once(cfg, batch, n, joiner_state, ranges_override=None):
+    """One forward + backward of the reference's CPU path (oracle port) on the first n utterances."""
+    from oracle import reference_port as port
+    jc = dict(input_dim=cfg["D"], output_dim=cfg["V"], inner_dim=max(cfg["I"], 1), activation=cfg["act"],
+              prune_range=cfg["R"], use_out_project=cfg["I"] > 0)
+    w = {k: v.clone().float().requires_grad_(True) for k, v in joiner_state.items()}
+    e = batch["enc"][:n].float().clone().requires_grad_(True)
+    p = batch["pred"][:n].float().clone().requires_grad_(True)
+    t_len, s_len, labels = batch["t_len"][:n], batch["s_len"][:n], batch["labels"][:n]
+    if cfg["R"] <= 0:
+        logits, _, _, _ = port.joiner_forward(w, jc, e, t_len, p, s_len, None)
+        total = port.rnnt_loss(logits, labels, t_len, s_len)
+        total.backward()
+        return dict(total=total.detach(), d_enc=e.grad, d_pred=p.grad)
+    logits, boundary, ranges, simple = port.joiner_forward(w, jc, e, t_len, p, s_len, labels,
+                                                           ranges_override=ranges_override)
+    pruned = port.pruned_rnnt_loss(logits, labels, boundary, ranges)
+    total = 0.5 * simple + 0.5 * pruned
+    if "ctc_proj.weight" in w:
+        ctc_logits = torch.nn.functional.linear(e, w["ctc_proj.weight"], w["ctc_proj.bias"])
+        total = total + port.ctc_loss(ctc_logits, labels, t_len, s_len)
+    total.backward()
+    return dict(total=total.detach(), simple=simple.detach(), pruned=pruned.detach(), ranges=ranges, d_enc=e.grad,
+                d_pred=p.grad)
+
+
 def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None, threads: int = 0):
     """Times the reference's CPU path (oracle port) on the first n utterances of the batch.  Returns (baseline dict,
     seconds per step, results of the last step) -- the results feed the bench line's ``parity`` block."""
     from oracle import reference_port as port
     n = min(n_utts, cfg["B"])
     torch.set_num_threads(threads if threads > 0 else (os.cpu_count() or 1))
-    jc = dict(input_dim=cfg["D"], output_dim=cfg["V"], inner_dim=max(cfg["I"], 1), activation=cfg["act"],
-              prune_range=cfg["R"], use_out_project=cfg["I"] > 0)
     if joiner_state is None:
+        jc = dict(input_dim=cfg["D"], output_dim=cfg["V"], inner_dim=max(cfg["I"], 1), activation=cfg["act"],
+                  prune_range=cfg["R"], use_out_project=cfg["I"] > 0)
         from oracle.cases import make_weights
         import numpy as np
         joiner_state = {k: torch.from_numpy(v) for k, v in make_weights(jc, np.random.RandomState(1234)).items()}
-    enc = batch["enc"][:n].float().clone()
-    pred = batch["pred"][:n].float().clone()
-    t_len, s_len, labels = batch["t_len"][:n].clone(), batch["s_len"][:n].clone(), batch["labels"][:n].clone()
-    # torchaudio-style constraint of the sample: keep padded shapes of the full batch
-
+        if cfg.get("ctc"):
+            lin = torch.nn.Linear(cfg["D"], cfg["V"])
+            joiner_state.update({"ctc_proj.weight": lin.weight.detach(), "ctc_proj.bias": lin.bias.detach()})
     last = {}
 
     def one():
-        w = {k: v.clone().float().requires_grad_(True) for k, v in joiner_state.items()}
-        e = enc.clone().requires_grad_(True)
-        p = pred.clone().requires_grad_(True)
-        if cfg["R"] <= 0:
-            logits, _, _, _ = port.joiner_forward(w, jc, e, t_len, p, s_len, None)
-            total = port.rnnt_loss(logits, labels, t_len, s_len)
-            total.backward()
-            last.update(total=total.detach(), d_enc=e.grad, d_pred=p.grad)
-            return
-        logits, boundary, ranges, simple = port.joiner_forward(w, jc, e, t_len, p, s_len, labels)
-        pruned = port.pruned_rnnt_loss(logits, labels, boundary, ranges)
-        total = 0.5 * simple + 0.5 * pruned
-        total.backward()
-        last.update(total=total.detach(), simple=simple.detach(), pruned=pruned.detach(), ranges=ranges, d_enc=e.grad,
-                    d_pred=p.grad)
+        last.clear()
+        last.update(port_once(cfg, batch, n, joiner_state))
 
     for _ in range(warmup):
         one()
@@ -287,7 +319,7 @@ def cpu_arm(cfg, batch, n_utts: int, steps: int, warmup: int, joiner_state=None,
                        f"{steps} steps after {warmup} warm-up, {sec:.2f} s/step"), sec, last
 
 
-def parity_block(cfg, batch, ref, n, joiner, loss_mod, dev, mode):
+def parity_block(cfg, batch, ref, n, joiner, loss_mod, dev, mode, joiner_state):
     """The timed configuration checked against the CPU baseline's results on the SAME batch and weights (first n
     utterances, one eager step): relative loss errors, the rate of prune-range entries that differ, and the
     gradient of encoder_out over the utterances whose windows all agree (max |diff| / max |ref|)."""
@@ -301,6 +333,8 @@ def parity_block(cfg, batch, ref, n, joiner, loss_mod, dev, mode):
         pruned = loss_mod({"logits": logits, "logits_length": sub["t_len"], "targets": sub["labels"],
                            "targets_length": sub["s_len"], "boundary": boundary, "ranges": ranges})
         total = 0.5 * simple + 0.5 * pruned
+        if hasattr(joiner, "ctc_proj"):
+            total = total + ctc_branch(joiner, enc, sub["t_len"], sub["labels"], sub["s_len"])
     else:
         logits, _, _, _ = joiner(enc, sub["t_len"], pred, sub["s_len"])
         total = loss_mod({"logits": logits, "logits_length": sub["t_len"], "targets": sub["labels"],
@@ -324,6 +358,14 @@ def parity_block(cfg, batch, ref, n, joiner, loss_mod, dev, mode):
         out["pruned_loss_rel"] = rel(pruned, ref["pruned"])
         out["grad_rel"] = rel(g[same], gr[same]) if bool(same.any()) else None
         out["grad_rel_all_utterances"] = rel(g, gr)
+        if out["ranges_mismatch"] > 0.0:
+            # the window is an argmax over fp32 sums that tie up to rounding whenever several windows hold all of a
+            # frame's occupation mass: the CPU path once more ON THE RANGES SELECTED HERE compares everything
+            # downstream of the selection, over all utterances
+            forced = port_once(cfg, batch, n, joiner_state, ranges_override=ranges.cpu())
+            out["forced_ranges"] = {"pruned_loss_rel": rel(pruned, forced["pruned"]), "loss_rel": rel(total, forced["total"]),
+                                    "grad_rel": rel(g, forced["d_enc"]),
+                                    "grad_pred_rel": rel(pred.grad.float().cpu(), forced["d_pred"])}
     else:
         out["grad_rel"] = rel(g, gr)
     return out
@@ -457,11 +499,12 @@ def main():
     step()
     launches_per_step = _lib.launch_count() - launches0
     graphed = None
+    graph_priority = int(os.environ.get("S2T_BENCH_GRAPH_PRIORITY", "0"))
     if not args.eager:
         from speech2text_b200.graph import GraphedStep
         if world > 1 and os.environ.get("S2T_BENCH_GRAPH_COLLECTIVE", "1") != "0":
             try:  # the all-reduce inside the graph: no launch gap between the last dW kernel and NCCL
-                graphed = GraphedStep(step)
+                graphed = GraphedStep(step, priority=graph_priority)
                 run_step = graphed
                 execution = "cuda graph replay of the step (forward + backward + the gradient/scalar all-reduce)"
             except Exception as exc:
@@ -471,7 +514,7 @@ def main():
                                  "capturing the compute part only\n")
         if graphed is None:
             try:
-                graphed = GraphedStep(step_core)
+                graphed = GraphedStep(step_core, priority=graph_priority)
                 run_step = lambda: finish(graphed())
                 execution = "cuda graph replay of the eager step (forward + backward)" + (
                     ", all-reduce issued after it" if world > 1 else "")
@@ -599,7 +642,12 @@ def main():
             Bc, Tc, Sc, Vc, Dc, Rc, Ic = (cfg[k] for k in ("B", "T", "U", "V", "D", "R", "I"))
             if Rc > 0:
                 fl = 6.0 * (Tc + Sc + 1) * Dc * Vc + 6.0 * (Sc + 1) * Tc * Vc + (12.0 * Tc * Rc * Vc * Ic if Ic > 0 else 0.0)
-                by = (3.0 * (Tc + Sc + 1) * Dc * (2 if in_dtype == "bf16" else 4) + 6.0 * (Tc + Sc + 1) * Vc * 4 + 4.0 * (Sc * (Tc + 1) + (Sc + 1) * Tc) * 4
+                fl += 6.0 * Tc * Dc * Vc if cfg.get("ctc") else 0.0
+                if cfg.get("ctc"):  # Projector D -> V (fwd, dx, dW) and the CTC loss on its logits (two reads, one gradient write)
+                    fl_ctc, by_ctc = 6.0 * Tc * Dc * Vc, 3.0 * Tc * Vc * 4 + 5.0 * Tc * (Sc + 1) * 4
+                else:
+                    fl_ctc = by_ctc = 0.0
+                by = (by_ctc + 3.0 * (Tc + Sc + 1) * Dc * (2 if in_dtype == "bf16" else 4) + 6.0 * (Tc + Sc + 1) * Vc * 4 + 4.0 * (Sc * (Tc + 1) + (Sc + 1) * Tc) * 4
                       + 2.0 * Tc * Rc * 8 + 4.0 * Tc * Rc * 2 * 4)
             else:
                 fl = 6.0 * (Tc + Sc + 1) * Dc * Vc + 12.0 * Tc * (Sc + 1) * Vc * max(Ic, 1)
@@ -637,7 +685,7 @@ def main():
             base["value_1thread"] = base1["value"]
             base["sample_1thread"] = f"1 step, {sec1:.2f} s"
             line["cpu_baseline"] = base
-            line["parity"] = parity_block(cfg, batch, ref, min(args.cpu_utts, cfg["B"]), joiner, loss_mod, dev, args.mode)
+            line["parity"] = parity_block(cfg, batch, ref, min(args.cpu_utts, cfg["B"]), joiner, loss_mod, dev, args.mode, state)
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = None
         emit(line)

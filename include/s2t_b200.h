@@ -178,6 +178,27 @@ int s2t_joiner_materialize(int mode, const float* am, const float* lm, const int
                            const float* b1, const float* W2, const float* b2, int B, int T, int S, int R, int V,
                            int I, int act, void* workspace, float* logits, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * CTC loss with the log-softmax fused in.
+ * Replaces F.log_softmax + transpose + nn.CTCLoss of /root/reference/model/loss/ctc_loss.py:35-41 (the CTC branch of
+ * PrunedRnntTask / CtcHybridRnnt, task_factory/rnnt_task.py:341-349, 485-496); the (T,B,V) log-probabilities are
+ * never written.
+ *   logits (B,T,V) fp32; targets (B,S) int64, padded; logit_lengths / target_lengths (B) int64.
+ *   fwd: lse (B,T) and nll (B) = -log P(targets | logits) per utterance (+inf without a valid alignment);
+ *        the workspace (s2t_ctc_workspace_bytes) holds the lattice and must reach bwd unchanged.
+ *   bwd: grad_logits (B,T,V) = grad_nll[b] * d nll[b] / d logits (fully written; zero for padding frames and,
+ *        with zero_infinity != 0, for utterances whose nll is infinite).
+ * Reductions ("mean" divides by the target lengths as torch does) stay with the caller.
+ * ------------------------------------------------------------------------- */
+size_t s2t_ctc_workspace_bytes(int B, int T, int S, int V);
+int s2t_ctc_loss_fwd(const float* logits, const int64_t* targets, const int64_t* logit_lengths,
+                     const int64_t* target_lengths, int B, int T, int S, int V, int blank, void* workspace, float* lse,
+                     float* nll, void* stream);
+int s2t_ctc_loss_bwd(const float* logits, const int64_t* targets, const int64_t* logit_lengths,
+                     const int64_t* target_lengths, int B, int T, int S, int V, int blank, const void* workspace,
+                     const float* lse, const float* nll, const float* grad_nll, int zero_infinity, float* grad_logits,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,8 +33,14 @@ def _act(name: str):
 
 def joiner_forward(w: Dict[str, torch.Tensor], cfg: dict, encoder_out, encoder_out_lengths,
                    predict_out, target_lengths, target: Optional[torch.Tensor] = None,
-                   prune_variant: Optional[str] = None):
-    """joiner.py:126-182.  ``w`` uses the reference's state_dict keys."""
+                   prune_variant: Optional[str] = None, ranges_override: Optional[torch.Tensor] = None):
+    """joiner.py:126-182.  ``w`` uses the reference's state_dict keys.
+
+    ``ranges_override`` (test hook, not in the reference): use these prune ranges instead of the ones selected
+    here.  The selection is an argmax over fp32 window sums; with the cumulative variant every window that holds
+    (nearly) all of a frame's occupation mass ties up to rounding, so two correct implementations pick different --
+    equivalent -- windows on some frames.  Forcing the ranges under test lets everything downstream of the
+    (non-differentiable) selection be compared at full tolerance."""
     prune_range = cfg.get("prune_range", 5)
     act = _act(cfg.get("activation", "relu"))
     am = F.linear(encoder_out, w["_enc_proj.weight"], w["_enc_proj.bias"])
@@ -59,6 +65,9 @@ def joiner_forward(w: Dict[str, torch.Tensor], cfg: dict, encoder_out, encoder_o
         )
         ranges = k2.get_rnnt_prune_ranges(px_grad=px_grad, py_grad=py_grad, boundary=boundary,
                                           s_range=prune_range, variant=prune_variant)
+        if ranges_override is not None:
+            assert ranges_override.shape == ranges.shape and ranges_override.dtype == ranges.dtype
+            ranges = ranges_override
         am, lm = k2.do_rnnt_pruning(am=am, lm=lm, ranges=ranges)
     else:
         am = am.unsqueeze(2)
@@ -89,20 +98,30 @@ def rnnt_loss(logits, targets, logits_length, targets_length, blank_label=0, cla
         targets_length.to(torch.int32), blank=blank_label, clamp=clamp, reduction=reduction)
 
 
-def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None):
+def ctc_loss(logits, targets, logits_length, targets_length, blank_label=0, reduction="mean", zero_infinity=True):
+    """ctc_loss.py:35-41 (torch's CPU kernel, the reference's own back end; fp64 logits give the fp64 oracle)."""
+    log_probs = F.log_softmax(logits, dim=-1).transpose(0, 1)
+    if log_probs.dtype != torch.float64:
+        log_probs = log_probs.to(dtype=torch.float32)
+    return F.ctc_loss(log_probs, targets, logits_length, targets_length, blank=blank_label, reduction=reduction,
+                      zero_infinity=zero_infinity)
+
+
+def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None, ranges_override=None):
     """One fwd+bwd of the hot path exactly as rnnt_task.py:469-514 strings it
     together.  Returns a dict of losses, ranges and gradients."""
     cfg = spec["joiner"]
-    w = {k: (torch.as_tensor(v).to(dtype)).requires_grad_(True) for k, v in w.items()}
-    enc = torch.as_tensor(case["encoder_out"]).to(dtype).requires_grad_(True)
-    pred = torch.as_tensor(case["predict_out"]).to(dtype).requires_grad_(True)
+    w = {k: torch.as_tensor(v).detach().to(dtype).clone().requires_grad_(True) for k, v in w.items()}
+    # detached copies: the caller's tensors must not become autograd leaves of this run
+    enc = torch.as_tensor(case["encoder_out"]).detach().to(dtype).clone().requires_grad_(True)
+    pred = torch.as_tensor(case["predict_out"]).detach().to(dtype).clone().requires_grad_(True)
     enc_len = torch.as_tensor(case["encoder_out_lengths"])
     tgt_len = torch.as_tensor(case["target_lengths"])
     tgt = torch.as_tensor(case["target"])
     out = {}
     if cfg.get("prune_range", 5) > 0:
         logits, boundary, ranges, simple = joiner_forward(w, cfg, enc, enc_len, pred, tgt_len,
-                                                          tgt, prune_variant)
+                                                          tgt, prune_variant, ranges_override)
         pruned = pruned_rnnt_loss(logits, tgt, boundary, ranges, **spec.get("loss", {}))
         total = (spec["simple_loss_scale"] * simple + spec["pruned_loss_scale"] * pruned).mean()
         out.update(simple_loss=simple.detach(), pruned_loss=pruned.detach(),

@@ -49,6 +49,9 @@ _SIGNATURES = {
     "s2t_linear_workspace_bytes": (c_size_t, [ctypes.c_int64, I, I]),
     "s2t_linear_fwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P]),
     "s2t_linear_bwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P, P, P]),
+    "s2t_ctc_workspace_bytes": (c_size_t, [I, I, I, I]),
+    "s2t_ctc_loss_fwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P]),
+    "s2t_ctc_loss_bwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P, I, P, P]),
     "s2t_joiner_materialize": (c_int, [I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P]),
 }
 
@@ -86,8 +89,19 @@ def launch_count() -> int:
     return int(lib().s2t_launch_count())
 
 
+_profiling = False
+
+
 def profile_enable(on: bool) -> None:
+    global _profiling
+    _profiling = bool(on)
     lib().s2t_profile_enable(1 if on else 0)
+
+
+def profiling() -> bool:
+    """True while the per-kernel event timer is on: the host side then keeps every kernel on one stream (exclusive
+    kernel times), as the library does for its own fork/join."""
+    return _profiling
 
 
 def profile_report() -> dict:

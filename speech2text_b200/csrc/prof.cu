@@ -76,11 +76,14 @@ struct SideStreams {
   cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr};
   bool ok = false;
 };
-SideStreams& side_streams() {
-  static thread_local SideStreams per_device[64];
+// One pair of side streams per (device, caller stream): two independent chains of the step that run on different
+// caller streams (the simple-loss gradients next to the joiner forward, functional._SimpleLoss) must not meet on a
+// shared side stream, where the second chain would queue behind the first one's kernels.
+SideStreams& side_streams(cudaStream_t main) {
+  static thread_local std::map<std::pair<int, cudaStream_t>, SideStreams> table;
   int dev = 0;
   cudaGetDevice(&dev);
-  SideStreams& st = per_device[dev & 63];
+  SideStreams& st = table[std::make_pair(dev, main)];
   if (!st.ok) {
     for (int i = 0; i < 2; ++i) {
       cudaStreamCreateWithFlags(&st.s[i], cudaStreamNonBlocking);
@@ -100,7 +103,7 @@ ForkJoin::ForkJoin(cudaStream_t main) : main_(main), used_{false, false} {
 
 cudaStream_t ForkJoin::side(int i) {
   if (!enabled_) return main_;
-  SideStreams& st = side_streams();
+  SideStreams& st = side_streams(main_);
   if (!used_[i]) {
     cudaEventRecord(st.fork, main_);
     cudaStreamWaitEvent(st.s[i], st.fork, 0);
@@ -111,7 +114,7 @@ cudaStream_t ForkJoin::side(int i) {
 
 void ForkJoin::join() {
   if (!enabled_) return;
-  SideStreams& st = side_streams();
+  SideStreams& st = side_streams(main_);
   for (int i = 0; i < 2; ++i) {
     if (!used_[i]) continue;
     cudaEventRecord(st.done[i], st.s[i]);

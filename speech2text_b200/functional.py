@@ -89,7 +89,35 @@ def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tens
 # ---------------------------------------------------------------------------
 # k2.rnnt_loss_smoothed(..., return_grad=True)      joiner.py:100-110
 # ---------------------------------------------------------------------------
+_SIDE_STREAMS: dict = {}
+_ONES: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
+
+
+def _ones(n: int, device) -> Tensor:
+    key = (n, device)
+    t = _ONES.get(key)
+    if t is None:
+        t = _ONES[key] = torch.ones((n,), dtype=torch.float32, device=device)
+    return t
+
+
+def _early_simple_backward() -> bool:
+    return os.environ.get("S2T_B200_EARLY_SIMPLE_BWD", "1") != "0" and not _lib.profiling()
+
+
 class _SimpleLoss(torch.autograd.Function):
+    """The occupation probabilities -- all the gradient of the simple loss needs besides a per-utterance scale --
+    exist at the end of the forward call (k2 computes them there too, for the prune ranges).  The gradient
+    contractions therefore start right away on a side stream, with unit scale, next to what the caller does
+    between this call and its backward pass (prune ranges, joiner forward, band lattice: the lattice kernels keep
+    one CTA per utterance busy and leave the other SMs idle); backward only waits for them and applies the scale."""
 
     @staticmethod
     @_on_tensor_device
@@ -116,6 +144,19 @@ class _SimpleLoss(torch.autograd.Function):
                                         float(lm_only_scale), float(am_only_scale), ptr(am_max), ptr(lm_max),
                                         ptr(px), ptr(py), ptr(nrm), ptr(alpha), ptr(scores), ptr(px_grad),
                                         ptr(py_grad), ptr(ws), stream()))
+        ctx.early = None
+        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _early_simple_backward():
+            cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                d_am, d_lm = torch.empty_like(am), torch.empty_like(lm)
+                check(lib().s2t_simple_loss_bwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
+                                                ptr(px_grad), ptr(py_grad), ptr(_ones(B, dev)), B, T, S, V, blank,
+                                                float(lm_only_scale), float(am_only_scale), ptr(ws), ptr(d_am),
+                                                ptr(d_lm), stream()))
+            for t in (am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws):
+                t.record_stream(side)
+            ctx.early = (d_am, d_lm, side)
         # the workspace travels to backward: in tensor-core mode it holds the bf16 exp(am - max) / exp(lm - max)
         # operands the forward pass produced on the side
         ctx.save_for_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws)
@@ -132,6 +173,17 @@ class _SimpleLoss(torch.autograd.Function):
         am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws = ctx.saved_tensors
         B, T, V = am.shape
         S = lm.shape[1] - 1
+        if ctx.early is not None:
+            d_am, d_lm, side = ctx.early
+            ctx.early = None
+            cur = torch.cuda.current_stream(am.device)
+            cur.wait_stream(side)  # also what joins the side stream back into a CUDA-graph capture of the step
+            d_am.record_stream(cur)
+            d_lm.record_stream(cur)
+            if grad_scores is None:
+                return (None,) * 8
+            g = _f32c(grad_scores).view(B, 1, 1)
+            return d_am.mul_(g), d_lm.mul_(g), None, None, None, None, None, None
         if grad_scores is None:
             return (None,) * 8
         grad_scores = _f32c(grad_scores)
@@ -365,6 +417,59 @@ def joiner_materialize(am: Tensor, lm: Tensor, W1, b1, W2, b2, ranges: Optional[
     check(lib().s2t_joiner_materialize(mode, ptr(am), ptr(lm), ptr(ranges), ptr(W1), ptr(b1), ptr(W2), ptr(b2),
                                        B, T, S, R, V, I, act, ptr(workspace), ptr(logits), stream()))
     return logits
+
+
+# ---------------------------------------------------------------------------
+# CTC loss with the log-softmax fused in               ctc_loss.py:35-41
+# ---------------------------------------------------------------------------
+class _CtcLoss(torch.autograd.Function):
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, logits: Tensor, targets: Tensor, logits_length: Tensor, targets_length: Tensor, blank: int,
+                zero_infinity: bool):
+        x = _f32c(logits)
+        B, T, V = x.shape
+        dev = x.device
+        targets = _i64c(targets.to(dev))
+        if targets.dim() != 2 or targets.shape[0] != B:
+            raise ValueError("ctc_loss: targets must be a padded (B, S) tensor (as the reference's dataset produces)")
+        S = targets.shape[1]
+        in_len, tgt_len = _i64c(logits_length.to(dev)), _i64c(targets_length.to(dev))
+        ws = torch.empty((lib().s2t_ctc_workspace_bytes(B, T, S, V),), dtype=torch.uint8, device=dev)
+        lse = torch.empty((B, T), dtype=torch.float32, device=dev)
+        nll = torch.empty((B,), dtype=torch.float32, device=dev)
+        check(lib().s2t_ctc_loss_fwd(ptr(x), ptr(targets) if S > 0 else ptr(None), ptr(in_len), ptr(tgt_len), B, T, S, V,
+                                     blank, ptr(ws), ptr(lse), ptr(nll), stream()))
+        ctx.save_for_backward(x, targets, in_len, tgt_len, ws, lse, nll)
+        ctx.meta = (S, blank, bool(zero_infinity), logits.dtype)
+        return torch.where(torch.isinf(nll), torch.zeros_like(nll), nll) if zero_infinity else nll.clone()
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, grad_nll):
+        x, targets, in_len, tgt_len, ws, lse, nll = ctx.saved_tensors
+        S, blank, zero_infinity, in_dtype = ctx.meta
+        B, T, V = x.shape
+        grad = torch.empty_like(x)
+        check(lib().s2t_ctc_loss_bwd(ptr(x), ptr(targets) if S > 0 else ptr(None), ptr(in_len), ptr(tgt_len), B, T, S, V,
+                                     blank, ptr(ws), ptr(lse), ptr(nll), ptr(_f32c(grad_nll)), 1 if zero_infinity else 0,
+                                     ptr(grad), stream()))
+        return (grad if in_dtype == torch.float32 else grad.to(in_dtype)), None, None, None, None, None
+
+
+def ctc_loss(logits: Tensor, targets: Tensor, logits_length: Tensor, targets_length: Tensor, blank: int = 0,
+             reduction: str = "mean", zero_infinity: bool = True) -> Tensor:
+    """``nn.CTCLoss(blank, reduction, zero_infinity)(F.log_softmax(logits, -1).transpose(0, 1), ...)`` on (B, T, V)
+    logits, with the log-softmax fused in and its gradient written straight into d logits."""
+    nll = _CtcLoss.apply(logits, targets, logits_length, targets_length, blank, zero_infinity)
+    if reduction == "none":
+        return nll
+    if reduction == "sum":
+        return nll.sum()
+    if reduction == "mean":  # torch: mean over the batch of nll / target length
+        return (nll / targets_length.to(nll.device).clamp_min(1).to(nll.dtype)).mean()
+    raise ValueError(f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
 
 
 # ---------------------------------------------------------------------------

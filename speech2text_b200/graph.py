@@ -16,10 +16,13 @@ import torch
 
 class GraphedStep:
 
-    def __init__(self, fn: Callable[[], Any], warmup: int = 3, pool: Optional[Any] = None):
+    def __init__(self, fn: Callable[[], Any], warmup: int = 3, pool: Optional[Any] = None, priority: int = 0):
+        """``priority`` < 0 captures the step on a high-priority stream: kernels that the step forks onto ordinary
+        side streams (the simple-loss gradients that start in the forward pass, functional._SimpleLoss) then only
+        take SMs the main chain leaves idle instead of competing with it."""
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedStep needs a CUDA device")
-        side = torch.cuda.Stream()
+        side = torch.cuda.Stream(priority=priority)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up off the default stream, as graph capture requires
             for _ in range(warmup):
@@ -27,7 +30,7 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool):
+        with torch.cuda.graph(self.graph, pool=pool, stream=side):
             self.outputs = fn()
 
     def pool(self):

@@ -1,0 +1,133 @@
+"""GPU parity tests of the fused CTC loss through the C ABI against the reference's own
+back end -- ``F.log_softmax`` + ``F.ctc_loss`` on the CPU (/root/reference/model/loss/ctc_loss.py:35-41), run in
+fp64 as the oracle (``oracle.reference_port.ctc_loss``).
+
+Tolerances (north_star): relative 1e-5 on the loss, 1e-4 on gradients (max |diff| / max |ref|).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import reference_port as port
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _case(B, T, S, V, seed, scale=2.0, in_len=None, tgt_len=None, repeat=True):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, T, V, generator=g) * scale
+    targets = torch.randint(1, V, (B, S), generator=g) if S > 0 else torch.zeros((B, 0), dtype=torch.int64)
+    if repeat and S >= 3 and B >= 2:
+        targets[0, 2] = targets[0, 1]  # a repeated label needs a blank in between
+        targets[1, :] = targets[1, 0]  # all labels equal
+    if in_len is None:
+        in_len = torch.randint(max(1, T // 2), T + 1, (B,), generator=g)
+        in_len[0] = T
+    if tgt_len is None:
+        tgt_len = torch.minimum(torch.randint(0, S + 1, (B,), generator=g), in_len // 2)
+        tgt_len[0] = min(S, T // 2)
+    for b in range(B):
+        targets[b, int(tgt_len[b]):] = 0  # padded like the reference's collate (dataset/utils.py:189-191)
+    return logits, targets, torch.as_tensor(in_len), torch.as_tensor(tgt_len)
+
+
+def _reference(logits, targets, in_len, tgt_len, reduction, zero_infinity, weights=None):
+    x = logits.detach().double().clone().requires_grad_(True)
+    loss = port.ctc_loss(x, targets, in_len, tgt_len, blank_label=0, reduction=reduction, zero_infinity=zero_infinity)
+    (loss if weights is None else (loss * weights.double())).sum().backward()
+    return loss.detach(), x.grad
+
+
+def _ours(logits, targets, in_len, tgt_len, reduction, zero_infinity, weights=None, dtype=torch.float32):
+    from speech2text_b200 import functional as F2
+    dev = torch.device("cuda:0")
+    x = logits.to(dev).to(dtype).requires_grad_(True)
+    loss = F2.ctc_loss(x, targets.to(dev), in_len.to(dev), tgt_len.to(dev), blank=0, reduction=reduction,
+                       zero_infinity=zero_infinity)
+    (loss if weights is None else (loss * weights.to(dev))).sum().backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), x.grad.detach().float().cpu()
+
+
+@pytest.mark.parametrize("reduction", ["none", "mean", "sum"])
+@pytest.mark.parametrize("B,T,S,V", [(5, 40, 9, 13), (3, 64, 20, 128), (4, 200, 15, 1000), (2, 33, 1, 6), (3, 17, 0, 5)])
+def test_ctc_loss_and_gradient_match_torch_fp64(B, T, S, V, reduction):
+    logits, targets, in_len, tgt_len = _case(B, T, S, V, seed=B * 1000 + T)
+    w = torch.linspace(0.5, 1.5, B) if reduction == "none" else None  # non-uniform upstream gradient
+    ref, gref = _reference(logits, targets, in_len, tgt_len, reduction, True, w)
+    got, ggot = _ours(logits, targets, in_len, tgt_len, reduction, True, w)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) <= LOSS_RTOL, (got, ref)
+    assert rel_err(ggot, gref) <= GRAD_RTOL
+
+
+def test_ctc_infeasible_alignments_and_zero_infinity():
+    """T_b too short for the target (repeats need a blank in between): torch returns inf, zero_infinity turns the
+    loss and that utterance's gradient into zeros."""
+    B, T, S, V = 4, 12, 6, 9
+    logits, targets, _, _ = _case(B, T, S, V, seed=3, repeat=False)
+    targets[1] = torch.tensor([2, 2, 2, 2, 2, 2])
+    in_len = torch.tensor([12, 8, 3, 12])    # utterance 1: 6 equal labels need 11 frames; utterance 2: 6 labels, 3 frames
+    tgt_len = torch.tensor([6, 6, 6, 2])
+    for zero_inf in (True, False):
+        ref, gref = _reference(logits, targets, in_len, tgt_len, "none", zero_inf)
+        got, ggot = _ours(logits, targets, in_len, tgt_len, "none", zero_inf)
+        assert torch.equal(torch.isinf(got), torch.isinf(ref)), (got, ref)
+        fin = torch.isfinite(ref)
+        assert rel_err(got[fin], ref[fin]) <= LOSS_RTOL
+        if zero_inf:
+            assert float(got[1]) == 0.0 and float(got[2]) == 0.0
+            assert float(ggot[1].abs().max()) == 0.0 and float(ggot[2].abs().max()) == 0.0
+        assert rel_err(ggot[fin], gref[fin]) <= GRAD_RTOL
+    # frames past the utterance's length carry no gradient
+    _, g = _ours(logits, targets, in_len, tgt_len, "sum", True)
+    assert float(g[3, :, :].abs().sum()) > 0 and float(g[1, 8:].abs().max()) == 0.0
+
+
+def test_ctc_module_has_the_reference_interface():
+    """Loss({"model": "CTC"}) routes here with the reference's kwargs (rnnt_task.py:485-493); bf16 logits come back
+    with a bf16 gradient."""
+    from model.loss.loss import Loss
+    from speech2text_b200.loss.ctc_loss import CtcLoss
+    mod = Loss({"model": "CTC", "config": {"blank_label": 0, "reduction": "mean", "zero_infinity": True}})
+    assert isinstance(mod.loss, CtcLoss)
+    logits, targets, in_len, tgt_len = _case(3, 50, 12, 40, seed=9)
+    dev = torch.device("cuda:0")
+    x = logits.to(dev).requires_grad_(True)
+    loss = mod({"logits": x, "logits_length": in_len.to(dev), "targets": targets.to(dev), "targets_length": tgt_len.to(dev)})
+    loss.backward()
+    ref, gref = _reference(logits, targets, in_len, tgt_len, "mean", True)
+    assert rel_err(loss.detach().cpu(), ref) <= LOSS_RTOL and rel_err(x.grad.cpu(), gref) <= GRAD_RTOL
+    xb = logits.to(dev).bfloat16().requires_grad_(True)
+    lb = mod({"logits": xb, "logits_length": in_len.to(dev), "targets": targets.to(dev), "targets_length": tgt_len.to(dev)})
+    lb.backward()
+    assert xb.grad.dtype == torch.bfloat16
+    refb, grefb = _reference(xb.detach().float().cpu(), targets, in_len, tgt_len, "mean", True)
+    assert rel_err(lb.detach().cpu(), refb) <= LOSS_RTOL and rel_err(xb.grad.float().cpu(), grefb) <= 1e-2
+    with pytest.raises(Exception):
+        mod({"logits": logits, "logits_length": in_len, "targets": targets, "targets_length": tgt_len})  # CPU tensors
+
+
+def test_ctc_at_baseline_config_4_shape():
+    """BASELINE config 4's CTC half per utterance (T=500, U=125, V=2000), batch cut to 16 for the CPU oracle."""
+    B, T, S, V = 16, 500, 125, 2000
+    g = torch.Generator().manual_seed(1234)
+    logits = torch.randn(B, T, V, generator=g)
+    in_len = torch.randint(300, T + 1, (B,), generator=g)
+    in_len[0] = T
+    tgt_len = torch.clamp((in_len.float() * S / T * 0.9).long(), 1, S)
+    tgt_len[0] = S
+    targets = torch.randint(1, V, (B, S), generator=g)
+    for b in range(B):
+        targets[b, int(tgt_len[b]):] = 0
+    ref, gref = _reference(logits, targets, in_len, tgt_len, "mean", True)
+    got, ggot = _ours(logits, targets, in_len, tgt_len, "mean", True)
+    assert rel_err(got, ref) <= LOSS_RTOL, (got, ref)
+    assert rel_err(ggot, gref) <= GRAD_RTOL
+    # property at size: every live frame's gradient sums to zero (softmax minus a distribution over the states)
+    rows = ggot.sum(-1)
+    assert float(rows.abs().max()) < 1e-5 * float(ggot.abs().max()) * V ** 0.5 + 1e-6
