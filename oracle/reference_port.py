@@ -33,14 +33,18 @@ def _act(name: str):
 
 def joiner_forward(w: Dict[str, torch.Tensor], cfg: dict, encoder_out, encoder_out_lengths,
                    predict_out, target_lengths, target: Optional[torch.Tensor] = None,
-                   prune_variant: Optional[str] = None, ranges_override: Optional[torch.Tensor] = None):
+                   prune_variant: Optional[str] = None, ranges_override: Optional[torch.Tensor] = None,
+                   exact: bool = False):
     """joiner.py:126-182.  ``w`` uses the reference's state_dict keys.
 
     ``ranges_override`` (test hook, not in the reference): use these prune ranges instead of the ones selected
     here.  The selection is an argmax over fp32 window sums; with the cumulative variant every window that holds
     (nearly) all of a frame's occupation mass ties up to rounding, so two correct implementations pick different --
     equivalent -- windows on some frames.  Forcing the ranges under test lets everything downstream of the
-    (non-differentiable) selection be compared at full tolerance."""
+    (non-differentiable) selection be compared at full tolerance.
+
+    ``exact`` (test hook): skip the reference's casts to float32 (joiner.py:99-102, pruned_rnnt_loss.py:40), so that
+    fp64 inputs give the exact result of the reference's formulas -- the yardstick for "which fp32 run is closer"."""
     prune_range = cfg.get("prune_range", 5)
     act = _act(cfg.get("activation", "relu"))
     am = F.linear(encoder_out, w["_enc_proj.weight"], w["_enc_proj.bias"])
@@ -53,8 +57,8 @@ def joiner_forward(w: Dict[str, torch.Tensor], cfg: dict, encoder_out, encoder_o
         boundary[:, 3] = encoder_out_lengths
         assert target.dim() == 2
         simple_loss, (px_grad, py_grad) = k2.rnnt_loss_smoothed(
-            lm=lm.to(dtype=torch.float32),  # "Pruned rnnt loss strictly required fp32" (joiner.py:99-102)
-            am=am.to(dtype=torch.float32),
+            lm=lm if exact else lm.to(dtype=torch.float32),  # "Pruned rnnt loss strictly required fp32" (joiner.py:99-102)
+            am=am if exact else am.to(dtype=torch.float32),
             symbols=target,
             termination_symbol=0,
             lm_only_scale=cfg.get("lm_scale", 0.0),
@@ -80,10 +84,10 @@ def joiner_forward(w: Dict[str, torch.Tensor], cfg: dict, encoder_out, encoder_o
 
 
 def pruned_rnnt_loss(logits, targets, boundary, ranges, termination_symbol=0,
-                     rnnt_type="regular", delay_penalty=0.0, reduction="mean"):
+                     rnnt_type="regular", delay_penalty=0.0, reduction="mean", exact=False):
     """pruned_rnnt_loss.py:34-50."""
     return k2.rnnt_loss_pruned(
-        logits=logits.to(torch.float32),  # pruned_rnnt_loss.py:40
+        logits=logits if exact else logits.to(torch.float32),  # pruned_rnnt_loss.py:40
         symbols=targets, ranges=ranges, termination_symbol=termination_symbol,
         boundary=boundary, rnnt_type=rnnt_type, delay_penalty=delay_penalty,
         reduction=reduction)
@@ -107,7 +111,8 @@ def ctc_loss(logits, targets, logits_length, targets_length, blank_label=0, redu
                       zero_infinity=zero_infinity)
 
 
-def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None, ranges_override=None):
+def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None, ranges_override=None,
+                       exact=False):
     """One fwd+bwd of the hot path exactly as rnnt_task.py:469-514 strings it
     together.  Returns a dict of losses, ranges and gradients."""
     cfg = spec["joiner"]
@@ -121,8 +126,8 @@ def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_var
     out = {}
     if cfg.get("prune_range", 5) > 0:
         logits, boundary, ranges, simple = joiner_forward(w, cfg, enc, enc_len, pred, tgt_len,
-                                                          tgt, prune_variant, ranges_override)
-        pruned = pruned_rnnt_loss(logits, tgt, boundary, ranges, **spec.get("loss", {}))
+                                                          tgt, prune_variant, ranges_override, exact)
+        pruned = pruned_rnnt_loss(logits, tgt, boundary, ranges, exact=exact, **spec.get("loss", {}))
         total = (spec["simple_loss_scale"] * simple + spec["pruned_loss_scale"] * pruned).mean()
         out.update(simple_loss=simple.detach(), pruned_loss=pruned.detach(),
                    boundary=boundary, ranges=ranges, logits=logits.detach())

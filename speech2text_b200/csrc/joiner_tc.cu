@@ -947,6 +947,345 @@ int pack_weights(const JoinerProblem& p, const TcDims& d, const TcWs& w, cudaStr
   return pack_jobs(jobs, 4, st);
 }
 
+
+// ---- fused forward -----------------------------------------------------------------------------
+// hidden = act(am + lm[ranges]) W1^T + b1 and logits = hidden W2^T + b2 -> (lse, px, py) in ONE persistent kernel:
+// a CTA owns a 128-row tile of the joiner lattice from the gather to the finished log-probabilities, so that neither
+// act(am + lm[ranges]) nor the logits ever exist outside the SM (the hidden rows are written once, for the backward
+// pass).  Replaces joint_pack_kernel + the hidden and logits contractions + lse_combine_kernel for inner_dim <= 256.
+//
+//   warps  8..15  producers: build the A operand of contraction 1, act(am + lm[ranges]) -> bf16, one 64-entry
+//                 vocabulary step at a time straight into the swizzled stage image (JointRowProducer)
+//   warp   0      bulk copies of W1 (256 x 64 bf16 = 32 KB per step) into the same stage ring
+//   warp   2      bulk copies of W2 blocks (128 vocabulary rows x 64 hidden entries = 16 KB) into a second ring
+//   warp   1      tcgen05.mma issue.  Contraction 1: 128 x 256 (hidden) accumulator in TMEM columns 0..255, K = V.
+//                 Contraction 2: for every 128-column vocabulary tile, 128 x 128 accumulators alternating between
+//                 TMEM columns 256..383 and 384..511, K = 256 with the A operand read from the hidden tile that the
+//                 epilogue warps parked in shared memory
+//   warps  4..7   epilogue (a thread = one lattice row = one TMEM lane): drain the hidden accumulator, add b1, round to
+//                 bf16, store the row into the shared-memory K-major image (and the same 16-byte pieces into the
+//                 packed hidden operand Hp in HBM); then, per vocabulary tile, the running (max, sum exp) and the
+//                 sym / blank gather; lse / px / py are final when the tile's last vocabulary tile has been drained
+//
+// Shared memory: 2 x 48 KB stage ring 1 + 64 KB hidden tile + 4 x 16 KB ring 2.  Per tile the SM pulls W1 and W2
+// (2 x Vp x 256 x 2 bytes) through L2 once: at V = 500 that is 512 KB against 8192 cycles of MMA issue.
+constexpr int kFS1 = 2;                          // stages of ring 1
+constexpr int kFS2 = 4;                          // stages of ring 2
+constexpr int kFStage1 = 3 * kBlockBytes;        // A (128 x 64) + B (256 x 64)
+constexpr int kFHBytes = 4 * kBlockBytes;        // hidden tile: 128 x 256 bf16
+constexpr int kFThreads = 32 * (kCtrlWarps + kEpiWarps + kProdWarps);
+constexpr size_t kFSmemBytes = (size_t)kFS1 * kFStage1 + kFHBytes + (size_t)kFS2 * kBlockBytes + 1024 /*align*/ + 512 /*barriers*/;
+static_assert(kFSmemBytes <= 227 * 1024, "fused joiner forward: shared memory");
+
+struct FusedFwdParams {
+  const float* am;
+  const float* lm;
+  const int* am_row;
+  const int* lm_row;
+  const int* row_sym;
+  const uint8_t* W1p;  // rows i (256), k-blocks over v
+  const uint8_t* W2p;  // rows v (Vp), k-blocks over i (4)
+  const float* b1;
+  const float* b2;
+  uint8_t* Hp;         // packed hidden rows (rows m, 4 k-blocks) for the backward pass
+  uint8_t* Jp;         // optional by-product: packed act(am + lm[ranges]) for the backward pass
+  const int* live_idx;     // live 128-row tiles (or null: all)
+  const int* live_prefix;
+  const int64_t* boundary;
+  float* lse;
+  float* px;
+  float* py;
+  int64_t M;
+  int Mt, V, I, kbV, nN, w2_row_blocks, act, blank, T, R;
+  float delay_penalty;
+};
+
+__global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const FusedFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  uint8_t* ring1 = smem;
+  uint8_t* H = ring1 + kFS1 * kFStage1;
+  uint8_t* ring2 = H + kFHBytes;
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(ring2 + kFS2 * kBlockBytes);
+  uint64_t* empty1 = full1 + kFS1;
+  uint64_t* full2 = empty1 + kFS1;
+  uint64_t* empty2 = full2 + kFS2;
+  uint64_t* acc1_full = empty2 + kFS2;
+  uint64_t* acc1_empty = acc1_full + 1;
+  uint64_t* h_full = acc1_empty + 1;
+  uint64_t* h_empty = h_full + 1;
+  uint64_t* acc2_full = h_empty + 1;   // [2]
+  uint64_t* acc2_empty = acc2_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool listed = p.live_idx != nullptr;
+  const int n_tiles = listed ? p.live_prefix[p.Mt] : p.Mt;
+  auto tile_of = [&](int j) { return listed ? p.live_idx[j] : j; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFS1; ++s) {
+      mbar_init(&full1[s], 1 + kProdWarps);
+      mbar_init(&empty1[s], 1);
+    }
+    for (int s = 0; s < kFS2; ++s) {
+      mbar_init(&full2[s], 1);
+      mbar_init(&empty2[s], 1);
+    }
+    mbar_init(acc1_full, 1);
+    mbar_init(acc1_empty, kEpiWarps);
+    mbar_init(h_full, kEpiWarps);
+    mbar_init(h_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc2_full[i], 1);
+      mbar_init(&acc2_empty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- W1 steps into ring 1 ----
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int j = blockIdx.x; j < n_tiles; j += gridDim.x) {
+        for (int ks = 0; ks < p.kbV; ++ks, ++g) {
+          const int s = g % kFS1;
+          mbar_wait(&empty1[s], ((g / kFS1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full1[s], 2 * kBlockBytes);
+          bulk_copy_g2s(ring1 + s * kFStage1 + kBlockBytes, p.W1p + (size_t)ks * 2 * kBlockBytes, 2 * kBlockBytes, &full1[s]);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ---- W2 blocks into ring 2 ----
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int j = blockIdx.x; j < n_tiles; j += gridDim.x) {
+        for (int n = 0; n < p.nN; ++n) {
+          for (int kb = 0; kb < 4; ++kb, ++g) {
+            const int s = g % kFS2;
+            mbar_wait(&empty2[s], ((g / kFS2) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full2[s], kBlockBytes);
+            bulk_copy_g2s(ring2 + s * kBlockBytes, p.W2p + packed_block_index(n, kb, p.w2_row_blocks) * kBlockBytes, kBlockBytes,
+                          &full2[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issue ----
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_bf16(128, 256), idesc2 = umma_idesc_bf16(128, 128);
+      uint32_t g1 = 0, g2 = 0, nt = 0, lt = 0;
+      for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
+        // contraction 1 -> TMEM columns 0..255 (drained by the epilogue of the previous tile)
+        mbar_wait(acc1_empty, (lt & 1) ^ 1);
+        tc_fence_after();
+        for (int ks = 0; ks < p.kbV; ++ks, ++g1) {
+          const int s = g1 % kFS1;
+          mbar_wait(&full1[s], (g1 / kFS1) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring1 + s * kFStage1), sb = sa + kBlockBytes;
+#pragma unroll
+          for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4)
+            umma_bf16(tmem_base, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc1,
+                      ks > 0 || k4 > 0);
+          umma_commit(&empty1[s]);
+        }
+        umma_commit(acc1_full);
+        // contraction 2: A = the hidden tile in shared memory
+        mbar_wait(h_full, lt & 1);
+        tc_fence_after();
+        const uint32_t sh = smem_u32(H);
+        for (int n = 0; n < p.nN; ++n, ++nt) {
+          const uint32_t buf = nt & 1;
+          mbar_wait(&acc2_empty[buf], ((nt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + 256 + buf * 128;
+          for (int kb = 0; kb < 4; ++kb, ++g2) {
+            const int s = g2 % kFS2;
+            mbar_wait(&full2[s], (g2 / kFS2) & 1);
+            tc_fence_after();
+            const uint32_t sa = sh + kb * kBlockBytes, sb = smem_u32(ring2 + s * kBlockBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4)
+              umma_bf16(acc, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc2,
+                        kb > 0 || k4 > 0);
+            umma_commit(&empty2[s]);
+          }
+          umma_commit(&acc2_full[buf]);
+        }
+        umma_commit(h_empty);  // every MMA that reads this tile's hidden rows has completed
+      }
+    }
+  } else if (warp >= kCtrlWarps && warp < kCtrlWarps + kEpiWarps) {
+    // ---- epilogue ----
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row inside the tile = TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t nt = 0, lt = 0;
+    for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
+      const int tile = tile_of(j);
+      const int64_t m = (int64_t)tile * 128 + r;
+      const bool live = m < p.M;
+      // hidden rows: TMEM -> + b1 -> bf16 -> shared-memory operand image (+ Hp)
+      mbar_wait(acc1_full, lt & 1);
+      tc_fence_after();
+      mbar_wait(h_empty, (lt & 1) ^ 1);
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        float v[32];
+        tmem_ld_32x32(lane_addr + cc * 32, v);
+        const int n = cc * 32;
+        float x[32];
+        if (n + 32 <= p.I) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) x[q] = live ? v[q] + __ldg(p.b1 + n + q) : 0.f;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) x[q] = (live && n + q < p.I) ? v[q] + __ldg(p.b1 + n + q) : 0.f;
+        }
+        uint4 mine[4];
+        pack_row32_bf16(x, mine);
+        const int kb = n >> 6, c0 = (n & 63) >> 3;
+        uint8_t* hs = H + kb * kBlockBytes;
+        uint8_t* hg = p.Hp + packed_block_index(tile, kb, p.Mt) * kBlockBytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = block_chunk_offset(r, c0 + q);
+          *reinterpret_cast<uint4*>(hs + off) = mine[q];
+          *reinterpret_cast<uint4*>(hg + off) = mine[q];  // the four pieces fill one 64-byte half of the row's block row
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc1_empty);
+        mbar_arrive(h_full);
+      }
+      // logits: running (max, sum exp) over the vocabulary tiles + the sym / blank gather
+      float mx = kNegInf, sum = 0.f, sym_logit = 0.f, blank_logit = 0.f;
+      const int csym = live ? __ldg(p.row_sym + m) : -1;
+      for (int nn = 0; nn < p.nN; ++nn, ++nt) {
+        const uint32_t buf = nt & 1;
+        mbar_wait(&acc2_full[buf], (nt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[32];
+          tmem_ld_32x32(lane_addr + 256 + buf * 128 + cc * 32, v);
+          const int n = nn * 128 + cc * 32;
+          if (!live || n >= p.V) continue;
+          float x[32];
+          float cm = kNegInf;
+          if (n + 32 <= p.V) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              x[q] = v[q] + __ldg(p.b2 + n + q);
+              cm = fmaxf(cm, x[q]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              x[q] = (n + q < p.V) ? v[q] + __ldg(p.b2 + n + q) : kNegInf;
+              cm = fmaxf(cm, x[q]);
+            }
+          }
+          if (cm > mx) {
+            sum *= ex2_approx((mx - cm) * kLog2e);
+            mx = cm;
+          }
+          const float nm = -mx * kLog2e;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            s0 += ex2_approx(fmaf(x[q], kLog2e, nm));
+            s1 += ex2_approx(fmaf(x[q + 1], kLog2e, nm));
+          }
+          sum += s0 + s1;
+          if (csym >= n && csym < n + 32) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (n + q == csym) sym_logit = x[q];
+          }
+          if (p.blank >= n && p.blank < n + 32) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (n + q == p.blank) blank_logit = x[q];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc2_empty[buf]);
+      }
+      if (live) {
+        const int64_t bt = m / p.R;
+        const int b = (int)(bt / p.T), t = (int)(bt % p.T);
+        const int Tb = p.boundary ? (int)p.boundary[4 * b + 3] : p.T;
+        if (p.boundary && t >= min(max(Tb, 0), p.T)) {  // padding frame: the lattice ignores these entries
+          p.lse[m] = 0.f;
+          p.px[m] = 0.f;
+          p.py[m] = 0.f;
+        } else {
+          const float l = mx + logf(sum);
+          float xv = sym_logit - l;
+          if (p.delay_penalty != 0.f) xv += p.delay_penalty * (0.5f * (float)(Tb - 1) - (float)t);
+          p.lse[m] = l;
+          p.px[m] = xv;
+          p.py[m] = blank_logit - l;
+        }
+      }
+    }
+  } else if (warp >= kCtrlWarps + kEpiWarps) {
+    // ---- producers: act(am + lm[ranges]) -> ring 1 ----
+    const JointRowProducer prod{p.am, p.lm, p.am_row, p.lm_row, p.M, p.V, p.act, p.Jp, p.Mt};
+    uint32_t g = 0;
+    for (int j = blockIdx.x; j < n_tiles; j += gridDim.x) {
+      ProdCtx pc;
+      pc.m_tile = tile_of(j);
+      pc.n_tile = 0;
+      pc.batch = 0;
+      pc.ks0 = 0;
+      pc.n_it = p.kbV;
+      pc.valid = true;
+      pc.t = (warp - kCtrlWarps - kEpiWarps) * 32 + lane;
+      pc.smem = ring1;
+      pc.stage_bytes = kFStage1;
+      pc.stages = kFS1;
+      pc.it0 = g;
+      pc.full = full1;
+      pc.empty = empty1;
+      prod.run(pc);
+      g += p.kbV;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+int launch_joiner_fwd_fused(const FusedFwdParams& p, cudaStream_t stream) {
+  static bool configured[kMaxDevices] = {};
+  if (int rc = configure_smem_once(joiner_fwd_fused_kernel, kFSmemBytes, configured, "tc_joiner_fwd_fused")) return rc;
+  const int sms = device_info().sms;
+  // upper bound of the live tiles (the exact count lives on the device): CTAs beyond it find no tile and leave
+  const int grid = p.Mt < sms ? p.Mt : sms;
+  ProfScope prof("tc_joiner_fwd_fused", stream);
+  joiner_fwd_fused_kernel<<<grid, kFThreads, kFSmemBytes, stream>>>(p);
+  return check_launch("tc_joiner_fwd_fused");
+}
+
+bool joiner_fused_fwd_ok(const TcDims& d) {
+  static const bool disabled = getenv("S2T_B200_NO_FUSED_FWD") != nullptr;
+  return !disabled && d.Ip == 256;
+}
+
 }  // namespace
 
 size_t joiner_tc_workspace_bytes(int64_t M, int V, int I) {
@@ -979,6 +1318,18 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   MnDebug live;
   live.live_idx = w.live_idx;
   live.live_prefix = w.live_prefix;
+  if (joiner_fused_fwd_ok(d)) {
+    // one kernel from the gather to (lse, px, py); tiles of padding frames are never computed: their entries are zeros
+    if (w.live_idx) {
+      cudaMemsetAsync(lse, 0, (size_t)M * sizeof(float), stream);
+      cudaMemsetAsync(px, 0, (size_t)M * sizeof(float), stream);
+      cudaMemsetAsync(py, 0, (size_t)M * sizeof(float), stream);
+    }
+    FusedFwdParams fp{p.am, p.lm, w.am_row, w.lm_row, w.row_sym, w.W1p, w.W2p, p.b1, p.b2, w.Hp, w.Jp, w.live_idx,
+                      w.live_prefix, p.boundary, lse, px, py, M, d.Mt, p.V, p.I, d.kbV, d.Vp / 128, d.Vp / 128, p.act,
+                      p.blank, p.T, p.R, p.delay_penalty};
+    return launch_joiner_fwd_fused(fp, stream);
+  }
   // hidden: M x Ip, K = V.  With J kept for the backward pass it is written once by a fully parallel kernel and the
   // contraction streams it like any packed operand; otherwise the producer warps build it on the fly.
   {

@@ -71,9 +71,8 @@ prune_argmax_kernel(const float* __restrict__ px_grad, const float* __restrict__
   const float* pyg = py_grad + (int64_t)b * S1 * T;
   const int Sb = (int)boundary[4 * b + 2], Tb = (int)boundary[4 * b + 3];
   const int ncand = S1 - R + 1;
-  // variant B carries a running sum from s = 0 (sequential by contract): one segment does all of it
-  const int per = VARIANT == 0 ? (ncand + kSegs - 1) / kSegs : ncand;
-  const int s0 = min(seg * per, ncand), s1 = min(s0 + per, ncand);
+  const int per = (ncand + kSegs - 1) / kSegs;
+  const int s0 = VARIANT == 0 ? min(seg * per, ncand) : 0, s1 = VARIANT == 0 ? min(s0 + per, ncand) : 0;
   float best_v = kNegInf;
   int best = s0;
   if (t < Tb - 1 && t < T && s0 < s1) {
@@ -123,13 +122,25 @@ prune_argmax_kernel(const float* __restrict__ px_grad, const float* __restrict__
           }
         }
       }
-    } else {
-      // B: cs[s+R] - cs[s] with cs the running sum over s of px_grad + py_grad, formed sequentially
-      // from 0 exactly as the oracle does: cs_lo and cs_hi are two pointers into the same running sum.
+    }
+  }
+  if (VARIANT == 1) {
+    // B: cs[s+R] - cs[s] with cs the running sum over s of tot[s] = px_grad[s] + py_grad[s], formed sequentially
+    // from 0 exactly as the oracle does (the contract leaves no freedom in the order of the sum).  What can run in
+    // parallel are the loads: all kSegs threads of a frame fetch tot[] into shared memory (coalesced along t, eight
+    // rows in flight per frame), then one thread per frame walks the two pointers cs_lo / cs_hi over it.
+    extern __shared__ float tot[];  // [S1][32]
+    if (t < T) {
+      for (int j = seg; j < S1; j += kSegs)
+        tot[j * 32 + threadIdx.x] = (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+    }
+    __syncthreads();
+    if (seg == 0 && t < Tb - 1 && t < T) {
+      const float* col = tot + threadIdx.x;
       float cs_hi = 0.f;
-      for (int j = 0; j < R; ++j)
-        cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+      for (int j = 0; j < R; ++j) cs_hi += col[j * 32];
       float cs_lo = 0.f;
+#pragma unroll 4
       for (int s = 0; s < ncand; ++s) {
         const float v = cs_hi - cs_lo;
         if (v > best_v) {
@@ -137,9 +148,8 @@ prune_argmax_kernel(const float* __restrict__ px_grad, const float* __restrict__
           best = s;
         }
         if (s + 1 < ncand) {
-          cs_lo += (s < S ? __ldg(pxg + (int64_t)s * T1 + t) : 0.f) + __ldg(pyg + (int64_t)s * T + t);
-          const int j = s + R;
-          cs_hi += (j < S ? __ldg(pxg + (int64_t)j * T1 + t) : 0.f) + __ldg(pyg + (int64_t)j * T + t);
+          cs_lo += col[s * 32];
+          cs_hi += col[(s + R) * 32];
         }
       }
     }
@@ -198,8 +208,15 @@ int prune_ranges(const float* px_grad, const float* py_grad, const int64_t* boun
   }
   ProfScope prof("prune_ranges_kernel", stream, 2);
   const dim3 grid((unsigned)((T + 31) / 32), (unsigned)B), block(32, kSegs);
-  if (variant == 0) prune_argmax_kernel<0><<<grid, block, 0, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
-  else prune_argmax_kernel<1><<<grid, block, 0, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
+  if (variant == 0) {
+    prune_argmax_kernel<0><<<grid, block, 0, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
+  } else {
+    const size_t smem_b = (size_t)(S + 1) * 32 * sizeof(float);
+    S2T_REQUIRE(smem_b <= 200 * 1024, "prune_ranges: S=%d too long for the cumulative variant's shared-memory column tile", S);
+    if (smem_b > 48 * 1024)
+      cudaFuncSetAttribute(prune_argmax_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    prune_argmax_kernel<1><<<grid, block, smem_b, stream>>>(px_grad, py_grad, boundary, S, T, R, ranges);
+  }
   prune_adjust_kernel<<<B, kThreads, smem, stream>>>(T, R, ranges);
   return check_launch("prune_ranges_kernel");
 }

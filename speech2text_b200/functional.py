@@ -109,7 +109,7 @@ def _ones(n: int, device) -> Tensor:
 
 
 def _early_simple_backward() -> bool:
-    return os.environ.get("S2T_B200_EARLY_SIMPLE_BWD", "1") != "0" and not _lib.profiling()
+    return os.environ.get("S2T_B200_EARLY_SIMPLE_BWD", "0") != "0" and not _lib.profiling()
 
 
 class _SimpleLoss(torch.autograd.Function):

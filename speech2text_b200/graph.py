@@ -30,7 +30,8 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool, stream=side):
+        # priority 0: torch's own capture stream (several graphs of one process then share it)
+        with torch.cuda.graph(self.graph, pool=pool, **({"stream": side} if priority != 0 else {})):
             self.outputs = fn()
 
     def pool(self):
