@@ -182,6 +182,75 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
   for (int i = threadIdx.x; i < 2 * (Lfull + 4); i += blockDim.x) sm[i] = kNegInf;
   __syncthreads();
   double base = 0.0;  // running offset (replicated in every thread)
+  if (L <= (int)blockDim.x) {
+    // One state per thread (every target the reference's configs produce: 2 S + 1 <= 1024).  tau counts the steps
+    // of this direction, t = tau (alpha) or T_b - 1 - tau (beta~); rows are indexed so that the two neighbours a
+    // state reads are the cells in front of it (alpha: r = s; beta: r = L - 1 - s).  The emissions of the next four
+    // steps are already in registers: the recursion itself never waits for global memory.
+    const int s = threadIdx.x;
+    const bool active = s < L;
+    const int j = (s & 1) ? (s + 1) >> 1 : 0;
+    const int r = dir == 0 ? s : L - 1 - s;
+    bool skip = false;
+    if (active && (s & 1)) {
+      if (dir == 0) skip = s >= 3 && lab[(s - 1) >> 1] != lab[(s - 3) >> 1];
+      else skip = s + 2 < L && lab[(s - 1) >> 1] != lab[(s + 1) >> 1];
+    }
+    const float* ep = Eb + j;
+    auto frame = [&](int tau) { return dir == 0 ? tau : Tb - 1 - tau; };
+    float eq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) eq[u] = (active && u < Tb) ? __ldg(ep + (int64_t)frame(u) * (S + 1)) : 0.f;
+    for (int tau0 = 0; tau0 < Tb; tau0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tau = tau0 + u;
+        if (tau >= Tb) break;
+        const int t = frame(tau);
+        const float e = eq[u];
+        if (active && tau + 4 < Tb) eq[u] = __ldg(ep + (int64_t)frame(tau + 4) * (S + 1));
+        float* cur = row[tau & 1];
+        const float* prev = row[(tau & 1) ^ 1];
+        float v = kNegInf;
+        if (active) {
+          float stored;
+          if (tau == 0) {
+            if (dir == 0) {
+              v = s <= 1 ? e : kNegInf;
+              stored = v;
+            } else {
+              stored = s >= L - 2 ? 0.f : kNegInf;
+              v = stored + e;
+            }
+          } else {
+            const float a3 = log_add3(prev[r], prev[r - 1], skip ? prev[r - 2] : kNegInf);
+            v = a3 + e;
+            stored = dir == 0 ? v : a3;
+          }
+          cur[r] = v;
+          out[(int64_t)t * Lfull + s] = stored;
+        }
+        if (threadIdx.x == 0) off[t] = base;  // the frame's stored values are relative to the base before a re-basing
+        if ((tau % kRebase) == kRebase - 1 && tau + 1 < Tb) {
+          const float m = block_max(v, red);  // includes the barrier that publishes cur
+          if (m > kNegInf) {
+            if (active) cur[r] -= m;
+            base += (double)m;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (dir == 0 && threadIdx.x == 0) {
+      const float* last = row[(Tb - 1) & 1];
+      const float a = last[L - 1], c = L >= 2 ? last[L - 2] : kNegInf;
+      const float m = fmaxf(a, c);
+      const double lp = m == kNegInf ? -INFINITY : (double)(m + __logf(__expf(a - m) + __expf(c - m))) + base;
+      nll[b] = (float)(-lp);
+    }
+    return;
+  }
+  // general path: several states per thread
   if (dir == 0) {
     // alpha_t(s) = e_t(s) + logadd(alpha_{t-1}(s), alpha_{t-1}(s-1), [skip] alpha_{t-1}(s-2))
     for (int t = 0; t < Tb; ++t) {

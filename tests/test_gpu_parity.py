@@ -814,6 +814,54 @@ def test_streaming_contraction_kernel_single_cta_and_cta_pair(shape, pair, monke
     assert ((C.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(3, 37, 9, 70, 40, 4, 24), (2, 150, 40, 500, 64, 5, 256), (2, 61, 12, 1000, 48, 5, 200)],
+                         ids=lambda s: "x".join(str(v) for v in s))
+def test_fused_joiner_forward_matches_the_three_kernel_path(shape, monkeypatch):
+    """The single-kernel joiner forward (gather -> hidden -> logits -> lse / px / py inside one CTA) against the
+    joint_pack + hidden + logits + combine kernels it replaces: same operands, same accumulation order, so the
+    log-probabilities agree to fp32 rounding of the log-sum-exp; gradients follow (the backward pass reads the hidden
+    rows either path stored)."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    B, T, U, V, D, R, I = shape
+    g = torch.Generator().manual_seed(5)
+    enc0 = torch.randn(B, T, D, generator=g) * 0.7
+    pred0 = torch.randn(B, U + 1, D, generator=g) * 0.7
+    tgt = torch.randint(1, V, (B, U), generator=g)
+    t_len = torch.randint(max(U, int(0.6 * T)), T + 1, (B,), generator=g)
+    t_len[0] = T
+    s_len = torch.clamp((t_len.float() * U / T * 0.9).long(), 1, U)
+    s_len[0] = U
+    torch.manual_seed(3)
+    joiner = Joiner(JoinerConfig(input_dim=D, output_dim=V, inner_dim=I, activation="tanh", prune_range=R)).to(_dev())
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", "bf16")
+    res = {}
+    for name, env in (("fused", None), ("split", "1")):
+        if env is None:
+            monkeypatch.delenv("S2T_B200_NO_FUSED_FWD", raising=False)
+        else:
+            monkeypatch.setenv("S2T_B200_NO_FUSED_FWD", env)
+        joiner.zero_grad(set_to_none=True)
+        enc = enc0.to(_dev()).requires_grad_(True)
+        pred = pred0.to(_dev()).requires_grad_(True)
+        loss_mod = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "none"}})
+        logits, boundary, ranges, simple = joiner(enc, t_len.to(_dev()), pred, s_len.to(_dev()), tgt.to(_dev()))
+        pruned = loss_mod({"logits": logits, "logits_length": t_len.to(_dev()), "targets": tgt.to(_dev()),
+                           "targets_length": s_len.to(_dev()), "boundary": boundary, "ranges": ranges})
+        (0.5 * simple + pruned.sum()).backward()
+        torch.cuda.synchronize()
+        res[name] = dict(pruned=pruned.detach().clone(), ranges=ranges.clone(), d_enc=enc.grad.clone(),
+                         d_pred=pred.grad.clone(), **{"d" + k: p.grad.clone() for k, p in joiner.named_parameters()})
+    a, b = res["split"], res["fused"]
+    assert torch.equal(a["ranges"], b["ranges"])
+    assert torch.isfinite(b["pruned"]).all()
+    assert rel_err(b["pruned"], a["pruned"]) < 1e-5
+    for k in a:
+        if k.startswith("d"):
+            assert rel_err(b[k], a[k]) < 5e-3, k  # 1-ulp differences of lse move the occupation probabilities by ~3e-5
+
+
 def test_bound_gradient_bucket_receives_the_same_gradients(monkeypatch):
     """FlatGradBucket.bind(): the weight-gradient kernels write straight into the flat all-reduce buffer
      and autograd's accumulate is skipped; the buffer must hold what autograd would have
