@@ -970,11 +970,30 @@ int pack_weights(const JoinerProblem& p, const TcDims& d, const TcWs& w, cudaStr
 // Shared memory: 2 x 48 KB stage ring 1 + 64 KB hidden tile + 4 x 16 KB ring 2.  Per tile the SM pulls W1 and W2
 // (2 x Vp x 256 x 2 bytes) through L2 once: at V = 500 that is 512 KB against 8192 cycles of MMA issue.
 constexpr int kFS1 = 2;                          // stages of ring 1
-constexpr int kFS2 = 4;                          // stages of ring 2
+constexpr int kFS2 = 2;                          // stages of ring 2
 constexpr int kFStage1 = 3 * kBlockBytes;        // A (128 x 64) + B (256 x 64)
 constexpr int kFHBytes = 4 * kBlockBytes;        // hidden tile: 128 x 256 bf16
 constexpr int kFThreads = 32 * (kCtrlWarps + kEpiWarps + kProdWarps);
-constexpr size_t kFSmemBytes = (size_t)kFS1 * kFStage1 + kFHBytes + (size_t)kFS2 * kBlockBytes + 1024 /*align*/ + 512 /*barriers*/;
+// Raw ring: the DISTINCT am / lm rows a tile's 128 lattice rows are built from (a frame's am row serves its R band
+// slots, an lm row serves every frame whose band holds that symbol position: ~40 distinct rows against 256 row
+// reads), one 64-entry vocabulary step per stage, brought in by bulk copies.  The producers then read them from
+// shared memory: what a tile pulls through the L2 -> SM path for its A operand drops from 512 KB to ~80 KB.
+constexpr int kRawStages = 2;
+constexpr int kRawAm = 32, kRawLm = 32;                 // staged rows per step (tiles that need more take the direct path)
+constexpr int kRawRowBytes = kBlockK * 4;               // 64 fp32
+constexpr int kRawBytes = (kRawAm + kRawLm) * kRawRowBytes;  // 16 KB
+constexpr size_t kFSmemBytes = (size_t)kFS1 * kFStage1 + kFHBytes + (size_t)kFS2 * kBlockBytes + (size_t)kRawStages * kRawBytes +
+                               1024 /*align*/ + 512 /*barriers, tile plans*/;
+
+// what the planner warp tells the producers about a tile (double-buffered by tile parity)
+struct TilePlan {
+  int fast;      // 1: rows staged in the raw ring; 0: direct global loads (too many distinct rows, or unaligned)
+  int am_first;  // first am row (b T + t) of the tile
+  int n_am;
+  int b0;        // utterance of the tile's first row
+  int lo0, n0;   // lm rows (b (S+1) + s) of utterance b0: lo0 .. lo0 + n0 - 1
+  int lo1, n1;   // lm rows of utterance b0 + 1
+};
 static_assert(kFSmemBytes <= 227 * 1024, "fused joiner forward: shared memory");
 
 struct FusedFwdParams {
@@ -1006,7 +1025,8 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
   uint8_t* ring1 = smem;
   uint8_t* H = ring1 + kFS1 * kFStage1;
   uint8_t* ring2 = H + kFHBytes;
-  uint64_t* full1 = reinterpret_cast<uint64_t*>(ring2 + kFS2 * kBlockBytes);
+  uint8_t* raw = ring2 + kFS2 * kBlockBytes;
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(raw + kRawStages * kRawBytes);
   uint64_t* empty1 = full1 + kFS1;
   uint64_t* full2 = empty1 + kFS1;
   uint64_t* empty2 = full2 + kFS2;
@@ -1016,7 +1036,10 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
   uint64_t* h_empty = h_full + 1;
   uint64_t* acc2_full = h_empty + 1;   // [2]
   uint64_t* acc2_empty = acc2_full + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 2);
+  uint64_t* raw_full = acc2_empty + 2;   // [kRawStages]
+  uint64_t* raw_empty = raw_full + kRawStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRawStages);
+  TilePlan* plans = reinterpret_cast<TilePlan*>(tmem_slot + 4);  // [2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool listed = p.live_idx != nullptr;
@@ -1039,6 +1062,10 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc2_full[i], 1);
       mbar_init(&acc2_empty[i], kEpiWarps);
+    }
+    for (int s = 0; s < kRawStages; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], kProdWarps);
     }
     fence_mbar_init();
   }
@@ -1074,6 +1101,80 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
             bulk_copy_g2s(ring2 + s * kBlockBytes, p.W2p + packed_block_index(n, kb, p.w2_row_blocks) * kBlockBytes, kBlockBytes,
                           &full2[s]);
           }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---- planner: which distinct am / lm rows a tile needs, and their bulk copies into the raw ring ----
+    const bool aligned = (p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.am) | reinterpret_cast<uintptr_t>(p.lm)) & 15) == 0;
+    uint32_t g = 0, lt = 0;
+    for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
+      const int64_t m0 = (int64_t)tile_of(j) * 128;
+      // the stage of the tile's first step must be free before the plan slot of two tiles ago is overwritten
+      mbar_wait(&raw_empty[g % kRawStages], ((g / kRawStages) & 1) ^ 1);
+      int am_lo = INT_MAX, am_hi = -1, lo0 = INT_MAX, hi0 = -1, lo1 = INT_MAX, hi1 = -1, bad = 0;
+      const int a_first = __ldg(p.am_row + m0);  // row m0 < M: the tile is live
+      const int b0 = a_first / p.T;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t m = m0 + lane + 32 * q;
+        if (m < p.M) {
+          const int ar = __ldg(p.am_row + m), lr = __ldg(p.lm_row + m);
+          am_lo = min(am_lo, ar);
+          am_hi = max(am_hi, ar);
+          const int seg = ar / p.T - b0;
+          if (seg == 0) {
+            lo0 = min(lo0, lr);
+            hi0 = max(hi0, lr);
+          } else if (seg == 1) {
+            lo1 = min(lo1, lr);
+            hi1 = max(hi1, lr);
+          } else {
+            bad = 1;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        am_lo = min(am_lo, __shfl_xor_sync(0xffffffffu, am_lo, o));
+        am_hi = max(am_hi, __shfl_xor_sync(0xffffffffu, am_hi, o));
+        lo0 = min(lo0, __shfl_xor_sync(0xffffffffu, lo0, o));
+        hi0 = max(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+        lo1 = min(lo1, __shfl_xor_sync(0xffffffffu, lo1, o));
+        hi1 = max(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+      }
+      const int n_am = am_hi - am_lo + 1, n0 = hi0 >= lo0 ? hi0 - lo0 + 1 : 0, n1 = hi1 >= lo1 ? hi1 - lo1 + 1 : 0;
+      const bool fast = aligned && !bad && n_am <= kRawAm && n0 + n1 <= kRawLm;
+      if (lane == 0) plans[lt & 1] = TilePlan{fast ? 1 : 0, am_lo, n_am, b0, lo0, n0, lo1, n1};
+      __syncwarp();
+      const int n_rows = n_am + n0 + n1;
+      for (int ks = 0; ks < p.kbV; ++ks, ++g) {
+        const int s = g % kRawStages;
+        if (ks > 0) mbar_wait(&raw_empty[s], ((g / kRawStages) & 1) ^ 1);
+        if (!fast) {
+          if (lane == 0) mbar_arrive(&raw_full[s]);
+          continue;
+        }
+        const int cols = min(kBlockK, p.V - ks * kBlockK);
+        const uint32_t row_bytes = (uint32_t)cols * 4;
+        if (lane == 0) mbar_arrive_expect_tx(&raw_full[s], row_bytes * (uint32_t)n_rows);
+        __syncwarp();
+        uint8_t* dst0 = raw + s * kRawBytes;
+        for (int i = lane; i < n_rows; i += 32) {
+          const float* src;
+          int slot;
+          if (i < n_am) {
+            src = p.am + (int64_t)(am_lo + i) * p.V;
+            slot = i;
+          } else if (i - n_am < n0) {
+            src = p.lm + (int64_t)(lo0 + i - n_am) * p.V;
+            slot = kRawAm + i - n_am;
+          } else {
+            src = p.lm + (int64_t)(lo1 + i - n_am - n0) * p.V;
+            slot = kRawAm + i - n_am;
+          }
+          bulk_copy_g2s(dst0 + slot * kRawRowBytes, src + ks * kBlockK, row_bytes, &raw_full[s]);
         }
       }
     }
@@ -1244,25 +1345,90 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     }
   } else if (warp >= kCtrlWarps + kEpiWarps) {
     // ---- producers: act(am + lm[ranges]) -> ring 1 ----
-    const JointRowProducer prod{p.am, p.lm, p.am_row, p.lm_row, p.M, p.V, p.act, p.Jp, p.Mt};
-    uint32_t g = 0;
-    for (int j = blockIdx.x; j < n_tiles; j += gridDim.x) {
-      ProdCtx pc;
-      pc.m_tile = tile_of(j);
-      pc.n_tile = 0;
-      pc.batch = 0;
-      pc.ks0 = 0;
-      pc.n_it = p.kbV;
-      pc.valid = true;
-      pc.t = (warp - kCtrlWarps - kEpiWarps) * 32 + lane;
-      pc.smem = ring1;
-      pc.stage_bytes = kFStage1;
-      pc.stages = kFS1;
-      pc.it0 = g;
-      pc.full = full1;
-      pc.empty = empty1;
-      prod.run(pc);
-      g += p.kbV;
+    // Thread (warp w, lane l) builds 8 consecutive lattice rows, (2 w + l / 16) * 8 + i, and the four vocabulary
+    // entries 4 (l % 16) .. + 3 of every step: sixteen lanes cover the 256 bytes a row contributes to a step.
+    const JointRowProducer direct{p.am, p.lm, p.am_row, p.lm_row, p.M, p.V, p.act, p.Jp, p.Mt};
+    const int pw = warp - kCtrlWarps - kEpiWarps;
+    const int c = lane & 15, rbase = (pw * 2 + (lane >> 4)) * 8;
+    uint32_t g = 0, graw = 0, lt = 0;
+    for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
+      const int tile = tile_of(j);
+      mbar_wait(&raw_full[graw % kRawStages], (graw / kRawStages) & 1);  // also publishes the tile's plan
+      const TilePlan plan = plans[lt & 1];
+      if (!plan.fast) {
+        // the raw ring carries nothing for this tile: hand its stages straight back, then load directly
+        for (int ks = 0; ks < p.kbV; ++ks, ++graw) {
+          if (ks > 0) mbar_wait(&raw_full[graw % kRawStages], (graw / kRawStages) & 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_empty[graw % kRawStages]);
+        }
+        ProdCtx pc;
+        pc.m_tile = tile;
+        pc.n_tile = 0;
+        pc.batch = 0;
+        pc.ks0 = 0;
+        pc.n_it = p.kbV;
+        pc.valid = true;
+        pc.t = pw * 32 + lane;
+        pc.smem = ring1;
+        pc.stage_bytes = kFStage1;
+        pc.stages = kFS1;
+        pc.it0 = g;
+        pc.full = full1;
+        pc.empty = empty1;
+        direct.run(pc);
+        g += p.kbV;
+        continue;
+      }
+      int a_off[8], l_off[8];  // byte offsets of the row's staged am / lm row inside a raw stage; -1: dead row
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = (int64_t)tile * 128 + rbase + i;
+        a_off[i] = -1;
+        l_off[i] = 0;
+        if (m < p.M) {
+          const int ar = __ldg(p.am_row + m), lr = __ldg(p.lm_row + m);
+          a_off[i] = (ar - plan.am_first) * kRawRowBytes + c * 16;
+          const int slot = (ar / p.T == plan.b0) ? lr - plan.lo0 : plan.n0 + lr - plan.lo1;
+          l_off[i] = (kRawAm + slot) * kRawRowBytes + c * 16;
+        }
+      }
+      for (int ks = 0; ks < p.kbV; ++ks, ++g, ++graw) {
+        const int sr = graw % kRawStages;
+        if (ks > 0) mbar_wait(&raw_full[sr], (graw / kRawStages) & 1);
+        const uint8_t* rs = raw + sr * kRawBytes;
+        const int v = ks * kBlockK + c * 4;
+        uint2 o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool live = a_off[i] >= 0;
+          const float4 a = *reinterpret_cast<const float4*>(rs + (live ? a_off[i] : 0));
+          const float4 l = *reinterpret_cast<const float4*>(rs + (live ? l_off[i] : 0));
+          // dead rows and the vocabulary padding must come out as exact zeros (the stage may hold stale bits there)
+          const float x0 = (live && v + 0 < p.V) ? act_fwd_fast(a.x + l.x, p.act) : 0.f;
+          const float x1 = (live && v + 1 < p.V) ? act_fwd_fast(a.y + l.y, p.act) : 0.f;
+          const float x2 = (live && v + 2 < p.V) ? act_fwd_fast(a.z + l.z, p.act) : 0.f;
+          const float x3 = (live && v + 3 < p.V) ? act_fwd_fast(a.w + l.w, p.act) : 0.f;
+          o[i] = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+        }
+        // the raw stage is consumed (its values sit in registers): the planner may refill it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[sr]);
+        const int s1 = g % kFS1;
+        mbar_wait(&empty1[s1], ((g / kFS1) & 1) ^ 1);
+        uint8_t* dst = ring1 + s1 * kFStage1;
+        uint8_t* jdst = p.Jp ? p.Jp + packed_block_index(tile, ks, p.Mt) * kBlockBytes : nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rbase + i;
+          const uint32_t off = (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 7)) & 7) << 4) + (c & 1) * 8);
+          *reinterpret_cast<uint2*>(dst + off) = o[i];
+          if (jdst) *reinterpret_cast<uint2*>(jdst + off) = o[i];
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full1[s1]);
+      }
     }
   }
   tc_fence_before();

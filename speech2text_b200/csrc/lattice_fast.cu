@@ -49,64 +49,6 @@ __device__ __forceinline__ float log2_add(float x, float y) {
   return (d >= kMinLog2Diff) ? mx + __log2f(1.f + ex2_fast(d)) : mx;
 }
 
-// ---- extended-exponent arithmetic of the recursions -------------------------------------------------------------
-// A lattice value (a path probability, 1e-1000 and below) is carried as f * 2^E with f an ordinary float and E a
-// per-lane integer.  One step of a recursion is then
-//     value' = nb * X + own * Y      ->      two multiplies, an exponent compare and one fused multiply-add
-// instead of the log-domain MAX, SUB, EX2, ADD, LG2, ADD: the dependent chain of a diagonal loses both of its
-// special-function round trips, and the rounding error per step is 2^-24 RELATIVE to the value (the log-domain form
-// rounds relative to |log value|, i.e. to thousands, which is what forced the fp64 offsets of the first version).
-// The term with the larger exponent is added unscaled, so f never shrinks; it grows by at most 4x per step and is
-// folded back into E every 16 steps.  Zero is f == 0 with E = kZeroE.  The transition probabilities X, Y arrive as
-// log2 values and are split into integer and fractional part off the dependent chain.
-constexpr int kZeroE = -(1 << 24);
-
-struct XF {
-  float f;
-  int e;
-};
-
-// 2^d for d <= 0 (0 below the normal range)
-__device__ __forceinline__ float pow2_nonpos(int d) { return __int_as_float(max(d + 127, 0) << 23); }
-
-// log2 transition value -> (2^frac in [1, 2), integer part); -inf (a move that does not exist) -> (0, kZeroE)
-__device__ __forceinline__ XF xf_from_log2(float l) {
-  XF r;
-  const bool zero = !(l > -1e30f);
-  const float fl = floorf(l);
-  r.f = zero ? 0.f : ex2_fast(l - fl);
-  r.e = zero ? kZeroE : (int)fl;
-  return r;
-}
-
-// nb * x + own * y
-__device__ __forceinline__ XF xf_step(const XF& nb, const XF& x, const XF& own, const XF& y) {
-  const float t1 = nb.f * x.f, t2 = own.f * y.f;
-  const int e1 = nb.e + x.e, e2 = own.e + y.e;
-  const int em = max(e1, e2);
-  XF r;
-  r.f = fmaf(t1, pow2_nonpos(e1 - em), t2 * pow2_nonpos(e2 - em));
-  r.e = max(em, kZeroE);
-  return r;
-}
-
-// fold the exponent of f into e (f becomes [1, 2)); zero stays zero
-__device__ __forceinline__ void xf_normalise(XF& v) {
-  const int bits = __float_as_int(v.f);
-  const bool zero = v.f == 0.f;
-  v.e = zero ? kZeroE : v.e + ((bits >> 23) & 0xff) - 127;
-  v.f = zero ? 0.f : __int_as_float((bits & 0x007fffff) | 0x3f800000);
-}
-
-// log2 of the value relative to 2^eref (-inf for zero)
-__device__ __forceinline__ float xf_log2_rel(const XF& v, int eref) { return __log2f(v.f) + (float)(v.e - eref); }
-
-__device__ __forceinline__ int warp_max_int(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
 // ------------------------------------------------------------------------------------------------
 // (1) simple lattice
 // ------------------------------------------------------------------------------------------------
@@ -140,9 +82,8 @@ constexpr int kSimpleProducerWarps = 8;
 struct SimpleSmem {
   float* ringX;   // [G][W * RS]
   float* ringY;   // [G][W * RS]
-  float* bnd;     // [G + 1][bnd_stride]: boundary-row value (f) per diagonal at index d + 1; array G stays zero
-  int* bnd_e;     // the exponents of those values
-  double* offs;   // [G][n_off] (unused by the extended-exponent recursion; kept for the layout)
+  float* bnd;     // [G + 1][bnd_stride]: boundary-row value per diagonal at index d + 1; array G stays -inf
+  double* offs;   // [G][n_off]
   uint64_t* full;   // [G][kRing]
   uint64_t* empty;  // [G][kRing]
   uint64_t* bfull;  // [G][nblk_max]
@@ -164,16 +105,17 @@ __device__ __forceinline__ void simple_recursion(const SimpleArgs& a, const Simp
   const int send_lane = kBeta ? 0 : 31;   // lane whose value the next group needs
   const float* gx = sh.ringX + g * W * RS + lane;
   float* my_bnd = sh.bnd + g * sh.bnd_stride + 1;
-  int* my_bnd_e = sh.bnd_e + g * sh.bnd_stride + 1;
   const float* dep_bnd = sh.bnd + (has_dep ? dep : G) * sh.bnd_stride + 1;
-  const int* dep_bnd_e = sh.bnd_e + (has_dep ? dep : G) * sh.bnd_stride + 1;
+  double* my_offs = sh.offs + g * a.n_off;
+  const double* dep_offs = sh.offs + (has_dep ? dep : 0) * a.n_off;
   double* g_offs = (kBeta ? a.boff : a.aoff) + ((int64_t)b * G + g) * a.n_off;
   float* out0 = (kBeta ? a.beta_diag : a.alpha_diag) + (int64_t)b * a.diag_rows * ROWS + 32 * g + lane;
   const int src_lane = kBeta ? ((lane + 1) & 31) : ((lane + 31) & 31);
   const bool fin_mine = (Sb >> 5) == g;
   const int fin_lane = Sb & 31;
   constexpr int kStep = kBeta ? -1 : 1;
-  XF v{0.f, kZeroE};  // this lane's lattice value, f * 2^e (absolute: no running offset to maintain)
+  float v = kNegInf;
+  double off = 0.0;
 
   for (int k = 0; k < nblk; ++k) {
     const int D = kBeta ? (nblk - 1 - k) : k;
@@ -184,81 +126,65 @@ __device__ __forceinline__ void simple_recursion(const SimpleArgs& a, const Simp
     for (int h = 0; h < 2; ++h) {  // two 16-diagonal periods per block
       const int dh = kBeta ? (32 * D + 31 - 16 * h) : (32 * D + 16 * h);  // first diagonal of the period
       const int p = dh >> kRebaseShift;
-      // The values of a period are stored as log2 relative to 2^eref, eref = the group's largest exponent when the
-      // period starts (the occupation kernel adds the offsets of alpha and beta back in fp64).
-      // Boundary values of this period, one per lane (lane i serves step i): the row of the neighbour group that
-      // borders this one, one diagonal earlier -- absolute (f, e) pairs, nothing to convert.
-      XF bvals{0.f, kZeroE};
-      if (has_dep && lane < 16) {
-        const int dp = kBeta ? dh - lane + 1 : dh + lane - 1;
-        bvals.f = dep_bnd[dp];
-        bvals.e = dep_bnd_e[dp];
+      if (lane == 0) {
+        my_offs[p] = off;
+        g_offs[p] = off;
       }
-      xf_normalise(v);
-      // a group the wavefront has not reached yet holds zeros only: its first values come in over the boundary
-      int eref = warp_max_int(max(v.e, bvals.e));
-      if (eref == kZeroE) eref = 0;  // nothing yet: the source cell (value 1) may appear in this period
-      if (lane == 0) g_offs[p] = (double)eref;
+      // Boundary values of this period, one per lane (lane i serves step i), converted from the neighbour
+      // group's offset of the period they were computed in to this group's current offset.
+      float bvals = kNegInf;
+      if (has_dep && lane < 16) {
+        const int pp = kBeta ? p + 1 : p - 1;
+        const bool pp_ok = kBeta ? (16 * pp < 32 * nblk) : (pp >= 0);
+        const double o = (lane == 0) ? (pp_ok ? dep_offs[pp] : off) : dep_offs[p];
+        const int dp = kBeta ? dh - lane + 1 : dh + lane - 1;
+        bvals = dep_bnd[dp] + (float)(o - off);
+      }
       const float* rx = gx + (slot * 32 + (dh & 31)) * RS;
       float* out = out0 + (int64_t)dh * ROWS;
       float* bp = my_bnd + dh;
-      int* bpe = my_bnd_e + dh;
       const bool special = kBeta ? (nd <= dh && nd > dh - 16) : (dh == 0 || (nd >= dh && nd < dh + 16));
       if (!special) {
 #pragma unroll
         for (int ii = 0; ii < 16; ++ii) {
-          XF nb;
-          nb.f = __shfl_sync(0xffffffffu, v.f, src_lane);
-          nb.e = __shfl_sync(0xffffffffu, v.e, src_lane);
-          const float bf = __shfl_sync(0xffffffffu, bvals.f, ii);
-          const int be = __shfl_sync(0xffffffffu, bvals.e, ii);
-          if (lane == edge_lane) {
-            nb.f = bf;
-            nb.e = be;
-          }
-          v = xf_step(nb, xf_from_log2(rx[kStep * ii * RS]), v, xf_from_log2(rx[kStep * ii * RS + kYOff]));
-          out[kStep * ii * ROWS] = xf_log2_rel(v, eref);
-          if (lane == send_lane) {
-            bp[kStep * ii] = v.f;
-            bpe[kStep * ii] = v.e;
-          }
+          const float rot = __shfl_sync(0xffffffffu, v, src_lane);
+          const float bv = __shfl_sync(0xffffffffu, bvals, ii);
+          const float nb = (lane == edge_lane) ? bv : rot;
+          v = log2_add(nb + rx[kStep * ii * RS], v + rx[kStep * ii * RS + kYOff]);
+          out[kStep * ii * ROWS] = v;
+          if (lane == send_lane) bp[kStep * ii] = v;
         }
       } else {
 #pragma unroll 4
         for (int ii = 0; ii < 16; ++ii) {
           const int d = dh + kStep * ii;
-          XF nb;
-          nb.f = __shfl_sync(0xffffffffu, v.f, src_lane);
-          nb.e = __shfl_sync(0xffffffffu, v.e, src_lane);
-          const float bf = __shfl_sync(0xffffffffu, bvals.f, ii);
-          const int be = __shfl_sync(0xffffffffu, bvals.e, ii);
-          if (lane == edge_lane) {
-            nb.f = bf;
-            nb.e = be;
-          }
-          XF nv = xf_step(nb, xf_from_log2(rx[kStep * ii * RS]), v, xf_from_log2(rx[kStep * ii * RS + kYOff]));
-          // the single source cell: alpha(0, 0) = 1 on diagonal 0, beta(S_b, T_b) = 1 on diagonal nd
+          const float rot = __shfl_sync(0xffffffffu, v, src_lane);
+          const float bv = __shfl_sync(0xffffffffu, bvals, ii);
+          const float nb = (lane == edge_lane) ? bv : rot;
+          float nv = log2_add(nb + rx[kStep * ii * RS], v + rx[kStep * ii * RS + kYOff]);
+          // the single source cell: alpha(0, 0) = 0 on diagonal 0, beta(S_b, T_b) = 0 on diagonal nd
           if (!kBeta) {
-            if (d == 0 && g == 0 && lane == 0) nv = XF{1.f, 0};
+            if (d == 0 && g == 0 && lane == 0) nv = 0.f;
           } else if (d == nd && fin_mine && lane == fin_lane) {
-            nv = XF{1.f, 0};
+            nv = 0.f;
           }
           v = nv;
-          out[kStep * ii * ROWS] = xf_log2_rel(v, eref);
-          if (lane == send_lane) {
-            bp[kStep * ii] = v.f;
-            bpe[kStep * ii] = v.e;
-          }
-          if (!kBeta && d == nd && fin_mine) {  // log P(y|x) = log alpha(S_b, T_b)
-            const float ff = __shfl_sync(0xffffffffu, v.f, fin_lane);
-            const int fe = __shfl_sync(0xffffffffu, v.e, fin_lane);
+          out[kStep * ii * ROWS] = v;
+          if (lane == send_lane) bp[kStep * ii] = v;
+          if (!kBeta && d == nd && fin_mine) {  // log P(y|x) = alpha(S_b, T_b)
+            const float fin = __shfl_sync(0xffffffffu, v, fin_lane);
             if (lane == 0) {
-              const double lp = ff > 0.f ? (log2((double)ff) + (double)fe) * (double)kLn2 : -INFINITY;
+              const double lp = ((double)fin + off) * (double)kLn2;
               a.logp_d[b] = lp;
               a.logp[b] = (float)lp;
             }
           }
         }
+      }
+      const float m = warp_max(v);
+      if (m - m == 0.f) {
+        v -= m;
+        off += (double)m;
       }
     }
     __syncwarp();
@@ -283,8 +209,7 @@ __global__ void __launch_bounds__(32 * (G + kSimpleProducerWarps), 1) simple_lat
   sh.ringX = sm;
   sh.ringY = sh.ringX + G * W * RS;
   sh.bnd = sh.ringY + G * W * RS;
-  sh.bnd_e = reinterpret_cast<int*>(sh.bnd + (G + 1) * sh.bnd_stride);
-  sh.offs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sh.bnd_e + (G + 1) * sh.bnd_stride) + 7) & ~(uintptr_t)7);
+  sh.offs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sh.bnd + (G + 1) * sh.bnd_stride) + 7) & ~(uintptr_t)7);
   sh.full = reinterpret_cast<uint64_t*>(sh.offs + G * a.n_off);
   sh.empty = sh.full + G * kRing;
   sh.bfull = sh.empty + G * kRing;
@@ -309,10 +234,7 @@ __global__ void __launch_bounds__(32 * (G + kSimpleProducerWarps), 1) simple_lat
     mbar_init(&sh.empty[i], 1);
   }
   for (int i = threadIdx.x; i < G * nblk_max; i += blockDim.x) mbar_init(&sh.bfull[i], 1);
-  for (int i = threadIdx.x; i < (G + 1) * sh.bnd_stride; i += blockDim.x) {
-    sh.bnd[i] = 0.f;
-    sh.bnd_e[i] = kZeroE;
-  }
+  for (int i = threadIdx.x; i < (G + 1) * sh.bnd_stride; i += blockDim.x) sh.bnd[i] = kNegInf;
   for (int i = threadIdx.x; i < G * a.n_off; i += blockDim.x) sh.offs[i] = 0.0;
   tc::fence_mbar_init();
   __syncthreads();
@@ -544,34 +466,29 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
     BandStep nxt = *rp;  // frame 1 (or the terminator written for t = T_b)
     rp += R;             // rp always points one record past nxt (reads beyond the terminator are never used)
     float* ap = als + lane;
-    XF last{0.f, kZeroE};  // this lane's newest cell as f * 2^e (zero on the diagonals the lane sits out)
-    int eref = 0;
+    float last = kNegInf;
+    double off = 0.0;
     for (int p = 0; p < n_periods; ++p) {
-      // stored values are log2 relative to 2^eref: the largest exponent on the wavefront when the period starts
-      xf_normalise(last);
-      const int em = warp_max_int(last.e);
-      if (em > kZeroE) eref = em;
-      if (lane == 0) aoff[p] = (double)eref;
+      if (lane == 0) aoff[p] = off;
 #pragma unroll 4
       for (int ii = 0; ii < 16; ++ii) {
         const int d = 16 * p + ii;
-        XF up, left;
-        up.f = __shfl_up_sync(0xffffffffu, last.f, 1);
-        up.e = __shfl_up_sync(0xffffffffu, last.e, 1);
-        left.f = __shfl_sync(0xffffffffu, last.f, (lane + cur.w) & 31);
-        left.e = __shfl_sync(0xffffffffu, last.e, (lane + cur.w) & 31);
-        if (lane == 0) up = XF{0.f, kZeroE};  // shfl_up leaves lane 0 with its own value: slot 0 has no symbol move
-        if (cur.w & 256) left = XF{1.f, 0};
+        const float up_src = __shfl_up_sync(0xffffffffu, last, 1);
+        const float left_src = __shfl_sync(0xffffffffu, last, (lane + cur.w) & 31);
         const BandStep cand = *rp;  // branch-free: fetched every step, consumed only when the lane advances
         const bool on = cur.f == d;
-        XF val = xf_step(up, xf_from_log2(cur.x), left, xf_from_log2(cur.y));
-        if (!on) val = XF{0.f, kZeroE};
-        if (on) *ap = xf_log2_rel(val, eref);
+        const float val = on ? log2_add(up_src + cur.x, ((cur.w & 256) ? 0.f : left_src) + cur.y) : kNegInf;
+        if (on) *ap = val;
         ap += on ? R : 0;
         rp += on ? R : 0;
         cur.x = on ? nxt.x : cur.x; cur.y = on ? nxt.y : cur.y; cur.f = on ? nxt.f : cur.f; cur.w = on ? nxt.w : cur.w;
         nxt.x = on ? cand.x : nxt.x; nxt.y = on ? cand.y : nxt.y; nxt.f = on ? cand.f : nxt.f; nxt.w = on ? cand.w : nxt.w;
         last = val;
+      }
+      const float m = warp_max(last);  // cells older than this diagonal already sit in als[]
+      if (m - m == 0.f) {
+        last -= m;
+        off += (double)m;
       }
     }
   } else if (warp == 1 && Tb > 0) {
@@ -584,33 +501,29 @@ __global__ void __launch_bounds__(128, 1) band_lattice_kernel(BandArgs a) {
     BandStep nxt = *rp;  // frame T_b - 2, or the terminator stored as frame -1
     rp -= R;             // rp always points one record past nxt
     float* bp = bes + (Tb - 1) * R + lane;
-    XF last{0.f, kZeroE};
-    int eref = 0;
+    float last = kNegInf;
+    double off = 0.0;
     for (int p = n_periods - 1; p >= 0; --p) {
-      xf_normalise(last);
-      const int em = warp_max_int(last.e);
-      if (em > kZeroE) eref = em;
-      if (lane == 0) boff[p] = (double)eref;
+      if (lane == 0) boff[p] = off;
 #pragma unroll 4
       for (int ii = 15; ii >= 0; --ii) {
         const int d = 16 * p + ii;
-        XF down, right;
-        down.f = __shfl_down_sync(0xffffffffu, last.f, 1);
-        down.e = __shfl_down_sync(0xffffffffu, last.e, 1);
-        right.f = __shfl_sync(0xffffffffu, last.f, (lane - cur.w) & 31);
-        right.e = __shfl_sync(0xffffffffu, last.e, (lane - cur.w) & 31);
-        if (lane == 31) down = XF{0.f, kZeroE};
-        if (cur.w & 256) right = XF{1.f, 0};
+        const float down_src = __shfl_down_sync(0xffffffffu, last, 1);
+        const float right_src = __shfl_sync(0xffffffffu, last, (lane - cur.w) & 31);
         const BandStep cand = *rp;
         const bool on = cur.f == d;
-        XF val = xf_step(down, xf_from_log2(cur.x), right, xf_from_log2(cur.y));
-        if (!on) val = XF{0.f, kZeroE};
-        if (on) *bp = xf_log2_rel(val, eref);
+        const float val = on ? log2_add(down_src + cur.x, ((cur.w & 256) ? 0.f : right_src) + cur.y) : kNegInf;
+        if (on) *bp = val;
         bp -= on ? R : 0;
         rp -= on ? R : 0;
         cur.x = on ? nxt.x : cur.x; cur.y = on ? nxt.y : cur.y; cur.f = on ? nxt.f : cur.f; cur.w = on ? nxt.w : cur.w;
         nxt.x = on ? cand.x : nxt.x; nxt.y = on ? cand.y : nxt.y; nxt.f = on ? cand.f : nxt.f; nxt.w = on ? cand.w : nxt.w;
         last = val;
+      }
+      const float m = warp_max(last);
+      if (m - m == 0.f) {
+        last -= m;
+        off += (double)m;
       }
     }
   }
@@ -688,7 +601,7 @@ size_t simple_lattice_fast_workspace_bytes(int B, int S, int T) {
 
 static size_t simple_smem_bytes(int G, int diag_rows, int n_off) {
   const int ring = G <= 4 ? 3 : 2;
-  return (size_t)2 * G * 32 * ring * 33 * sizeof(float) + (size_t)2 * (G + 1) * (diag_rows + 2) * sizeof(float) + 8 +
+  return (size_t)2 * G * 32 * ring * 33 * sizeof(float) + (size_t)(G + 1) * (diag_rows + 2) * sizeof(float) + 8 +
          (size_t)G * n_off * sizeof(double) + (size_t)(2 * G * ring + G * (diag_rows / 32)) * 8 + 16;
 }
 
