@@ -199,6 +199,20 @@ int s2t_ctc_loss_bwd(const float* logits, const int64_t* targets, const int64_t*
                      const float* lse, const float* nll, const float* grad_nll, int zero_infinity, float* grad_logits,
                      void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Stateless predictor front end: embedding lookup + depthwise Conv1d over the token context.
+ * Replaces self._embedding + self._conv of /root/reference/model/predictor/stateless_predictor.py:90-97
+ * (StatelessPredictor.forward); the Linear that follows goes through s2t_linear_fwd/bwd.
+ *   emb (N,E) fp32 = _embedding.weight; conv_w (E,C) fp32 = _conv.weight viewed (E,1,C) -> (E,C);
+ *   ctx (B,L) int64 = [state | blank | tokens], L = U + C; h (B, L-C+1, E):
+ *   h[b,u,e] = sum_k conv_w[e,k] * emb[ctx[b,u+k], e].  Context sizes 1..8.
+ *   bwd: d_emb (N,E) and d_conv_w (E,C) are fully written.
+ * ------------------------------------------------------------------------- */
+int s2t_predictor_embed_conv_fwd(const float* emb, const float* conv_w, const int64_t* ctx, int B, int L, int C, int E,
+                                 int N, float* h, void* stream);
+int s2t_predictor_embed_conv_bwd(const float* emb, const float* conv_w, const int64_t* ctx, const float* d_h, int B,
+                                 int L, int C, int E, int N, float* d_emb, float* d_conv_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

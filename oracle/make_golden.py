@@ -124,8 +124,59 @@ def run_case(name, joiner_mod, pruned_mod, rnnt_mod, dtype=torch.float32, varian
     return res
 
 
+PREDICTOR_CASES = {
+    # zipformer_stateless_pruned_rnnt.yaml:74-80 shape (context 5) at a small size, and an odd one
+    "stateless_predictor": dict(num_symbols=128, output_dim=96, symbol_embedding_dim=64, context_size=5, B=4, U=23),
+    "stateless_predictor_ctx2": dict(num_symbols=37, output_dim=20, symbol_embedding_dim=18, context_size=2, B=3, U=9),
+}
+
+
+def make_predictor_case(name):
+    """Seeded weights (reference state_dict keys), tokens and an upstream gradient for a predictor case."""
+    cfg = PREDICTOR_CASES[name]
+    rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+    N, D, E, C = cfg["num_symbols"], cfg["output_dim"], cfg["symbol_embedding_dim"], cfg["context_size"]
+    w = {
+        "_embedding.weight": rs.standard_normal((N, E)).astype(np.float32),
+        "_conv.weight": (rs.uniform(-1, 1, (E, 1, C)) / np.sqrt(C)).astype(np.float32),
+        "_output_linear.weight": (rs.uniform(-1, 1, (D, E)) / np.sqrt(E)).astype(np.float32),
+        "_output_linear.bias": (rs.uniform(-1, 1, (D,)) / np.sqrt(E)).astype(np.float32),
+    }
+    tokens = rs.randint(1, N, (cfg["B"], cfg["U"])).astype(np.int64)
+    grad = rs.standard_normal((cfg["B"], cfg["U"] + 1, D)).astype(np.float32)
+    return cfg, w, tokens, grad
+
+
+def run_predictor_case(name):
+    """The reference's StatelessPredictor, verbatim, on a seeded case: output, out_state and all gradients."""
+    import importlib.util
+    sys.modules.setdefault("onnx", types.ModuleType("onnx"))
+    spec = importlib.util.spec_from_file_location("_reference_stateless_predictor",
+                                                  os.path.join(REFERENCE, "model/predictor/stateless_predictor.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg, w, tokens, grad = make_predictor_case(name)
+    pred = mod.StatelessPredictor(mod.StatelessPredictorConfig(
+        num_symbols=cfg["num_symbols"], output_dim=cfg["output_dim"],
+        symbol_embedding_dim=cfg["symbol_embedding_dim"], context_size=cfg["context_size"]))
+    pred.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    lengths = torch.full((cfg["B"],), cfg["U"], dtype=torch.int64)
+    out, out_len, out_state = pred(torch.from_numpy(tokens), lengths, pred.init_state())
+    (out * torch.from_numpy(grad)).sum().backward()
+    res = {"output": out.detach().numpy(), "out_state": out_state.numpy(), "lengths": out_len.numpy()}
+    for k, p in pred.named_parameters():
+        res["d" + k] = p.grad.numpy()
+    return res
+
+
 def main():
     from oracle.cases import CASES
+    os.makedirs(OUT, exist_ok=True)
+    for name in PREDICTOR_CASES:
+        res = run_predictor_case(name)
+        path = os.path.join(OUT, f"{name}.npz")
+        np.savez_compressed(path, **res)
+        print(f"{name}: output {res['output'].shape} -> {os.path.getsize(path) / 1024:.0f} KiB")
     joiner_mod, pruned_mod, rnnt_mod = _import_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, spec in CASES.items():

@@ -111,6 +111,20 @@ def ctc_loss(logits, targets, logits_length, targets_length, blank_label=0, redu
                       zero_infinity=zero_infinity)
 
 
+def stateless_predictor_forward(w: Dict[str, torch.Tensor], tokens, state, context_size: int):
+    """StatelessPredictor.forward, /root/reference/model/predictor/stateless_predictor.py:74-99: left-pad with
+    <blank> = 0, prepend the state, embedding -> depthwise Conv1d(kernel = context_size) -> Linear.
+    ``w`` uses the reference's state_dict keys.  Returns (output (B, 1 + U, D), out_state)."""
+    bs = tokens.shape[0]
+    state = state.repeat(bs, 1)
+    padded = F.pad(tokens.float(), (1, 0, 0, 0), value=0.0).to(torch.int32)
+    ctxed = torch.concat([state, padded], dim=1)
+    out_state = ctxed[:, ctxed.shape[1] - context_size:]
+    embs = F.embedding(ctxed, w["_embedding.weight"]).transpose(1, 2)
+    conv = F.conv1d(embs, w["_conv.weight"], groups=w["_conv.weight"].shape[0]).transpose(1, 2)
+    return F.linear(conv, w["_output_linear.weight"], w["_output_linear.bias"]), out_state
+
+
 def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None, ranges_override=None,
                        exact=False):
     """One fwd+bwd of the hot path exactly as rnnt_task.py:469-514 strings it

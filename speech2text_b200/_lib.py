@@ -52,6 +52,8 @@ _SIGNATURES = {
     "s2t_ctc_workspace_bytes": (c_size_t, [I, I, I, I]),
     "s2t_ctc_loss_fwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P]),
     "s2t_ctc_loss_bwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P, I, P, P]),
+    "s2t_predictor_embed_conv_fwd": (c_int, [P, P, P, I, I, I, I, I, P, P]),
+    "s2t_predictor_embed_conv_bwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P]),
     "s2t_joiner_materialize": (c_int, [I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P]),
 }
 

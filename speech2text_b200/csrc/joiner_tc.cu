@@ -979,11 +979,12 @@ constexpr int kFThreads = 32 * (kCtrlWarps + kEpiWarps + kProdWarps);
 // reads), one 64-entry vocabulary step per stage, brought in by bulk copies.  The producers then read them from
 // shared memory: what a tile pulls through the L2 -> SM path for its A operand drops from 512 KB to ~80 KB.
 constexpr int kRawStages = 2;
-constexpr int kRawAm = 32, kRawLm = 32;                 // staged rows per step (tiles that need more take the direct path)
+constexpr int kRawAm = 32, kRawLm = 24;                 // staged rows per step (tiles that need more take the direct path)
 constexpr int kRawRowBytes = kBlockK * 4;               // 64 fp32
-constexpr int kRawBytes = (kRawAm + kRawLm) * kRawRowBytes;  // 16 KB
+constexpr int kRawBytes = (kRawAm + kRawLm) * kRawRowBytes;  // 14 KB
 constexpr size_t kFSmemBytes = (size_t)kFS1 * kFStage1 + kFHBytes + (size_t)kFS2 * kBlockBytes + (size_t)kRawStages * kRawBytes +
-                               1024 /*align*/ + 512 /*barriers, tile plans*/;
+                               (256 + 2 * 128) * sizeof(float) /*b1, two vocabulary tiles of b2*/ + 1024 /*align*/ +
+                               512 /*barriers, tile plans*/;
 
 // what the planner warp tells the producers about a tile (double-buffered by tile parity)
 struct TilePlan {
@@ -1019,6 +1020,7 @@ struct FusedFwdParams {
   float delay_penalty;
 };
 
+template <int kAct>
 __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const FusedFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -1026,7 +1028,9 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
   uint8_t* H = ring1 + kFS1 * kFStage1;
   uint8_t* ring2 = H + kFHBytes;
   uint8_t* raw = ring2 + kFS2 * kBlockBytes;
-  uint64_t* full1 = reinterpret_cast<uint64_t*>(raw + kRawStages * kRawBytes);
+  float* sb1 = reinterpret_cast<float*>(raw + kRawStages * kRawBytes);  // b1, zero beyond I
+  float* sb2 = sb1 + 256;                                               // b2 of the vocabulary tile in flight, x 2
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(sb2 + 2 * 128);
   uint64_t* empty1 = full1 + kFS1;
   uint64_t* full2 = empty1 + kFS1;
   uint64_t* empty2 = full2 + kFS2;
@@ -1070,6 +1074,9 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  // the bias values live in shared memory: the epilogue reads 32 of them per accumulator chunk, and with 224 KB of
+  // shared memory in use the L1 that would otherwise serve those loads is a few KB
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sb1[i] = i < p.I ? __ldg(p.b1 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1180,48 +1187,79 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     }
   } else if (warp == 1) {
     // ---- MMA issue ----
+    // One thread serves both contractions.  Contraction 1 of tile i + 1 (fed by the producers) and contraction 2 of
+    // tile i (paced by the log-sum-exp epilogue) use different accumulators, stage rings and hand-over barriers, so
+    // they are interleaved: the thread polls both pipelines and issues whichever has a stage ready -- blocking on
+    // one would serialise "build the hidden rows" and "reduce the logits", each of which keeps other warps busy.
     if (lane == 0) {
       const uint32_t idesc1 = umma_idesc_bf16(128, 256), idesc2 = umma_idesc_bf16(128, 128);
-      uint32_t g1 = 0, g2 = 0, nt = 0, lt = 0;
-      for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
-        // contraction 1 -> TMEM columns 0..255 (drained by the epilogue of the previous tile)
-        mbar_wait(acc1_empty, (lt & 1) ^ 1);
-        tc_fence_after();
-        for (int ks = 0; ks < p.kbV; ++ks, ++g1) {
-          const int s = g1 % kFS1;
-          mbar_wait(&full1[s], (g1 / kFS1) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(ring1 + s * kFStage1), sb = sa + kBlockBytes;
-#pragma unroll
-          for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4)
-            umma_bf16(tmem_base, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc1,
-                      ks > 0 || k4 > 0);
-          umma_commit(&empty1[s]);
-        }
-        umma_commit(acc1_full);
-        // contraction 2: A = the hidden tile in shared memory
-        mbar_wait(h_full, lt & 1);
-        tc_fence_after();
-        const uint32_t sh = smem_u32(H);
-        for (int n = 0; n < p.nN; ++n, ++nt) {
-          const uint32_t buf = nt & 1;
-          mbar_wait(&acc2_empty[buf], ((nt >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t acc = tmem_base + 256 + buf * 128;
-          for (int kb = 0; kb < 4; ++kb, ++g2) {
+      const int n_mine = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const uint32_t sh = smem_u32(H);
+      uint32_t g1 = 0, g2 = 0, nt = 0;
+      int t1 = 0, k1 = 0;           // contraction 1: tile (in this CTA's sequence), vocabulary step
+      int t2 = 0, n2 = 0, kb2 = 0;  // contraction 2: tile, vocabulary tile, hidden k-block
+      bool acc1_ready = false, h_ready = false, acc2_ready = false;
+      uint32_t idle = 0;
+      while (t2 < n_mine) {
+        bool progressed = false;
+        if (t2 < t1) {  // the hidden rows of tile t2 are (being) produced: contraction 2
+          if (!h_ready) h_ready = mbar_test(h_full, t2 & 1);
+          if (h_ready) {
+            const uint32_t buf = nt & 1;
+            if (!acc2_ready) acc2_ready = mbar_test(&acc2_empty[buf], ((nt >> 1) & 1) ^ 1);
             const int s = g2 % kFS2;
-            mbar_wait(&full2[s], (g2 / kFS2) & 1);
+            if (acc2_ready && mbar_test(&full2[s], (g2 / kFS2) & 1)) {
+              tc_fence_after();
+              const uint32_t acc = tmem_base + 256 + buf * 128;
+              const uint32_t sa = sh + kb2 * kBlockBytes, sb = smem_u32(ring2 + s * kBlockBytes);
+#pragma unroll
+              for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4)
+                umma_bf16(acc, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc2,
+                          kb2 > 0 || k4 > 0);
+              umma_commit(&empty2[s]);
+              ++g2;
+              progressed = true;
+              if (++kb2 == 4) {
+                umma_commit(&acc2_full[buf]);
+                kb2 = 0;
+                ++nt;
+                acc2_ready = false;
+                if (++n2 == p.nN) {
+                  umma_commit(h_empty);  // every MMA that reads this tile's hidden rows has completed
+                  n2 = 0;
+                  ++t2;
+                  h_ready = false;
+                }
+              }
+            }
+          }
+        }
+        if (t1 < n_mine) {  // contraction 1 of tile t1 -> TMEM columns 0..255 (drained by the epilogue of tile t1 - 1)
+          if (!acc1_ready) acc1_ready = mbar_test(acc1_empty, (t1 & 1) ^ 1);
+          const int s = g1 % kFS1;
+          if (acc1_ready && mbar_test(&full1[s], (g1 / kFS1) & 1)) {
             tc_fence_after();
-            const uint32_t sa = sh + kb * kBlockBytes, sb = smem_u32(ring2 + s * kBlockBytes);
+            const uint32_t sa = smem_u32(ring1 + s * kFStage1), sb = sa + kBlockBytes;
 #pragma unroll
             for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4)
-              umma_bf16(acc, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc2,
-                        kb > 0 || k4 > 0);
-            umma_commit(&empty2[s]);
+              umma_bf16(tmem_base, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc1,
+                        k1 > 0 || k4 > 0);
+            umma_commit(&empty1[s]);
+            ++g1;
+            progressed = true;
+            if (++k1 == p.kbV) {
+              umma_commit(acc1_full);
+              k1 = 0;
+              ++t1;
+              acc1_ready = false;
+            }
           }
-          umma_commit(&acc2_full[buf]);
         }
-        umma_commit(h_empty);  // every MMA that reads this tile's hidden rows has completed
+        if (progressed) {
+          idle = 0;
+        } else if (++idle > (1u << 28)) {
+          __trap();  // a protocol bug must not hang the GPU
+        }
       }
     }
   } else if (warp >= kCtrlWarps && warp < kCtrlWarps + kEpiWarps) {
@@ -1244,12 +1282,13 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         tmem_ld_32x32(lane_addr + cc * 32, v);
         const int n = cc * 32;
         float x[32];
-        if (n + 32 <= p.I) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) x[q] = live ? v[q] + __ldg(p.b1 + n + q) : 0.f;
-        } else {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) x[q] = (live && n + q < p.I) ? v[q] + __ldg(p.b1 + n + q) : 0.f;
+        for (int q = 0; q < 32; q += 4) {  // columns beyond I hold exact zeros (zero rows of W1, zero bias)
+          const float4 bq = *reinterpret_cast<const float4*>(sb1 + n + q);
+          x[q] = live ? v[q] + bq.x : 0.f;
+          x[q + 1] = live ? v[q + 1] + bq.y : 0.f;
+          x[q + 2] = live ? v[q + 2] + bq.z : 0.f;
+          x[q + 3] = live ? v[q + 3] + bq.w : 0.f;
         }
         uint4 mine[4];
         pack_row32_bf16(x, mine);
@@ -1275,6 +1314,13 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
       const int csym = live ? __ldg(p.row_sym + m) : -1;
       for (int nn = 0; nn < p.nN; ++nn, ++nt) {
         const uint32_t buf = nt & 1;
+        // this vocabulary tile's 128 bias values (-inf beyond V: those columns drop out of max and sum)
+        float* b2s = sb2 + buf * 128;
+        {
+          const int col = nn * 128 + r;
+          b2s[r] = col < p.V ? __ldg(p.b2 + col) : kNegInf;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps; also orders the reuse two tiles on
         mbar_wait(&acc2_full[buf], (nt >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -1285,18 +1331,14 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
           if (!live || n >= p.V) continue;
           float x[32];
           float cm = kNegInf;
-          if (n + 32 <= p.V) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              x[q] = v[q] + __ldg(p.b2 + n + q);
-              cm = fmaxf(cm, x[q]);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              x[q] = (n + q < p.V) ? v[q] + __ldg(p.b2 + n + q) : kNegInf;
-              cm = fmaxf(cm, x[q]);
-            }
+          for (int q = 0; q < 32; q += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(b2s + cc * 32 + q);
+            x[q] = v[q] + bq.x;
+            x[q + 1] = v[q + 1] + bq.y;
+            x[q + 2] = v[q + 2] + bq.z;
+            x[q + 3] = v[q + 3] + bq.w;
+            cm = fmaxf(cm, fmaxf(fmaxf(x[q], x[q + 1]), fmaxf(x[q + 2], x[q + 3])));
           }
           if (cm > mx) {
             sum *= ex2_approx((mx - cm) * kLog2e);
@@ -1404,12 +1446,18 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
           const bool live = a_off[i] >= 0;
           const float4 a = *reinterpret_cast<const float4*>(rs + (live ? a_off[i] : 0));
           const float4 l = *reinterpret_cast<const float4*>(rs + (live ? l_off[i] : 0));
-          // dead rows and the vocabulary padding must come out as exact zeros (the stage may hold stale bits there)
-          const float x0 = (live && v + 0 < p.V) ? act_fwd_fast(a.x + l.x, p.act) : 0.f;
-          const float x1 = (live && v + 1 < p.V) ? act_fwd_fast(a.y + l.y, p.act) : 0.f;
-          const float x2 = (live && v + 2 < p.V) ? act_fwd_fast(a.z + l.z, p.act) : 0.f;
-          const float x3 = (live && v + 3 < p.V) ? act_fwd_fast(a.w + l.w, p.act) : 0.f;
-          o[i] = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+          // Dead rows and the vocabulary padding must come out as exact zeros (the stage may hold stale bits there):
+          // the INPUT is selected to 0 and act(0) = 0, so that the activation itself is straight-line code -- a
+          // conditional around it compiles to one divergence region per element, which exposes the latency of every
+          // single MUFU instead of pipelining the 32 of a step.
+          const float s0 = (live && v + 0 < p.V) ? a.x + l.x : 0.f;
+          const float s1 = (live && v + 1 < p.V) ? a.y + l.y : 0.f;
+          const float s2 = (live && v + 2 < p.V) ? a.z + l.z : 0.f;
+          const float s3 = (live && v + 3 < p.V) ? a.w + l.w : 0.f;
+          if (kAct == kRelu)
+            o[i] = make_uint2(pack_bf16x2(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), pack_bf16x2(fmaxf(s2, 0.f), fmaxf(s3, 0.f)));
+          else
+            o[i] = make_uint2(pack_bf16x2(tanh_fast(s0), tanh_fast(s1)), pack_bf16x2(tanh_fast(s2), tanh_fast(s3)));
         }
         // the raw stage is consumed (its values sit in registers): the planner may refill it
         __syncwarp();
@@ -1437,13 +1485,17 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
 }
 
 int launch_joiner_fwd_fused(const FusedFwdParams& p, cudaStream_t stream) {
-  static bool configured[kMaxDevices] = {};
-  if (int rc = configure_smem_once(joiner_fwd_fused_kernel, kFSmemBytes, configured, "tc_joiner_fwd_fused")) return rc;
+  static bool configured[2][kMaxDevices] = {};
+  const bool relu = p.act == kRelu;
+  if (int rc = relu ? configure_smem_once(joiner_fwd_fused_kernel<kRelu>, kFSmemBytes, configured[0], "tc_joiner_fwd_fused")
+                    : configure_smem_once(joiner_fwd_fused_kernel<kTanh>, kFSmemBytes, configured[1], "tc_joiner_fwd_fused"))
+    return rc;
   const int sms = device_info().sms;
   // upper bound of the live tiles (the exact count lives on the device): CTAs beyond it find no tile and leave
   const int grid = p.Mt < sms ? p.Mt : sms;
   ProfScope prof("tc_joiner_fwd_fused", stream);
-  joiner_fwd_fused_kernel<<<grid, kFThreads, kFSmemBytes, stream>>>(p);
+  if (relu) joiner_fwd_fused_kernel<kRelu><<<grid, kFThreads, kFSmemBytes, stream>>>(p);
+  else joiner_fwd_fused_kernel<kTanh><<<grid, kFThreads, kFSmemBytes, stream>>>(p);
   return check_launch("tc_joiner_fwd_fused");
 }
 

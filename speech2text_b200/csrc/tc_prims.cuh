@@ -77,6 +77,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Non-blocking probe of a phase parity (a role that serves two pipelines polls both instead of blocking on one).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // Wait on a barrier whose arrivals come from the peer CTA of a pair (same default semantics as the remote arrive
 // below: a cluster-scope release / acquire pair costs the forwarding thread most of a microsecond per stage).
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {

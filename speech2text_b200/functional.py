@@ -473,6 +473,47 @@ def ctc_loss(logits: Tensor, targets: Tensor, logits_length: Tensor, targets_len
 
 
 # ---------------------------------------------------------------------------
+# stateless predictor front end: embedding + depthwise conv      stateless_predictor.py:90-97
+# ---------------------------------------------------------------------------
+class _PredictorEmbedConv(torch.autograd.Function):
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, tokens: Tensor, emb: Tensor, conv_w: Tensor):
+        tokens = _i64c(tokens)
+        emb = _f32c(emb)
+        E = emb.shape[1]
+        C = conv_w.shape[-1]
+        w = _f32c(conv_w).reshape(E, C)
+        B, L = tokens.shape
+        N = emb.shape[0]
+        h = torch.empty((B, L - C + 1, E), dtype=torch.float32, device=emb.device)
+        check(lib().s2t_predictor_embed_conv_fwd(ptr(emb), ptr(w), ptr(tokens), B, L, C, E, N, ptr(h), stream()))
+        ctx.save_for_backward(tokens, emb, w)
+        ctx.w_shape = conv_w.shape
+        return h
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, d_h):
+        tokens, emb, w = ctx.saved_tensors
+        B, L = tokens.shape
+        N, E = emb.shape
+        C = w.shape[1]
+        d_emb = torch.empty_like(emb)
+        d_w = torch.empty_like(w)
+        check(lib().s2t_predictor_embed_conv_bwd(ptr(emb), ptr(w), ptr(tokens), ptr(_f32c(d_h)), B, L, C, E, N, ptr(d_emb),
+                                                 ptr(d_w), stream()))
+        return None, d_emb, d_w.reshape(ctx.w_shape)
+
+
+def predictor_embed_conv(tokens: Tensor, emb: Tensor, conv_w: Tensor) -> Tensor:
+    """``conv1d(embedding(tokens).transpose(1, 2), conv_w, groups=E).transpose(1, 2)`` for a depthwise ``conv_w`` of
+    shape (E, 1, C): (B, L) tokens -> (B, L - C + 1, E), as one fused kernel."""
+    return _PredictorEmbedConv.apply(tokens, emb, conv_w)
+
+
+# ---------------------------------------------------------------------------
 # nn.Linear on the tensor cores (joiner projections, bf16 mode)
 # ---------------------------------------------------------------------------
 class _LinearTC(torch.autograd.Function):
