@@ -213,6 +213,21 @@ int s2t_predictor_embed_conv_fwd(const float* emb, const float* conv_w, const in
 int s2t_predictor_embed_conv_bwd(const float* emb, const float* conv_w, const int64_t* ctx, const float* d_h, int B,
                                  int L, int C, int E, int N, float* d_emb, float* d_conv_w, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Batched greedy RNN-T decoding, device resident: one CTA per utterance walks its lattice.
+ * Replaces the Python loop of RnntGreedyDecoding.decode (/root/reference/model/decoding.py:225-271), i.e. the
+ * per-step calls of Joiner.streaming_step (model/joiner/joiner.py:184-207) and StatelessPredictor.streaming_step
+ * (model/predictor/stateless_predictor.py:107-124), for a whole batch (batch_search, decoding.py:32-48).
+ *   am (B,T,V) fp32 = enc_proj(encoder_out), computed by the caller; lengths (B) int64;
+ *   predictor: emb (N,E), conv_w (E,C), Wo (D,E), bo (D); joiner: Wp (V,D), bp (V) [_pre_proj] and the
+ *   out-projection W1 (I,V), b1, W2 (V,I), b2 (NULL / I = 0 when use_out_project = False).
+ *   A frame emits at most max_token_step + 1 tokens (decoding.py:252).  tokens (B,max_out) int64, n_tokens (B) int32.
+ * ------------------------------------------------------------------------- */
+int s2t_rnnt_greedy_decode(const float* am, const int64_t* lengths, const float* emb, const float* conv_w, const float* Wo,
+                           const float* bo, const float* Wp, const float* bp, const float* W1, const float* b1,
+                           const float* W2, const float* b2, int B, int T, int V, int N, int E, int C, int D, int I, int act,
+                           int blank, int max_token_step, int max_out, int64_t* tokens, int* n_tokens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

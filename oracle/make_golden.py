@@ -169,6 +169,88 @@ def run_predictor_case(name):
     return res
 
 
+GREEDY_CASES = {
+    # (predictor case, joiner config, T per utterance, blank bias): small models with a blank-leaning joiner bias so
+    # that the search emits a realistic mix of blanks and symbols
+    "greedy_outproj": dict(predictor="stateless_predictor", T=[40, 27, 33], blank_bias=12.0,
+                           joiner=dict(input_dim=96, output_dim=128, inner_dim=32, activation="tanh", prune_range=5)),
+    "greedy_plain": dict(predictor="stateless_predictor_ctx2", T=[25, 31], blank_bias=7.0,
+                         joiner=dict(input_dim=20, output_dim=37, activation="relu", prune_range=5, use_out_project=False)),
+}
+
+
+def make_greedy_case(name):
+    from oracle.cases import make_weights
+    g = GREEDY_CASES[name]
+    pcfg, pw, _, _ = make_predictor_case(g["predictor"])
+    rs = np.random.RandomState(sum(map(ord, name)))
+    jw = make_weights(g["joiner"], rs)
+    for k in jw:  # larger weights: peaked distributions, no near-ties between the two arithmetic orders
+        jw[k] = (jw[k] * 4.0).astype(np.float32)
+    last = "_out_projection.1.bias" if g["joiner"].get("use_out_project", True) else "_pre_proj.bias"
+    jw[last][0] += g["blank_bias"]
+    enc = [rs.standard_normal((1, t, g["joiner"]["input_dim"])).astype(np.float32) for t in g["T"]]
+    return g, pcfg, pw, jw, enc
+
+
+def run_greedy_case(name):
+    """The reference's RnntGreedyDecoding.decode (model/decoding.py:225-271), verbatim, with the reference's Joiner and
+    StatelessPredictor, on seeded weights and encoder outputs.  Its imports of the tokenizer / factory modules are
+    satisfied by stubs (they are type annotations there); the tokenizer stub returns the token ids."""
+    import importlib.util
+    from oracle import k2_shim
+    sys.modules["k2"] = k2_shim
+    for stub in ("onnx", "glog"):
+        sys.modules.setdefault(stub, types.ModuleType(stub))
+    sys.modules["glog"].info = lambda *a, **k: None
+    saved = {k: sys.modules.get(k) for k in ("dataset", "dataset.utils", "model.predictor.predictor", "model.joiner.joiner",
+                                             "torchaudio.models.decoder")}
+
+    def load(modname, rel):
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(REFERENCE, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    joiner_mod = load("_reference_joiner", "model/joiner/joiner.py")
+    pred_mod = load("_reference_stateless_predictor", "model/predictor/stateless_predictor.py")
+    ds, dsu = types.ModuleType("dataset"), types.ModuleType("dataset.utils")
+    dsu.Tokenizer = object
+    pp = types.ModuleType("model.predictor.predictor")
+    pp.Predictor = object
+    jj = types.ModuleType("model.joiner.joiner")
+    jj.Joiner = joiner_mod.Joiner
+    tad = types.ModuleType("torchaudio.models.decoder")  # the CTC lexicon decoder needs flashlight-text (not installed)
+    tad.ctc_decoder = None
+    sys.modules.update({"dataset": ds, "dataset.utils": dsu, "model.predictor.predictor": pp, "model.joiner.joiner": jj,
+                        "torchaudio.models.decoder": tad})
+    try:
+        dec_mod = load("_reference_decoding", "model/decoding.py")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    g, pcfg, pw, jw, enc = make_greedy_case(name)
+    pred = pred_mod.StatelessPredictor(pred_mod.StatelessPredictorConfig(
+        num_symbols=pcfg["num_symbols"], output_dim=pcfg["output_dim"],
+        symbol_embedding_dim=pcfg["symbol_embedding_dim"], context_size=pcfg["context_size"]))
+    pred.load_state_dict({k: torch.from_numpy(v) for k, v in pw.items()})
+    joiner = joiner_mod.Joiner(joiner_mod.JoinerConfig(**g["joiner"]))
+    joiner.load_state_dict({k: torch.from_numpy(v) for k, v in jw.items()})
+
+    class Tok:
+        def decode(self, t):
+            return [int(x) for x in t.tolist()]
+
+    session = dec_mod.RnntGreedyDecoding(Tok(), pred.eval(), joiner.eval())
+    res = {}
+    for i, e in enumerate(enc):
+        res[f"tokens_{i}"] = np.asarray(session.decode(torch.from_numpy(e)), dtype=np.int64)
+    return res
+
+
 def main():
     from oracle.cases import CASES
     os.makedirs(OUT, exist_ok=True)
@@ -177,6 +259,10 @@ def main():
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **res)
         print(f"{name}: output {res['output'].shape} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    for name in GREEDY_CASES:
+        res = run_greedy_case(name)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **res)
+        print(f"{name}: " + ", ".join(f"{k}: {len(v)} tokens" for k, v in res.items()))
     joiner_mod, pruned_mod, rnnt_mod = _import_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, spec in CASES.items():

@@ -125,6 +125,45 @@ def stateless_predictor_forward(w: Dict[str, torch.Tensor], tokens, state, conte
     return F.linear(conv, w["_output_linear.weight"], w["_output_linear.bias"]), out_state
 
 
+def rnnt_greedy_decode(pw: Dict[str, torch.Tensor], jw: Dict[str, torch.Tensor], jcfg: dict, hidden_states,
+                       context_size: int, max_token_step: int = 10):
+    """RnntGreedyDecoding.decode, /root/reference/model/decoding.py:225-271, for ONE utterance (1, T, D) with a
+    stateless predictor (streaming_step, stateless_predictor.py:107-124) and the joiner's streaming_step
+    (joiner.py:184-207).  ``pw`` / ``jw``: predictor / joiner weights under the reference's state_dict keys."""
+    act = _act(jcfg.get("activation", "relu"))
+
+    def pred_step(token, state):  # token (1,1), state (1, C-1)
+        ctxed = torch.concat([state, token], dim=1)
+        out_state = ctxed[:, ctxed.shape[1] - context_size + 1:]
+        embs = F.embedding(ctxed, pw["_embedding.weight"]).transpose(1, 2)
+        conv = F.conv1d(embs, pw["_conv.weight"], groups=pw["_conv.weight"].shape[0]).transpose(1, 2)
+        return F.linear(conv, pw["_output_linear.weight"], pw["_output_linear.bias"]), out_state
+
+    def joiner_step(enc, pred):  # (1,1,D), (1,1,D) -> (1, V) log-probs
+        a = F.linear(enc, jw["_enc_proj.weight"], jw["_enc_proj.bias"]).unsqueeze(2)
+        l = F.linear(pred, jw["_pre_proj.weight"], jw["_pre_proj.bias"]).unsqueeze(1)
+        h = act(a + l)
+        if jcfg.get("use_out_project", True):
+            h = F.linear(h, jw["_out_projection.0.weight"], jw["_out_projection.0.bias"])
+            h = F.linear(h, jw["_out_projection.1.weight"], jw["_out_projection.1.bias"])
+        return torch.log_softmax(h, dim=-1).squeeze(1).squeeze(1)
+
+    state = torch.zeros(1, context_size - 1, dtype=torch.int32)
+    token = torch.zeros(1, 1, dtype=torch.long)
+    pred_out, state = pred_step(token, state)
+    t, n_step, out = 0, 0, []
+    while t < hidden_states.shape[1]:
+        tok = joiner_step(hidden_states[:, t:t + 1, :], pred_out).argmax(dim=-1).unsqueeze(0)
+        if torch.allclose(tok, torch.zeros(1, 1).long()) or n_step > max_token_step:
+            t, n_step = t + 1, 0
+            continue
+        n_step += 1
+        token = tok
+        pred_out, state = pred_step(token, state)
+        out.append(tok.item())
+    return out
+
+
 def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None, ranges_override=None,
                        exact=False):
     """One fwd+bwd of the hot path exactly as rnnt_task.py:469-514 strings it

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "s2t_ctc_loss_bwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P, I, P, P]),
     "s2t_predictor_embed_conv_fwd": (c_int, [P, P, P, I, I, I, I, I, P, P]),
     "s2t_predictor_embed_conv_bwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P]),
+    "s2t_rnnt_greedy_decode": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, P, P]),
     "s2t_joiner_materialize": (c_int, [I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P]),
 }
 

@@ -149,3 +149,38 @@ def test_prune_range_invariants():
 def test_monotonic_lower_bound():
     x = torch.tensor([[3, 1, 4, 1, 5, 9, 2, 6]])
     assert k2.monotonic_lower_bound(x).tolist() == [[1, 1, 1, 1, 2, 2, 2, 6]]
+
+
+@pytest.mark.parametrize("name", ["stateless_predictor", "stateless_predictor_ctx2"])
+def test_predictor_port_matches_reference_goldens(name):
+    """oracle.reference_port.stateless_predictor_forward against the outputs of the reference's StatelessPredictor
+    run verbatim (oracle/make_golden.py::run_predictor_case)."""
+    from conftest import GOLDEN
+    import os
+    from oracle.make_golden import make_predictor_case
+    gold = dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+    cfg, w, tokens, grad = make_predictor_case(name)
+    wt = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in w.items()}
+    state = torch.zeros(1, cfg["context_size"] - 1, dtype=torch.int32)
+    out, out_state = port.stateless_predictor_forward(wt, torch.from_numpy(tokens), state, cfg["context_size"])
+    (out * torch.from_numpy(grad)).sum().backward()
+    np.testing.assert_allclose(out.detach().numpy(), gold["output"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(out_state.numpy(), gold["out_state"])
+    for k, v in wt.items():
+        np.testing.assert_allclose(v.grad.numpy(), gold["d" + k], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["greedy_outproj", "greedy_plain"])
+def test_greedy_decode_port_matches_reference_goldens(name):
+    """oracle.reference_port.rnnt_greedy_decode against the token sequences the reference's RnntGreedyDecoding
+    produced (verbatim run, oracle/make_golden.py::run_greedy_case)."""
+    import os
+    from conftest import GOLDEN
+    from oracle.make_golden import make_greedy_case
+    gold = dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+    g, pcfg, pw, jw, enc = make_greedy_case(name)
+    pw = {k: torch.from_numpy(v) for k, v in pw.items()}
+    jw = {k: torch.from_numpy(v) for k, v in jw.items()}
+    for i, e in enumerate(enc):
+        got = port.rnnt_greedy_decode(pw, jw, g["joiner"], torch.from_numpy(e), pcfg["context_size"])
+        assert got == gold[f"tokens_{i}"].tolist(), (name, i)
