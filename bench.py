@@ -690,7 +690,14 @@ def main():
             line["cpu_baseline"] = None
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graphs hold NCCL kernels; tearing the communicator down under them can block at exit.  Every
+        # rank has finished its work: meet once more, then leave without the teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define S2T_ABI_VERSION 1
+#define S2T_ABI_VERSION 2
 
 /* dtype codes for logits tensors */
 #define S2T_F32 0
@@ -82,12 +82,14 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
  * mode: S2T_MODE_FP32_SIMT = fp32 FMA contraction; S2T_MODE_BF16_TC = 3xTF32 tensor-core
  * normaliser (fp32-level accuracy) and bf16 tensor-core backward contractions.
  * workspace: s2t_simple_workspace_bytes(mode,B,T,S,V) bytes.
+ * row_max_ready != 0: am_max / lm_max already hold the row maxima of am / lm (by-products of s2t_linear_fwd);
+ * the row-max pass over am and lm is skipped (tensor-core mode).
  */
 size_t s2t_simple_workspace_bytes(int mode, int B, int T, int S, int V);
 int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
                         int B, int T, int S, int V, int blank, float lm_only_scale, float am_only_scale,
                         float* am_max, float* lm_max, float* px, float* py, float* nrm, void* alpha_ws,
-                        float* scores, float* px_grad, float* py_grad, void* workspace, void* stream);
+                        float* scores, float* px_grad, float* py_grad, void* workspace, int row_max_ready, void* stream);
 
 /* Backward of the above: grad_scores (B) = d loss / d scores[b].
  * workspace: THE buffer the forward call wrote (in S2T_MODE_BF16_TC it holds the bf16 exp(am - max) /
@@ -168,8 +170,10 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
  * terms are added while dy is packed instead of by a separate pass over (M,N).
  */
 size_t s2t_linear_workspace_bytes(int64_t M, int N, int K);
+/* row_max (M) or NULL: by-product max_n y[m, n] from the epilogue: what the simple-loss normaliser
+ * needs as am_max / lm_max, without a second pass over y (pass it on with row_max_ready = 1). */
 int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, int N, int K, void* workspace,
-                   float* y, void* stream);
+                   float* y, float* row_max, void* stream);
 int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M, int N, int K, void* workspace,
                    float* dx, float* dW, float* db, void* stream);
 

@@ -36,7 +36,7 @@ _SIGNATURES = {
     "s2t_lattice_workspace_bytes": (c_size_t, [I, I, I, I]),
     "s2t_mutual_information": (c_int, [P, P, P, I, I, I, P, P, P, P, P]),
     "s2t_simple_workspace_bytes": (c_size_t, [I, I, I, I, I]),
-    "s2t_simple_loss_fwd": (c_int, [I, P, P, P, P, I, I, I, I, I, F, F, P, P, P, P, P, P, P, P, P, P, P]),
+    "s2t_simple_loss_fwd": (c_int, [I, P, P, P, P, I, I, I, I, I, F, F, P, P, P, P, P, P, P, P, P, P, I, P]),
     "s2t_simple_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, F, P, P, P, P]),
     "s2t_prune_ranges": (c_int, [P, P, P, I, I, I, I, I, P, P]),
     "s2t_logits_loss_fwd": (c_int, [P, I, P, P, P, I, I, I, I, I, I, F, P, P, P, P, P, P, P, P]),
@@ -47,7 +47,7 @@ _SIGNATURES = {
     "s2t_joiner_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P,
                                     P, P, P, P, P]),
     "s2t_linear_workspace_bytes": (c_size_t, [ctypes.c_int64, I, I]),
-    "s2t_linear_fwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P]),
+    "s2t_linear_fwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P, P]),
     "s2t_linear_bwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P, P, P]),
     "s2t_ctc_workspace_bytes": (c_size_t, [I, I, I, I]),
     "s2t_ctc_loss_fwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P]),
@@ -82,7 +82,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.s2t_abi_version() != 1:
+        if handle.s2t_abi_version() != 2:
             raise S2TError("libs2t_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -39,7 +39,7 @@ int simple_backward(const float* am, const float* lm, const int64_t* sym, const 
 size_t simple_tc_workspace_bytes(int B, int T, int S, int V);
 int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
                        int S, int V, int blank, float* am_max, float* lm_max, float* px, float* py, float* nrm,
-                       void* ws, cudaStream_t stream);
+                       void* ws, bool row_max_ready, cudaStream_t stream);
 int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, const float* am_max,
                        const float* lm_max, const float* nrm, const float* occ_px, const float* occ_py,
                        const float* coef, int B, int T, int S, int V, int blank, void* ws, float* d_am, float* d_lm,
@@ -181,7 +181,7 @@ size_t s2t_simple_workspace_bytes(int mode, int B, int T, int S, int V) {
 int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
                         int B, int T, int S, int V, int blank, float lm_only_scale, float am_only_scale,
                         float* am_max, float* lm_max, float* px, float* py, float* nrm, void* alpha_ws,
-                        float* scores, float* px_grad, float* py_grad, void* workspace, void* stream) {
+                        float* scores, float* px_grad, float* py_grad, void* workspace, int row_max_ready, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(lm_only_scale >= 0.f && am_only_scale >= 0.f && lm_only_scale + am_only_scale < 1.f,
               "simple_loss: lm_only_scale/am_only_scale (%g, %g) must be >= 0 and sum to less than 1", lm_only_scale,
@@ -190,9 +190,10 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
   S2T_REQUIRE(blank >= 0 && blank < V, "simple_loss: blank %d out of range", blank);
   if (mode == S2T_MODE_BF16_TC) {
     if (int rc = simple_logprobs_tc(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm,
-                                    workspace, st))
+                                    workspace, row_max_ready != 0, st))
       return rc;
   } else {
+    // the fp32 path forms its own row maxima (it overwrites am_max / lm_max)
     if (int rc = simple_logprobs(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm, st))
       return rc;
   }

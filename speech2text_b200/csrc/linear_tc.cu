@@ -38,6 +38,11 @@ LinDims lin_dims(int64_t M, int N, int K) {
   return d;
 }
 
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 }  // namespace
 }  // namespace s2t
 
@@ -52,9 +57,10 @@ size_t s2t_linear_workspace_bytes(int64_t M, int N, int K) {
 }
 
 int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, int N, int K, void* ws, float* y,
-                   void* stream) {
+                   float* row_max, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
+  if (row_max) fill_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(row_max, M, kNegInf);
   LinDims d = lin_dims(M, N, K);
   uint8_t* px = (uint8_t*)ws;
   uint8_t* pw = px + d.px;
@@ -65,6 +71,7 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
   uint8_t* pw_small = pw + d.pw / 2;
   uint8_t* pwt = pw + d.pw + d.pdy;
   tc::StoreRowMajorEpi ep{y, N, (int)M, N, false, b};
+  ep.row_max = row_max;
   tc::MnDebug extra;
   extra.b_small = pw_small;
   if (f16) {

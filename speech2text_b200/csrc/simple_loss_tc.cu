@@ -47,6 +47,19 @@ __global__ void tc_row_max_kernel(const float* __restrict__ x, int64_t rows, int
   }
 }
 
+// With the row maxima already known (by-products of the projection epilogue): the per-symbol-position record the
+// normaliser epilogue needs, {max, lm[blank], lm[sym[b, s]]}, is three loads per row instead of a pass over the row.
+__global__ void tc_lm_info_kernel(const float* __restrict__ lm, const float* __restrict__ lm_max, int64_t rows, int V,
+                                  const int64_t* __restrict__ sym, int S, int blank, float4* __restrict__ info) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const float* p = lm + row * V;
+  const int64_t b = row / (S + 1);
+  const int s = (int)(row % (S + 1));
+  const float ls = (s < S) ? __ldg(p + (int)sym[b * S + s]) : 0.f;
+  info[row] = make_float4(lm_max[row], __ldg(p + blank), ls, 0.f);
+}
+
 // K-major 3xTF32 A: rows = frames t of batch b, 32 vocabulary entries per k-step, value exp(am - am_max).
 // Same thread mapping as RowCopyProducerF32: eight lanes read the 128 contiguous bytes of one row.
 struct ExpRowProducerF32 {
@@ -422,7 +435,7 @@ size_t simple_tc_workspace_bytes(int B, int T, int S, int V) {
 
 int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
                        int S, int V, int blank, float* am_max, float* lm_max, float* px, float* py, float* nrm,
-                       void* ws, cudaStream_t stream) {
+                       void* ws, bool row_max_ready, cudaStream_t stream) {
   SimpleTcDims d = simple_tc_dims(B, T, S, V);
   uint8_t* lm_big = (uint8_t*)ws;
   uint8_t* lm_small = lm_big + d.lm_f32;
@@ -430,7 +443,10 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   const int wpb = 8;
   const int64_t rows_am = (int64_t)B * T, rows_lm = (int64_t)B * (S + 1);
   // lm first: its hi/lo split (the B operand of the normaliser) then runs on a side stream next to the am row maxima
-  {
+  if (row_max_ready) {
+    ProfScope prof("lm_info_kernel", stream);
+    tc_lm_info_kernel<<<(unsigned)((rows_lm + 255) / 256), 256, 0, stream>>>(lm, lm_max, rows_lm, V, sym, S, blank, lm_info);
+  } else {
     ProfScope prof("row_max_kernel", stream);
     tc_row_max_kernel<<<(unsigned)((rows_lm + wpb - 1) / wpb), wpb * 32, 0, stream>>>(lm, rows_lm, V, lm_max, sym, S,
                                                                                       blank, lm_info);
@@ -449,6 +465,7 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   extra.b_small = lm_small;
   extra.b_batch_off = d.Spad / 128;
   auto row_max_am = [&]() {
+    if (row_max_ready) return;  // am_max came out of the projection epilogue
     ProfScope prof("row_max_kernel", stream);
     tc_row_max_kernel<<<(unsigned)((rows_am + wpb - 1) / wpb), wpb * 32, 0, stream>>>(am, rows_am, V, am_max, nullptr, S,
                                                                                       blank, nullptr);

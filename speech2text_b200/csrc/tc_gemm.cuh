@@ -761,6 +761,13 @@ __device__ __forceinline__ void pack_row32_bf16(const float (&x)[32], uint4 (&ou
                         pack_bf16x2(x[c * 8 + 4], x[c * 8 + 5]), pack_bf16x2(x[c * 8 + 6], x[c * 8 + 7]));
 }
 
+// max(*addr, v) for floats through the integer atomics (IEEE order: non-negative floats compare like ints, negative
+// ones like reversed unsigneds); *addr must start at -inf or any float
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 struct StoreRowMajorEpi {
   float* C;
   int64_t ldc;
@@ -768,12 +775,17 @@ struct StoreRowMajorEpi {
   bool atomic;
   const float* bias = nullptr;  // added per column when not atomic
   float scale = 1.f;            // applied to the accumulator first (undoes a power-of-two operand pre-scale)
+  // By-product: row_max[m] = max_n C[m, n], the stabiliser the simple-loss normaliser needs for every
+  // projected row -- formed from the values on their way to memory instead of by a second pass over C.  Must hold
+  // -inf on entry (column tiles meet through an atomic max).
+  float* row_max = nullptr;
   static constexpr int kScratchBytes = kTransposeScratchBytes;
   // The lane's bias values for the NEXT 32-column chunk (two 16-column halves x 4 columns) are fetched while the
   // current chunk is transposed: a bias load inside the store callback exposes one L2 round trip per pass, because
   // the producers' streaming loads leave nothing of the small L1 carve-out.
   struct State {
     float4 nb[2];
+    float rm[4];  // running maxima of the rows pass * 8 + lane % 8 this lane serves after the transpose
   };
   __device__ __forceinline__ void load_bias(float4 (&b)[2], int n, int lane) const {
     const bool vec = (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
@@ -792,8 +804,22 @@ struct StoreRowMajorEpi {
       }
     }
   }
-  __device__ void begin(State& st, const EpiCtx& ctx) const { load_bias(st.nb, ctx.col0, ctx.t & 31); }
-  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void begin(State& st, const EpiCtx& ctx) const {
+    load_bias(st.nb, ctx.col0, ctx.t & 31);
+    st.rm[0] = st.rm[1] = st.rm[2] = st.rm[3] = kNegInf;
+  }
+  __device__ void end(State& st, const EpiCtx& ctx) const {
+    if (row_max == nullptr) return;
+    const int lane = ctx.t & 31, m0 = ctx.m - lane;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      float v = st.rm[pass];  // the four lanes l, l+8, l+16, l+24 hold the four column groups of one row
+      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+      const int m = m0 + pass * 8 + (lane & 7);
+      if (lane < 8 && m < M && v > kNegInf) atomic_max_float(row_max + m, v);
+    }
+  }
   __device__ void chunk(State& st, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
     const int m0 = ctx.m - (ctx.t & 31);  // first row of this warp
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
@@ -804,6 +830,13 @@ struct StoreRowMajorEpi {
       if (m >= M || col >= N) return;
       const float4 b = cur[c >> 4];
       v.x = v.x * scale + b.x; v.y = v.y * scale + b.y; v.z = v.z * scale + b.z; v.w = v.w * scale + b.w;
+      if (row_max != nullptr) {
+        float mx = v.x;
+        if (col + 1 < N) mx = fmaxf(mx, v.y);
+        if (col + 2 < N) mx = fmaxf(mx, v.z);
+        if (col + 3 < N) mx = fmaxf(mx, v.w);
+        st.rm[r >> 3] = fmaxf(st.rm[r >> 3], mx);
+      }
       float* dst = C + (int64_t)m * ldc + col;
       if (vec_ok && col + 4 <= N) {
         if (atomic) atomicAdd(reinterpret_cast<float4*>(dst), v);

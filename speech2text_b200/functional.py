@@ -122,7 +122,7 @@ class _SimpleLoss(torch.autograd.Function):
     @staticmethod
     @_on_tensor_device
     def forward(ctx, am: Tensor, lm: Tensor, symbols: Tensor, boundary: Tensor, blank: int,
-                lm_only_scale: float, am_only_scale: float, mode: int):
+                lm_only_scale: float, am_only_scale: float, mode: int, row_max=None):
         am, lm = _f32c(am), _f32c(lm)
         symbols, boundary = _i64c(symbols), _i64c(boundary)
         B, T, V = am.shape
@@ -130,8 +130,11 @@ class _SimpleLoss(torch.autograd.Function):
         assert lm.shape == (B, S + 1, V) and symbols.shape == (B, S), (am.shape, lm.shape, symbols.shape)
         dev = am.device
         f32 = dict(dtype=torch.float32, device=dev)
-        am_max = torch.empty((B, T), **f32)
-        lm_max = torch.empty((B, S + 1), **f32)
+        # the row maxima may arrive with am / lm (by-products of the projection epilogue)
+        ready = (row_max is not None and mode == _lib.MODE_BF16_TC and row_max[0].shape == (B, T)
+                 and row_max[1].shape == (B, S + 1))
+        am_max = _f32c(row_max[0]) if ready else torch.empty((B, T), **f32)
+        lm_max = _f32c(row_max[1]) if ready else torch.empty((B, S + 1), **f32)
         px = torch.empty((B, S, T + 1), **f32)
         py = torch.empty((B, S + 1, T), **f32)
         nrm = torch.empty((B, S + 1, T), **f32)
@@ -143,7 +146,7 @@ class _SimpleLoss(torch.autograd.Function):
         check(lib().s2t_simple_loss_fwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(boundary), B, T, S, V, blank,
                                         float(lm_only_scale), float(am_only_scale), ptr(am_max), ptr(lm_max),
                                         ptr(px), ptr(py), ptr(nrm), ptr(alpha), ptr(scores), ptr(px_grad),
-                                        ptr(py_grad), ptr(ws), stream()))
+                                        ptr(py_grad), ptr(ws), 1 if ready else 0, stream()))
         ctx.early = None
         if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _early_simple_backward():
             cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
@@ -181,24 +184,24 @@ class _SimpleLoss(torch.autograd.Function):
             d_am.record_stream(cur)
             d_lm.record_stream(cur)
             if grad_scores is None:
-                return (None,) * 8
+                return (None,) * 9
             g = _f32c(grad_scores).view(B, 1, 1)
-            return d_am.mul_(g), d_lm.mul_(g), None, None, None, None, None, None
+            return d_am.mul_(g), d_lm.mul_(g), None, None, None, None, None, None, None
         if grad_scores is None:
-            return (None,) * 8
+            return (None,) * 9
         grad_scores = _f32c(grad_scores)
         d_am = torch.empty_like(am)
         d_lm = torch.empty_like(lm)
         check(lib().s2t_simple_loss_bwd(ctx.mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
                                         ptr(px_grad), ptr(py_grad), ptr(grad_scores), B, T, S, V, ctx.blank,
                                         ctx.scales[0], ctx.scales[1], ptr(ws), ptr(d_am), ptr(d_lm), stream()))
-        return d_am, d_lm, None, None, None, None, None, None
+        return d_am, d_lm, None, None, None, None, None, None, None
 
 
 def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                        lm_only_scale: float = 0.0, am_only_scale: float = 0.0,
                        boundary: Optional[Tensor] = None, reduction: str = "mean",
-                       return_grad: bool = False, mode: int = _lib.MODE_FP32_SIMT):
+                       return_grad: bool = False, mode: int = _lib.MODE_FP32_SIMT, row_max=None):
     """Drop-in for ``k2.rnnt_loss_smoothed`` (rnnt_type='regular').  ``mode`` picks the arithmetic of
     the normaliser contraction: fp32 FMA, or tensor cores (3xTF32 forward, bf16 backward)."""
     if boundary is None:
@@ -207,7 +210,7 @@ def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symb
         boundary[:, 2] = lm.shape[1] - 1
         boundary[:, 3] = T
     scores, px_grad, py_grad = _SimpleLoss.apply(am, lm, symbols, boundary, termination_symbol,
-                                                 lm_only_scale, am_only_scale, mode)
+                                                 lm_only_scale, am_only_scale, mode, row_max)
     loss = _reduce(scores, reduction)
     return (loss, (px_grad, py_grad)) if return_grad else loss
 
@@ -524,7 +527,7 @@ class _LinearTC(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, x: Tensor, W: Tensor, b: Tensor, sink_params=None):
+    def forward(ctx, x: Tensor, W: Tensor, b: Tensor, sink_params=None, want_row_max: bool = False):
         ctx.sink_params = sink_params  # (W, b) parameters when they may carry a bound gradient sink
         lead = x.shape[:-1]
         K = x.shape[-1]
@@ -533,21 +536,27 @@ class _LinearTC(torch.autograd.Function):
         M, N = x2.shape[0], W.shape[0]
         ws = torch.empty((lib().s2t_linear_workspace_bytes(M, N, K),), dtype=torch.uint8, device=x.device)
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        check(lib().s2t_linear_fwd(ptr(x2), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y), stream()))
+        # by-product of the epilogue: max over the output features of every row
+        row_max = torch.empty((M,), dtype=torch.float32, device=x.device) if want_row_max else None
+        check(lib().s2t_linear_fwd(ptr(x2), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y), ptr(row_max), stream()))
         ctx.save_for_backward(W, ws)
         ctx.dims = (M, N, K, lead, x.requires_grad, x.dtype)
         y = y.reshape(*lead, N)
+        if want_row_max:
+            row_max = row_max.reshape(*lead)
+            ctx.mark_non_differentiable(row_max)
+            return y, y.view_as(y), row_max
         return y, y.view_as(y)
 
     @staticmethod
     @_on_tensor_device
-    def backward(ctx, dy, dy_alias):
+    def backward(ctx, dy, dy_alias, _row_max_grad=None):
         W, ws = ctx.saved_tensors
         M, N, K, lead, need_dx, x_dtype = ctx.dims
         if dy is None:
             dy, dy_alias = dy_alias, None
         if dy is None:
-            return None, None, None, None
+            return None, None, None, None, None
         sinks = claim_grad_sinks(ctx.sink_params)
         sink_W, sink_b = sinks if sinks is not None else (None, None)
         dy2 = _f32c(dy).reshape(M, N)
@@ -560,7 +569,7 @@ class _LinearTC(torch.autograd.Function):
         if need_dx and x_dtype != torch.float32:
             dx = dx.to(x_dtype)  # bf16 activations in (BASELINE config 3's "bf16 joiner"): their gradient goes back as bf16
         return ((dx.reshape(*lead, K) if need_dx else None), None if sink_W is not None else dW,
-                None if sink_b is not None else db, None)
+                None if sink_b is not None else db, None, None)
 
 
 def grad_sink(p: Optional[Tensor]) -> Optional[Tensor]:
@@ -606,7 +615,8 @@ def linear_tc(x: Tensor, W: Tensor, b: Tensor) -> Tensor:
     return linear_tc_pair(x, W, b)[0]
 
 
-def linear_tc_pair(x: Tensor, W: Tensor, b: Tensor) -> Tuple[Tensor, Tensor]:
-    """Same, as two aliases of the result for two consumers (see _LinearTC)."""
+def linear_tc_pair(x: Tensor, W: Tensor, b: Tensor, row_max: bool = False):
+    """Same, as two aliases of the result for two consumers (see _LinearTC).  ``row_max=True`` appends the per-row
+    maximum of the result (a by-product of the epilogue) as a third output."""
     params = (W, b)
-    return _LinearTC.apply(x, W, b, params if all(grad_sink(p) is not None for p in params) else None)
+    return _LinearTC.apply(x, W, b, params if all(grad_sink(p) is not None for p in params) else None, row_max)

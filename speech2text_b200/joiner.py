@@ -155,7 +155,7 @@ class Joiner(nn.Module):
 
     @torch.jit.unused
     def _simple_loss_and_ranges(self, am: torch.Tensor, encoder_out_lengths: torch.Tensor, lm: torch.Tensor,
-                                target_lengths: torch.Tensor, target: torch.Tensor, mode: int = 0):
+                                target_lengths: torch.Tensor, target: torch.Tensor, mode: int = 0, row_max=None):
         """joiner.py:74-117 without the pruning gather: boundary, simple loss, ranges."""
         boundary = F2.make_boundary(target_lengths, encoder_out_lengths, am.device)
         assert len(target.shape) == 2  # (B, U)
@@ -174,6 +174,7 @@ class Joiner(nn.Module):
             reduction="mean",
             return_grad=True,
             mode=mode,
+            row_max=row_max,
         )
         ranges = F2.get_rnnt_prune_ranges(px_grad=px_grad, py_grad=py_grad, boundary=boundary,
                                           s_range=self.prune_range)
@@ -202,16 +203,20 @@ class Joiner(nn.Module):
         mode = _mode_from_env()
         if mode == _lib.MODE_BF16_TC and os.environ.get("S2T_B200_PROJ_TC", "1") != "0":
             # two aliases of each projection: one for the simple loss, one for the joiner (functional._LinearTC)
-            am, am_j = F2.linear_tc_pair(encoder_out, self._enc_proj.weight, self._enc_proj.bias)
-            lm, lm_j = F2.linear_tc_pair(predict_out, self._pre_proj.weight, self._pre_proj.bias)
+            # ... and, when the simple loss follows, the row maxima it needs as a by-product of the GEMM epilogue
+            want = self.prune_range > 0
+            am, am_j, *am_max = F2.linear_tc_pair(encoder_out, self._enc_proj.weight, self._enc_proj.bias, row_max=want)
+            lm, lm_j, *lm_max = F2.linear_tc_pair(predict_out, self._pre_proj.weight, self._pre_proj.bias, row_max=want)
+            row_max = (am_max[0], lm_max[0]) if want else None
         else:
             am = am_j = self._enc_proj(encoder_out)
             lm = lm_j = self._pre_proj(predict_out)
+            row_max = None
 
         if self.prune_range > 0:
             assert target.shape[0] == target_lengths.shape[0]
             boundary, ranges, simple_loss = self._simple_loss_and_ranges(am, encoder_out_lengths, lm,
-                                                                         target_lengths, target, mode)
+                                                                         target_lengths, target, mode, row_max)
         else:
             # For API consistency
             boundary = None
