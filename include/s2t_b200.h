@@ -172,10 +172,11 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
 size_t s2t_linear_workspace_bytes(int64_t M, int N, int K);
 /* row_max (M) or NULL: by-product max_n y[m, n] from the epilogue: what the simple-loss normaliser
  * needs as am_max / lm_max, without a second pass over y (pass it on with row_max_ready = 1). */
-int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, int N, int K, void* workspace,
+/* x_dtype / dx_dtype: S2T_F32 or S2T_BF16 -- bf16 activations are read (and their gradient written) as such. */
+int s2t_linear_fwd(const void* x, int x_dtype, const float* W, const float* b, int64_t M, int N, int K, void* workspace,
                    float* y, float* row_max, void* stream);
 int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M, int N, int K, void* workspace,
-                   float* dx, float* dW, float* db, void* stream);
+                   void* dx, int dx_dtype, float* dW, float* db, void* stream);
 
 /* Debug / materialised mode: write the logits (B,T,R,V) fp32 the fused path never stores. */
 int s2t_joiner_materialize(int mode, const float* am, const float* lm, const int64_t* ranges, const float* W1,

@@ -47,8 +47,8 @@ _SIGNATURES = {
     "s2t_joiner_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P,
                                     P, P, P, P, P]),
     "s2t_linear_workspace_bytes": (c_size_t, [ctypes.c_int64, I, I]),
-    "s2t_linear_fwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P, P]),
-    "s2t_linear_bwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, P, P, P]),
+    "s2t_linear_fwd": (c_int, [P, I, P, P, ctypes.c_int64, I, I, P, P, P, P]),
+    "s2t_linear_bwd": (c_int, [P, P, P, ctypes.c_int64, I, I, P, P, I, P, P, P]),
     "s2t_ctc_workspace_bytes": (c_size_t, [I, I, I, I]),
     "s2t_ctc_loss_fwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P]),
     "s2t_ctc_loss_bwd": (c_int, [P, P, P, P, I, I, I, I, I, P, P, P, P, I, P, P]),

@@ -11,6 +11,7 @@
 //             db = column sums of dy (a by-product of packing dy)
 // pack(x) is written once in the forward call and reused by the backward call (workspace).
 #include <stdlib.h>
+#include "../../include/s2t_b200.h"
 #include "tc_gemm.cuh"
 
 namespace s2t {
@@ -56,8 +57,9 @@ size_t s2t_linear_workspace_bytes(int64_t M, int N, int K) {
   return d.px + d.pw + d.pdy + d.pwt + 1024;
 }
 
-int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, int N, int K, void* ws, float* y,
+int s2t_linear_fwd(const void* x, int x_dtype, const float* W, const float* b, int64_t M, int N, int K, void* ws, float* y,
                    float* row_max, void* stream) {
+  S2T_REQUIRE(x_dtype == S2T_F32 || x_dtype == S2T_BF16, "linear_fwd: x must be fp32 or bf16 (dtype code %d)", x_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
   if (row_max) fill_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(row_max, M, kNegInf);
@@ -85,11 +87,17 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
         {W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, 0},
     };
     if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
-    tc::RowSplitProducerF16 a{x, K, M, K, px, d.Mt};
     ep.scale = 1.f / kWScale;
+    if (x_dtype == S2T_BF16) {
+      tc::RowSplitProducerF16T<__nv_bfloat16> a{(const __nv_bfloat16*)x, K, M, K, px, d.Mt};
+      return tc::launch_gemm_stream<256, 2, false, 3, kPair>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 63) / 64, 1, ep, st,
+                                                             "tc_linear_fwd_gemm_3xf16", extra);
+    }
+    tc::RowSplitProducerF16 a{(const float*)x, K, M, K, px, d.Mt};
     return tc::launch_gemm_stream<256, 2, false, 3, kPair>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 63) / 64, 1, ep, st,
                                                            "tc_linear_fwd_gemm_3xf16", extra);
   }
+  S2T_REQUIRE(x_dtype == S2T_F32, "linear_fwd: the 3xTF32 path (S2T_B200_LINEAR_TF32) takes fp32 activations");
   {
     const tc::PackJob jobs[3] = {
         {W, K, 1, N, K, d.Np / 128, d.Kp / 32, pw, 1},
@@ -98,14 +106,15 @@ int s2t_linear_fwd(const float* x, const float* W, const float* b, int64_t M, in
     };
     if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
   }
-  tc::RowCopyProducerF32 a{x, K, M, K, true, px, d.Mt};
+  tc::RowCopyProducerF32 a{(const float*)x, K, M, K, true, px, d.Mt};
   return tc::launch_gemm_stream<256, 2, false, 2, kPair>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 31) / 32, 1, ep, st,
                                                   "tc_linear_fwd_gemm_3xtf32", extra);
 }
 
 // dx (M,K), dW (N,K), db (N) are overwritten; the upstream gradient is dy (+ dy2 when not null)
-int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M, int N, int K, void* ws, float* dx,
-                   float* dW, float* db, void* stream) {
+int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M, int N, int K, void* ws, void* dx,
+                   int dx_dtype, float* dW, float* db, void* stream) {
+  S2T_REQUIRE(dx_dtype == S2T_F32 || dx_dtype == S2T_BF16, "linear_bwd: dx must be fp32 or bf16 (dtype code %d)", dx_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
   LinDims d = lin_dims(M, N, K);
@@ -119,10 +128,17 @@ int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M,
   cudaStream_t s_dw = dx ? fj.side(0) : st;
   if (dx) {
     tc::BulkA a{pdy, d.Mt};
-    tc::StoreRowMajorEpi ep{dx, K, (int)M, K, false, nullptr};
-    if (int rc = tc::launch_gemm_stream<256, 4, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
-                                                       "tc_linear_dx_gemm"))
-      return rc;
+    if (dx_dtype == S2T_BF16) {
+      tc::StoreRowMajorBf16Epi ep{(__nv_bfloat16*)dx, K, (int)M, K};
+      if (int rc = tc::launch_gemm_stream<256, 4, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
+                                                         "tc_linear_dx_gemm"))
+        return rc;
+    } else {
+      tc::StoreRowMajorEpi ep{(float*)dx, K, (int)M, K, false, nullptr};
+      if (int rc = tc::launch_gemm_stream<256, 4, false, 0>(a, pwt, d.Kp / 128, d.Mt, d.Kp / 256, (N + 63) / 64, 1, ep, st,
+                                                         "tc_linear_dx_gemm"))
+        return rc;
+    }
   }
   {
     cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s_dw);

@@ -992,9 +992,12 @@ struct RowCopyProducerF32 {
 // On-the-fly K-major A for the 3xF16 contraction: 128 rows x 64 fp32 of a row-major matrix -> hi | lo half blocks of
 // the stage.  Sixteen lanes cover the 256 bytes one row contributes to a k-step; thread (warp w, lane l) serves rows
 // 2w + l/16 + 16 i, i = 0..7.  Optional by-product: the bf16 packed image of x (same block geometry).
-struct RowSplitProducerF16 {
+// TX = float or __nv_bfloat16 (BASELINE config 3's "bf16 joiner": the activations arrive as bf16 and are read as such --
+// half the bytes, and the packed bf16 image kept for the weight gradient is then exact).
+template <typename TX>
+struct RowSplitProducerF16T {
   static constexpr bool kBulk = false;
-  const float* x;
+  const TX* x;
   int64_t ld;
   int64_t M;
   int K;
@@ -1013,13 +1016,19 @@ struct RowSplitProducerF16 {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int64_t m = (int64_t)pc.m_tile * 128 + rbase + 16 * j;
-        const float* row = x + m * ld;
+        const TX* row = x + m * ld;
         if (m < M && vec && k + 4 <= K) {
-          dst[j] = __ldg(reinterpret_cast<const float4*>(row + k));
+          if constexpr (sizeof(TX) == 4) {
+            dst[j] = __ldg(reinterpret_cast<const float4*>(row + k));
+          } else {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + k));  // four bf16
+            dst[j] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                                 __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+          }
         } else {
           float v[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = (m < M && k + e < K) ? __ldg(row + k + e) : 0.f;
+          for (int e = 0; e < 4; ++e) v[e] = (m < M && k + e < K) ? to_float<TX>(row[k + e]) : 0.f;
           dst[j] = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
@@ -1056,6 +1065,37 @@ struct RowSplitProducerF16 {
         pc.arrive_full(it + 1);
       }
     }
+  }
+};
+
+using RowSplitProducerF16 = RowSplitProducerF16T<float>;
+
+// C[m * ldc + n] = bf16(acc): plain row-major bf16 result (the gradient of bf16 activations), transposed through shared
+// memory like StoreRowMajorEpi so that a warp store covers whole sectors
+struct StoreRowMajorBf16Epi {
+  __nv_bfloat16* C;
+  int64_t ldc;
+  int M, N;
+  static constexpr int kScratchBytes = kTransposeScratchBytes;
+  struct State {};
+  __device__ void begin(State&, const EpiCtx&) const {}
+  __device__ void end(State&, const EpiCtx&) const {}
+  __device__ void chunk(State&, const EpiCtx& ctx, int n, const float (&acc)[32]) const {
+    const int m0 = ctx.m - (ctx.t & 31);
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 7) == 0);
+    warp_transposed_chunk(ctx, acc, N - n, [&](int r, int c, float4 v) {
+      const int m = m0 + r, col = n + c;
+      if (m >= M || col >= N) return;
+      __nv_bfloat16* dst = C + (int64_t)m * ldc + col;
+      if (vec_ok && col + 4 <= N) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < N) dst[j] = __float2bfloat16(e[j]);
+      }
+    });
   }
 };
 

@@ -531,14 +531,16 @@ class _LinearTC(torch.autograd.Function):
         ctx.sink_params = sink_params  # (W, b) parameters when they may carry a bound gradient sink
         lead = x.shape[:-1]
         K = x.shape[-1]
-        x2 = _f32c(x).reshape(-1, K)
+        # fp32 or bf16 activations are read as they are (anything else goes through fp32)
+        x2 = (x if x.dtype in (torch.float32, torch.bfloat16) else x.float()).contiguous().reshape(-1, K)
         W, b = _f32c(W), _f32c(b)
         M, N = x2.shape[0], W.shape[0]
         ws = torch.empty((lib().s2t_linear_workspace_bytes(M, N, K),), dtype=torch.uint8, device=x.device)
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         # by-product of the epilogue: max over the output features of every row
         row_max = torch.empty((M,), dtype=torch.float32, device=x.device) if want_row_max else None
-        check(lib().s2t_linear_fwd(ptr(x2), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y), ptr(row_max), stream()))
+        check(lib().s2t_linear_fwd(ptr(x2), _lib.dtype_code(x2.dtype), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y),
+                                   ptr(row_max), stream()))
         ctx.save_for_backward(W, ws)
         ctx.dims = (M, N, K, lead, x.requires_grad, x.dtype)
         y = y.reshape(*lead, N)
@@ -561,13 +563,15 @@ class _LinearTC(torch.autograd.Function):
         sink_W, sink_b = sinks if sinks is not None else (None, None)
         dy2 = _f32c(dy).reshape(M, N)
         dy3 = _f32c(dy_alias).reshape(M, N) if dy_alias is not None else None
-        dx = torch.empty((M, K), dtype=torch.float32, device=dy.device) if need_dx else None
+        dx_dtype = x_dtype if x_dtype == torch.bfloat16 else torch.float32  # bf16 activations: bf16 gradient, written as such
+        dx = torch.empty((M, K), dtype=dx_dtype, device=dy.device) if need_dx else None
         # a bound gradient buffer (FlatGradBucket.bind) is written in place and autograd gets no gradient to add
         dW = sink_W if sink_W is not None else torch.empty_like(W)
         db = sink_b if sink_b is not None else torch.empty((N,), dtype=torch.float32, device=dy.device)
-        check(lib().s2t_linear_bwd(ptr(dy2), ptr(dy3), ptr(W), M, N, K, ptr(ws), ptr(dx), ptr(dW), ptr(db), stream()))
-        if need_dx and x_dtype != torch.float32:
-            dx = dx.to(x_dtype)  # bf16 activations in (BASELINE config 3's "bf16 joiner"): their gradient goes back as bf16
+        check(lib().s2t_linear_bwd(ptr(dy2), ptr(dy3), ptr(W), M, N, K, ptr(ws), ptr(dx), _lib.dtype_code(dx_dtype), ptr(dW),
+                                   ptr(db), stream()))
+        if need_dx and x_dtype != dx_dtype:
+            dx = dx.to(x_dtype)
         return ((dx.reshape(*lead, K) if need_dx else None), None if sink_W is not None else dW,
                 None if sink_b is not None else db, None, None)
 

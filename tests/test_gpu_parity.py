@@ -961,3 +961,30 @@ def test_padding_tiles_are_skipped_without_changing_results(monkeypatch):
     # padding frames receive exactly zero gradient
     for b in range(B):
         assert float(skip[2][b, int(t_len[b]):].abs().max()) == 0.0 if int(t_len[b]) < T else True
+
+
+def test_linear_tc_reads_bf16_activations_natively():
+    """bf16 activations (BASELINE config 3's "bf16 joiner") go through the projection as they are: the forward must
+    equal the fp32 path on the same (bf16-representable) values bit for bit, the row-max by-product must be the max of
+    the stored result, and the gradient comes back as bf16 (the fp32 gradient rounded once)."""
+    from speech2text_b200 import functional as F2
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    for M, K, N in ((300, 96, 70), (1000, 512, 500)):
+        x = (torch.randn(2, M // 2, K, generator=g) * 0.5).bfloat16().to(dev)
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+        b = torch.randn(N, generator=g).to(dev)
+        dy = torch.randn(2, M // 2, N, generator=g).to(dev)
+        xb = x.clone().requires_grad_(True)
+        xf = x.float().requires_grad_(True)
+        yb, _, rm = F2.linear_tc_pair(xb, W, b, row_max=True)
+        yf = F2.linear_tc(xf, W, b)
+        assert torch.equal(yb, yf)
+        assert torch.equal(rm, yb.max(dim=-1).values)
+        ref = torch.nn.functional.linear(x.double(), W.double(), b.double())
+        assert rel_err(yb, ref) < 1e-5
+        (yb * dy).sum().backward()
+        (yf * dy).sum().backward()
+        torch.cuda.synchronize()
+        assert xb.grad.dtype == torch.bfloat16 and xf.grad.dtype == torch.float32
+        assert torch.equal(xb.grad, xf.grad.bfloat16())
