@@ -44,6 +44,7 @@
 // per epilogue group (EpiCtx::scratch); epi_sync(ctx) is a barrier over the 128 threads of a group.
 #pragma once
 #include <cstdio>
+#include <type_traits>
 #include <cstring>
 
 #include "common.cuh"
@@ -1003,43 +1004,50 @@ struct RowSplitProducerF16T {
   int K;
   uint8_t* bf16_pack = nullptr;
   int pack_row_blocks = 0;
+  // four consecutive elements as loaded: the conversion to fp32 happens when the step is emitted, NOT at the load --
+  // a conversion next to the load would make the warp wait for the data before the barrier wait and the stores of the
+  // step in front, i.e. take the loads out of flight
+  using Raw = typename std::conditional<sizeof(TX) == 4, float4, uint2>::type;
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[4]) {
+    if constexpr (sizeof(TX) == 4) {
+      v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    } else {
+      v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+      v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+  }
   __device__ void run(const ProdCtx& pc) const {
     const int warp = pc.t >> 5, lane = pc.t & 31;
     const int c = lane & 15, rbase = warp * 2 + (lane >> 4);
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const bool emit = bf16_pack != nullptr && pc.n_tile == 0 && pc.valid;
     const int off = rbase * 128 + ((((c >> 1) ^ (rbase & 7)) & 7) << 4) + (c & 1) * 8;
-    // Two whole k-steps of raw fp32 (2 x 8 float4 per lane, 64 KB per CTA) are kept in flight: with one k-step
-    // every iteration costs a full DRAM round trip, Little's law then caps the CTA at ~32 KB per microsecond.
-    auto load = [&](float4 (&dst)[8], int ks) {
+    // Two whole k-steps of raw rows (2 x 8 pieces per lane) are kept in flight: with one k-step every iteration costs a
+    // full DRAM round trip, Little's law then caps the CTA at ~32 KB per microsecond.
+    auto load = [&](Raw (&dst)[8], int ks) {
       const int k = ks * 64 + c * 4;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int64_t m = (int64_t)pc.m_tile * 128 + rbase + 16 * j;
         const TX* row = x + m * ld;
         if (m < M && vec && k + 4 <= K) {
-          if constexpr (sizeof(TX) == 4) {
-            dst[j] = __ldg(reinterpret_cast<const float4*>(row + k));
-          } else {
-            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + k));  // four bf16
-            dst[j] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
-                                 __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
-          }
+          dst[j] = __ldg(reinterpret_cast<const Raw*>(row + k));
         } else {
-          float v[4];
+          TX v[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = (m < M && k + e < K) ? to_float<TX>(row[k + e]) : 0.f;
-          dst[j] = make_float4(v[0], v[1], v[2], v[3]);
+          for (int e = 0; e < 4; ++e) v[e] = (m < M && k + e < K) ? row[k + e] : from_float<TX>(0.f);
+          dst[j] = *reinterpret_cast<const Raw*>(v);
         }
       }
     };
-    auto emit_step = [&](const float4 (&src)[8], int it) {
+    auto emit_step = [&](const Raw (&src)[8], int it) {
       uint8_t* dst = pc.stage(it) + off;
       const int ks = pc.ks0 + it;
       uint8_t* blk = emit ? bf16_pack + packed_block_index(pc.m_tile, ks, pack_row_blocks) * kBlockBytes + off : nullptr;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float v[4] = {src[j].x, src[j].y, src[j].z, src[j].w};
+        float v[4];
+        unpack(src[j], v);
         uint2 hi, lo;
         split_f16x4(v, hi, lo);
         const int ro = j * 16 * 128;
@@ -1048,7 +1056,7 @@ struct RowSplitProducerF16T {
         if (emit) *reinterpret_cast<uint2*>(blk + ro) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
       }
     };
-    float4 qa[8], qb[8];
+    Raw qa[8], qb[8];
     load(qa, pc.ks0);
     for (int it = 0; it < pc.n_it; it += 2) {
       if (it + 1 < pc.n_it) load(qb, pc.ks0 + it + 1);
