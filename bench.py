@@ -166,6 +166,9 @@ def kernel_work(cfg, live_frames: float = 1.0):
         "simple_d_am_gemm": (simple, 4.0 * (B * S1 * T + B * S1 * V + B * T * V)),
         "simple_d_lm_gemm": (simple, 4.0 * (B * S1 * T + B * S1 * V + B * T * V)),
         # bf16 tensor-core mode (tcgen05): every joiner contraction is 2*M*V*I
+        # fused forward (both contractions in one kernel, the hidden tile never leaves the SM on its way to GEMM2):
+        # am and lm rows read once (fp32), hidden rows written once in bf16 for the backward, lse / px / py out
+        "tc_joiner_fwd_fused": (2.0 * gemm, 4.0 * (B * T * V * live_frames + B * S1 * V) + 2.0 * M * Ii + 12.0 * M),
         "tc_joiner_hidden_gemm": (gemm, 2.0 * M * V + 2.0 * M * Ii),            # act(am+lm) rows in, hidden rows out
         "tc_joiner_logits_lse_gemm": (gemm, 2.0 * M * Ii + 12.0 * M),            # hidden in, lse / px / py out
         "tc_joiner_grad_logits_gemm": (gemm, 2.0 * M * Ii + 2.0 * M * V),        # hidden in, d logits (bf16) out
