@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define S2T_ABI_VERSION 2
+#define S2T_ABI_VERSION 3
 
 /* dtype codes for logits tensors */
 #define S2T_F32 0
@@ -151,6 +151,27 @@ int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_
                         int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
                         void* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream);
 
+/* The two halves of s2t_joiner_loss_fwd as separate calls (same arguments, same results): the joiner's log-probs
+ * lse / px / py (k2.get_rnnt_logprobs_pruned's role in k2.rnnt_loss_pruned) and the band lattice over them
+ * (k2.mutual_information_recursion's role).  The lattice keeps one CTA per utterance busy and leaves the other SMs
+ * idle, so a caller with independent work at hand -- the gradient contractions of the simple loss, which only need the
+ * occupation probabilities of ITS lattice -- issues that work on a second stream between the two calls. */
+int s2t_joiner_logprobs_fwd(int mode, const float* am, const float* lm, const int64_t* symbols,
+                            const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
+                            const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
+                            int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
+                            void* stream);
+int s2t_band_lattice_fwd(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary, int B,
+                         int S, int T, int R, void* alpha_ws, float* scores, float* occ_px, float* occ_py,
+                         void* stream);
+
+/* x0[g, 0..n0) and x1[g, 0..n1) (either may be NULL) are multiplied by num[g] / den[g] for every group g whose two
+ * values differ -- groups with num == den cost no memory traffic -- and den[g] becomes (num[g] != 0 ? num[g] : 1).
+ * Used for gradients that were computed ahead of the backward pass with a predicted upstream scale `den`
+ * (the scale of the previous step): the backward pass corrects them with the actual scale `num`. */
+int s2t_rescale_groups(float* x0, int64_t n0, float* x1, int64_t n1, int groups, const float* num, float* den,
+                       void* stream);
+
 /* d_am (B,T,V), d_lm (B,S+1,V), dW1, db1, dW2, db2 are overwritten. */
 int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols,
                         const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
@@ -162,7 +183,7 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
 /* ---------------------------------------------------------------------------
  * nn.Linear for the joiner's projections in bf16 tensor-core mode
  *   reference: self._enc_proj / self._pre_proj, model/joiner/joiner.py:41-42, 148-149.
- * x (M,K), W (N,K), b (N) fp32 -> y (M,N) fp32 = x W^T + b: 3xTF32 forward (fp32-level accuracy), bf16 operands in
+ * x (M,K), W (N,K), b (N) fp32 -> y (M,N) fp32 = x W^T + b: 3xF16 forward (fp32-level accuracy), bf16 operands in
  * the backward contractions, fp32 accumulation.
  * workspace: s2t_linear_workspace_bytes(M,N,K) bytes, the same buffer for fwd and bwd
  * (it carries the packed bf16 x and W^T).  bwd overwrites dx (may be NULL), dW, db.  The upstream gradient is

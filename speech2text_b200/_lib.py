@@ -44,6 +44,9 @@ _SIGNATURES = {
     "s2t_joiner_workspace_bytes": (c_size_t, [I, I, I, I, I, I]),
     "s2t_joiner_loss_fwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P,
                                     P, P]),
+    "s2t_joiner_logprobs_fwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P]),
+    "s2t_band_lattice_fwd": (c_int, [P, P, P, P, I, I, I, I, P, P, P, P, P]),
+    "s2t_rescale_groups": (c_int, [P, ctypes.c_int64, P, ctypes.c_int64, I, P, P, P]),
     "s2t_joiner_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P,
                                     P, P, P, P, P]),
     "s2t_linear_workspace_bytes": (c_size_t, [ctypes.c_int64, I, I]),
@@ -82,7 +85,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.s2t_abi_version() != 2:
+        if handle.s2t_abi_version() != 3:
             raise S2TError("libs2t_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -145,6 +145,36 @@ static JoinerProblem make_problem(const float* am, const float* lm, const int64_
 
 }  // namespace s2t
 
+namespace s2t {
+namespace {
+
+// x[g, :] *= num[g] / den[g] where the two differ; a block whose group needs no correction leaves after two loads
+__global__ void __launch_bounds__(256) rescale_groups_kernel(float* __restrict__ x0, int64_t n0, float* __restrict__ x1,
+                                                             int64_t n1, const float* __restrict__ num,
+                                                             const float* __restrict__ den) {
+  const int g = blockIdx.y;
+  const float a = num[g], b = den[g];
+  if (a == b) return;
+  const float r = a / b;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (x0) {
+    float* p = x0 + (int64_t)g * n0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += stride) p[i] *= r;
+  }
+  if (x1) {
+    float* p = x1 + (int64_t)g * n1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) p[i] *= r;
+  }
+}
+
+__global__ void rescale_update_kernel(const float* __restrict__ num, float* __restrict__ den, int groups) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < groups) den[g] = num[g] != 0.f ? num[g] : 1.f;
+}
+
+}  // namespace
+}  // namespace s2t
+
 using namespace s2t;
 
 extern "C" {
@@ -279,23 +309,54 @@ size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {
   return joiner_simt_workspace_bytes((int64_t)B * T * R, V, I, nullptr);
 }
 
-int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols,
-                        const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
-                        const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
-                        int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
-                        void* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream) {
+int s2t_rescale_groups(float* x0, int64_t n0, float* x1, int64_t n1, int groups, const float* num, float* den,
+                       void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  S2T_REQUIRE(groups > 0 && groups <= 65535 && num && den, "rescale_groups: bad arguments (groups=%d)", groups);
+  {
+    ProfScope prof("rescale_groups_kernel", st);
+    const int64_t n = n0 > n1 ? n0 : n1;
+    int bx = (int)((n + 256 * 8 - 1) / (256 * 8));
+    const int cap = device_info().sms * 8 / groups + 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    rescale_groups_kernel<<<dim3((unsigned)bx, (unsigned)groups), 256, 0, st>>>(x0, n0, x1, n1, num, den);
+    rescale_update_kernel<<<(groups + 255) / 256, 256, 0, st>>>(num, den, groups);
+  }
+  return check_launch("rescale_groups_kernel");
+}
+
+int s2t_joiner_logprobs_fwd(int mode, const float* am, const float* lm, const int64_t* symbols,
+                            const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
+                            const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
+                            int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
+                            void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT || mode == S2T_MODE_BF16_TC, "joiner_loss_fwd: unknown mode %d", mode);
   S2T_REQUIRE(ranges != nullptr || R == S + 1, "joiner_loss: unpruned joiner needs R == S+1 (R=%d, S=%d)", R, S);
   S2T_REQUIRE(I == 0 || (W1 && b1 && W2 && b2), "joiner_loss: out-projection weights missing");
   JoinerProblem p = make_problem(am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
                                  delay_penalty);
-  if (joiner_uses_tc(mode, I)) {
-    if (int rc = joiner_tc_forward(p, workspace, lse, px, py, st)) return rc;
-  } else {
-    if (int rc = joiner_simt_forward(p, workspace, lse, px, py, st)) return rc;
-  }
-  return band_dp(px, py, ranges, boundary, B, S, T, R, alpha_ws, scores, occ_px, occ_py, st);
+  if (joiner_uses_tc(mode, I)) return joiner_tc_forward(p, workspace, lse, px, py, st);
+  return joiner_simt_forward(p, workspace, lse, px, py, st);
+}
+
+int s2t_band_lattice_fwd(const float* px, const float* py, const int64_t* ranges, const int64_t* boundary, int B,
+                         int S, int T, int R, void* alpha_ws, float* scores, float* occ_px, float* occ_py,
+                         void* stream) {
+  S2T_REQUIRE(ranges != nullptr || R == S + 1, "band_lattice: unpruned lattice needs R == S+1 (R=%d, S=%d)", R, S);
+  return band_dp(px, py, ranges, boundary, B, S, T, R, alpha_ws, scores, occ_px, occ_py, (cudaStream_t)stream);
+}
+
+int s2t_joiner_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols,
+                        const int64_t* ranges, const int64_t* boundary, const float* W1, const float* b1,
+                        const float* W2, const float* b2, int B, int T, int S, int R, int V, int I, int act,
+                        int blank, float delay_penalty, void* workspace, float* lse, float* px, float* py,
+                        void* alpha_ws, float* scores, float* occ_px, float* occ_py, void* stream) {
+  if (int rc = s2t_joiner_logprobs_fwd(mode, am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
+                                       delay_penalty, workspace, lse, px, py, stream))
+    return rc;
+  return s2t_band_lattice_fwd(px, py, ranges, boundary, B, S, T, R, alpha_ws, scores, occ_px, occ_py, stream);
 }
 
 int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols,

@@ -569,7 +569,7 @@ struct GradEpi {
     store_packed_row32(ctx, Gp, g_row_blocks, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
-    if (n + lane < V && cs != 0.f) atomicAdd(db2 + n + lane, cs);
+    if (n + lane < V && cs != 0.f && !(ctx.dbg & 32)) atomicAdd(db2 + n + lane, cs);
   }
 };
 
@@ -595,7 +595,7 @@ struct DHiddenEpi {
     store_packed_row32(ctx, DHp, dh_row_blocks, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
-    if (n + lane < I && cs != 0.f) atomicAdd(db1 + n + lane, cs);
+    if (n + lane < I && cs != 0.f && !(ctx.dbg & 32)) atomicAdd(db1 + n + lane, cs);
   }
 };
 
@@ -1046,9 +1046,6 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
   TilePlan* plans = reinterpret_cast<TilePlan*>(tmem_slot + 4);  // [2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool listed = p.live_idx != nullptr;
-  const int n_tiles = listed ? p.live_prefix[p.Mt] : p.Mt;
-  auto tile_of = [&](int j) { return listed ? p.live_idx[j] : j; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFS1; ++s) {
@@ -1074,6 +1071,13 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  // programmatic dependent launch: barrier init and the TMEM allocation overlap the tail of the previous kernel; no
+  // global memory is read before it has completed
+  griddep_wait();
+  griddep_launch_dependents();
+  const bool listed = p.live_idx != nullptr;
+  const int n_tiles = listed ? p.live_prefix[p.Mt] : p.Mt;
+  auto tile_of = [&](int j) { return listed ? p.live_idx[j] : j; };
   // the bias values live in shared memory: the epilogue reads 32 of them per accumulator chunk, and with 224 KB of
   // shared memory in use the L1 that would otherwise serve those loads is a few KB
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sb1[i] = i < p.I ? __ldg(p.b1 + i) : 0.f;
@@ -1494,8 +1498,12 @@ int launch_joiner_fwd_fused(const FusedFwdParams& p, cudaStream_t stream) {
   // upper bound of the live tiles (the exact count lives on the device): CTAs beyond it find no tile and leave
   const int grid = p.Mt < sms ? p.Mt : sms;
   ProfScope prof("tc_joiner_fwd_fused", stream);
-  if (relu) joiner_fwd_fused_kernel<kRelu><<<grid, kFThreads, kFSmemBytes, stream>>>(p);
-  else joiner_fwd_fused_kernel<kTanh><<<grid, kFThreads, kFSmemBytes, stream>>>(p);
+  const cudaError_t e = relu ? tc::launch_pdl(joiner_fwd_fused_kernel<kRelu>, (unsigned)grid, kFThreads, kFSmemBytes, stream, 1, p)
+                             : tc::launch_pdl(joiner_fwd_fused_kernel<kTanh>, (unsigned)grid, kFThreads, kFSmemBytes, stream, 1, p);
+  if (e != cudaSuccess) {
+    set_error("tc_joiner_fwd_fused: launch: %s", cudaGetErrorString(e));
+    return 2;
+  }
   return check_launch("tc_joiner_fwd_fused");
 }
 
@@ -1613,7 +1621,12 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
-      if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
+      static const int bs128 = getenv("S2T_B200_BS128") ? atoi(getenv("S2T_B200_BS128")) : 0;
+      if (bs128 & 1) {
+        if (int rc = launch_gemm_bstationary<128, 7, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.Vp / 128, d.kbI, ep, stream,
+                                                                "tc_joiner_grad_logits_gemm", live))
+          return rc;
+      } else if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
                                                                        "tc_joiner_grad_logits_gemm", live))
         return rc;
     }
@@ -1659,7 +1672,12 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       StoreRowsBf16Epi ep{w.dh, d.Vp};
-      if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
+      static const int bs128 = getenv("S2T_B200_BS128") ? atoi(getenv("S2T_B200_BS128")) : 0;
+      if (bs128 & 2) {
+        if (int rc = launch_gemm_bstationary<128, 7, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.Vp / 128, d.kbI, ep, stream,
+                                                                "tc_joiner_dh_gemm", live))
+          return rc;
+      } else if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
                                                                        "tc_joiner_dh_gemm", live))
         return rc;
       const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;

@@ -43,6 +43,7 @@
 // Epi::kScratchBytes of shared memory are reserved for CTA-level reductions of the epilogue
 // per epilogue group (EpiCtx::scratch); epi_sync(ctx) is a barrier over the 128 threads of a group.
 #pragma once
+#include <utility>
 #include <cstdio>
 #include <type_traits>
 #include <cstring>
@@ -272,6 +273,33 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   static_assert(kCluster == 1 || !kMn, "CTA pairs are built for K-major operands");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + kProdWarps);
+      mbar_init(&empty[s], 1);
+      mbar_init(&pfull[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      // one CTA: every epilogue thread arrives; pair: one lane per epilogue warp of both CTAs, on the leader's barrier
+      mbar_init(&tempty[i], kCluster == 1 ? 32 * kEpiWarps * kGroups : kCluster * kEpiWarps * kGroups);
+    }
+    mbar_init(bres_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    if constexpr (kCluster == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    else tmem_alloc_pair<kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel of the stream; nothing
+  // below (the live-tile list included) is read before that kernel has completed
+  griddep_wait();
+  griddep_launch_dependents();
   // streaming: tiles of all (n, m, split, batch), n fastest; B-stationary: the CTA's own column tile, row tiles strided
   const int first_tile = kBRes > 0 ? (int)blockIdx.x / n_tiles : (int)blockIdx.x / kCluster;
   const int tile_stride = kBRes > 0 ? (int)gridDim.x / n_tiles : (int)gridDim.x / kCluster;
@@ -313,29 +341,6 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
     return c;
   };
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], ASrc::kBulk ? 1 : 1 + kProdWarps);
-      mbar_init(&empty[s], 1);
-      mbar_init(&pfull[s], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      // one CTA: every epilogue thread arrives; pair: one lane per epilogue warp of both CTAs, on the leader's barrier
-      mbar_init(&tempty[i], kCluster == 1 ? 32 * kEpiWarps * kGroups : kCluster * kEpiWarps * kGroups);
-    }
-    mbar_init(bres_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    if constexpr (kCluster == 1) tmem_alloc<kTmemCols>(tmem_slot);
-    else tmem_alloc_pair<kTmemCols>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if constexpr (kCluster > 1) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ---------------- bulk-copy issuer ----------------
@@ -598,6 +603,75 @@ inline int configure_smem_once(Kern kern, size_t smem, bool (&done)[kMaxDevices]
   return 0;
 }
 
+// S2T_TRACE=<kernel label>: the third and fourth launch of that kernel record CTA 0's role timeline, printed to stderr
+// when the launch has finished (developer aid; synchronises the stream).
+struct TraceScope {
+  unsigned long long* buf = nullptr;
+  cudaStream_t st;
+  const char* what;
+  TraceScope(const char* what_, cudaStream_t stream, MnDebug& mn) : st(stream), what(what_) {
+    static unsigned long long* trace_buf = nullptr;
+    static int trace_left = 2;
+    static int trace_seen = 0;  // the first launches of a process are cold
+    const char* trace_env = getenv("S2T_TRACE");
+    const bool tracing = trace_env && strstr(what, trace_env) && trace_seen++ >= 2 && trace_left > 0;
+    if (!tracing) return;
+    if (!trace_buf) cudaMalloc(&trace_buf, (kTraceCap + 1) * sizeof(unsigned long long));
+    cudaMemsetAsync(trace_buf, 0, (kTraceCap + 1) * sizeof(unsigned long long), stream);
+    mn.trace = trace_buf;
+    buf = trace_buf;
+    --trace_left;
+  }
+  ~TraceScope() {
+    if (!buf) return;
+    cudaStreamSynchronize(st);
+    static unsigned long long host[kTraceCap + 1];
+    cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
+    const unsigned long long n = host[0] < (unsigned long long)kTraceCap ? host[0] : kTraceCap;
+    unsigned long long t0 = ~0ull;
+    for (unsigned long long i = 0; i < n; ++i) if ((host[1 + i] >> 16) < t0) t0 = host[1 + i] >> 16;
+    fprintf(stderr, "S2T_TRACE %s events=%llu\n", what, n);
+    for (unsigned long long i = 0; i < n; ++i)
+      fprintf(stderr, "T %llu %d %d\n", (host[1 + i] >> 16) - t0, (int)((host[1 + i] >> 12) & 15), (int)(host[1 + i] & 0xfff));
+  }
+};
+
+// Launch with the programmatic-dependent-launch attribute (and the cluster shape, if any): the kernel may become resident
+// while its predecessor in the stream drains; it calls griddep_wait() before it touches global memory.
+// S2T_B200_NO_PDL=1 launches plainly (A/B switch; the device-side calls are no-ops then).
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("S2T_B200_NO_PDL") ? 0 : 1;
+  return on == 1;
+}
+
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, int cluster,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 template <int BN, int kStages, bool kMn, int kKind, int kCluster = 1, class ASrc, class Epi>
 int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_blocks, int m_tiles, int n_tiles,
                        int k_steps, int k_splits, const Epi& epi, cudaStream_t stream, const char* what,
@@ -618,53 +692,13 @@ int launch_gemm_stream(const ASrc& asrc, const uint8_t* b_packed, int b_row_bloc
     if (dbg < 0) dbg = getenv("S2T_DBG") ? atoi(getenv("S2T_DBG")) : 0;
     mn.dbg = dbg;
   }
-  static unsigned long long* trace_buf = nullptr;
-  static int trace_left = 2;  // launches to trace
-  const char* trace_env = getenv("S2T_TRACE");
-  static int trace_seen = 0;  // the first launches of a process are cold: trace the third and fourth
-  const bool tracing = trace_env && strstr(what, trace_env) && trace_seen++ >= 2 && trace_left > 0;
-  if (tracing) {
-    if (!trace_buf) cudaMalloc(&trace_buf, (kTraceCap + 1) * sizeof(unsigned long long));
-    cudaMemsetAsync(trace_buf, 0, (kTraceCap + 1) * sizeof(unsigned long long), stream);
-    mn.trace = trace_buf;
-  }
-  struct TraceDump {
-    unsigned long long* buf; cudaStream_t st; const char* what; int* left;
-    ~TraceDump() {
-      if (!buf) return;
-      cudaStreamSynchronize(st);
-      static unsigned long long host[kTraceCap + 1];
-      cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
-      const unsigned long long n = host[0] < (unsigned long long)kTraceCap ? host[0] : kTraceCap;
-      unsigned long long t0 = ~0ull;
-      for (unsigned long long i = 0; i < n; ++i) if ((host[1 + i] >> 16) < t0) t0 = host[1 + i] >> 16;
-      fprintf(stderr, "S2T_TRACE %s events=%llu\n", what, n);
-      for (unsigned long long i = 0; i < n; ++i)
-        fprintf(stderr, "T %llu %d %d\n", (host[1 + i] >> 16) - t0, (int)((host[1 + i] >> 12) & 15), (int)(host[1 + i] & 0xfff));
-      --*left;
-    }
-  } trace_dump{tracing ? trace_buf : nullptr, stream, what, &trace_left};
+  TraceScope trace_scope(what, stream, mn);
   ProfScope prof(what, stream);
-  if constexpr (kCluster == 1) {
-    kern<<<grid, gemm_threads<ASrc, Epi>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps,
-                                                            k_splits, epi, mn);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)gemm_threads<ASrc, Epi>());
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, asrc, b_packed, b_row_blocks, m_tiles, n_tiles, batches, k_steps, k_splits,
-                                       epi, mn);
+  {
+    cudaError_t e = launch_pdl(kern, (unsigned)grid, (unsigned)gemm_threads<ASrc, Epi>(), smem, stream, kCluster, asrc, b_packed,
+                               b_row_blocks, m_tiles, n_tiles, batches, k_steps, k_splits, epi, mn);
     if (e != cudaSuccess) {
-      set_error("%s: cluster launch: %s", what, cudaGetErrorString(e));
+      set_error("%s: launch: %s", what, cudaGetErrorString(e));
       return 2;
     }
   }
@@ -698,8 +732,16 @@ int launch_gemm_bstationary(const ASrc& asrc, const uint8_t* b_packed, int b_row
     if (dbg < 0) dbg = getenv("S2T_DBG") ? atoi(getenv("S2T_DBG")) : 0;
     mn.dbg = dbg;
   }
+  TraceScope trace_scope(what, stream, mn);
   ProfScope prof(what, stream);
-  kern<<<grid, gemm_threads<ASrc, Epi>(), smem, stream>>>(asrc, b_packed, b_row_blocks, m_tiles, n_tiles, 1, k_steps, 1, epi, mn);
+  {
+    cudaError_t e = launch_pdl(kern, (unsigned)grid, (unsigned)gemm_threads<ASrc, Epi>(), smem, stream, 1, asrc, b_packed,
+                               b_row_blocks, m_tiles, n_tiles, 1, k_steps, 1, epi, mn);
+    if (e != cudaSuccess) {
+      set_error("%s: launch: %s", what, cudaGetErrorString(e));
+      return 2;
+    }
+  }
   return check_launch(what);
 }
 

@@ -77,6 +77,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream is still draining.  Everything before griddep_wait() (shared-memory
+// carve-up, barrier init, TMEM allocation) overlaps the predecessor's tail; griddep_wait() returns once the predecessor
+// grid has completed and its writes are visible.  griddep_launch_dependents() lets the NEXT kernel's CTAs be scheduled as
+// soon as every CTA of this grid has issued it (called after the own wait, so "my successor runs" implies "my
+// predecessor is complete").  Both are no-ops in a kernel that was launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Non-blocking probe of a phase parity (a role that serves two pipelines polls both instead of blocking on one).
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;

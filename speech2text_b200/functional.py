@@ -108,16 +108,69 @@ def _ones(n: int, device) -> Tensor:
     return t
 
 
-def _early_simple_backward() -> bool:
-    return os.environ.get("S2T_B200_EARLY_SIMPLE_BWD", "0") != "0" and not _lib.profiling()
+def _early_simple_backward(mode: int) -> bool:
+    """S2T_B200_EARLY_SIMPLE_BWD: "0" off, "1" on; default: on in tensor-core mode.  Off while the library's
+    per-launch event timer runs (side-stream launches would be timed against the wrong neighbours)."""
+    v = os.environ.get("S2T_B200_EARLY_SIMPLE_BWD")
+    on = (mode == _lib.MODE_BF16_TC) if v is None else v != "0"
+    return on and not _lib.profiling()
+
+
+_PENDING = []  # at most one _EarlySimpleBackward per device, waiting for its slot next to the band lattice
+_PRED = {}     # (device, B) -> upstream scale of the simple loss's scores seen by the previous backward pass (never 0)
+
+
+def _predicted_scale(B: int, device) -> Tensor:
+    key = (device, B)
+    t = _PRED.get(key)
+    if t is None:
+        t = _PRED[key] = torch.ones((B,), dtype=torch.float32, device=device)
+    return t
+
+
+class _EarlySimpleBackward:
+    """The gradient of the simple loss needs nothing that the backward pass brings besides one scale per utterance:
+    the occupation probabilities exist at the end of its forward call (k2 computes them there too, for the prune
+    ranges).  Its contractions are therefore issued ahead of time on a side stream, in the one place of the step
+    where most of the GPU idles -- next to the joiner's band lattice, which keeps one CTA per utterance busy --
+    with the scale the previous step's backward pass saw; backward waits for them and corrects the scale where it
+    differs (`s2t_rescale_groups`: no memory traffic for utterances whose scale was predicted right)."""
+
+    def __init__(self, mode, tensors, dims, blank, scales):
+        self.mode, self.tensors, self.dims, self.blank, self.scales = mode, tensors, dims, blank, scales
+        am, lm = tensors[0], tensors[1]
+        self.d_am, self.d_lm = torch.empty_like(am), torch.empty_like(lm)
+        self.pred = _predicted_scale(dims[0], am.device)
+        self.side = None
+
+    def launch(self):
+        am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws = self.tensors
+        B, T, S, V = self.dims
+        dev = am.device
+        cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            check(lib().s2t_simple_loss_bwd(self.mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max),
+                                            ptr(nrm), ptr(px_grad), ptr(py_grad), ptr(self.pred), B, T, S, V,
+                                            self.blank, self.scales[0], self.scales[1], ptr(ws), ptr(self.d_am),
+                                            ptr(self.d_lm), stream()))
+        for t in self.tensors + (self.d_am, self.d_lm, self.pred):
+            t.record_stream(side)
+        self.side = side
+        self.tensors = None
+
+
+def _launch_pending(device) -> None:
+    """Called where a latency-bound kernel is about to own the GPU (between the joiner's log-prob kernels and its
+    band lattice)."""
+    for e in [e for e in _PENDING if e.d_am.device == device]:
+        _PENDING.remove(e)
+        e.launch()
 
 
 class _SimpleLoss(torch.autograd.Function):
-    """The occupation probabilities -- all the gradient of the simple loss needs besides a per-utterance scale --
-    exist at the end of the forward call (k2 computes them there too, for the prune ranges).  The gradient
-    contractions therefore start right away on a side stream, with unit scale, next to what the caller does
-    between this call and its backward pass (prune ranges, joiner forward, band lattice: the lattice kernels keep
-    one CTA per utterance busy and leave the other SMs idle); backward only waits for them and applies the scale."""
+    """k2.rnnt_loss_smoothed(return_grad=True); the backward contractions may run ahead of time
+    (_EarlySimpleBackward)."""
 
     @staticmethod
     @_on_tensor_device
@@ -148,18 +201,11 @@ class _SimpleLoss(torch.autograd.Function):
                                         ptr(px), ptr(py), ptr(nrm), ptr(alpha), ptr(scores), ptr(px_grad),
                                         ptr(py_grad), ptr(ws), 1 if ready else 0, stream()))
         ctx.early = None
-        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _early_simple_backward():
-            cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                d_am, d_lm = torch.empty_like(am), torch.empty_like(lm)
-                check(lib().s2t_simple_loss_bwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
-                                                ptr(px_grad), ptr(py_grad), ptr(_ones(B, dev)), B, T, S, V, blank,
-                                                float(lm_only_scale), float(am_only_scale), ptr(ws), ptr(d_am),
-                                                ptr(d_lm), stream()))
-            for t in (am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws):
-                t.record_stream(side)
-            ctx.early = (d_am, d_lm, side)
+        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _early_simple_backward(mode):
+            _PENDING[:] = [e for e in _PENDING if e.d_am.device != dev]  # an older one falls back to the plain path
+            ctx.early = _EarlySimpleBackward(mode, (am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws),
+                                             (B, T, S, V), blank, (float(lm_only_scale), float(am_only_scale)))
+            _PENDING.append(ctx.early)
         # the workspace travels to backward: in tensor-core mode it holds the bf16 exp(am - max) / exp(lm - max)
         # operands the forward pass produced on the side
         ctx.save_for_backward(am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws)
@@ -176,17 +222,17 @@ class _SimpleLoss(torch.autograd.Function):
         am, lm, symbols, am_max, lm_max, nrm, px_grad, py_grad, ws = ctx.saved_tensors
         B, T, V = am.shape
         S = lm.shape[1] - 1
-        if ctx.early is not None:
-            d_am, d_lm, side = ctx.early
-            ctx.early = None
+        early, ctx.early = ctx.early, None
+        if early is not None and early in _PENDING:
+            _PENDING.remove(early)  # no lattice kernel came by: the plain path below
+        if early is not None and early.side is not None:
             cur = torch.cuda.current_stream(am.device)
-            cur.wait_stream(side)  # also what joins the side stream back into a CUDA-graph capture of the step
-            d_am.record_stream(cur)
-            d_lm.record_stream(cur)
+            cur.wait_stream(early.side)  # also what joins the side stream back into a CUDA-graph capture of the step
             if grad_scores is None:
                 return (None,) * 9
-            g = _f32c(grad_scores).view(B, 1, 1)
-            return d_am.mul_(g), d_lm.mul_(g), None, None, None, None, None, None, None
+            check(lib().s2t_rescale_groups(ptr(early.d_am), T * V, ptr(early.d_lm), (S + 1) * V, B,
+                                           ptr(_f32c(grad_scores)), ptr(early.pred), stream()))
+            return early.d_am, early.d_lm, None, None, None, None, None, None, None
         if grad_scores is None:
             return (None,) * 9
         grad_scores = _f32c(grad_scores)
@@ -195,6 +241,9 @@ class _SimpleLoss(torch.autograd.Function):
         check(lib().s2t_simple_loss_bwd(ctx.mode, ptr(am), ptr(lm), ptr(symbols), ptr(am_max), ptr(lm_max), ptr(nrm),
                                         ptr(px_grad), ptr(py_grad), ptr(grad_scores), B, T, S, V, ctx.blank,
                                         ctx.scales[0], ctx.scales[1], ptr(ws), ptr(d_am), ptr(d_lm), stream()))
+        if _early_simple_backward(ctx.mode):  # what the next step's early launch will assume
+            check(lib().s2t_rescale_groups(None, 0, None, 0, B, ptr(grad_scores), ptr(_predicted_scale(B, am.device)),
+                                           stream()))
         return d_am, d_lm, None, None, None, None, None, None, None
 
 
@@ -353,10 +402,13 @@ class _JoinerLoss(torch.autograd.Function):
         occ_py = torch.empty((B, T, R), **f32)
         alpha = _dp_scratch(B, S, T, R, dev)
         scores = torch.empty((B,), **f32)
-        check(lib().s2t_joiner_loss_fwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(ranges), ptr(boundary),
-                                        ptr(W1), ptr(b1), ptr(W2), ptr(b2), B, T, S, R, V, I, act, blank,
-                                        float(delay_penalty), ptr(workspace), ptr(lse), ptr(px), ptr(py),
-                                        ptr(alpha), ptr(scores), ptr(occ_px), ptr(occ_py), stream()))
+        check(lib().s2t_joiner_logprobs_fwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(ranges), ptr(boundary),
+                                            ptr(W1), ptr(b1), ptr(W2), ptr(b2), B, T, S, R, V, I, act, blank,
+                                            float(delay_penalty), ptr(workspace), ptr(lse), ptr(px), ptr(py),
+                                            stream()))
+        _launch_pending(dev)  # the simple loss's gradient contractions run next to the lattice kernel
+        check(lib().s2t_band_lattice_fwd(ptr(px), ptr(py), ptr(ranges), ptr(boundary), B, S, T, R, ptr(alpha),
+                                         ptr(scores), ptr(occ_px), ptr(occ_py), stream()))
         empty = torch.empty(0, device=dev)
         ctx.save_for_backward(am, lm, W1 if has_proj else empty, b1 if has_proj else empty,
                               W2 if has_proj else empty, b2 if has_proj else empty, symbols,

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     missing = [s for s in _declared_symbols() if not hasattr(handle, s)]
     assert not missing, f"declared in include/s2t_b200.h but not exported: {missing}"
     handle.s2t_abi_version.restype = ctypes.c_int
-    assert handle.s2t_abi_version() == 2
+    assert handle.s2t_abi_version() == 3
 
 
 def test_ctypes_signatures_cover_the_header():

@@ -988,3 +988,58 @@ def test_linear_tc_reads_bf16_activations_natively():
         torch.cuda.synchronize()
         assert xb.grad.dtype == torch.bfloat16 and xf.grad.dtype == torch.float32
         assert torch.equal(xb.grad, xf.grad.bfloat16())
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_simple_loss_gradient_issued_next_to_the_band_lattice(mode, monkeypatch):
+    """The simple loss's gradient contractions may be issued ahead of the backward pass, next to the joiner's band
+    lattice, with the upstream scale of the previous step (functional._EarlySimpleBackward); backward corrects the scale.
+    Same kernels, same operands: the gradients equal the plain path's bit for bit when the prediction was right, and up
+    to the rounding of one extra multiply (fp32 mode) or of the bf16 operand coef * W (tensor-core mode) when it was not.  Scales 0.5 -> 0.5 -> 0.125 -> 0 -> 2 cover: first use
+    (prediction = 1), a right prediction, a wrong one, a zero scale (the prediction must not become 0), recovery."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    from speech2text_b200 import functional as F2
+    B, T, U, V, D, R, I = 3, 90, 21, 120, 48, 5, 256
+    g = torch.Generator().manual_seed(11)
+    enc0 = torch.randn(B, T, D, generator=g) * 0.7
+    pred0 = torch.randn(B, U + 1, D, generator=g) * 0.7
+    tgt = torch.randint(1, V, (B, U), generator=g).to(_dev())
+    t_len = torch.tensor([T, T - 17, T - 40]).to(_dev())
+    s_len = torch.tensor([U, U - 3, U - 9]).to(_dev())
+    torch.manual_seed(3)
+    joiner = Joiner(JoinerConfig(input_dim=D, output_dim=V, inner_dim=I, activation="tanh", prune_range=R)).to(_dev())
+    loss_mod = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", mode)
+
+    def step(scale):
+        joiner.zero_grad(set_to_none=True)
+        enc = enc0.to(_dev()).requires_grad_(True)
+        pred = pred0.to(_dev()).requires_grad_(True)
+        logits, boundary, ranges, simple = joiner(enc, t_len, pred, s_len, tgt)
+        pruned = loss_mod({"logits": logits, "logits_length": t_len, "targets": tgt, "targets_length": s_len,
+                           "boundary": boundary, "ranges": ranges})
+        (scale * simple + 0.5 * pruned).backward()
+        torch.cuda.synchronize()
+        return dict(d_enc=enc.grad.clone(), d_pred=pred.grad.clone(),
+                    **{"d" + k: p.grad.clone() for k, p in joiner.named_parameters()})
+
+    scales = [0.5, 0.5, 0.125, 0.0, 2.0]
+    monkeypatch.setenv("S2T_B200_EARLY_SIMPLE_BWD", "0")
+    plain = [step(s) for s in scales]
+    monkeypatch.setenv("S2T_B200_EARLY_SIMPLE_BWD", "1")
+    F2._PRED.clear()
+    launched = []
+    real_launch = F2._EarlySimpleBackward.launch
+    monkeypatch.setattr(F2._EarlySimpleBackward, "launch", lambda self: (launched.append(1), real_launch(self))[1])
+    early = [step(s) for s in scales]
+    assert len(launched) == len(scales) and not F2._PENDING  # every step took the early path
+    for i, (a, b) in enumerate(zip(plain, early)):
+        for k in a:
+            if i == 1:  # prediction right: nothing is rescaled
+                assert torch.equal(a[k], b[k]), (i, k)
+            else:
+                # tensor-core mode rounds coef * W to bf16: a different coef is a different (equally good) rounding
+                assert rel_err(b[k], a[k]) < (1e-2 if mode == "bf16" else 1e-6), (i, k, rel_err(b[k], a[k]))
+    assert all(float(v.abs().min()) > 0 for v in F2._PRED.values())
