@@ -978,15 +978,19 @@ constexpr int kFThreads = 32 * (kCtrlWarps + kEpiWarps + kProdWarps);
 // slots, an lm row serves every frame whose band holds that symbol position: ~40 distinct rows against 256 row
 // reads), one 64-entry vocabulary step per stage, brought in by bulk copies.  The producers then read them from
 // shared memory: what a tile pulls through the L2 -> SM path for its A operand drops from 512 KB to ~80 KB.
-constexpr int kRawStages = 2;
-constexpr int kRawAm = 32, kRawLm = 24;                 // staged rows per step (tiles that need more take the direct path)
+// Three stages of 42 rows: what a stage holds is in flight for the ~1.7 us a bulk copy takes under load, so the ring
+// depth (not the bandwidth) paces contraction 1 -- with two stages the producers spent 37 % of their time waiting for
+// rows (ncu).  42 rows (am rows first, lm rows behind them) cover the ~27 frames + ~13 symbol positions of a tile
+// inside one utterance; the tile in ~16 that straddles two utterances takes the direct path.
+constexpr int kRawStages = 3;
+constexpr int kRawRows = 42;                            // staged rows per step (tiles that need more take the direct path)
 constexpr int kRawRowBytes = kBlockK * 4;               // 64 fp32
-constexpr int kRawBytes = (kRawAm + kRawLm) * kRawRowBytes;  // 14 KB
+constexpr int kRawBytes = kRawRows * kRawRowBytes;      // 10.5 KB
 constexpr size_t kFSmemBytes = (size_t)kFS1 * kFStage1 + kFHBytes + (size_t)kFS2 * kBlockBytes + (size_t)kRawStages * kRawBytes +
                                (256 + 2 * 128) * sizeof(float) /*b1, two vocabulary tiles of b2*/ + 1024 /*align*/ +
                                512 /*barriers, tile plans*/;
 
-// what the planner warp tells the producers about a tile (double-buffered by tile parity)
+// what the planner warp tells the producers about a tile (four slots, by tile index)
 struct TilePlan {
   int fast;      // 1: rows staged in the raw ring; 0: direct global loads (too many distinct rows, or unaligned)
   int am_first;  // first am row (b T + t) of the tile
@@ -1043,7 +1047,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
   uint64_t* raw_full = acc2_empty + 2;   // [kRawStages]
   uint64_t* raw_empty = raw_full + kRawStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRawStages);
-  TilePlan* plans = reinterpret_cast<TilePlan*>(tmem_slot + 4);  // [2]
+  TilePlan* plans = reinterpret_cast<TilePlan*>(tmem_slot + 4);  // [4]: the planner runs at most kRawStages steps ahead
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -1156,8 +1160,8 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         bad |= __shfl_xor_sync(0xffffffffu, bad, o);
       }
       const int n_am = am_hi - am_lo + 1, n0 = hi0 >= lo0 ? hi0 - lo0 + 1 : 0, n1 = hi1 >= lo1 ? hi1 - lo1 + 1 : 0;
-      const bool fast = aligned && !bad && n_am <= kRawAm && n0 + n1 <= kRawLm;
-      if (lane == 0) plans[lt & 1] = TilePlan{fast ? 1 : 0, am_lo, n_am, b0, lo0, n0, lo1, n1};
+      const bool fast = aligned && !bad && n_am + n0 + n1 <= kRawRows;
+      if (lane == 0) plans[lt & 3] = TilePlan{fast ? 1 : 0, am_lo, n_am, b0, lo0, n0, lo1, n1};
       __syncwarp();
       const int n_rows = n_am + n0 + n1;
       for (int ks = 0; ks < p.kbV; ++ks, ++g) {
@@ -1174,18 +1178,10 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         uint8_t* dst0 = raw + s * kRawBytes;
         for (int i = lane; i < n_rows; i += 32) {
           const float* src;
-          int slot;
-          if (i < n_am) {
-            src = p.am + (int64_t)(am_lo + i) * p.V;
-            slot = i;
-          } else if (i - n_am < n0) {
-            src = p.lm + (int64_t)(lo0 + i - n_am) * p.V;
-            slot = kRawAm + i - n_am;
-          } else {
-            src = p.lm + (int64_t)(lo1 + i - n_am - n0) * p.V;
-            slot = kRawAm + i - n_am;
-          }
-          bulk_copy_g2s(dst0 + slot * kRawRowBytes, src + ks * kBlockK, row_bytes, &raw_full[s]);
+          if (i < n_am) src = p.am + (int64_t)(am_lo + i) * p.V;
+          else if (i - n_am < n0) src = p.lm + (int64_t)(lo0 + i - n_am) * p.V;
+          else src = p.lm + (int64_t)(lo1 + i - n_am - n0) * p.V;
+          bulk_copy_g2s(dst0 + i * kRawRowBytes, src + ks * kBlockK, row_bytes, &raw_full[s]);
         }
       }
     }
@@ -1400,7 +1396,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
       const int tile = tile_of(j);
       mbar_wait(&raw_full[graw % kRawStages], (graw / kRawStages) & 1);  // also publishes the tile's plan
-      const TilePlan plan = plans[lt & 1];
+      const TilePlan plan = plans[lt & 3];
       if (!plan.fast) {
         // the raw ring carries nothing for this tile: hand its stages straight back, then load directly
         for (int ks = 0; ks < p.kbV; ++ks, ++graw) {
@@ -1436,7 +1432,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
           const int ar = __ldg(p.am_row + m), lr = __ldg(p.lm_row + m);
           a_off[i] = (ar - plan.am_first) * kRawRowBytes + c * 16;
           const int slot = (ar / p.T == plan.b0) ? lr - plan.lo0 : plan.n0 + lr - plan.lo1;
-          l_off[i] = (kRawAm + slot) * kRawRowBytes + c * 16;
+          l_off[i] = (plan.n_am + slot) * kRawRowBytes + c * 16;
         }
       }
       for (int ks = 0; ks < p.kbV; ++ks, ++g, ++graw) {

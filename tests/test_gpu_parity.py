@@ -1037,8 +1037,11 @@ def test_simple_loss_gradient_issued_next_to_the_band_lattice(mode, monkeypatch)
     assert len(launched) == len(scales) and not F2._PENDING  # every step took the early path
     for i, (a, b) in enumerate(zip(plain, early)):
         for k in a:
-            if i == 1:  # prediction right: nothing is rescaled
-                assert torch.equal(a[k], b[k]), (i, k)
+            if i == 1:  # prediction right: nothing is rescaled (weight gradients meet in atomics: order noise only)
+                if k in ("d_enc", "d_pred"):
+                    assert torch.equal(a[k], b[k]), (i, k)
+                else:
+                    assert rel_err(b[k], a[k]) < 1e-5, (i, k, rel_err(b[k], a[k]))
             else:
                 # tensor-core mode rounds coef * W to bf16: a different coef is a different (equally good) rounding
                 assert rel_err(b[k], a[k]) < (1e-2 if mode == "bf16" else 1e-6), (i, k, rel_err(b[k], a[k]))
