@@ -569,8 +569,10 @@ struct GradEpi {
     store_packed_row32(ctx, Gp, g_row_blocks, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
-    if (n + lane < V && cs != 0.f && !(ctx.dbg & 32)) atomicAdd(db2 + n + lane, cs);
+    if (n + lane < V && cs != 0.f) atomicAdd(db2 + n + lane, cs);
   }
+  // no kColSums: measured 0.0705 -> 0.074 ms with the shared-memory sums here (this epilogue is issue-bound and its
+  // global reductions are fire-and-forget), whereas the dhidden epilogue below gained 0.058 -> 0.0455
 };
 
 // dhidden -> DHp (rows chunk-local m, cols i), db1
@@ -595,7 +597,14 @@ struct DHiddenEpi {
     store_packed_row32(ctx, DHp, dh_row_blocks, n, x);
     const float cs = warp_column_sums(x);
     const int lane = threadIdx.x & 31;
-    if (n + lane < I && cs != 0.f && !(ctx.dbg & 32)) atomicAdd(db1 + n + lane, cs);
+    if (n + lane < I && cs != 0.f) {
+      if (ctx.colsum) atomicAdd(ctx.colsum + (n - ctx.tile_col0) + lane, cs);
+      else atomicAdd(db1 + n + lane, cs);
+    }
+  }
+  static constexpr bool kColSums = true;
+  __device__ void flush_colsum(int col, float v) const {
+    if (col < I) atomicAdd(db1 + col, v);
   }
 };
 

@@ -66,6 +66,12 @@ struct EpiCtx {
   uint8_t* scratch;  // this group's Epi::kScratchBytes
   int scratch_bytes;
   int dbg;
+  // Column sums (bias gradients), Epi::kColSums: when the CTA keeps ONE column tile for its whole life, the epilogue
+  // adds its per-chunk column sums into this shared-memory row (index = column - tile_col0) and the kernel hands every
+  // column's total to Epi::flush_colsum once, at the end -- instead of one global atomic per column, warp and tile,
+  // all CTAs on the same few hundred addresses.  Null: add to global memory directly.
+  float* colsum;
+  int tile_col0;
 };
 
 // barrier over the 128 threads of one epilogue group
@@ -104,6 +110,14 @@ template <class Epi>
 struct EpiBulkGroups<Epi, decltype((void)Epi::kBulkGroups)> {
   static constexpr int value = Epi::kBulkGroups;
 };
+template <class Epi, class = void>
+struct EpiColSums {
+  static constexpr bool value = false;
+};
+template <class Epi>
+struct EpiColSums<Epi, decltype((void)Epi::kColSums)> {
+  static constexpr bool value = Epi::kColSums;
+};
 template <class ASrc, class Epi>
 constexpr int gemm_epi_groups() {
   return ASrc::kBulk ? EpiBulkGroups<Epi>::value : 1;
@@ -129,7 +143,8 @@ template <int BN, int kStages, int kKind, class ASrc, class Epi, int kBRes = 0>
 constexpr size_t gemm_stream_smem_bytes_for(int stages) {
   return (size_t)stages * (kBRes > 0 ? kBlockBytes : gemm_stage_bytes<BN, kKind>()) +
          (size_t)kBRes * (BN / 128) * kBlockBytes +
-         (size_t)gemm_epi_groups<ASrc, Epi>() * (((Epi::kScratchBytes + 127) / 128) * 128) + 1024 /*align*/ + 256 /*barriers*/;
+         (size_t)gemm_epi_groups<ASrc, Epi>() * (((Epi::kScratchBytes + 127) / 128) * 128) + 1024 /*align*/ + 256 /*barriers*/ +
+         (EpiColSums<Epi>::value ? BN * sizeof(float) : 0);
 }
 // ring depth actually used: the requested one, less when the epilogue scratch of all groups would not fit
 template <int BN, int kStages, int kKind, class ASrc, class Epi, int kBRes = 0>
@@ -268,6 +283,8 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   uint64_t* bres_full = tempty + 2;
   uint64_t* pfull = bres_full + 1;  // leader of a pair: the peer's half of stage s has landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + kStages);
+  constexpr bool kColSums = EpiColSums<Epi>::value;
+  float* colsum_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [BN] when kColSums
 
   static_assert(kCluster == 1 || kCluster == 2, "clusters of one or two CTAs");
   static_assert(kCluster == 1 || !kMn, "CTA pairs are built for K-major operands");
@@ -290,6 +307,9 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   if (warp == 1) {
     if constexpr (kCluster == 1) tmem_alloc<kTmemCols>(tmem_slot);
     else tmem_alloc_pair<kTmemCols>(tmem_slot);
+  }
+  if constexpr (kColSums) {
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) colsum_smem[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -529,6 +549,12 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       ctx.scratch = scratch + group * kScratch;
       ctx.scratch_bytes = kScratch;
       ctx.dbg = mn.dbg;
+      ctx.colsum = nullptr;
+      ctx.tile_col0 = c.n_tile * BN;
+      if constexpr (kColSums) {
+        // one column tile per CTA: B-stationary launches, or a streaming launch with a single column tile and no splits
+        if (kBRes > 0 || (n_tiles == 1 && k_splits == 1 && batches == 1)) ctx.colsum = colsum_smem;
+      }
       if (c.valid) {
         typename Epi::State st;
         epi.begin(st, ctx);
@@ -549,6 +575,18 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
         if (lane == 0) mbar_arrive_cluster(&tempty[buf], 0);
       }
       ++lt;
+    }
+    if constexpr (kColSums) {
+      if (kBRes > 0 || (n_tiles == 1 && k_splits == 1 && batches == 1)) {
+        // all epilogue warps have added their sums: hand the CTA's totals over, one global atomic per column
+        constexpr int kEpiThreads = 32 * kEpiWarps * kGroups;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + kGroups), "n"(kEpiThreads) : "memory");
+        const int col0 = (kBRes > 0 ? (int)blockIdx.x % n_tiles : 0) * BN;
+        for (int i = (int)threadIdx.x - 32 * kCtrlWarps; i < BN; i += kEpiThreads) {
+          const float v = colsum_smem[i];
+          if (v != 0.f) epi.flush_colsum(col0 + i, v);
+        }
+      }
     }
   } else if (warp >= kCtrlWarps + kEpiWarps * kGroups) {
     // ---------------- on-the-fly A producers ----------------
