@@ -1626,12 +1626,8 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.Hp + (size_t)tile0 * kBlockBytes, d.Mt};  // block(rb, kb) = kb * Mt + rb: shift rb by tile0
       GradEpi ep{p.b2, w.row_sym, lse, occ_px, occ_py, coef, row0, M, p.T * p.R, p.V, p.blank, clamp, w.Gp, ct, db2};
-      static const int bs128 = getenv("S2T_B200_BS128") ? atoi(getenv("S2T_B200_BS128")) : 0;
-      if (bs128 & 1) {
-        if (int rc = launch_gemm_bstationary<128, 7, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.Vp / 128, d.kbI, ep, stream,
-                                                                "tc_joiner_grad_logits_gemm", live))
-          return rc;
-      } else if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
+      // (a 128-column resident tile with a 7-stage A ring instead of 256 columns / 3 stages: 0.071 -> 0.083 ms)
+      if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W2p, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
                                                                        "tc_joiner_grad_logits_gemm", live))
         return rc;
     }
@@ -1677,12 +1673,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
     {
       BulkA a{w.DHp, ct};
       StoreRowsBf16Epi ep{w.dh, d.Vp};
-      static const int bs128 = getenv("S2T_B200_BS128") ? atoi(getenv("S2T_B200_BS128")) : 0;
-      if (bs128 & 2) {
-        if (int rc = launch_gemm_bstationary<128, 7, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.Vp / 128, d.kbI, ep, stream,
-                                                                "tc_joiner_dh_gemm", live))
-          return rc;
-      } else if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
+      if (int rc = launch_gemm_bstationary<kBN, kNStagesRes, kResSteps>(a, w.W1Tp, d.Vp / 128, ct, d.n_tiles_v, d.kbI, ep, stream,
                                                                        "tc_joiner_dh_gemm", live))
         return rc;
       const int64_t rows_live = (M - row0 < rows_pad) ? (M - row0) : rows_pad;

@@ -39,11 +39,6 @@ LinDims lin_dims(int64_t M, int N, int K) {
   return d;
 }
 
-__global__ void fill_kernel(float* p, int64_t n, float v) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
-
 }  // namespace
 }  // namespace s2t
 
@@ -62,7 +57,6 @@ int s2t_linear_fwd(const void* x, int x_dtype, const float* W, const float* b, i
   S2T_REQUIRE(x_dtype == S2T_F32 || x_dtype == S2T_BF16, "linear_fwd: x must be fp32 or bf16 (dtype code %d)", x_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
-  if (row_max) fill_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(row_max, M, kNegInf);
   LinDims d = lin_dims(M, N, K);
   uint8_t* px = (uint8_t*)ws;
   uint8_t* pw = px + d.px;
@@ -86,7 +80,7 @@ int s2t_linear_fwd(const void* x, int x_dtype, const float* W, const float* b, i
         // W^T for dx in backward: rows k, cols n -> element (k, n) = W[n * K + k]
         {W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, 0},
     };
-    if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
+    if (int rc = tc::pack_jobs(jobs, 3, st, row_max, M, kNegInf)) return rc;  // + row_max = -inf for the epilogue's atomic max
     ep.scale = 1.f / kWScale;
     if (x_dtype == S2T_BF16) {
       tc::RowSplitProducerF16T<__nv_bfloat16> a{(const __nv_bfloat16*)x, K, M, K, px, d.Mt};
@@ -104,7 +98,7 @@ int s2t_linear_fwd(const void* x, int x_dtype, const float* W, const float* b, i
         {W, K, 1, N, K, d.Np / 128, d.Kp / 32, pw_small, 2},
         {W, 1, K, K, N, d.Kp / 128, d.Np / 64, pwt, 0},
     };
-    if (int rc = tc::pack_jobs(jobs, 3, st)) return rc;
+    if (int rc = tc::pack_jobs(jobs, 3, st, row_max, M, kNegInf)) return rc;
   }
   tc::RowCopyProducerF32 a{(const float*)x, K, M, K, true, px, d.Mt};
   return tc::launch_gemm_stream<256, 2, false, 2, kPair>(a, pw, d.Np / 128, d.Mt, d.Np / 256, (K + 31) / 32, 1, ep, st,

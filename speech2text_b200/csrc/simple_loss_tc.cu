@@ -219,7 +219,8 @@ struct ExpRowSplitProducerF16 {
 // accumulator rows = frames t (ctx.m inside batch ctx.batch), columns = symbol positions s.
 // Writes nrm and py (lane = frame, so every store instruction is one contiguous 128-byte row segment of the
 // k2 (B, S+1, T) layout); px needs the gather am[b, t, sym[b, s]] and is finished by simple_px_kernel with
-// the whole GPU instead of the four epilogue warps.
+// the whole GPU instead of the four epilogue warps (measured: the gather inside this epilogue -- eight loads in flight
+// per thread, four warps -- took the kernel from 0.057 to 0.105 ms; simple_px_kernel does it in 0.023).
 struct SimpleEmitTcEpi {
   static constexpr int kScratchBytes = 0;
   const float* am;

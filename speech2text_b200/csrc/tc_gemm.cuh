@@ -966,8 +966,11 @@ struct PackJobs {
   PackJob job[kMax];
   int64_t first[kMax + 1];  // first chunk (thread) of every job
   int n;
+  float* fill = nullptr;  // optional: fill[0 .. fill_n) = fill_value by the threads behind the last job (saves a launch)
+  int64_t fill_n = 0;
+  float fill_value = 0.f;
 };
-int pack_jobs(const PackJob* list, int n, cudaStream_t stream);
+int pack_jobs(const PackJob* list, int n, cudaStream_t stream, float* fill = nullptr, int64_t fill_n = 0, float fill_value = 0.f);
 
 // Batched packing with an optional fused exp: element (batch, r, k) = f(src[batch*batch_stride + r*row_stride + k])
 // with f(x) = exp(x - row_sub[batch*rows + r]) when row_sub != nullptr.  Every batch is padded to rows_pad

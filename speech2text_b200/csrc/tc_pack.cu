@@ -118,7 +118,11 @@ __global__ void __launch_bounds__(256) pack_rows_colsum_kernel(const float* __re
 // several small matrices (the weights of one module) in ONE launch: one thread per 16-byte chunk of any job
 __global__ void pack_jobs_kernel(PackJobs jobs) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= jobs.first[jobs.n]) return;
+  if (i >= jobs.first[jobs.n]) {
+    const int64_t f = i - jobs.first[jobs.n];
+    if (f < jobs.fill_n) jobs.fill[f] = jobs.fill_value;
+    return;
+  }
   int j = 0;
 #pragma unroll
   for (int q = 1; q < PackJobs::kMax; ++q)
@@ -289,7 +293,7 @@ int pack_rows_colsum(const float* src, const float* src2, int64_t ld, int rows, 
   return check_launch("pack_rows_colsum_kernel");
 }
 
-int pack_jobs(const PackJob* list, int n, cudaStream_t stream) {
+int pack_jobs(const PackJob* list, int n, cudaStream_t stream, float* fill, int64_t fill_n, float fill_value) {
   S2T_REQUIRE(n >= 1 && n <= PackJobs::kMax, "pack_jobs: %d jobs", n);
   PackJobs jobs;
   jobs.n = n;
@@ -301,7 +305,10 @@ int pack_jobs(const PackJob* list, int n, cudaStream_t stream) {
     jobs.job[j] = q;
     jobs.first[j + 1] = jobs.first[j] + (int64_t)q.row_blocks * 128 * q.k_blocks * 8;
   }
-  const int64_t total = jobs.first[n];
+  jobs.fill = fill;
+  jobs.fill_n = fill ? fill_n : 0;
+  jobs.fill_value = fill_value;
+  const int64_t total = jobs.first[n] + jobs.fill_n;
   if (total == 0) return 0;
   ProfScope prof("pack_operand_kernel", stream);
   pack_jobs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(jobs);

@@ -58,10 +58,15 @@ def make_boundary(target_lengths: Tensor, encoder_out_lengths: Tensor, device) -
     """/root/reference/model/joiner/joiner.py:89-93 -- rows [0, 0, S_b, T_b], int64.
     Lengths may arrive as float tensors (joiner_test.py:56-58)."""
     B = target_lengths.shape[0]
-    boundary = torch.zeros((B, 4), dtype=torch.int64, device=device)
-    boundary[:, 2] = target_lengths.to(device)
-    boundary[:, 3] = encoder_out_lengths.to(device)
-    return boundary
+    s = target_lengths.to(device=device, dtype=torch.int64)
+    t = encoder_out_lengths.to(device=device, dtype=torch.int64)
+    if not s.is_cuda:
+        boundary = torch.zeros((B, 4), dtype=torch.int64, device=device)
+        boundary[:, 2] = s
+        boundary[:, 3] = t
+        return boundary
+    z = _zeros_i64(B, device)
+    return torch.stack((z, z, s, t), dim=1)  # one kernel instead of a fill and two strided copies
 
 
 # ---------------------------------------------------------------------------
@@ -91,6 +96,7 @@ def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tens
 # ---------------------------------------------------------------------------
 _SIDE_STREAMS: dict = {}
 _ONES: dict = {}
+_ZEROS_I64: dict = {}
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
@@ -98,6 +104,14 @@ def _side_stream(device) -> "torch.cuda.Stream":
     if s is None:
         s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
     return s
+
+
+def _zeros_i64(n: int, device) -> Tensor:
+    key = (n, device)
+    t = _ZEROS_I64.get(key)
+    if t is None:
+        t = _ZEROS_I64[key] = torch.zeros((n,), dtype=torch.int64, device=device)
+    return t
 
 
 def _ones(n: int, device) -> Tensor:
