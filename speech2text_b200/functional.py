@@ -6,6 +6,7 @@ Function names mirror the k2 / torchaudio calls of the reference they replace.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional, Tuple
 
@@ -593,7 +594,8 @@ class _LinearTC(torch.autograd.Function):
 
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, x: Tensor, W: Tensor, b: Tensor, sink_params=None, want_row_max: bool = False):
+    def forward(ctx, x: Tensor, W: Tensor, b: Tensor, sink_params=None, want_row_max: bool = False,
+                on_side_stream: bool = False):
         ctx.sink_params = sink_params  # (W, b) parameters when they may carry a bound gradient sink
         lead = x.shape[:-1]
         K = x.shape[-1]
@@ -605,8 +607,20 @@ class _LinearTC(torch.autograd.Function):
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         # by-product of the epilogue: max over the output features of every row
         row_max = torch.empty((M,), dtype=torch.float32, device=x.device) if want_row_max else None
+        if on_side_stream:
+            # The caller has a second, independent projection to launch (the predictor side is 0.7 of a wave of
+            # tiles, the encoder side 2.7: together 3.4 instead of 1 + 3 rounds) and joins with join_side_stream().
+            # Everything is allocated on the current stream; the side stream only runs the kernels.
+            cur, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
+            side.wait_stream(cur)
+            for t in (x2, W, b, ws, y, row_max):
+                if t is not None:
+                    t.record_stream(side)
+            st = ctypes.c_void_p(side.cuda_stream)
+        else:
+            st = stream()
         check(lib().s2t_linear_fwd(ptr(x2), _lib.dtype_code(x2.dtype), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y),
-                                   ptr(row_max), stream()))
+                                   ptr(row_max), st))
         ctx.save_for_backward(W, ws)
         ctx.dims = (M, N, K, lead, x.requires_grad, x.dtype)
         y = y.reshape(*lead, N)
@@ -624,7 +638,7 @@ class _LinearTC(torch.autograd.Function):
         if dy is None:
             dy, dy_alias = dy_alias, None
         if dy is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         sinks = claim_grad_sinks(ctx.sink_params)
         sink_W, sink_b = sinks if sinks is not None else (None, None)
         dy2 = _f32c(dy).reshape(M, N)
@@ -639,7 +653,7 @@ class _LinearTC(torch.autograd.Function):
         if need_dx and x_dtype != dx_dtype:
             dx = dx.to(x_dtype)
         return ((dx.reshape(*lead, K) if need_dx else None), None if sink_W is not None else dW,
-                None if sink_b is not None else db, None, None)
+                None if sink_b is not None else db, None, None, None)
 
 
 def grad_sink(p: Optional[Tensor]) -> Optional[Tensor]:
@@ -685,8 +699,16 @@ def linear_tc(x: Tensor, W: Tensor, b: Tensor) -> Tensor:
     return linear_tc_pair(x, W, b)[0]
 
 
-def linear_tc_pair(x: Tensor, W: Tensor, b: Tensor, row_max: bool = False):
+def linear_tc_pair(x: Tensor, W: Tensor, b: Tensor, row_max: bool = False, on_side_stream: bool = False):
     """Same, as two aliases of the result for two consumers (see _LinearTC).  ``row_max=True`` appends the per-row
-    maximum of the result (a by-product of the epilogue) as a third output."""
+    maximum of the result (a by-product of the epilogue) as a third output.  ``on_side_stream=True`` launches the
+    kernels on the library's side stream: the caller issues its other independent work and then calls
+    ``join_side_stream`` before anything reads the results."""
     params = (W, b)
-    return _LinearTC.apply(x, W, b, params if all(grad_sink(p) is not None for p in params) else None, row_max)
+    return _LinearTC.apply(x, W, b, params if all(grad_sink(p) is not None for p in params) else None, row_max,
+                           on_side_stream)
+
+
+def join_side_stream(device) -> None:
+    """The current stream waits for what was launched with ``on_side_stream=True``."""
+    torch.cuda.current_stream(device).wait_stream(_side_stream(device))

@@ -205,8 +205,13 @@ class Joiner(nn.Module):
             # two aliases of each projection: one for the simple loss, one for the joiner (functional._LinearTC)
             # ... and, when the simple loss follows, the row maxima it needs as a by-product of the GEMM epilogue
             want = self.prune_range > 0
+            # the predictor-side projection (under one wave of tiles) runs on a side stream next to the encoder-side one
+            side = os.environ.get("S2T_B200_PROJ_OVERLAP", "1") != "0" and not _lib.profiling()
+            lm, lm_j, *lm_max = F2.linear_tc_pair(predict_out, self._pre_proj.weight, self._pre_proj.bias, row_max=want,
+                                                  on_side_stream=side)
             am, am_j, *am_max = F2.linear_tc_pair(encoder_out, self._enc_proj.weight, self._enc_proj.bias, row_max=want)
-            lm, lm_j, *lm_max = F2.linear_tc_pair(predict_out, self._pre_proj.weight, self._pre_proj.bias, row_max=want)
+            if side:
+                F2.join_side_stream(encoder_out.device)
             row_max = (am_max[0], lm_max[0]) if want else None
         else:
             am = am_j = self._enc_proj(encoder_out)
