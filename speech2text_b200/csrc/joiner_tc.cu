@@ -19,6 +19,8 @@
 #include "joiner.cuh"
 #include "tc_gemm.cuh"
 
+#include <cuda.h>
+
 namespace s2t {
 namespace {
 
@@ -976,8 +978,20 @@ int pack_weights(const JoinerProblem& p, const TcDims& d, const TcWs& w, cudaStr
 //                 packed hidden operand Hp in HBM); then, per vocabulary tile, the running (max, sum exp) and the
 //                 sym / blank gather; lse / px / py are final when the tile's last vocabulary tile has been drained
 //
-// Shared memory: 2 x 48 KB stage ring 1 + 64 KB hidden tile + 4 x 16 KB ring 2.  Per tile the SM pulls W1 and W2
-// (2 x Vp x 256 x 2 bytes) through L2 once: at V = 500 that is 512 KB against 8192 cycles of MMA issue.
+// Shared memory: 2 x 48 KB stage ring 1 (A stage + a W1 k-step) + 64 KB hidden tile + 2 x 16 KB ring 2 (W2 blocks) + the raw
+// ring.  What paces the kernel is the weight stream: per 128-row tile every SM pulls W1 and W2 (2 x Vp x 256 x 2 bytes =
+// 512 KB at V = 500) through L2, and with all 148 SMs doing so the blocks arrive at ~17 bytes per cycle and SM (~5 TB/s
+// over the chip) however many are in flight (role timeline, S2T_TRACE=tc_joiner_fwd_fused: a W2 block every ~1500 cycles
+// with 2 blocks in flight, every ~2000 with W1 as half k-steps and three blocks in each weight ring -- Little's law with
+// a fixed rate; that variant measured 0.145 ms against 0.134).  Fewer weight bytes per row would need both contractions
+// on CTA pairs (cta_group::2: each SM holds half of every weight block).
+// role timeline of CTA 0 (S2T_TRACE=tc_joiner_fwd_fused): compiled in with -DS2T_FUSED_TRACE only -- the marks cost the
+// kernel ~3 % (registers)
+#ifdef S2T_FUSED_TRACE
+#define S2T_FUSED_MARK(code, idx) trace_mark(p.trace, code, idx)
+#else
+#define S2T_FUSED_MARK(code, idx) ((void)0)
+#endif
 constexpr int kFS1 = 2;                          // stages of ring 1
 constexpr int kFS2 = 2;                          // stages of ring 2
 constexpr int kFStage1 = 3 * kBlockBytes;        // A (128 x 64) + B (256 x 64)
@@ -1010,6 +1024,51 @@ struct TilePlan {
 };
 static_assert(kFSmemBytes <= 227 * 1024, "fused joiner forward: shared memory");
 
+// Tensor maps of am (B T, V) and lm (B (S+1), V) with boxes of 1, 2, 4, .. 32 rows x 64 columns: the n distinct rows a
+// tile needs from a tensor are consecutive rows, fetched as the binary decomposition of n -- ~7 tensor copies per step
+// instead of ~40 row copies of 256 bytes (the copy engine's per-instruction cost, not the bytes, paced the raw ring).
+constexpr int kRawBoxes = 6;
+struct alignas(64) RawMaps {
+  CUtensorMap am[kRawBoxes];
+  CUtensorMap lm[kRawBoxes];
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// rows x V fp32, row-major; false when the tensor cannot be described (unaligned base, V not a multiple of 4)
+bool encode_row_boxes(const float* base, int64_t rows, int V, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || rows <= 0 || (V & 3) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  for (int i = 0; i < kRawBoxes; ++i) {
+    const cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)V * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, 1u << i};
+    const cuuint32_t estr[2] = {1, 1};
+    if (fn(&out[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
 struct FusedFwdParams {
   const float* am;
   const float* lm;
@@ -1031,10 +1090,13 @@ struct FusedFwdParams {
   int64_t M;
   int Mt, V, I, kbV, nN, w2_row_blocks, act, blank, T, R;
   float delay_penalty;
+  int maps_ok = 0;  // RawMaps describe am / lm (set by the launcher): the raw ring is fed by tensor copies
+  unsigned long long* trace = nullptr;  // S2T_TRACE=tc_joiner_fwd_fused: role timeline of CTA 0
 };
 
 template <int kAct>
-__global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const FusedFwdParams p) {
+__global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const FusedFwdParams p,
+                                                                        const __grid_constant__ RawMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   uint8_t* ring1 = smem;
@@ -1132,18 +1194,30 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     // ---- planner: which distinct am / lm rows a tile needs, and their bulk copies into the raw ring ----
     const bool aligned = (p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.am) | reinterpret_cast<uintptr_t>(p.lm)) & 15) == 0;
     uint32_t g = 0, lt = 0;
+    // the row indices of a tile (am_row / lm_row of its 128 rows: four per lane) are fetched one tile ahead, so that
+    // their round trip through L2 runs under the previous tile's copies instead of in front of this tile's first one
+    int ar_q[4], lr_q[4], a_first = 0;
+    auto fetch_rows = [&](int jj) {
+      const int64_t mm0 = (int64_t)tile_of(jj) * 128;
+      a_first = __ldg(p.am_row + mm0);  // row m0 < M: the tile is live
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t m = mm0 + lane + 32 * q;
+        ar_q[q] = m < p.M ? __ldg(p.am_row + m) : -1;
+        lr_q[q] = m < p.M ? __ldg(p.lm_row + m) : 0;
+      }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch_rows(blockIdx.x);
     for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
-      const int64_t m0 = (int64_t)tile_of(j) * 128;
-      // the stage of the tile's first step must be free before the plan slot of two tiles ago is overwritten
+      // the stage of the tile's first step must be free before a plan slot is overwritten (four slots, the planner
+      // is at most kRawStages steps ahead of the producers)
       mbar_wait(&raw_empty[g % kRawStages], ((g / kRawStages) & 1) ^ 1);
       int am_lo = INT_MAX, am_hi = -1, lo0 = INT_MAX, hi0 = -1, lo1 = INT_MAX, hi1 = -1, bad = 0;
-      const int a_first = __ldg(p.am_row + m0);  // row m0 < M: the tile is live
       const int b0 = a_first / p.T;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int64_t m = m0 + lane + 32 * q;
-        if (m < p.M) {
-          const int ar = __ldg(p.am_row + m), lr = __ldg(p.lm_row + m);
+        if (ar_q[q] >= 0) {
+          const int ar = ar_q[q], lr = lr_q[q];
           am_lo = min(am_lo, ar);
           am_hi = max(am_hi, ar);
           const int seg = ar / p.T - b0;
@@ -1158,6 +1232,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
           }
         }
       }
+      if (j + (int)gridDim.x < n_tiles) fetch_rows(j + gridDim.x);  // next tile's indices: in flight during this tile's steps
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         am_lo = min(am_lo, __shfl_xor_sync(0xffffffffu, am_lo, o));
@@ -1169,10 +1244,28 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         bad |= __shfl_xor_sync(0xffffffffu, bad, o);
       }
       const int n_am = am_hi - am_lo + 1, n0 = hi0 >= lo0 ? hi0 - lo0 + 1 : 0, n1 = hi1 >= lo1 ? hi1 - lo1 + 1 : 0;
-      const bool fast = aligned && !bad && n_am + n0 + n1 <= kRawRows;
+      const bool fast = aligned && p.maps_ok && !bad && n_am + n0 + n1 <= kRawRows;
       if (lane == 0) plans[lt & 3] = TilePlan{fast ? 1 : 0, am_lo, n_am, b0, lo0, n0, lo1, n1};
       __syncwarp();
       const int n_rows = n_am + n0 + n1;
+      // this lane's tensor copy of every step: lanes 0..5 the set bits of n_am (32, 16, .. 1 rows), lanes 6..11 those of
+      // n0, lanes 12..17 those of n1; a box of 2^bit rows sits behind the boxes of the higher bits of its segment
+      int my_h = 0, my_bit = 0, my_row = 0, my_slot = 0;
+      bool my_lm = false;
+      if (fast && lane < 3 * kRawBoxes) {
+        const int seg = lane / kRawBoxes;
+        my_bit = kRawBoxes - 1 - lane % kRawBoxes;
+        const int n = seg == 0 ? n_am : (seg == 1 ? n0 : n1);
+        const int first = seg == 0 ? am_lo : (seg == 1 ? lo0 : lo1);
+        const int slot0 = seg == 0 ? 0 : (seg == 1 ? n_am : n_am + n0);
+        if (n & (1 << my_bit)) {
+          const int before = (n >> (my_bit + 1)) << (my_bit + 1);  // rows covered by the higher bits
+          my_h = 1 << my_bit;
+          my_row = first + before;
+          my_slot = slot0 + before;
+          my_lm = seg != 0;
+        }
+      }
       for (int ks = 0; ks < p.kbV; ++ks, ++g) {
         const int s = g % kRawStages;
         if (ks > 0) mbar_wait(&raw_empty[s], ((g / kRawStages) & 1) ^ 1);
@@ -1180,18 +1273,14 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
           if (lane == 0) mbar_arrive(&raw_full[s]);
           continue;
         }
-        const int cols = min(kBlockK, p.V - ks * kBlockK);
-        const uint32_t row_bytes = (uint32_t)cols * 4;
-        if (lane == 0) mbar_arrive_expect_tx(&raw_full[s], row_bytes * (uint32_t)n_rows);
+        // a box arrives whole (columns beyond V as zeros): 256 bytes per row whatever the step
+        if (lane == 0) mbar_arrive_expect_tx(&raw_full[s], (uint32_t)kRawRowBytes * (uint32_t)n_rows);
         __syncwarp();
         uint8_t* dst0 = raw + s * kRawBytes;
-        for (int i = lane; i < n_rows; i += 32) {
-          const float* src;
-          if (i < n_am) src = p.am + (int64_t)(am_lo + i) * p.V;
-          else if (i - n_am < n0) src = p.lm + (int64_t)(lo0 + i - n_am) * p.V;
-          else src = p.lm + (int64_t)(lo1 + i - n_am - n0) * p.V;
-          bulk_copy_g2s(dst0 + i * kRawRowBytes, src + ks * kBlockK, row_bytes, &raw_full[s]);
-        }
+        if (lane == 0) S2T_FUSED_MARK(7, (int)g);
+        if (my_h > 0)
+          tma_load_2d(dst0 + my_slot * kRawRowBytes, my_lm ? (const void*)&maps.lm[my_bit] : (const void*)&maps.am[my_bit],
+                      ks * kBlockK, my_row, &raw_full[s]);
       }
     }
   } else if (warp == 1) {
@@ -1230,6 +1319,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
               progressed = true;
               if (++kb2 == 4) {
                 umma_commit(&acc2_full[buf]);
+                S2T_FUSED_MARK(10, (int)nt);
                 kb2 = 0;
                 ++nt;
                 acc2_ready = false;
@@ -1254,10 +1344,12 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
               umma_bf16(tmem_base, umma_smem_desc(sa + k4 * kUmmaK * 2), umma_smem_desc(sb + k4 * kUmmaK * 2), idesc1,
                         k1 > 0 || k4 > 0);
             umma_commit(&empty1[s]);
+            S2T_FUSED_MARK(3, (int)g1);
             ++g1;
             progressed = true;
             if (++k1 == p.kbV) {
               umma_commit(acc1_full);
+              S2T_FUSED_MARK(4, t1);
               k1 = 0;
               ++t1;
               acc1_ready = false;
@@ -1283,6 +1375,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
       const bool live = m < p.M;
       // hidden rows: TMEM -> + b1 -> bf16 -> shared-memory operand image (+ Hp)
       mbar_wait(acc1_full, lt & 1);
+      if (warp == kCtrlWarps && lane == 0) S2T_FUSED_MARK(5, (int)lt);
       tc_fence_after();
       mbar_wait(h_empty, (lt & 1) ^ 1);
 #pragma unroll 1
@@ -1317,6 +1410,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
       if (lane == 0) {
         mbar_arrive(acc1_empty);
         mbar_arrive(h_full);
+        if (warp == kCtrlWarps && lane == 0) S2T_FUSED_MARK(6, (int)lt);
       }
       // logits: running (max, sum exp) over the vocabulary tiles + the sym / blank gather
       float mx = kNegInf, sum = 0.f, sym_logit = 0.f, blank_logit = 0.f;
@@ -1331,6 +1425,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps; also orders the reuse two tiles on
         mbar_wait(&acc2_full[buf], (nt >> 1) & 1);
+        if (warp == kCtrlWarps && lane == 0) S2T_FUSED_MARK(11, (int)nt);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
@@ -1375,6 +1470,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc2_empty[buf]);
+        if (warp == kCtrlWarps && lane == 0) S2T_FUSED_MARK(12, (int)nt);
       }
       if (live) {
         const int64_t bt = m / p.R;
@@ -1402,11 +1498,23 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     const int pw = warp - kCtrlWarps - kEpiWarps;
     const int c = lane & 15, rbase = (pw * 2 + (lane >> 4)) * 8;
     uint32_t g = 0, graw = 0, lt = 0;
+    // this thread's eight (am row, lm row) pairs, fetched one tile ahead like the planner's
+    int ar_n[8], lr_n[8];
+    auto fetch_rows = [&](int jj) {
+      const int64_t mm0 = (int64_t)tile_of(jj) * 128 + rbase;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ar_n[i] = mm0 + i < p.M ? __ldg(p.am_row + mm0 + i) : -1;
+        lr_n[i] = mm0 + i < p.M ? __ldg(p.lm_row + mm0 + i) : 0;
+      }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch_rows(blockIdx.x);
     for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
       const int tile = tile_of(j);
       mbar_wait(&raw_full[graw % kRawStages], (graw / kRawStages) & 1);  // also publishes the tile's plan
       const TilePlan plan = plans[lt & 3];
       if (!plan.fast) {
+        if (j + (int)gridDim.x < n_tiles) fetch_rows(j + gridDim.x);
         // the raw ring carries nothing for this tile: hand its stages straight back, then load directly
         for (int ks = 0; ks < p.kbV; ++ks, ++graw) {
           if (ks > 0) mbar_wait(&raw_full[graw % kRawStages], (graw / kRawStages) & 1);
@@ -1434,19 +1542,20 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
       int a_off[8], l_off[8];  // byte offsets of the row's staged am / lm row inside a raw stage; -1: dead row
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int64_t m = (int64_t)tile * 128 + rbase + i;
         a_off[i] = -1;
         l_off[i] = 0;
-        if (m < p.M) {
-          const int ar = __ldg(p.am_row + m), lr = __ldg(p.lm_row + m);
+        if (ar_n[i] >= 0) {
+          const int ar = ar_n[i], lr = lr_n[i];
           a_off[i] = (ar - plan.am_first) * kRawRowBytes + c * 16;
           const int slot = (ar / p.T == plan.b0) ? lr - plan.lo0 : plan.n0 + lr - plan.lo1;
           l_off[i] = (plan.n_am + slot) * kRawRowBytes + c * 16;
         }
       }
+      if (j + (int)gridDim.x < n_tiles) fetch_rows(j + gridDim.x);  // in flight during this tile's steps
       for (int ks = 0; ks < p.kbV; ++ks, ++g, ++graw) {
         const int sr = graw % kRawStages;
         if (ks > 0) mbar_wait(&raw_full[sr], (graw / kRawStages) & 1);
+        if (pw == 0 && lane == 0) S2T_FUSED_MARK(8, (int)graw);
         const uint8_t* rs = raw + sr * kRawBytes;
         const int v = ks * kBlockK + c * 4;
         uint2 o[8];
@@ -1485,6 +1594,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full1[s1]);
+        if (pw == 0 && lane == 0) S2T_FUSED_MARK(9, (int)g);
       }
     }
   }
@@ -1493,7 +1603,10 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-int launch_joiner_fwd_fused(const FusedFwdParams& p, cudaStream_t stream) {
+int launch_joiner_fwd_fused(FusedFwdParams p, int64_t am_rows, int64_t lm_rows, cudaStream_t stream) {
+  RawMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.maps_ok = encode_row_boxes(p.am, am_rows, p.V, maps.am) && encode_row_boxes(p.lm, lm_rows, p.V, maps.lm) ? 1 : 0;
   static bool configured[2][kMaxDevices] = {};
   const bool relu = p.act == kRelu;
   if (int rc = relu ? configure_smem_once(joiner_fwd_fused_kernel<kRelu>, kFSmemBytes, configured[0], "tc_joiner_fwd_fused")
@@ -1502,9 +1615,13 @@ int launch_joiner_fwd_fused(const FusedFwdParams& p, cudaStream_t stream) {
   const int sms = device_info().sms;
   // upper bound of the live tiles (the exact count lives on the device): CTAs beyond it find no tile and leave
   const int grid = p.Mt < sms ? p.Mt : sms;
+  tc::MnDebug trace_mn;
+  tc::TraceScope trace_scope("tc_joiner_fwd_fused", stream, trace_mn);
+  p.trace = trace_mn.trace;
   ProfScope prof("tc_joiner_fwd_fused", stream);
-  const cudaError_t e = relu ? tc::launch_pdl(joiner_fwd_fused_kernel<kRelu>, (unsigned)grid, kFThreads, kFSmemBytes, stream, 1, p)
-                             : tc::launch_pdl(joiner_fwd_fused_kernel<kTanh>, (unsigned)grid, kFThreads, kFSmemBytes, stream, 1, p);
+  const cudaError_t e =
+      relu ? tc::launch_pdl(joiner_fwd_fused_kernel<kRelu>, (unsigned)grid, kFThreads, kFSmemBytes, stream, 1, p, maps)
+           : tc::launch_pdl(joiner_fwd_fused_kernel<kTanh>, (unsigned)grid, kFThreads, kFSmemBytes, stream, 1, p, maps);
   if (e != cudaSuccess) {
     set_error("tc_joiner_fwd_fused: launch: %s", cudaGetErrorString(e));
     return 2;
@@ -1558,7 +1675,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
     FusedFwdParams fp{p.am, p.lm, w.am_row, w.lm_row, w.row_sym, w.W1p, w.W2p, p.b1, p.b2, w.Hp, w.Jp, w.live_idx,
                       w.live_prefix, p.boundary, lse, px, py, M, d.Mt, p.V, p.I, d.kbV, d.Vp / 128, d.Vp / 128, p.act,
                       p.blank, p.T, p.R, p.delay_penalty};
-    return launch_joiner_fwd_fused(fp, stream);
+    return launch_joiner_fwd_fused(fp, (int64_t)p.B * p.T, (int64_t)p.B * (p.S + 1), stream);
   }
   // hidden: M x Ip, K = V.  With J kept for the backward pass it is written once by a fully parallel kernel and the
   // contraction streams it like any packed operand; otherwise the producer warps build it on the fly.

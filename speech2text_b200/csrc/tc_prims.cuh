@@ -134,6 +134,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 2-D tiled tensor copy global -> shared through a CUtensorMap (cuTensorMapEncodeTiled; the map lives in kernel
+// parameter space, __grid_constant__): one instruction moves a box of rows x columns, c0 = first column (innermost
+// dimension), c1 = first row; elements outside the tensor arrive as zeros and still count in the transaction bytes.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
 // same copy delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask of the cluster
 __device__ __forceinline__ void bulk_copy_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                                         uint64_t* bar, uint16_t cta_mask) {
