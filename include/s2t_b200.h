@@ -79,7 +79,7 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
  * px_grad (B,S,T+1), py_grad (B,S+1,T).
  * lm_only_scale / am_only_scale: k2's lm-only / am-only interpolation (JoinerConfig.lm_scale / am_scale);
  * both >= 0, sum < 1; 0 drops the term.
- * mode: S2T_MODE_FP32_SIMT = fp32 FMA contraction; S2T_MODE_BF16_TC = 3xTF32 tensor-core
+ * mode: S2T_MODE_FP32_SIMT = fp32 FMA contraction; S2T_MODE_BF16_TC = 3xF16 tensor-core
  * normaliser (fp32-level accuracy) and bf16 tensor-core backward contractions.
  * workspace: s2t_simple_workspace_bytes(mode,B,T,S,V) bytes.
  * row_max_ready != 0: am_max / lm_max already hold the row maxima of am / lm (by-products of s2t_linear_fwd);
