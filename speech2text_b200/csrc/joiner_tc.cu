@@ -1614,7 +1614,8 @@ int launch_joiner_fwd_fused(FusedFwdParams p, int64_t am_rows, int64_t lm_rows, 
     return rc;
   const int sms = device_info().sms;
   // upper bound of the live tiles (the exact count lives on the device): CTAs beyond it find no tile and leave
-  const int grid = p.Mt < sms ? p.Mt : sms;
+  int grid = p.Mt < sms ? p.Mt : sms;
+  if (const char* e = getenv("S2T_FUSED_GRID")) grid = atoi(e) < grid ? atoi(e) : grid;  // experiment: fewer CTAs
   tc::MnDebug trace_mn;
   tc::TraceScope trace_scope("tc_joiner_fwd_fused", stream, trace_mn);
   p.trace = trace_mn.trace;
