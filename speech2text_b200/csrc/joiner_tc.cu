@@ -992,6 +992,10 @@ int pack_weights(const JoinerProblem& p, const TcDims& d, const TcWs& w, cudaStr
 #else
 #define S2T_FUSED_MARK(code, idx) ((void)0)
 #endif
+#ifndef S2T_W_PIECES
+#define S2T_W_PIECES 1
+#endif
+constexpr int kWPieces = S2T_W_PIECES;             // bulk copies per 16 KB weight block (4 pieces: 0.136 vs 0.134 ms, no gain)
 constexpr int kFS1 = 2;                          // stages of ring 1
 constexpr int kFS2 = 2;                          // stages of ring 2
 constexpr int kFStage1 = 3 * kBlockBytes;        // A (128 x 64) + B (256 x 64)
@@ -1170,7 +1174,13 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
           const int s = g % kFS1;
           mbar_wait(&empty1[s], ((g / kFS1) & 1) ^ 1);
           mbar_arrive_expect_tx(&full1[s], 2 * kBlockBytes);
-          bulk_copy_g2s(ring1 + s * kFStage1 + kBlockBytes, p.W1p + (size_t)ks * 2 * kBlockBytes, 2 * kBlockBytes, &full1[s]);
+          {
+            uint8_t* dst = ring1 + s * kFStage1 + kBlockBytes;
+            const uint8_t* src = p.W1p + (size_t)ks * 2 * kBlockBytes;
+#pragma unroll
+            for (int q = 0; q < kWPieces * 2; ++q)
+              bulk_copy_g2s(dst + q * (kBlockBytes / kWPieces), src + q * (kBlockBytes / kWPieces), kBlockBytes / kWPieces, &full1[s]);
+          }
         }
       }
     }
@@ -1184,8 +1194,13 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
             const int s = g % kFS2;
             mbar_wait(&empty2[s], ((g / kFS2) & 1) ^ 1);
             mbar_arrive_expect_tx(&full2[s], kBlockBytes);
-            bulk_copy_g2s(ring2 + s * kBlockBytes, p.W2p + packed_block_index(n, kb, p.w2_row_blocks) * kBlockBytes, kBlockBytes,
-                          &full2[s]);
+            {
+              uint8_t* dst = ring2 + s * kBlockBytes;
+              const uint8_t* src = p.W2p + packed_block_index(n, kb, p.w2_row_blocks) * kBlockBytes;
+#pragma unroll
+              for (int q = 0; q < kWPieces; ++q)
+                bulk_copy_g2s(dst + q * (kBlockBytes / kWPieces), src + q * (kBlockBytes / kWPieces), kBlockBytes / kWPieces, &full2[s]);
+            }
           }
         }
       }
