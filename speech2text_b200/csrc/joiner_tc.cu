@@ -16,6 +16,9 @@
 // TODO(perf): chain logits -> G -> dhidden inside one kernel so G stays in smem.
 #include <stdlib.h>
 #include <limits.h>
+#include <mutex>
+#include <unordered_map>
+#include <deque>
 #include "joiner.cuh"
 #include "tc_gemm.cuh"
 
@@ -863,6 +866,7 @@ struct TcDims {
   int n_parts_v;   // LSE partials per row
   int64_t chunk;   // rows per backward chunk (multiple of 128)
   bool keep_joint; // keep act(am + lm[ranges]) as a bf16 operand from forward to backward
+  bool dead_skip;  // row tiles of padding frames are skipped (their blocks are never written nor read)
 };
 
 TcDims tc_dims(int64_t M, int V, int I) {
@@ -888,7 +892,43 @@ TcDims tc_dims(int64_t M, int V, int I) {
   // Jp is kept while it fits an eighth of the device memory (22 GB of a B200's 180 GB: c5's 13 GB fits); beyond that
   // the hidden and dW1 contractions rebuild it on the fly in their producer warps
   d.keep_joint = (size_t)d.Mt * (d.Vp / 64) * kBlockBytes <= jp_budget && !getenv("S2T_B200_NO_KEEP_JOINT");
+  d.dead_skip = d.keep_joint && !getenv("S2T_B200_NO_DEAD_SKIP");  // producer-fed paths touch every row
   return d;
+}
+
+// The layout a forward call carved into a workspace, remembered by workspace address: the backward call of the same
+// step reads it back instead of re-deriving it from the environment (the row-chunk and keep-J test hooks) and the
+// current device, so a change of either between the two calls cannot make them disagree about where things are.
+class LayoutMemo {
+ public:
+  void put(const void* ws, const TcDims& d) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!map_.count(ws)) {
+      order_.push_back(ws);
+      if (order_.size() > kCap) {
+        map_.erase(order_.front());
+        order_.pop_front();
+      }
+    }
+    map_[ws] = d;
+  }
+  bool get(const void* ws, int64_t M, TcDims* out) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = map_.find(ws);
+    if (it == map_.end() || it->second.M != M) return false;
+    *out = it->second;
+    return true;
+  }
+
+ private:
+  static constexpr size_t kCap = 64;
+  std::mutex mu_;
+  std::unordered_map<const void*, TcDims> map_;
+  std::deque<const void*> order_;
+};
+LayoutMemo& layout_memo() {
+  static LayoutMemo m;
+  return m;
 }
 
 struct TcWs {
@@ -936,7 +976,7 @@ TcWs tc_carve(void* ws, const TcDims& d) {
   w.tile_live = (uint8_t*)take((size_t)d.Mt);
   w.live_idx = (int*)take((size_t)d.Mt * sizeof(int));
   w.live_prefix = (int*)take((size_t)(d.Mt + 1) * sizeof(int));
-  if (!d.keep_joint || getenv("S2T_B200_NO_DEAD_SKIP")) {  // producer-fed paths touch every row
+  if (!d.dead_skip) {
     w.tile_live = nullptr;
     w.live_idx = w.live_prefix = nullptr;
   }
@@ -1664,6 +1704,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   const int64_t M = (int64_t)p.B * p.T * p.R;
   if (M == 0) return 0;
   TcDims d = tc_dims(M, p.V, p.I);
+  layout_memo().put(workspace, d);
   TcWs w = tc_carve(workspace, d);
   ForkJoin fj(stream);
   if (w.tile_live) {
@@ -1744,6 +1785,10 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
   const int64_t M = (int64_t)p.B * p.T * p.R;
   if (M == 0) return 0;
   TcDims d = tc_dims(M, p.V, p.I);
+  {
+    TcDims fwd;  // what the forward call of this workspace used
+    if (layout_memo().get(workspace, M, &fwd) && fwd.Vp == d.Vp && fwd.Ip == d.Ip) d = fwd;
+  }
   TcWs w = tc_carve(workspace, d);
   const int sms = device_info().sms;
   for (int64_t row0 = 0; row0 < (int64_t)d.Mt * 128; row0 += d.chunk) {

@@ -1043,3 +1043,45 @@ def test_simple_loss_gradient_issued_next_to_the_band_lattice(mode, monkeypatch)
                 # tensor-core mode rounds coef * W to bf16: a different coef is a different (equally good) rounding
                 assert rel_err(b[k], a[k]) < (1e-2 if mode == "bf16" else 1e-6), (i, k, rel_err(b[k], a[k]))
     assert all(float(v.abs().min()) > 0 for v in F2._PRED.values())
+
+
+def test_backward_uses_the_layout_its_forward_carved(monkeypatch):
+    """The workspace layout (backward row chunks, kept J, skipped padding tiles) depends on test hooks read from the
+    environment; the backward call takes what ITS forward call used (remembered by workspace address) even if the
+    environment changed in between."""
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.loss.loss import Loss
+    B, T, U, V, D, R, I = 3, 120, 30, 300, 64, 5, 256
+    g = torch.Generator().manual_seed(21)
+    enc0 = torch.randn(B, T, D, generator=g) * 0.7
+    pred0 = torch.randn(B, U + 1, D, generator=g) * 0.7
+    tgt = torch.randint(1, V, (B, U), generator=g).to(_dev())
+    t_len = torch.tensor([T, T - 31, T - 50]).to(_dev())
+    s_len = torch.tensor([U, U - 5, U - 12]).to(_dev())
+    torch.manual_seed(3)
+    joiner = Joiner(JoinerConfig(input_dim=D, output_dim=V, inner_dim=I, activation="tanh", prune_range=R)).to(_dev())
+    loss_mod = Loss({"model": "Pruned_Rnnt", "config": {"termination_symbol": 0, "reduction": "mean"}})
+    monkeypatch.setenv("S2T_B200_FUSED", "1")
+    monkeypatch.setenv("S2T_B200_JOINER_MODE", "bf16")
+
+    def run(switch_env):
+        joiner.zero_grad(set_to_none=True)
+        monkeypatch.setenv("S2T_B200_CHUNK_ROWS", "256")
+        monkeypatch.setenv("S2T_B200_NO_KEEP_JOINT", "1")
+        enc = enc0.to(_dev()).requires_grad_(True)
+        pred = pred0.to(_dev()).requires_grad_(True)
+        logits, boundary, ranges, simple = joiner(enc, t_len, pred, s_len, tgt)
+        pruned = loss_mod({"logits": logits, "logits_length": t_len, "targets": tgt, "targets_length": s_len,
+                           "boundary": boundary, "ranges": ranges})
+        if switch_env:
+            monkeypatch.delenv("S2T_B200_CHUNK_ROWS")
+            monkeypatch.delenv("S2T_B200_NO_KEEP_JOINT")
+        (0.5 * simple + 0.5 * pruned).backward()
+        torch.cuda.synchronize()
+        return dict(d_enc=enc.grad.clone(), d_pred=pred.grad.clone(),
+                    **{"d" + k: p.grad.clone() for k, p in joiner.named_parameters()})
+
+    a, b = run(False), run(True)
+    for k in a:
+        assert torch.isfinite(b[k]).all(), k
+        assert rel_err(b[k], a[k]) < 1e-5, (k, rel_err(b[k], a[k]))
