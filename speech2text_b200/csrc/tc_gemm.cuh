@@ -133,9 +133,11 @@ constexpr int gemm_threads() {
 // kKind: 0 = bf16 operands; 1 = tf32 (fp32 in smem, single pass); 2 = 3xTF32: every fp32 operand is held
 // as big = rn_tf32(x) and small = x - big, and D += A_big B_big + A_big B_small + A_small B_big, which
 // recovers fp32-level accuracy (error ~2^-21) on the tensor cores.
+// kKind 5 = 2xF16: as 3xF16 but the A operand is EXACT in f16 (bf16 activations inside the f16 range: 8 mantissa bits fit
+// the 11 of a half) and carries no lo part: D += A B_lo + A B_hi -- two MMAs per product instead of three, half the A stage.
 template <int BN, int kKind>
 constexpr int gemm_stage_bytes() {
-  return (kKind >= 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
+  return kKind == 5 ? kBlockBytes + 2 * (BN / 128) * kBlockBytes : (kKind >= 2 ? 2 : 1) * (kBlockBytes + (BN / 128) * kBlockBytes);
 }
 // kBRes > 0: the B operand of the CTA's column tile (kBRes k-steps) stays resident in shared memory and the ring
 // carries A stages only
@@ -258,7 +260,7 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   static_assert(kBRes == 0 || (!kMn && kKind == 0 && ASrc::kBulk && kCluster == 1),
                 "B-stationary mode: K-major bf16, bulk-fed, no cluster");
   constexpr int kParts = kKind >= 2 ? 2 : 1;
-  constexpr int kABytes = kParts * kBlockBytes;
+  constexpr int kABytes = (kKind == 5 ? 1 : kParts) * kBlockBytes;
   constexpr int kBPart = (BN / 128) * kBlockBytes / kCluster;  // this CTA's rows of one B part
   constexpr int kBBytes = kParts * kBPart;
   constexpr int kStageBytes = kBRes > 0 ? kABytes : kABytes + kBBytes;
@@ -442,7 +444,8 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
       }
     } else if (lane == 0) {
       constexpr int kM = 128 * kCluster;
-      uint32_t idesc = kKind == 0 ? umma_idesc_bf16(kM, BN) : (kKind == 3 ? umma_idesc_f16(kM, BN) : umma_idesc_tf32(kM, BN));
+      uint32_t idesc = kKind == 0 ? umma_idesc_bf16(kM, BN)
+                                  : ((kKind == 3 || kKind == 5) ? umma_idesc_f16(kM, BN) : umma_idesc_tf32(kM, BN));
       if (kMn) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       auto mma16 = [](uint32_t acc, uint64_t da, uint64_t db, uint32_t id, bool accum) {
         if constexpr (kCluster == 1) umma_bf16(acc, da, db, id, accum);
@@ -497,6 +500,10 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
               const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
               mma16(acc, da_s, db, idesc, accum);  // small terms first
               mma16(acc, da, db_s, idesc, true);
+              mma16(acc, da, db, idesc, true);
+            } else if constexpr (kKind == 5) {
+              const uint64_t db_s = umma_smem_desc(sb + kBPart + k4 * kUmmaK * 2);
+              mma16(acc, da, db_s, idesc, accum);  // small term first
               mma16(acc, da, db, idesc, true);
             } else {
               const uint64_t da_s = umma_smem_desc(sa + kBlockBytes + k4 * kUmmaK * 2);
@@ -1078,7 +1085,7 @@ struct RowCopyProducerF32 {
 // 2w + l/16 + 16 i, i = 0..7.  Optional by-product: the bf16 packed image of x (same block geometry).
 // TX = float or __nv_bfloat16 (BASELINE config 3's "bf16 joiner": the activations arrive as bf16 and are read as such --
 // half the bytes, and the packed bf16 image kept for the weight gradient is then exact).
-template <typename TX>
+template <typename TX, bool kLo = true>
 struct RowSplitProducerF16T {
   static constexpr bool kBulk = false;
   const TX* x;
@@ -1131,11 +1138,19 @@ struct RowSplitProducerF16T {
       for (int j = 0; j < 8; ++j) {
         float v[4];
         unpack(src[j], v);
-        uint2 hi, lo;
-        split_f16x4(v, hi, lo);
         const int ro = j * 16 * 128;
-        *reinterpret_cast<uint2*>(dst + ro) = hi;
-        *reinterpret_cast<uint2*>(dst + kBlockBytes + ro) = lo;
+        if constexpr (kLo) {
+          uint2 hi, lo;
+          split_f16x4(v, hi, lo);
+          *reinterpret_cast<uint2*>(dst + ro) = hi;
+          *reinterpret_cast<uint2*>(dst + kBlockBytes + ro) = lo;
+        } else {
+          // exact for bf16 inputs inside the f16 range (clamped like the split path); no residual part
+          const __half2 h01 = __floats2half2_rn(fminf(fmaxf(v[0], -65504.f), 65504.f), fminf(fmaxf(v[1], -65504.f), 65504.f));
+          const __half2 h23 = __floats2half2_rn(fminf(fmaxf(v[2], -65504.f), 65504.f), fminf(fmaxf(v[3], -65504.f), 65504.f));
+          *reinterpret_cast<uint2*>(dst + ro) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        }
         if (emit) *reinterpret_cast<uint2*>(blk + ro) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
       }
     };
