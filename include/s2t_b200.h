@@ -165,6 +165,10 @@ int s2t_band_lattice_fwd(const float* px, const float* py, const int64_t* ranges
                          int S, int T, int R, void* alpha_ws, float* scores, float* occ_px, float* occ_py,
                          void* stream);
 
+/* out[0] = sum_i x[i] * w[i], n <= 1024: the loss reduction (-mean / -sum of the per-utterance scores, with a constant
+ * weight vector) as one launch. */
+int s2t_weighted_sum(const float* x, const float* w, int n, float* out, void* stream);
+
 /* x0[g, 0..n0) and x1[g, 0..n1) (either may be NULL) are multiplied by num[g] / den[g] for every group g whose two
  * values differ -- groups with num == den cost no memory traffic -- and den[g] becomes (num[g] != 0 ? num[g] : 1).
  * Used for gradients that were computed ahead of the backward pass with a predicted upstream scale `den`

@@ -46,6 +46,7 @@ _SIGNATURES = {
                                     P, P]),
     "s2t_joiner_logprobs_fwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P]),
     "s2t_band_lattice_fwd": (c_int, [P, P, P, P, I, I, I, I, P, P, P, P, P]),
+    "s2t_weighted_sum": (c_int, [P, P, I, P, P]),
     "s2t_rescale_groups": (c_int, [P, ctypes.c_int64, P, ctypes.c_int64, I, P, P, P]),
     "s2t_joiner_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P,
                                     P, P, P, P, P]),

@@ -167,6 +167,21 @@ __global__ void __launch_bounds__(256) rescale_groups_kernel(float* __restrict__
   }
 }
 
+__global__ void __launch_bounds__(1024) weighted_sum_kernel(const float* __restrict__ x, const float* __restrict__ w, int n,
+                                                            float* __restrict__ out) {
+  __shared__ float red[32];
+  const int i = threadIdx.x;
+  float v = i < n ? x[i] * w[i] : 0.f;
+  v = warp_sum(v);
+  if ((i & 31) == 0) red[i >> 5] = v;
+  __syncthreads();
+  if (i < 32) {
+    v = i < (int)((blockDim.x + 31) >> 5) ? red[i] : 0.f;
+    v = warp_sum(v);
+    if (i == 0) out[0] = v;
+  }
+}
+
 __global__ void rescale_update_kernel(const float* __restrict__ num, float* __restrict__ den, int groups) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < groups) den[g] = num[g] != 0.f ? num[g] : 1.f;
@@ -307,6 +322,13 @@ static bool joiner_uses_tc(int mode, int I) { return mode == S2T_MODE_BF16_TC &&
 size_t s2t_joiner_workspace_bytes(int mode, int B, int T, int R, int V, int I) {
   if (joiner_uses_tc(mode, I)) return joiner_tc_workspace_bytes((int64_t)B * T * R, V, I);
   return joiner_simt_workspace_bytes((int64_t)B * T * R, V, I, nullptr);
+}
+
+int s2t_weighted_sum(const float* x, const float* w, int n, float* out, void* stream) {
+  S2T_REQUIRE(n >= 1 && n <= 1024 && x && w && out, "weighted_sum: n = %d (1..1024)", n);
+  const int threads = ((n + 31) / 32) * 32;
+  weighted_sum_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(x, w, n, out);
+  return check_launch("weighted_sum_kernel");
 }
 
 int s2t_rescale_groups(float* x0, int64_t n0, float* x1, int64_t n1, int groups, const float* num, float* den,

@@ -282,6 +282,24 @@ def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symb
 _REDUCE_WEIGHTS: dict = {}
 
 
+class _ScaledSum(torch.autograd.Function):
+    """sum_b scores[b] * w[b] for a constant weight vector w, in one launch."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, scores: Tensor, w: Tensor):
+        scores = _f32c(scores)
+        out = torch.empty((), dtype=torch.float32, device=scores.device)
+        check(lib().s2t_weighted_sum(ptr(scores), ptr(w), scores.numel(), ptr(out), stream()))
+        ctx.save_for_backward(w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        return g * w, None
+
+
 def _reduce(scores: Tensor, reduction: str) -> Tensor:
     """-scores / -mean / -sum.  mean and sum are ONE dot product with a cached constant vector (-1/B or -1): the
     step is a chain of short kernels, and ``-torch.mean(x)`` is two of them forward and two more backward."""
@@ -295,6 +313,8 @@ def _reduce(scores: Tensor, reduction: str) -> Tensor:
     if w is None:
         w = torch.full((n,), -1.0 / n if reduction == "mean" else -1.0, dtype=scores.dtype, device=scores.device)
         _REDUCE_WEIGHTS[key] = w
+    if scores.is_cuda and scores.dtype == torch.float32 and n <= 1024:
+        return _ScaledSum.apply(scores.reshape(-1), w)  # one launch (cuBLAS' dot is two; a (1 x n) mv dispatches to it too)
     return torch.dot(scores.reshape(-1), w)
 
 
