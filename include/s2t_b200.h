@@ -258,6 +258,17 @@ int s2t_rnnt_greedy_decode(const float* am, const int64_t* lengths, const float*
                            const float* W2, const float* b2, int B, int T, int V, int N, int E, int C, int D, int I, int act,
                            int blank, int max_token_step, int max_out, int64_t* tokens, int* n_tokens, void* stream);
 
+/* Beam search of the same models (RnntBeamDecoding, model/decoding.py:295-425): at most one token per frame, every
+ * beam proposes its top_k classes, the beam best candidates by accumulated log-probability survive (stable order,
+ * hypotheses are not merged).  tokens (B, T) / n_tokens (B): the best hypothesis; best_score (B): its log-probability.
+ * workspace: s2t_rnnt_beam_workspace_bytes(B, T, V, beam).  beam <= 8, top_k <= 8. */
+size_t s2t_rnnt_beam_workspace_bytes(int B, int T, int V, int beam);
+int s2t_rnnt_beam_decode(const float* am, const int64_t* lengths, const float* emb, const float* conv_w, const float* Wo,
+                         const float* bo, const float* Wp, const float* bp, const float* W1, const float* b1,
+                         const float* W2, const float* b2, int B, int T, int V, int N, int E, int C, int D, int I, int act,
+                         int blank, int beam, int top_k, void* workspace, int64_t* tokens, int* n_tokens, float* best_score,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

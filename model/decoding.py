@@ -1,6 +1,7 @@
 """Drop-in for /root/reference/model/decoding.py: everything the reference defines there (CTC decoders, the RNN-T
-beam search, ...) is re-exported from the reference checkout when it is importable; ``RnntGreedyDecoding`` and
-``batch_search`` are the device-resident versions (speech2text_b200.decoding)."""
+lexicon search, ...) is re-exported from the reference checkout when it is importable; ``RnntGreedyDecoding``,
+``RnntBeamDecoding`` and ``batch_search`` are the device-resident versions (speech2text_b200.decoding, SURVEY.md 8
+row f-4), also inside ``DecodingFactory``."""
 import importlib.util as _ilu
 import os as _os
 import sys as _sys
@@ -22,4 +23,11 @@ for _root in list(_roots):
             globals().update({k: v for k, v in vars(_mod).items() if not k.startswith("_")})
         break
 
-from speech2text_b200.decoding import RnntGreedyDecoding, batch_search  # noqa: E402,F401
+from speech2text_b200.decoding import RnntBeamDecoding, RnntGreedyDecoding, batch_search  # noqa: E402,F401
+
+# the reference's factory enum (decoding.py:427-435) holds the classes themselves: rebuild it around the replacements
+import enum as _enum  # noqa: E402
+
+_members = {m.name: m.value for m in globals()["DecodingFactory"]} if "DecodingFactory" in globals() else {}
+_members.update(rnnt_greedy_decoding=RnntGreedyDecoding, rnnt_beam_decoding=RnntBeamDecoding)
+DecodingFactory = _enum.unique(_enum.Enum("DecodingFactory", _members))  # without the reference: the two RNN-T searches

@@ -169,6 +169,8 @@ def run_predictor_case(name):
     return res
 
 
+BEAM_SIZE, BEAM_TOP_K = 4, 4  # RnntBeamDecoding's defaults (model/decoding.py:310-311)
+
 GREEDY_CASES = {
     # (predictor case, joiner config, T per utterance, blank bias): small models with a blank-leaning joiner bias so
     # that the search emits a realistic mix of blanks and symbols
@@ -194,7 +196,8 @@ def make_greedy_case(name):
 
 
 def run_greedy_case(name):
-    """The reference's RnntGreedyDecoding.decode (model/decoding.py:225-271), verbatim, with the reference's Joiner and
+    """The reference's RnntGreedyDecoding.decode (model/decoding.py:225-271) and RnntBeamDecoding.decode (:350-425),
+    verbatim, with the reference's Joiner and
     StatelessPredictor, on seeded weights and encoder outputs.  Its imports of the tokenizer / factory modules are
     satisfied by stubs (they are type annotations there); the tokenizer stub returns the token ids."""
     import importlib.util
@@ -245,10 +248,13 @@ def run_greedy_case(name):
             return [int(x) for x in t.tolist()]
 
     session = dec_mod.RnntGreedyDecoding(Tok(), pred.eval(), joiner.eval())
-    res = {}
+    beam_session = dec_mod.RnntBeamDecoding(Tok(), pred.eval(), joiner.eval(), beam_size=BEAM_SIZE, cutoff_top_k=BEAM_TOP_K)
+    res, beam = {}, {}
     for i, e in enumerate(enc):
         res[f"tokens_{i}"] = np.asarray(session.decode(torch.from_numpy(e)), dtype=np.int64)
-    return res
+        beam[f"tokens_{i}"] = np.asarray(beam_session.decode(torch.from_numpy(e)), dtype=np.int64)
+        beam[f"score_{i}"] = np.asarray(float(beam_session._decoding_state.best_beam.score), dtype=np.float64)
+    return res, beam
 
 
 def main():
@@ -260,9 +266,11 @@ def main():
         np.savez_compressed(path, **res)
         print(f"{name}: output {res['output'].shape} -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name in GREEDY_CASES:
-        res = run_greedy_case(name)
+        res, beam = run_greedy_case(name)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **res)
+        np.savez_compressed(os.path.join(OUT, name.replace("greedy", "beam") + ".npz"), **beam)
         print(f"{name}: " + ", ".join(f"{k}: {len(v)} tokens" for k, v in res.items()))
+        print(f"  beam: " + ", ".join(f"{k}: {v.tolist() if v.ndim == 0 else len(v)}" for k, v in beam.items()))
     joiner_mod, pruned_mod, rnnt_mod = _import_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, spec in CASES.items():

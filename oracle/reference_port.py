@@ -164,6 +164,51 @@ def rnnt_greedy_decode(pw: Dict[str, torch.Tensor], jw: Dict[str, torch.Tensor],
     return out
 
 
+def rnnt_beam_decode(pw: Dict[str, torch.Tensor], jw: Dict[str, torch.Tensor], jcfg: dict, hidden_states,
+                     context_size: int, beam_size: int = 4, cutoff_top_k: int = 4):
+    """RnntBeamDecoding.decode, /root/reference/model/decoding.py:295-425, for ONE utterance (1, T, D) with a stateless
+    predictor: at most one token per frame; every beam proposes its ``cutoff_top_k`` best classes; a blank (class 0)
+    keeps the hypothesis, any other class extends it; the ``beam_size`` best candidates by accumulated log-probability
+    survive (Python's stable sort: ties in order of creation); hypotheses are not merged.  Returns (tokens, score)."""
+    act = _act(jcfg.get("activation", "relu"))
+
+    def pred_step(token, state):
+        ctxed = torch.concat([state, token], dim=1)
+        out_state = ctxed[:, ctxed.shape[1] - context_size + 1:]
+        embs = F.embedding(ctxed, pw["_embedding.weight"]).transpose(1, 2)
+        conv = F.conv1d(embs, pw["_conv.weight"], groups=pw["_conv.weight"].shape[0]).transpose(1, 2)
+        return F.linear(conv, pw["_output_linear.weight"], pw["_output_linear.bias"]), out_state
+
+    def joiner_step(enc, pred):  # (1,1,D), (n,1,D) -> (n, V) log-probs
+        a = F.linear(enc, jw["_enc_proj.weight"], jw["_enc_proj.bias"]).unsqueeze(2)
+        l = F.linear(pred, jw["_pre_proj.weight"], jw["_pre_proj.bias"]).unsqueeze(1)
+        h = act(a + l)
+        if jcfg.get("use_out_project", True):
+            h = F.linear(h, jw["_out_projection.0.weight"], jw["_out_projection.0.bias"])
+            h = F.linear(h, jw["_out_projection.1.weight"], jw["_out_projection.1.bias"])
+        return torch.log_softmax(h, dim=-1).squeeze(1).squeeze(1)
+
+    state = torch.zeros(1, context_size - 1, dtype=torch.int32)
+    pred_out, state = pred_step(torch.zeros(1, 1, dtype=torch.long), state)
+    beams = [dict(tokens=[], blank=True, score=0.0, state=state, pred=pred_out)]
+    for t in range(hidden_states.shape[1]):
+        logp = joiner_step(hidden_states[:, t:t + 1, :], torch.cat([b["pred"] for b in beams], dim=0))
+        new = []
+        for i, b in enumerate(beams):
+            for tok in torch.argsort(logp[i], descending=True).tolist()[:cutoff_top_k]:
+                sc = b["score"] + logp[i][tok]
+                if tok == 0:
+                    new.append(dict(tokens=b["tokens"], blank=True, score=sc, state=b["state"], pred=b["pred"]))
+                else:
+                    new.append(dict(tokens=b["tokens"] + [tok], blank=False, score=sc, state=b["state"], pred=None))
+        beams = sorted(new, key=lambda x: x["score"], reverse=True)[:beam_size]
+        for b in beams:
+            if not b["blank"]:
+                b["pred"], b["state"] = pred_step(torch.tensor([[b["tokens"][-1]]]).long(), b["state"])
+                b["blank"] = True
+    return beams[0]["tokens"], float(beams[0]["score"])
+
+
 def training_step_loss(w, spec: dict, case: dict, dtype=torch.float32, prune_variant=None, ranges_override=None,
                        exact=False):
     """One fwd+bwd of the hot path exactly as rnnt_task.py:469-514 strings it

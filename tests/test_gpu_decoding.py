@@ -111,3 +111,66 @@ def test_other_predictors_take_the_stepwise_path():
     slow = RnntGreedyDecoding(_Tok(), Opaque(session._predictor), session._joiner)
     gold = dict(np.load(os.path.join(GOLDEN, "greedy_plain.npz")))
     assert slow.decode(torch.from_numpy(enc[1]).to(dev)) == gold["tokens_1"].tolist()
+
+
+def _beam_session(name, dev):
+    from model.decoding import RnntBeamDecoding
+    from oracle.make_golden import BEAM_SIZE, BEAM_TOP_K
+    greedy, g, pcfg, pw, jw, enc = _session(name, dev)
+    return RnntBeamDecoding(_Tok(), greedy._predictor, greedy._joiner, beam_size=BEAM_SIZE, cutoff_top_k=BEAM_TOP_K), enc
+
+
+@pytest.mark.parametrize("name", list(GREEDY_CASES))
+def test_batched_beam_search_matches_reference_goldens(name):
+    """The device-resident beam search (one CTA per utterance, one launch per batch) against the hypotheses of the
+    reference's RnntBeamDecoding (/root/reference/model/decoding.py:295-425, run verbatim by oracle/make_golden.py):
+    identical token sequences, log-probabilities of the best hypothesis to 1e-4."""
+    from model.decoding import DecodingFactory, RnntBeamDecoding, batch_search
+    assert DecodingFactory.rnnt_beam_decoding.value is RnntBeamDecoding  # the factory hands out the replacement
+    dev = torch.device("cuda:0")
+    session, enc = _beam_session(name, dev)
+    gold = dict(np.load(os.path.join(GOLDEN, name.replace("greedy", "beam") + ".npz")))
+    T = max(e.shape[1] for e in enc)
+    batch = torch.zeros(len(enc), T, enc[0].shape[2])
+    for i, e in enumerate(enc):
+        batch[i, :e.shape[1]] = torch.from_numpy(e[0])
+    lengths = torch.tensor([e.shape[1] for e in enc])
+    got = batch_search(batch.to(dev), lengths.to(dev), session)
+    for i in range(len(enc)):
+        assert got[i] == gold[f"tokens_{i}"].tolist(), (name, i)
+        ref = float(gold[f"score_{i}"])
+        assert abs(session.best_scores[i] - ref) < 1e-4 * abs(ref), (session.best_scores[i], ref)
+    assert session.decode(torch.from_numpy(enc[0]).to(dev)) == gold["tokens_0"].tolist()
+    # the stepwise path (what an LSTM predictor takes) gives the same hypotheses
+    toks, score = session._beam_stepwise(torch.from_numpy(enc[1]).to(dev))
+    assert toks == gold["tokens_1"].tolist()
+
+
+def test_beam_search_at_size_matches_the_port():
+    """c3-like evaluation shape (V=500, D=512, E=512, I=256, context 5), 6 utterances of up to 100 frames, beam 4."""
+    from model.decoding import RnntBeamDecoding
+    from model.joiner.joiner import Joiner, JoinerConfig
+    from model.predictor.stateless_predictor import StatelessPredictor, StatelessPredictorConfig
+    dev = torch.device("cuda:0")
+    torch.manual_seed(23)
+    V, D, E, I, C = 500, 512, 512, 256, 5
+    pred = StatelessPredictor(StatelessPredictorConfig(num_symbols=V, output_dim=D, symbol_embedding_dim=E, context_size=C))
+    jc = dict(input_dim=D, output_dim=V, inner_dim=I, activation="tanh", prune_range=5)
+    joiner = Joiner(JoinerConfig(**jc))
+    with torch.no_grad():
+        for p in joiner.parameters():
+            p.mul_(6.0)
+        joiner._out_projection[1].bias[0] += 30.0
+    lens = torch.tensor([100, 77, 64, 100, 33, 5])
+    hidden = torch.randn(len(lens), 100, D)
+    pw = {k: v.detach() for k, v in pred.state_dict().items()}
+    jw = {k: v.detach() for k, v in joiner.state_dict().items()}
+    session = RnntBeamDecoding(_Tok(), pred.to(dev).eval(), joiner.to(dev).eval(), beam_size=4, cutoff_top_k=4)
+    got = session.batch_decode_tokens(hidden.to(dev), lens.to(dev))
+    same = 0
+    for i in range(len(lens)):
+        ref, score = port.rnnt_beam_decode(pw, jw, jc, hidden[i:i + 1, :int(lens[i])], C, 4, 4)
+        # the best hypothesis' log-probability agrees even where two hypotheses tie to fp32 rounding and swap places
+        assert abs(session.best_scores[i] - score) < 2e-4 * max(1.0, abs(score)), (i, session.best_scores[i], score)
+        same += got[i] == ref
+    assert same >= len(lens) - 1, f"{same} of {len(lens)} utterances identical"

@@ -184,3 +184,21 @@ def test_greedy_decode_port_matches_reference_goldens(name):
     for i, e in enumerate(enc):
         got = port.rnnt_greedy_decode(pw, jw, g["joiner"], torch.from_numpy(e), pcfg["context_size"])
         assert got == gold[f"tokens_{i}"].tolist(), (name, i)
+
+
+@pytest.mark.parametrize("name", ["greedy_outproj", "greedy_plain"])
+def test_beam_decode_port_matches_reference_goldens(name):
+    """oracle.reference_port.rnnt_beam_decode against the hypotheses (and their log-probabilities) the reference's
+    RnntBeamDecoding produced (verbatim run, beam 4, top-k 4, oracle/make_golden.py::run_greedy_case)."""
+    import os
+    from conftest import GOLDEN
+    from oracle.make_golden import BEAM_SIZE, BEAM_TOP_K, make_greedy_case
+    gold = dict(np.load(os.path.join(GOLDEN, name.replace("greedy", "beam") + ".npz")))
+    g, pcfg, pw, jw, enc = make_greedy_case(name)
+    pw = {k: torch.from_numpy(v) for k, v in pw.items()}
+    jw = {k: torch.from_numpy(v) for k, v in jw.items()}
+    for i, e in enumerate(enc):
+        toks, score = port.rnnt_beam_decode(pw, jw, g["joiner"], torch.from_numpy(e), pcfg["context_size"], BEAM_SIZE,
+                                            BEAM_TOP_K)
+        assert toks == gold[f"tokens_{i}"].tolist(), (name, i)
+        assert abs(score - float(gold[f"score_{i}"])) < 1e-4 * abs(float(gold[f"score_{i}"]))
