@@ -1135,6 +1135,7 @@ struct FusedFwdParams {
   int Mt, V, I, kbV, nN, w2_row_blocks, act, blank, T, R;
   float delay_penalty;
   int maps_ok = 0;  // RawMaps describe am / lm (set by the launcher): the raw ring is fed by tensor copies
+  int raw_stages = kRawStages, raw_rows = kRawRows;  // the ring's 126 row slots as 3 x 42 (pruned bands) or 2 x 63 (wide bands)
   unsigned long long* trace = nullptr;  // S2T_TRACE=tc_joiner_fwd_fused: role timeline of CTA 0
 };
 
@@ -1204,6 +1205,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int raw_stages = p.raw_stages, raw_bytes = p.raw_rows * kRawRowBytes;
 
   if (warp == 0) {
     // ---- W1 steps into ring 1 ----
@@ -1266,7 +1268,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
       // the stage of the tile's first step must be free before a plan slot is overwritten (four slots, the planner
       // is at most kRawStages steps ahead of the producers)
-      mbar_wait(&raw_empty[g % kRawStages], ((g / kRawStages) & 1) ^ 1);
+      mbar_wait(&raw_empty[g % raw_stages], ((g / raw_stages) & 1) ^ 1);
       int am_lo = INT_MAX, am_hi = -1, lo0 = INT_MAX, hi0 = -1, lo1 = INT_MAX, hi1 = -1, bad = 0;
       const int b0 = a_first / p.T;
 #pragma unroll
@@ -1299,7 +1301,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         bad |= __shfl_xor_sync(0xffffffffu, bad, o);
       }
       const int n_am = am_hi - am_lo + 1, n0 = hi0 >= lo0 ? hi0 - lo0 + 1 : 0, n1 = hi1 >= lo1 ? hi1 - lo1 + 1 : 0;
-      const bool fast = aligned && p.maps_ok && !bad && n_am + n0 + n1 <= kRawRows;
+      const bool fast = aligned && p.maps_ok && !bad && n_am + n0 + n1 <= p.raw_rows;
       if (lane == 0) plans[lt & 3] = TilePlan{fast ? 1 : 0, am_lo, n_am, b0, lo0, n0, lo1, n1};
       __syncwarp();
       const int n_rows = n_am + n0 + n1;
@@ -1322,8 +1324,8 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         }
       }
       for (int ks = 0; ks < p.kbV; ++ks, ++g) {
-        const int s = g % kRawStages;
-        if (ks > 0) mbar_wait(&raw_empty[s], ((g / kRawStages) & 1) ^ 1);
+        const int s = g % raw_stages;
+        if (ks > 0) mbar_wait(&raw_empty[s], ((g / raw_stages) & 1) ^ 1);
         if (!fast) {
           if (lane == 0) mbar_arrive(&raw_full[s]);
           continue;
@@ -1331,7 +1333,7 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
         // a box arrives whole (columns beyond V as zeros): 256 bytes per row whatever the step
         if (lane == 0) mbar_arrive_expect_tx(&raw_full[s], (uint32_t)kRawRowBytes * (uint32_t)n_rows);
         __syncwarp();
-        uint8_t* dst0 = raw + s * kRawBytes;
+        uint8_t* dst0 = raw + s * raw_bytes;
         if (lane == 0) S2T_FUSED_MARK(7, (int)g);
         if (my_h > 0)
           tma_load_2d(dst0 + my_slot * kRawRowBytes, my_lm ? (const void*)&maps.lm[my_bit] : (const void*)&maps.am[my_bit],
@@ -1566,15 +1568,15 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
     if ((int)blockIdx.x < n_tiles) fetch_rows(blockIdx.x);
     for (int j = blockIdx.x; j < n_tiles; j += gridDim.x, ++lt) {
       const int tile = tile_of(j);
-      mbar_wait(&raw_full[graw % kRawStages], (graw / kRawStages) & 1);  // also publishes the tile's plan
+      mbar_wait(&raw_full[graw % raw_stages], (graw / raw_stages) & 1);  // also publishes the tile's plan
       const TilePlan plan = plans[lt & 3];
       if (!plan.fast) {
         if (j + (int)gridDim.x < n_tiles) fetch_rows(j + gridDim.x);
         // the raw ring carries nothing for this tile: hand its stages straight back, then load directly
         for (int ks = 0; ks < p.kbV; ++ks, ++graw) {
-          if (ks > 0) mbar_wait(&raw_full[graw % kRawStages], (graw / kRawStages) & 1);
+          if (ks > 0) mbar_wait(&raw_full[graw % raw_stages], (graw / raw_stages) & 1);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&raw_empty[graw % kRawStages]);
+          if (lane == 0) mbar_arrive(&raw_empty[graw % raw_stages]);
         }
         ProdCtx pc;
         pc.m_tile = tile;
@@ -1608,10 +1610,10 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
       }
       if (j + (int)gridDim.x < n_tiles) fetch_rows(j + gridDim.x);  // in flight during this tile's steps
       for (int ks = 0; ks < p.kbV; ++ks, ++g, ++graw) {
-        const int sr = graw % kRawStages;
-        if (ks > 0) mbar_wait(&raw_full[sr], (graw / kRawStages) & 1);
+        const int sr = graw % raw_stages;
+        if (ks > 0) mbar_wait(&raw_full[sr], (graw / raw_stages) & 1);
         if (pw == 0 && lane == 0) S2T_FUSED_MARK(8, (int)graw);
-        const uint8_t* rs = raw + sr * kRawBytes;
+        const uint8_t* rs = raw + sr * raw_bytes;
         const int v = ks * kBlockK + c * 4;
         uint2 o[8];
 #pragma unroll
@@ -1661,6 +1663,10 @@ __global__ void __launch_bounds__(kFThreads, 1) joiner_fwd_fused_kernel(const Fu
 int launch_joiner_fwd_fused(FusedFwdParams p, int64_t am_rows, int64_t lm_rows, cudaStream_t stream) {
   RawMaps maps;
   memset(&maps, 0, sizeof(maps));
+  if (p.R > 8) {  // wide bands (the unpruned lattice: R = S + 1 rows per frame share one am row and need R lm rows)
+    p.raw_stages = 2;
+    p.raw_rows = kRawStages * kRawRows / 2;
+  }
   p.maps_ok = encode_row_boxes(p.am, am_rows, p.V, maps.am) && encode_row_boxes(p.lm, lm_rows, p.V, maps.lm) ? 1 : 0;
   static bool configured[2][kMaxDevices] = {};
   const bool relu = p.act == kRelu;
