@@ -744,6 +744,81 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
             reduce_frame(fb, i + 1);
           }
         }
+      } else if (kVec && ranges == nullptr && (w_hi - w_lo + 1) % kRB == 0 && w_hi <= S && (bt0 + t0) * R >= row0 &&
+                 (bt0 + t1) * R <= row_end) {
+        // Wide band without pruning (R = S + 1, every frame holds every symbol position): the window's slots are the
+        // same kRB-row blocks in every frame, all live -- the frame loop of the lean path over (frame, block) pairs.
+        struct Blk {
+          uint2 g[kRB];
+          float4 l[kRB];
+          float4 a;
+        };
+        const int n_blk = (w_hi - w_lo + 1) / kRB, nf = t1 - t0, n_it = nf * n_blk;
+        const __nv_bfloat16* dhp = dh + ((bt0 + t0) * R + w_lo - row0) * ld + v;
+        const float* amp = am + (bt0 + t0) * V + v;
+        const float* lmb = lm + ((int64_t)b * (S + 1) + w_lo) * V + v;
+        const int64_t frame_stride = (int64_t)R * ld;
+        auto load_blk = [&](Blk& f, int it) {
+          const int i = it / n_blk, q0 = (it - i * n_blk) * kRB;
+          const __nv_bfloat16* gp = dhp + i * frame_stride + (int64_t)q0 * ld;
+          const float* lp = lmb + (int64_t)q0 * V;
+          f.a = __ldg(reinterpret_cast<const float4*>(amp + (int64_t)i * V));
+#pragma unroll
+          for (int q = 0; q < kRB; ++q) {
+            f.g[q] = *reinterpret_cast<const uint2*>(gp + (int64_t)q * ld);
+            f.l[q] = __ldg(reinterpret_cast<const float4*>(lp + (int64_t)q * V));
+          }
+        };
+        float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto reduce_blk = [&](const Blk& f, int it) {
+          const int i = it / n_blk, blk = it - i * n_blk;
+          float* cell0 = mine + blk * kRB * kDjCols;
+#pragma unroll
+          for (int q = 0; q < kRB; ++q) {
+            float4* cell = reinterpret_cast<float4*>(cell0 + q * kDjCols);
+            float4 c = *cell;
+            const float x0 = __uint_as_float(f.g[q].x << 16) * act_bwd_fast(f.a.x + f.l[q].x, act);
+            const float x1 = __uint_as_float(f.g[q].x & 0xffff0000u) * act_bwd_fast(f.a.y + f.l[q].y, act);
+            const float x2 = __uint_as_float(f.g[q].y << 16) * act_bwd_fast(f.a.z + f.l[q].z, act);
+            const float x3 = __uint_as_float(f.g[q].y & 0xffff0000u) * act_bwd_fast(f.a.w + f.l[q].w, act);
+            ds.x += x0; ds.y += x1; ds.z += x2; ds.w += x3;
+            c.x += x0; c.y += x1; c.z += x2; c.w += x3;
+            *cell = c;
+          }
+          if (blk == n_blk - 1) {  // the frame's share of this window is complete
+            float* drow = d_am + (bt0 + t0 + i) * V + v;
+            if (am_accumulate || w_lo > s_lo) {
+              const float4 old = *reinterpret_cast<float4*>(drow);
+              ds.x += old.x; ds.y += old.y; ds.z += old.z; ds.w += old.w;
+            }
+            *reinterpret_cast<float4*>(drow) = ds;
+            ds = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        auto prefetch_blk = [&](int it) {  // the dh rows of a block a few blocks ahead: into L2 before their loads
+          if (it < n_it) {
+            const int i = it / n_blk, q0 = (it - i * n_blk) * kRB;
+            const __nv_bfloat16* gp = dhp + i * frame_stride + (int64_t)q0 * ld;
+#pragma unroll
+            for (int q = 0; q < kRB; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + (int64_t)q * ld));
+          }
+        };
+        prefetch_blk(2);
+        prefetch_blk(3);
+        prefetch_blk(4);
+        prefetch_blk(5);
+        Blk fa, fb;
+        load_blk(fa, 0);
+        for (int it = 0; it < n_it; it += 2) {
+          if (it + 1 < n_it) load_blk(fb, it + 1);
+          prefetch_blk(it + 6);
+          reduce_blk(fa, it);
+          if (it + 1 < n_it) {
+            if (it + 2 < n_it) load_blk(fa, it + 2);
+            prefetch_blk(it + 7);
+            reduce_blk(fb, it + 1);
+          }
+        }
       } else {
       for (int t = t0; t < t1; ++t) {
           const int sbt = sbs[t - t0];
