@@ -83,7 +83,10 @@ int s2t_mutual_information(const float* px, const float* py, const int64_t* boun
  * normaliser (fp32-level accuracy) and bf16 tensor-core backward contractions.
  * workspace: s2t_simple_workspace_bytes(mode,B,T,S,V) bytes.
  * row_max_ready != 0: am_max / lm_max already hold the row maxima of am / lm (by-products of s2t_linear_fwd);
- * the row-max pass over am and lm is skipped (tensor-core mode).
+ * the row-max pass over am and lm is skipped (tensor-core mode).  row_max_ready == 2: in addition
+ * s2t_simple_loss_prep_lm has run on this workspace (the lm side of the normaliser: per-position records and the
+ * split operand of exp(lm - max)) -- it depends on lm only, so a caller that computes lm on a second stream issues it
+ * there, next to whatever produces am.
  */
 size_t s2t_simple_workspace_bytes(int mode, int B, int T, int S, int V);
 int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_t* symbols, const int64_t* boundary,
@@ -95,6 +98,8 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
  * workspace: THE buffer the forward call wrote (in S2T_MODE_BF16_TC it holds the bf16 exp(am - max) /
  * exp(lm - max) operands that the forward pass produced as a by-product), unchanged.
  * d_am (B,T,V), d_lm (B,S+1,V) are overwritten. */
+int s2t_simple_loss_prep_lm(int mode, const float* lm, const float* lm_max, const int64_t* symbols, int B, int T, int S,
+                            int V, int blank, void* workspace, void* stream);
 int s2t_simple_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols, const float* am_max,
                         const float* lm_max, const float* nrm, const float* px_grad, const float* py_grad,
                         const float* grad_scores, int B, int T, int S, int V, int blank, float lm_only_scale,

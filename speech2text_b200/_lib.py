@@ -48,6 +48,7 @@ _SIGNATURES = {
     "s2t_band_lattice_fwd": (c_int, [P, P, P, P, I, I, I, I, P, P, P, P, P]),
     "s2t_rnnt_beam_workspace_bytes": (c_size_t, [I, I, I, I]),
     "s2t_rnnt_beam_decode": (c_int, [P] * 12 + [I] * 12 + [P, P, P, P, P]),
+    "s2t_simple_loss_prep_lm": (c_int, [I, P, P, P, I, I, I, I, I, P, P]),
     "s2t_weighted_sum": (c_int, [P, P, I, P, P]),
     "s2t_rescale_groups": (c_int, [P, ctypes.c_int64, P, ctypes.c_int64, I, P, P, P]),
     "s2t_joiner_loss_bwd": (c_int, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P,

@@ -39,7 +39,9 @@ int simple_backward(const float* am, const float* lm, const int64_t* sym, const 
 size_t simple_tc_workspace_bytes(int B, int T, int S, int V);
 int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
                        int S, int V, int blank, float* am_max, float* lm_max, float* px, float* py, float* nrm,
-                       void* ws, bool row_max_ready, cudaStream_t stream);
+                       void* ws, int ready, cudaStream_t stream);
+int simple_prep_lm_tc(const float* lm, const float* lm_max, const int64_t* sym, int B, int T, int S, int V, int blank,
+                      void* ws, cudaStream_t stream);
 int simple_backward_tc(const float* am, const float* lm, const int64_t* sym, const float* am_max,
                        const float* lm_max, const float* nrm, const float* occ_px, const float* occ_py,
                        const float* coef, int B, int T, int S, int V, int blank, void* ws, float* d_am, float* d_lm,
@@ -235,7 +237,7 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
   S2T_REQUIRE(blank >= 0 && blank < V, "simple_loss: blank %d out of range", blank);
   if (mode == S2T_MODE_BF16_TC) {
     if (int rc = simple_logprobs_tc(am, lm, symbols, boundary, B, T, S, V, blank, am_max, lm_max, px, py, nrm,
-                                    workspace, row_max_ready != 0, st))
+                                    workspace, row_max_ready, st))
       return rc;
   } else {
     // the fp32 path forms its own row maxima (it overwrites am_max / lm_max)
@@ -249,6 +251,14 @@ int s2t_simple_loss_fwd(int mode, const float* am, const float* lm, const int64_
       return rc;
   }
   return s2t_mutual_information(px, py, boundary, B, S, T, alpha_ws, scores, px_grad, py_grad, stream);
+}
+
+int s2t_simple_loss_prep_lm(int mode, const float* lm, const float* lm_max, const int64_t* symbols, int B, int T, int S,
+                            int V, int blank, void* workspace, void* stream) {
+  S2T_REQUIRE(mode == S2T_MODE_BF16_TC, "simple_loss_prep_lm: tensor-core mode only (mode %d)", mode);
+  S2T_REQUIRE(B > 0 && T > 0 && S >= 0 && V > 0 && blank >= 0 && blank < V, "simple_loss_prep_lm: bad dims B=%d T=%d S=%d V=%d", B,
+              T, S, V);
+  return simple_prep_lm_tc(lm, lm_max, symbols, B, T, S, V, blank, workspace, (cudaStream_t)stream);
 }
 
 int s2t_simple_loss_bwd(int mode, const float* am, const float* lm, const int64_t* symbols, const float* am_max,

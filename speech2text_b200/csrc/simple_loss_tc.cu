@@ -434,9 +434,41 @@ size_t simple_tc_workspace_bytes(int B, int T, int S, int V) {
   return 2 * d.lm_f32 + d.am_bf16 + d.lm_bf16 + d.wst + d.wts + d.info + 4096;
 }
 
+// The lm side of the normaliser, separately: {max, lm[blank], lm[sym]} per symbol position and the hi / lo split of
+// exp(lm - max) (the B operand).  It depends on the predictor-side projection only, so a caller that launches that
+// projection on a second stream issues this right behind it -- under the (three times larger) encoder-side projection.
+int simple_prep_lm_tc(const float* lm, const float* lm_max, const int64_t* sym, int B, int T, int S, int V, int blank,
+                      void* ws, cudaStream_t stream) {
+  SimpleTcDims d = simple_tc_dims(B, T, S, V);
+  uint8_t* lm_big = (uint8_t*)ws;
+  uint8_t* lm_small = lm_big + d.lm_f32;
+  float4* lm_info = (float4*)((uint8_t*)ws + 2 * d.lm_f32 + d.am_bf16 + d.lm_bf16 + d.wst + d.wts);
+  const int64_t rows_lm = (int64_t)B * (S + 1);
+  {
+    ProfScope prof("lm_info_kernel", stream);
+    tc_lm_info_kernel<<<(unsigned)((rows_lm + 255) / 256), 256, 0, stream>>>(lm, lm_max, rows_lm, V, sym, S, blank, lm_info);
+  }
+  if (int rc = check_launch("lm_info_kernel")) return rc;
+  uint8_t* am_p = lm_small + d.lm_f32;
+  uint8_t* lm_p = am_p + d.am_bf16;
+  const bool f16 = getenv("S2T_B200_SIMPLE_TF32") == nullptr;
+  const int kstep = f16 ? 64 : 32;
+  const int ksteps = (V + kstep - 1) / kstep;
+  if (ksteps * kstep < d.Vp) cudaMemsetAsync(lm_p, 0, d.lm_bf16, stream);  // vocabulary padding the k-steps never visit
+  if (f16) {
+    constexpr float kScale = 4096.f;
+    PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, ksteps, lm_max};
+    return pack_f16_split(ps, kScale, lm_big, lm_small, lm_p, stream);
+  }
+  PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
+  return pack_f32_split(ps, lm_big, lm_small, stream, lm_p, d.kb64);
+}
+
+// ready: 0 = nothing known; 1 = am_max / lm_max hold the row maxima; 2 = also simple_prep_lm_tc has run on this workspace
 int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, const int64_t* boundary, int B, int T,
                        int S, int V, int blank, float* am_max, float* lm_max, float* px, float* py, float* nrm,
-                       void* ws, bool row_max_ready, cudaStream_t stream) {
+                       void* ws, int ready, cudaStream_t stream) {
+  const bool row_max_ready = ready != 0, lm_ready = ready == 2;
   SimpleTcDims d = simple_tc_dims(B, T, S, V);
   uint8_t* lm_big = (uint8_t*)ws;
   uint8_t* lm_small = lm_big + d.lm_f32;
@@ -444,7 +476,8 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   const int wpb = 8;
   const int64_t rows_am = (int64_t)B * T, rows_lm = (int64_t)B * (S + 1);
   // lm first: its hi/lo split (the B operand of the normaliser) then runs on a side stream next to the am row maxima
-  if (row_max_ready) {
+  if (lm_ready) {
+  } else if (row_max_ready) {
     ProfScope prof("lm_info_kernel", stream);
     tc_lm_info_kernel<<<(unsigned)((rows_lm + 255) / 256), 256, 0, stream>>>(lm, lm_max, rows_lm, V, sym, S, blank, lm_info);
   } else {
@@ -460,7 +493,7 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   const int kstep = f16 ? 64 : 32;
   const int ksteps = (V + kstep - 1) / kstep;
   if (ksteps * kstep < d.Vp) {  // vocabulary padding the k-steps never visit
-    cudaMemsetAsync(am_p, 0, d.am_bf16 + d.lm_bf16, stream);
+    cudaMemsetAsync(am_p, 0, d.am_bf16 + (lm_ready ? 0 : d.lm_bf16), stream);
   }
   MnDebug extra;
   extra.b_small = lm_small;
@@ -476,7 +509,7 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
     // is scaled back (2^-24, exact) before the log
     constexpr float kScale = 4096.f;
     PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, ksteps, lm_max};
-    {
+    if (!lm_ready) {
       ForkJoin fj(stream);
       if (int rc = pack_f16_split(ps, kScale, lm_big, lm_small, lm_p, fj.side(0))) return rc;
       row_max_am();
@@ -491,7 +524,8 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
     PackSpec ps{lm, (int64_t)(S + 1) * V, V, B, S + 1, d.Spad, V, d.kb32, lm_max};
     row_max_am();
     if (int rc = check_launch("row_max_kernel")) return rc;
-    if (int rc = pack_f32_split(ps, lm_big, lm_small, stream, lm_p, d.kb64)) return rc;
+    if (!lm_ready)
+      if (int rc = pack_f32_split(ps, lm_big, lm_small, stream, lm_p, d.kb64)) return rc;
     ExpRowProducerF32 a{am, am_max, T, V, am_p, d.Tpad / 128, B * (d.Tpad / 128)};
     SimpleEmitTcEpi ep{am, am_max, lm_info, T, S, V, blank, py, nrm, 1.f};
     if (int rc = launch_gemm_stream<128, 3, false, 2, kPair>(a, lm_big, B * (d.Spad / 128), d.Tpad / 128, d.Spad / 128, d.kb32,

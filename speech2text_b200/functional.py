@@ -190,7 +190,7 @@ class _SimpleLoss(torch.autograd.Function):
     @staticmethod
     @_on_tensor_device
     def forward(ctx, am: Tensor, lm: Tensor, symbols: Tensor, boundary: Tensor, blank: int,
-                lm_only_scale: float, am_only_scale: float, mode: int, row_max=None):
+                lm_only_scale: float, am_only_scale: float, mode: int, row_max=None, prepared_ws=None):
         am, lm = _f32c(am), _f32c(lm)
         symbols, boundary = _i64c(symbols), _i64c(boundary)
         B, T, V = am.shape
@@ -210,11 +210,14 @@ class _SimpleLoss(torch.autograd.Function):
         scores = torch.empty((B,), **f32)
         px_grad = torch.empty((B, S, T + 1), **f32)
         py_grad = torch.empty((B, S + 1, T), **f32)
-        ws = torch.empty((lib().s2t_simple_workspace_bytes(mode, B, T, S, V),), dtype=torch.uint8, device=dev)
+        nbytes = lib().s2t_simple_workspace_bytes(mode, B, T, S, V)
+        # the lm side of the normaliser may already sit in the workspace (simple_loss_prepare_lm)
+        lm_ready = ready and prepared_ws is not None and prepared_ws.numel() == nbytes and prepared_ws.device == dev
+        ws = prepared_ws if lm_ready else torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         check(lib().s2t_simple_loss_fwd(mode, ptr(am), ptr(lm), ptr(symbols), ptr(boundary), B, T, S, V, blank,
                                         float(lm_only_scale), float(am_only_scale), ptr(am_max), ptr(lm_max),
                                         ptr(px), ptr(py), ptr(nrm), ptr(alpha), ptr(scores), ptr(px_grad),
-                                        ptr(py_grad), ptr(ws), 1 if ready else 0, stream()))
+                                        ptr(py_grad), ptr(ws), 2 if lm_ready else (1 if ready else 0), stream()))
         ctx.early = None
         if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _early_simple_backward(mode):
             _PENDING[:] = [e for e in _PENDING if e.d_am.device != dev]  # an older one falls back to the plain path
@@ -244,12 +247,12 @@ class _SimpleLoss(torch.autograd.Function):
             cur = torch.cuda.current_stream(am.device)
             cur.wait_stream(early.side)  # also what joins the side stream back into a CUDA-graph capture of the step
             if grad_scores is None:
-                return (None,) * 9
+                return (None,) * 10
             check(lib().s2t_rescale_groups(ptr(early.d_am), T * V, ptr(early.d_lm), (S + 1) * V, B,
                                            ptr(_f32c(grad_scores)), ptr(early.pred), stream()))
-            return early.d_am, early.d_lm, None, None, None, None, None, None, None
+            return early.d_am, early.d_lm, None, None, None, None, None, None, None, None
         if grad_scores is None:
-            return (None,) * 9
+            return (None,) * 10
         grad_scores = _f32c(grad_scores)
         d_am = torch.empty_like(am)
         d_lm = torch.empty_like(lm)
@@ -259,13 +262,40 @@ class _SimpleLoss(torch.autograd.Function):
         if _early_simple_backward(ctx.mode):  # what the next step's early launch will assume
             check(lib().s2t_rescale_groups(None, 0, None, 0, B, ptr(grad_scores), ptr(_predicted_scale(B, am.device)),
                                            stream()))
-        return d_am, d_lm, None, None, None, None, None, None, None
+        return d_am, d_lm, None, None, None, None, None, None, None, None
+
+
+def simple_loss_prepare_lm(lm: Tensor, lm_max: Tensor, symbols: Tensor, T: int, blank: int, mode: int,
+                           on_side_stream: bool = False) -> Optional[Tensor]:
+    """The lm side of ``rnnt_loss_smoothed``'s normaliser (per-position records and the split operand of
+    exp(lm - max)) ahead of the call: it needs lm and its row maxima only.  Returns the workspace to hand to
+    ``rnnt_loss_smoothed(prepared_ws=...)``, or None when this mode has nothing to prepare.  ``on_side_stream``: launch
+    behind a projection that was launched with ``on_side_stream=True`` (the caller joins with ``join_side_stream``)."""
+    if mode != _lib.MODE_BF16_TC or not lm.is_cuda or lm.dtype != torch.float32 or not lm.is_contiguous():
+        return None
+    dev = lm.device
+    with torch.cuda.device(dev):
+        B, S1, V = lm.shape
+        S = S1 - 1
+        symbols = _i64c(symbols.to(dev))
+        if symbols.shape != (B, S) or lm_max.shape != (B, S1):
+            return None
+        ws = torch.empty((lib().s2t_simple_workspace_bytes(mode, B, T, S, V),), dtype=torch.uint8, device=dev)
+        if on_side_stream:
+            side = _side_stream(dev)  # ordered behind the projection that produced lm on this stream
+            for t in (lm, lm_max, symbols, ws):
+                t.record_stream(side)
+            st = ctypes.c_void_p(side.cuda_stream)
+        else:
+            st = stream()
+        check(lib().s2t_simple_loss_prep_lm(mode, ptr(lm), ptr(_f32c(lm_max)), ptr(symbols), B, T, S, V, blank, ptr(ws), st))
+    return ws
 
 
 def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                        lm_only_scale: float = 0.0, am_only_scale: float = 0.0,
                        boundary: Optional[Tensor] = None, reduction: str = "mean",
-                       return_grad: bool = False, mode: int = _lib.MODE_FP32_SIMT, row_max=None):
+                       return_grad: bool = False, mode: int = _lib.MODE_FP32_SIMT, row_max=None, prepared_ws=None):
     """Drop-in for ``k2.rnnt_loss_smoothed`` (rnnt_type='regular').  ``mode`` picks the arithmetic of
     the normaliser contraction: fp32 FMA, or tensor cores (3xTF32 forward, bf16 backward)."""
     if boundary is None:
@@ -274,7 +304,7 @@ def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symb
         boundary[:, 2] = lm.shape[1] - 1
         boundary[:, 3] = T
     scores, px_grad, py_grad = _SimpleLoss.apply(am, lm, symbols, boundary, termination_symbol,
-                                                 lm_only_scale, am_only_scale, mode, row_max)
+                                                 lm_only_scale, am_only_scale, mode, row_max, prepared_ws)
     loss = _reduce(scores, reduction)
     return (loss, (px_grad, py_grad)) if return_grad else loss
 

@@ -155,7 +155,8 @@ class Joiner(nn.Module):
 
     @torch.jit.unused
     def _simple_loss_and_ranges(self, am: torch.Tensor, encoder_out_lengths: torch.Tensor, lm: torch.Tensor,
-                                target_lengths: torch.Tensor, target: torch.Tensor, mode: int = 0, row_max=None):
+                                target_lengths: torch.Tensor, target: torch.Tensor, mode: int = 0, row_max=None,
+                                prepared_ws=None):
         """joiner.py:74-117 without the pruning gather: boundary, simple loss, ranges."""
         boundary = F2.make_boundary(target_lengths, encoder_out_lengths, am.device)
         assert len(target.shape) == 2  # (B, U)
@@ -175,6 +176,7 @@ class Joiner(nn.Module):
             return_grad=True,
             mode=mode,
             row_max=row_max,
+            prepared_ws=prepared_ws,
         )
         ranges = F2.get_rnnt_prune_ranges(px_grad=px_grad, py_grad=py_grad, boundary=boundary,
                                           s_range=self.prune_range)
@@ -201,14 +203,19 @@ class Joiner(nn.Module):
                                 "CPU path (streaming_step and the ONNX exports are plain torch).")
         # Project both encoder_out and predictor_out into vocab_size
         mode = _mode_from_env()
+        prepared_ws = None
         if mode == _lib.MODE_BF16_TC and os.environ.get("S2T_B200_PROJ_TC", "1") != "0":
             # two aliases of each projection: one for the simple loss, one for the joiner (functional._LinearTC)
             # ... and, when the simple loss follows, the row maxima it needs as a by-product of the GEMM epilogue
             want = self.prune_range > 0
-            # the predictor-side projection (under one wave of tiles) runs on a side stream next to the encoder-side one
+            # the predictor-side projection (under one wave of tiles) runs on a side stream next to the encoder-side one,
+            # and so does the lm side of the simple loss's normaliser, which needs nothing else
             side = os.environ.get("S2T_B200_PROJ_OVERLAP", "1") != "0" and not _lib.profiling()
             lm, lm_j, *lm_max = F2.linear_tc_pair(predict_out, self._pre_proj.weight, self._pre_proj.bias, row_max=want,
                                                   on_side_stream=side)
+            if want and side and target.dim() == 2:
+                prepared_ws = F2.simple_loss_prepare_lm(lm, lm_max[0], target, encoder_out.shape[1], self.blank_token, mode,
+                                                        on_side_stream=True)
             am, am_j, *am_max = F2.linear_tc_pair(encoder_out, self._enc_proj.weight, self._enc_proj.bias, row_max=want)
             if side:
                 F2.join_side_stream(encoder_out.device)
@@ -221,7 +228,7 @@ class Joiner(nn.Module):
         if self.prune_range > 0:
             assert target.shape[0] == target_lengths.shape[0]
             boundary, ranges, simple_loss = self._simple_loss_and_ranges(am, encoder_out_lengths, lm,
-                                                                         target_lengths, target, mode, row_max)
+                                                                         target_lengths, target, mode, row_max, prepared_ws)
         else:
             # For API consistency
             boundary = None
