@@ -1899,6 +1899,7 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
       BulkA a{w.Gp, ct};
       DHiddenEpi ep{p.I, w.DHp, ct, db1};
       // (W2^T resident per 128-column tile and G streamed twice instead: 0.0455 -> 0.060 ms at c3)
+      // (as a CTA pair over the live-tile list -- half of W2^T per SM: 0.0457 vs 0.0455 ms, no gain)
       if (int rc = launch_gemm_stream<kBN, kNStages, false, 0>(a, w.W2Tp, d.Ip / 128, ct, d.Ip / kBN, d.kbV, 1, ep, stream,
                                                                "tc_joiner_dhidden_gemm", live))
         return rc;

@@ -326,7 +326,9 @@ gemm_stream_kernel(ASrc asrc, const uint8_t* __restrict__ b_packed, int b_row_bl
   const int first_tile = kBRes > 0 ? (int)blockIdx.x / n_tiles : (int)blockIdx.x / kCluster;
   const int tile_stride = kBRes > 0 ? (int)gridDim.x / n_tiles : (int)gridDim.x / kCluster;
   // live-block list: lo = first list entry of this launch's block range, n_live = live blocks in it
-  const bool listed = kCluster == 1 && (kMn ? ASrc::kBulk : true) && mn.live_idx != nullptr;
+  // (a CTA pair walks the list as well: its two CTAs take consecutive LIVE row tiles -- they share the column tile and the
+  // k range, which row tiles they hold is free)
+  const bool listed = (kCluster == 1 || !kMn) && (kMn ? ASrc::kBulk : true) && mn.live_idx != nullptr;
   const int live_lo = listed ? mn.live_prefix[mn.live_off] : 0;
   const int n_live = listed ? mn.live_prefix[mn.live_off + (kMn ? (k_steps + 1) / 2 : m_tiles)] - live_lo : 0;
   const int m_rows = (listed && !kMn) ? n_live : m_tiles;      // row tiles to walk
