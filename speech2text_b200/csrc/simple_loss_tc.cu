@@ -274,6 +274,42 @@ struct SimpleEmitTcEpi {
 };
 
 // px[b, s, t] = am[b, t, sym[b, s]] + lm[b, s, sym[b, s]] - nrm[b, s, t]   (-inf at t = T_b and in column T)
+// Tiled version: one CTA per (utterance, 32 frames).  Warp w gathers the S symbol entries of am row t0 + w (one 2 KB
+// row: a handful of lines per warp load, instead of 32 rows per load when consecutive lanes are consecutive frames)
+// into a shared-memory tile; the tile is then read frame-fastest, so that nrm is read and px written in 128-byte
+// segments of the k2 layout (t contiguous).  Shared memory: 32 x (S | 1) floats.
+__global__ void __launch_bounds__(1024) simple_px_tiled_kernel(const float* __restrict__ am, const float4* __restrict__ lm_info,
+                                                               const float* __restrict__ nrm, const int64_t* __restrict__ sym,
+                                                               const int64_t* __restrict__ boundary, int B, int T, int S,
+                                                               int V, float* __restrict__ px) {
+  extern __shared__ float tile[];  // [32][ld]
+  const int ld = S | 1;
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tb = boundary ? (int)boundary[4 * b + 3] : T;
+  const int64_t* sy = sym + (int64_t)b * S;
+  {
+    const int t = t0 + warp;
+    if (t < T) {
+      const float* row = am + ((int64_t)b * T + t) * V;
+      for (int s = lane; s < S; s += 32) {
+        const int c = min(max((int)sy[s], 0), V - 1);
+        tile[warp * ld + s] = __ldg(row + c);
+      }
+    }
+  }
+  __syncthreads();
+  // warp w now owns the symbol positions w, w + 32, ...; lane = frame inside the tile
+  const int t = t0 + lane;
+  for (int s = warp; s < S; s += 32) {
+    const int64_t row = (int64_t)b * (S + 1) + s;
+    float v = kNegInf;
+    if (t < T && t != Tb) v = tile[lane * ld + s] + __ldg(lm_info + row).z - __ldg(nrm + row * T + t);
+    if (t < T) px[((int64_t)b * S + s) * (T + 1) + t] = v;
+    if (t0 + 32 >= T && lane == 0) px[((int64_t)b * S + s) * (T + 1) + T] = kNegInf;  // column T
+  }
+}
+
 __global__ void simple_px_kernel(const float* __restrict__ am, const float4* __restrict__ lm_info,
                                  const float* __restrict__ nrm, const int64_t* __restrict__ sym,
                                  const int64_t* __restrict__ boundary, int B, int T, int S, int V,
@@ -535,7 +571,13 @@ int simple_logprobs_tc(const float* am, const float* lm, const int64_t* sym, con
   const int64_t total = (int64_t)B * S * (T + 1);
   if (total > 0) {
     ProfScope prof("simple_px_kernel", stream);
-    simple_px_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(am, lm_info, nrm, sym, boundary, B, T, S, V, px);
+    const size_t smem = (size_t)32 * (S | 1) * sizeof(float);
+    if (smem <= 48 * 1024 && B <= 65535 && getenv("S2T_B200_PX_FLAT") == nullptr) {
+      simple_px_tiled_kernel<<<dim3((unsigned)((T + 31) / 32), (unsigned)B), 1024, smem, stream>>>(am, lm_info, nrm, sym, boundary,
+                                                                                                  B, T, S, V, px);
+    } else {
+      simple_px_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(am, lm_info, nrm, sym, boundary, B, T, S, V, px);
+    }
   }
   return check_launch("simple_px_kernel");
 }
