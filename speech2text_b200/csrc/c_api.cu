@@ -401,7 +401,8 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
   S2T_REQUIRE(mode == S2T_MODE_FP32_SIMT || mode == S2T_MODE_BF16_TC, "joiner_loss_bwd: unknown mode %d", mode);
   JoinerProblem p = make_problem(am, lm, symbols, ranges, boundary, W1, b1, W2, b2, B, T, S, R, V, I, act, blank,
                                  0.f);
-  cudaMemsetAsync(d_am, 0, (size_t)B * T * V * sizeof(float), st);
+  const bool tc = joiner_uses_tc(mode, I);
+  if (!tc) cudaMemsetAsync(d_am, 0, (size_t)B * T * V * sizeof(float), st);  // the tensor-core path writes d_am itself
   cudaMemsetAsync(d_lm, 0, (size_t)B * (S + 1) * V * sizeof(float), st);
   if (I > 0) {
     cudaMemsetAsync(dW1, 0, (size_t)I * V * sizeof(float), st);

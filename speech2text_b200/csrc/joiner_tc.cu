@@ -657,6 +657,14 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
   const int b = blockIdx.y, t0 = blockIdx.x * kDjFrames;
   const int Tb = boundary ? min((int)boundary[4 * b + 3], T) : T;  // padding frames carry no gradient
   const int t1 = min(t0 + kDjFrames, Tb);
+  if (!am_accumulate) {
+    // padding frames carry no gradient: their d_am rows are zero-filled here (the buffer is not memset beforehand:
+    // every live frame below is first written with a plain store)
+    for (int t = max(t0, Tb); t < min(t0 + kDjFrames, T); ++t) {
+      float* drow = d_am + ((int64_t)b * T + t) * V;
+      for (int v = threadIdx.x; v < V; v += blockDim.x) drow[v] = 0.f;
+    }
+  }
   if (t0 >= t1) return;
   const int64_t bt0 = (int64_t)b * T;
   const int64_t row_end = min(row0 + rows, M);
@@ -787,7 +795,7 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
           }
           if (blk == n_blk - 1) {  // the frame's share of this window is complete
             float* drow = d_am + (bt0 + t0 + i) * V + v;
-            if (am_accumulate || w_lo > s_lo) {
+            if (am_accumulate || w_lo > 0) {  // an earlier window already stored this frame's first slots
               const float4 old = *reinterpret_cast<float4*>(drow);
               ds.x += old.x; ds.y += old.y; ds.z += old.z; ds.w += old.w;
             }
@@ -875,7 +883,7 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
           float* drow = d_am + (bt0 + t) * V + v;
           if (kVec) {
             float4 o = make_float4(dsum[0], dsum[1], dsum[2], dsum[3]);
-            if (am_accumulate || w_lo > s_lo) {  // later windows add to what the first one stored
+            if (am_accumulate || r_lo > 0) {  // an earlier window already stored this frame's first slots
               const float4 old = *reinterpret_cast<float4*>(drow);
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
@@ -883,7 +891,7 @@ __global__ void __launch_bounds__(128) djoint_reduce_kernel(const __nv_bfloat16*
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (v + j < V) drow[j] = ((am_accumulate || w_lo > s_lo) ? drow[j] : 0.f) + dsum[j];
+              if (v + j < V) drow[j] = ((am_accumulate || r_lo > 0) ? drow[j] : 0.f) + dsum[j];
           }
         }
       }
@@ -1859,7 +1867,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   return check_launch("lse_combine_kernel");
 }
 
-// Gradients are ACCUMULATED into d_am, d_lm, dW1, db1, dW2, db2 (the caller zero-fills).
+// Gradients are ACCUMULATED into d_lm, dW1, db1, dW2, db2 (the caller zero-fills); d_am is fully written here.
 int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse, const float* occ_px,
                        const float* occ_py, const float* coef, float clamp, float* d_am, float* d_lm, float* dW1,
                        float* db1, float* dW2, float* db2, cudaStream_t stream) {
@@ -1872,6 +1880,9 @@ int joiner_tc_backward(const JoinerProblem& p, void* workspace, const float* lse
   }
   TcWs w = tc_carve(workspace, d);
   const int sms = device_info().sms;
+  // d_am: with one row chunk the dJoint reduction writes every row itself (plain first stores, zeros for padding
+  // frames); with several chunks a frame can straddle two launches, which then accumulate into a zero-filled buffer
+  if (d.chunk < (int64_t)d.Mt * 128) cudaMemsetAsync(d_am, 0, (size_t)p.B * p.T * p.V * sizeof(float), stream);
   for (int64_t row0 = 0; row0 < (int64_t)d.Mt * 128; row0 += d.chunk) {
     const int64_t rows_pad = ((int64_t)d.Mt * 128 - row0 < d.chunk) ? ((int64_t)d.Mt * 128 - row0) : d.chunk;
     const int ct = (int)(rows_pad / 128);       // row tiles of this chunk
