@@ -405,10 +405,15 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
   if (!tc) cudaMemsetAsync(d_am, 0, (size_t)B * T * V * sizeof(float), st);  // the tensor-core path writes d_am itself
   cudaMemsetAsync(d_lm, 0, (size_t)B * (S + 1) * V * sizeof(float), st);
   if (I > 0) {
-    cudaMemsetAsync(dW1, 0, (size_t)I * V * sizeof(float), st);
-    cudaMemsetAsync(db1, 0, (size_t)I * sizeof(float), st);
-    cudaMemsetAsync(dW2, 0, (size_t)V * I * sizeof(float), st);
-    cudaMemsetAsync(db2, 0, (size_t)V * sizeof(float), st);
+    if (db1 == dW1 + (size_t)I * V && dW2 == db1 + I && db2 == dW2 + (size_t)V * I) {
+      // the four gradients are neighbours in a flat gradient bucket (FlatGradBucket.bind): one memset node
+      cudaMemsetAsync(dW1, 0, ((size_t)2 * I * V + I + V) * sizeof(float), st);
+    } else {
+      cudaMemsetAsync(dW1, 0, (size_t)I * V * sizeof(float), st);
+      cudaMemsetAsync(db1, 0, (size_t)I * sizeof(float), st);
+      cudaMemsetAsync(dW2, 0, (size_t)V * I * sizeof(float), st);
+      cudaMemsetAsync(db2, 0, (size_t)V * sizeof(float), st);
+    }
   }
   if (joiner_uses_tc(mode, I)) {
     return joiner_tc_backward(p, workspace, lse, occ_px, occ_py, grad_scores, clamp, d_am, d_lm, dW1, db1, dW2, db2,

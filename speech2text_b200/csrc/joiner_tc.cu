@@ -1814,9 +1814,13 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
   if (joiner_fused_fwd_ok(d)) {
     // one kernel from the gather to (lse, px, py); tiles of padding frames are never computed: their entries are zeros
     if (w.live_idx) {
-      cudaMemsetAsync(lse, 0, (size_t)M * sizeof(float), stream);
-      cudaMemsetAsync(px, 0, (size_t)M * sizeof(float), stream);
-      cudaMemsetAsync(py, 0, (size_t)M * sizeof(float), stream);
+      if (px == lse + M && py == px + M) {  // one buffer (functional.py allocates them so): one memset node
+        cudaMemsetAsync(lse, 0, (size_t)3 * M * sizeof(float), stream);
+      } else {
+        cudaMemsetAsync(lse, 0, (size_t)M * sizeof(float), stream);
+        cudaMemsetAsync(px, 0, (size_t)M * sizeof(float), stream);
+        cudaMemsetAsync(py, 0, (size_t)M * sizeof(float), stream);
+      }
     }
     FusedFwdParams fp{p.am, p.lm, w.am_row, w.lm_row, w.row_sym, w.W1p, w.W2p, p.b1, p.b2, w.Hp, w.Jp, w.live_idx,
                       w.live_prefix, p.boundary, lse, px, py, M, d.Mt, p.V, p.I, d.kbV, d.Vp / 128, d.Vp / 128, p.act,

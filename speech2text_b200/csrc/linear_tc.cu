@@ -122,7 +122,10 @@ int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M,
   uint8_t* pdy = px + d.px + d.pw;
   uint8_t* pwt = pdy + d.pdy;
   // pack(dy) also yields db = column sums of dy
-  cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
+  // dW and db neighbours in a flat gradient bucket (weight, then bias): one memset node in front of everything
+  const bool one_memset = db == dW + (size_t)N * K;
+  if (one_memset) cudaMemsetAsync(dW, 0, ((size_t)N * K + N) * sizeof(float), st);
+  else cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
   if (int rc = tc::pack_rows_colsum(dy, dy2, N, (int)M, N, d.Mt, d.Np / 64, pdy, db, st)) return rc;
   ForkJoin fj(st);  // dx and dW only share the packed dy: the weight gradient runs on a side stream
   cudaStream_t s_dw = dx ? fj.side(0) : st;
@@ -141,7 +144,7 @@ int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M,
     }
   }
   {
-    cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s_dw);
+    if (!one_memset) cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), s_dw);
     const int k_steps = d.Mt * 2;
     const int tiles = (d.Np / 128) * (d.Kp / 256);
     int splits = device_info().sms / (tiles > 0 ? tiles : 1);

@@ -392,9 +392,7 @@ class _LogitsLoss(torch.autograd.Function):
             assert ranges.shape == (B, T, R), (ranges.shape, logits.shape)
         dev = logits.device
         f32 = dict(dtype=torch.float32, device=dev)
-        lse = torch.empty((B, T, R), **f32)
-        px = torch.empty((B, T, R), **f32)
-        py = torch.empty((B, T, R), **f32)
+        lse, px, py = torch.empty((3, B, T, R), **f32).unbind(0)  # one buffer: the library zero-fills padding rows in one go
         occ_px = torch.empty((B, T, R), **f32)
         occ_py = torch.empty((B, T, R), **f32)
         alpha = _dp_scratch(B, S, T, R, dev)
