@@ -403,11 +403,11 @@ int s2t_joiner_loss_bwd(int mode, const float* am, const float* lm, const int64_
                                  0.f);
   const bool tc = joiner_uses_tc(mode, I);
   if (!tc) cudaMemsetAsync(d_am, 0, (size_t)B * T * V * sizeof(float), st);  // the tensor-core path writes d_am itself
-  cudaMemsetAsync(d_lm, 0, (size_t)B * (S + 1) * V * sizeof(float), st);
+  zero_async(d_lm, (size_t)B * (S + 1) * V * sizeof(float), st);
   if (I > 0) {
     if (db1 == dW1 + (size_t)I * V && dW2 == db1 + I && db2 == dW2 + (size_t)V * I) {
       // the four gradients are neighbours in a flat gradient bucket (FlatGradBucket.bind): one memset node
-      cudaMemsetAsync(dW1, 0, ((size_t)2 * I * V + I + V) * sizeof(float), st);
+      zero_async(dW1, ((size_t)2 * I * V + I + V) * sizeof(float), st);
     } else {
       cudaMemsetAsync(dW1, 0, (size_t)I * V * sizeof(float), st);
       cudaMemsetAsync(db1, 0, (size_t)I * sizeof(float), st);

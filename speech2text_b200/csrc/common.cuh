@@ -56,6 +56,10 @@ struct DeviceInfo {
   size_t total_mem;   // bytes of device memory
 };
 const DeviceInfo& device_info();  // of the CURRENT device
+
+// Zero-fill of the hot path's accumulation buffers as a kernel (16-byte stores); S2T_B200_MEMSET_NODES=1 uses
+// cudaMemsetAsync instead (measured equal inside the step's CUDA graph: 0.9326 vs 0.9334 ms).
+void zero_async(void* p, size_t bytes, cudaStream_t stream);
 constexpr int kMaxDevices = 64;
 
 #define S2T_REQUIRE(cond, ...)            \

@@ -1815,7 +1815,7 @@ int joiner_tc_forward(const JoinerProblem& p, void* workspace, float* lse, float
     // one kernel from the gather to (lse, px, py); tiles of padding frames are never computed: their entries are zeros
     if (w.live_idx) {
       if (px == lse + M && py == px + M) {  // one buffer (functional.py allocates them so): one memset node
-        cudaMemsetAsync(lse, 0, (size_t)3 * M * sizeof(float), stream);
+        zero_async(lse, (size_t)3 * M * sizeof(float), stream);
       } else {
         cudaMemsetAsync(lse, 0, (size_t)M * sizeof(float), stream);
         cudaMemsetAsync(px, 0, (size_t)M * sizeof(float), stream);

@@ -124,7 +124,7 @@ int s2t_linear_bwd(const float* dy, const float* dy2, const float* W, int64_t M,
   // pack(dy) also yields db = column sums of dy
   // dW and db neighbours in a flat gradient bucket (weight, then bias): one memset node in front of everything
   const bool one_memset = db == dW + (size_t)N * K;
-  if (one_memset) cudaMemsetAsync(dW, 0, ((size_t)N * K + N) * sizeof(float), st);
+  if (one_memset) zero_async(dW, ((size_t)N * K + N) * sizeof(float), st);
   else cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
   if (int rc = tc::pack_rows_colsum(dy, dy2, N, (int)M, N, d.Mt, d.Np / 64, pdy, db, st)) return rc;
   ForkJoin fj(st);  // dx and dW only share the packed dy: the weight gradient runs on a side stream

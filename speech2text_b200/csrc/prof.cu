@@ -46,6 +46,27 @@ ProfScope::~ProfScope() {
 }
 
 // ---- DeviceInfo ----------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) zero_kernel(uint4* __restrict__ p, size_t n16) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+}  // namespace
+
+void zero_async(void* p, size_t bytes, cudaStream_t stream) {
+  static const bool nodes = getenv("S2T_B200_MEMSET_NODES") != nullptr;
+  if (bytes == 0) return;
+  if (nodes || (reinterpret_cast<uintptr_t>(p) & 15) != 0 || (bytes & 15) != 0) {
+    cudaMemsetAsync(p, 0, bytes, stream);
+    return;
+  }
+  const size_t n16 = bytes / 16;
+  size_t blocks = (n16 + 255) / 256;
+  const size_t cap = (size_t)device_info().sms * 8;
+  if (blocks > cap) blocks = cap;
+  zero_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(p), n16);
+}
+
 const DeviceInfo& device_info() {
   static DeviceInfo info[kMaxDevices];
   static std::atomic<int> ready[kMaxDevices];
