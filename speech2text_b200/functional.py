@@ -670,6 +670,7 @@ class _LinearTC(torch.autograd.Function):
         check(lib().s2t_linear_fwd(ptr(x2), _lib.dtype_code(x2.dtype), ptr(W), ptr(b), M, N, K, ptr(ws), ptr(y),
                                    ptr(row_max), st))
         ctx.save_for_backward(W, ws)
+        ctx.set_materialize_grads(False)  # no zero-filled gradient for the row-max by-product (or an unused alias)
         ctx.dims = (M, N, K, lead, x.requires_grad, x.dtype)
         y = y.reshape(*lead, N)
         if want_row_max:
